@@ -1,0 +1,74 @@
+// pg_common.cuh -- handle layouts and launch declarations shared by the translation units of
+// libphysics_gpu.so.  Nothing in here is part of the C-ABI (include/physics_gpu.h is).
+#pragma once
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cuda_runtime.h>
+
+#include "../../include/physics_gpu.h"
+
+void pg_set_error(const char *fmt, ...);
+
+#define PG_CUDA(call)                                                                         \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      pg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));      \
+      return PG_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+#define PG_CUDA_NULL(call)                                                                    \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      pg_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));      \
+      return nullptr;                                                                         \
+    }                                                                                         \
+  } while (0)
+
+enum PgMode { PG_MODE_GENERAL = 0, PG_MODE_SPHERES = 1 };
+
+// Device-side view of a batch of worlds (passed by value to kernels).
+struct WorldsView {
+  int n_worlds;
+  int cap[3];                 // capacity per class (static, dynamic, player)
+  PgBody *bodies[3];          // [n_worlds * cap[c]] full records (general mode; cold data in sphere mode)
+  int *counts;                // [n_worlds * 3]
+  PgEvent *events;            // [n_worlds * max_events]
+  int *n_events;              // [n_worlds] events written by the current step call (may exceed max_events)
+  int max_events;
+  // sphere mode: structure-of-arrays hot state, one float4 pair per dynamic sphere
+  float4 *pos_rest;           // [n_worlds * cap[1]]  x, y, z, at_rest (0.0f / 1.0f)
+  float4 *vel_rad;            // [n_worlds * cap[1]]  vx, vy, vz, world radius
+  float4 *planes;             // [n_worlds * cap[0]]  nx, ny, nz, d    (statics are planes in sphere mode)
+  float restitution;          // uniform in sphere mode
+};
+
+struct PgWorlds {
+  int device;
+  PgMode mode;
+  WorldsView v;               // device pointers
+  int *h_counts;              // host mirror of counts
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  long long launches;
+  int last_steps;
+  double *d_stats;            // 8 doubles
+  int sm_count;
+  bool static_pass_parallel_ok;   // recomputed on upload (general mode)
+  // device staging for packed [body][3] state exchange (sphere mode)
+  float *d_stage_pos, *d_stage_vel;
+  unsigned char *d_stage_rest;
+  size_t stage_bodies;
+};
+
+// pg_general.cu
+int pg_launch_general_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes);
+// pg_spheres.cu
+int pg_launch_sphere_step(PgWorlds *w, float dt, int n_steps);
+int pg_launch_worlds_stats(PgWorlds *w, void *dev_out8);
+int pg_launch_pack_state(PgWorlds *w, int first, int count, int n, const float *pos, const float *vel, const unsigned char *rest);
+int pg_launch_unpack_state(PgWorlds *w, int first, int count, int n, float *pos, float *vel, unsigned char *rest);

@@ -1,0 +1,771 @@
+// pg_math.cuh -- exact per-pair arithmetic of the Crux physics step, device side.
+//
+// Every function here must produce the SAME BITS as the reference's C built by gcc for x86-64
+// (SSE2 scalar math, no FMA contraction).  Rules that make that true on sm_100a:
+//   * this header is only ever compiled with  -fmad=false  (no FFMA/DFMA contraction), default
+//     -prec-div=true -prec-sqrt=true -ftz=false, never --use_fast_math;
+//   * products are summed left to right exactly as cglm's scalar vec3/mat4 routines do;
+//   * wherever the reference's C promotes to double (a double literal such as 0.001 / 0.0001 / 0.5,
+//     or a <math.h> double function: sqrt, fabs) the same operation is done in double here [f64];
+//   * sinf/cosf are never evaluated on the device: the two Euler matrices the path needs are
+//     computed by the host with libm (PgBody.euler_raw / euler_node, include/physics_gpu.h).
+// Explicit __fmaf_rn / float-only shortcuts appear ONLY in conservative filters whose outcome is
+// proven to equal the exact predicate (see interval tests below); anything inside the proven band
+// falls through to the exact [f64] evaluation.
+//
+// Reference citations are relative to /root/reference/src/physics/.
+#pragma once
+
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/physics_gpu.h"
+
+namespace pgm {
+
+constexpr float kGravity = 9.8f;            // world.c:363,550; resolution.c:28,159,314,421,472,583,633
+constexpr double kMaxDt = 0.01666;          // world.c:18 (double)
+constexpr float kIntervalEps = 0.000001f;   // world.c:21
+constexpr double kNpEps = 0.0001;           // narrow_phase.c:6 (double)
+constexpr int kMaxIntervalDepth = 40;
+
+struct V3 { float x, y, z; };
+
+__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 v3p(const float *p) { return v3(p[0], p[1], p[2]); }
+__device__ __forceinline__ void store(float *p, V3 a) { p[0] = a.x; p[1] = a.y; p[2] = a.z; }
+__device__ __forceinline__ float get(const V3 &a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+__device__ __forceinline__ void set(V3 &a, int i, float v) { if (i == 0) a.x = v; else if (i == 1) a.y = v; else a.z = v; }
+
+// ---- cglm scalar forms (vec3.h) ----
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float norm(V3 a) { return sqrtf(dot(a, a)); }
+__device__ __forceinline__ V3 add(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 sub(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 scale(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ V3 muladds(V3 a, float s, V3 d) { return v3(d.x + a.x * s, d.y + a.y * s, d.z + a.z * s); }
+__device__ __forceinline__ V3 mulsubs(V3 a, float s, V3 d) { return v3(d.x - a.x * s, d.y - a.y * s, d.z - a.z * s); }
+__device__ __forceinline__ V3 normalize(V3 a) {
+  float n = norm(a);
+  if (n < FLT_EPSILON) return v3(0.0f, 0.0f, 0.0f);
+  return scale(a, 1.0f / n);
+}
+__device__ __forceinline__ float glm_max(float a, float b) { if (a > b) return a; return b; }
+__device__ __forceinline__ float glm_min(float a, float b) { if (a < b) return a; return b; }
+__device__ __forceinline__ float glm_clamp(float v, float lo, float hi) { return glm_min(glm_max(v, lo), hi); }
+
+// glm_mat4_mulv3(m, v, 1.0f): column-major m[c*4+r]
+__device__ __forceinline__ V3 xform_point(const float *m, V3 v) {
+  V3 r;
+  r.x = m[0] * v.x + m[4] * v.y + m[8] * v.z + m[12] * 1.0f;
+  r.y = m[1] * v.x + m[5] * v.y + m[9] * v.z + m[13] * 1.0f;
+  r.z = m[2] * v.x + m[6] * v.y + m[10] * v.z + m[14] * 1.0f;
+  return r;
+}
+// glm_mat3_mulv, column-major m[c*3+r]
+__device__ __forceinline__ V3 mat3_mulv(const float *m, V3 v) {
+  V3 r;
+  r.x = m[0] * v.x + m[3] * v.y + m[6] * v.z;
+  r.y = m[1] * v.x + m[4] * v.y + m[7] * v.z;
+  r.z = m[2] * v.x + m[5] * v.y + m[8] * v.z;
+  return r;
+}
+
+// World-space decomposition every AABB path repeats (distance.c:27-35): translation, per-column
+// norms, upper 3x3 divided by scale[0].
+struct NodeFrame { V3 pos; V3 scl; float rot[9]; };
+__device__ inline void node_decompose(const float *m, NodeFrame &f) {
+  f.pos = xform_point(m, v3(0.0f, 0.0f, 0.0f));
+  f.scl.x = norm(v3(m[0], m[1], m[2]));
+  f.scl.y = norm(v3(m[4], m[5], m[6]));
+  f.scl.z = norm(v3(m[8], m[9], m[10]));
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) f.rot[c * 3 + r] = m[c * 4 + r];
+  if (f.scl.x != 0.0f) {
+    float s = 1.0f / f.scl.x;
+#pragma unroll
+    for (int k = 0; k < 9; k++) f.rot[k] *= s;
+  }
+}
+
+struct Box { V3 c, e; };
+struct Ball { V3 c; float r; };
+struct Pill { V3 a, b; float r; };
+struct Flat { V3 n; float d; };
+
+// AABB_update, aabb.c:59-78.  [f64]: fabs() products are double, accumulated into a float.
+__device__ inline Box aabb_update(const float *shape, const float *rot, V3 tr, V3 scl) {
+  Box o;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float c = get(tr, i);
+    float e = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      c += rot[j * 3 + i] * shape[j];
+      e = (float)((double)e + fabs((double)rot[j * 3 + i]) * (double)shape[3 + j] * fabs((double)get(scl, i)));
+    }
+    set(o.c, i, c);
+    set(o.e, i, e);
+  }
+  return o;
+}
+__device__ __forceinline__ Box zero_box() { Box b; b.c = v3(0, 0, 0); b.e = v3(0, 0, 0); return b; }
+
+// Box through the scene-node transform, advanced by adv*time (distance.c:26-37; resolution.c:41-52).
+__device__ inline Box box_from_node(const PgBody &b, bool advance, V3 adv, float time) {
+  if (!b.has_node) return zero_box();
+  NodeFrame f; node_decompose(b.node_xform, f);
+  if (advance) f.pos = muladds(adv, time, f.pos);
+  return aabb_update(b.shape, f.rot, f.pos, f.scl);
+}
+// Box from body rotation (degrees read as radians) / position / scale: distance.c:253-264.
+__device__ inline Box box_from_body(const PgBody &b, V3 pos) {
+  return aabb_update(b.shape, b.euler_raw, pos, v3p(b.scale));
+}
+__device__ __forceinline__ Ball ball_from_body(const PgBody &b, V3 pos) {   // distance.c:282-285
+  Ball s; s.c = add(v3p(b.shape), pos); s.r = b.shape[3] * b.scale[0]; return s;
+}
+__device__ inline Ball ball_from_node(const PgBody &b, bool advance, V3 adv, float time) {   // distance.c:113-125
+  Ball s; s.c = v3(0, 0, 0); s.r = 0.0f;
+  if (!b.has_node) return s;
+  NodeFrame f; node_decompose(b.node_xform, f);
+  if (advance) f.pos = muladds(adv, time, f.pos);
+  s.c = add(v3p(b.shape), f.pos);
+  s.r = b.shape[3] * f.scl.x;
+  return s;
+}
+__device__ inline Pill pill_from_node(const PgBody &b) {   // distance.c:185-189,209
+  Pill p; p.a = v3(0, 0, 0); p.b = v3(0, 0, 0);
+  if (b.has_node) {
+    p.a = xform_point(b.node_xform, v3p(b.shape));
+    p.b = xform_point(b.node_xform, v3p(b.shape + 3));
+  }
+  p.r = b.shape[6] * b.scale[0];
+  return p;
+}
+__device__ inline Pill pill_from_body(const PgBody &b) {   // distance.c:366-379
+  Pill p;
+  p.a = scale(v3p(b.shape), b.scale[0]);
+  p.b = scale(v3p(b.shape + 3), b.scale[0]);
+  p.a = mat3_mulv(b.euler_raw, p.a);
+  p.b = mat3_mulv(b.euler_raw, p.b);
+  p.a = add(p.a, v3p(b.position));
+  p.b = add(p.b, v3p(b.position));
+  p.r = b.shape[6] * b.scale[0];
+  return p;
+}
+// Plane as a capsule sees it: rotated by the PARENT node (distance.c:342-364).
+__device__ inline Flat flat_for_pill(const PgBody &b) {
+  Flat f; f.n = v3(0, 0, 0); f.d = 0.0f;
+  if (!b.has_node) return f;
+  NodeFrame nf; node_decompose(b.parent_xform, nf);
+  f.n = normalize(mat3_mulv(nf.rot, v3p(b.shape)));
+  f.d = b.shape[3] + dot(nf.pos, f.n);
+  return f;
+}
+__device__ inline V3 pill_closest_to_flat(const Pill &p, const Flat &f) {   // distance.c:391-400
+  float n_dot_a = dot(f.n, p.a);
+  V3 seg = sub(p.b, p.a);
+  float n_dot_seg = dot(f.n, seg);
+  float t = (f.d - n_dot_a) / n_dot_seg;
+  if (t <= 0) return p.a;
+  if (t >= 1) return p.b;
+  V3 v = sub(p.b, p.a);                       // glm_vec3_lerp: from + t*(to-from)
+  v = v3(t * v.x, t * v.y, t * v.z);
+  return add(p.a, v);
+}
+__device__ inline V3 pill_box_pq(const Pill &p, const Box &bx) {   // distance.c:211-238
+  V3 seg = sub(p.b, p.a), a2c = sub(bx.c, p.a);
+  float proj = dot(seg, a2c);
+  float t = proj / dot(seg, seg);
+  t = glm_clamp(t, 0.0f, 1.0f);
+  V3 cp = muladds(seg, t, p.a);
+  V3 q;
+  q.x = glm_clamp(cp.x, bx.c.x - bx.e.x, bx.c.x + bx.e.x);
+  q.y = glm_clamp(cp.y, bx.c.y - bx.e.y, bx.c.y + bx.e.y);
+  q.z = glm_clamp(cp.z, bx.c.z - bx.e.z, bx.c.z + bx.e.z);
+  return sub(q, cp);
+}
+__device__ __forceinline__ float proj_radius_f64(V3 e, V3 n) {   // distance.c:267-270 [f64]
+  return (float)((double)e.x * fabs((double)n.x) + (double)e.y * fabs((double)n.y) + (double)e.z * fabs((double)n.z));
+}
+
+// =====================================================================================
+// Sphere-only scalar kernels: the hot path of configs C2-C4.  The general table below calls the
+// same functions, so both paths share one definition.
+// =====================================================================================
+
+// min_dist_at_time_sphere_sphere tail, distance.c:293-298.  d2 = |cA - cB|^2, rs = rA + rB.
+__device__ __forceinline__ float ss_dist_from_d2(float d2, float rs) {
+  return d2 < (rs * rs) ? 0.0f : (float)(sqrt((double)d2) - (double)rs);   // [f64]
+}
+// Does `ss_dist_from_d2(d2, rs) > mm` hold?  Exact, but decided in float whenever d2 is outside a
+// 1e-6-relative band around (rs+mm)^2:
+//   d2 < T2(1-4e-7)  =>  sqrt(d2)-rs < mm               => fl32(.) <= mm  => false
+//   d2 > T2(1+1e-6)  =>  sqrt(d2)-rs > mm(1+4e-7)+...   => fl32(.) >  mm  => true
+// with T2 = fl(fl(rs+mm)^2), whose relative error is < 1.8e-7.  Non-finite inputs take the exact path.
+__device__ __forceinline__ bool ss_dist_exceeds(float d2, float rs, float mm) {
+  float T = rs + mm;
+  float T2 = T * T;
+  if (d2 < T2 * 0.9999996f) return false;
+  if (d2 > T2 * 1.000001f && d2 < 3.0e38f) return true;
+  return ss_dist_from_d2(d2, rs) > mm;
+}
+__device__ __forceinline__ float ss_d2_at(V3 cA, V3 vA, V3 cB, V3 vB, float t) {   // distance.c:283-295
+  V3 a = muladds(vA, t, cA), b = muladds(vB, t, cB);
+  V3 d = sub(a, b);
+  return dot(d, d);
+}
+
+// interval_collision for two spheres, world.c:557-582 with distance.c:278-299 inlined.
+// cA/cB = centre + position at t=0, nA/nB = |v| (glm_vec3_norm), rs = rA + rB.
+// Depth-first, left child first, like the recursion; an explicit stack keeps the right siblings.
+__device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float nB, float rs,
+                                   float t_begin, float t_end) {
+  float st0[kMaxIntervalDepth], st1[kMaxIntervalDepth];
+  int sp = 0;
+  float t0 = t_begin, t1 = t_end;
+  for (;;) {
+    float len = t1 - t0;
+    float mm = nA * len + nB * len;
+    bool alive = !ss_dist_exceeds(ss_d2_at(cA, vA, cB, vB, t0), rs, mm) &&
+                 !ss_dist_exceeds(ss_d2_at(cA, vA, cB, vB, t1), rs, mm);
+    if (alive) {
+      if (len < kIntervalEps) return true;
+      float mid = (t0 + t1) * 0.5f;
+      if (sp < kMaxIntervalDepth) { st0[sp] = mid; st1[sp] = t1; sp++; }
+      t1 = mid;
+      continue;
+    }
+    if (sp == 0) return false;
+    sp--; t0 = st0[sp]; t1 = st1[sp];
+  }
+}
+
+// min_dist_at_time_sphere_plane, distance.c:305-321: max(|s| - r, 0), |s|-r in double.
+__device__ __forceinline__ float sp_dist(V3 c, V3 n, float d, float r) {
+  float s = dot(c, n) - d;
+  float dist = (float)(fabs((double)s) - (double)r);   // [f64]
+  return glm_max(dist, 0);
+}
+__device__ inline bool sp_interval(V3 c, V3 v, float nv, V3 n, float d, float r, float t_begin, float t_end) {
+  float st0[kMaxIntervalDepth], st1[kMaxIntervalDepth];
+  int sp = 0;
+  float t0 = t_begin, t1 = t_end;
+  for (;;) {
+    float len = t1 - t0;
+    float mm = nv * len + 0.0f * len;            // the plane's |v| is 0 (world.c:51): 0*len, then the sum
+    bool alive = !(sp_dist(muladds(v, t0, c), n, d, r) > mm) && !(sp_dist(muladds(v, t1, c), n, d, r) > mm);
+    if (alive) {
+      if (len < kIntervalEps) return true;
+      float mid = (t0 + t1) * 0.5f;
+      if (sp < kMaxIntervalDepth) { st0[sp] = mid; st1[sp] = t1; sp++; }
+      t1 = mid;
+      continue;
+    }
+    if (sp == 0) return false;
+    sp--; t0 = st0[sp]; t1 = st1[sp];
+  }
+}
+
+struct Contact { float t; bool hit; };
+__device__ __forceinline__ Contact contact(float t, bool hit) { Contact c; c.t = t; c.hit = hit; return c; }
+
+// narrow_phase_sphere_sphere, narrow_phase.c:459-520 (the early-outs fall through; see oracle).
+__device__ __forceinline__ Contact ss_narrow(V3 cA, V3 vA, V3 cB, V3 vB, float rs) {
+  V3 s = sub(cA, cB), v = sub(vA, vB);
+  float c = dot(s, s) - (rs * rs);
+  if (c < 0.0f) return contact(0.0f, true);
+  float a = dot(v, v);
+  float b = dot(v, s);
+  float d = (b * b) - a * c;
+  float t = (float)(((double)(-b) - sqrt((double)d)) / (double)a);   // [f64]
+  return contact(t, true);
+}
+// narrow_phase.c:553-585 / 663-695 tail.
+__device__ __forceinline__ Contact plane_tail(float s, float ndv, float r, float dt) {
+  float disc = s * ndv;
+  if (disc == 0) return fabs((double)s) <= (double)r ? contact(0.0f, true) : contact(-1.0f, false);
+  float t = disc < 0 ? (r - s) / ndv : (-r - s) / ndv;
+  if (t >= 0 && t <= dt) return contact(t, true);
+  if (s <= r) return contact(0.0f, true);
+  return contact(-1.0f, false);
+}
+__device__ __forceinline__ Contact sp_narrow(V3 c, V3 v, V3 n, float d, float r, float dt) {   // narrow_phase.c:526-588
+  float s = dot(c, n) - d;
+  float ndv = dot(v, n);
+  return plane_tail(s, ndv, r, dt);
+}
+
+// "advance to hit time under gravity", resolution.c:474-479 and siblings.
+__device__ __forceinline__ void advance_to_hit(V3 &pos, V3 vel, float t, V3 &vb) {
+  vb = vel;
+  vb.y -= kGravity * t;
+  pos = muladds(vb, t, pos);
+}
+__device__ __forceinline__ V3 reflect(V3 vb, V3 n, float restitution) {   // resolution.c:606-609
+  float vdn = dot(vb, n);
+  V3 refl = scale(n, -2.0f * vdn * restitution);
+  return add(vb, refl);
+}
+__device__ __forceinline__ void exchange_normal(V3 vbA, V3 vbB, V3 n, V3 &vA, V3 &vB) {   // resolution.c:515-528
+  float a = dot(vbA, n), b = dot(vbB, n);
+  V3 na = scale(n, a), nb = scale(n, b);
+  vA = add(sub(vbA, na), nb);
+  vB = add(sub(vbB, nb), na);
+}
+// resting rule, resolution.c:613-618: (double)v.n < 0.5 is the same set as v.n < 0.5f
+__device__ __forceinline__ bool rest_rule(V3 n, V3 vel) {
+  float vdn = dot(n, vel);
+  return (vdn < 0.5f) && (dot(n, v3(0.0f, -1.0f, 0.0f)) < 0);
+}
+
+// resolve_collision_sphere_sphere, resolution.c:467-570.  oA/oB = local sphere centres.
+__device__ inline void ss_resolve(V3 &pA, V3 &vA, V3 oA, V3 &pB, V3 &vB, V3 oB, float rs, float t) {
+  V3 vbA, vbB;
+  advance_to_hit(pA, vA, t, vbA);
+  advance_to_hit(pB, vB, t, vbB);
+  V3 diff = sub(add(oB, pB), add(oA, pA));
+  float s = norm(diff);
+  float pen = (s < rs) ? (float)((double)(rs - s) + 0.001) : 0.0f;   // [f64]
+  V3 n = normalize(diff);
+  if (pen <= 0.0f) return;
+  V3 rv = sub(vbB, vbA);
+  if (dot(rv, n) < 0.0f) {
+    pB = muladds(n, pen / 2, pB);
+    pA = mulsubs(n, pen / 2, pA);
+    exchange_normal(vbA, vbB, n, vA, vB);
+  } else { vA = vbA; vB = vbB; }
+}
+// resolve_collision_sphere_plane, resolution.c:576-622.  Returns true if the body came to rest.
+__device__ inline bool sp_resolve(V3 &p, V3 &v, V3 o, float r, float restitution, V3 n, float d, float t) {
+  V3 vb;
+  advance_to_hit(p, v, t, vb);
+  V3 c = add(o, p);
+  float s = dot(c, n) - d;
+  float pen = (s < r) ? (float)((double)(r - s) + 0.001) : 0.0f;   // [f64]
+  if (pen > 0.0f) p = add(p, scale(n, pen));
+  v = reflect(vb, n, restitution);
+  if (rest_rule(n, v)) { v = v3(0.0f, 0.0f, 0.0f); return true; }
+  return false;
+}
+
+// =====================================================================================
+// General path: all collider pairs, on PgBody records.
+// =====================================================================================
+
+__device__ __forceinline__ float max_move(const PgBody &b, float t0, float t1) {   // world.c:584-589
+  float dt = t1 - t0;
+  return norm(v3p(b.velocity)) * dt;
+}
+
+__device__ inline float dist_box_box(const PgBody &A, const PgBody &B, float t) {   // distance.c:20-92
+  Box a = box_from_node(A, true, v3p(A.velocity), t), b = box_from_node(B, true, v3p(B.velocity), t);
+  float d2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float minA = get(a.c, i) - get(a.e, i), maxA = get(a.c, i) + get(a.e, i);
+    float minB = get(b.c, i) - get(b.e, i), maxB = get(b.c, i) + get(b.e, i);
+    if (minB > maxA) d2 += (minB - maxA) * (minB - maxA);
+    else if (maxB < minA) d2 += (minA - maxB) * (minA - maxB);
+  }
+  return (float)sqrt((double)d2);   // [f64]
+}
+__device__ inline float dist_box_ball(const PgBody &A, const PgBody &B, float t) {   // distance.c:94-158
+  Box bx = box_from_node(A, true, v3p(A.velocity), t);
+  Ball s = ball_from_node(B, true, v3p(B.velocity), t);
+  float d2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float v = get(s.c, i), lo = get(bx.c, i) - get(bx.e, i), hi = get(bx.c, i) + get(bx.e, i);
+    if (v < lo) d2 += (lo - v) * (lo - v);
+    if (v > hi) d2 += (v - hi) * (v - hi);
+  }
+  return d2 < (s.r * s.r) ? 0.0f : (float)(sqrt((double)d2) - (double)s.r);   // [f64]
+}
+__device__ inline float dist_box_pill(const PgBody &A, const PgBody &B, float t) {   // distance.c:160-244
+  Box bx = box_from_node(A, true, v3p(A.velocity), t);
+  Pill p = pill_from_node(B);
+  V3 pq = pill_box_pq(p, bx);
+  return glm_max(norm(pq) - p.r, 0);
+}
+__device__ inline float dist_box_flat(const PgBody &A, const PgBody &B, float t) {   // distance.c:246-276
+  V3 pos = muladds(v3p(A.velocity), t, v3p(A.position));
+  Box bx = box_from_body(A, pos);
+  V3 n = v3p(B.shape);
+  float r = proj_radius_f64(bx.e, n);
+  float s = dot(n, bx.c) - B.shape[3];
+  return glm_max(s - r, 0);
+}
+__device__ inline float dist_ball_ball(const PgBody &A, const PgBody &B, float t) {   // distance.c:278-299
+  Ball a = ball_from_body(A, v3p(A.position)), b = ball_from_body(B, v3p(B.position));
+  float d2 = ss_d2_at(a.c, v3p(A.velocity), b.c, v3p(B.velocity), t);
+  return ss_dist_from_d2(d2, a.r + b.r);
+}
+__device__ inline float dist_ball_flat(const PgBody &A, const PgBody &B, float t) {   // distance.c:305-321
+  Ball a = ball_from_body(A, v3p(A.position));
+  return sp_dist(muladds(v3p(A.velocity), t, a.c), v3p(B.shape), B.shape[3], a.r);
+}
+__device__ inline float dist_pill_flat(const PgBody &A, const PgBody &B, float) {   // distance.c:327-410
+  Flat f = flat_for_pill(B);
+  Pill p = pill_from_body(A);
+  V3 cp = pill_closest_to_flat(p, f);
+  float s = dot(cp, f.n) - f.d;
+  float d = (float)(fabs((double)s) - (double)p.r);   // [f64]
+  return glm_max(d, 0);
+}
+
+// distance_functions table, distance.c:7-17.  Missing / undefined entries report 0 ("always close").
+__device__ inline float min_dist(const PgBody &A, const PgBody &B, float t) {
+  switch (A.collider_type * 4 + B.collider_type) {
+    case PG_AABB * 4 + PG_AABB: return dist_box_box(A, B, t);
+    case PG_AABB * 4 + PG_SPHERE: return dist_box_ball(A, B, t);
+    case PG_AABB * 4 + PG_CAPSULE: return dist_box_pill(A, B, t);
+    case PG_AABB * 4 + PG_PLANE: return dist_box_flat(A, B, t);
+    case PG_SPHERE * 4 + PG_SPHERE: return dist_ball_ball(A, B, t);
+    case PG_SPHERE * 4 + PG_PLANE: return dist_ball_flat(A, B, t);
+    case PG_CAPSULE * 4 + PG_PLANE: return dist_pill_flat(A, B, t);
+    default: return 0.0f;
+  }
+}
+
+// interval_collision, world.c:557-582 (general collider pair).
+__device__ inline bool interval_hit(const PgBody &A, const PgBody &B, float t_begin, float t_end, float *hit) {
+  float st0[kMaxIntervalDepth], st1[kMaxIntervalDepth];
+  int sp = 0;
+  float t0 = t_begin, t1 = t_end;
+  for (;;) {
+    float mm = max_move(A, t0, t1) + max_move(B, t0, t1);
+    bool alive = !(min_dist(A, B, t0) > mm) && !(min_dist(A, B, t1) > mm);
+    if (alive) {
+      if (t1 - t0 < kIntervalEps) { *hit = t0; return true; }
+      float mid = (t0 + t1) * 0.5f;
+      if (sp < kMaxIntervalDepth) { st0[sp] = mid; st1[sp] = t1; sp++; }
+      t1 = mid;
+      continue;
+    }
+    if (sp == 0) return false;
+    sp--; t0 = st0[sp]; t1 = st1[sp];
+  }
+}
+
+__device__ inline bool aabb_hits_aabb(const Box &a, const Box &b) {   // aabb.c:100-105
+  if (fabs((double)(a.c.x - b.c.x)) > (double)(a.e.x + b.e.x)) return false;
+  if (fabs((double)(a.c.y - b.c.y)) > (double)(a.e.y + b.e.y)) return false;
+  if (fabs((double)(a.c.z - b.c.z)) > (double)(a.e.z + b.e.z)) return false;
+  return true;
+}
+
+__device__ inline Contact np_box_box(const PgBody &A, const PgBody &B, float dt) {   // narrow_phase.c:21-141
+  Box a = box_from_node(A, false, v3(0, 0, 0), 0), b = box_from_node(B, false, v3(0, 0, 0), 0);
+  if (aabb_hits_aabb(a, b)) return contact(0.0f, true);
+  V3 rv = sub(v3p(A.velocity), v3p(B.velocity));
+  float t_first = 0.0f, t_last = dt;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float minA = get(a.c, i) - get(a.e, i), maxA = get(a.c, i) + get(a.e, i);
+    float minB = get(b.c, i) - get(b.e, i), maxB = get(b.c, i) + get(b.e, i);
+    float r = get(rv, i);
+    if (r < 0.0f) {
+      if (maxA < minB) return contact(-1.0f, false);
+      if (minA > maxB) t_first = fmaxf((maxB - minA) / r, t_first);
+      if (maxA > minB) t_last = fminf((minB - maxA) / r, t_last);
+    }
+    if (r > 0.0f) {
+      if (minA > maxB) return contact(-1.0f, false);
+      if (maxA < minB) t_first = fmaxf((minB - maxA) / r, t_first);
+      if (minA < maxB) t_last = fminf((maxB - minA) / r, t_last);
+    }
+    if (t_first > t_last) return contact(-1.0f, false);
+  }
+  return contact(t_first, true);
+}
+__device__ inline bool ray_box(V3 p, V3 d, V3 c, V3 e, float *hit, float t_end) {   // narrow_phase.c:702-739
+  *hit = 0.0f;
+  float t_max = t_end;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float lo = get(c, i) - get(e, i), hi = get(c, i) + get(e, i), pi = get(p, i), di = get(d, i);
+    if ((double)fabsf(di) < kNpEps) {
+      if (pi < lo || pi > hi) return false;
+    } else {
+      float t1 = (lo - pi) / di;
+      float t2 = (hi - pi) / di;
+      if (t1 > t2) { float tmp = t1; t1 = t2; t2 = tmp; }
+      if (t1 > *hit) *hit = t1;
+      if (t2 < t_max) t_max = t2;
+      if (*hit > t_max) return false;
+    }
+  }
+  return true;
+}
+__device__ inline Contact np_box_ball(const PgBody &A, const PgBody &B, float dt) {   // narrow_phase.c:143-196
+  Box bx = box_from_node(A, false, v3(0, 0, 0), 0);
+  Ball s = ball_from_node(B, false, v3(0, 0, 0), 0);
+  V3 e = v3(bx.e.x + s.r, bx.e.y + s.r, bx.e.z + s.r);
+  V3 rv = sub(v3p(B.velocity), v3p(A.velocity));
+  float tmin;
+  bool hit = ray_box(s.c, rv, bx.c, e, &tmin, dt);
+  if (!hit || tmin > dt) return contact(-1.0f, false);
+  return contact(tmin, true);
+}
+__device__ inline Contact np_box_pill(const PgBody &A, const PgBody &B, float dt) {   // narrow_phase.c:233-342
+  Box bx = box_from_node(A, false, v3(0, 0, 0), 0);
+  Pill p = pill_from_node(B);
+  V3 pq = pill_box_pq(p, bx);
+  float distance = norm(pq) - p.r;
+  pq = normalize(pq);
+  float pq_dot_v = dot(v3p(B.velocity), pq);
+  float disc = distance * pq_dot_v;
+  if (disc == 0) return distance < 0 ? contact(0.0f, true) : contact(-1.0f, false);
+  float t = distance / pq_dot_v;
+  if (t >= 0 && t <= dt) return contact(t, true);
+  if (distance <= 0) return contact(0.0f, true);
+  return contact(-1.0f, false);
+}
+__device__ inline Contact np_box_flat(const PgBody &A, const PgBody &B, float dt) {   // narrow_phase.c:344-457
+  Box bx = box_from_body(A, v3p(A.position));
+  V3 n = v3p(B.shape);
+  float r = proj_radius_f64(bx.e, n);
+  float s = dot(n, bx.c) - B.shape[3];
+  float ndv = dot(n, v3p(A.velocity));
+  bool inside = fabs((double)s) <= (double)r;
+  if (ndv == 0) return inside ? contact(0.0f, true) : contact(-1.0f, false);
+  Contact c;
+  if (ndv < 0) { c.t = (r - s) / -ndv; c.hit = (c.t >= 0 && c.t <= dt); }
+  else if (inside) { c.t = 0.0f; c.hit = true; }
+  else { c.t = (r + s) / -ndv; c.hit = (c.t >= 0 && c.t <= dt); }
+  if (c.hit) c.t = fmaxf(0.0f, fminf(c.t, dt));
+  if (!c.hit) { if (inside) return contact(0.0f, true); c.t = -1.0f; }
+  return c;
+}
+__device__ inline Contact np_ball_ball(const PgBody &A, const PgBody &B, float) {
+  Ball a = ball_from_body(A, v3p(A.position)), b = ball_from_body(B, v3p(B.position));
+  return ss_narrow(a.c, v3p(A.velocity), b.c, v3p(B.velocity), a.r + b.r);
+}
+__device__ inline Contact np_ball_flat(const PgBody &A, const PgBody &B, float dt) {
+  Ball a = ball_from_body(A, v3p(A.position));
+  return sp_narrow(a.c, v3p(A.velocity), v3p(B.shape), B.shape[3], a.r, dt);
+}
+__device__ inline Contact np_pill_flat(const PgBody &A, const PgBody &B, float dt) {   // narrow_phase.c:594-698
+  Flat f = flat_for_pill(B);
+  Pill p = pill_from_body(A);
+  V3 cp = pill_closest_to_flat(p, f);
+  float s = dot(cp, f.n) - f.d;
+  float ndv = dot(v3p(A.velocity), f.n);
+  return plane_tail(s, ndv, p.r, dt);
+}
+// narrow_phase_functions table, narrow_phase.c:8-19.  *has=false for NULL / empty-body entries.
+__device__ inline Contact narrow(const PgBody &A, const PgBody &B, float dt, bool *has) {
+  *has = true;
+  switch (A.collider_type * 4 + B.collider_type) {
+    case PG_AABB * 4 + PG_AABB: return np_box_box(A, B, dt);
+    case PG_AABB * 4 + PG_SPHERE: return np_box_ball(A, B, dt);
+    case PG_AABB * 4 + PG_CAPSULE: return np_box_pill(A, B, dt);
+    case PG_AABB * 4 + PG_PLANE: return np_box_flat(A, B, dt);
+    case PG_SPHERE * 4 + PG_SPHERE: return np_ball_ball(A, B, dt);
+    case PG_SPHERE * 4 + PG_PLANE: return np_ball_flat(A, B, dt);
+    case PG_CAPSULE * 4 + PG_PLANE: return np_pill_flat(A, B, dt);
+    default: *has = false; return contact(0.0f, false);
+  }
+}
+
+// ---- resolution (resolution.c) on records ----
+__device__ __forceinline__ void body_advance(PgBody &b, float t, V3 &vb) {
+  V3 p = v3p(b.position);
+  advance_to_hit(p, v3p(b.velocity), t, vb);
+  store(b.position, p);
+}
+__device__ __forceinline__ void body_rest_rule(PgBody &b, V3 n) {
+  if (rest_rule(n, v3p(b.velocity))) { b.velocity[0] = b.velocity[1] = b.velocity[2] = 0.0f; b.at_rest = 1; }
+}
+__device__ inline void dyn_dyn_tail(PgBody &A, PgBody &B, V3 vbA, V3 vbB, V3 dir, V3 n, float half_pen) {
+  V3 rv = sub(vbB, vbA);
+  if (dot(rv, n) < 0.0f) {
+    store(B.position, muladds(dir, half_pen, v3p(B.position)));
+    store(A.position, mulsubs(dir, half_pen, v3p(A.position)));
+    V3 vA, vB; exchange_normal(vbA, vbB, n, vA, vB);
+    store(A.velocity, vA); store(B.velocity, vB);
+  } else { store(A.velocity, vbA); store(B.velocity, vbB); }
+}
+__device__ inline void rs_box_box(PgBody &A, PgBody &B, float t) {   // resolution.c:21-150
+  V3 vbA = v3(0, 0, 0), vbB = v3(0, 0, 0);      // static side: 0 (uninitialised upstream)
+  if (A.dynamic) body_advance(A, t, vbA);
+  if (B.dynamic) body_advance(B, t, vbB);
+  Box a = box_from_node(A, true, vbA, t), b = box_from_node(B, true, vbB, t);
+  V3 cd = sub(b.c, a.c);
+  float min_pen = FLT_MAX; int axis = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float s = (float)fabs((double)get(cd, i));
+    float r = get(a.e, i) + get(b.e, i);
+    float pen = r - s;
+    if (pen < min_pen) { min_pen = pen; axis = i; }
+  }
+  if (min_pen <= 0.0f) return;
+  V3 sep = v3(0, 0, 0);
+  set(sep, axis, get(cd, axis) < 0 ? -1.0f : 1.0f);
+  V3 n = normalize(sep);
+  if (A.dynamic && !B.dynamic) {
+    store(A.position, mulsubs(sep, min_pen, v3p(A.position)));
+    store(A.velocity, reflect(vbA, n, A.restitution));
+  } else if (!A.dynamic && B.dynamic) {
+    store(B.position, muladds(sep, min_pen, v3p(B.position)));
+    float vdn = dot(vbB, n);
+    V3 refl = scale(n, -2.0f * vdn * B.restitution);
+    store(B.velocity, add(vbA, refl));          // sic: velocity_before_A, resolution.c:118
+  } else {
+    dyn_dyn_tail(A, B, vbA, vbB, sep, n, min_pen * 0.5f);
+  }
+}
+__device__ inline void rs_box_ball(PgBody &A, PgBody &B, float t) {   // resolution.c:152-302
+  V3 vbA = v3(0, 0, 0), vbB = v3(0, 0, 0);
+  if (A.dynamic) body_advance(A, t, vbA);
+  if (B.dynamic) body_advance(B, t, vbB);
+  Box bx = box_from_node(A, true, vbA, t);
+  Ball s = ball_from_node(B, true, vbB, t);
+  V3 closest;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float lo = get(bx.c, i) - get(bx.e, i), hi = get(bx.c, i) + get(bx.e, i), ci = get(s.c, i);
+    set(closest, i, lo > ci ? lo : (hi > ci ? ci : hi));
+  }
+  V3 diff = sub(s.c, closest);
+  float d = norm(diff);
+  float pen = (d < s.r) ? (float)((double)(s.r - d) + 0.001) : 0.0f;   // [f64]
+  if (pen <= 0) return;
+  V3 n = normalize(diff);
+  if (A.dynamic && !B.dynamic) {
+    store(A.position, mulsubs(n, pen * 0.5f, v3p(A.position)));
+    store(A.velocity, reflect(vbA, n, A.restitution));
+  } else if (!A.dynamic && B.dynamic) {
+    store(B.position, muladds(n, pen * 0.5f, v3p(B.position)));
+    store(B.velocity, reflect(vbB, n, B.restitution));
+  } else {
+    dyn_dyn_tail(A, B, vbA, vbB, n, n, pen * 0.5f);
+  }
+}
+__device__ inline void rs_box_pill(PgBody &A, PgBody &B, float t) {   // resolution.c:304-414
+  V3 vb; body_advance(B, t, vb);
+  Box bx = box_from_node(A, false, v3(0, 0, 0), 0);
+  Pill p = pill_from_node(B);
+  if (B.has_node) { p.a = muladds(vb, t, p.a); p.b = muladds(vb, t, p.b); }
+  V3 pq = pill_box_pq(p, bx);
+  float distance = norm(pq);
+  pq = normalize(pq);
+  float pen = distance < p.r ? (p.r - distance) + 0.001f : 0.0f;
+  if (pen <= 0.0f) return;
+  store(B.position, sub(v3p(B.position), scale(pq, pen)));
+  store(B.velocity, reflect(vb, pq, B.restitution));
+  body_rest_rule(B, v3(-pq.x, -pq.y, -pq.z));
+}
+__device__ inline void rs_box_flat(PgBody &A, PgBody &B, float t) {   // resolution.c:416-466
+  V3 vb; body_advance(A, t, vb);
+  Box bx = box_from_body(A, v3p(A.position));
+  V3 n = v3p(B.shape);
+  float r = bx.e.x * fabsf(n.x) + bx.e.y * fabsf(n.y) + bx.e.z * fabsf(n.z);
+  float s = dot(n, bx.c) - B.shape[3];
+  float pen = (s < r) ? (float)((double)(r - s) + 0.001) : 0.0f;   // [f64]
+  if (pen > 0.0f) store(A.position, add(v3p(A.position), scale(n, pen)));
+  store(A.velocity, reflect(vb, n, A.restitution));
+  body_rest_rule(A, n);
+}
+__device__ inline void rs_ball_ball(PgBody &A, PgBody &B, float t) {
+  V3 pA = v3p(A.position), vA = v3p(A.velocity), pB = v3p(B.position), vB = v3p(B.velocity);
+  float rs = A.shape[3] * A.scale[0] + B.shape[3] * B.scale[0];
+  ss_resolve(pA, vA, v3p(A.shape), pB, vB, v3p(B.shape), rs, t);
+  store(A.position, pA); store(A.velocity, vA); store(B.position, pB); store(B.velocity, vB);
+}
+__device__ inline void rs_ball_flat(PgBody &A, PgBody &B, float t) {
+  V3 p = v3p(A.position), v = v3p(A.velocity);
+  bool rest = sp_resolve(p, v, v3p(A.shape), A.shape[3] * A.scale[0], A.restitution, v3p(B.shape), B.shape[3], t);
+  store(A.position, p); store(A.velocity, v);
+  if (rest) A.at_rest = 1;
+}
+__device__ inline void rs_pill_flat(PgBody &A, PgBody &B, float t) {   // resolution.c:628-717
+  V3 vb; body_advance(A, t, vb);
+  Flat f = flat_for_pill(B);
+  Pill p = pill_from_body(A);
+  V3 cp = pill_closest_to_flat(p, f);
+  float s = dot(cp, f.n) - f.d;
+  float pen = (s < p.r) ? (float)((double)(p.r - s) + 0.001) : 0.0f;   // [f64]
+  if (pen <= 0.0f) return;
+  store(A.position, add(v3p(A.position), scale(f.n, pen)));
+  store(A.velocity, reflect(vb, f.n, A.restitution));
+  body_rest_rule(A, f.n);
+}
+// resolution_functions table, resolution.c:8-18.
+__device__ inline bool resolve(PgBody &A, PgBody &B, float t) {
+  switch (A.collider_type * 4 + B.collider_type) {
+    case PG_AABB * 4 + PG_AABB: rs_box_box(A, B, t); return true;
+    case PG_AABB * 4 + PG_SPHERE: rs_box_ball(A, B, t); return true;
+    case PG_AABB * 4 + PG_CAPSULE: rs_box_pill(A, B, t); return true;
+    case PG_AABB * 4 + PG_PLANE: rs_box_flat(A, B, t); return true;
+    case PG_SPHERE * 4 + PG_SPHERE: rs_ball_ball(A, B, t); return true;
+    case PG_SPHERE * 4 + PG_PLANE: rs_ball_flat(A, B, t); return true;
+    case PG_CAPSULE * 4 + PG_PLANE: rs_pill_flat(A, B, t); return true;
+    default: return false;
+  }
+}
+
+__device__ __forceinline__ int collision_behavior(int ta, int tb) {   // collider.c:7-17; 0 = PHYSICS
+  // rows/cols GROUPING, WORLD, ITEM, PLAYER: TRIGGER iff either side is GROUPING or the pair is {ITEM, PLAYER}
+  if (ta == PG_ENT_GROUPING || tb == PG_ENT_GROUPING) return 1;
+  if ((ta == PG_ENT_ITEM && tb == PG_ENT_PLAYER) || (ta == PG_ENT_PLAYER && tb == PG_ENT_ITEM)) return 1;
+  return 0;
+}
+__device__ __forceinline__ int event_type(int ta, int tb) {   // event.c:14-20
+  return ((ta == PG_ENT_ITEM && tb == PG_ENT_PLAYER) || (ta == PG_ENT_PLAYER && tb == PG_ENT_ITEM)) ? 1 : 0;
+}
+
+// One visit of world.c:481-547 on two records ALREADY ordered by collider type.
+// Returns true when the reference would enqueue an event.
+__device__ inline bool visit_ordered(PgBody &A, PgBody &B, float dt) {
+  float hit;
+  Contact c = contact(0.0f, false);
+  if (interval_hit(A, B, 0.0f, dt, &hit)) {
+    bool has;
+    Contact r = narrow(A, B, dt, &has);
+    if (has) c = r;
+  }
+  if (!(c.hit && c.t >= 0)) return false;
+  if (collision_behavior(A.entity_type, B.entity_type) == 0) resolve(A, B, c.t);
+  return true;
+}
+
+__device__ __forceinline__ void integrate(V3 &p, V3 &v, float dt) {   // world.c:549-553
+  v.y -= kGravity * dt;
+  p = muladds(v, dt, p);
+}
+__device__ __forceinline__ float clamp_dt(float dt) { if ((double)dt > kMaxDt) dt = (float)kMaxDt; return dt; }
+
+// scene_node_update (scene.c:1051-1079) for a node whose parent is static:
+// local = [R * diag(scale) | pos], world = parent * local (glm_mat4_mul, scalar order).
+__device__ inline void node_refresh(PgBody &b) {
+  float local[16];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+#pragma unroll
+    for (int r = 0; r < 3; r++) local[c * 4 + r] = b.euler_node[c * 3 + r] * b.scale[c];
+    local[c * 4 + 3] = 0.0f * b.scale[c];
+  }
+  local[12] = b.position[0]; local[13] = b.position[1]; local[14] = b.position[2]; local[15] = 1.0f;
+  if (!b.has_parent) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) b.node_xform[k] = local[k];
+    return;
+  }
+  const float *p = b.parent_xform;
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      b.node_xform[c * 4 + k] = p[0 * 4 + k] * local[c * 4 + 0] + p[1 * 4 + k] * local[c * 4 + 1] +
+                                p[2 * 4 + k] * local[c * 4 + 2] + p[3 * 4 + k] * local[c * 4 + 3];
+}
+
+}  // namespace pgm

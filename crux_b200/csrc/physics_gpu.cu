@@ -1,0 +1,530 @@
+// physics_gpu.cu -- C-ABI entry points of libphysics_gpu.so (include/physics_gpu.h): handle
+// lifetime, host<->device state exchange, launches.  Kernels live in pg_general.cu (any collider
+// mix, block per world), pg_spheres.cu (sphere batches, warp per world) and pg_large.cu (one big
+// world).  No CPU fallback: without a usable CUDA device every call fails with PG_ERR_CUDA.
+#include "pg_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+
+void pg_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+// glm_euler_xyz upper 3x3 (cglm euler.h), host libm sinf/cosf -- same library the reference links.
+void euler_xyz(const float *a, float *rot) {
+  float sx = sinf(a[0]), cx = cosf(a[0]);
+  float sy = sinf(a[1]), cy = cosf(a[1]);
+  float sz = sinf(a[2]), cz = cosf(a[2]);
+  float czsx = cz * sx, cxcz = cx * cz, sysz = sy * sz;
+  rot[0] = cy * cz;
+  rot[1] = czsx * sy + cx * sz;
+  rot[2] = -cxcz * sy + sx * sz;
+  rot[3] = -cy * sz;
+  rot[4] = cxcz - sx * sysz;
+  rot[5] = czsx + cx * sysz;
+  rot[6] = sy;
+  rot[7] = -cy * sx;
+  rot[8] = cx * cy;
+}
+
+inline float to_rad(float deg) { return deg * 3.14159265358979323846264338327950288f / 180.0f; }   // glm_rad
+
+bool valid_world(const PgWorlds *w, int world) { return w && world >= 0 && world < w->v.n_worlds; }
+
+// Can a resolver write to a STATIC body?  (sphere-sphere always moves both, box-capsule always
+// moves the capsule, ...; see pg_general.cu.)  Pass 3 may run one thread per dynamic body only if not.
+bool statics_read_only(const PgBody *st, int n) {
+  for (int i = 0; i < n; i++)
+    if (st[i].collider_type != PG_AABB && st[i].collider_type != PG_PLANE) return false;
+  return true;
+}
+
+int refresh_parallel_flag(PgWorlds *w) {
+  // conservative: inspect every world's statics and dynamics on the host copy
+  std::vector<PgBody> tmp;
+  bool ok = true;
+  for (int wd = 0; wd < w->v.n_worlds && ok; wd++) {
+    int ns = w->h_counts[wd * 3 + 0], nd = w->h_counts[wd * 3 + 1];
+    if (ns) {
+      tmp.resize(ns);
+      PG_CUDA(cudaMemcpy(tmp.data(), w->v.bodies[0] + (size_t)wd * w->v.cap[0], sizeof(PgBody) * ns, cudaMemcpyDeviceToHost));
+      ok = ok && statics_read_only(tmp.data(), ns);
+    }
+    if (nd && ok) {
+      tmp.resize(nd);
+      PG_CUDA(cudaMemcpy(tmp.data(), w->v.bodies[1] + (size_t)wd * w->v.cap[1], sizeof(PgBody) * nd, cudaMemcpyDeviceToHost));
+      for (int i = 0; i < nd; i++) if (tmp[i].collider_type == PG_PLANE) ok = false;   // AABB-plane resolver writes the AABB
+    }
+  }
+  w->static_pass_parallel_ok = ok;
+  return PG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *pg_last_error(void) { return g_err; }
+
+int pg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void pg_body_prepare(PgBody *b, int n) {
+  for (int i = 0; i < n; i++) {
+    euler_xyz(b[i].rotation, b[i].euler_raw);
+    float rad[3] = {to_rad(b[i].rotation[0]), to_rad(b[i].rotation[1]), to_rad(b[i].rotation[2])};
+    euler_xyz(rad, b[i].euler_node);
+  }
+}
+
+void pg_node_transform(const float *pos, const float *rot_deg, const float *scale,
+                       const float *parent, float *world) {
+  float rad[3] = {to_rad(rot_deg[0]), to_rad(rot_deg[1]), to_rad(rot_deg[2])};
+  float r[9];
+  euler_xyz(rad, r);
+  float local[16];
+  for (int c = 0; c < 3; c++) {
+    for (int k = 0; k < 3; k++) local[c * 4 + k] = r[c * 3 + k] * scale[c];
+    local[c * 4 + 3] = 0.0f * scale[c];
+  }
+  local[12] = pos[0]; local[13] = pos[1]; local[14] = pos[2]; local[15] = 1.0f;
+  if (!parent) { memcpy(world, local, sizeof(local)); return; }
+  float out[16];
+  for (int c = 0; c < 4; c++)
+    for (int k = 0; k < 4; k++)
+      out[c * 4 + k] = parent[0 * 4 + k] * local[c * 4 + 0] + parent[1 * 4 + k] * local[c * 4 + 1] +
+                       parent[2 * 4 + k] * local[c * 4 + 2] + parent[3 * 4 + k] * local[c * 4 + 3];
+  memcpy(world, out, sizeof(out));
+}
+
+void *pg_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { pg_set_error("cudaHostAlloc(%zu) failed", bytes); cudaGetLastError(); return nullptr; }
+  return p;
+}
+void pg_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ------------------------------------------------------------------ batched worlds
+
+PgWorlds *pg_worlds_create(int n_worlds, int max_static, int max_dynamic, int max_player,
+                           int max_events_per_world, int device) {
+  if (n_worlds <= 0 || max_static < 0 || max_dynamic < 0 || max_player < 0 || max_events_per_world < 0) {
+    pg_set_error("pg_worlds_create: bad argument");
+    return nullptr;
+  }
+  PG_CUDA_NULL(cudaSetDevice(device));
+  PgWorlds *w = new PgWorlds();
+  memset(w, 0, sizeof(*w));
+  w->device = device;
+  w->mode = PG_MODE_GENERAL;
+  w->v.n_worlds = n_worlds;
+  w->v.cap[0] = std::max(max_static, 1);
+  w->v.cap[1] = std::max(max_dynamic, 1);
+  w->v.cap[2] = std::max(max_player, 1);
+  w->v.max_events = max_events_per_world;
+  w->static_pass_parallel_ok = true;
+  cudaDeviceProp prop;
+  PG_CUDA_NULL(cudaGetDeviceProperties(&prop, device));
+  w->sm_count = prop.multiProcessorCount;
+  PG_CUDA_NULL(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+  PG_CUDA_NULL(cudaEventCreate(&w->ev0));
+  PG_CUDA_NULL(cudaEventCreate(&w->ev1));
+  PG_CUDA_NULL(cudaMalloc(&w->v.counts, sizeof(int) * 3 * (size_t)n_worlds));
+  PG_CUDA_NULL(cudaMemset(w->v.counts, 0, sizeof(int) * 3 * (size_t)n_worlds));
+  PG_CUDA_NULL(cudaMalloc(&w->v.n_events, sizeof(int) * (size_t)n_worlds));
+  PG_CUDA_NULL(cudaMemset(w->v.n_events, 0, sizeof(int) * (size_t)n_worlds));
+  if (max_events_per_world > 0)
+    PG_CUDA_NULL(cudaMalloc(&w->v.events, sizeof(PgEvent) * (size_t)n_worlds * max_events_per_world));
+  PG_CUDA_NULL(cudaMalloc(&w->d_stats, 8 * sizeof(double)));
+  w->h_counts = (int *)calloc((size_t)n_worlds * 3, sizeof(int));
+  return w;
+}
+
+void pg_worlds_destroy(PgWorlds *w) {
+  if (!w) return;
+  cudaSetDevice(w->device);
+  cudaStreamSynchronize(w->stream);
+  for (int c = 0; c < 3; c++) if (w->v.bodies[c]) cudaFree(w->v.bodies[c]);
+  if (w->v.counts) cudaFree(w->v.counts);
+  if (w->v.events) cudaFree(w->v.events);
+  if (w->v.n_events) cudaFree(w->v.n_events);
+  if (w->v.pos_rest) cudaFree(w->v.pos_rest);
+  if (w->v.vel_rad) cudaFree(w->v.vel_rad);
+  if (w->v.planes) cudaFree(w->v.planes);
+  if (w->d_stats) cudaFree(w->d_stats);
+  if (w->d_stage_pos) { cudaFree(w->d_stage_pos); cudaFree(w->d_stage_vel); cudaFree(w->d_stage_rest); }
+  cudaEventDestroy(w->ev0);
+  cudaEventDestroy(w->ev1);
+  cudaStreamDestroy(w->stream);
+  free(w->h_counts);
+  delete w;
+}
+
+int pg_worlds_count(const PgWorlds *w) { return w ? w->v.n_worlds : 0; }
+
+static int ensure_records(PgWorlds *w) {
+  for (int c = 0; c < 3; c++) {
+    if (!w->v.bodies[c]) {
+      size_t bytes = sizeof(PgBody) * (size_t)w->v.n_worlds * w->v.cap[c];
+      PG_CUDA(cudaMalloc(&w->v.bodies[c], bytes));
+      PG_CUDA(cudaMemset(w->v.bodies[c], 0, bytes));
+    }
+  }
+  return PG_OK;
+}
+
+static int push_counts(PgWorlds *w, int world) {
+  PG_CUDA(cudaMemcpyAsync(w->v.counts + world * 3, w->h_counts + world * 3, 3 * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  return PG_OK;
+}
+
+int pg_worlds_set_bodies(PgWorlds *w, int world, int cls, const PgBody *bodies, int n) {
+  if (!valid_world(w, world) || cls < 0 || cls > 2 || n < 0) { pg_set_error("pg_worlds_set_bodies: bad argument"); return PG_ERR_ARG; }
+  if (w->mode != PG_MODE_GENERAL) { pg_set_error("handle is in sphere mode"); return PG_ERR_ARG; }
+  if (n > w->v.cap[cls]) { pg_set_error("class %d: %d bodies > capacity %d", cls, n, w->v.cap[cls]); return PG_ERR_CAPACITY; }
+  PG_CUDA(cudaSetDevice(w->device));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  int rc = ensure_records(w);
+  if (rc) return rc;
+  if (n) {
+    std::vector<PgBody> tmp(bodies, bodies + n);
+    for (int i = 0; i < n; i++) {
+      // physics_add_body / physics_add_player field rules, world.c:41-142
+      if (cls == PG_CLASS_STATIC) { tmp[i].velocity[0] = tmp[i].velocity[1] = tmp[i].velocity[2] = 0.0f; tmp[i].dynamic = 0; }
+      if (cls == PG_CLASS_DYNAMIC) tmp[i].dynamic = 1;
+      if (cls == PG_CLASS_PLAYER) { tmp[i].restitution = 0.0f; tmp[i].dynamic = 0; }
+    }
+    PG_CUDA(cudaMemcpy(w->v.bodies[cls] + (size_t)world * w->v.cap[cls], tmp.data(), sizeof(PgBody) * (size_t)n, cudaMemcpyHostToDevice));
+  }
+  w->h_counts[world * 3 + cls] = n;
+  rc = push_counts(w, world);
+  if (rc) return rc;
+  return refresh_parallel_flag(w);
+}
+
+int pg_worlds_add_body(PgWorlds *w, int world, const PgBody *body, int as_player) {
+  if (!valid_world(w, world) || !body) { pg_set_error("pg_worlds_add_body: bad argument"); return PG_ERR_ARG; }
+  if (w->mode != PG_MODE_GENERAL) { pg_set_error("handle is in sphere mode"); return PG_ERR_ARG; }
+  // collider type check of world.c:56 / :125 (`> COLLIDER_COUNT`, so 4 slips through upstream; rejected here)
+  if (body->collider_type < 0 || body->collider_type > PG_PLANE) {
+    pg_set_error("Error: collider type provided to physics_add_body is invalid");
+    return PG_ERR_ARG;
+  }
+  int cls = as_player ? PG_CLASS_PLAYER : (body->dynamic ? PG_CLASS_DYNAMIC : PG_CLASS_STATIC);
+  int n = w->h_counts[world * 3 + cls];
+  if (n >= w->v.cap[cls]) { pg_set_error("class %d full (%d)", cls, n); return PG_ERR_CAPACITY; }
+  PG_CUDA(cudaSetDevice(w->device));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  int rc = ensure_records(w);
+  if (rc) return rc;
+  PgBody tmp = *body;
+  if (cls == PG_CLASS_STATIC) { tmp.velocity[0] = tmp.velocity[1] = tmp.velocity[2] = 0.0f; }
+  if (cls == PG_CLASS_PLAYER) { tmp.restitution = 0.0f; tmp.dynamic = 0; }
+  PG_CUDA(cudaMemcpy(w->v.bodies[cls] + (size_t)world * w->v.cap[cls] + n, &tmp, sizeof(PgBody), cudaMemcpyHostToDevice));
+  w->h_counts[world * 3 + cls] = n + 1;
+  rc = push_counts(w, world);
+  if (rc) return rc;
+  rc = refresh_parallel_flag(w);
+  return rc ? rc : n;
+}
+
+int pg_worlds_remove_body(PgWorlds *w, int world, int cls, int index) {
+  if (!valid_world(w, world) || cls < 0 || cls > 2) { pg_set_error("pg_worlds_remove_body: bad argument"); return PG_ERR_ARG; }
+  if (w->mode != PG_MODE_GENERAL) { pg_set_error("handle is in sphere mode"); return PG_ERR_ARG; }
+  int n = w->h_counts[world * 3 + cls];
+  if (index < 0 || index >= n) { pg_set_error("pg_worlds_remove_body: index %d out of %d", index, n); return PG_ERR_ARG; }
+  PG_CUDA(cudaSetDevice(w->device));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  PgBody *base = w->v.bodies[cls] + (size_t)world * w->v.cap[cls];
+  if (index != n - 1) PG_CUDA(cudaMemcpy(base + index, base + (n - 1), sizeof(PgBody), cudaMemcpyDeviceToDevice));
+  w->h_counts[world * 3 + cls] = n - 1;
+  return push_counts(w, world);
+}
+
+int pg_worlds_body_count(const PgWorlds *w, int world, int cls) {
+  if (!valid_world(w, world) || cls < 0 || cls > 2) return PG_ERR_ARG;
+  return w->h_counts[world * 3 + cls];
+}
+
+int pg_worlds_set_spheres(PgWorlds *w, int first, int count, const PgBody *statics, int n_static,
+                          int n_spheres, const float *pos, const float *vel, float radius,
+                          float restitution) {
+  if (!w || first < 0 || count <= 0 || first + count > w->v.n_worlds || n_static < 0 || n_spheres < 0 || !pos || !vel) {
+    pg_set_error("pg_worlds_set_spheres: bad argument");
+    return PG_ERR_ARG;
+  }
+  if (n_static > w->v.cap[0] || n_spheres > w->v.cap[1]) { pg_set_error("pg_worlds_set_spheres: over capacity"); return PG_ERR_CAPACITY; }
+  for (int i = 0; i < n_static; i++)
+    if (statics[i].collider_type != PG_PLANE) { pg_set_error("sphere mode: static bodies must be planes"); return PG_ERR_UNSUPPORTED; }
+  if (w->v.bodies[0] || w->v.bodies[1] || w->v.bodies[2]) { pg_set_error("handle already holds general bodies"); return PG_ERR_ARG; }
+  PG_CUDA(cudaSetDevice(w->device));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  const size_t nd_all = (size_t)w->v.n_worlds * w->v.cap[1];
+  if (!w->v.pos_rest) {
+    PG_CUDA(cudaMalloc(&w->v.pos_rest, sizeof(float4) * nd_all));
+    PG_CUDA(cudaMalloc(&w->v.vel_rad, sizeof(float4) * nd_all));
+    PG_CUDA(cudaMalloc(&w->v.planes, sizeof(float4) * (size_t)w->v.n_worlds * w->v.cap[0]));
+    PG_CUDA(cudaMemset(w->v.pos_rest, 0, sizeof(float4) * nd_all));
+    PG_CUDA(cudaMemset(w->v.vel_rad, 0, sizeof(float4) * nd_all));
+  }
+  w->mode = PG_MODE_SPHERES;
+  w->v.restitution = restitution;
+  std::vector<float4> hp((size_t)count * w->v.cap[1]), hv((size_t)count * w->v.cap[1]), pl((size_t)count * w->v.cap[0]);
+  for (int wd = 0; wd < count; wd++) {
+    for (int i = 0; i < n_spheres; i++) {
+      const float *p = pos + ((size_t)wd * n_spheres + i) * 3, *q = vel + ((size_t)wd * n_spheres + i) * 3;
+      hp[(size_t)wd * w->v.cap[1] + i] = make_float4(p[0], p[1], p[2], 0.0f);
+      hv[(size_t)wd * w->v.cap[1] + i] = make_float4(q[0], q[1], q[2], radius * 1.0f);   // radius * scale[0], scale = 1
+    }
+    for (int i = 0; i < n_static; i++)
+      pl[(size_t)wd * w->v.cap[0] + i] = make_float4(statics[i].shape[0], statics[i].shape[1], statics[i].shape[2], statics[i].shape[3]);
+    w->h_counts[(first + wd) * 3 + 0] = n_static;
+    w->h_counts[(first + wd) * 3 + 1] = n_spheres;
+    w->h_counts[(first + wd) * 3 + 2] = 0;
+  }
+  PG_CUDA(cudaMemcpy(w->v.pos_rest + (size_t)first * w->v.cap[1], hp.data(), sizeof(float4) * hp.size(), cudaMemcpyHostToDevice));
+  PG_CUDA(cudaMemcpy(w->v.vel_rad + (size_t)first * w->v.cap[1], hv.data(), sizeof(float4) * hv.size(), cudaMemcpyHostToDevice));
+  PG_CUDA(cudaMemcpy(w->v.planes + (size_t)first * w->v.cap[0], pl.data(), sizeof(float4) * pl.size(), cudaMemcpyHostToDevice));
+  PG_CUDA(cudaMemcpy(w->v.counts + first * 3, w->h_counts + first * 3, sizeof(int) * 3 * (size_t)count, cudaMemcpyHostToDevice));
+  return PG_OK;
+}
+
+int pg_worlds_get_bodies(PgWorlds *w, int world, int cls, PgBody *out, int cap) {
+  if (!valid_world(w, world) || cls < 0 || cls > 2 || !out) { pg_set_error("pg_worlds_get_bodies: bad argument"); return PG_ERR_ARG; }
+  int n = w->h_counts[world * 3 + cls];
+  if (n > cap) { pg_set_error("pg_worlds_get_bodies: need room for %d records", n); return PG_ERR_CAPACITY; }
+  PG_CUDA(cudaSetDevice(w->device));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  if (n == 0) return 0;
+  if (w->mode == PG_MODE_GENERAL) {
+    PG_CUDA(cudaMemcpy(out, w->v.bodies[cls] + (size_t)world * w->v.cap[cls], sizeof(PgBody) * (size_t)n, cudaMemcpyDeviceToHost));
+    return n;
+  }
+  // sphere mode: synthesise records from the SoA state
+  memset(out, 0, sizeof(PgBody) * (size_t)n);
+  if (cls == PG_CLASS_STATIC) {
+    std::vector<float4> pl(n);
+    PG_CUDA(cudaMemcpy(pl.data(), w->v.planes + (size_t)world * w->v.cap[0], sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+      out[i].collider_type = PG_PLANE; out[i].entity_type = PG_ENT_WORLD;
+      out[i].scale[0] = out[i].scale[1] = out[i].scale[2] = 1.0f;
+      out[i].shape[0] = pl[i].x; out[i].shape[1] = pl[i].y; out[i].shape[2] = pl[i].z; out[i].shape[3] = pl[i].w;
+    }
+  } else if (cls == PG_CLASS_DYNAMIC) {
+    std::vector<float4> hp(n), hv(n);
+    PG_CUDA(cudaMemcpy(hp.data(), w->v.pos_rest + (size_t)world * w->v.cap[1], sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    PG_CUDA(cudaMemcpy(hv.data(), w->v.vel_rad + (size_t)world * w->v.cap[1], sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; i++) {
+      out[i].collider_type = PG_SPHERE; out[i].entity_type = PG_ENT_WORLD; out[i].dynamic = 1;
+      out[i].scale[0] = out[i].scale[1] = out[i].scale[2] = 1.0f;
+      out[i].restitution = w->v.restitution;
+      out[i].position[0] = hp[i].x; out[i].position[1] = hp[i].y; out[i].position[2] = hp[i].z;
+      out[i].velocity[0] = hv[i].x; out[i].velocity[1] = hv[i].y; out[i].velocity[2] = hv[i].z;
+      out[i].shape[3] = hv[i].w;
+      out[i].at_rest = hp[i].w != 0.0f;
+    }
+  }
+  pg_body_prepare(out, n);
+  return n;
+}
+
+static int sphere_range_count(PgWorlds *w, int first, int count, int *n_out) {
+  const int n = w->h_counts[first * 3 + 1];
+  for (int wd = 1; wd < count; wd++)
+    if (w->h_counts[(first + wd) * 3 + 1] != n) { pg_set_error("sphere mode state exchange needs the same sphere count in every world of the range"); return PG_ERR_ARG; }
+  *n_out = n;
+  return PG_OK;
+}
+static int ensure_stage(PgWorlds *w, size_t bodies) {
+  if (bodies <= w->stage_bodies) return PG_OK;
+  if (w->d_stage_pos) { cudaFree(w->d_stage_pos); cudaFree(w->d_stage_vel); cudaFree(w->d_stage_rest); }
+  PG_CUDA(cudaMalloc(&w->d_stage_pos, sizeof(float) * 3 * bodies));
+  PG_CUDA(cudaMalloc(&w->d_stage_vel, sizeof(float) * 3 * bodies));
+  PG_CUDA(cudaMalloc(&w->d_stage_rest, bodies));
+  w->stage_bodies = bodies;
+  return PG_OK;
+}
+
+// SoA state exchange.  In sphere mode this is two strided copies; in general mode a gather/scatter
+// through a host staging buffer (game-sized worlds).
+int pg_worlds_upload_state(PgWorlds *w, int first, int count, const float *pos, const float *vel,
+                           const uint8_t *at_rest) {
+  if (!w || first < 0 || count <= 0 || first + count > w->v.n_worlds || !pos || !vel) { pg_set_error("pg_worlds_upload_state: bad argument"); return PG_ERR_ARG; }
+  PG_CUDA(cudaSetDevice(w->device));
+  const int cap = w->v.cap[1];
+  if (w->mode == PG_MODE_SPHERES) {
+    int n = 0;
+    int rc = sphere_range_count(w, first, count, &n);
+    if (rc) return rc;
+    const size_t total = (size_t)count * n;
+    rc = ensure_stage(w, total);
+    if (rc) return rc;
+    // one H2D copy per array (async when the caller's buffers are pinned), then a pack kernel
+    PG_CUDA(cudaMemcpyAsync(w->d_stage_pos, pos, sizeof(float) * 3 * total, cudaMemcpyHostToDevice, w->stream));
+    PG_CUDA(cudaMemcpyAsync(w->d_stage_vel, vel, sizeof(float) * 3 * total, cudaMemcpyHostToDevice, w->stream));
+    if (at_rest) PG_CUDA(cudaMemcpyAsync(w->d_stage_rest, at_rest, total, cudaMemcpyHostToDevice, w->stream));
+    return pg_launch_pack_state(w, first, count, n, w->d_stage_pos, w->d_stage_vel, at_rest ? w->d_stage_rest : nullptr);
+  }
+  std::vector<PgBody> tmp((size_t)count * cap);
+  PG_CUDA(cudaMemcpy(tmp.data(), w->v.bodies[1] + (size_t)first * cap, sizeof(PgBody) * tmp.size(), cudaMemcpyDeviceToHost));
+  size_t k = 0;
+  for (int wd = 0; wd < count; wd++) {
+    const int n = w->h_counts[(first + wd) * 3 + 1];
+    for (int i = 0; i < n; i++, k++) {
+      PgBody &b = tmp[(size_t)wd * cap + i];
+      memcpy(b.position, pos + 3 * k, 12);
+      memcpy(b.velocity, vel + 3 * k, 12);
+      if (at_rest) b.at_rest = at_rest[k] != 0;
+    }
+  }
+  PG_CUDA(cudaMemcpy(w->v.bodies[1] + (size_t)first * cap, tmp.data(), sizeof(PgBody) * tmp.size(), cudaMemcpyHostToDevice));
+  return PG_OK;
+}
+
+int pg_worlds_download_state(PgWorlds *w, int first, int count, float *pos, float *vel, uint8_t *at_rest) {
+  if (!w || first < 0 || count <= 0 || first + count > w->v.n_worlds || !pos || !vel) { pg_set_error("pg_worlds_download_state: bad argument"); return PG_ERR_ARG; }
+  PG_CUDA(cudaSetDevice(w->device));
+  const int cap = w->v.cap[1];
+  size_t k = 0;
+  if (w->mode == PG_MODE_SPHERES) {
+    int n = 0;
+    int rc = sphere_range_count(w, first, count, &n);
+    if (rc) return rc;
+    const size_t total = (size_t)count * n;
+    rc = ensure_stage(w, total);
+    if (rc) return rc;
+    rc = pg_launch_unpack_state(w, first, count, n, w->d_stage_pos, w->d_stage_vel, at_rest ? w->d_stage_rest : nullptr);
+    if (rc) return rc;
+    PG_CUDA(cudaMemcpyAsync(pos, w->d_stage_pos, sizeof(float) * 3 * total, cudaMemcpyDeviceToHost, w->stream));
+    PG_CUDA(cudaMemcpyAsync(vel, w->d_stage_vel, sizeof(float) * 3 * total, cudaMemcpyDeviceToHost, w->stream));
+    if (at_rest) PG_CUDA(cudaMemcpyAsync(at_rest, w->d_stage_rest, total, cudaMemcpyDeviceToHost, w->stream));
+    PG_CUDA(cudaStreamSynchronize(w->stream));
+    return PG_OK;
+  }
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  std::vector<PgBody> tmp((size_t)count * cap);
+  PG_CUDA(cudaMemcpy(tmp.data(), w->v.bodies[1] + (size_t)first * cap, sizeof(PgBody) * tmp.size(), cudaMemcpyDeviceToHost));
+  for (int wd = 0; wd < count; wd++) {
+    const int n = w->h_counts[(first + wd) * 3 + 1];
+    for (int i = 0; i < n; i++, k++) {
+      const PgBody &b = tmp[(size_t)wd * cap + i];
+      memcpy(pos + 3 * k, b.position, 12);
+      memcpy(vel + 3 * k, b.velocity, 12);
+      if (at_rest) at_rest[k] = b.at_rest != 0;
+    }
+  }
+  return PG_OK;
+}
+
+int pg_worlds_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes) {
+  if (!w || n_steps < 0) { pg_set_error("pg_worlds_step: bad argument"); return PG_ERR_ARG; }
+  PG_CUDA(cudaSetDevice(w->device));
+  PG_CUDA(cudaMemsetAsync(w->v.n_events, 0, sizeof(int) * (size_t)w->v.n_worlds, w->stream));
+  PG_CUDA(cudaEventRecord(w->ev0, w->stream));
+  int rc = PG_OK;
+  if (n_steps > 0) {
+    if (w->mode == PG_MODE_SPHERES) rc = pg_launch_sphere_step(w, dt, n_steps);
+    else {
+      rc = ensure_records(w);
+      if (!rc) rc = pg_launch_general_step(w, dt, n_steps, refresh_nodes);
+    }
+  }
+  PG_CUDA(cudaEventRecord(w->ev1, w->stream));
+  w->last_steps = n_steps;
+  return rc;
+}
+
+int pg_worlds_sync(PgWorlds *w) {
+  if (!w) return PG_ERR_ARG;
+  PG_CUDA(cudaSetDevice(w->device));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  return PG_OK;
+}
+
+static inline long long event_key_row(const PgEvent &e) {
+  const int pass = e.pad_ >> 8;
+  const bool swapped = e.pad_ & 1;
+  // the ROW body of the pass: player in passes 1-2, dynamic in 3-4 (world.c:180,277,369,473)
+  int row, col;
+  if (pass == 1 || pass == 2) { row = e.a_class == PG_CLASS_PLAYER ? e.a_index : e.b_index; col = e.a_class == PG_CLASS_PLAYER ? e.b_index : e.a_index; }
+  else if (pass == 3) { row = e.a_class == PG_CLASS_DYNAMIC ? e.a_index : e.b_index; col = e.a_class == PG_CLASS_DYNAMIC ? e.b_index : e.a_index; }
+  else { row = swapped ? e.b_index : e.a_index; col = swapped ? e.a_index : e.b_index; }
+  return ((long long)row << 32) | (unsigned)col;
+}
+
+long long pg_worlds_events(PgWorlds *w, PgEvent *out, long long cap, int *overflowed) {
+  if (!w) { pg_set_error("pg_worlds_events: bad handle"); return PG_ERR_ARG; }
+  if (cudaSetDevice(w->device) != cudaSuccess || cudaStreamSynchronize(w->stream) != cudaSuccess) { pg_set_error("pg_worlds_events: cuda failure"); return PG_ERR_CUDA; }
+  std::vector<int> cnt(w->v.n_worlds);
+  if (cudaMemcpy(cnt.data(), w->v.n_events, sizeof(int) * cnt.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { pg_set_error("pg_worlds_events: copy failed"); return PG_ERR_CUDA; }
+  long long total = 0;
+  int over = 0;
+  std::vector<PgEvent> buf;
+  for (int wd = 0; wd < w->v.n_worlds; wd++) {
+    int n = cnt[wd];
+    if (n > w->v.max_events) { over = 1; n = w->v.max_events; }
+    if (n > 0 && out) {
+      buf.resize(n);
+      if (cudaMemcpy(buf.data(), w->v.events + (size_t)wd * w->v.max_events, sizeof(PgEvent) * n, cudaMemcpyDeviceToHost) != cudaSuccess) { pg_set_error("pg_worlds_events: copy failed"); return PG_ERR_CUDA; }
+      // restore solve order: step, pass, row, column (device slots are claimed atomically)
+      std::stable_sort(buf.begin(), buf.end(), [](const PgEvent &a, const PgEvent &b) {
+        if (a.step != b.step) return a.step < b.step;
+        const int pa = a.pad_ >> 8, pb = b.pad_ >> 8;
+        if (pa != pb) return pa < pb;
+        return event_key_row(a) < event_key_row(b);
+      });
+      for (int i = 0; i < n; i++) {
+        if (total + i < cap) { out[total + i] = buf[i]; out[total + i].pad_ = buf[i].pad_ >> 8; }
+      }
+    }
+    total += n;
+  }
+  if (overflowed) *overflowed = over;
+  return total;
+}
+
+int pg_worlds_stats(PgWorlds *w, PgStats *host_out, void *dev_out8) {
+  if (!w) return PG_ERR_ARG;
+  PG_CUDA(cudaSetDevice(w->device));
+  if (w->mode == PG_MODE_GENERAL) { int rc = ensure_records(w); if (rc) return rc; }
+  int rc = pg_launch_worlds_stats(w, dev_out8);
+  if (rc) return rc;
+  if (host_out) {
+    double h[8];
+    PG_CUDA(cudaMemcpyAsync(h, w->d_stats, sizeof(h), cudaMemcpyDeviceToHost, w->stream));
+    PG_CUDA(cudaStreamSynchronize(w->stream));
+    host_out->bodies = h[0]; host_out->kinetic = h[1];
+    host_out->momentum[0] = h[2]; host_out->momentum[1] = h[3]; host_out->momentum[2] = h[4];
+    host_out->contacts = h[5]; host_out->at_rest = h[6]; host_out->nonfinite = h[7];
+  }
+  return PG_OK;
+}
+
+long long pg_worlds_launches(const PgWorlds *w) { return w ? w->launches : 0; }
+
+float pg_worlds_last_step_ms(PgWorlds *w) {
+  if (!w) return -1.0f;
+  float ms = -1.0f;
+  if (cudaSetDevice(w->device) != cudaSuccess) return -1.0f;
+  if (cudaEventSynchronize(w->ev1) != cudaSuccess) return -1.0f;
+  if (cudaEventElapsedTime(&ms, w->ev0, w->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+void *pg_worlds_stream(PgWorlds *w) { return w ? (void *)w->stream : nullptr; }
+
+}  // extern "C"

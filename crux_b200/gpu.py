@@ -1,0 +1,284 @@
+"""ctypes binding of libphysics_gpu.so (the C-ABI declared in include/physics_gpu.h).
+
+Nothing here computes physics: every method forwards to the CUDA library.  Loading fails loudly if
+the library has not been built (python -m crux_b200.build) -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .scenes import BODY_DTYPE, CLASS_DYNAMIC, CLASS_PLAYER, CLASS_STATIC
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GPU_SO = os.path.join(HERE, "lib", "libphysics_gpu.so")
+
+PG_EVENT_DTYPE = np.dtype([("world", "<i4"), ("step", "<i4"), ("event_type", "<i4"), ("a_class", "<i4"),
+                           ("a_index", "<i4"), ("b_class", "<i4"), ("b_index", "<i4"), ("pass_", "<i4")])
+PG_STATS_FIELDS = ("bodies", "kinetic", "px", "py", "pz", "contacts", "at_rest", "nonfinite")
+
+# every symbol include/physics_gpu.h declares: (name, restype, argtypes)
+_vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+API = [
+    ("pg_last_error", C.c_char_p, []),
+    ("pg_device_count", _i, []),
+    ("pg_body_prepare", None, [_vp, _i]),
+    ("pg_node_transform", None, [_vp, _vp, _vp, _vp, _vp]),
+    ("pg_host_alloc", _vp, [C.c_size_t]),
+    ("pg_host_free", None, [_vp]),
+    ("pg_worlds_create", _vp, [_i, _i, _i, _i, _i, _i]),
+    ("pg_worlds_destroy", None, [_vp]),
+    ("pg_worlds_count", _i, [_vp]),
+    ("pg_worlds_set_bodies", _i, [_vp, _i, _i, _vp, _i]),
+    ("pg_worlds_add_body", _i, [_vp, _i, _vp, _i]),
+    ("pg_worlds_remove_body", _i, [_vp, _i, _i, _i]),
+    ("pg_worlds_body_count", _i, [_vp, _i, _i]),
+    ("pg_worlds_get_bodies", _i, [_vp, _i, _i, _vp, _i]),
+    ("pg_worlds_set_spheres", _i, [_vp, _i, _i, _vp, _i, _i, _vp, _vp, _f, _f]),
+    ("pg_worlds_upload_state", _i, [_vp, _i, _i, _vp, _vp, _vp]),
+    ("pg_worlds_download_state", _i, [_vp, _i, _i, _vp, _vp, _vp]),
+    ("pg_worlds_step", _i, [_vp, _f, _i, _i]),
+    ("pg_worlds_sync", _i, [_vp]),
+    ("pg_worlds_events", _ll, [_vp, _vp, _ll, _vp]),
+    ("pg_worlds_stats", _i, [_vp, _vp, _vp]),
+    ("pg_worlds_launches", _ll, [_vp]),
+    ("pg_worlds_last_step_ms", _f, [_vp]),
+    ("pg_worlds_stream", _vp, [_vp]),
+    ("pg_large_create", _vp, [_i, _i, _i]),
+    ("pg_large_destroy", None, [_vp]),
+    ("pg_large_set", _i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _f, _f]),
+    ("pg_large_upload_state", _i, [_vp, _vp, _vp, _vp]),
+    ("pg_large_download_state", _i, [_vp, _vp, _vp, _vp]),
+    ("pg_large_step", _i, [_vp, _f, _i]),
+    ("pg_large_sync", _i, [_vp]),
+    ("pg_large_pairs", _ll, [_vp, _f, _vp, _ll]),
+    ("pg_large_events", _ll, [_vp, _vp, _ll, _vp]),
+    ("pg_large_stats", _i, [_vp, _vp, _vp]),
+    ("pg_large_launches", _ll, [_vp]),
+    ("pg_large_last_step_ms", _f, [_vp]),
+    ("pg_large_kernel_count", _i, []),
+    ("pg_large_kernel_name", C.c_char_p, [_i]),
+    ("pg_large_kernel_ms", _f, [_vp, _i]),
+    ("pg_large_exactness", _i, [_vp, _vp, _vp, _vp, _vp]),
+    ("pg_pair_max_move", _i, [_vp, _i, _f, _f, _vp]),
+    ("pg_pair_min_dist", _i, [_vp, _vp, _i, _vp, _vp]),
+    ("pg_pair_interval_collision", _i, [_vp, _vp, _i, _f, _f, _vp, _vp]),
+    ("pg_pair_narrow_phase", _i, [_vp, _vp, _i, _f, _vp, _vp]),
+    ("pg_pair_resolve", _i, [_vp, _vp, _i, _vp, _f]),
+    ("pg_pair_visit", _i, [_vp, _vp, _i, _f, _vp]),
+]
+
+
+class PgError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libphysics_gpu.so and bind every declared symbol (raises if the build is missing)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(GPU_SO):
+            raise PgError(f"{GPU_SO} not built: run `python -m crux_b200.build` (needs nvcc). "
+                          "There is no CPU fallback.")
+        dll = C.CDLL(GPU_SO)
+        for name, restype, argtypes in API:
+            fn = getattr(dll, name)          # AttributeError here = header/library mismatch
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = dll
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _check(rc, what: str):
+    if rc is None or (isinstance(rc, int) and rc < 0):
+        msg = lib().pg_last_error()
+        raise PgError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+    return rc
+
+
+def prepare(bodies: np.ndarray) -> np.ndarray:
+    """Fill the two host-computed Euler matrices of BODY_DTYPE records (in place) and return them."""
+    bodies = np.ascontiguousarray(bodies, dtype=BODY_DTYPE)
+    lib().pg_body_prepare(_ptr(bodies), len(bodies))
+    return bodies
+
+
+def node_transform(pos, rot_deg, scale, parent=None) -> np.ndarray:
+    out = np.zeros(16, np.float32)
+    p = np.ascontiguousarray(pos, np.float32); r = np.ascontiguousarray(rot_deg, np.float32)
+    s = np.ascontiguousarray(scale, np.float32)
+    par = None if parent is None else np.ascontiguousarray(parent, np.float32)
+    lib().pg_node_transform(_ptr(p), _ptr(r), _ptr(s), _ptr(par), _ptr(out))
+    return out
+
+
+class PinnedArray:
+    """A numpy view over page-locked host memory from pg_host_alloc."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib().pg_host_alloc(max(self.nbytes, 1))
+        if not self.ptr:
+            raise PgError("pg_host_alloc failed: " + lib().pg_last_error().decode())
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().pg_host_free(self.ptr)
+            self.ptr = None
+
+
+class GpuWorlds:
+    """A batch of physics worlds resident on one GPU (PgWorlds handle)."""
+
+    def __init__(self, n_worlds: int, max_static: int, max_dynamic: int, max_player: int = 0,
+                 max_events_per_world: int = 0, device: int = 0):
+        self.L = lib()
+        self.n_worlds = n_worlds
+        self.max_dynamic = max_dynamic
+        self.h = self.L.pg_worlds_create(n_worlds, max_static, max_dynamic, max_player,
+                                         max_events_per_world, device)
+        if not self.h:
+            raise PgError("pg_worlds_create failed: " + self.L.pg_last_error().decode())
+
+    # -- general records
+    def set_bodies(self, world: int, cls: int, bodies: np.ndarray):
+        b = prepare(bodies)
+        _check(self.L.pg_worlds_set_bodies(self.h, world, cls, _ptr(b), len(b)), "pg_worlds_set_bodies")
+
+    def add_body(self, world: int, body: np.ndarray, as_player: bool = False) -> int:
+        b = prepare(np.atleast_1d(body))
+        return _check(self.L.pg_worlds_add_body(self.h, world, _ptr(b), int(as_player)), "pg_worlds_add_body")
+
+    def remove_body(self, world: int, cls: int, index: int):
+        _check(self.L.pg_worlds_remove_body(self.h, world, cls, index), "pg_worlds_remove_body")
+
+    def body_count(self, world: int, cls: int) -> int:
+        return _check(self.L.pg_worlds_body_count(self.h, world, cls), "pg_worlds_body_count")
+
+    def get_bodies(self, world: int, cls: int) -> np.ndarray:
+        n = self.body_count(world, cls)
+        out = np.zeros(max(n, 1), dtype=BODY_DTYPE)
+        got = _check(self.L.pg_worlds_get_bodies(self.h, world, cls, _ptr(out), len(out)), "pg_worlds_get_bodies")
+        return out[:got]
+
+    # -- sphere batches
+    def set_spheres(self, first: int, statics: np.ndarray, pos: np.ndarray, vel: np.ndarray,
+                    radius: float = 0.15, restitution: float = 1.0):
+        pos = np.ascontiguousarray(pos, np.float32); vel = np.ascontiguousarray(vel, np.float32)
+        count, n = pos.shape[0], pos.shape[1]
+        st = prepare(statics)
+        _check(self.L.pg_worlds_set_spheres(self.h, first, count, _ptr(st), len(st), n, _ptr(pos), _ptr(vel),
+                                            np.float32(radius), np.float32(restitution)), "pg_worlds_set_spheres")
+
+    def upload_state(self, first: int, count: int, pos: np.ndarray, vel: np.ndarray, at_rest=None):
+        _check(self.L.pg_worlds_upload_state(self.h, first, count, _ptr(pos), _ptr(vel), _ptr(at_rest)),
+               "pg_worlds_upload_state")
+
+    def download_state(self, first: int, count: int, pos: np.ndarray, vel: np.ndarray, at_rest=None):
+        _check(self.L.pg_worlds_download_state(self.h, first, count, _ptr(pos), _ptr(vel), _ptr(at_rest)),
+               "pg_worlds_download_state")
+
+    # -- stepping
+    def step(self, dt: float, n_steps: int = 1, refresh_nodes: bool = True):
+        _check(self.L.pg_worlds_step(self.h, np.float32(dt), n_steps, int(refresh_nodes)), "pg_worlds_step")
+
+    def sync(self):
+        _check(self.L.pg_worlds_sync(self.h), "pg_worlds_sync")
+
+    def events(self) -> np.ndarray:
+        over = C.c_int(0)
+        n = _check(self.L.pg_worlds_events(self.h, None, 0, C.byref(over)), "pg_worlds_events")
+        out = np.zeros(max(int(n), 1), dtype=PG_EVENT_DTYPE)
+        n = _check(self.L.pg_worlds_events(self.h, _ptr(out), len(out), C.byref(over)), "pg_worlds_events")
+        self.events_overflowed = bool(over.value)
+        return out[:int(n)]
+
+    def stats(self, dev_out_ptr: int | None = None, want_host: bool = True) -> dict | None:
+        h = np.zeros(8, np.float64) if want_host else None
+        _check(self.L.pg_worlds_stats(self.h, _ptr(h), C.c_void_p(dev_out_ptr) if dev_out_ptr else None),
+               "pg_worlds_stats")
+        return dict(zip(PG_STATS_FIELDS, h.tolist())) if want_host else None
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.pg_worlds_launches(self.h))
+
+    def last_step_ms(self) -> float:
+        return float(self.L.pg_worlds_last_step_ms(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pg_worlds_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# -- per-pair entry points --------------------------------------------------------------------
+
+def _pair_arrays(a, b=None):
+    a = prepare(np.atleast_1d(a).copy())
+    b = None if b is None else prepare(np.atleast_1d(b).copy())
+    return a, b
+
+
+def pair_max_move(a, t0, t1):
+    a, _ = _pair_arrays(a)
+    out = np.zeros(len(a), np.float32)
+    _check(lib().pg_pair_max_move(_ptr(a), len(a), np.float32(t0), np.float32(t1), _ptr(out)), "pg_pair_max_move")
+    return out
+
+
+def pair_min_dist(a, b, t):
+    a, b = _pair_arrays(a, b)
+    t = np.ascontiguousarray(np.broadcast_to(np.asarray(t, np.float32), (len(a),)))
+    out = np.zeros(len(a), np.float32)
+    _check(lib().pg_pair_min_dist(_ptr(a), _ptr(b), len(a), _ptr(t), _ptr(out)), "pg_pair_min_dist")
+    return out
+
+
+def pair_interval_collision(a, b, t0, t1):
+    a, b = _pair_arrays(a, b)
+    hit = np.zeros(len(a), np.int32); ht = np.zeros(len(a), np.float32)
+    _check(lib().pg_pair_interval_collision(_ptr(a), _ptr(b), len(a), np.float32(t0), np.float32(t1), _ptr(hit), _ptr(ht)),
+           "pg_pair_interval_collision")
+    return hit, ht
+
+
+def pair_narrow_phase(a, b, dt):
+    a, b = _pair_arrays(a, b)
+    col = np.zeros(len(a), np.int32); ht = np.zeros(len(a), np.float32)
+    _check(lib().pg_pair_narrow_phase(_ptr(a), _ptr(b), len(a), np.float32(dt), _ptr(col), _ptr(ht)), "pg_pair_narrow_phase")
+    return col, ht
+
+
+def pair_resolve(a, b, hit_time, dt):
+    a, b = _pair_arrays(a, b)
+    ht = np.ascontiguousarray(np.broadcast_to(np.asarray(hit_time, np.float32), (len(a),)))
+    _check(lib().pg_pair_resolve(_ptr(a), _ptr(b), len(a), _ptr(ht), np.float32(dt)), "pg_pair_resolve")
+    return a, b
+
+
+def pair_visit(a, b, dt):
+    a, b = _pair_arrays(a, b)
+    ev = np.zeros(len(a), np.int32)
+    _check(lib().pg_pair_visit(_ptr(a), _ptr(b), len(a), np.float32(dt), _ptr(ev)), "pg_pair_visit")
+    return ev, a, b

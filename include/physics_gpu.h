@@ -1,0 +1,213 @@
+/*
+ * physics_gpu.h -- thin C-ABI between Crux's C host code and the B200 physics step.
+ *
+ * This is the boundary BASELINE.json's north_star names ("Host code stays in C and calls CUDA
+ * through a thin C-ABI layer (physics_gpu.h/.cu)").  Plain C types only: pointers, sizes, POD
+ * records.  No CUDA or torch type crosses it; device buffers an outside caller owns are passed as
+ * `void *` device addresses.  The library is libphysics_gpu.so (crux_b200/csrc/physics_gpu.cu and
+ * the kernel translation units next to it), sm_100a only, no CPU fallback: every entry point that
+ * needs the GPU returns PG_ERR_CUDA when there is none.
+ *
+ * What each group replaces in the reference (paths relative to /root/reference):
+ *   pg_worlds_*        struct PhysicsWorld + physics_world_create / physics_add_body /
+ *                      physics_add_player / physics_remove_body     include/physics/world.h:28-43,
+ *                                                                   src/physics/world.c:23-172
+ *   pg_worlds_step     physics_step                                 world.h:44, world.c:174-555
+ *                      (+ the per-frame scene_node_update refresh   src/scene.c:1051-1079)
+ *   pg_worlds_events   the game_event_queue_enqueue calls made from the step
+ *                                                                   world.c:232-259, 329-352, 441-457, 524-540
+ *   pg_pair_*          interval_collision, minimum_object_distance_at_time,
+ *                      maximum_object_movement_over_time and the three function tables
+ *                                                                   world.h:47-50, distance.h:13-28,
+ *                                                                   narrow_phase.h:16-33, resolution.h:8-20
+ *   pg_large_*         the same physics_step for ONE world too large for a thread block
+ *                      (uniform-grid broadphase; new acceleration structure)
+ *
+ * The reference-named C API (physics_world_create, physics_step, ...) lives one layer up, in
+ * crux_b200/csrc/host/crux_world.c, and is written against this header.
+ */
+#ifndef PHYSICS_GPU_H
+#define PHYSICS_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums mirror include/physics/collider.h:18-24 and include/types.h:3-9 ---- */
+enum { PG_AABB = 0, PG_SPHERE = 1, PG_CAPSULE = 2, PG_PLANE = 3 };
+enum { PG_ENT_GROUPING = 0, PG_ENT_WORLD = 1, PG_ENT_ITEM = 2, PG_ENT_PLAYER = 3 };
+enum { PG_CLASS_STATIC = 0, PG_CLASS_DYNAMIC = 1, PG_CLASS_PLAYER = 2 };
+
+enum {
+  PG_OK = 0,
+  PG_ERR_CUDA = -1,       /* a CUDA runtime call failed (pg_last_error() has the text) */
+  PG_ERR_ARG = -2,        /* bad handle / index / count */
+  PG_ERR_CAPACITY = -3,   /* more bodies than the handle was created for */
+  PG_ERR_UNSUPPORTED = -4 /* collider pair the reference leaves undefined (sphere-capsule,
+                             capsule-capsule: distance.c:301-303,323-325; narrow_phase.c:522-524,590-592) */
+};
+
+/*
+ * Flat, pointer-free body record: `struct PhysicsBody` (world.h:8-26) field for field, plus the
+ * matrices the physics path reads through body->scene_node (distance.c:26-49, 345-347) and two
+ * rotation matrices the host computes with libm so that the device never evaluates sinf/cosf:
+ *   euler_raw  = upper 3x3 of glm_euler_xyz(rotation)            -- rotation (DEGREES) passed as
+ *                radians, exactly as distance.c:255,373 / narrow_phase.c:352,629 / resolution.c:431,667 do
+ *   euler_node = upper 3x3 of glm_euler_xyz(glm_rad(rotation))   -- scene.c:1062-1068
+ * Both are column-major (cglm mat3): m[col*3 + row].  pg_body_prepare() fills them.
+ */
+typedef struct PgBody {
+  float position[3];
+  float rotation[3];      /* degrees */
+  float scale[3];
+  float velocity[3];
+  float restitution;
+  float shape[7];         /* AABB: center,extents | sphere: center,radius | capsule: A,B,radius | plane: normal,distance */
+  int32_t collider_type;
+  int32_t entity_type;
+  int32_t dynamic;
+  int32_t at_rest;
+  int32_t has_node;       /* scene_node != NULL */
+  int32_t has_parent;     /* scene_node->parent_node != NULL */
+  float node_xform[16];   /* scene_node->world_transform, column-major */
+  float parent_xform[16]; /* scene_node->parent_node->world_transform */
+  float euler_raw[9];
+  float euler_node[9];
+} PgBody;                 /* 304 bytes */
+
+/* One contact = one game_event_queue_enqueue call of the reference, in solve order. */
+typedef struct PgEvent {
+  int32_t world;
+  int32_t step;           /* 0-based within the pg_worlds_step call that produced it */
+  int32_t event_type;     /* 0 = EVENT_COLLISION, 1 = EVENT_PLAYER_ITEM_PICKUP (event.h:8-11) */
+  int32_t a_class, a_index;   /* body_A after the type-order swap (world.c:482-488) */
+  int32_t b_class, b_index;
+  int32_t pad_;           /* pass of physics_step that produced it (1..4, world.c:180,277,369,473) */
+} PgEvent;                /* 32 bytes */
+
+/* Per-step aggregate statistics over all dynamic bodies a handle owns (the vector a multi-GPU
+ * run all-reduces; SURVEY.md section 5 "Metrics").  Plain doubles so that SUM is the reduction. */
+typedef struct PgStats {
+  double bodies;          /* number of dynamic bodies */
+  double kinetic;         /* sum 0.5 |v|^2 (unit mass) */
+  double momentum[3];     /* sum v */
+  double contacts;        /* events emitted by the last pg_*_step call */
+  double at_rest;         /* bodies with at_rest set */
+  double nonfinite;       /* bodies with a NaN/Inf position or velocity component */
+} PgStats;                /* 8 doubles */
+
+const char *pg_last_error(void);
+int  pg_device_count(void);
+/* Fill euler_raw / euler_node of n records from their rotation field (host libm). */
+void pg_body_prepare(PgBody *bodies, int n);
+/* scene_node_update for one node (scene.c:1051-1079): world = parent * T(pos) R(rad(rot)) S(scale). */
+void pg_node_transform(const float *pos3, const float *rot_deg3, const float *scale3,
+                       const float *parent16_or_null, float *world16);
+
+/* Page-locked host memory for the state-exchange calls (plain malloc'd buffers work too, slower). */
+void *pg_host_alloc(size_t bytes);
+void pg_host_free(void *p);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched worlds, reference solve order preserved (one thread block per world).
+ * All worlds of a handle share the same capacities; each keeps its own counts.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct PgWorlds PgWorlds;
+
+PgWorlds *pg_worlds_create(int n_worlds, int max_static, int max_dynamic, int max_player,
+                           int max_events_per_world, int device);
+void pg_worlds_destroy(PgWorlds *w);
+int  pg_worlds_count(const PgWorlds *w);
+
+/* Replace the bodies of one class of one world (n may be 0).  Order = reference array order. */
+int  pg_worlds_set_bodies(PgWorlds *w, int world, int cls, const PgBody *bodies, int n);
+/* physics_add_body / physics_add_player: append one record; returns its index or <0. */
+int  pg_worlds_add_body(PgWorlds *w, int world, const PgBody *body, int as_player);
+/* physics_remove_body: swap-with-last and pop (world.c:147-172). */
+int  pg_worlds_remove_body(PgWorlds *w, int world, int cls, int index);
+int  pg_worlds_body_count(const PgWorlds *w, int world, int cls);
+/* Copy one class of one world back (returns the count, <0 on error). */
+int  pg_worlds_get_bodies(PgWorlds *w, int world, int cls, PgBody *out, int cap);
+
+/* Homogeneous sphere worlds (the RL-style batch): every world [first, first+count) gets the same
+ * static bodies and n_spheres dynamic spheres (local centre 0, scale 1) from SoA host arrays of
+ * shape [count][n_spheres][3] (pos, vel) -- one call, one H2D copy per array. */
+int  pg_worlds_set_spheres(PgWorlds *w, int first, int count, const PgBody *statics, int n_static,
+                           int n_spheres, const float *pos, const float *vel, float radius,
+                           float restitution);
+/* SoA state exchange for the same worlds: pos/vel [count][n_dynamic][3], at_rest [count][n_dynamic]. */
+int  pg_worlds_upload_state(PgWorlds *w, int first, int count, const float *pos, const float *vel,
+                            const uint8_t *at_rest_or_null);
+int  pg_worlds_download_state(PgWorlds *w, int first, int count, float *pos, float *vel,
+                              uint8_t *at_rest_or_null);
+
+/* n_steps x { physics_step(dt) ; if refresh_nodes: scene_node_update of every body's node }.
+ * Asynchronous on the handle's stream; pg_worlds_sync() waits. */
+int  pg_worlds_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes);
+int  pg_worlds_sync(PgWorlds *w);
+/* Events of the last pg_worlds_step call, world-major then solve order.  Returns the total
+ * number produced (may exceed cap; a world that overflowed max_events_per_world is reported
+ * through *overflowed). */
+long long pg_worlds_events(PgWorlds *w, PgEvent *out, long long cap, int *overflowed);
+/* Aggregate statistics.  If dev_out8 != NULL the 8 doubles are ALSO written (by the reducing
+ * kernel, on the handle's stream) to that device address -- the buffer a caller hands to
+ * ncclAllReduce / torch.distributed.all_reduce; host_out may be NULL to stay asynchronous. */
+int  pg_worlds_stats(PgWorlds *w, PgStats *host_out, void *dev_out8);
+/* Number of kernel launches this handle has issued (bench.py's gpu_launches) and the device
+ * time, in ms, of the last pg_worlds_step call measured with CUDA events on the handle's stream. */
+long long pg_worlds_launches(const PgWorlds *w);
+float pg_worlds_last_step_ms(PgWorlds *w);
+void *pg_worlds_stream(PgWorlds *w);   /* cudaStream_t as void* */
+
+/* ------------------------------------------------------------------------------------------
+ * One large world of dynamic spheres + static bodies (uniform-grid broadphase).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct PgLarge PgLarge;
+
+PgLarge *pg_large_create(int max_spheres, int max_static, int device);
+void pg_large_destroy(PgLarge *w);
+int  pg_large_set(PgLarge *w, const PgBody *statics, int n_static, int n_spheres,
+                  const float *pos, const float *vel, const float *radius_or_null, float radius,
+                  float restitution);
+int  pg_large_upload_state(PgLarge *w, const float *pos, const float *vel, const uint8_t *at_rest_or_null);
+int  pg_large_download_state(PgLarge *w, float *pos, float *vel, uint8_t *at_rest_or_null);
+int  pg_large_step(PgLarge *w, float dt, int n_steps);
+int  pg_large_sync(PgLarge *w);
+/* Broadphase pair set on the current (frozen) state: unordered pairs i<j for which
+ * interval_collision(i,j,0,dt) holds, sorted lexicographically.  Returns the count. */
+long long pg_large_pairs(PgLarge *w, float dt, int32_t *out_ij, long long cap);
+/* Contacts (events) of the last step call in solve order; same record as the batched path. */
+long long pg_large_events(PgLarge *w, PgEvent *out, long long cap, int *overflowed);
+int  pg_large_stats(PgLarge *w, PgStats *host_out, void *dev_out8);
+long long pg_large_launches(const PgLarge *w);
+float pg_large_last_step_ms(PgLarge *w);
+/* Per-kernel device time of the last step (ms), in pipeline order; names via pg_large_kernel_name. */
+int  pg_large_kernel_count(void);
+const char *pg_large_kernel_name(int k);
+float pg_large_kernel_ms(PgLarge *w, int k);
+/* Fixed-point statistics of the last step: iterations used, 1 if the step is proven identical to
+ * the sequential reference order, candidate-visit and hit counts. */
+int  pg_large_exactness(PgLarge *w, int *iterations, int *proven_exact, long long *candidates, long long *hits);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-pair entry points: the reference's public predicate/table functions evaluated on the GPU
+ * for n independent pairs (records in host memory; results in host memory).  A[k] must already be
+ * the lower collider type, as the tables require (world.c:482-488).
+ * ------------------------------------------------------------------------------------------ */
+int  pg_pair_max_move(const PgBody *a, int n, float t0, float t1, float *out);
+int  pg_pair_min_dist(const PgBody *a, const PgBody *b, int n, const float *t, float *out);
+int  pg_pair_interval_collision(const PgBody *a, const PgBody *b, int n, float t0, float t1,
+                                int32_t *out_hit, float *out_hit_time);
+int  pg_pair_narrow_phase(const PgBody *a, const PgBody *b, int n, float dt,
+                          int32_t *out_colliding, float *out_hit_time);
+int  pg_pair_resolve(PgBody *a, PgBody *b, int n, const float *hit_time, float dt);
+/* one full visit (order swap, gate, narrowphase, behaviour, resolve); out_event[k] = 1 if an event fires */
+int  pg_pair_visit(PgBody *a, PgBody *b, int n, float dt, int32_t *out_event);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHYSICS_GPU_H */
