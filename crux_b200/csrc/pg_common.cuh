@@ -10,6 +10,8 @@
 #include "../../include/physics_gpu.h"
 
 void pg_set_error(const char *fmt, ...);
+// Exact shortest/longest leaf interval of interval_collision's recursion from (t0, t1) (host).
+void pg_leaf_lengths(float t0, float t1, float *lo, float *hi);
 
 #define PG_CUDA(call)                                                                         \
   do {                                                                                        \
@@ -45,6 +47,7 @@ struct WorldsView {
   float4 *vel_rad;            // [n_worlds * cap[1]]  vx, vy, vz, world radius
   float4 *planes;             // [n_worlds * cap[0]]  nx, ny, nz, d    (statics are planes in sphere mode)
   float restitution;          // uniform in sphere mode
+  float leaf_lo, leaf_hi;     // extreme leaf lengths of the interval walk for (0, clamp(dt)); set per step call
 };
 
 struct PgWorlds {

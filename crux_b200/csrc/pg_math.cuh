@@ -28,7 +28,6 @@ constexpr float kGravity = 9.8f;            // world.c:363,550; resolution.c:28,
 constexpr double kMaxDt = 0.01666;          // world.c:18 (double)
 constexpr float kIntervalEps = 0.000001f;   // world.c:21
 constexpr double kNpEps = 0.0001;           // narrow_phase.c:6 (double)
-constexpr int kMaxIntervalDepth = 40;
 
 struct V3 { float x, y, z; };
 
@@ -221,55 +220,187 @@ __device__ __forceinline__ float ss_d2_at(V3 cA, V3 vA, V3 cB, V3 vB, float t) {
   return dot(d, d);
 }
 
-// interval_collision for two spheres, world.c:557-582 with distance.c:278-299 inlined.
-// cA/cB = centre + position at t=0, nA/nB = |v| (glm_vec3_norm), rs = rA + rB.
-// Depth-first, left child first, like the recursion; an explicit stack keeps the right siblings.
-__device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float nB, float rs,
-                                   float t_begin, float t_end) {
-  float st0[kMaxIntervalDepth], st1[kMaxIntervalDepth];
-  int sp = 0;
+
+// Depth-first walk of interval_collision's recursion tree (world.c:557-582) WITHOUT a stack.
+// A node is (depth, path): bit k of `path` (k = depth-1 .. 0, root side first) says whether the
+// walk went to the right child at that level.  End points of any node are re-derived from the
+// root by the very same sequence of (t0+t1)*0.5f operations the recursion performs, so they are
+// bit-identical to the recursive ones.  `probe(t0, t1)` evaluates a node and answers
+//   kDead  : an end-point test fails, or the subtree provably holds no surviving leaf
+//   kOpen  : both end-point tests pass, descend (a leaf that is kOpen survives)
+//   kSure  : every node of the subtree provably passes, so a surviving leaf exists
+// The walk visits children left first and returns true at the first surviving leaf; since only the
+// boolean is consumed by physics_step (hit_time is never read, world.c:196-198), proofs that skip
+// or short-cut a subtree leave the result unchanged.
+enum { kDead = 0, kOpen = 1, kSure = 2 };
+
+template <typename Probe>
+__device__ __forceinline__ bool interval_walk(float t_begin, float t_end, float *hit, Probe probe) {
+  unsigned long long path = 0;
+  int depth = 0;
   float t0 = t_begin, t1 = t_end;
   for (;;) {
-    float len = t1 - t0;
-    float mm = nA * len + nB * len;
-    bool alive = !ss_dist_exceeds(ss_d2_at(cA, vA, cB, vB, t0), rs, mm) &&
-                 !ss_dist_exceeds(ss_d2_at(cA, vA, cB, vB, t1), rs, mm);
-    if (alive) {
-      if (len < kIntervalEps) return true;
-      float mid = (t0 + t1) * 0.5f;
-      if (sp < kMaxIntervalDepth) { st0[sp] = mid; st1[sp] = t1; sp++; }
-      t1 = mid;
+    const int st = probe(t0, t1);
+    if (st == kSure) { if (hit) *hit = t0; return true; }
+    if (st == kOpen) {
+      if (t1 - t0 < kIntervalEps) { if (hit) *hit = t0; return true; }
+      if (depth >= 62) return false;                 // unreachable for finite end points
+      path <<= 1; depth++;
+      t1 = (t0 + t1) * 0.5f;
       continue;
     }
-    if (sp == 0) return false;
-    sp--; t0 = st0[sp]; t1 = st1[sp];
+    while (depth > 0 && (path & 1ull)) { path >>= 1; depth--; }   // right children are finished
+    if (depth == 0) return false;
+    path |= 1ull;                                    // left child failed: take its right sibling
+    t0 = t_begin; t1 = t_end;
+    for (int k = depth - 1; k >= 0; k--) {
+      const float mid = (t0 + t1) * 0.5f;
+      if ((path >> k) & 1ull) t0 = mid; else t1 = mid;
+    }
   }
 }
 
-// min_dist_at_time_sphere_plane, distance.c:305-321: max(|s| - r, 0), |s|-r in double.
-__device__ __forceinline__ float sp_dist(V3 c, V3 n, float d, float r) {
-  float s = dot(c, n) - d;
-  float dist = (float)(fabs((double)s) - (double)r);   // [f64]
-  return glm_max(dist, 0);
-}
-__device__ inline bool sp_interval(V3 c, V3 v, float nv, V3 n, float d, float r, float t_begin, float t_end) {
-  float st0[kMaxIntervalDepth], st1[kMaxIntervalDepth];
-  int sp = 0;
+// Guided variant for the sphere paths.  Because only the boolean "some leaf survives" is consumed,
+// the ORDER in which children are explored is free: at every node the child that contains t_pref
+// (where the caller expects the bodies to be closest) is explored first, so a real contact is
+// confirmed in O(depth) nodes with no backtracking.  End-point samples are carried down the tree:
+// a child shares one end point with its parent, and eval(t) at the same float t gives the same
+// bits, so each level costs one new sample.  path bit = 1 means "the non-preferred child".
+//   eval(t)                       -> Sample   (the computed quantity at time t)
+//   probe(t0, t1, Sample, Sample) -> kDead / kOpen / kSure
+template <typename Sample, typename Eval, typename Probe>
+__device__ __forceinline__ bool interval_walk_guided(float t_begin, float t_end, float t_pref, Eval eval, Probe probe) {
+  unsigned long long path = 0;
+  int depth = 0;
   float t0 = t_begin, t1 = t_end;
+  Sample Sa = eval(t0), Sb = eval(t1);
   for (;;) {
-    float len = t1 - t0;
-    float mm = nv * len + 0.0f * len;            // the plane's |v| is 0 (world.c:51): 0*len, then the sum
-    bool alive = !(sp_dist(muladds(v, t0, c), n, d, r) > mm) && !(sp_dist(muladds(v, t1, c), n, d, r) > mm);
-    if (alive) {
-      if (len < kIntervalEps) return true;
-      float mid = (t0 + t1) * 0.5f;
-      if (sp < kMaxIntervalDepth) { st0[sp] = mid; st1[sp] = t1; sp++; }
-      t1 = mid;
+    const int st = probe(t0, t1, Sa, Sb);
+    if (st == kSure) return true;
+    if (st == kOpen) {
+      if (t1 - t0 < kIntervalEps) return true;
+      if (depth >= 62) return false;
+      const float mid = (t0 + t1) * 0.5f;
+      const Sample Sm = eval(mid);
+      path <<= 1; depth++;
+      if (t_pref >= mid) { t0 = mid; Sa = Sm; } else { t1 = mid; Sb = Sm; }
       continue;
     }
-    if (sp == 0) return false;
-    sp--; t0 = st0[sp]; t1 = st1[sp];
+    while (depth > 0 && (path & 1ull)) { path >>= 1; depth--; }
+    if (depth == 0) return false;
+    path |= 1ull;
+    t0 = t_begin; t1 = t_end;
+    for (int k = depth - 1; k >= 0; k--) {
+      const float mid = (t0 + t1) * 0.5f;
+      const bool right = (t_pref >= mid) != (((path >> k) & 1ull) != 0ull);
+      if (right) t0 = mid; else t1 = mid;
+    }
+    Sa = eval(t0); Sb = eval(t1);
   }
+}
+
+// Shortest and longest leaf interval (len < 1e-6) the walk can reach from a given root interval.
+// The defaults hold for ANY root: a leaf's parent has len >= 1e-6, a midpoint splits it in halves
+// up to a few ulps of t.  pg_leaf_lengths() (host) tabulates the exact extremes for a given root.
+struct LeafLen { float lo, hi; };
+__host__ __device__ __forceinline__ LeafLen default_leaf_len() { LeafLen l; l.lo = 0.4990e-6f; l.hi = 1.0e-6f; return l; }
+constexpr float kU = 5.9604645e-8f;                  // 2^-24, unit roundoff of binary32
+
+// interval_collision for two spheres, world.c:557-582 with distance.c:278-299 inlined.
+// cA/cB = centre + position at t=0, nA/nB = |v| (glm_vec3_norm), rs = rA + rB.
+// Depth-first, left child first, like the recursion; an explicit stack keeps the right siblings.
+// Enclosures (exactness-preserving).  The walk only needs to know whether SOME leaf survives; a
+// leaf survives iff the COMPUTED distance is <= mm(len) = fl(fl(nA len) + fl(nB len)) at both end
+// points, and mm is monotone in len.  For any float t in a node [a,b] the computed centre distance
+// Dc(t) differs from the real D(t) = |s + u t| (real arithmetic on the float inputs) by at most
+//   E = 1.25 u (|cA|_1 + |cB|_1 + 2 (|vA|_1 + |vB|_1) t_max) + 8 u D     (u = 2^-24)
+// (roundings of v t, c + v t, the difference, the dot product and the square root).  D is convex
+// and |u|-Lipschitz, so on the node  D <= max(D(a), D(b))  and  D >= (D(a)+D(b))/2 - |u| len/2.
+//   lower bound of dist > mm(longest leaf)   -> no leaf below can survive          -> kDead
+//   upper bound of dist <= mm(shortest leaf) -> every node below passes            -> kSure
+// Fast bodies moving almost in parallel (|u| << nA+nB) would otherwise make the recursion visit
+// O(2^depth) nodes; with the enclosures it is O(depth) except inside a ~1e-6-wide band.
+__device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float nB, float rs,
+                                   float t_begin, float t_end, LeafLen leaf = default_leaf_len()) {
+  const V3 u = sub(vA, vB);
+  const float L = sqrtf(__fmaf_rn(u.x, u.x, __fmaf_rn(u.y, u.y, u.z * u.z))) * 1.0001f;
+  const float tmax = fmaxf(fabsf(t_begin), fabsf(t_end));
+  const float c1 = fabsf(cA.x) + fabsf(cA.y) + fabsf(cA.z) + fabsf(cB.x) + fabsf(cB.y) + fabsf(cB.z);
+  const float v1 = fabsf(vA.x) + fabsf(vA.y) + fabsf(vA.z) + fabsf(vB.x) + fabsf(vB.y) + fabsf(vB.z);
+  const float E0 = 1.25f * kU * (c1 + 2.0f * v1 * tmax) + 1.0e-30f;
+  const float mm_hi = (nA * leaf.hi + nB * leaf.hi) * 1.000001f;   // >= mm of any leaf
+  const float mm_lo = (nA * leaf.lo + nB * leaf.lo) * 0.999999f;   // <= mm of any node
+  const bool finite_ok = (nA + nB < 1.0e30f) && (c1 < 1.0e30f) && (rs < 1.0e30f) && (v1 < 1.0e30f);
+  // closest approach of the two linear paths: where a contact, if any, is
+  const V3 s0 = sub(cA, cB);
+  const float uu = __fmaf_rn(u.x, u.x, __fmaf_rn(u.y, u.y, u.z * u.z));
+  const float su = __fmaf_rn(s0.x, u.x, __fmaf_rn(s0.y, u.y, s0.z * u.z));
+  const float t_pref = uu > 0.0f ? fminf(fmaxf(-su / uu, t_begin), t_end) : t_begin;
+  return interval_walk_guided<float>(t_begin, t_end, t_pref,
+    [&](float t) { return ss_d2_at(cA, vA, cB, vB, t); },
+    [&](float t0, float t1, float d2a, float d2b) -> int {
+      const float len = t1 - t0;
+      const float mm = nA * len + nB * len;
+      if (ss_dist_exceeds(d2a, rs, mm) || ss_dist_exceeds(d2b, rs, mm)) return kDead;
+      if (len < kIntervalEps || !finite_ok) return kOpen;       // leaves are decided by the tests above
+      const float Da = sqrtf(d2a), Db = sqrtf(d2b);
+      const float Dmax = fmaxf(Da, Db);
+      const float E = E0 + 8.0f * kU * Dmax;       // |computed - real| at any t of the node
+      // computed end points -> real end points (E) -> real interior (convexity/Lipschitz) -> computed interior (E)
+      const float lower = 0.5f * (Da + Db) * 0.9999999f - 0.5f * L * len - 2.0f * E - rs;   // <= dist anywhere in the node
+      if (lower * 0.999999f > mm_hi) return kDead;
+      const float upper = fmaxf((Dmax + 2.0f * E) * 1.0000001f - rs, 0.0f) * 1.000001f;     // >= dist anywhere in the node
+      if (upper <= mm_lo) return kSure;
+      return kOpen;
+    });
+}
+
+// min_dist_at_time_sphere_plane, distance.c:305-321: max(|s| - r, 0), |s|-r in double.
+__device__ __forceinline__ float sp_signed(V3 c, V3 n, float d) { return dot(c, n) - d; }
+__device__ __forceinline__ float sp_dist_from_s(float s, float r) {
+  // (float)(fabs((double)s) - (double)r): the double difference of two floats is exact unless
+  // their exponents are > 28 apart, so one float subtraction gives the same bits.
+  const float a = fabsf(s);
+  float dist = (a < 1.0e8f * fabsf(r) && fabsf(r) < 1.0e8f * a) || a == 0.0f || r == 0.0f
+                   ? a - r : (float)((double)a - (double)r);   // [f64]
+  return glm_max(dist, 0);
+}
+__device__ __forceinline__ float sp_dist(V3 c, V3 n, float d, float r) { return sp_dist_from_s(sp_signed(c, n, d), r); }
+// Same enclosure idea as ss_interval.  The real signed distance s(t) = n.(c + v t) - d is linear in
+// t, the computed one differs from it by at most
+//   Es = 1.5 u (5 (|c|_1 + |v|_1 t_max) + |d|)          (|n_k| <= 1; rigorous bound has factor 1.0)
+// and is EXACTLY constant in t when every product v_k n_k vanishes (a body at rest that was
+// pushed sideways along an axis-aligned plane: the case that otherwise costs 2^depth nodes every
+// step, for ever, because a resting body is never integrated).
+__device__ inline bool sp_interval(V3 c, V3 v, float nv, V3 n, float d, float r, float t_begin, float t_end,
+                                   LeafLen leaf = default_leaf_len()) {
+  const float tmax = fmaxf(fabsf(t_begin), fabsf(t_end));
+  const float c1 = fabsf(c.x) + fabsf(c.y) + fabsf(c.z), v1 = fabsf(v.x) + fabsf(v.y) + fabsf(v.z);
+  const bool constant_s = (v.x == 0.0f || n.x == 0.0f) && (v.y == 0.0f || n.y == 0.0f) && (v.z == 0.0f || n.z == 0.0f);
+  const bool unit_n = fabsf(n.x) <= 1.0000001f && fabsf(n.y) <= 1.0000001f && fabsf(n.z) <= 1.0000001f;
+  const float Es = constant_s ? 0.0f : 1.5f * kU * (5.0f * (c1 + v1 * tmax) + fabsf(d)) + 1.0e-30f;
+  const float mm_hi = (nv * leaf.hi + 0.0f * leaf.hi) * 1.000001f;
+  const float mm_lo = (nv * leaf.lo + 0.0f * leaf.lo) * 0.999999f;
+  const bool finite_ok = unit_n && (nv < 1.0e30f) && (c1 < 1.0e30f) && (fabsf(d) < 1.0e30f) && (r < 1.0e30f) && (r >= 0.0f);
+  // where the centre is closest to the plane (crossing time of the linear signed distance)
+  const float s_begin = __fmaf_rn(c.x, n.x, __fmaf_rn(c.y, n.y, c.z * n.z)) - d;
+  const float ndv = __fmaf_rn(v.x, n.x, __fmaf_rn(v.y, n.y, v.z * n.z));
+  const float t_pref = ndv != 0.0f ? fminf(fmaxf(-s_begin / ndv, t_begin), t_end) : t_begin;
+  return interval_walk_guided<float>(t_begin, t_end, t_pref,
+    [&](float t) { return sp_signed(muladds(v, t, c), n, d); },
+    [&](float t0, float t1, float sa, float sb) -> int {
+      const float len = t1 - t0;
+      const float mm = nv * len + 0.0f * len;      // the plane's |v| is 0 (world.c:51): 0*len, then the sum
+      if (sp_dist_from_s(sa, r) > mm || sp_dist_from_s(sb, r) > mm) return kDead;
+      if (len < kIntervalEps || !finite_ok) return kOpen;
+      // computed s anywhere in the node lies in [lo, hi]
+      const float lo = fminf(sa, sb) - 2.0f * Es, hi = fmaxf(sa, sb) + 2.0f * Es;
+      const float amin = (lo <= 0.0f && hi >= 0.0f) ? 0.0f : fminf(fabsf(lo), fabsf(hi));
+      const float amax = fmaxf(fabsf(lo), fabsf(hi));
+      if ((amin - r) * 0.999999f > mm_hi) return kDead;
+      if (fmaxf(amax - r, 0.0f) * 1.000001f <= mm_lo) return kSure;
+      return kOpen;
+    });
 }
 
 struct Contact { float t; bool hit; };
@@ -435,22 +566,10 @@ __device__ inline float min_dist(const PgBody &A, const PgBody &B, float t) {
 
 // interval_collision, world.c:557-582 (general collider pair).
 __device__ inline bool interval_hit(const PgBody &A, const PgBody &B, float t_begin, float t_end, float *hit) {
-  float st0[kMaxIntervalDepth], st1[kMaxIntervalDepth];
-  int sp = 0;
-  float t0 = t_begin, t1 = t_end;
-  for (;;) {
-    float mm = max_move(A, t0, t1) + max_move(B, t0, t1);
-    bool alive = !(min_dist(A, B, t0) > mm) && !(min_dist(A, B, t1) > mm);
-    if (alive) {
-      if (t1 - t0 < kIntervalEps) { *hit = t0; return true; }
-      float mid = (t0 + t1) * 0.5f;
-      if (sp < kMaxIntervalDepth) { st0[sp] = mid; st1[sp] = t1; sp++; }
-      t1 = mid;
-      continue;
-    }
-    if (sp == 0) return false;
-    sp--; t0 = st0[sp]; t1 = st1[sp];
-  }
+  return interval_walk(t_begin, t_end, hit, [&](float t0, float t1) {
+    const float mm = max_move(A, t0, t1) + max_move(B, t0, t1);
+    return !(min_dist(A, B, t0) > mm) && !(min_dist(A, B, t1) > mm);
+  });
 }
 
 __device__ inline bool aabb_hits_aabb(const Box &a, const Box &b) {   // aabb.c:100-105

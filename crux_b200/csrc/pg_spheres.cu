@@ -28,7 +28,9 @@ namespace {
 using pgm::V3;
 using pgm::v3;
 
-constexpr int kWarpsPerBlock = 4;
+#ifndef PG_SPH_WARPS
+#define PG_SPH_WARPS 16   // resident warps (worlds) per SM the register budget is sized for
+#endif
 constexpr int kMaxPlanes = 16;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr float kHuge = 1.0e30f;
@@ -46,7 +48,7 @@ __device__ __forceinline__ float reach(float r, float vx, float vy, float vz, fl
 
 // Exact visit of two spheres (world.c:481-541 with the sphere-sphere table entries).
 // All lanes call it with identical arguments.  Returns true if an event fires; A and B updated.
-__device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, float dt) {
+__device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
   V3 cA = v3(0.0f + A.px, 0.0f + A.py, 0.0f + A.pz);     // centre (0,0,0) + position, distance.c:283
   V3 cB = v3(0.0f + B.px, 0.0f + B.py, 0.0f + B.pz);
   V3 vA = v3(A.vx, A.vy, A.vz), vB = v3(B.vx, B.vy, B.vz);
@@ -54,9 +56,9 @@ __device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, float dt) {
   float nA = pgm::norm(vA), nB = pgm::norm(vB);
   {
     // Closest approach of the linear paths over [0,dt].  A leaf interval of interval_collision
-    // (len < 1e-6 s) passes only if the computed distance is <= (nA+nB)*len <= 1e-6 (nA+nB) at
-    // both ends; computed and real distances differ by a few ulps of the coordinates.  So if the
-    // real minimum gap exceeds delta below, no leaf passes and the predicate is false.
+    // (len < 1e-6 s) passes only if the computed distance is <= (nA+nB)*len < 1e-6 (nA+nB) at
+    // both ends; computed and real distances differ by less than 4e-6 x the coordinate magnitude
+    // (see ss_interval).  If the real minimum gap exceeds delta, no leaf passes: predicate false.
     V3 s = pgm::sub(cA, cB), v = pgm::sub(vA, vB);
     float vv = __fmaf_rn(v.x, v.x, __fmaf_rn(v.y, v.y, v.z * v.z));
     float sv = __fmaf_rn(s.x, v.x, __fmaf_rn(s.y, v.y, s.z * v.z));
@@ -65,11 +67,11 @@ __device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, float dt) {
     float dmin2 = __fmaf_rn(qx, qx, __fmaf_rn(qy, qy, qz * qz));
     float cmax = fmaxf(fmaxf(fmaxf(fabsf(cA.x), fabsf(cA.y)), fabsf(cA.z)),
                        fmaxf(fmaxf(fabsf(cB.x), fabsf(cB.y)), fabsf(cB.z)));
-    float delta = 2.0e-5f * (nA + nB) + 8.0e-6f * (cmax + (nA + nB) * dt) + 2.0e-6f;
+    float delta = 1.1e-6f * (nA + nB) + 4.0e-6f * (cmax + (nA + nB) * dt) + 1.0e-6f;
     float lim = (rs + delta) * 1.00001f;
     if (dmin2 > lim * lim && dmin2 < 3.0e38f) return false;
   }
-  if (!pgm::ss_interval(cA, vA, nA, cB, vB, nB, rs, 0.0f, dt)) return false;
+  if (!pgm::ss_interval(cA, vA, nA, cB, vB, nB, rs, 0.0f, dt, leaf)) return false;
   pgm::Contact c = pgm::ss_narrow(cA, vA, cB, vB, rs);
   if (!(c.hit && c.t >= 0)) return false;
   V3 pA = v3(A.px, A.py, A.pz), pB = v3(B.px, B.py, B.pz);
@@ -80,12 +82,12 @@ __device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, float dt) {
 }
 
 // Exact visit sphere x plane (per lane, divergent).  Returns true if an event fires.
-__device__ __noinline__ bool sphere_plane_exact(Sphere &A, float4 pl, float restitution, float dt) {
+__device__ __noinline__ bool sphere_plane_exact(Sphere &A, float4 pl, float restitution, float dt, pgm::LeafLen leaf) {
   V3 c = v3(0.0f + A.px, 0.0f + A.py, 0.0f + A.pz);
   V3 v = v3(A.vx, A.vy, A.vz);
   V3 n = v3(pl.x, pl.y, pl.z);
   float nv = pgm::norm(v);
-  if (!pgm::sp_interval(c, v, nv, n, pl.w, A.r, 0.0f, dt)) return false;
+  if (!pgm::sp_interval(c, v, nv, n, pl.w, A.r, 0.0f, dt, leaf)) return false;
   pgm::Contact k = pgm::sp_narrow(c, v, n, pl.w, A.r, dt);
   if (!(k.hit && k.t >= 0)) return false;
   V3 p = v3(A.px, A.py, A.pz);
@@ -105,68 +107,142 @@ __device__ __forceinline__ void emit_event(const WorldsView &v, int w, int step,
   v.events[(size_t)w * v.max_events + slot] = e;
 }
 
-template <int CPT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+// Shared-memory image of one world: every body as two float4.
+//   P4[i] = (px, py, pz, rho)   rho = conservative reach (r + |v| dt)(1+1e-4), refreshed with v
+//   V4[i] = (vx, vy, vz, r)
+// Lanes additionally cache (px,py,pz,rho) of their own CPT bodies in registers for the hot filter.
+
+// Slow half of one pass-4 row: candidates of row i (bit s of `mask` = this lane's column s*32+lane
+// passed the reach filter) are evaluated in increasing column order with the exact predicate.
+// Warp-uniform control flow; state is read from / written to shared memory.  Returns true if any
+// body changed (callers then reload their register caches).
+__device__ __noinline__ bool row_slow_path(float4 *P4, float4 *V4, int i, unsigned mask, int lane, int ncols_slots,
+                                           float dt, const WorldsView &v, int w, int step, bool record) {
+  __syncwarp();
+  pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
+  bool dirty = false;
+  int j0 = 0;
+  for (;;) {
+    // lowest candidate column >= j0 of this lane: slot bits below the first admissible slot are dropped
+    const int smin = (j0 >> 5) + ((lane < (j0 & 31)) ? 1 : 0);
+    const unsigned m = smin < 32 ? (mask >> smin) << smin : 0u;
+    const int jl = m ? (__ffs((int)m) - 1) * 32 + lane : 0x7fffffff;
+    const int j = __reduce_min_sync(kFull, jl);
+    if (j == 0x7fffffff) break;
+    const float4 ap = P4[i], av = V4[i], bp = P4[j], bv = V4[j];
+    Sphere A, B;
+    A.px = ap.x; A.py = ap.y; A.pz = ap.z; A.vx = av.x; A.vy = av.y; A.vz = av.z; A.r = av.w; A.rest = 0;
+    B.px = bp.x; B.py = bp.y; B.pz = bp.z; B.vx = bv.x; B.vy = bv.y; B.vz = bv.z; B.r = bv.w; B.rest = 0;
+    if (sphere_pair_exact(A, B, dt, leaf)) {
+      const float rhoA = reach(A.r, A.vx, A.vy, A.vz, dt), rhoB = reach(B.r, B.vx, B.vy, B.vz, dt);
+      __syncwarp();
+      if (lane == 0) {
+        P4[i] = make_float4(A.px, A.py, A.pz, rhoA); V4[i] = make_float4(A.vx, A.vy, A.vz, A.r);
+        P4[j] = make_float4(B.px, B.py, B.pz, rhoB); V4[j] = make_float4(B.vx, B.vy, B.vz, B.r);
+        if (record) emit_event(v, w, step, 4, PG_CLASS_DYNAMIC, i, PG_CLASS_DYNAMIC, j);
+      }
+      __syncwarp();
+      dirty = true;
+      // the row body changed: re-filter this lane's columns against its new state
+      mask = 0;
+      for (int s = 0; s < ncols_slots; s++) {
+        const int c = s * 32 + lane;
+        const float4 q = P4[c];
+        const float dx = A.px - q.x, dy = A.py - q.y, dz = A.pz - q.z;
+        const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
+        const float T = rhoA + q.w;
+        if (d2 <= T * T && c != i) mask |= 1u << s;
+      }
+    }
+    j0 = j + 1;
+  }
+  return dirty;
+}
+
+// Slow half of pass 3 for one body against one plane (per lane, divergent): refined gate, then the
+// exact visit.  Returns true if the body changed; *rest is set when it came to rest.
+__device__ __noinline__ bool plane_slow_path(float4 *P4, float4 *V4, int i, float4 pl, float restitution, float dt,
+                                             bool gate_ok, int *rest, pgm::LeafLen leaf) {
+  const float4 p = P4[i], q = V4[i];
+  if (gate_ok) {
+    // signed distance is linear in t; if the sphere surface stays farther than delta from the
+    // plane over [0,dt] no leaf of the interval search can pass (see sphere_pair_exact).
+    const float s0 = __fmaf_rn(p.x, pl.x, __fmaf_rn(p.y, pl.y, p.z * pl.z)) - pl.w;
+    const float ndv = __fmaf_rn(q.x, pl.x, __fmaf_rn(q.y, pl.y, q.z * pl.z));
+    const float s1 = __fmaf_rn(ndv, dt, s0);
+    const float gap = (s0 > 0.0f) == (s1 > 0.0f) ? fminf(fabsf(s0), fabsf(s1)) : 0.0f;
+    const float spd = sqrtf(__fmaf_rn(q.x, q.x, __fmaf_rn(q.y, q.y, q.z * q.z))) * 1.0001f;
+    const float delta = 1.1e-6f * spd + 4.0e-6f * (fabsf(pl.w) + fabsf(p.x) + fabsf(p.y) + fabsf(p.z) + 2.0f * spd * dt) + 1.0e-6f;
+    if (gap > (q.w + delta) * 1.00001f) return false;
+  }
+  Sphere A;
+  A.px = p.x; A.py = p.y; A.pz = p.z; A.vx = q.x; A.vy = q.y; A.vz = q.z; A.r = q.w; A.rest = 0;
+  if (!sphere_plane_exact(A, pl, restitution, dt, leaf)) return false;
+  P4[i] = make_float4(A.px, A.py, A.pz, reach(A.r, A.vx, A.vy, A.vz, dt));
+  V4[i] = make_float4(A.vx, A.vy, A.vz, A.r);
+  if (A.rest) *rest = 1;
+  return true;
+}
+
+template <int CPT, int WPB>
+__global__ void __launch_bounds__(WPB * 32, (CPT <= 8) ? PG_SPH_WARPS / WPB : 2)
 k_step_spheres(WorldsView v, float dt_in, int n_steps) {
-  __shared__ float4 s_planes[kWarpsPerBlock][kMaxPlanes];
-  __shared__ float4 s_rowp[kWarpsPerBlock][32];   // row cache: px,py,pz,rho
-  __shared__ float4 s_rowv[kWarpsPerBlock][32];   //            vx,vy,vz,r
+  __shared__ float4 s_planes[WPB][kMaxPlanes];
+  __shared__ float4 s_P4[WPB][CPT * 32];
+  __shared__ float4 s_V4[WPB][CPT * 32];
 
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int w = blockIdx.x * kWarpsPerBlock + wib;
+  const int w = blockIdx.x * WPB + wib;
   if (w >= v.n_worlds) return;
   const int n = v.counts[w * 3 + 1];
-  const int ns = v.counts[w * 3 + 0];
+  const int ns = min(v.counts[w * 3 + 0], kMaxPlanes);
   const float dt = pgm::clamp_dt(dt_in);
   const float restitution = v.restitution;
   const bool record = v.max_events > 0;
-  const bool gate_ok = dt > 1.0e-9f;             // the conservative gates divide by dt
-  const float inv_dt = gate_ok ? 1.0f / dt : 0.0f;
+  const bool gate_ok = dt > 1.0e-9f;
+  float4 *P4 = s_P4[wib], *V4 = s_V4[wib];
+  pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
 
-  if (lane < ns && lane < kMaxPlanes) s_planes[wib][lane] = v.planes[(size_t)w * v.cap[0] + lane];
+  if (lane < ns) s_planes[wib][lane] = v.planes[(size_t)w * v.cap[0] + lane];
 
-  float px[CPT], py[CPT], pz[CPT], vx[CPT], vy[CPT], vz[CPT], rad[CPT], rho[CPT];
+  float px[CPT], py[CPT], pz[CPT], rho[CPT];
   unsigned rest = 0;
   const size_t base = (size_t)w * v.cap[1];
 #pragma unroll
   for (int s = 0; s < CPT; s++) {
     const int i = s * 32 + lane;
+    float4 a, b;
     if (i < n) {
-      float4 a = v.pos_rest[base + i], b = v.vel_rad[base + i];
-      px[s] = a.x; py[s] = a.y; pz[s] = a.z; vx[s] = b.x; vy[s] = b.y; vz[s] = b.z; rad[s] = b.w;
+      a = v.pos_rest[base + i]; b = v.vel_rad[base + i];
       if (a.w != 0.0f) rest |= 1u << s;
-      rho[s] = reach(rad[s], vx[s], vy[s], vz[s], dt);
+      a.w = reach(b.w, b.x, b.y, b.z, dt);
     } else {
-      px[s] = kHuge * (float)(i + 1); py[s] = kHuge; pz[s] = kHuge; vx[s] = vy[s] = vz[s] = 0.0f; rad[s] = 0.0f; rho[s] = 0.0f;
+      // padding bodies sit far away from everything (and from each other) with zero reach
+      a = make_float4(kHuge * (float)(i + 1), kHuge, kHuge, 0.0f);
+      b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
+    P4[i] = a; V4[i] = b;
+    px[s] = a.x; py[s] = a.y; pz[s] = a.z; rho[s] = a.w;
   }
   __syncwarp();
 
   for (int step = 0; step < n_steps; step++) {
-    // ---------------- pass 3: every sphere against the planes, in plane order
+    // ---------------- pass 3: every sphere against the planes, in plane order (world.c:369-471)
 #pragma unroll
     for (int s = 0; s < CPT; s++) {
       const int i = s * 32 + lane;
       if (i < n) {
         for (int k = 0; k < ns; k++) {
           const float4 pl = s_planes[wib][k];
-          // conservative gate: signed distance is linear in t; if the sphere surface stays farther
-          // than delta from the plane over [0,dt] no leaf of the interval search can pass.
-          float s0 = __fmaf_rn(px[s], pl.x, __fmaf_rn(py[s], pl.y, pz[s] * pl.z)) - pl.w;
-          float ndv = __fmaf_rn(vx[s], pl.x, __fmaf_rn(vy[s], pl.y, vz[s] * pl.z));
-          float s1 = __fmaf_rn(ndv, dt, s0);
-          float gap = (s0 > 0.0f) == (s1 > 0.0f) ? fminf(fabsf(s0), fabsf(s1)) : 0.0f;
-          float spd = (rho[s] - rad[s]) * inv_dt;   // >= |v| (rho >= r + |v| dt)
-          float delta = 2.0e-5f * spd + 8.0e-6f * (fabsf(s0) + fabsf(pl.w) + fabsf(px[s]) + fabsf(py[s]) + fabsf(pz[s]) + spd * dt) + 2.0e-6f;
-          if (gate_ok && gap > (rad[s] + delta) * 1.00001f) continue;
-          Sphere A;
-          A.px = px[s]; A.py = py[s]; A.pz = pz[s]; A.vx = vx[s]; A.vy = vy[s]; A.vz = vz[s]; A.r = rad[s];
-          A.rest = (rest >> s) & 1;
-          if (sphere_plane_exact(A, pl, restitution, dt)) {
-            px[s] = A.px; py[s] = A.py; pz[s] = A.pz; vx[s] = A.vx; vy[s] = A.vy; vz[s] = A.vz;
-            if (A.rest) rest |= 1u << s;
-            rho[s] = reach(rad[s], vx[s], vy[s], vz[s], dt);
+          // cheap gate: |signed distance| beyond the reach -> the root test of the interval search fails
+          const float s0 = __fmaf_rn(px[s], pl.x, __fmaf_rn(py[s], pl.y, pz[s] * pl.z)) - pl.w;
+          if (gate_ok && fabsf(s0) > rho[s] * 1.0001f + 1.0e-5f * (fabsf(s0) + fabsf(pl.w) + 1.0f)) continue;
+          int came_to_rest = 0;
+          if (plane_slow_path(P4, V4, i, pl, restitution, dt, gate_ok, &came_to_rest, leaf)) {
+            const float4 a = P4[i];
+            px[s] = a.x; py[s] = a.y; pz[s] = a.z; rho[s] = a.w;
+            if (came_to_rest) rest |= 1u << s;
             if (record) emit_event(v, w, step, 3, PG_CLASS_DYNAMIC, i, PG_CLASS_STATIC, k);
           }
         }
@@ -174,100 +250,63 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps) {
     }
     __syncwarp();
 
-    // ---------------- pass 4: rows in order
-#pragma unroll 1
+    // ---------------- pass 4: rows in order (world.c:473-554)
+#pragma unroll
     for (int rs_ = 0; rs_ < CPT; rs_++) {
-      if (rs_ * 32 >= n) break;
-      // stage this block of 32 row bodies in the row cache
-      {
-        float sx = 0, sy = 0, sz = 0, sr = 0, svx = 0, svy = 0, svz = 0, srad = 0;
-#pragma unroll
-        for (int s = 0; s < CPT; s++) if (s == rs_) { sx = px[s]; sy = py[s]; sz = pz[s]; sr = rho[s]; svx = vx[s]; svy = vy[s]; svz = vz[s]; srad = rad[s]; }
-        s_rowp[wib][lane] = make_float4(sx, sy, sz, sr);
-        s_rowv[wib][lane] = make_float4(svx, svy, svz, srad);
-      }
-      __syncwarp();
-      const int rows_here = min(32, n - rs_ * 32);
+      if (rs_ * 32 < n) {
+        // speculative integration of this lane's row body (committed when its row completes;
+        // recomputed if a contact touches the block before that)
+        float ipx, ipy, ipz, ivx, ivy, ivz, irho, irad;
+        auto speculate = [&]() {
+          const float4 a = P4[rs_ * 32 + lane], b = V4[rs_ * 32 + lane];
+          V3 p = v3(a.x, a.y, a.z), vel = v3(b.x, b.y, b.z);
+          irho = a.w; irad = b.w;
+          if (!((rest >> rs_) & 1u)) { pgm::integrate(p, vel, dt); irho = reach(b.w, vel.x, vel.y, vel.z, dt); }
+          ipx = p.x; ipy = p.y; ipz = p.z; ivx = vel.x; ivy = vel.y; ivz = vel.z;
+        };
+        speculate();
+        const int rows_here = min(32, n - rs_ * 32);
 #pragma unroll 1
-      for (int rl = 0; rl < rows_here; rl++) {
-        const int i = rs_ * 32 + rl;
-        int j0 = 0;
-        for (;;) {
-          const float4 rp = s_rowp[wib][rl];
-          // reach filter over this lane's columns
-          int jl = 0x7fffffff;
-#pragma unroll
-          for (int s = CPT - 1; s >= 0; s--) {
-            const int j = s * 32 + lane;
-            float dx = rp.x - px[s], dy = rp.y - py[s], dz = rp.z - pz[s];
-            float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
-            float T = rp.w + rho[s];
-            if (d2 <= T * T && j >= j0 && j != i) jl = j;
-          }
-          const int j = __reduce_min_sync(kFull, jl);
-          if (j == 0x7fffffff) break;
-          // gather column j and the row body, evaluate exactly (uniform across the warp)
-          const int cs = j >> 5, cl = j & 31;
-          float cx = 0, cy = 0, cz = 0, cvx = 0, cvy = 0, cvz = 0, cr = 0;
-          unsigned crest_bits = 0;
-#pragma unroll
-          for (int s = 0; s < CPT; s++) if (s == cs) { cx = px[s]; cy = py[s]; cz = pz[s]; cvx = vx[s]; cvy = vy[s]; cvz = vz[s]; cr = rad[s]; }
-          Sphere B;
-          B.px = __shfl_sync(kFull, cx, cl); B.py = __shfl_sync(kFull, cy, cl); B.pz = __shfl_sync(kFull, cz, cl);
-          B.vx = __shfl_sync(kFull, cvx, cl); B.vy = __shfl_sync(kFull, cvy, cl); B.vz = __shfl_sync(kFull, cvz, cl);
-          B.r = __shfl_sync(kFull, cr, cl); B.rest = 0;
-          (void)crest_bits;
-          const float4 rv = s_rowv[wib][rl];
-          Sphere A;
-          A.px = rp.x; A.py = rp.y; A.pz = rp.z; A.vx = rv.x; A.vy = rv.y; A.vz = rv.z; A.r = rv.w; A.rest = 0;
-          if (sphere_pair_exact(A, B, dt)) {
-            const float rhoA = reach(A.r, A.vx, A.vy, A.vz, dt), rhoB = reach(B.r, B.vx, B.vy, B.vz, dt);
-            // write back: row body to its owner lane + row cache; column body to its owner lane
-            if (lane == rl) {
-#pragma unroll
-              for (int s = 0; s < CPT; s++) if (s == rs_) { px[s] = A.px; py[s] = A.py; pz[s] = A.pz; vx[s] = A.vx; vy[s] = A.vy; vz[s] = A.vz; rho[s] = rhoA; }
-            }
-            if (lane == cl) {
-#pragma unroll
-              for (int s = 0; s < CPT; s++) if (s == cs) { px[s] = B.px; py[s] = B.py; pz[s] = B.pz; vx[s] = B.vx; vy[s] = B.vy; vz[s] = B.vz; rho[s] = rhoB; }
-            }
-            __syncwarp();
-            if (lane == 0) {
-              s_rowp[wib][rl] = make_float4(A.px, A.py, A.pz, rhoA);
-              s_rowv[wib][rl] = make_float4(A.vx, A.vy, A.vz, A.r);
-              if (cs == rs_) {      // the column is a later (or earlier) row of this block: refresh its cache line
-                s_rowp[wib][cl] = make_float4(B.px, B.py, B.pz, rhoB);
-                s_rowv[wib][cl] = make_float4(B.vx, B.vy, B.vz, B.r);
-              }
-              if (record) emit_event(v, w, step, 4, PG_CLASS_DYNAMIC, i, PG_CLASS_DYNAMIC, j);
-            }
-            __syncwarp();
-          }
-          j0 = j + 1;
-        }
-        // integrate row i (world.c:549-553) in its owner lane
-        if (lane == rl) {
+        for (int rl = 0; rl < rows_here; rl++) {
+          const int i = rs_ * 32 + rl;
+          const float4 rp = P4[i];
+          unsigned mask = 0;
 #pragma unroll
           for (int s = 0; s < CPT; s++) {
-            if (s == rs_ && !((rest >> s) & 1)) {
-              V3 p = v3(px[s], py[s], pz[s]), vel = v3(vx[s], vy[s], vz[s]);
-              pgm::integrate(p, vel, dt);
-              px[s] = p.x; py[s] = p.y; pz[s] = p.z; vx[s] = vel.x; vy[s] = vel.y; vz[s] = vel.z;
-              rho[s] = reach(rad[s], vx[s], vy[s], vz[s], dt);
+            const float dx = rp.x - px[s], dy = rp.y - py[s], dz = rp.z - pz[s];
+            const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
+            const float T = rp.w + rho[s];
+            bool c = d2 <= T * T;
+            if (s == rs_) c = c && (lane != rl);
+            mask |= (c ? 1u : 0u) << s;
+          }
+          if (__any_sync(kFull, mask != 0)) {
+            if (row_slow_path(P4, V4, i, mask, lane, CPT, dt, v, w, step, record)) {
+#pragma unroll
+              for (int s = 0; s < CPT; s++) { const float4 a = P4[s * 32 + lane]; px[s] = a.x; py[s] = a.y; pz[s] = a.z; rho[s] = a.w; }
+              speculate();
             }
           }
+          // integrate row i (world.c:549-553): commit the owner lane's speculative state
+          if (lane == rl) {
+            px[rs_] = ipx; py[rs_] = ipy; pz[rs_] = ipz; rho[rs_] = irho;
+            P4[i] = make_float4(ipx, ipy, ipz, irho);
+            V4[i] = make_float4(ivx, ivy, ivz, irad);
+          }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
 
+  __syncwarp();
 #pragma unroll
   for (int s = 0; s < CPT; s++) {
     const int i = s * 32 + lane;
     if (i < n) {
-      v.pos_rest[base + i] = make_float4(px[s], py[s], pz[s], ((rest >> s) & 1) ? 1.0f : 0.0f);
-      v.vel_rad[base + i] = make_float4(vx[s], vy[s], vz[s], rad[s]);
+      const float4 a = P4[i];
+      v.pos_rest[base + i] = make_float4(a.x, a.y, a.z, ((rest >> s) & 1u) ? 1.0f : 0.0f);
+      v.vel_rad[base + i] = V4[i];
     }
   }
 }
@@ -369,16 +408,27 @@ int pg_launch_unpack_state(PgWorlds *w, int first, int count, int n, float *pos,
   return PG_OK;
 }
 
+template <int CPT, int WPB>
+static int launch_spheres(PgWorlds *w, float dt, int n_steps) {
+  static bool configured = false;
+  if (!configured) {
+    // all shared memory the SM has: the kernel wants 24 resident warps, each with an 8 KB world image
+    cudaFuncSetAttribute(k_step_spheres<CPT, WPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  const int blocks = (w->v.n_worlds + WPB - 1) / WPB;
+  k_step_spheres<CPT, WPB><<<blocks, WPB * 32, 0, w->stream>>>(w->v, dt, n_steps);
+  return PG_OK;
+}
+
 int pg_launch_sphere_step(PgWorlds *w, float dt, int n_steps) {
   const int cap = w->v.cap[1];
-  const int blocks = (w->v.n_worlds + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const int threads = kWarpsPerBlock * 32;
   if (w->v.cap[0] > kMaxPlanes) { pg_set_error("sphere mode supports at most %d static planes", kMaxPlanes); return PG_ERR_CAPACITY; }
-  if (cap <= 32) k_step_spheres<1><<<blocks, threads, 0, w->stream>>>(w->v, dt, n_steps);
-  else if (cap <= 64) k_step_spheres<2><<<blocks, threads, 0, w->stream>>>(w->v, dt, n_steps);
-  else if (cap <= 128) k_step_spheres<4><<<blocks, threads, 0, w->stream>>>(w->v, dt, n_steps);
-  else if (cap <= 256) k_step_spheres<8><<<blocks, threads, 0, w->stream>>>(w->v, dt, n_steps);
-  else if (cap <= 512) k_step_spheres<16><<<blocks, threads, 0, w->stream>>>(w->v, dt, n_steps);
+  if (cap <= 32) launch_spheres<1, 4>(w, dt, n_steps);
+  else if (cap <= 64) launch_spheres<2, 4>(w, dt, n_steps);
+  else if (cap <= 128) launch_spheres<4, 4>(w, dt, n_steps);
+  else if (cap <= 256) launch_spheres<8, 4>(w, dt, n_steps);
+  else if (cap <= 512) launch_spheres<16, 2>(w, dt, n_steps);
   else { pg_set_error("sphere mode supports at most 512 spheres per world (got capacity %d)", cap); return PG_ERR_CAPACITY; }
   PG_CUDA(cudaGetLastError());
   w->launches++;

@@ -18,6 +18,26 @@ void pg_set_error(const char *fmt, ...) {
   va_end(ap);
 }
 
+// Enumerate the leaves of world.c:557-582's recursion for the root (t0, t1): same float midpoints,
+// same `end - start < 1e-6` stop rule.  2^15 leaves for dt = 0.01666; cached per (t0, t1).
+static void leaf_rec(float a, float b, float *lo, float *hi, int depth) {
+  const float len = b - a;
+  if (len < 0.000001f || depth > 40 || !(len == len)) { if (len < *lo) *lo = len; if (len > *hi) *hi = len; return; }
+  const float mid = (a + b) * 0.5f;
+  leaf_rec(a, mid, lo, hi, depth + 1);
+  leaf_rec(mid, b, lo, hi, depth + 1);
+}
+void pg_leaf_lengths(float t0, float t1, float *lo, float *hi) {
+  static thread_local float c_t0 = -1.0f, c_t1 = -1.0f, c_lo = 0.0f, c_hi = 0.0f;
+  if (!(t0 == c_t0 && t1 == c_t1)) {
+    float l = 1.0e30f, h = -1.0e30f;
+    if (t1 - t0 < 1.0f && t1 > t0) leaf_rec(t0, t1, &l, &h, 0);
+    if (!(l <= h) || l <= 0.0f) { l = 0.4990e-6f; h = 1.0e-6f; }   // degenerate root: generic bounds
+    c_t0 = t0; c_t1 = t1; c_lo = l; c_hi = h;
+  }
+  *lo = c_lo; *hi = c_hi;
+}
+
 namespace {
 
 // glm_euler_xyz upper 3x3 (cglm euler.h), host libm sinf/cosf -- same library the reference links.
@@ -435,6 +455,11 @@ int pg_worlds_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes) {
   PG_CUDA(cudaSetDevice(w->device));
   PG_CUDA(cudaMemsetAsync(w->v.n_events, 0, sizeof(int) * (size_t)w->v.n_worlds, w->stream));
   PG_CUDA(cudaEventRecord(w->ev0, w->stream));
+  {
+    float cdt = dt;
+    if ((double)cdt > 0.01666) cdt = (float)0.01666;                 // world.c:175-177
+    pg_leaf_lengths(0.0f, cdt, &w->v.leaf_lo, &w->v.leaf_hi);
+  }
   int rc = PG_OK;
   if (n_steps > 0) {
     if (w->mode == PG_MODE_SPHERES) rc = pg_launch_sphere_step(w, dt, n_steps);

@@ -13,7 +13,7 @@ import numpy as np
 from .scenes import BODY_DTYPE, CLASS_DYNAMIC, CLASS_PLAYER, CLASS_STATIC
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-GPU_SO = os.path.join(HERE, "lib", "libphysics_gpu.so")
+GPU_SO = os.environ.get("CRUX_PG_LIB") or os.path.join(HERE, "lib", "libphysics_gpu.so")
 
 PG_EVENT_DTYPE = np.dtype([("world", "<i4"), ("step", "<i4"), ("event_type", "<i4"), ("a_class", "<i4"),
                            ("a_index", "<i4"), ("b_class", "<i4"), ("b_index", "<i4"), ("pass_", "<i4")])
