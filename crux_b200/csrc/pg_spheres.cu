@@ -184,6 +184,11 @@ __device__ __noinline__ bool plane_slow_path(float4 *P4, float4 *V4, int i, floa
   return true;
 }
 
+// The register cache is kept ROTATED: while row block `rb` (rows rb*32 .. rb*32+31) is swept,
+// static slot k of the cache holds the body of actual slot (rb + k) mod CPT, so the block's own
+// bodies always sit in static slot 0.  That keeps every register index a compile-time constant
+// with ONE copy of the row loop in the instruction stream (a fully unrolled variant was 9.5k SASS
+// instructions and spent most of its time in instruction-cache misses).
 template <int CPT, int WPB>
 __global__ void __launch_bounds__(WPB * 32, (CPT <= 8) ? PG_SPH_WARPS / WPB : 2)
 k_step_spheres(WorldsView v, float dt_in, int n_steps) {
@@ -197,6 +202,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps) {
   if (w >= v.n_worlds) return;
   const int n = v.counts[w * 3 + 1];
   const int ns = min(v.counts[w * 3 + 0], kMaxPlanes);
+  const int n_blocks = (n + 31) >> 5;
   const float dt = pgm::clamp_dt(dt_in);
   const float restitution = v.restitution;
   const bool record = v.max_events > 0;
@@ -206,10 +212,9 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps) {
 
   if (lane < ns) s_planes[wib][lane] = v.planes[(size_t)w * v.cap[0] + lane];
 
-  float px[CPT], py[CPT], pz[CPT], rho[CPT];
-  unsigned rest = 0;
+  unsigned rest = 0;                       // bit s: this lane's body of actual slot s is at rest
   const size_t base = (size_t)w * v.cap[1];
-#pragma unroll
+#pragma unroll 1
   for (int s = 0; s < CPT; s++) {
     const int i = s * 32 + lane;
     float4 a, b;
@@ -223,25 +228,27 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps) {
       b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     P4[i] = a; V4[i] = b;
-    px[s] = a.x; py[s] = a.y; pz[s] = a.z; rho[s] = a.w;
   }
   __syncwarp();
 
+  float px[CPT], py[CPT], pz[CPT], rho[CPT];
+
   for (int step = 0; step < n_steps; step++) {
     // ---------------- pass 3: every sphere against the planes, in plane order (world.c:369-471)
-#pragma unroll
-    for (int s = 0; s < CPT; s++) {
+#pragma unroll 1
+    for (int s = 0; s < n_blocks; s++) {
       const int i = s * 32 + lane;
       if (i < n) {
+        float4 a = P4[i];
+#pragma unroll 1
         for (int k = 0; k < ns; k++) {
           const float4 pl = s_planes[wib][k];
           // cheap gate: |signed distance| beyond the reach -> the root test of the interval search fails
-          const float s0 = __fmaf_rn(px[s], pl.x, __fmaf_rn(py[s], pl.y, pz[s] * pl.z)) - pl.w;
-          if (gate_ok && fabsf(s0) > rho[s] * 1.0001f + 1.0e-5f * (fabsf(s0) + fabsf(pl.w) + 1.0f)) continue;
+          const float s0 = __fmaf_rn(a.x, pl.x, __fmaf_rn(a.y, pl.y, a.z * pl.z)) - pl.w;
+          if (gate_ok && fabsf(s0) > a.w * 1.0001f + 1.0e-5f * (fabsf(s0) + fabsf(pl.w) + 1.0f)) continue;
           int came_to_rest = 0;
           if (plane_slow_path(P4, V4, i, pl, restitution, dt, gate_ok, &came_to_rest, leaf)) {
-            const float4 a = P4[i];
-            px[s] = a.x; py[s] = a.y; pz[s] = a.z; rho[s] = a.w;
+            a = P4[i];
             if (came_to_rest) rest |= 1u << s;
             if (record) emit_event(v, w, step, 3, PG_CLASS_DYNAMIC, i, PG_CLASS_STATIC, k);
           }
@@ -252,56 +259,69 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps) {
 
     // ---------------- pass 4: rows in order (world.c:473-554)
 #pragma unroll
-    for (int rs_ = 0; rs_ < CPT; rs_++) {
-      if (rs_ * 32 < n) {
-        // speculative integration of this lane's row body (committed when its row completes;
-        // recomputed if a contact touches the block before that)
-        float ipx, ipy, ipz, ivx, ivy, ivz, irho, irad;
-        auto speculate = [&]() {
-          const float4 a = P4[rs_ * 32 + lane], b = V4[rs_ * 32 + lane];
-          V3 p = v3(a.x, a.y, a.z), vel = v3(b.x, b.y, b.z);
-          irho = a.w; irad = b.w;
-          if (!((rest >> rs_) & 1u)) { pgm::integrate(p, vel, dt); irho = reach(b.w, vel.x, vel.y, vel.z, dt); }
-          ipx = p.x; ipy = p.y; ipz = p.z; ivx = vel.x; ivy = vel.y; ivz = vel.z;
-        };
-        speculate();
-        const int rows_here = min(32, n - rs_ * 32);
+    for (int k = 0; k < CPT; k++) { const float4 a = P4[k * 32 + lane]; px[k] = a.x; py[k] = a.y; pz[k] = a.z; rho[k] = a.w; }
+
 #pragma unroll 1
-        for (int rl = 0; rl < rows_here; rl++) {
-          const int i = rs_ * 32 + rl;
-          const float4 rp = P4[i];
-          unsigned mask = 0;
+    for (int rb = 0; rb < n_blocks; rb++) {
+      // speculative integration of this lane's row body (committed when its row completes;
+      // recomputed if a contact touches the world before that)
+      float ipx, ipy, ipz, ivx, ivy, ivz, irho, irad;
+      auto speculate = [&]() {
+        const float4 a = P4[rb * 32 + lane], b = V4[rb * 32 + lane];
+        V3 p = v3(a.x, a.y, a.z), vel = v3(b.x, b.y, b.z);
+        irho = a.w; irad = b.w;
+        if (!((rest >> rb) & 1u)) { pgm::integrate(p, vel, dt); irho = reach(b.w, vel.x, vel.y, vel.z, dt); }
+        ipx = p.x; ipy = p.y; ipz = p.z; ivx = vel.x; ivy = vel.y; ivz = vel.z;
+      };
+      speculate();
+      const int rows_here = min(32, n - rb * 32);
+#pragma unroll 1
+      for (int rl = 0; rl < rows_here; rl++) {
+        const int i = rb * 32 + rl;
+        const float4 rp = P4[i];
+        unsigned mask = 0;
 #pragma unroll
-          for (int s = 0; s < CPT; s++) {
-            const float dx = rp.x - px[s], dy = rp.y - py[s], dz = rp.z - pz[s];
-            const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
-            const float T = rp.w + rho[s];
-            bool c = d2 <= T * T;
-            if (s == rs_) c = c && (lane != rl);
-            mask |= (c ? 1u : 0u) << s;
-          }
-          if (__any_sync(kFull, mask != 0)) {
-            if (row_slow_path(P4, V4, i, mask, lane, CPT, dt, v, w, step, record)) {
+        for (int k = 0; k < CPT; k++) {
+          const float dx = rp.x - px[k], dy = rp.y - py[k], dz = rp.z - pz[k];
+          const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
+          const float T = rp.w + rho[k];
+          mask |= (d2 <= T * T ? 1u : 0u) << k;
+        }
+        if (lane == rl) mask &= ~1u;                 // the row body itself lives in static slot 0
+        if (__any_sync(kFull, mask != 0)) {
+          // static slot k is actual slot (rb + k) mod CPT: rotate the bits into column order
+          const unsigned full = (CPT == 32) ? 0xffffffffu : ((1u << CPT) - 1u);
+          const unsigned amask = ((mask << rb) | (mask >> ((CPT - rb) & 31))) & full;
+          if (row_slow_path(P4, V4, i, rb == 0 ? mask : amask, lane, CPT, dt, v, w, step, record)) {
 #pragma unroll
-              for (int s = 0; s < CPT; s++) { const float4 a = P4[s * 32 + lane]; px[s] = a.x; py[s] = a.y; pz[s] = a.z; rho[s] = a.w; }
-              speculate();
+            for (int k = 0; k < CPT; k++) {
+              int sa = rb + k; if (sa >= CPT) sa -= CPT;
+              const float4 a = P4[sa * 32 + lane]; px[k] = a.x; py[k] = a.y; pz[k] = a.z; rho[k] = a.w;
             }
-          }
-          // integrate row i (world.c:549-553): commit the owner lane's speculative state
-          if (lane == rl) {
-            px[rs_] = ipx; py[rs_] = ipy; pz[rs_] = ipz; rho[rs_] = irho;
-            P4[i] = make_float4(ipx, ipy, ipz, irho);
-            V4[i] = make_float4(ivx, ivy, ivz, irad);
+            speculate();
           }
         }
-        __syncwarp();
+        // integrate row i (world.c:549-553): commit the owner lane's speculative state
+        if (lane == rl) {
+          px[0] = ipx; py[0] = ipy; pz[0] = ipz; rho[0] = irho;
+          P4[i] = make_float4(ipx, ipy, ipz, irho);
+          V4[i] = make_float4(ivx, ivy, ivz, irad);
+        }
+      }
+      __syncwarp();
+      // rotate the cache: the next block's bodies move into static slot 0
+      {
+        const float tx = px[0], ty = py[0], tz = pz[0], tr = rho[0];
+#pragma unroll
+        for (int k = 0; k + 1 < CPT; k++) { px[k] = px[k + 1]; py[k] = py[k + 1]; pz[k] = pz[k + 1]; rho[k] = rho[k + 1]; }
+        px[CPT - 1] = tx; py[CPT - 1] = ty; pz[CPT - 1] = tz; rho[CPT - 1] = tr;
       }
     }
   }
 
   __syncwarp();
-#pragma unroll
-  for (int s = 0; s < CPT; s++) {
+#pragma unroll 1
+  for (int s = 0; s < n_blocks; s++) {
     const int i = s * 32 + lane;
     if (i < n) {
       const float4 a = P4[i];
