@@ -1,0 +1,355 @@
+#!/usr/bin/env python3
+"""bench.py -- body-steps/s of the Crux physics step on B200 (and the reference CPU step beside it).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU physics
+
+Workload (config.workload = "c3"): BASELINE.json configs[2], the one the headline metric is quoted
+on -- 4096 independent 256-sphere "bouncehouse" worlds per GPU (6 wall planes, r = 0.15, LCG seed
+12345 + world index), dt = 1/60 -> clamped to 0.01666.  One "step" is one
+physics_step of every world.  Worlds shard across ranks with no data-path collective (weak scaling:
+4096 worlds per GPU); the only exchange is the 8-double aggregate statistics vector, all-reduced
+over NCCL once per launch.
+
+Timing: W warm-up steps, then K timed steps issued as launches of --steps-per-launch steps.  Every
+launch is bracketed by CUDA events on the library's own stream (pg_worlds_last_step_ms); L2 is
+flushed between launches outside the event pairs.  ms_per_step = max over ranks of the summed event
+times / K.  `e2e` repeats the measurement through the host-buffer API (pinned host arrays in,
+pinned host arrays out, every step).  `cpu_baseline` times the reference CPU step on this box.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from crux_b200 import scenes  # noqa: E402
+
+METRIC = "body_steps_per_sec"
+UNIT = "body-steps/s"
+ALGO_BYTES_PER_BODY_STEP = 52          # integrate R 28 B + W 24 B
+WORKLOADS = {
+    "c3": dict(n_worlds=4096, n_spheres=256, L=10.0, desc="4096 batched 256-sphere bouncehouse worlds per GPU"),
+    "c3-small": dict(n_worlds=256, n_spheres=256, L=10.0, desc="256 batched 256-sphere worlds per GPU (smoke size)"),
+}
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu_index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for name, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU step (oracle/_ref = the unmodified reference compiled here; else the plain-C port)
+# ------------------------------------------------------------------------------------------------
+
+def _cpu_lib():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ora
+    if os.path.exists(ora.REF_SO):
+        return ora, ora.RefLib(), "reference"
+    if not os.path.exists(ora.ORACLE_SO):
+        ora.build_oracles()
+    return ora, ora.OracleLib(), "port"
+
+
+def cpu_reference_rate(cfg: dict, n_worlds: int, steps: int, warmup: int, threads: int, first_world: int = 0):
+    """Step `n_worlds` sample worlds of the workload for `steps` steps on `threads` host threads.
+
+    ctypes releases the GIL, so plain Python threads run the C step concurrently, one world each."""
+    ora, lib, kind = _cpu_lib()
+    st = scenes.plane_bodies(scenes.box_planes(cfg["L"]))
+    pos, vel = scenes.sphere_worlds(n_worlds, cfg["n_spheres"], cfg["L"], first_world=first_world)
+    worlds = [ora.World(lib, st, scenes.sphere_bodies(pos[k], vel[k])) for k in range(n_worlds)]
+    for w in worlds:
+        w.record_events(False)
+
+    def run(nsteps):
+        it = iter(worlds)
+        lock = threading.Lock()
+
+        def worker():
+            while True:
+                with lock:
+                    w = next(it, None)
+                if w is None:
+                    return
+                w.step(scenes.DT_60HZ, nsteps, 0)
+        ts = [threading.Thread(target=worker) for _ in range(threads)]
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        return time.perf_counter() - t0
+
+    if warmup:
+        run(warmup)
+    el = run(steps)
+    for w in worlds:
+        w.close()
+    return n_worlds * cfg["n_spheres"] * steps / el, el, kind
+
+
+def run_reference_arm(args, cfg):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = min(cores, 64)
+    n_sample = threads * 2
+    # bound the run: ~1.2 ms per world-step on one core
+    steps = args.steps
+    rate, el, kind = cpu_reference_rate(cfg, n_sample, steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": el / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": cfg["desc"], "n_spheres": cfg["n_spheres"], "dt": float(scenes.MAX_DELTA_TIME),
+                   "sample": f"{n_sample} worlds x {cfg['n_spheres']} spheres, {threads} host threads"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": f"{n_sample} worlds x {steps} steps (of {cfg['n_worlds']} per GPU)"},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# the CUDA path
+# ------------------------------------------------------------------------------------------------
+
+def run_gpu_arm(args, cfg):
+    import torch
+    import torch.distributed as dist
+    from crux_b200 import gpu
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    nw, n, L = cfg["n_worlds"], cfg["n_spheres"], cfg["L"]
+    bodies = nw * n
+    first_world = rank * nw                                 # weak scaling: every rank owns nw worlds
+    pos, vel = scenes.sphere_worlds(nw, n, L, first_world=first_world)
+    statics = scenes.plane_bodies(scenes.box_planes(L))
+    worlds = gpu.GpuWorlds(nw, len(statics), n, 0, max_events_per_world=0, device=local_rank)
+    worlds.set_spheres(0, statics, pos, vel)
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
+    stats_dev = torch.zeros(8, dtype=torch.float64, device="cuda")
+    spl = max(1, min(args.steps_per_launch, args.steps))
+    dt = float(scenes.DT_60HZ)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def launch(k):
+        flush.zero_()
+        torch.cuda.synchronize()
+        worlds.step(dt, k)
+        worlds.stats(dev_out_ptr=stats_dev.data_ptr(), want_host=False)     # fused partials -> device vector
+        worlds.sync()
+        ms = worlds.last_step_ms()
+        if world_size > 1:
+            dist.all_reduce(stats_dev)                                      # NCCL, 64 bytes
+        return ms
+
+    # warm-up
+    done = 0
+    while done < args.warmup:
+        k = min(spl, args.warmup - done)
+        launch(k)
+        done += k
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = worlds.launches
+    ev_ms = 0.0
+    launch_ms = []
+    t_wall0 = time.perf_counter()
+    done = 0
+    while done < args.steps:
+        k = min(spl, args.steps - done)
+        ms = launch(k)
+        ev_ms += ms
+        launch_ms.append(ms / k)
+        done += k
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    gpu_launches = worlds.launches - launches0
+    stats_host = stats_dev.cpu().numpy().copy()
+
+    t = torch.tensor([ev_ms], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ev_ms_max = float(t.item())
+    value = bodies * world_size * args.steps / (ev_ms_max * 1e-3)
+
+    # ---- end to end through the host-buffer API: H2D state, one step, D2H state, every step
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    hp = gpu.PinnedArray((nw, n, 3), np.float32); hv = gpu.PinnedArray((nw, n, 3), np.float32)
+    hr = gpu.PinnedArray((nw, n), np.uint8)
+    worlds.download_state(0, nw, hp.array, hv.array, hr.array)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        worlds.upload_state(0, nw, hp.array, hv.array, hr.array)
+        worlds.step(dt, 1)
+        worlds.download_state(0, nw, hp.array, hv.array, hr.array)      # synchronises
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = bodies * world_size * e2e_steps / float(t.item())
+    h2d = bodies * (12 + 12 + 1)
+    d2h = bodies * (12 + 12 + 1)
+    checksum = float(np.abs(hp.array).sum())
+    hp.free(); hv.free(); hr.free()
+
+    if rank == 0:
+        peak, peak_src = read_peaks()
+        avg_launch_ms = ev_ms_max / max(1, len(launch_ms))
+        algo_bytes = ALGO_BYTES_PER_BODY_STEP * bodies * spl
+        achieved = algo_bytes / (avg_launch_ms * 1e-3) / 1e9
+        traffic = None
+        rj = os.path.join(ROOT, "profiles", "roofline_r01.json")
+        if os.path.exists(rj):
+            try:
+                traffic = json.load(open(rj)).get("dram_bytes_per_step")
+                traffic = traffic * spl if traffic else None
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": cfg["desc"], "worlds_per_gpu": nw, "n_spheres": n, "n_planes": 6,
+                       "dt": float(scenes.MAX_DELTA_TIME), "steps_per_launch": spl, "parallelism": f"worlds-sharded x{world_size}",
+                       "l2": "256 MiB flush between launches, outside the CUDA-event pairs"},
+            "roofline": {"bound": "hbm", "kernel": "k_step_spheres<8,4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes,
+                         "note": "state lives in registers/shared memory for the whole launch; the kernel is "
+                                 "SM-issue-bound, not HBM-bound (SURVEY.md section 8d), see profiles/"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "pg_worlds_upload_state + pg_worlds_step(1) + pg_worlds_download_state, pinned host buffers"},
+            "gpu_launches": int(gpu_launches),
+            "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
+            "launch_ms_per_step_min_max": [min(launch_ms), max(launch_ms)],
+            "stats": {"bodies": stats_host[0], "kinetic": stats_host[1], "at_rest": stats_host[6], "nonfinite": stats_host[7]},
+            "state_checksum": checksum,
+        }
+        if world_size == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            threads = min(cores, 64)
+            # ~10 s of CPU work per thread: 6 worlds per thread x 1000 steps at ~1.3 ms per world-step
+            cpu_steps = 1000
+            rate, el, kind = cpu_reference_rate(cfg, threads * 6, cpu_steps, 0, threads)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+                                    "sample": f"{threads * 6} worlds x {cpu_steps} steps of the same workload, {el:.1f} s wall"}
+        print(json.dumps(line), flush=True)
+
+    worlds.close()
+    if world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--steps-per-launch", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+    else:
+        run_gpu_arm(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

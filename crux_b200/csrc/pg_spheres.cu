@@ -29,7 +29,7 @@ using pgm::V3;
 using pgm::v3;
 
 #ifndef PG_SPH_WARPS
-#define PG_SPH_WARPS 16   // resident warps (worlds) per SM the register budget is sized for
+#define PG_SPH_WARPS 12   // resident warps (worlds) per SM the register budget is sized for
 #endif
 constexpr int kMaxPlanes = 16;
 constexpr unsigned kFull = 0xffffffffu;

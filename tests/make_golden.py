@@ -1,0 +1,156 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference compiled in this container
+(oracle/_ref/libcrux_ref.so, built by oracle/Makefile from /root/reference/src/physics/*.c).
+
+    python tests/make_golden.py
+
+The fixtures travel with the repo so that boxes without /root/reference (the GPU box) can still pin
+the plain-C restatement and the CUDA path to the reference's own outputs:
+  pairs_kat.npz        per-pair known answers for the 7 live collider pairs: distance, interval
+                       gate, narrowphase, resolver and full-visit outputs on seeded random and
+                       adversarial inputs (touching, NaN root, zero relative velocity, behind-plane)
+  spheres_256.npz      256-sphere bouncehouse world (world 0): state after
+                       1, 10, 100, 1000 steps + the contact-event sequence of the first 100 steps
+  mixed_world.npz      planes + static AABBs + dynamic AABBs (incl. an item) + capsule player with
+                       scene nodes refreshed every step: states after 25/50/150 steps + events
+  aabb_unity.npz       inputs/expected outputs of the reference's own Unity test
+                       (test/physics/test_aabb.c:24-141)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import gen  # noqa: E402
+import ora  # noqa: E402
+from crux_b200 import scenes  # noqa: E402
+
+OUT = os.path.join(HERE, "golden")
+
+
+def oracle_node_transform(orc):
+    import ctypes as C
+
+    def f(pos, rot, scale, parent=None):
+        out = np.zeros(16, np.float32)
+        p = np.ascontiguousarray(pos, np.float32); r = np.ascontiguousarray(rot, np.float32)
+        s = np.ascontiguousarray(scale, np.float32)
+        par = None if parent is None else np.ascontiguousarray(parent, np.float32)
+        orc.dll.ora_node_transform(p.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p),
+                                   None if par is None else par.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        return out
+    return f
+
+
+def adversarial_pairs():
+    """Hand-made sphere/plane records for the narrowphase quirks listed in SURVEY.md a23/a24."""
+    A, B = [], []
+
+    def sph(p, v, r=0.15):
+        return scenes.sphere_bodies(np.array([p], np.float32), np.array([v], np.float32), radius=r)[0]
+
+    def pln(n, d):
+        return scenes.plane_bodies(np.array([[*n, d]], np.float32))[0]
+    A.append(sph([0, 1, 0], [0, 0, 0])); B.append(sph([0.3, 1, 0], [0, 0, 0]))            # touching, a = 0 -> NaN root
+    A.append(sph([0, 1, 0], [1, 0, 0])); B.append(sph([0.30001, 1, 0], [-1, 0, 0]))        # head-on, just apart
+    A.append(sph([0, 1, 0], [1, 0, 0])); B.append(sph([0.29, 1, 0], [1, 0, 0]))            # overlapping, same velocity
+    A.append(sph([0, 1, 0], [-1, 0, 0])); B.append(sph([0.4, 1, 0], [1, 0, 0]))            # receding -> negative root
+    A.append(sph([0, 1, 0], [3, 0, 0])); B.append(sph([0.35, 1.29, 0], [0, 0, 0]))         # grazing, d < 0
+    A.append(sph([0, 0.1, 0], [0, -1, 0])); B.append(pln([0, 1, 0], 0))                    # penetrating floor
+    A.append(sph([0, -0.5, 0], [0, 1, 0])); B.append(pln([0, 1, 0], 0))                    # behind the plane
+    A.append(sph([0, 0.15, 0], [1, 0, 0])); B.append(pln([0, 1, 0], 0))                    # resting contact, tangential motion
+    A.append(sph([0, 0.150024, 0], [0.75, 0, 11.65])); B.append(pln([0, 1, 0], 0))         # the 2^depth case
+    A.append(sph([0, 0.2, 0], [0, -0.3, 0])); B.append(pln([0, 1, 0], 0))                  # slow approach -> resting rule
+    return np.array(A, dtype=scenes.BODY_DTYPE), np.array(B, dtype=scenes.BODY_DTYPE)
+
+
+def main():
+    ora.build_oracles()
+    ref = ora.RefLib()
+    orc = ora.OracleLib()
+    nt = oracle_node_transform(orc)
+    os.makedirs(OUT, exist_ok=True)
+    dt = gen.DT
+
+    # ---- per-pair KATs
+    rng = np.random.default_rng(20261019)
+    A, B = gen.rand_pairs(rng, 700, nt)
+    A2, B2 = adversarial_pairs()
+    A = np.concatenate([A, A2]); B = np.concatenate([B, B2])
+    n = len(A)
+    t = rng.uniform(0, dt, n).astype(np.float32)
+    out = dict(A=A, B=B, t=t, dist=np.zeros(n, np.float32), maxmove=np.zeros(n, np.float32),
+               interval=np.zeros(n, np.int32), colliding=np.zeros(n, np.int32), hit_time=np.zeros(n, np.float32),
+               visit=np.zeros(n, np.int32), A_after=scenes_core(n), B_after=scenes_core(n),
+               A_resolved=scenes_core(n), B_resolved=scenes_core(n), resolve_time=np.zeros(n, np.float32))
+    for k in range(n):
+        a, b = A[k:k + 1], B[k:k + 1]
+        out["dist"][k] = ref.k_min_dist(a, b, t[k])
+        out["maxmove"][k] = ref.k_max_move(a, 0.0, dt)
+        out["interval"][k] = ref.k_interval(a, b, 0.0, dt)[0]
+        c, ht = ref.k_narrow(a, b, dt)
+        out["colliding"][k], out["hit_time"][k] = c, ht
+        ev, aa, bb = ref.k_visit(a, b, dt)
+        out["visit"][k] = ev; out["A_after"][k] = aa[0]; out["B_after"][k] = bb[0]
+        rt = ht if ht >= 0 else np.float32(0.004)
+        out["resolve_time"][k] = rt
+        _, aa, bb = ref.k_resolve(a, b, rt, dt)
+        out["A_resolved"][k] = aa[0]; out["B_resolved"][k] = bb[0]
+    np.savez_compressed(os.path.join(OUT, "pairs_kat.npz"), **out)
+    print("pairs_kat:", n, "pairs,", int(out["visit"].sum()), "visits fire")
+
+    # ---- 256-sphere world trajectory
+    st, dy = scenes.bouncehouse_world(0)
+    w = ora.World(ref, st, dy)
+    snaps = {}
+    done = 0
+    events100 = None
+    for target in (1, 10, 100, 1000):
+        w.step(scenes.DT_60HZ, target - done)
+        done = target
+        snaps[f"state_{target}"] = w.read(1)
+        if target == 100:
+            events100 = w.events(clear=False)
+    ev_all = w.events()
+    np.savez_compressed(os.path.join(OUT, "spheres_256.npz"), events_first100=events100, n_events_1000=len(ev_all), **snaps)
+    print("spheres_256: events in 1000 steps =", len(ev_all))
+
+    # ---- mixed world with scene nodes
+    rng = np.random.default_rng(5)
+    s_, d_, p_ = gen.mixed_world(rng, nt, with_player=True)
+    w = ora.World(ref, s_, d_, p_)
+    mixed = dict(statics=s_, dynamics=d_, players=p_)
+    done = 0
+    for target in (25, 50, 150):
+        w.step(scenes.DT_60HZ, target - done, 1)
+        done = target
+        for cls, name in ((0, "S"), (1, "D"), (2, "P")):
+            mixed[f"{name}_{target}"] = w.read(cls)
+    mixed["events"] = w.events()
+    np.savez_compressed(os.path.join(OUT, "mixed_world.npz"), **mixed)
+    print("mixed_world: events =", len(mixed["events"]))
+
+    # ---- the reference's own Unity vectors (test/physics/test_aabb.c)
+    unity = dict(
+        aabb_true_a=np.array([1.5, 1.5, 1.5, 0.5, 0.5, 0.5], np.float32), aabb_true_b=np.array([2.0, 2.0, 2.0, 0.5, 0.5, 0.5], np.float32),
+        aabb_false_a=np.array([1.5, 1.5, 1.5, 0.5, 0.5, 0.5], np.float32), aabb_false_b=np.array([3.5, 3.5, 3.5, 0.5, 0.5, 0.5], np.float32),
+        plane_box=np.array([1.5, 1.5, 1.5, 0.5, 0.5, 0.5], np.float32),
+        plane_true_1=np.array([0.0, 1.0, 0.0, 1.5], np.float32), plane_true_2=np.array([0.577, 0.577, 0.577, 2.0], np.float32),
+        plane_false_1=np.array([0.0, 1.0, 0.0, 0.0], np.float32), plane_false_2=np.array([0.577, 0.577, 0.577, 10.0], np.float32),
+        update_src=np.array([0, 0, 0, 1, 1, 1], np.float32), update_translation=np.array([5, 0, 0], np.float32),
+        update_scale=np.array([1, 1, 1], np.float32), update_rot_y_deg=np.float32(90.0),
+        update_expected=np.array([5, 0, 0, 1, 1, 1], np.float32), update_tol=np.float32(1e-4))
+    np.savez_compressed(os.path.join(OUT, "aabb_unity.npz"), **unity)
+    print("wrote", sorted(os.listdir(OUT)))
+
+
+def scenes_core(n):
+    return np.zeros(n, dtype=scenes.CORE_DTYPE)
+
+
+if __name__ == "__main__":
+    main()

@@ -145,3 +145,84 @@ def test_no_gpu_fallback_is_an_error(gpu_lib):
     with pytest.raises(gpu_lib.PgError):
         w.set_bodies(0, scenes.CLASS_DYNAMIC, scenes.sphere_bodies(np.zeros((9, 3)), np.zeros((9, 3))))
     w.close()
+
+
+def test_cuda_path_against_reference_fixtures(gpu_lib):
+    """The CUDA path against committed outputs of the unmodified reference (tests/golden/), so the
+    chain reference -> fixtures -> GPU does not depend on the port being right."""
+    import os
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(G, "pairs_kat.npz"))
+    A = ora.from_core(z["A"]); B = ora.from_core(z["B"])
+    d = gpu_lib.pair_min_dist(A, B, z["t"])
+    assert gen.same_bits(d, z["dist"])
+    hit, _ = gpu_lib.pair_interval_collision(A, B, 0.0, gen.DT)
+    assert np.array_equal(hit, z["interval"])
+    col, ht = gpu_lib.pair_narrow_phase(A, B, gen.DT)
+    assert np.array_equal(col, z["colliding"]) and gen.same_bits(ht, z["hit_time"])
+    ev, Av, Bv = gpu_lib.pair_visit(A, B, gen.DT)
+    assert np.array_equal(ev, z["visit"]) and gen.state_equal(Av, z["A_after"]) and gen.state_equal(Bv, z["B_after"])
+    Ar, Br = gpu_lib.pair_resolve(A, B, z["resolve_time"], gen.DT)
+    assert gen.state_equal(Ar, z["A_resolved"]) and gen.state_equal(Br, z["B_resolved"])
+
+    z = np.load(os.path.join(G, "spheres_256.npz"))
+    pos, vel = scenes.sphere_worlds(1, 256, 10.0)
+    st = scenes.plane_bodies(scenes.box_planes(10.0))
+    w = gpu_lib.GpuWorlds(1, len(st), 256, 0, max_events_per_world=4096)
+    w.set_spheres(0, st, pos, vel)
+    done = 0
+    for target in (1, 10, 100, 1000):
+        w.step(DT, target - done)
+        if target == 100:
+            pass
+        done = target
+        assert gen.state_equal(w.get_bodies(0, scenes.CLASS_DYNAMIC), z[f"state_{target}"]), target
+    w.close()
+    w = gpu_lib.GpuWorlds(1, len(st), 256, 0, max_events_per_world=4096)
+    w.set_spheres(0, st, pos, vel)
+    w.step(DT, 100)
+    assert _events_tuple(w.events()) == _events_tuple(z["events_first100"])
+    w.close()
+
+    z = np.load(os.path.join(G, "mixed_world.npz"))
+    g = gpu_lib.GpuWorlds(1, len(z["statics"]), len(z["dynamics"]), len(z["players"]), max_events_per_world=4096)
+    g.set_bodies(0, scenes.CLASS_STATIC, ora.from_core(z["statics"]))
+    g.set_bodies(0, scenes.CLASS_DYNAMIC, ora.from_core(z["dynamics"]))
+    g.set_bodies(0, scenes.CLASS_PLAYER, ora.from_core(z["players"]))
+    done = 0
+    events = []
+    for target in (25, 50, 150):
+        g.step(DT, target - done, refresh_nodes=True)
+        ev = g.events()
+        ev["step"] += done
+        events.extend(_events_tuple(ev))
+        done = target
+        for cls, name in ((0, "S"), (1, "D"), (2, "P")):
+            assert gen.state_equal(g.get_bodies(0, cls), z[f"{name}_{target}"]), (target, name)
+    assert events == _events_tuple(z["events"])
+    g.close()
+
+
+def test_large_batch_properties(gpu_lib, oracle_lib):
+    """Full C3 size (4096 x 256): size-independent properties -- the batch result equals running
+    any sampled world alone (worlds are independent), no NaNs, every body stays accounted for --
+    plus the oracle on a handful of sampled worlds."""
+    nw, n = 4096, 256
+    pos, vel = scenes.sphere_worlds(nw, n, 10.0)
+    st = scenes.plane_bodies(scenes.box_planes(10.0))
+    w = gpu_lib.GpuWorlds(nw, len(st), n, 0, max_events_per_world=0)
+    w.set_spheres(0, st, pos, vel)
+    w.step(DT, 50)
+    P = np.zeros((nw, n, 3), np.float32); V = np.zeros_like(P); R = np.zeros((nw, n), np.uint8)
+    w.download_state(0, nw, P, V, R)
+    s = w.stats()
+    assert s["bodies"] == nw * n and s["nonfinite"] == 0 and np.isfinite(P).all()
+    from crux_b200 import shard
+    want = shard.stats_from_state(V, R)
+    assert np.isclose(s["kinetic"], want[1], rtol=1e-9) and s["at_rest"] == want[6]
+    for k in (0, 1, 2047, 4095):
+        o = ora.World(oracle_lib, st, scenes.sphere_bodies(pos[k], vel[k]))
+        o.step(DT, 50)
+        r = o.read(1)
+        assert gen.same_bits(P[k], r["position"]) and gen.same_bits(V[k], r["velocity"]), k
+    w.close()
