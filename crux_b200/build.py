@@ -30,6 +30,7 @@ NVCC_FLAGS = [
 ]
 CU_SOURCES = ["physics_gpu.cu", "pg_general.cu", "pg_spheres.cu", "pg_large.cu"]
 HOST_SOURCES = ["host/crux_world.c", "host/crux_colliders.c", "host/crux_scene.c"]
+HEADLESS = os.path.join(LIB, "crux_headless")
 
 
 def _newer(target: str, deps: list[str]) -> bool:
@@ -88,6 +89,15 @@ def build_host(force: bool = False) -> str | None:
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("gcc failed on the host layer")
+    main_c = os.path.join(CSRC, "host", "crux_headless.c")
+    if os.path.exists(main_c) and (force or _newer(HEADLESS, [main_c, HOST_SO] + _headers())):
+        cmd = ["gcc", "-std=gnu11", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-rdynamic",
+               "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(CSRC, "host"),
+               "-o", HEADLESS, main_c, "-L" + LIB, "-lcrux_physics", "-lphysics_gpu", "-Wl,-rpath,$ORIGIN", "-lm"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("gcc failed on crux_headless")
     return HOST_SO
 
 

@@ -220,16 +220,8 @@ int pg_worlds_set_bodies(PgWorlds *w, int world, int cls, const PgBody *bodies, 
   PG_CUDA(cudaStreamSynchronize(w->stream));
   int rc = ensure_records(w);
   if (rc) return rc;
-  if (n) {
-    std::vector<PgBody> tmp(bodies, bodies + n);
-    for (int i = 0; i < n; i++) {
-      // physics_add_body / physics_add_player field rules, world.c:41-142
-      if (cls == PG_CLASS_STATIC) { tmp[i].velocity[0] = tmp[i].velocity[1] = tmp[i].velocity[2] = 0.0f; tmp[i].dynamic = 0; }
-      if (cls == PG_CLASS_DYNAMIC) tmp[i].dynamic = 1;
-      if (cls == PG_CLASS_PLAYER) { tmp[i].restitution = 0.0f; tmp[i].dynamic = 0; }
-    }
-    PG_CUDA(cudaMemcpy(w->v.bodies[cls] + (size_t)world * w->v.cap[cls], tmp.data(), sizeof(PgBody) * (size_t)n, cudaMemcpyHostToDevice));
-  }
+  if (n)   // verbatim: the add-time field rules (world.c:41-142) belong to pg_worlds_add_body
+    PG_CUDA(cudaMemcpy(w->v.bodies[cls] + (size_t)world * w->v.cap[cls], bodies, sizeof(PgBody) * (size_t)n, cudaMemcpyHostToDevice));
   w->h_counts[world * 3 + cls] = n;
   rc = push_counts(w, world);
   if (rc) return rc;
@@ -252,8 +244,8 @@ int pg_worlds_add_body(PgWorlds *w, int world, const PgBody *body, int as_player
   int rc = ensure_records(w);
   if (rc) return rc;
   PgBody tmp = *body;
-  if (cls == PG_CLASS_STATIC) { tmp.velocity[0] = tmp.velocity[1] = tmp.velocity[2] = 0.0f; }
-  if (cls == PG_CLASS_PLAYER) { tmp.restitution = 0.0f; tmp.dynamic = 0; }
+  if (cls == PG_CLASS_STATIC) { tmp.velocity[0] = tmp.velocity[1] = tmp.velocity[2] = 0.0f; }   // world.c:51
+  if (cls == PG_CLASS_PLAYER) { tmp.restitution = 0.0f; tmp.dynamic = 0; }                           // world.c:137 (+calloc)
   PG_CUDA(cudaMemcpy(w->v.bodies[cls] + (size_t)world * w->v.cap[cls] + n, &tmp, sizeof(PgBody), cudaMemcpyHostToDevice));
   w->h_counts[world * 3 + cls] = n + 1;
   rc = push_counts(w, world);

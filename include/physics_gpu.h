@@ -122,9 +122,12 @@ PgWorlds *pg_worlds_create(int n_worlds, int max_static, int max_dynamic, int ma
 void pg_worlds_destroy(PgWorlds *w);
 int  pg_worlds_count(const PgWorlds *w);
 
-/* Replace the bodies of one class of one world (n may be 0).  Order = reference array order. */
+/* Replace the bodies of one class of one world (n may be 0), records taken VERBATIM (the caller's
+ * mirror is the truth, as it is for the reference's physics_step).  Order = reference array order. */
 int  pg_worlds_set_bodies(PgWorlds *w, int world, int cls, const PgBody *bodies, int n);
-/* physics_add_body / physics_add_player: append one record; returns its index or <0. */
+/* physics_add_body / physics_add_player: append one record applying the reference's add-time rules
+ * (static velocity forced to 0, world.c:51; player restitution 0 and dynamic=false, world.c:137);
+ * returns its index or <0. */
 int  pg_worlds_add_body(PgWorlds *w, int world, const PgBody *body, int as_player);
 /* physics_remove_body: swap-with-last and pop (world.c:147-172). */
 int  pg_worlds_remove_body(PgWorlds *w, int world, int cls, int index);

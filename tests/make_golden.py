@@ -154,3 +154,46 @@ def scenes_core(n):
 
 if __name__ == "__main__":
     main()
+
+
+# ---- scene-file fixtures (config C1): reduced copies of the reference's scene DATA + dumps of the
+# reference-linked headless driver (oracle/_ref/crux_headless_ref)
+SCENES = [("bouncehouse", True, 1000), ("bouncehouse3", False, 600), ("scene_sphere", False, 600)]
+
+
+def _reduce(node):
+    keep = ("position", "rotation", "scale", "velocity", "collider", "entity_type", "components")
+    out = {k: node[k] for k in keep if k in node}
+    if "components" in out:
+        out["components"] = []                      # marks the Gen-3 schema; contents are not physics
+    if "children" in node:
+        out["children"] = [_reduce(c) for c in node["children"]]
+    return out
+
+
+def make_scene_fixtures():
+    import json
+    import subprocess
+    out_dir = os.path.join(OUT, "scenes")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(ROOT, "oracle", "_ref", "crux_headless_ref")
+    for name, player, steps in SCENES:
+        src = os.path.join(ora.REFERENCE_ROOT, "scenes", name + ".json")
+        doc = json.load(open(src))
+        red = {}
+        if "nodes" in doc:
+            red["nodes"] = _reduce(doc["nodes"])
+        if "meshes" in doc:
+            red["meshes"] = {k: [_reduce(m) for m in v] for k, v in doc["meshes"].items()}
+        dst = os.path.join(out_dir, name + ".json")
+        json.dump(red, open(dst, "w"), indent=1)
+        args = ["--player"] if player else []
+        full = os.path.join(out_dir, f"{name}_{steps}_fromfull.bin")
+        subprocess.run([exe, src, str(steps), full] + args, check=True)
+        subprocess.run([exe, dst, str(steps), os.path.join(out_dir, f"{name}_{steps}.bin")] + args, check=True)
+        assert open(full, "rb").read() == open(os.path.join(out_dir, f"{name}_{steps}.bin"), "rb").read(), "reduction changed the workload"
+        os.remove(full)
+
+
+if __name__ == "__main__":
+    make_scene_fixtures()
