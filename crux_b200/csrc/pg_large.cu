@@ -1,22 +1,949 @@
-// pg_large.cu -- one large world (uniform-grid broadphase).  PLACEHOLDER entry points: the
-// pipeline lands in the next commit; until then every call reports PG_ERR_UNSUPPORTED loudly.
+// pg_large.cu -- physics_step for ONE large world of dynamic spheres + static planes (configs C2, C4).
+//
+// The reference visits all N(N-1) ordered pairs in array order, mutating bodies in place
+// (world.c:473-554).  Here the same RESULT is produced without the quadratic sweep and without
+// giving up the solve order:
+//
+//   1. pass 3 (spheres x planes) touches only the sphere -> one thread per sphere           [k_pass3]
+//   2. uniform grid over the post-pass-3 centres; every body carries an envelope
+//        env = r + 2 (|v| + g dt) dt (1+eps)
+//      that bounds where it can be, plus how far interval_collision can reach from there, at ANY
+//      moment of pass 4 as long as no contact changes it.  Two bodies whose envelopes do not
+//      touch can never pass the root test of interval_collision (world.c:559-565), so only pairs
+//      from the 27-cell neighbourhood with touching envelopes are candidates.
+//                                           [k_cell_count, scan, k_scatter (counting sort), k_pairs]
+//   3. ORDER-PRESERVING FIXED POINT.  Each body keeps a timeline: the contacts it has suffered so
+//      far, keyed by (row, column) = the position of the visit in the reference's sweep, with the
+//      state they left behind.  Every candidate pair is evaluated as its two visits (i,j) and (j,i)
+//      on the states the timelines imply AT THAT KEY (including whether the body's own row, hence
+//      its integration, lies before the key).  The hits found form the next timelines; iterate
+//      until nothing changes.  The earliest event of the true sequential sweep is found in the
+//      first iteration and never changes again; by induction iteration k fixes the k-th link of
+//      every dependency chain, so the fixed point IS the sequential result -- bit for bit, since
+//      every visit runs the exact arithmetic of pg_math.cuh.               [k_eval, k_check]
+//   4. envelopes are re-validated against the final timelines (a contact may have sped a body
+//      up); if one grew, candidates are regenerated and the fixed point repeated.  [k_check, host loop]
+//   5. final state = timeline tail, integrated if the body's own row came after it.        [k_finalize]
+//
+// Steps 2 and 5 are the streaming, HBM-bound kernels of SURVEY.md section 8(d).
 #include "pg_common.cuh"
+#include "pg_math.cuh"
+#include "pg_sphere_exact.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace {
+
+using pgm::V3;
+using pgm::v3;
+using pgs::Sphere;
+
+constexpr int kMaxPlanesL = 16;
+constexpr int kTimeline = 4;            // contacts per body per step the timelines can hold
+constexpr int kMaxIter = 24;
+constexpr int kMaxRounds = 4;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+enum { K_PASS3 = 0, K_BOUNDS, K_CELLS, K_SCAN, K_SCATTER, K_PAIRS, K_EVAL, K_CHECK, K_FINAL, K_COUNT };
+const char *kKernelNames[K_COUNT] = {"k_pass3", "k_bounds", "k_cell_count", "k_scan", "k_scatter", "k_pairs", "k_eval", "k_check", "k_finalize"};
+
+struct GridParams {
+  float org[3];
+  float inv_h;
+  int dim[3];
+  int n_cells;
+  int ok;
+};
+
+struct Flags {
+  int changed;            // fixed point: some timeline differs from the previous iteration
+  int grew;               // an envelope had to grow
+  int overflow_pairs;
+  int overflow_timeline;
+  int unsafe;             // non-finite state or an envelope the grid cannot hold
+  unsigned long long n_pairs;
+  unsigned long long n_hits;
+  float max_env_bits_pad;
+};
+
+struct LargeView {
+  int n, ns;
+  float4 *pos_rest, *vel_rad;        // state (in/out), body order = reference array order
+  float4 *planes;
+  float restitution;
+  float *env;                        // envelope radius per body
+  // reductions
+  unsigned *bbox;                    // 6 ordered-uint encodings: min xyz, max xyz ; [6] = max env
+  GridParams *grid;
+  // grid
+  unsigned *cell_of;                 // [n]
+  unsigned *cell_cnt;                // [cells_cap + 1]  counts -> exclusive starts
+  unsigned *cell_fill;               // [cells_cap]
+  unsigned *block_sums;              // scan scratch
+  int cells_cap;
+  unsigned *sorted_idx;              // [n]
+  float4 *sorted_cenv;               // [n]  centre xyz, env
+  // candidates
+  int2 *pairs;
+  long long pairs_cap;
+  // timelines, double buffered
+  unsigned char *tl_cnt[2];
+  unsigned long long *tl_key[2];
+  float4 *tl_pos[2], *tl_vel[2];
+  Flags *flags;
+  // events
+  PgEvent *events;
+  int *n_events;
+  int max_events;
+  float leaf_lo, leaf_hi;
+};
+
+// order-preserving float <-> uint for atomicMin/Max
+__device__ __forceinline__ unsigned f2o(float f) { unsigned u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
+__host__ __device__ __forceinline__ float o2f(unsigned o) {
+  unsigned u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+__device__ __forceinline__ void emit_event(const LargeView &v, int step, int pass, int ac, int ai, int bc, int bi) {
+  if (v.max_events <= 0) return;
+  int slot = atomicAdd(v.n_events, 1);
+  if (slot >= v.max_events) return;
+  PgEvent e;
+  e.world = 0; e.step = step; e.event_type = 0;
+  e.a_class = ac; e.a_index = ai; e.b_class = bc; e.b_index = bi;
+  e.pad_ = pass << 8;
+  v.events[slot] = e;
+}
+
+__device__ __forceinline__ float envelope(float r, float vx, float vy, float vz, float dt) {
+  // r + 2 (|v| + g dt) dt, rounded up: displacement of one integration + the predicate's reach
+  const float sp = sqrtf(__fmaf_rn(vx, vx, __fmaf_rn(vy, vy, vz * vz)));
+  return (r + 2.0f * (sp + pgm::kGravity * dt) * dt) * 1.0002f + 2.0e-6f;
+}
+
+// ---------------------------------------------------------------- 1. pass 3 + envelope + bounds
+__global__ void k_pass3(LargeView v, float dt, int step, int do_planes) {
+  __shared__ float4 s_pl[kMaxPlanesL];
+  if (threadIdx.x < v.ns) s_pl[threadIdx.x] = v.planes[threadIdx.x];
+  __syncthreads();
+  pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
+  const bool gate_ok = dt > 1.0e-9f;
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f}, emax = 0.0f;
+  bool bad = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
+    float4 p = v.pos_rest[i], q = v.vel_rad[i];
+    if (do_planes) {
+      bool touched = false;
+      for (int k = 0; k < v.ns; k++) {
+        const float4 pl = s_pl[k];
+        const float rho = pgs::reach(q.w, q.x, q.y, q.z, dt);
+        const float s0 = __fmaf_rn(p.x, pl.x, __fmaf_rn(p.y, pl.y, p.z * pl.z)) - pl.w;
+        if (gate_ok && fabsf(s0) > rho * 1.0001f + 1.0e-5f * (fabsf(s0) + fabsf(pl.w) + 1.0f)) continue;
+        Sphere A;
+        A.px = p.x; A.py = p.y; A.pz = p.z; A.vx = q.x; A.vy = q.y; A.vz = q.z; A.r = q.w; A.rest = 0;
+        if (pgs::sphere_plane_exact(A, pl, v.restitution, dt, leaf)) {
+          p.x = A.px; p.y = A.py; p.z = A.pz; q.x = A.vx; q.y = A.vy; q.z = A.vz;
+          if (A.rest) p.w = 1.0f;
+          touched = true;
+          emit_event(v, step, 3, PG_CLASS_DYNAMIC, i, PG_CLASS_STATIC, k);
+        }
+      }
+      if (touched) { v.pos_rest[i] = p; v.vel_rad[i] = q; }
+    }
+    const float e = envelope(q.w, q.x, q.y, q.z, dt);
+    v.env[i] = e;
+    v.tl_cnt[0][i] = 0;
+    v.tl_cnt[1][i] = 0;
+    if (!(fabsf(p.x) < 1.0e15f && fabsf(p.y) < 1.0e15f && fabsf(p.z) < 1.0e15f && e < 1.0e15f)) { bad = true; continue; }
+    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    emax = fmaxf(emax, e);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int k = 0; k < 3; k++) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(kFullMask, lo[k], o));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(kFullMask, hi[k], o));
+    }
+    emax = fmaxf(emax, __shfl_xor_sync(kFullMask, emax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    for (int k = 0; k < 3; k++) { atomicMin(v.bbox + k, f2o(lo[k])); atomicMax(v.bbox + 3 + k, f2o(hi[k])); }
+    atomicMax(v.bbox + 6, f2o(emax));
+  }
+  if (bad) atomicExch(&v.flags->unsafe, 1);
+}
+
+// Recompute only the bounds (after envelopes grew, or for the frozen-state pair query).
+__global__ void k_bounds(LargeView v) {
+  float emax = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) emax = fmaxf(emax, v.env[i]);
+  for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(kFullMask, emax, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(v.bbox + 6, f2o(emax));
+}
+
+__global__ void k_grid_params(LargeView v) {
+  GridParams g;
+  float lo[3], hi[3];
+  for (int k = 0; k < 3; k++) { lo[k] = o2f(v.bbox[k]); hi[k] = o2f(v.bbox[3 + k]); }
+  const float emax = o2f(v.bbox[6]);
+  // cell edge: two envelopes (one per body of a pair) with 25 % head room for envelopes that grow
+  float h = 2.0f * emax * 1.25f + 1.0e-6f;
+  g.ok = 1;
+  if (!(h > 0.0f) || !(h < 1.0e15f) || !(lo[0] <= hi[0])) { g.ok = 0; h = 1.0f; lo[0] = lo[1] = lo[2] = 0.0f; hi[0] = hi[1] = hi[2] = 0.0f; }
+  for (;;) {
+    double cells = 1.0;
+    for (int k = 0; k < 3; k++) {
+      double d = floor(((double)hi[k] - (double)lo[k]) / (double)h) + 2.0;
+      g.dim[k] = (int)fmin(d, 2.0e9);
+      cells *= d;
+    }
+    if (cells <= (double)v.cells_cap) { g.n_cells = g.dim[0] * g.dim[1] * g.dim[2]; break; }
+    h *= 1.26f;                                // too many cells for the table: coarser grid (still conservative)
+  }
+  for (int k = 0; k < 3; k++) g.org[k] = lo[k] - 0.5f * h * 0.001f;
+  g.inv_h = 1.0f / h;
+  *v.grid = g;
+}
+
+__device__ __forceinline__ int3 cell_coords(const GridParams &g, float x, float y, float z) {
+  int3 c;
+  c.x = min(max((int)((x - g.org[0]) * g.inv_h), 0), g.dim[0] - 1);
+  c.y = min(max((int)((y - g.org[1]) * g.inv_h), 0), g.dim[1] - 1);
+  c.z = min(max((int)((z - g.org[2]) * g.inv_h), 0), g.dim[2] - 1);
+  return c;
+}
+
+// ---------------------------------------------------------------- 2. counting sort into cells
+__global__ void k_cell_count(LargeView v) {
+  const GridParams g = *v.grid;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
+    const float4 p = v.pos_rest[i];
+    const int3 c = cell_coords(g, p.x, p.y, p.z);
+    const unsigned cell = (unsigned)((c.z * g.dim[1] + c.y) * g.dim[0] + c.x);
+    v.cell_of[i] = cell;
+    atomicAdd(v.cell_cnt + cell, 1u);
+  }
+}
+
+// exclusive scan of cell_cnt[0..n_cells] in three launches (block sums, scan of sums, add)
+constexpr int kScanBlock = 1024;
+constexpr int kScanItems = 4;
+__global__ void k_scan_local(LargeView v) {
+  __shared__ unsigned s_warp[32];
+  const int n = v.grid->n_cells + 1;
+  const int base = blockIdx.x * kScanBlock * kScanItems + threadIdx.x * kScanItems;
+  unsigned x[kScanItems], sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) { x[k] = (base + k < n) ? v.cell_cnt[base + k] : 0u; sum += x[k]; }
+  unsigned incl = sum;
+  for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(kFullMask, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    unsigned w = s_warp[threadIdx.x], wi = w;
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(kFullMask, wi, o); if (threadIdx.x >= o) wi += t; }
+    s_warp[threadIdx.x] = wi - w;
+    if (threadIdx.x == 31) v.block_sums[blockIdx.x] = wi;
+  }
+  __syncthreads();
+  unsigned excl = incl - sum + s_warp[threadIdx.x >> 5];
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) { if (base + k < n) v.cell_cnt[base + k] = excl; excl += x[k]; }
+}
+__global__ void k_scan_sums(LargeView v, int n_blocks) {
+  // single block: serial over chunks of 1024 block sums (n_blocks <= a few thousand)
+  __shared__ unsigned s_warp[32];
+  __shared__ unsigned s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_blocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    unsigned x = i < n_blocks ? v.block_sums[i] : 0u, incl = x;
+    for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(kFullMask, incl, o); if ((threadIdx.x & 31) >= o) incl += t; }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      unsigned w = s_warp[threadIdx.x], wi = w;
+      for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(kFullMask, wi, o); if (threadIdx.x >= o) wi += t; }
+      s_warp[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    const unsigned excl = incl - x + s_warp[threadIdx.x >> 5] + s_carry;
+    if (i < n_blocks) v.block_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = excl + x;
+    __syncthreads();
+  }
+}
+__global__ void k_scan_add(LargeView v) {
+  const int n = v.grid->n_cells + 1;
+  const unsigned add = v.block_sums[blockIdx.x];
+  const int base = blockIdx.x * kScanBlock * kScanItems + threadIdx.x * kScanItems;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) if (base + k < n) { v.cell_cnt[base + k] += add; if (base + k < n - 1) v.cell_fill[base + k] = 0u; }
+}
+
+__global__ void k_scatter(LargeView v) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
+    const unsigned cell = v.cell_of[i];
+    const unsigned slot = v.cell_cnt[cell] + atomicAdd(v.cell_fill + cell, 1u);
+    const float4 p = v.pos_rest[i];
+    v.sorted_idx[slot] = (unsigned)i;
+    v.sorted_cenv[slot] = make_float4(p.x, p.y, p.z, v.env[i]);
+  }
+}
+
+// ---------------------------------------------------------------- candidate pairs (27 cells = 9 x-runs)
+__global__ void k_pairs(LargeView v) {
+  const GridParams g = *v.grid;
+  const int lane = threadIdx.x & 31;
+  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < ((v.n + 31) & ~31); a += gridDim.x * blockDim.x) {
+    const bool live = a < v.n;
+    float4 ca = make_float4(0, 0, 0, 0);
+    unsigned ia = 0;
+    int3 c = make_int3(0, 0, 0);
+    if (live) { ca = v.sorted_cenv[a]; ia = v.sorted_idx[a]; c = cell_coords(g, ca.x, ca.y, ca.z); }
+    for (int dz = -1; dz <= 1; dz++) {
+      for (int dy = -1; dy <= 1; dy++) {
+        unsigned b0 = 0, b1 = 0;
+        const int y = c.y + dy, z = c.z + dz;
+        if (live && y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
+          const int x0 = max(c.x - 1, 0), x1 = min(c.x + 1, g.dim[0] - 1);
+          const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+          b0 = v.cell_cnt[row + x0];
+          b1 = v.cell_cnt[row + x1 + 1];
+        }
+        // lanes walk their runs together; appends are warp-aggregated
+        for (unsigned b = b0; __any_sync(kFullMask, b < b1); b++) {
+          bool hit = false;
+          unsigned ib = 0;
+          if (b < b1) {
+            const float4 cb = v.sorted_cenv[b];
+            ib = v.sorted_idx[b];
+            const float dx = ca.x - cb.x, dyy = ca.y - cb.y, dzz = ca.z - cb.z;
+            const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
+            const float T = ca.w + cb.w;
+            hit = (ia < ib) && (d2 <= T * T);
+          }
+          const unsigned m = __ballot_sync(kFullMask, hit);
+          if (m) {
+            unsigned long long base = 0;
+            if (lane == __ffs(m) - 1) base = atomicAdd(&v.flags->n_pairs, (unsigned long long)__popc(m));
+            base = __shfl_sync(kFullMask, base, __ffs(m) - 1);
+            if (hit) {
+              const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+              if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2((int)ia, (int)ib);
+              else atomicExch(&v.flags->overflow_pairs, 1);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- 3. fixed point over timelines
+struct BodyState { float px, py, pz, vx, vy, vz; };
+
+// State of body b just before the visit with key (row, col): post-pass-3 state, then the latest
+// timeline entry with a smaller key, then the body's own integration if its row lies between.
+__device__ __forceinline__ BodyState state_at(const LargeView &v, int src, int b, unsigned long long key, float dt, float *radius) {
+  const float4 p = v.pos_rest[b], q = v.vel_rad[b];
+  BodyState s;
+  s.px = p.x; s.py = p.y; s.pz = p.z; s.vx = q.x; s.vy = q.y; s.vz = q.z;
+  *radius = q.w;
+  long long last_row = -1;
+  const int cnt = min((int)v.tl_cnt[src][b], kTimeline);
+  unsigned long long best = 0;
+  int best_k = -1;
+  for (int k = 0; k < cnt; k++) {
+    const unsigned long long kk = v.tl_key[src][(size_t)b * kTimeline + k];
+    if (kk < key && (best_k < 0 || kk > best)) { best = kk; best_k = k; }
+  }
+  if (best_k >= 0) {
+    const float4 tp = v.tl_pos[src][(size_t)b * kTimeline + best_k], tv = v.tl_vel[src][(size_t)b * kTimeline + best_k];
+    s.px = tp.x; s.py = tp.y; s.pz = tp.z; s.vx = tv.x; s.vy = tv.y; s.vz = tv.z;
+    last_row = (long long)(best >> 32);
+  }
+  const long long row = (long long)(key >> 32);
+  if (row > b && last_row <= b && p.w == 0.0f) {            // own row finished in between: integrate (world.c:549-553)
+    V3 pp = v3(s.px, s.py, s.pz), vv = v3(s.vx, s.vy, s.vz);
+    pgm::integrate(pp, vv, dt);
+    s.px = pp.x; s.py = pp.y; s.pz = pp.z; s.vx = vv.x; s.vy = vv.y; s.vz = vv.z;
+  }
+  return s;
+}
+
+__device__ __forceinline__ void timeline_push(const LargeView &v, int dst, int b, unsigned long long key, const Sphere &s) {
+  // tl_cnt is a byte array; claim a slot with a 32-bit CAS on the containing word
+  unsigned *word = (unsigned *)(v.tl_cnt[dst] + (b & ~3));
+  const int sh = (b & 3) * 8;
+  unsigned old = *word, assumed;
+  int slot;
+  do {
+    assumed = old;
+    slot = (int)((assumed >> sh) & 0xffu);
+    if (slot >= 250) break;
+    old = atomicCAS(word, assumed, assumed + (1u << sh));
+  } while (old != assumed);
+  if (slot >= kTimeline) { atomicExch(&v.flags->overflow_timeline, 1); return; }
+  v.tl_key[dst][(size_t)b * kTimeline + slot] = key;
+  v.tl_pos[dst][(size_t)b * kTimeline + slot] = make_float4(s.px, s.py, s.pz, 0.0f);
+  v.tl_vel[dst][(size_t)b * kTimeline + slot] = make_float4(s.vx, s.vy, s.vz, 0.0f);
+}
+
+__device__ __forceinline__ void eval_visit(const LargeView &v, int src, int dst, int row, int col, float dt, pgm::LeafLen leaf) {
+  const unsigned long long key = ((unsigned long long)(unsigned)row << 32) | (unsigned)col;
+  float ra, rb;
+  const BodyState a = state_at(v, src, row, key, dt, &ra), b = state_at(v, src, col, key, dt, &rb);
+  Sphere A, B;
+  A.px = a.px; A.py = a.py; A.pz = a.pz; A.vx = a.vx; A.vy = a.vy; A.vz = a.vz; A.r = ra; A.rest = 0;
+  B.px = b.px; B.py = b.py; B.pz = b.pz; B.vx = b.vx; B.vy = b.vy; B.vz = b.vz; B.r = rb; B.rest = 0;
+  if (!pgs::sphere_pair_exact(A, B, dt, leaf)) return;
+  timeline_push(v, dst, row, key, A);
+  timeline_push(v, dst, col, key, B);
+  atomicAdd(&v.flags->n_hits, 1ull);
+}
+
+__global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) {
+  pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
+  const long long np = (long long)min((unsigned long long)v.pairs_cap, v.flags->n_pairs);
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < np; k += (long long)gridDim.x * blockDim.x) {
+    const int2 pr = v.pairs[k];
+    // a pair whose bodies both had empty timelines was evaluated on unchanged inputs before: skip
+    if (iter > 0 && v.tl_cnt[src][pr.x] == 0 && v.tl_cnt[src][pr.y] == 0) continue;
+    eval_visit(v, src, dst, pr.x, pr.y, dt, leaf);     // visit (i, j) of row i
+    eval_visit(v, src, dst, pr.y, pr.x, dt, leaf);     // visit (j, i) of row j
+  }
+}
+
+// Compare timelines of two iterations (as sorted-by-key sequences) and validate envelopes.
+__global__ void k_check(LargeView v, int src, int dst, float dt) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < v.n; b += gridDim.x * blockDim.x) {
+    const int c0 = min((int)v.tl_cnt[src][b], kTimeline), c1 = min((int)v.tl_cnt[dst][b], kTimeline);
+    if (c0 == 0 && c1 == 0) continue;
+    bool same = (v.tl_cnt[src][b] == v.tl_cnt[dst][b]);
+    if (same) {
+      for (int k = 0; k < c1 && same; k++) {
+        const unsigned long long key = v.tl_key[dst][(size_t)b * kTimeline + k];
+        bool found = false;
+        for (int m = 0; m < c0; m++) {
+          if (v.tl_key[src][(size_t)b * kTimeline + m] != key) continue;
+          const float4 p0 = v.tl_pos[src][(size_t)b * kTimeline + m], p1 = v.tl_pos[dst][(size_t)b * kTimeline + k];
+          const float4 q0 = v.tl_vel[src][(size_t)b * kTimeline + m], q1 = v.tl_vel[dst][(size_t)b * kTimeline + k];
+          found = __float_as_uint(p0.x) == __float_as_uint(p1.x) && __float_as_uint(p0.y) == __float_as_uint(p1.y) &&
+                  __float_as_uint(p0.z) == __float_as_uint(p1.z) && __float_as_uint(q0.x) == __float_as_uint(q1.x) &&
+                  __float_as_uint(q0.y) == __float_as_uint(q1.y) && __float_as_uint(q0.z) == __float_as_uint(q1.z);
+          break;
+        }
+        same = found;
+      }
+    }
+    if (!same) v.flags->changed = 1;
+    // envelope validation on the new timeline: every state the body takes must stay inside env[b]
+    const float4 p = v.pos_rest[b], q = v.vel_rad[b];
+    float need = 0.0f;
+    for (int k = 0; k < c1; k++) {
+      const unsigned long long key = v.tl_key[dst][(size_t)b * kTimeline + k];
+      const float4 tp = v.tl_pos[dst][(size_t)b * kTimeline + k], tv = v.tl_vel[dst][(size_t)b * kTimeline + k];
+      const float dx = tp.x - p.x, dy = tp.y - p.y, dz = tp.z - p.z;
+      const float dev = sqrtf(dx * dx + dy * dy + dz * dz);
+      const float sp = sqrtf(tv.x * tv.x + tv.y * tv.y + tv.z * tv.z);
+      const bool before_own_row = (long long)(key >> 32) <= (long long)b;
+      // before its own row the body will still be integrated once: one more displacement and speed bump
+      const float reach = before_own_row ? 2.0f * (sp + pgm::kGravity * dt) * dt : sp * dt;
+      need = fmaxf(need, (q.w + dev + reach) * 1.0002f + 2.0e-6f);
+    }
+    if (need > v.env[b]) {
+      v.env[b] = need * 1.05f;
+      v.flags->grew = 1;
+      if (!(need < 1.0e15f)) v.flags->unsafe = 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- 5. final state + pass-4 events
+__global__ void k_finalize(LargeView v, int src, float dt, int step) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < v.n; b += gridDim.x * blockDim.x) {
+    float4 p = v.pos_rest[b], q = v.vel_rad[b];
+    const int cnt = min((int)v.tl_cnt[src][b], kTimeline);
+    long long last_row = -1;
+    if (cnt > 0) {
+      unsigned long long best = 0; int best_k = -1;
+      for (int k = 0; k < cnt; k++) {
+        const unsigned long long kk = v.tl_key[src][(size_t)b * kTimeline + k];
+        if (best_k < 0 || kk > best) { best = kk; best_k = k; }
+        if ((int)(kk >> 32) == b) emit_event(v, step, 4, PG_CLASS_DYNAMIC, b, PG_CLASS_DYNAMIC, (int)(kk & 0xffffffffu));
+      }
+      const float4 tp = v.tl_pos[src][(size_t)b * kTimeline + best_k], tv = v.tl_vel[src][(size_t)b * kTimeline + best_k];
+      p.x = tp.x; p.y = tp.y; p.z = tp.z; q.x = tv.x; q.y = tv.y; q.z = tv.z;
+      last_row = (long long)(best >> 32);
+    }
+    if (last_row <= b && p.w == 0.0f) {
+      V3 pp = v3(p.x, p.y, p.z), vv = v3(q.x, q.y, q.z);
+      pgm::integrate(pp, vv, dt);
+      p.x = pp.x; p.y = pp.y; p.z = pp.z; q.x = vv.x; q.y = vv.y; q.z = vv.z;
+    }
+    v.pos_rest[b] = p;
+    v.vel_rad[b] = q;
+  }
+}
+
+// ---------------------------------------------------------------- frozen-state broadphase pairs
+__global__ void k_env_frozen(LargeView v, float dt) {
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f}, emax = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
+    const float4 p = v.pos_rest[i], q = v.vel_rad[i];
+    const float e = pgs::reach(q.w, q.x, q.y, q.z, dt);      // r + |v| dt: the predicate's own reach, nothing moves
+    v.env[i] = e;
+    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    emax = fmaxf(emax, e);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    for (int k = 0; k < 3; k++) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(kFullMask, lo[k], o));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(kFullMask, hi[k], o));
+    }
+    emax = fmaxf(emax, __shfl_xor_sync(kFullMask, emax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    for (int k = 0; k < 3; k++) { atomicMin(v.bbox + k, f2o(lo[k])); atomicMax(v.bbox + 3 + k, f2o(hi[k])); }
+    atomicMax(v.bbox + 6, f2o(emax));
+  }
+}
+__global__ void k_pairs_exact(LargeView v, float dt, unsigned char *keep) {
+  pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
+  const long long np = (long long)min((unsigned long long)v.pairs_cap, v.flags->n_pairs);
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < np; k += (long long)gridDim.x * blockDim.x) {
+    const int2 pr = v.pairs[k];
+    const float4 pa = v.pos_rest[pr.x], qa = v.vel_rad[pr.x], pb = v.pos_rest[pr.y], qb = v.vel_rad[pr.y];
+    const V3 cA = v3(0.0f + pa.x, 0.0f + pa.y, 0.0f + pa.z), cB = v3(0.0f + pb.x, 0.0f + pb.y, 0.0f + pb.z);
+    const V3 vA = v3(qa.x, qa.y, qa.z), vB = v3(qb.x, qb.y, qb.z);
+    keep[k] = pgm::ss_interval(cA, vA, pgm::norm(vA), cB, vB, pgm::norm(vB), qa.w + qb.w, 0.0f, dt, leaf) ? 1 : 0;
+  }
+}
+
+}  // namespace
+
+// ==================================================================== host side
+
+struct PgLarge {
+  int device;
+  int cap_n, cap_static;
+  LargeView v;
+  cudaStream_t stream;
+  cudaEvent_t ev0, ev1;
+  cudaEvent_t kev[K_COUNT][2];
+  float kms[K_COUNT];
+  long long launches;
+  int sm_count;
+  double *d_stats;
+  float *d_stage_pos, *d_stage_vel;
+  unsigned char *d_stage_rest;
+  int last_iterations, last_proven;
+  long long last_candidates, last_hits;
+  int step_in_call;
+};
+
+#define LW_LAUNCH(w, kid, kern, grid, block, ...)                                 \
+  do {                                                                            \
+    cudaEventRecord((w)->kev[kid][0], (w)->stream);                               \
+    kern<<<(grid), (block), 0, (w)->stream>>>(__VA_ARGS__);                       \
+    cudaEventRecord((w)->kev[kid][1], (w)->stream);                               \
+    (w)->launches++;                                                              \
+  } while (0)
+
+static int lw_grid(const PgLarge *w, int n, int block) { return std::max(1, std::min((n + block - 1) / block, w->sm_count * 8)); }
+
+static void lw_accumulate(PgLarge *w, int kid) {
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, w->kev[kid][0], w->kev[kid][1]) == cudaSuccess) w->kms[kid] += ms;
+}
+
+// build grid + candidate pairs from v.env / current positions
+static int lw_build_pairs(PgLarge *w) {
+  LargeView &v = w->v;
+  k_grid_params<<<1, 1, 0, w->stream>>>(v);
+  w->launches++;
+  PG_CUDA(cudaMemsetAsync(v.cell_cnt, 0, sizeof(unsigned) * ((size_t)v.cells_cap + 1), w->stream));
+  PG_CUDA(cudaMemsetAsync(&v.flags->n_pairs, 0, sizeof(unsigned long long), w->stream));
+  LW_LAUNCH(w, K_CELLS, k_cell_count, lw_grid(w, v.n, 256), 256, v);
+  GridParams g;
+  PG_CUDA(cudaMemcpyAsync(&g, v.grid, sizeof(g), cudaMemcpyDeviceToHost, w->stream));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  lw_accumulate(w, K_CELLS);
+  if (!g.ok) { pg_set_error("large world: non-finite state, grid cannot be built"); return PG_ERR_ARG; }
+  const int scan_blocks = (g.n_cells + 1 + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems);
+  cudaEventRecord(w->kev[K_SCAN][0], w->stream);
+  k_scan_local<<<scan_blocks, kScanBlock, 0, w->stream>>>(v);
+  k_scan_sums<<<1, 1024, 0, w->stream>>>(v, scan_blocks);
+  k_scan_add<<<scan_blocks, kScanBlock, 0, w->stream>>>(v);
+  cudaEventRecord(w->kev[K_SCAN][1], w->stream);
+  w->launches += 3;
+  LW_LAUNCH(w, K_SCATTER, k_scatter, lw_grid(w, v.n, 256), 256, v);
+  LW_LAUNCH(w, K_PAIRS, k_pairs, lw_grid(w, v.n, 128), 128, v);
+  PG_CUDA(cudaGetLastError());
+  return PG_OK;
+}
+
+static int lw_read_flags(PgLarge *w, Flags *f) {
+  PG_CUDA(cudaMemcpyAsync(f, w->v.flags, sizeof(Flags), cudaMemcpyDeviceToHost, w->stream));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  return PG_OK;
+}
+
+static int lw_step_once(PgLarge *w, float dt_in) {
+  LargeView &v = w->v;
+  float dt = dt_in;
+  if ((double)dt > 0.01666) dt = (float)0.01666;
+  pg_leaf_lengths(0.0f, dt, &v.leaf_lo, &v.leaf_hi);
+  const unsigned bbox_init[7] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u};
+  PG_CUDA(cudaMemcpyAsync(v.bbox, bbox_init, sizeof(bbox_init), cudaMemcpyHostToDevice, w->stream));
+  PG_CUDA(cudaMemsetAsync(v.flags, 0, sizeof(Flags), w->stream));
+  LW_LAUNCH(w, K_PASS3, k_pass3, lw_grid(w, v.n, 256), 256, v, dt, w->step_in_call, 1);
+  w->last_proven = 1;
+  w->last_iterations = 0;
+  int src = 0;
+  for (int round = 0; round < kMaxRounds; round++) {
+    int rc = lw_build_pairs(w);
+    if (rc) return rc;
+    Flags f;
+    int dst = 1;
+    src = 0;
+    bool converged = false;
+    for (int it = 0; it < kMaxIter; it++) {
+      PG_CUDA(cudaMemsetAsync(v.tl_cnt[dst], 0, (size_t)v.n + 4, w->stream));
+      PG_CUDA(cudaMemsetAsync(&v.flags->changed, 0, sizeof(int), w->stream));
+      PG_CUDA(cudaMemsetAsync(&v.flags->n_hits, 0, sizeof(unsigned long long), w->stream));
+      if (it == 0) {
+        rc = lw_read_flags(w, &f);          // pair count: size the eval grid, detect overflow
+        if (rc) return rc;
+        lw_accumulate(w, K_PASS3); lw_accumulate(w, K_SCAN); lw_accumulate(w, K_SCATTER); lw_accumulate(w, K_PAIRS);
+        if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
+        if (f.unsafe) { pg_set_error("large world: non-finite body state"); return PG_ERR_ARG; }
+        w->last_candidates = (long long)f.n_pairs;
+      }
+      const int np = (int)std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
+      LW_LAUNCH(w, K_EVAL, k_eval, lw_grid(w, std::max(np, 1), 128), 128, v, src, dst, it, dt);
+      LW_LAUNCH(w, K_CHECK, k_check, lw_grid(w, v.n, 256), 256, v, src, dst, dt);
+      Flags g;
+      rc = lw_read_flags(w, &g);
+      if (rc) return rc;
+      lw_accumulate(w, K_EVAL); lw_accumulate(w, K_CHECK);
+      w->last_iterations++;
+      w->last_hits = (long long)g.n_hits;
+      if (g.overflow_timeline) { pg_set_error("large world: more than %d contacts on one body in one step", kTimeline); return PG_ERR_CAPACITY; }
+      std::swap(src, dst);
+      f = g;
+      if (!g.changed) { converged = true; break; }
+    }
+    if (!converged) w->last_proven = 0;
+    if (!f.grew) break;
+    if (round == kMaxRounds - 1) { w->last_proven = 0; break; }
+    // envelopes grew: regenerate candidates with the new envelopes and redo the fixed point
+    const unsigned zero = 0;
+    PG_CUDA(cudaMemcpyAsync(v.bbox + 6, &zero, sizeof(unsigned), cudaMemcpyHostToDevice, w->stream));
+    PG_CUDA(cudaMemsetAsync(&v.flags->grew, 0, sizeof(int), w->stream));
+    PG_CUDA(cudaMemsetAsync(v.tl_cnt[0], 0, (size_t)v.n + 4, w->stream));
+    PG_CUDA(cudaMemsetAsync(v.tl_cnt[1], 0, (size_t)v.n + 4, w->stream));
+    LW_LAUNCH(w, K_BOUNDS, k_bounds, lw_grid(w, v.n, 256), 256, v);
+  }
+  LW_LAUNCH(w, K_FINAL, k_finalize, lw_grid(w, v.n, 256), 256, v, src, dt, w->step_in_call);
+  PG_CUDA(cudaGetLastError());
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  lw_accumulate(w, K_FINAL);
+  return PG_OK;
+}
 
 extern "C" {
-PgLarge *pg_large_create(int, int, int) { pg_set_error("pg_large_*: not built yet"); return nullptr; }
-void pg_large_destroy(PgLarge *) {}
-int pg_large_set(PgLarge *, const PgBody *, int, int, const float *, const float *, const float *, float, float) { return PG_ERR_UNSUPPORTED; }
-int pg_large_upload_state(PgLarge *, const float *, const float *, const uint8_t *) { return PG_ERR_UNSUPPORTED; }
-int pg_large_download_state(PgLarge *, float *, float *, uint8_t *) { return PG_ERR_UNSUPPORTED; }
-int pg_large_step(PgLarge *, float, int) { return PG_ERR_UNSUPPORTED; }
-int pg_large_sync(PgLarge *) { return PG_ERR_UNSUPPORTED; }
-long long pg_large_pairs(PgLarge *, float, int32_t *, long long) { return PG_ERR_UNSUPPORTED; }
-long long pg_large_events(PgLarge *, PgEvent *, long long, int *) { return PG_ERR_UNSUPPORTED; }
-int pg_large_stats(PgLarge *, PgStats *, void *) { return PG_ERR_UNSUPPORTED; }
-long long pg_large_launches(const PgLarge *) { return 0; }
-float pg_large_last_step_ms(PgLarge *) { return -1.0f; }
-int pg_large_kernel_count(void) { return 0; }
-const char *pg_large_kernel_name(int) { return ""; }
-float pg_large_kernel_ms(PgLarge *, int) { return -1.0f; }
-int pg_large_exactness(PgLarge *, int *, int *, long long *, long long *) { return PG_ERR_UNSUPPORTED; }
+
+PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
+  if (max_spheres <= 0 || max_static < 0 || max_static > kMaxPlanesL) { pg_set_error("pg_large_create: bad argument (at most %d static planes)", kMaxPlanesL); return nullptr; }
+  PG_CUDA_NULL(cudaSetDevice(device));
+  PgLarge *w = new PgLarge();
+  memset(w, 0, sizeof(*w));
+  w->device = device;
+  w->cap_n = max_spheres;
+  w->cap_static = std::max(max_static, 1);
+  cudaDeviceProp prop;
+  PG_CUDA_NULL(cudaGetDeviceProperties(&prop, device));
+  w->sm_count = prop.multiProcessorCount;
+  PG_CUDA_NULL(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+  PG_CUDA_NULL(cudaEventCreate(&w->ev0));
+  PG_CUDA_NULL(cudaEventCreate(&w->ev1));
+  for (int k = 0; k < K_COUNT; k++) { PG_CUDA_NULL(cudaEventCreate(&w->kev[k][0])); PG_CUDA_NULL(cudaEventCreate(&w->kev[k][1])); }
+  LargeView &v = w->v;
+  const size_t n = (size_t)max_spheres;
+  v.cells_cap = (int)std::min<size_t>(4 * n + 4096, (size_t)1 << 28);
+  v.pairs_cap = (long long)(4 * n + 65536);
+  v.max_events = (int)std::max<size_t>(n / 4, 65536);
+  PG_CUDA_NULL(cudaMalloc(&v.pos_rest, sizeof(float4) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.vel_rad, sizeof(float4) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.planes, sizeof(float4) * kMaxPlanesL));
+  PG_CUDA_NULL(cudaMalloc(&v.env, sizeof(float) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.bbox, sizeof(unsigned) * 8));
+  PG_CUDA_NULL(cudaMalloc(&v.grid, sizeof(GridParams)));
+  PG_CUDA_NULL(cudaMalloc(&v.cell_of, sizeof(unsigned) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.cell_cnt, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
+  PG_CUDA_NULL(cudaMalloc(&v.cell_fill, sizeof(unsigned) * (size_t)v.cells_cap));
+  PG_CUDA_NULL(cudaMalloc(&v.block_sums, sizeof(unsigned) * ((size_t)v.cells_cap / (kScanBlock * kScanItems) + 2)));
+  PG_CUDA_NULL(cudaMalloc(&v.sorted_idx, sizeof(unsigned) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.sorted_cenv, sizeof(float4) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.pairs, sizeof(int2) * (size_t)v.pairs_cap));
+  for (int k = 0; k < 2; k++) {
+    PG_CUDA_NULL(cudaMalloc(&v.tl_cnt[k], n + 8));
+    PG_CUDA_NULL(cudaMemset(v.tl_cnt[k], 0, n + 8));
+    PG_CUDA_NULL(cudaMalloc(&v.tl_key[k], sizeof(unsigned long long) * n * kTimeline));
+    PG_CUDA_NULL(cudaMalloc(&v.tl_pos[k], sizeof(float4) * n * kTimeline));
+    PG_CUDA_NULL(cudaMalloc(&v.tl_vel[k], sizeof(float4) * n * kTimeline));
+  }
+  PG_CUDA_NULL(cudaMalloc(&v.flags, sizeof(Flags)));
+  PG_CUDA_NULL(cudaMalloc(&v.events, sizeof(PgEvent) * (size_t)v.max_events));
+  PG_CUDA_NULL(cudaMalloc(&v.n_events, sizeof(int)));
+  PG_CUDA_NULL(cudaMemset(v.n_events, 0, sizeof(int)));
+  PG_CUDA_NULL(cudaMalloc(&w->d_stats, 8 * sizeof(double)));
+  PG_CUDA_NULL(cudaMalloc(&w->d_stage_pos, sizeof(float) * 3 * n));
+  PG_CUDA_NULL(cudaMalloc(&w->d_stage_vel, sizeof(float) * 3 * n));
+  PG_CUDA_NULL(cudaMalloc(&w->d_stage_rest, n));
+  return w;
 }
+
+void pg_large_destroy(PgLarge *w) {
+  if (!w) return;
+  cudaSetDevice(w->device);
+  cudaStreamSynchronize(w->stream);
+  LargeView &v = w->v;
+  void *ptrs[] = {v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.cell_fill, v.block_sums, v.sorted_idx,
+                  v.sorted_cenv, v.pairs, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
+                  v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  cudaEventDestroy(w->ev0); cudaEventDestroy(w->ev1);
+  for (int k = 0; k < K_COUNT; k++) { cudaEventDestroy(w->kev[k][0]); cudaEventDestroy(w->kev[k][1]); }
+  cudaStreamDestroy(w->stream);
+  delete w;
+}
+
+}  // extern "C"
+
+namespace {
+__global__ void k_lw_pack(float4 *pos_rest, float4 *vel_rad, int n, const float *pos, const float *vel, const unsigned char *rest,
+                          const float *radius, float r_uniform, int set_radius) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    pos_rest[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], (rest && rest[i]) ? 1.0f : 0.0f);
+    const float r = set_radius ? (radius ? radius[i] : r_uniform) : vel_rad[i].w;
+    vel_rad[i] = make_float4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], r);
+  }
+}
+__global__ void k_lw_unpack(const float4 *pos_rest, const float4 *vel_rad, int n, float *pos, float *vel, unsigned char *rest) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 a = pos_rest[i], b = vel_rad[i];
+    pos[3 * i] = a.x; pos[3 * i + 1] = a.y; pos[3 * i + 2] = a.z;
+    vel[3 * i] = b.x; vel[3 * i + 1] = b.y; vel[3 * i + 2] = b.z;
+    if (rest) rest[i] = a.w != 0.0f ? 1 : 0;
+  }
+}
+__global__ void k_lw_stats(LargeView v, double *out, double *out2) {
+  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
+    const float4 a = v.pos_rest[i], b = v.vel_rad[i];
+    acc[0] += 1.0;
+    acc[1] += 0.5 * ((double)b.x * b.x + (double)b.y * b.y + (double)b.z * b.z);
+    acc[2] += b.x; acc[3] += b.y; acc[4] += b.z;
+    acc[6] += a.w != 0.0f ? 1.0 : 0.0;
+    const bool fin = isfinite(a.x) && isfinite(a.y) && isfinite(a.z) && isfinite(b.x) && isfinite(b.y) && isfinite(b.z);
+    acc[7] += fin ? 0.0 : 1.0;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) acc[5] += (double)*v.n_events;
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    double x = acc[q];
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFullMask, x, o);
+    if ((threadIdx.x & 31) == 0 && x != 0.0) { atomicAdd(out + q, x); if (out2) atomicAdd(out2 + q, x); }
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int pg_large_set(PgLarge *w, const PgBody *statics, int n_static, int n_spheres, const float *pos, const float *vel,
+                 const float *radius_or_null, float radius, float restitution) {
+  if (!w || n_spheres < 0 || n_spheres > w->cap_n || n_static < 0 || n_static > kMaxPlanesL || !pos || !vel) { pg_set_error("pg_large_set: bad argument"); return PG_ERR_ARG; }
+  for (int i = 0; i < n_static; i++)
+    if (statics[i].collider_type != PG_PLANE) { pg_set_error("pg_large_set: static bodies must be planes"); return PG_ERR_UNSUPPORTED; }
+  PG_CUDA(cudaSetDevice(w->device));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  LargeView &v = w->v;
+  v.n = n_spheres; v.ns = n_static; v.restitution = restitution;
+  float4 pl[kMaxPlanesL];
+  for (int i = 0; i < n_static; i++) pl[i] = make_float4(statics[i].shape[0], statics[i].shape[1], statics[i].shape[2], statics[i].shape[3]);
+  if (n_static) PG_CUDA(cudaMemcpy(v.planes, pl, sizeof(float4) * n_static, cudaMemcpyHostToDevice));
+  const size_t n = (size_t)n_spheres;
+  PG_CUDA(cudaMemcpyAsync(w->d_stage_pos, pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, w->stream));
+  PG_CUDA(cudaMemcpyAsync(w->d_stage_vel, vel, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, w->stream));
+  float *d_rad = nullptr;
+  if (radius_or_null) {
+    PG_CUDA(cudaMalloc(&d_rad, sizeof(float) * n));
+    PG_CUDA(cudaMemcpyAsync(d_rad, radius_or_null, sizeof(float) * n, cudaMemcpyHostToDevice, w->stream));
+  }
+  k_lw_pack<<<lw_grid(w, n_spheres, 256), 256, 0, w->stream>>>(v.pos_rest, v.vel_rad, n_spheres, w->d_stage_pos, w->d_stage_vel, nullptr, d_rad, radius * 1.0f, 1);
+  w->launches++;
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  if (d_rad) cudaFree(d_rad);
+  return PG_OK;
+}
+
+int pg_large_upload_state(PgLarge *w, const float *pos, const float *vel, const uint8_t *at_rest) {
+  if (!w || !pos || !vel) return PG_ERR_ARG;
+  PG_CUDA(cudaSetDevice(w->device));
+  const size_t n = (size_t)w->v.n;
+  PG_CUDA(cudaMemcpyAsync(w->d_stage_pos, pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, w->stream));
+  PG_CUDA(cudaMemcpyAsync(w->d_stage_vel, vel, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, w->stream));
+  if (at_rest) PG_CUDA(cudaMemcpyAsync(w->d_stage_rest, at_rest, n, cudaMemcpyHostToDevice, w->stream));
+  k_lw_pack<<<lw_grid(w, w->v.n, 256), 256, 0, w->stream>>>(w->v.pos_rest, w->v.vel_rad, w->v.n, w->d_stage_pos, w->d_stage_vel,
+                                                              at_rest ? w->d_stage_rest : nullptr, nullptr, 0.0f, 0);
+  w->launches++;
+  PG_CUDA(cudaGetLastError());
+  return PG_OK;
+}
+
+int pg_large_download_state(PgLarge *w, float *pos, float *vel, uint8_t *at_rest) {
+  if (!w || !pos || !vel) return PG_ERR_ARG;
+  PG_CUDA(cudaSetDevice(w->device));
+  const size_t n = (size_t)w->v.n;
+  k_lw_unpack<<<lw_grid(w, w->v.n, 256), 256, 0, w->stream>>>(w->v.pos_rest, w->v.vel_rad, w->v.n, w->d_stage_pos, w->d_stage_vel,
+                                                                at_rest ? w->d_stage_rest : nullptr);
+  w->launches++;
+  PG_CUDA(cudaMemcpyAsync(pos, w->d_stage_pos, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, w->stream));
+  PG_CUDA(cudaMemcpyAsync(vel, w->d_stage_vel, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, w->stream));
+  if (at_rest) PG_CUDA(cudaMemcpyAsync(at_rest, w->d_stage_rest, n, cudaMemcpyDeviceToHost, w->stream));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  return PG_OK;
+}
+
+int pg_large_step(PgLarge *w, float dt, int n_steps) {
+  if (!w || n_steps < 0) return PG_ERR_ARG;
+  PG_CUDA(cudaSetDevice(w->device));
+  PG_CUDA(cudaMemsetAsync(w->v.n_events, 0, sizeof(int), w->stream));
+  for (int k = 0; k < K_COUNT; k++) w->kms[k] = 0.0f;
+  PG_CUDA(cudaEventRecord(w->ev0, w->stream));
+  int rc = PG_OK;
+  for (int s = 0; s < n_steps && rc == PG_OK; s++) { w->step_in_call = s; rc = lw_step_once(w, dt); }
+  PG_CUDA(cudaEventRecord(w->ev1, w->stream));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  return rc;
+}
+
+int pg_large_sync(PgLarge *w) {
+  if (!w) return PG_ERR_ARG;
+  PG_CUDA(cudaSetDevice(w->device));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  return PG_OK;
+}
+
+long long pg_large_pairs(PgLarge *w, float dt_in, int32_t *out_ij, long long cap) {
+  if (!w) return PG_ERR_ARG;
+  if (cudaSetDevice(w->device) != cudaSuccess) return PG_ERR_CUDA;
+  LargeView &v = w->v;
+  float dt = dt_in;
+  if ((double)dt > 0.01666) dt = (float)0.01666;
+  pg_leaf_lengths(0.0f, dt, &v.leaf_lo, &v.leaf_hi);
+  const unsigned bbox_init[7] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u};
+  PG_CUDA(cudaMemcpyAsync(v.bbox, bbox_init, sizeof(bbox_init), cudaMemcpyHostToDevice, w->stream));
+  PG_CUDA(cudaMemsetAsync(v.flags, 0, sizeof(Flags), w->stream));
+  k_env_frozen<<<lw_grid(w, v.n, 256), 256, 0, w->stream>>>(v, dt);
+  w->launches++;
+  int rc = lw_build_pairs(w);
+  if (rc) return rc;
+  Flags f;
+  rc = lw_read_flags(w, &f);
+  if (rc) return rc;
+  if (f.overflow_pairs) { pg_set_error("pg_large_pairs: candidate buffer too small"); return PG_ERR_CAPACITY; }
+  const long long np = (long long)f.n_pairs;
+  if (np == 0) return 0;
+  unsigned char *d_keep = nullptr;
+  PG_CUDA(cudaMalloc(&d_keep, (size_t)np));
+  k_pairs_exact<<<lw_grid(w, (int)np, 128), 128, 0, w->stream>>>(v, dt, d_keep);
+  w->launches++;
+  std::vector<unsigned char> keep((size_t)np);
+  std::vector<int2> pairs((size_t)np);
+  PG_CUDA(cudaMemcpyAsync(keep.data(), d_keep, (size_t)np, cudaMemcpyDeviceToHost, w->stream));
+  PG_CUDA(cudaMemcpyAsync(pairs.data(), v.pairs, sizeof(int2) * (size_t)np, cudaMemcpyDeviceToHost, w->stream));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  cudaFree(d_keep);
+  std::vector<std::pair<int, int>> out;
+  for (long long k = 0; k < np; k++) if (keep[k]) out.emplace_back(pairs[k].x, pairs[k].y);
+  std::sort(out.begin(), out.end());
+  for (size_t k = 0; k < out.size() && (long long)k < cap; k++) { out_ij[2 * k] = out[k].first; out_ij[2 * k + 1] = out[k].second; }
+  return (long long)out.size();
+}
+
+long long pg_large_events(PgLarge *w, PgEvent *out, long long cap, int *overflowed) {
+  if (!w) return PG_ERR_ARG;
+  if (cudaSetDevice(w->device) != cudaSuccess || cudaStreamSynchronize(w->stream) != cudaSuccess) return PG_ERR_CUDA;
+  int n = 0;
+  if (cudaMemcpy(&n, w->v.n_events, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return PG_ERR_CUDA;
+  int over = 0;
+  if (n > w->v.max_events) { over = 1; n = w->v.max_events; }
+  if (overflowed) *overflowed = over;
+  if (!out || n == 0) return n;
+  std::vector<PgEvent> buf((size_t)n);
+  if (cudaMemcpy(buf.data(), w->v.events, sizeof(PgEvent) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) return PG_ERR_CUDA;
+  std::sort(buf.begin(), buf.end(), [](const PgEvent &a, const PgEvent &b) {
+    if (a.step != b.step) return a.step < b.step;
+    if (a.pad_ != b.pad_) return a.pad_ < b.pad_;
+    if (a.a_index != b.a_index) return a.a_index < b.a_index;      // row body: the dynamic sphere (A in both passes)
+    return a.b_index < b.b_index;
+  });
+  for (long long i = 0; i < n && i < cap; i++) { out[i] = buf[(size_t)i]; out[i].pad_ = buf[(size_t)i].pad_ >> 8; }
+  return n;
+}
+
+int pg_large_stats(PgLarge *w, PgStats *host_out, void *dev_out8) {
+  if (!w) return PG_ERR_ARG;
+  PG_CUDA(cudaSetDevice(w->device));
+  PG_CUDA(cudaMemsetAsync(w->d_stats, 0, 8 * sizeof(double), w->stream));
+  if (dev_out8) PG_CUDA(cudaMemsetAsync(dev_out8, 0, 8 * sizeof(double), w->stream));
+  k_lw_stats<<<w->sm_count * 4, 256, 0, w->stream>>>(w->v, w->d_stats, (double *)dev_out8);
+  w->launches++;
+  if (host_out) {
+    double h[8];
+    PG_CUDA(cudaMemcpyAsync(h, w->d_stats, sizeof(h), cudaMemcpyDeviceToHost, w->stream));
+    PG_CUDA(cudaStreamSynchronize(w->stream));
+    host_out->bodies = h[0]; host_out->kinetic = h[1];
+    host_out->momentum[0] = h[2]; host_out->momentum[1] = h[3]; host_out->momentum[2] = h[4];
+    host_out->contacts = h[5]; host_out->at_rest = h[6]; host_out->nonfinite = h[7];
+  }
+  return PG_OK;
+}
+
+long long pg_large_launches(const PgLarge *w) { return w ? w->launches : 0; }
+
+float pg_large_last_step_ms(PgLarge *w) {
+  if (!w) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(w->ev1) != cudaSuccess) return -1.0f;
+  if (cudaEventElapsedTime(&ms, w->ev0, w->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+int pg_large_kernel_count(void) { return K_COUNT; }
+const char *pg_large_kernel_name(int k) { return (k >= 0 && k < K_COUNT) ? kKernelNames[k] : ""; }
+float pg_large_kernel_ms(PgLarge *w, int k) { return (w && k >= 0 && k < K_COUNT) ? w->kms[k] : -1.0f; }
+
+int pg_large_exactness(PgLarge *w, int *iterations, int *proven_exact, long long *candidates, long long *hits) {
+  if (!w) return PG_ERR_ARG;
+  if (iterations) *iterations = w->last_iterations;
+  if (proven_exact) *proven_exact = w->last_proven;
+  if (candidates) *candidates = w->last_candidates;
+  if (hits) *hits = w->last_hits;
+  return PG_OK;
+}
+
+}  // extern "C"

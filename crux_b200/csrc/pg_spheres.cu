@@ -22,6 +22,7 @@
 // runs it for its own bodies, planes in array order.
 #include "pg_common.cuh"
 #include "pg_math.cuh"
+#include "pg_sphere_exact.cuh"
 
 namespace {
 
@@ -35,67 +36,10 @@ constexpr int kMaxPlanes = 16;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr float kHuge = 1.0e30f;
 
-struct Sphere {          // one body's hot state as scalars (register resident)
-  float px, py, pz, vx, vy, vz, r;
-  int rest;
-};
-
-__device__ __forceinline__ float reach(float r, float vx, float vy, float vz, float dt) {
-  // >= r + |v| dt with a 1e-4 relative cushion; FMA is fine, this is only a filter
-  float sp = sqrtf(__fmaf_rn(vx, vx, __fmaf_rn(vy, vy, vz * vz)));
-  return __fmaf_rn(sp, dt, r) * 1.0001f + 1.0e-6f;
-}
-
-// Exact visit of two spheres (world.c:481-541 with the sphere-sphere table entries).
-// All lanes call it with identical arguments.  Returns true if an event fires; A and B updated.
-__device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
-  V3 cA = v3(0.0f + A.px, 0.0f + A.py, 0.0f + A.pz);     // centre (0,0,0) + position, distance.c:283
-  V3 cB = v3(0.0f + B.px, 0.0f + B.py, 0.0f + B.pz);
-  V3 vA = v3(A.vx, A.vy, A.vz), vB = v3(B.vx, B.vy, B.vz);
-  float rs = A.r + B.r;
-  float nA = pgm::norm(vA), nB = pgm::norm(vB);
-  {
-    // Closest approach of the linear paths over [0,dt].  A leaf interval of interval_collision
-    // (len < 1e-6 s) passes only if the computed distance is <= (nA+nB)*len < 1e-6 (nA+nB) at
-    // both ends; computed and real distances differ by less than 4e-6 x the coordinate magnitude
-    // (see ss_interval).  If the real minimum gap exceeds delta, no leaf passes: predicate false.
-    V3 s = pgm::sub(cA, cB), v = pgm::sub(vA, vB);
-    float vv = __fmaf_rn(v.x, v.x, __fmaf_rn(v.y, v.y, v.z * v.z));
-    float sv = __fmaf_rn(s.x, v.x, __fmaf_rn(s.y, v.y, s.z * v.z));
-    float t = vv > 0.0f ? fminf(fmaxf(-sv / vv, 0.0f), dt) : 0.0f;
-    float qx = __fmaf_rn(v.x, t, s.x), qy = __fmaf_rn(v.y, t, s.y), qz = __fmaf_rn(v.z, t, s.z);
-    float dmin2 = __fmaf_rn(qx, qx, __fmaf_rn(qy, qy, qz * qz));
-    float cmax = fmaxf(fmaxf(fmaxf(fabsf(cA.x), fabsf(cA.y)), fabsf(cA.z)),
-                       fmaxf(fmaxf(fabsf(cB.x), fabsf(cB.y)), fabsf(cB.z)));
-    float delta = 1.1e-6f * (nA + nB) + 4.0e-6f * (cmax + (nA + nB) * dt) + 1.0e-6f;
-    float lim = (rs + delta) * 1.00001f;
-    if (dmin2 > lim * lim && dmin2 < 3.0e38f) return false;
-  }
-  if (!pgm::ss_interval(cA, vA, nA, cB, vB, nB, rs, 0.0f, dt, leaf)) return false;
-  pgm::Contact c = pgm::ss_narrow(cA, vA, cB, vB, rs);
-  if (!(c.hit && c.t >= 0)) return false;
-  V3 pA = v3(A.px, A.py, A.pz), pB = v3(B.px, B.py, B.pz);
-  pgm::ss_resolve(pA, vA, v3(0.0f, 0.0f, 0.0f), pB, vB, v3(0.0f, 0.0f, 0.0f), rs, c.t);
-  A.px = pA.x; A.py = pA.y; A.pz = pA.z; A.vx = vA.x; A.vy = vA.y; A.vz = vA.z;
-  B.px = pB.x; B.py = pB.y; B.pz = pB.z; B.vx = vB.x; B.vy = vB.y; B.vz = vB.z;
-  return true;
-}
-
-// Exact visit sphere x plane (per lane, divergent).  Returns true if an event fires.
-__device__ __noinline__ bool sphere_plane_exact(Sphere &A, float4 pl, float restitution, float dt, pgm::LeafLen leaf) {
-  V3 c = v3(0.0f + A.px, 0.0f + A.py, 0.0f + A.pz);
-  V3 v = v3(A.vx, A.vy, A.vz);
-  V3 n = v3(pl.x, pl.y, pl.z);
-  float nv = pgm::norm(v);
-  if (!pgm::sp_interval(c, v, nv, n, pl.w, A.r, 0.0f, dt, leaf)) return false;
-  pgm::Contact k = pgm::sp_narrow(c, v, n, pl.w, A.r, dt);
-  if (!(k.hit && k.t >= 0)) return false;
-  V3 p = v3(A.px, A.py, A.pz);
-  bool rest = pgm::sp_resolve(p, v, v3(0.0f, 0.0f, 0.0f), A.r, restitution, n, pl.w, k.t);
-  A.px = p.x; A.py = p.y; A.pz = p.z; A.vx = v.x; A.vy = v.y; A.vz = v.z;
-  if (rest) A.rest = 1;
-  return true;
-}
+using pgs::Sphere;
+using pgs::reach;
+using pgs::sphere_pair_exact;
+using pgs::sphere_plane_exact;
 
 __device__ __forceinline__ void emit_event(const WorldsView &v, int w, int step, int pass, int ac, int ai, int bc, int bi) {
   int slot = atomicAdd(v.n_events + w, 1);

@@ -282,3 +282,87 @@ def pair_visit(a, b, dt):
     ev = np.zeros(len(a), np.int32)
     _check(lib().pg_pair_visit(_ptr(a), _ptr(b), len(a), np.float32(dt), _ptr(ev)), "pg_pair_visit")
     return ev, a, b
+
+
+class GpuLargeWorld:
+    """One large world of dynamic spheres + static planes (PgLarge handle, uniform-grid broadphase)."""
+
+    def __init__(self, max_spheres: int, max_static: int = 6, device: int = 0):
+        self.L = lib()
+        self.h = self.L.pg_large_create(max_spheres, max_static, device)
+        if not self.h:
+            raise PgError("pg_large_create failed: " + self.L.pg_last_error().decode())
+        self.n = 0
+
+    def set(self, statics: np.ndarray, pos: np.ndarray, vel: np.ndarray, radius=0.15, restitution: float = 1.0):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1, 3); vel = np.ascontiguousarray(vel, np.float32).reshape(-1, 3)
+        st = prepare(statics)
+        rad_arr = None
+        r_uniform = 0.0
+        if np.ndim(radius) == 0:
+            r_uniform = float(radius)
+        else:
+            rad_arr = np.ascontiguousarray(radius, np.float32)
+        self.n = len(pos)
+        _check(self.L.pg_large_set(self.h, _ptr(st), len(st), self.n, _ptr(pos), _ptr(vel), _ptr(rad_arr),
+                                   np.float32(r_uniform), np.float32(restitution)), "pg_large_set")
+
+    def upload_state(self, pos, vel, at_rest=None):
+        _check(self.L.pg_large_upload_state(self.h, _ptr(pos), _ptr(vel), _ptr(at_rest)), "pg_large_upload_state")
+
+    def download_state(self, pos=None, vel=None, at_rest=None):
+        pos = np.zeros((self.n, 3), np.float32) if pos is None else pos
+        vel = np.zeros((self.n, 3), np.float32) if vel is None else vel
+        at_rest = np.zeros(self.n, np.uint8) if at_rest is None else at_rest
+        _check(self.L.pg_large_download_state(self.h, _ptr(pos), _ptr(vel), _ptr(at_rest)), "pg_large_download_state")
+        return pos, vel, at_rest
+
+    def step(self, dt: float, n_steps: int = 1):
+        _check(self.L.pg_large_step(self.h, np.float32(dt), n_steps), "pg_large_step")
+
+    def pairs(self, dt: float) -> np.ndarray:
+        n = _check(self.L.pg_large_pairs(self.h, np.float32(dt), None, 0), "pg_large_pairs")
+        out = np.zeros((max(int(n), 1), 2), np.int32)
+        n = _check(self.L.pg_large_pairs(self.h, np.float32(dt), _ptr(out), len(out)), "pg_large_pairs")
+        return out[:int(n)]
+
+    def events(self) -> np.ndarray:
+        over = C.c_int(0)
+        n = _check(self.L.pg_large_events(self.h, None, 0, C.byref(over)), "pg_large_events")
+        out = np.zeros(max(int(n), 1), dtype=PG_EVENT_DTYPE)
+        n = _check(self.L.pg_large_events(self.h, _ptr(out), len(out), C.byref(over)), "pg_large_events")
+        self.events_overflowed = bool(over.value)
+        return out[:int(n)]
+
+    def stats(self, dev_out_ptr: int | None = None, want_host: bool = True):
+        h = np.zeros(8, np.float64) if want_host else None
+        _check(self.L.pg_large_stats(self.h, _ptr(h), C.c_void_p(dev_out_ptr) if dev_out_ptr else None), "pg_large_stats")
+        return dict(zip(PG_STATS_FIELDS, h.tolist())) if want_host else None
+
+    def exactness(self) -> dict:
+        it, pr = C.c_int(0), C.c_int(0)
+        ca, hi = C.c_longlong(0), C.c_longlong(0)
+        _check(self.L.pg_large_exactness(self.h, C.byref(it), C.byref(pr), C.byref(ca), C.byref(hi)), "pg_large_exactness")
+        return {"iterations": it.value, "proven_exact": bool(pr.value), "candidates": ca.value, "hits": hi.value}
+
+    def kernel_ms(self) -> dict:
+        return {self.L.pg_large_kernel_name(k).decode(): float(self.L.pg_large_kernel_ms(self.h, k))
+                for k in range(self.L.pg_large_kernel_count())}
+
+    def last_step_ms(self) -> float:
+        return float(self.L.pg_large_last_step_ms(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.pg_large_launches(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pg_large_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
