@@ -60,6 +60,7 @@ struct PgWorlds {
   long long launches;
   int last_steps;
   double *d_stats;            // 8 doubles
+  int *d_work_counter;        // world hand-out counter of the sphere kernel
   int sm_count;
   bool static_pass_parallel_ok;   // recomputed on upload (general mode)
   // device staging for packed [body][3] state exchange (sphere mode)

@@ -20,6 +20,25 @@ __device__ __forceinline__ float reach(float r, float vx, float vy, float vz, fl
   return __fmaf_rn(sp, dt, r) * 1.0001f + 1.0e-6f;
 }
 
+// Conservative gate in front of the exact sphere-sphere predicate.  Closest approach of the two
+// linear paths over [0,dt]: a leaf interval of interval_collision (len < 1e-6 s) passes only if the
+// COMPUTED distance is <= (nA+nB)*len < 1e-6 (nA+nB) at both ends, and computed and real distances
+// differ by less than 4e-6 x the coordinate magnitude (see pgm::ss_interval).  If the real minimum
+// gap exceeds delta, no leaf passes and the predicate is false.  `vsum` >= |vA| + |vB|.
+static __device__ __forceinline__ bool pair_gate_rejects(V3 cA, V3 vA, V3 cB, V3 vB, float rs, float vsum, float dt) {
+  const V3 s = pgm::sub(cA, cB), v = pgm::sub(vA, vB);
+  const float vv = __fmaf_rn(v.x, v.x, __fmaf_rn(v.y, v.y, v.z * v.z));
+  const float sv = __fmaf_rn(s.x, v.x, __fmaf_rn(s.y, v.y, s.z * v.z));
+  const float t = vv > 0.0f ? fminf(fmaxf(-sv / vv, 0.0f), dt) : 0.0f;
+  const float qx = __fmaf_rn(v.x, t, s.x), qy = __fmaf_rn(v.y, t, s.y), qz = __fmaf_rn(v.z, t, s.z);
+  const float dmin2 = __fmaf_rn(qx, qx, __fmaf_rn(qy, qy, qz * qz));
+  const float cmax = fmaxf(fmaxf(fmaxf(fabsf(cA.x), fabsf(cA.y)), fabsf(cA.z)),
+                           fmaxf(fmaxf(fabsf(cB.x), fabsf(cB.y)), fabsf(cB.z)));
+  const float delta = 1.1e-6f * vsum + 4.0e-6f * (cmax + vsum * dt) + 1.0e-6f;
+  const float lim = (rs + delta) * 1.00001f;
+  return dmin2 > lim * lim && dmin2 < 3.0e38f;
+}
+
 // Exact visit of two spheres (world.c:481-541 with the sphere-sphere table entries).
 // All lanes call it with identical arguments.  Returns true if an event fires; A and B updated.
 static __device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
@@ -28,23 +47,7 @@ static __device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, floa
   V3 vA = v3(A.vx, A.vy, A.vz), vB = v3(B.vx, B.vy, B.vz);
   float rs = A.r + B.r;
   float nA = pgm::norm(vA), nB = pgm::norm(vB);
-  {
-    // Closest approach of the linear paths over [0,dt].  A leaf interval of interval_collision
-    // (len < 1e-6 s) passes only if the computed distance is <= (nA+nB)*len < 1e-6 (nA+nB) at
-    // both ends; computed and real distances differ by less than 4e-6 x the coordinate magnitude
-    // (see ss_interval).  If the real minimum gap exceeds delta, no leaf passes: predicate false.
-    V3 s = pgm::sub(cA, cB), v = pgm::sub(vA, vB);
-    float vv = __fmaf_rn(v.x, v.x, __fmaf_rn(v.y, v.y, v.z * v.z));
-    float sv = __fmaf_rn(s.x, v.x, __fmaf_rn(s.y, v.y, s.z * v.z));
-    float t = vv > 0.0f ? fminf(fmaxf(-sv / vv, 0.0f), dt) : 0.0f;
-    float qx = __fmaf_rn(v.x, t, s.x), qy = __fmaf_rn(v.y, t, s.y), qz = __fmaf_rn(v.z, t, s.z);
-    float dmin2 = __fmaf_rn(qx, qx, __fmaf_rn(qy, qy, qz * qz));
-    float cmax = fmaxf(fmaxf(fmaxf(fabsf(cA.x), fabsf(cA.y)), fabsf(cA.z)),
-                       fmaxf(fmaxf(fabsf(cB.x), fabsf(cB.y)), fabsf(cB.z)));
-    float delta = 1.1e-6f * (nA + nB) + 4.0e-6f * (cmax + (nA + nB) * dt) + 1.0e-6f;
-    float lim = (rs + delta) * 1.00001f;
-    if (dmin2 > lim * lim && dmin2 < 3.0e38f) return false;
-  }
+  if (pair_gate_rejects(cA, vA, cB, vB, rs, nA + nB, dt)) return false;
   if (!pgm::ss_interval(cA, vA, nA, cB, vB, nB, rs, 0.0f, dt, leaf)) return false;
   pgm::Contact c = pgm::ss_narrow(cA, vA, cB, vB, rs);
   if (!(c.hit && c.t >= 0)) return false;

@@ -24,6 +24,8 @@
 #include "pg_math.cuh"
 #include "pg_sphere_exact.cuh"
 
+#include <algorithm>
+
 namespace {
 
 using pgm::V3;
@@ -34,7 +36,7 @@ using pgm::v3;
 #endif
 constexpr int kMaxPlanes = 16;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr float kHuge = 1.0e30f;
+constexpr float kHuge = 1.0e8f;      // padding bodies: far from everything, squares still finite
 
 using pgs::Sphere;
 using pgs::reach;
@@ -66,6 +68,22 @@ __device__ __noinline__ bool row_slow_path(float4 *P4, float4 *V4, int i, unsign
   pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
   bool dirty = false;
   int j0 = 0;
+  // Lane-parallel refinement: every lane runs the closest-approach gate on its own candidate
+  // columns, so the serial part below only sees pairs that really come within contact range.
+  auto refine = [&](unsigned m, float4 ap, float4 av) {
+    unsigned keep = 0;
+    const float na2 = __fmaf_rn(av.x, av.x, __fmaf_rn(av.y, av.y, av.z * av.z));
+    for (; m; m &= m - 1) {
+      const int s = __ffs((int)m) - 1;
+      const float4 bp = P4[s * 32 + lane], bv = V4[s * 32 + lane];
+      const float nb2 = __fmaf_rn(bv.x, bv.x, __fmaf_rn(bv.y, bv.y, bv.z * bv.z));
+      const float vsum = sqrtf(2.0f * (na2 + nb2)) * 1.0001f;            // >= |vA| + |vB|
+      if (!pgs::pair_gate_rejects(v3(ap.x, ap.y, ap.z), v3(av.x, av.y, av.z), v3(bp.x, bp.y, bp.z), v3(bv.x, bv.y, bv.z),
+                                  av.w + bv.w, vsum, dt)) keep |= 1u << s;
+    }
+    return keep;
+  };
+  if (dt > 1.0e-9f) mask = refine(mask, P4[i], V4[i]);
   for (;;) {
     // lowest candidate column >= j0 of this lane: slot bits below the first admissible slot are dropped
     const int smin = (j0 >> 5) + ((lane < (j0 & 31)) ? 1 : 0);
@@ -97,6 +115,7 @@ __device__ __noinline__ bool row_slow_path(float4 *P4, float4 *V4, int i, unsign
         const float T = rhoA + q.w;
         if (d2 <= T * T && c != i) mask |= 1u << s;
       }
+      if (dt > 1.0e-9f) mask = refine(mask, P4[i], V4[i]);
     }
     j0 = j + 1;
   }
@@ -135,15 +154,21 @@ __device__ __noinline__ bool plane_slow_path(float4 *P4, float4 *V4, int i, floa
 // instructions and spent most of its time in instruction-cache misses).
 template <int CPT, int WPB>
 __global__ void __launch_bounds__(WPB * 32, (CPT <= 8) ? PG_SPH_WARPS / WPB : 2)
-k_step_spheres(WorldsView v, float dt_in, int n_steps) {
+k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter) {
   __shared__ float4 s_planes[WPB][kMaxPlanes];
   __shared__ float4 s_P4[WPB][CPT * 32];
   __shared__ float4 s_V4[WPB][CPT * 32];
 
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  const int w = blockIdx.x * WPB + wib;
+  // Worlds are handed out through an atomic counter: the grid holds exactly the warps that fit on
+  // the GPU, each warp keeps pulling worlds until none are left, so there is no partial last wave.
+  for (;;) {
+  int w = 0;
+  if (lane == 0) w = atomicAdd(work_counter, 1);
+  w = __shfl_sync(kFull, w, 0);
   if (w >= v.n_worlds) return;
+  __syncwarp();
   const int n = v.counts[w * 3 + 1];
   const int ns = min(v.counts[w * 3 + 0], kMaxPlanes);
   const int n_blocks = (n + 31) >> 5;
@@ -168,47 +193,116 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps) {
       a.w = reach(b.w, b.x, b.y, b.z, dt);
     } else {
       // padding bodies sit far away from everything (and from each other) with zero reach
-      a = make_float4(kHuge * (float)(i + 1), kHuge, kHuge, 0.0f);
+      a = make_float4(kHuge + 1000.0f * (float)i, kHuge, kHuge, 0.0f);
       b = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     P4[i] = a; V4[i] = b;
   }
   __syncwarp();
 
-  float px[CPT], py[CPT], pz[CPT], rho[CPT];
+  // Register cache of this lane's CPT bodies for the reach filter, in coordinates relative to the
+  // world's centre: q = p - centre, qr = rho, qc = |q|^2 - rho^2.  With them
+  //   |ci - ck|^2 <= (rho_i + rho_k)^2   <=>   qc_k - 2 q_i.q_k - 2 rho_i rho_k <= rho_i^2 - |q_i|^2
+  // is four FMAs and a compare per pair; the rounding of the expanded form is covered by `slack`
+  // (>= 60 eps of the largest term), which keeps the filter a superset of the exact root test.
+  float qx[CPT], qy[CPT], qz[CPT], qr[CPT], qc[CPT];
+  float cx0 = 0.0f, cy0 = 0.0f, cz0 = 0.0f;
+  auto cache_slot = [&](int k, const float4 a) {
+    qx[k] = a.x - cx0; qy[k] = a.y - cy0; qz[k] = a.z - cz0; qr[k] = a.w;
+    qc[k] = __fmaf_rn(qx[k], qx[k], __fmaf_rn(qy[k], qy[k], qz[k] * qz[k])) - a.w * a.w;
+  };
 
   for (int step = 0; step < n_steps; step++) {
     // ---------------- pass 3: every sphere against the planes, in plane order (world.c:369-471)
+    float bl[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bh[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    // cheap gate: |signed distance| beyond the reach -> the root test of the interval search fails
+    auto plane_near = [&](const float4 a, const float4 pl) {
+      const float s0 = __fmaf_rn(a.x, pl.x, __fmaf_rn(a.y, pl.y, a.z * pl.z)) - pl.w;
+      return !(gate_ok && fabsf(s0) > a.w * 1.0001f + 1.0e-5f * (fabsf(s0) + fabsf(pl.w) + 1.0f));
+    };
+    if (ns <= 8 && n_blocks <= 8) {
+      // Every lane first lists its (body, plane) visits that pass the cheap gate, then all lanes
+      // work through their own lists TOGETHER: the exact evaluations of different bodies run in
+      // the same SIMT pass instead of one after the other.  Per body the planes stay in order, and
+      // a contact re-gates that body's remaining planes against its new state.
+      unsigned long long pend = 0;
 #pragma unroll 1
-    for (int s = 0; s < n_blocks; s++) {
-      const int i = s * 32 + lane;
-      if (i < n) {
-        float4 a = P4[i];
-#pragma unroll 1
-        for (int k = 0; k < ns; k++) {
-          const float4 pl = s_planes[wib][k];
-          // cheap gate: |signed distance| beyond the reach -> the root test of the interval search fails
-          const float s0 = __fmaf_rn(a.x, pl.x, __fmaf_rn(a.y, pl.y, a.z * pl.z)) - pl.w;
-          if (gate_ok && fabsf(s0) > a.w * 1.0001f + 1.0e-5f * (fabsf(s0) + fabsf(pl.w) + 1.0f)) continue;
+      for (int s = 0; s < n_blocks; s++) {
+        const int i = s * 32 + lane;
+        if (i < n) {
+          const float4 a = P4[i];
+          for (int k = 0; k < ns; k++) if (plane_near(a, s_planes[wib][k])) pend |= 1ull << (s * 8 + k);
+        }
+      }
+      while (__any_sync(kFull, pend != 0ull)) {
+        if (pend) {
+          const int bit = __ffsll((long long)pend) - 1;
+          pend &= pend - 1ull;
+          const int s = bit >> 3, k = bit & 7, i = s * 32 + lane;
           int came_to_rest = 0;
-          if (plane_slow_path(P4, V4, i, pl, restitution, dt, gate_ok, &came_to_rest, leaf)) {
-            a = P4[i];
+          if (plane_slow_path(P4, V4, i, s_planes[wib][k], restitution, dt, gate_ok, &came_to_rest, leaf)) {
             if (came_to_rest) rest |= 1u << s;
             if (record) emit_event(v, w, step, 3, PG_CLASS_DYNAMIC, i, PG_CLASS_STATIC, k);
+            const float4 a = P4[i];
+            for (int k2 = k + 1; k2 < ns; k2++) {
+              const unsigned long long b2 = 1ull << (s * 8 + k2);
+              if (plane_near(a, s_planes[wib][k2])) pend |= b2; else pend &= ~b2;
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll 1
+      for (int s = 0; s < n_blocks; s++) {
+        const int i = s * 32 + lane;
+        if (i < n) {
+          float4 a = P4[i];
+#pragma unroll 1
+          for (int k = 0; k < ns; k++) {
+            const float4 pl = s_planes[wib][k];
+            if (!plane_near(a, pl)) continue;
+            int came_to_rest = 0;
+            if (plane_slow_path(P4, V4, i, pl, restitution, dt, gate_ok, &came_to_rest, leaf)) {
+              a = P4[i];
+              if (came_to_rest) rest |= 1u << s;
+              if (record) emit_event(v, w, step, 3, PG_CLASS_DYNAMIC, i, PG_CLASS_STATIC, k);
+            }
           }
         }
       }
     }
+#pragma unroll 1
+    for (int s = 0; s < n_blocks; s++) {
+      const int i = s * 32 + lane;
+      if (i < n) {
+        const float4 a = P4[i];
+        bl[0] = fminf(bl[0], a.x); bl[1] = fminf(bl[1], a.y); bl[2] = fminf(bl[2], a.z);
+        bh[0] = fmaxf(bh[0], a.x); bh[1] = fmaxf(bh[1], a.y); bh[2] = fmaxf(bh[2], a.z);
+      }
+    }
+    // world centre and the magnitude the filter's rounding slack is scaled with
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        bl[k] = fminf(bl[k], __shfl_xor_sync(kFull, bl[k], o));
+        bh[k] = fmaxf(bh[k], __shfl_xor_sync(kFull, bh[k], o));
+      }
+    }
+    cx0 = 0.5f * (bl[0] + bh[0]); cy0 = 0.5f * (bl[1] + bh[1]); cz0 = 0.5f * (bl[2] + bh[2]);
+    if (!(fabsf(cx0) < 1.0e30f && fabsf(cy0) < 1.0e30f && fabsf(cz0) < 1.0e30f)) { cx0 = cy0 = cz0 = 0.0f; }
+    const float hx = bh[0] - cx0 + 2.0f, hy = bh[1] - cy0 + 2.0f, hz = bh[2] - cz0 + 2.0f;   // + room to move within the step
+    const float maxn2 = hx * hx + hy * hy + hz * hz;
     __syncwarp();
 
     // ---------------- pass 4: rows in order (world.c:473-554)
 #pragma unroll
-    for (int k = 0; k < CPT; k++) { const float4 a = P4[k * 32 + lane]; px[k] = a.x; py[k] = a.y; pz[k] = a.z; rho[k] = a.w; }
+    for (int k = 0; k < CPT; k++) cache_slot(k, P4[k * 32 + lane]);
 
 #pragma unroll 1
     for (int rb = 0; rb < n_blocks; rb++) {
-      // speculative integration of this lane's row body (committed when its row completes;
-      // recomputed if a contact touches the world before that)
+      // speculative integration of this lane's row body (committed to the register cache when its
+      // row completes, written back to shared memory lazily; recomputed if a contact intervenes)
       float ipx, ipy, ipz, ivx, ivy, ivz, irho, irad;
       auto speculate = [&]() {
         const float4 a = P4[rb * 32 + lane], b = V4[rb * 32 + lane];
@@ -219,20 +313,29 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps) {
       };
       speculate();
       const int rows_here = min(32, n - rb * 32);
+      int flushed = 0;                              // rows [0, flushed) of this block are committed in shared memory
 #pragma unroll 1
       for (int rl = 0; rl < rows_here; rl++) {
         const int i = rb * 32 + rl;
         const float4 rp = P4[i];
+        const float rx = rp.x - cx0, ry = rp.y - cy0, rz = rp.z - cz0;
+        const float n2 = __fmaf_rn(rx, rx, __fmaf_rn(ry, ry, rz * rz));
+        const float ea = -2.0f * rx, eb = -2.0f * ry, ec = -2.0f * rz, ed = -2.0f * rp.w;
+        const float ee = __fmaf_rn(rp.w, rp.w, -n2) + (8.0e-6f * (n2 + maxn2) + 1.0e-6f);
         unsigned mask = 0;
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
-          const float dx = rp.x - px[k], dy = rp.y - py[k], dz = rp.z - pz[k];
-          const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
-          const float T = rp.w + rho[k];
-          mask |= (d2 <= T * T ? 1u : 0u) << k;
+          const float t = __fmaf_rn(ea, qx[k], __fmaf_rn(eb, qy[k], __fmaf_rn(ec, qz[k], __fmaf_rn(ed, qr[k], qc[k]))));
+          mask |= (t <= ee ? 1u : 0u) << k;
         }
         if (lane == rl) mask &= ~1u;                 // the row body itself lives in static slot 0
         if (__any_sync(kFull, mask != 0)) {
+          // bring shared memory up to date with the rows committed so far in this block
+          if (lane >= flushed && lane < rl) {
+            P4[rb * 32 + lane] = make_float4(ipx, ipy, ipz, irho);
+            V4[rb * 32 + lane] = make_float4(ivx, ivy, ivz, irad);
+          }
+          flushed = rl;
           // static slot k is actual slot (rb + k) mod CPT: rotate the bits into column order
           const unsigned full = (CPT == 32) ? 0xffffffffu : ((1u << CPT) - 1u);
           const unsigned amask = ((mask << rb) | (mask >> ((CPT - rb) & 31))) & full;
@@ -240,25 +343,30 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps) {
 #pragma unroll
             for (int k = 0; k < CPT; k++) {
               int sa = rb + k; if (sa >= CPT) sa -= CPT;
-              const float4 a = P4[sa * 32 + lane]; px[k] = a.x; py[k] = a.y; pz[k] = a.z; rho[k] = a.w;
+              cache_slot(k, P4[sa * 32 + lane]);
             }
-            speculate();
+            if (lane >= rl) speculate();
+            else {                                   // already integrated: keep what shared memory now holds
+              const float4 a = P4[rb * 32 + lane], b = V4[rb * 32 + lane];
+              ipx = a.x; ipy = a.y; ipz = a.z; irho = a.w; ivx = b.x; ivy = b.y; ivz = b.z; irad = b.w;
+            }
           }
         }
-        // integrate row i (world.c:549-553): commit the owner lane's speculative state
-        if (lane == rl) {
-          px[0] = ipx; py[0] = ipy; pz[0] = ipz; rho[0] = irho;
-          P4[i] = make_float4(ipx, ipy, ipz, irho);
-          V4[i] = make_float4(ivx, ivy, ivz, irad);
-        }
+        // integrate row i (world.c:549-553): the owner lane's cache takes the speculative state
+        if (lane == rl) cache_slot(0, make_float4(ipx, ipy, ipz, irho));
+      }
+      __syncwarp();
+      if (lane >= flushed && lane < rows_here) {
+        P4[rb * 32 + lane] = make_float4(ipx, ipy, ipz, irho);
+        V4[rb * 32 + lane] = make_float4(ivx, ivy, ivz, irad);
       }
       __syncwarp();
       // rotate the cache: the next block's bodies move into static slot 0
       {
-        const float tx = px[0], ty = py[0], tz = pz[0], tr = rho[0];
+        const float t0 = qx[0], t1 = qy[0], t2 = qz[0], t3 = qr[0], t4 = qc[0];
 #pragma unroll
-        for (int k = 0; k + 1 < CPT; k++) { px[k] = px[k + 1]; py[k] = py[k + 1]; pz[k] = pz[k + 1]; rho[k] = rho[k + 1]; }
-        px[CPT - 1] = tx; py[CPT - 1] = ty; pz[CPT - 1] = tz; rho[CPT - 1] = tr;
+        for (int k = 0; k + 1 < CPT; k++) { qx[k] = qx[k + 1]; qy[k] = qy[k + 1]; qz[k] = qz[k + 1]; qr[k] = qr[k + 1]; qc[k] = qc[k + 1]; }
+        qx[CPT - 1] = t0; qy[CPT - 1] = t1; qz[CPT - 1] = t2; qr[CPT - 1] = t3; qc[CPT - 1] = t4;
       }
     }
   }
@@ -273,6 +381,8 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps) {
       v.vel_rad[base + i] = V4[i];
     }
   }
+  __syncwarp();
+  }   // next world
 }
 
 // ---------------------------------------------------------------- aggregate statistics
@@ -380,8 +490,15 @@ static int launch_spheres(PgWorlds *w, float dt, int n_steps) {
     cudaFuncSetAttribute(k_step_spheres<CPT, WPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  const int blocks = (w->v.n_worlds + WPB - 1) / WPB;
-  k_step_spheres<CPT, WPB><<<blocks, WPB * 32, 0, w->stream>>>(w->v, dt, n_steps);
+  static int resident_blocks = 0;
+  if (!resident_blocks) {
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_spheres<CPT, WPB>, WPB * 32, 0);
+    resident_blocks = std::max(1, per_sm) * w->sm_count;
+  }
+  const int blocks = std::min((w->v.n_worlds + WPB - 1) / WPB, resident_blocks);
+  cudaMemsetAsync(w->d_work_counter, 0, sizeof(int), w->stream);
+  k_step_spheres<CPT, WPB><<<blocks, WPB * 32, 0, w->stream>>>(w->v, dt, n_steps, w->d_work_counter);
   return PG_OK;
 }
 

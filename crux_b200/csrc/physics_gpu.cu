@@ -169,6 +169,7 @@ PgWorlds *pg_worlds_create(int n_worlds, int max_static, int max_dynamic, int ma
   if (max_events_per_world > 0)
     PG_CUDA_NULL(cudaMalloc(&w->v.events, sizeof(PgEvent) * (size_t)n_worlds * max_events_per_world));
   PG_CUDA_NULL(cudaMalloc(&w->d_stats, 8 * sizeof(double)));
+  PG_CUDA_NULL(cudaMalloc(&w->d_work_counter, sizeof(int)));
   w->h_counts = (int *)calloc((size_t)n_worlds * 3, sizeof(int));
   return w;
 }
@@ -185,6 +186,7 @@ void pg_worlds_destroy(PgWorlds *w) {
   if (w->v.vel_rad) cudaFree(w->v.vel_rad);
   if (w->v.planes) cudaFree(w->v.planes);
   if (w->d_stats) cudaFree(w->d_stats);
+  if (w->d_work_counter) cudaFree(w->d_work_counter);
   if (w->d_stage_pos) { cudaFree(w->d_stage_pos); cudaFree(w->d_stage_vel); cudaFree(w->d_stage_rest); }
   cudaEventDestroy(w->ev0);
   cudaEventDestroy(w->ev1);
