@@ -390,9 +390,7 @@ def run_gpu_arm(args, cfg):
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        worlds.upload_state(0, nw, hp.array, hv.array, hr.array)
-        worlds.step(dt, 1)
-        worlds.download_state(0, nw, hp.array, hv.array, hr.array)      # synchronises
+        worlds.step_host(dt, 1, hp.array, hv.array, hr.array)           # H2D + step + D2H, synchronous
     barrier()
     e2e_wall = time.perf_counter() - t0
     t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
@@ -431,7 +429,7 @@ def run_gpu_arm(args, cfg):
                                  "SM-issue-bound, not HBM-bound (SURVEY.md section 8d), see profiles/"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "pg_worlds_upload_state + pg_worlds_step(1) + pg_worlds_download_state, pinned host buffers"},
+                    "steps": e2e_steps, "api": "pg_worlds_step_host(dt, 1, pos, vel, at_rest): pinned host arrays in and out every step, 8 world chunks pipelined over 3 streams"},
             "gpu_launches": int(gpu_launches),
             "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
             "launch_ms_per_step_min_max": [min(launch_ms), max(launch_ms)],

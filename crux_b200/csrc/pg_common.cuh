@@ -67,12 +67,20 @@ struct PgWorlds {
   float *d_stage_pos, *d_stage_vel;
   unsigned char *d_stage_rest;
   size_t stage_bodies;
+  // chunked host pipeline (pg_worlds_step_host)
+  cudaStream_t pipe_stream[3];
+  cudaEvent_t pipe_done[3];
+  int *d_pipe_counters;       // one hand-out counter per chunk
+  bool pipe_ready;
 };
 
 // pg_general.cu
 int pg_launch_general_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes);
 // pg_spheres.cu
 int pg_launch_sphere_step(PgWorlds *w, float dt, int n_steps);
+int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter);
+int pg_launch_pack_state_on(PgWorlds *w, cudaStream_t st, int first, int count, int n, const float *pos, const float *vel, const unsigned char *rest);
+int pg_launch_unpack_state_on(PgWorlds *w, cudaStream_t st, int first, int count, int n, float *pos, float *vel, unsigned char *rest);
 int pg_launch_worlds_stats(PgWorlds *w, void *dev_out8);
 int pg_launch_pack_state(PgWorlds *w, int first, int count, int n, const float *pos, const float *vel, const unsigned char *rest);
 int pg_launch_unpack_state(PgWorlds *w, int first, int count, int n, float *pos, float *vel, unsigned char *rest);

@@ -32,7 +32,7 @@ using pgm::V3;
 using pgm::v3;
 
 #ifndef PG_SPH_WARPS
-#define PG_SPH_WARPS 12   // resident warps (worlds) per SM the register budget is sized for
+#define PG_SPH_WARPS 12   // resident warps (worlds) per SM the register budget is sized for (measured best: 8 -> 0.41, 12 -> 0.28, 16 -> 0.44 ms/step)
 #endif
 constexpr int kMaxPlanes = 16;
 constexpr unsigned kFull = 0xffffffffu;
@@ -154,7 +154,7 @@ __device__ __noinline__ bool plane_slow_path(float4 *P4, float4 *V4, int i, floa
 // instructions and spent most of its time in instruction-cache misses).
 template <int CPT, int WPB>
 __global__ void __launch_bounds__(WPB * 32, (CPT <= 8) ? PG_SPH_WARPS / WPB : 2)
-k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter) {
+k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int first_world, int end_world) {
   __shared__ float4 s_planes[WPB][kMaxPlanes];
   __shared__ float4 s_P4[WPB][CPT * 32];
   __shared__ float4 s_V4[WPB][CPT * 32];
@@ -165,9 +165,9 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter) {
   // the GPU, each warp keeps pulling worlds until none are left, so there is no partial last wave.
   for (;;) {
   int w = 0;
-  if (lane == 0) w = atomicAdd(work_counter, 1);
+  if (lane == 0) w = first_world + atomicAdd(work_counter, 1);
   w = __shfl_sync(kFull, w, 0);
-  if (w >= v.n_worlds) return;
+  if (w >= end_world) return;
   __syncwarp();
   const int n = v.counts[w * 3 + 1];
   const int ns = min(v.counts[w * 3 + 0], kMaxPlanes);
@@ -469,6 +469,18 @@ __global__ void k_unpack_state(WorldsView v, int first, int count, int n, float 
 
 }  // namespace
 
+int pg_launch_pack_state_on(PgWorlds *w, cudaStream_t st, int first, int count, int n, const float *pos, const float *vel, const unsigned char *rest) {
+  k_pack_state<<<w->sm_count * 2, 256, 0, st>>>(w->v, first, count, n, pos, vel, rest);
+  PG_CUDA(cudaGetLastError());
+  w->launches++;
+  return PG_OK;
+}
+int pg_launch_unpack_state_on(PgWorlds *w, cudaStream_t st, int first, int count, int n, float *pos, float *vel, unsigned char *rest) {
+  k_unpack_state<<<w->sm_count * 2, 256, 0, st>>>(w->v, first, count, n, pos, vel, rest);
+  PG_CUDA(cudaGetLastError());
+  w->launches++;
+  return PG_OK;
+}
 int pg_launch_pack_state(PgWorlds *w, int first, int count, int n, const float *pos, const float *vel, const unsigned char *rest) {
   k_pack_state<<<w->sm_count * 4, 256, 0, w->stream>>>(w->v, first, count, n, pos, vel, rest);
   PG_CUDA(cudaGetLastError());
@@ -483,37 +495,40 @@ int pg_launch_unpack_state(PgWorlds *w, int first, int count, int n, float *pos,
 }
 
 template <int CPT, int WPB>
-static int launch_spheres(PgWorlds *w, float dt, int n_steps) {
+static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter) {
   static bool configured = false;
-  if (!configured) {
-    // all shared memory the SM has: the kernel wants 24 resident warps, each with an 8 KB world image
-    cudaFuncSetAttribute(k_step_spheres<CPT, WPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
-  }
   static int resident_blocks = 0;
-  if (!resident_blocks) {
+  if (!configured) {
+    // all shared memory the SM has: the kernel wants an 8 KB world image per resident warp
+    cudaFuncSetAttribute(k_step_spheres<CPT, WPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_spheres<CPT, WPB>, WPB * 32, 0);
     resident_blocks = std::max(1, per_sm) * w->sm_count;
+    configured = true;
   }
-  const int blocks = std::min((w->v.n_worlds + WPB - 1) / WPB, resident_blocks);
-  cudaMemsetAsync(w->d_work_counter, 0, sizeof(int), w->stream);
-  k_step_spheres<CPT, WPB><<<blocks, WPB * 32, 0, w->stream>>>(w->v, dt, n_steps, w->d_work_counter);
+  const int blocks = std::min((count + WPB - 1) / WPB, resident_blocks);
+  cudaMemsetAsync(counter, 0, sizeof(int), stream);
+  k_step_spheres<CPT, WPB><<<blocks, WPB * 32, 0, stream>>>(w->v, dt, n_steps, counter, first, first + count);
   return PG_OK;
 }
 
-int pg_launch_sphere_step(PgWorlds *w, float dt, int n_steps) {
+// Step worlds [first, first+count) on `stream` (the whole batch on the handle's stream by default).
+int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter) {
   const int cap = w->v.cap[1];
   if (w->v.cap[0] > kMaxPlanes) { pg_set_error("sphere mode supports at most %d static planes", kMaxPlanes); return PG_ERR_CAPACITY; }
-  if (cap <= 32) launch_spheres<1, 4>(w, dt, n_steps);
-  else if (cap <= 64) launch_spheres<2, 4>(w, dt, n_steps);
-  else if (cap <= 128) launch_spheres<4, 4>(w, dt, n_steps);
-  else if (cap <= 256) launch_spheres<8, 4>(w, dt, n_steps);
-  else if (cap <= 512) launch_spheres<16, 2>(w, dt, n_steps);
+  if (cap <= 32) launch_spheres<1, 4>(w, dt, n_steps, first, count, stream, counter);
+  else if (cap <= 64) launch_spheres<2, 4>(w, dt, n_steps, first, count, stream, counter);
+  else if (cap <= 128) launch_spheres<4, 4>(w, dt, n_steps, first, count, stream, counter);
+  else if (cap <= 256) launch_spheres<8, 4>(w, dt, n_steps, first, count, stream, counter);
+  else if (cap <= 512) launch_spheres<16, 2>(w, dt, n_steps, first, count, stream, counter);
   else { pg_set_error("sphere mode supports at most 512 spheres per world (got capacity %d)", cap); return PG_ERR_CAPACITY; }
   PG_CUDA(cudaGetLastError());
   w->launches++;
   return PG_OK;
+}
+
+int pg_launch_sphere_step(PgWorlds *w, float dt, int n_steps) {
+  return pg_launch_sphere_range(w, dt, n_steps, 0, w->v.n_worlds, w->stream, w->d_work_counter);
 }
 
 int pg_launch_worlds_stats(PgWorlds *w, void *dev_out8) {

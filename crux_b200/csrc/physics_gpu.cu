@@ -187,6 +187,10 @@ void pg_worlds_destroy(PgWorlds *w) {
   if (w->v.planes) cudaFree(w->v.planes);
   if (w->d_stats) cudaFree(w->d_stats);
   if (w->d_work_counter) cudaFree(w->d_work_counter);
+  if (w->pipe_ready) {
+    for (int k = 0; k < 3; k++) { cudaStreamDestroy(w->pipe_stream[k]); cudaEventDestroy(w->pipe_done[k]); }
+    cudaFree(w->d_pipe_counters);
+  }
   if (w->d_stage_pos) { cudaFree(w->d_stage_pos); cudaFree(w->d_stage_vel); cudaFree(w->d_stage_rest); }
   cudaEventDestroy(w->ev0);
   cudaEventDestroy(w->ev1);
@@ -465,6 +469,72 @@ int pg_worlds_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes) {
   PG_CUDA(cudaEventRecord(w->ev1, w->stream));
   w->last_steps = n_steps;
   return rc;
+}
+
+// Host-to-host step: state in from `pos/vel/at_rest`, n_steps steps, state back out into the same
+// arrays.  The batch is cut into chunks of worlds that flow through three streams, so the H2D copy
+// of chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex).
+int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *vel, uint8_t *at_rest) {
+  if (!w || n_steps < 0 || !pos || !vel) { pg_set_error("pg_worlds_step_host: bad argument"); return PG_ERR_ARG; }
+  if (w->mode != PG_MODE_SPHERES) { pg_set_error("pg_worlds_step_host: handle must be in sphere mode"); return PG_ERR_UNSUPPORTED; }
+  PG_CUDA(cudaSetDevice(w->device));
+  const int nw = w->v.n_worlds;
+  int n = 0;
+  int rc = sphere_range_count(w, 0, nw, &n);
+  if (rc) return rc;
+  rc = ensure_stage(w, (size_t)nw * n);
+  if (rc) return rc;
+  constexpr int kChunks = 8;
+  if (!w->pipe_ready) {
+    for (int k = 0; k < 3; k++) {
+      PG_CUDA(cudaStreamCreateWithFlags(&w->pipe_stream[k], cudaStreamNonBlocking));
+      PG_CUDA(cudaEventCreateWithFlags(&w->pipe_done[k], cudaEventDisableTiming));
+    }
+    PG_CUDA(cudaMalloc(&w->d_pipe_counters, sizeof(int) * kChunks));
+    w->pipe_ready = true;
+  }
+  {
+    float cdt = dt;
+    if ((double)cdt > 0.01666) cdt = (float)0.01666;
+    pg_leaf_lengths(0.0f, cdt, &w->v.leaf_lo, &w->v.leaf_hi);
+  }
+  PG_CUDA(cudaMemsetAsync(w->v.n_events, 0, sizeof(int) * (size_t)nw, w->stream));
+  PG_CUDA(cudaEventRecord(w->ev0, w->stream));
+  for (int k = 0; k < 3; k++) PG_CUDA(cudaStreamWaitEvent(w->pipe_stream[k], w->ev0, 0));
+  const int per = (nw + kChunks - 1) / kChunks;
+  for (int c = 0; c < kChunks; c++) {
+    const int first = c * per, count = std::min(per, nw - first);
+    if (count <= 0) break;
+    cudaStream_t st = w->pipe_stream[c % 3];
+    const size_t off = (size_t)first * n, bodies = (size_t)count * n;
+    PG_CUDA(cudaMemcpyAsync(w->d_stage_pos + 3 * off, pos + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(w->d_stage_vel + 3 * off, vel + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyHostToDevice, st));
+    if (at_rest) PG_CUDA(cudaMemcpyAsync(w->d_stage_rest + off, at_rest + off, bodies, cudaMemcpyHostToDevice, st));
+    rc = pg_launch_pack_state_on(w, st, first, count, n, w->d_stage_pos + 3 * off, w->d_stage_vel + 3 * off, at_rest ? w->d_stage_rest + off : nullptr);
+    if (rc) return rc;
+    if (n_steps > 0) { rc = pg_launch_sphere_range(w, dt, n_steps, first, count, st, w->d_pipe_counters + c); if (rc) return rc; }
+    rc = pg_launch_unpack_state_on(w, st, first, count, n, w->d_stage_pos + 3 * off, w->d_stage_vel + 3 * off, at_rest ? w->d_stage_rest + off : nullptr);
+    if (rc) return rc;
+  }
+  // downloads are issued after ALL uploads: a copy engine serves its queue in order, and a D2H that
+  // waits for its chunk's kernels must not sit in front of the next chunk's H2D
+  for (int c = 0; c < kChunks; c++) {
+    const int first = c * per, count = std::min(per, nw - first);
+    if (count <= 0) break;
+    cudaStream_t st = w->pipe_stream[c % 3];
+    const size_t off = (size_t)first * n, bodies = (size_t)count * n;
+    PG_CUDA(cudaMemcpyAsync(pos + 3 * off, w->d_stage_pos + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaMemcpyAsync(vel + 3 * off, w->d_stage_vel + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyDeviceToHost, st));
+    if (at_rest) PG_CUDA(cudaMemcpyAsync(at_rest + off, w->d_stage_rest + off, bodies, cudaMemcpyDeviceToHost, st));
+  }
+  for (int k = 0; k < 3; k++) {
+    PG_CUDA(cudaEventRecord(w->pipe_done[k], w->pipe_stream[k]));
+    PG_CUDA(cudaStreamWaitEvent(w->stream, w->pipe_done[k], 0));
+  }
+  PG_CUDA(cudaEventRecord(w->ev1, w->stream));
+  w->last_steps = n_steps;
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  return PG_OK;
 }
 
 int pg_worlds_sync(PgWorlds *w) {

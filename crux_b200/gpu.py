@@ -41,6 +41,7 @@ API = [
     ("pg_worlds_download_state", _i, [_vp, _i, _i, _vp, _vp, _vp]),
     ("pg_worlds_step", _i, [_vp, _f, _i, _i]),
     ("pg_worlds_sync", _i, [_vp]),
+    ("pg_worlds_step_host", _i, [_vp, _f, _i, _vp, _vp, _vp]),
     ("pg_worlds_events", _ll, [_vp, _vp, _ll, _vp]),
     ("pg_worlds_stats", _i, [_vp, _vp, _vp]),
     ("pg_worlds_launches", _ll, [_vp]),
@@ -198,6 +199,11 @@ class GpuWorlds:
 
     def sync(self):
         _check(self.L.pg_worlds_sync(self.h), "pg_worlds_sync")
+
+    def step_host(self, dt: float, n_steps: int, pos: np.ndarray, vel: np.ndarray, at_rest=None):
+        """Host arrays in, n_steps steps, host arrays out (in place); chunk-pipelined inside the library."""
+        _check(self.L.pg_worlds_step_host(self.h, np.float32(dt), n_steps, _ptr(pos), _ptr(vel), _ptr(at_rest)),
+               "pg_worlds_step_host")
 
     def events(self) -> np.ndarray:
         over = C.c_int(0)

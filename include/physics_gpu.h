@@ -151,6 +151,10 @@ int  pg_worlds_download_state(PgWorlds *w, int first, int count, float *pos, flo
  * Asynchronous on the handle's stream; pg_worlds_sync() waits. */
 int  pg_worlds_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes);
 int  pg_worlds_sync(PgWorlds *w);
+/* Host-to-host step for sphere batches: upload pos/vel/at_rest ([n_worlds][n][3] / [n_worlds][n]),
+ * run n_steps steps, download into the same arrays -- one call, internally pipelined over chunks of
+ * worlds so that both PCIe directions and the kernels overlap.  Synchronous. */
+int  pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *vel, uint8_t *at_rest_or_null);
 /* Events of the last pg_worlds_step call, world-major then solve order.  Returns the total
  * number produced (may exceed cap; a world that overflowed max_events_per_world is reported
  * through *overflowed). */
