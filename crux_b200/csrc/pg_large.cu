@@ -46,7 +46,7 @@ constexpr int kMaxRounds = 4;
 constexpr unsigned kFullMask = 0xffffffffu;
 
 enum { K_PASS3 = 0, K_BOUNDS, K_CELLS, K_SCAN, K_SCATTER, K_PAIRS, K_EVAL, K_CHECK, K_FINAL, K_COUNT };
-const char *kKernelNames[K_COUNT] = {"k_pass3", "k_bounds", "k_cell_count", "k_scan", "k_scatter", "k_pairs", "k_eval", "k_check", "k_finalize"};
+const char *kKernelNames[K_COUNT] = {"k_pass3", "k_requery", "k_cell_count", "k_scan", "k_scatter", "k_pairs", "k_eval", "k_check", "k_finalize"};
 
 struct GridParams {
   float org[3];
@@ -89,6 +89,9 @@ struct LargeView {
   long long pairs_cap;
   // timelines, double buffered
   unsigned char *tl_cnt[2];
+  unsigned char *tl_dirty[2];         // timeline of the body differs from the previous iteration's
+  unsigned char *grown;               // envelope grew during the current fixed point
+  float *env_prev;                   // envelope the current candidate list was built with
   unsigned long long *tl_key[2];
   float4 *tl_pos[2], *tl_vel[2];
   Flags *flags;
@@ -158,8 +161,12 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes) {
     }
     const float e = envelope(q.w, q.x, q.y, q.z, dt);
     v.env[i] = e;
+    v.env_prev[i] = e;
+    v.grown[i] = 0;
     v.tl_cnt[0][i] = 0;
     v.tl_cnt[1][i] = 0;
+    v.tl_dirty[0][i] = 0;
+    v.tl_dirty[1][i] = 0;
     if (!(fabsf(p.x) < 1.0e15f && fabsf(p.y) < 1.0e15f && fabsf(p.z) < 1.0e15f && e < 1.0e15f)) { bad = true; continue; }
     lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
     hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
@@ -177,14 +184,6 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes) {
     atomicMax(v.bbox + 6, f2o(emax));
   }
   if (bad) atomicExch(&v.flags->unsafe, 1);
-}
-
-// Recompute only the bounds (after envelopes grew, or for the frozen-state pair query).
-__global__ void k_bounds(LargeView v) {
-  float emax = 0.0f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) emax = fmaxf(emax, v.env[i]);
-  for (int o = 16; o > 0; o >>= 1) emax = fmaxf(emax, __shfl_xor_sync(kFullMask, emax, o));
-  if ((threadIdx.x & 31) == 0) atomicMax(v.bbox + 6, f2o(emax));
 }
 
 __global__ void k_grid_params(LargeView v) {
@@ -353,7 +352,13 @@ struct BodyState { float px, py, pz, vx, vy, vz; };
 
 // State of body b just before the visit with key (row, col): post-pass-3 state, then the latest
 // timeline entry with a smaller key, then the body's own integration if its row lies between.
-__device__ __forceinline__ BodyState state_at(const LargeView &v, int src, int b, unsigned long long key, float dt, float *radius) {
+// `skip_key` (if non-zero) names an entry to ignore and `ovr` an entry to use in its place: the
+// fresh outcome of the pair's first visit when its second visit is evaluated (Gauss-Seidel inside
+// a pair; the fixed points are the same as without it).
+struct Override { unsigned long long key; bool present; float px, py, pz, vx, vy, vz; };
+
+__device__ __forceinline__ BodyState state_at(const LargeView &v, int src, int b, unsigned long long key, float dt, float *radius,
+                                             unsigned long long skip_key, const Override *ovr) {
   const float4 p = v.pos_rest[b], q = v.vel_rad[b];
   BodyState s;
   s.px = p.x; s.py = p.y; s.pz = p.z; s.vx = q.x; s.vy = q.y; s.vz = q.z;
@@ -364,12 +369,17 @@ __device__ __forceinline__ BodyState state_at(const LargeView &v, int src, int b
   int best_k = -1;
   for (int k = 0; k < cnt; k++) {
     const unsigned long long kk = v.tl_key[src][(size_t)b * kTimeline + k];
+    if (kk == skip_key) continue;
     if (kk < key && (best_k < 0 || kk > best)) { best = kk; best_k = k; }
   }
   if (best_k >= 0) {
     const float4 tp = v.tl_pos[src][(size_t)b * kTimeline + best_k], tv = v.tl_vel[src][(size_t)b * kTimeline + best_k];
     s.px = tp.x; s.py = tp.y; s.pz = tp.z; s.vx = tv.x; s.vy = tv.y; s.vz = tv.z;
     last_row = (long long)(best >> 32);
+  }
+  if (ovr && ovr->present && ovr->key < key && (best_k < 0 || ovr->key > best)) {
+    s.px = ovr->px; s.py = ovr->py; s.pz = ovr->pz; s.vx = ovr->vx; s.vy = ovr->vy; s.vz = ovr->vz;
+    last_row = (long long)(ovr->key >> 32);
   }
   const long long row = (long long)(key >> 32);
   if (row > b && last_row <= b && p.w == 0.0f) {            // own row finished in between: integrate (world.c:549-553)
@@ -398,17 +408,37 @@ __device__ __forceinline__ void timeline_push(const LargeView &v, int dst, int b
   v.tl_vel[dst][(size_t)b * kTimeline + slot] = make_float4(s.vx, s.vy, s.vz, 0.0f);
 }
 
-__device__ __forceinline__ void eval_visit(const LargeView &v, int src, int dst, int row, int col, float dt, pgm::LeafLen leaf) {
+// Evaluate one visit on the hypothesis `src`; on a hit append the outcome to both bodies' `dst`
+// timelines and report it through ovr_row / ovr_col.
+__device__ __forceinline__ bool eval_visit(const LargeView &v, int src, int dst, int row, int col, float dt, pgm::LeafLen leaf,
+                                           unsigned long long skip_key, const Override *in_row, const Override *in_col,
+                                           Override *out_row, Override *out_col) {
   const unsigned long long key = ((unsigned long long)(unsigned)row << 32) | (unsigned)col;
   float ra, rb;
-  const BodyState a = state_at(v, src, row, key, dt, &ra), b = state_at(v, src, col, key, dt, &rb);
+  const BodyState a = state_at(v, src, row, key, dt, &ra, skip_key, in_row), b = state_at(v, src, col, key, dt, &rb, skip_key, in_col);
   Sphere A, B;
   A.px = a.px; A.py = a.py; A.pz = a.pz; A.vx = a.vx; A.vy = a.vy; A.vz = a.vz; A.r = ra; A.rest = 0;
   B.px = b.px; B.py = b.py; B.pz = b.pz; B.vx = b.vx; B.vy = b.vy; B.vz = b.vz; B.r = rb; B.rest = 0;
-  if (!pgs::sphere_pair_exact(A, B, dt, leaf)) return;
+  if (!pgs::sphere_pair_exact(A, B, dt, leaf)) return false;
   timeline_push(v, dst, row, key, A);
   timeline_push(v, dst, col, key, B);
   atomicAdd(&v.flags->n_hits, 1ull);
+  if (out_row) { out_row->key = key; out_row->present = true; out_row->px = A.px; out_row->py = A.py; out_row->pz = A.pz; out_row->vx = A.vx; out_row->vy = A.vy; out_row->vz = A.vz; }
+  if (out_col) { out_col->key = key; out_col->present = true; out_col->px = B.px; out_col->py = B.py; out_col->pz = B.pz; out_col->vx = B.vx; out_col->vy = B.vy; out_col->vz = B.vz; }
+  return true;
+}
+
+// Copy the entry with `key` (if any) of body b from the src to the dst timeline.
+__device__ __forceinline__ bool carry_entry(const LargeView &v, int src, int dst, int b, unsigned long long key) {
+  const int cnt = min((int)v.tl_cnt[src][b], kTimeline);
+  for (int k = 0; k < cnt; k++) {
+    if (v.tl_key[src][(size_t)b * kTimeline + k] != key) continue;
+    const float4 tp = v.tl_pos[src][(size_t)b * kTimeline + k], tv = v.tl_vel[src][(size_t)b * kTimeline + k];
+    Sphere S; S.px = tp.x; S.py = tp.y; S.pz = tp.z; S.vx = tv.x; S.vy = tv.y; S.vz = tv.z; S.r = 0.0f; S.rest = 0;
+    timeline_push(v, dst, b, key, S);
+    return true;
+  }
+  return false;
 }
 
 __global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) {
@@ -416,10 +446,22 @@ __global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) {
   const long long np = (long long)min((unsigned long long)v.pairs_cap, v.flags->n_pairs);
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < np; k += (long long)gridDim.x * blockDim.x) {
     const int2 pr = v.pairs[k];
-    // a pair whose bodies both had empty timelines was evaluated on unchanged inputs before: skip
-    if (iter > 0 && v.tl_cnt[src][pr.x] == 0 && v.tl_cnt[src][pr.y] == 0) continue;
-    eval_visit(v, src, dst, pr.x, pr.y, dt, leaf);     // visit (i, j) of row i
-    eval_visit(v, src, dst, pr.y, pr.x, dt, leaf);     // visit (j, i) of row j
+    const int i = pr.x, j = pr.y;
+    const unsigned long long key1 = ((unsigned long long)(unsigned)i << 32) | (unsigned)j;
+    const unsigned long long key2 = ((unsigned long long)(unsigned)j << 32) | (unsigned)i;
+    if (iter > 0 && !v.tl_dirty[src][i] && !v.tl_dirty[src][j]) {
+      // both inputs are what they were one iteration ago: the outcome is too.  Nothing to do if
+      // there was none; otherwise carry the recorded contacts over unchanged.
+      if (v.tl_cnt[src][i] == 0 || v.tl_cnt[src][j] == 0) continue;
+      if (carry_entry(v, src, dst, i, key1)) { carry_entry(v, src, dst, j, key1); atomicAdd(&v.flags->n_hits, 1ull); }
+      if (carry_entry(v, src, dst, i, key2)) { carry_entry(v, src, dst, j, key2); atomicAdd(&v.flags->n_hits, 1ull); }
+      continue;
+    }
+    // visit (i, j) of row i, then visit (j, i) of row j on top of the first one's fresh outcome
+    Override oi, oj;
+    oi.present = false; oj.present = false; oi.key = key1; oj.key = key1;
+    eval_visit(v, src, dst, i, j, dt, leaf, 0ull, nullptr, nullptr, &oi, &oj);
+    eval_visit(v, src, dst, j, i, dt, leaf, key1, &oj, &oi, nullptr, nullptr);
   }
 }
 
@@ -427,7 +469,7 @@ __global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) {
 __global__ void k_check(LargeView v, int src, int dst, float dt) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < v.n; b += gridDim.x * blockDim.x) {
     const int c0 = min((int)v.tl_cnt[src][b], kTimeline), c1 = min((int)v.tl_cnt[dst][b], kTimeline);
-    if (c0 == 0 && c1 == 0) continue;
+    if (c0 == 0 && c1 == 0) { v.tl_dirty[dst][b] = 0; continue; }
     bool same = (v.tl_cnt[src][b] == v.tl_cnt[dst][b]);
     if (same) {
       for (int k = 0; k < c1 && same; k++) {
@@ -445,6 +487,7 @@ __global__ void k_check(LargeView v, int src, int dst, float dt) {
         same = found;
       }
     }
+    v.tl_dirty[dst][b] = same ? 0 : 1;
     if (!same) v.flags->changed = 1;
     // envelope validation on the new timeline: every state the body takes must stay inside env[b]
     const float4 p = v.pos_rest[b], q = v.vel_rad[b];
@@ -462,9 +505,55 @@ __global__ void k_check(LargeView v, int src, int dst, float dt) {
     }
     if (need > v.env[b]) {
       v.env[b] = need * 1.05f;
+      v.grown[b] = 1;
       v.flags->grew = 1;
+      atomicMax(v.bbox + 6, f2o(need * 1.05f));      // largest envelope in the world, for k_requery's search radius
       if (!(need < 1.0e15f)) v.flags->unsafe = 1;
     }
+  }
+}
+
+// Envelopes of a few bodies grew (a contact sped them up).  Find the candidate pairs they gain --
+// touching under the new envelopes but not under the ones the list was built with -- through the
+// existing grid, append them, and mark the grown bodies dirty so that the next iteration evaluates
+// everything they are part of.  If both bodies of a pair grew, the lower index appends it.
+__global__ void k_requery(LargeView v, int src) {
+  const GridParams g = *v.grid;
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < v.n; b += gridDim.x * blockDim.x) {
+    if (!v.grown[b]) continue;
+    const float4 p = v.pos_rest[b];
+    const float eb = v.env[b], eb_old = v.env_prev[b];
+    v.tl_dirty[src][b] = 1;
+    // a partner x can be up to eb + env_x <= eb + emax away: search that many cells in every direction
+    const float emax = o2f(v.bbox[6]);
+    const int R = (int)ceilf((eb + emax) * g.inv_h * 1.001f);
+    if (!(R >= 1) || R > 8) { v.flags->unsafe = 2; continue; }
+    const int3 c = cell_coords(g, p.x, p.y, p.z);
+    for (int dz = -R; dz <= R; dz++) for (int dy = -R; dy <= R; dy++) {
+      const int y = c.y + dy, z = c.z + dz;
+      if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
+      const int x0 = max(c.x - R, 0), x1 = min(c.x + R, g.dim[0] - 1);
+      const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+      for (unsigned a = v.cell_cnt[row + x0]; a < v.cell_cnt[row + x1 + 1]; a++) {
+        const int x = (int)v.sorted_idx[a];
+        if (x == b) continue;
+        const float4 cx = v.sorted_cenv[a];
+        const float dx = p.x - cx.x, dyy = p.y - cx.y, dzz = p.z - cx.z;
+        const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
+        const float ex = v.env[x], ex_old = v.env_prev[x];
+        const float Tn = eb + ex, To = eb_old + ex_old;
+        if (!(d2 <= Tn * Tn) || d2 <= To * To) continue;          // not a candidate, or already listed
+        if (v.grown[x] && x < b) continue;                        // the other grown body appends it
+        const unsigned long long slot = atomicAdd(&v.flags->n_pairs, 1ull);
+        if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2(min(b, x), max(b, x));
+        else atomicExch(&v.flags->overflow_pairs, 1);
+      }
+    }
+  }
+}
+__global__ void k_requery_done(LargeView v) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < v.n; b += gridDim.x * blockDim.x) {
+    if (v.grown[b]) { v.grown[b] = 0; v.env_prev[b] = v.env[b]; }
   }
 }
 
@@ -610,51 +699,60 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   LW_LAUNCH(w, K_PASS3, k_pass3, lw_grid(w, v.n, 256), 256, v, dt, w->step_in_call, 1);
   w->last_proven = 1;
   w->last_iterations = 0;
-  int src = 0;
-  for (int round = 0; round < kMaxRounds; round++) {
-    int rc = lw_build_pairs(w);
-    if (rc) return rc;
-    Flags f;
-    int dst = 1;
-    src = 0;
-    bool converged = false;
-    for (int it = 0; it < kMaxIter; it++) {
-      PG_CUDA(cudaMemsetAsync(v.tl_cnt[dst], 0, (size_t)v.n + 4, w->stream));
-      PG_CUDA(cudaMemsetAsync(&v.flags->changed, 0, sizeof(int), w->stream));
-      PG_CUDA(cudaMemsetAsync(&v.flags->n_hits, 0, sizeof(unsigned long long), w->stream));
-      if (it == 0) {
-        rc = lw_read_flags(w, &f);          // pair count: size the eval grid, detect overflow
-        if (rc) return rc;
-        lw_accumulate(w, K_PASS3); lw_accumulate(w, K_SCAN); lw_accumulate(w, K_SCATTER); lw_accumulate(w, K_PAIRS);
-        if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
-        if (f.unsafe) { pg_set_error("large world: non-finite body state"); return PG_ERR_ARG; }
-        w->last_candidates = (long long)f.n_pairs;
-      }
-      const int np = (int)std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
-      LW_LAUNCH(w, K_EVAL, k_eval, lw_grid(w, std::max(np, 1), 128), 128, v, src, dst, it, dt);
-      LW_LAUNCH(w, K_CHECK, k_check, lw_grid(w, v.n, 256), 256, v, src, dst, dt);
-      Flags g;
-      rc = lw_read_flags(w, &g);
-      if (rc) return rc;
-      lw_accumulate(w, K_EVAL); lw_accumulate(w, K_CHECK);
-      w->last_iterations++;
-      w->last_hits = (long long)g.n_hits;
-      if (g.overflow_timeline) { pg_set_error("large world: more than %d contacts on one body in one step", kTimeline); return PG_ERR_CAPACITY; }
-      std::swap(src, dst);
-      f = g;
-      if (!g.changed) { converged = true; break; }
-    }
-    if (!converged) w->last_proven = 0;
-    if (!f.grew) break;
-    if (round == kMaxRounds - 1) { w->last_proven = 0; break; }
-    // envelopes grew: regenerate candidates with the new envelopes and redo the fixed point
-    const unsigned zero = 0;
-    PG_CUDA(cudaMemcpyAsync(v.bbox + 6, &zero, sizeof(unsigned), cudaMemcpyHostToDevice, w->stream));
+  int src = 0, dst = 1;
+  int rc = lw_build_pairs(w);
+  if (rc) return rc;
+  Flags f;
+  rc = lw_read_flags(w, &f);            // pair count: sizes the eval grid, detects overflow
+  if (rc) return rc;
+  lw_accumulate(w, K_PASS3); lw_accumulate(w, K_SCAN); lw_accumulate(w, K_SCATTER); lw_accumulate(w, K_PAIRS);
+  if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
+  if (f.unsafe) { pg_set_error("large world: non-finite body state"); return PG_ERR_ARG; }
+  w->last_candidates = (long long)f.n_pairs;
+  const bool debug = getenv("PG_LARGE_DEBUG") != nullptr;
+  bool converged = false;
+  int requeries = 0;
+  for (int it = 0; it < kMaxIter; it++) {
+    PG_CUDA(cudaMemsetAsync(v.tl_cnt[dst], 0, (size_t)v.n + 4, w->stream));
+    PG_CUDA(cudaMemsetAsync(&v.flags->changed, 0, sizeof(int), w->stream));
     PG_CUDA(cudaMemsetAsync(&v.flags->grew, 0, sizeof(int), w->stream));
-    PG_CUDA(cudaMemsetAsync(v.tl_cnt[0], 0, (size_t)v.n + 4, w->stream));
-    PG_CUDA(cudaMemsetAsync(v.tl_cnt[1], 0, (size_t)v.n + 4, w->stream));
-    LW_LAUNCH(w, K_BOUNDS, k_bounds, lw_grid(w, v.n, 256), 256, v);
+    PG_CUDA(cudaMemsetAsync(&v.flags->n_hits, 0, sizeof(unsigned long long), w->stream));
+    const int np = (int)std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
+    LW_LAUNCH(w, K_EVAL, k_eval, lw_grid(w, std::max(np, 1), 128), 128, v, src, dst, it, dt);
+    LW_LAUNCH(w, K_CHECK, k_check, lw_grid(w, v.n, 256), 256, v, src, dst, dt);
+    rc = lw_read_flags(w, &f);
+    if (rc) return rc;
+    lw_accumulate(w, K_EVAL); lw_accumulate(w, K_CHECK);
+    if (debug) {
+      float e = 0, c = 0;
+      cudaEventElapsedTime(&e, w->kev[K_EVAL][0], w->kev[K_EVAL][1]);
+      cudaEventElapsedTime(&c, w->kev[K_CHECK][0], w->kev[K_CHECK][1]);
+      fprintf(stderr, "  [pg_large] iter %d: eval %.3f ms check %.3f ms hits %llu changed %d grew %d pairs %llu\n", it, e, c,
+              (unsigned long long)f.n_hits, f.changed, f.grew, (unsigned long long)f.n_pairs);
+    }
+    w->last_iterations++;
+    w->last_hits = (long long)f.n_hits;
+    if (f.overflow_timeline) { pg_set_error("large world: more than %d contacts on one body in one step", kTimeline); return PG_ERR_CAPACITY; }
+    std::swap(src, dst);
+    if (f.grew) {
+      // candidates the grown envelopes add; their bodies are marked dirty so the next iteration
+      // re-evaluates them on top of the current timelines (warm start)
+      LW_LAUNCH(w, K_BOUNDS, k_requery, lw_grid(w, v.n, 256), 256, v, src);
+      k_requery_done<<<lw_grid(w, v.n, 256), 256, 0, w->stream>>>(v);
+      w->launches++;
+      rc = lw_read_flags(w, &f);
+      if (rc) return rc;
+      lw_accumulate(w, K_BOUNDS);
+      if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
+      if (f.unsafe) { w->last_proven = 0; if (debug) fprintf(stderr, "  [pg_large] envelope outgrew the grid: result not proven\n"); }
+      w->last_candidates = (long long)f.n_pairs;
+      requeries++;
+      continue;                           // at least one more iteration with the new pairs
+    }
+    if (!f.changed) { converged = true; break; }
   }
+  if (!converged) w->last_proven = 0;
+  (void)requeries;
   LW_LAUNCH(w, K_FINAL, k_finalize, lw_grid(w, v.n, 256), 256, v, src, dt, w->step_in_call);
   PG_CUDA(cudaGetLastError());
   PG_CUDA(cudaStreamSynchronize(w->stream));
@@ -697,7 +795,12 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   PG_CUDA_NULL(cudaMalloc(&v.sorted_idx, sizeof(unsigned) * n));
   PG_CUDA_NULL(cudaMalloc(&v.sorted_cenv, sizeof(float4) * n));
   PG_CUDA_NULL(cudaMalloc(&v.pairs, sizeof(int2) * (size_t)v.pairs_cap));
+  PG_CUDA_NULL(cudaMalloc(&v.grown, n + 8));
+  PG_CUDA_NULL(cudaMemset(v.grown, 0, n + 8));
+  PG_CUDA_NULL(cudaMalloc(&v.env_prev, sizeof(float) * n));
   for (int k = 0; k < 2; k++) {
+    PG_CUDA_NULL(cudaMalloc(&v.tl_dirty[k], n + 8));
+    PG_CUDA_NULL(cudaMemset(v.tl_dirty[k], 0, n + 8));
     PG_CUDA_NULL(cudaMalloc(&v.tl_cnt[k], n + 8));
     PG_CUDA_NULL(cudaMemset(v.tl_cnt[k], 0, n + 8));
     PG_CUDA_NULL(cudaMalloc(&v.tl_key[k], sizeof(unsigned long long) * n * kTimeline));
@@ -721,7 +824,7 @@ void pg_large_destroy(PgLarge *w) {
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
   void *ptrs[] = {v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.cell_fill, v.block_sums, v.sorted_idx,
-                  v.sorted_cenv, v.pairs, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
+                  v.sorted_cenv, v.pairs, v.grown, v.env_prev, v.tl_dirty[0], v.tl_dirty[1], v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
                   v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);
   cudaEventDestroy(w->ev0); cudaEventDestroy(w->ev1);
