@@ -64,6 +64,8 @@ struct Flags {
   int unsafe;             // non-finite state or an envelope the grid cannot hold
   unsigned long long n_pairs;
   unsigned long long n_hits;
+  unsigned n_touched;
+  unsigned pad0;
   float max_env_bits_pad;
 };
 
@@ -89,7 +91,11 @@ struct LargeView {
   long long pairs_cap;
   // timelines, double buffered
   unsigned char *tl_cnt[2];
-  unsigned char *tl_dirty[2];         // timeline of the body differs from the previous iteration's
+  unsigned long long *tl_chg[2];      // smallest key of an entry that DISAPPEARED since the previous iteration (~0 = none);
+                                      // new / changed entries carry a flag in tl_pos[..].w
+  int *seen;                          // body already on the touched list (this step)
+  int *touched;                       // bodies that ever received a timeline entry this step
+  unsigned *cell_rank;                // rank of a body inside its cell (returned by the counting atomic)
   unsigned char *grown;               // envelope grew during the current fixed point
   float *env_prev;                   // envelope the current candidate list was built with
   unsigned long long *tl_key[2];
@@ -165,8 +171,9 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes) {
     v.grown[i] = 0;
     v.tl_cnt[0][i] = 0;
     v.tl_cnt[1][i] = 0;
-    v.tl_dirty[0][i] = 0;
-    v.tl_dirty[1][i] = 0;
+    v.tl_chg[0][i] = 0xffffffffffffffffull;
+    v.tl_chg[1][i] = 0xffffffffffffffffull;
+    v.seen[i] = 0;
     if (!(fabsf(p.x) < 1.0e15f && fabsf(p.y) < 1.0e15f && fabsf(p.z) < 1.0e15f && e < 1.0e15f)) { bad = true; continue; }
     lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
     hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
@@ -226,7 +233,7 @@ __global__ void k_cell_count(LargeView v) {
     const int3 c = cell_coords(g, p.x, p.y, p.z);
     const unsigned cell = (unsigned)((c.z * g.dim[1] + c.y) * g.dim[0] + c.x);
     v.cell_of[i] = cell;
-    atomicAdd(v.cell_cnt + cell, 1u);
+    v.cell_rank[i] = atomicAdd(v.cell_cnt + cell, 1u);
   }
 }
 
@@ -285,13 +292,13 @@ __global__ void k_scan_add(LargeView v) {
   const unsigned add = v.block_sums[blockIdx.x];
   const int base = blockIdx.x * kScanBlock * kScanItems + threadIdx.x * kScanItems;
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++) if (base + k < n) { v.cell_cnt[base + k] += add; if (base + k < n - 1) v.cell_fill[base + k] = 0u; }
+  for (int k = 0; k < kScanItems; k++) if (base + k < n) v.cell_cnt[base + k] += add;
 }
 
 __global__ void k_scatter(LargeView v) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
     const unsigned cell = v.cell_of[i];
-    const unsigned slot = v.cell_cnt[cell] + atomicAdd(v.cell_fill + cell, 1u);
+    const unsigned slot = v.cell_cnt[cell] + v.cell_rank[i];
     const float4 p = v.pos_rest[i];
     v.sorted_idx[slot] = (unsigned)i;
     v.sorted_cenv[slot] = make_float4(p.x, p.y, p.z, v.env[i]);
@@ -403,6 +410,7 @@ __device__ __forceinline__ void timeline_push(const LargeView &v, int dst, int b
     old = atomicCAS(word, assumed, assumed + (1u << sh));
   } while (old != assumed);
   if (slot >= kTimeline) { atomicExch(&v.flags->overflow_timeline, 1); return; }
+  if (slot == 0 && atomicExch(&v.seen[b], 1) == 0) v.touched[atomicAdd(&v.flags->n_touched, 1u)] = b;
   v.tl_key[dst][(size_t)b * kTimeline + slot] = key;
   v.tl_pos[dst][(size_t)b * kTimeline + slot] = make_float4(s.px, s.py, s.pz, 0.0f);
   v.tl_vel[dst][(size_t)b * kTimeline + slot] = make_float4(s.vx, s.vy, s.vz, 0.0f);
@@ -441,21 +449,46 @@ __device__ __forceinline__ bool carry_entry(const LargeView &v, int src, int dst
   return false;
 }
 
+// Did anything body b contributes to a visit with key K change since the previous iteration?
+// (entries with key < K other than `except`: new or different state -> flagged in .w; gone -> tl_chg)
+__device__ __forceinline__ bool affected(const LargeView &v, int src, int b, unsigned long long K, unsigned long long except) {
+  const unsigned long long rem = v.tl_chg[src][b];
+  if (rem < K) return true;                    // (conservative when rem == except: other removals may hide behind it)
+  const int cnt = min((int)v.tl_cnt[src][b], kTimeline);
+  for (int k = 0; k < cnt; k++) {
+    const unsigned long long kk = v.tl_key[src][(size_t)b * kTimeline + k];
+    if (kk < K && kk != except && v.tl_pos[src][(size_t)b * kTimeline + k].w != 0.0f) return true;
+  }
+  return false;
+}
+
 __global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) {
   pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
   const long long np = (long long)min((unsigned long long)v.pairs_cap, v.flags->n_pairs);
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < np; k += (long long)gridDim.x * blockDim.x) {
     const int2 pr = v.pairs[k];
-    const int i = pr.x, j = pr.y;
+    const bool fresh = pr.x < 0;                     // appended by k_requery: never evaluated yet
+    const int i = fresh ? ~pr.x : pr.x, j = pr.y;
+    if (fresh) v.pairs[k].x = i;
     const unsigned long long key1 = ((unsigned long long)(unsigned)i << 32) | (unsigned)j;
     const unsigned long long key2 = ((unsigned long long)(unsigned)j << 32) | (unsigned)i;
-    if (iter > 0 && !v.tl_dirty[src][i] && !v.tl_dirty[src][j]) {
-      // both inputs are what they were one iteration ago: the outcome is too.  Nothing to do if
-      // there was none; otherwise carry the recorded contacts over unchanged.
-      if (v.tl_cnt[src][i] == 0 || v.tl_cnt[src][j] == 0) continue;
-      if (carry_entry(v, src, dst, i, key1)) { carry_entry(v, src, dst, j, key1); atomicAdd(&v.flags->n_hits, 1ull); }
-      if (carry_entry(v, src, dst, i, key2)) { carry_entry(v, src, dst, j, key2); atomicAdd(&v.flags->n_hits, 1ull); }
-      continue;
+    if (iter > 0 && !fresh) {
+      // A visit depends only on the entries with SMALLER keys of its two bodies.  If none of those
+      // appeared, changed or disappeared since the previous iteration, its outcome is the recorded
+      // one: carry it over instead of re-evaluating.  The second visit saw the first one's outcome
+      // directly (Gauss-Seidel), so that entry is excluded from its test.
+      const bool need1 = affected(v, src, i, key1, 0ull) || affected(v, src, j, key1, 0ull);
+      if (!need1) {
+        const bool have_i = v.tl_cnt[src][i] != 0, have_j = v.tl_cnt[src][j] != 0;
+        if (have_i && have_j && carry_entry(v, src, dst, i, key1)) { carry_entry(v, src, dst, j, key1); atomicAdd(&v.flags->n_hits, 1ull); }
+        const bool need2 = affected(v, src, i, key2, key1) || affected(v, src, j, key2, key1);
+        if (!need2) {
+          if (have_i && have_j && carry_entry(v, src, dst, i, key2)) { carry_entry(v, src, dst, j, key2); atomicAdd(&v.flags->n_hits, 1ull); }
+        } else {
+          eval_visit(v, src, dst, j, i, dt, leaf, 0ull, nullptr, nullptr, nullptr, nullptr);
+        }
+        continue;
+      }
     }
     // visit (i, j) of row i, then visit (j, i) of row j on top of the first one's fresh outcome
     Override oi, oj;
@@ -465,30 +498,41 @@ __global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) {
   }
 }
 
-// Compare timelines of two iterations (as sorted-by-key sequences) and validate envelopes.
+// Compare the timelines of two iterations (as sets keyed by visit) and validate envelopes, for the
+// bodies that have ever been touched this step.
+__device__ __forceinline__ bool same_state(float4 p0, float4 q0, float4 p1, float4 q1) {
+  return __float_as_uint(p0.x) == __float_as_uint(p1.x) && __float_as_uint(p0.y) == __float_as_uint(p1.y) &&
+         __float_as_uint(p0.z) == __float_as_uint(p1.z) && __float_as_uint(q0.x) == __float_as_uint(q1.x) &&
+         __float_as_uint(q0.y) == __float_as_uint(q1.y) && __float_as_uint(q0.z) == __float_as_uint(q1.z);
+}
 __global__ void k_check(LargeView v, int src, int dst, float dt) {
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < v.n; b += gridDim.x * blockDim.x) {
+  const int nt = (int)v.flags->n_touched;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    const int b = v.touched[t];
     const int c0 = min((int)v.tl_cnt[src][b], kTimeline), c1 = min((int)v.tl_cnt[dst][b], kTimeline);
-    if (c0 == 0 && c1 == 0) { v.tl_dirty[dst][b] = 0; continue; }
-    bool same = (v.tl_cnt[src][b] == v.tl_cnt[dst][b]);
-    if (same) {
-      for (int k = 0; k < c1 && same; k++) {
-        const unsigned long long key = v.tl_key[dst][(size_t)b * kTimeline + k];
-        bool found = false;
-        for (int m = 0; m < c0; m++) {
-          if (v.tl_key[src][(size_t)b * kTimeline + m] != key) continue;
-          const float4 p0 = v.tl_pos[src][(size_t)b * kTimeline + m], p1 = v.tl_pos[dst][(size_t)b * kTimeline + k];
-          const float4 q0 = v.tl_vel[src][(size_t)b * kTimeline + m], q1 = v.tl_vel[dst][(size_t)b * kTimeline + k];
-          found = __float_as_uint(p0.x) == __float_as_uint(p1.x) && __float_as_uint(p0.y) == __float_as_uint(p1.y) &&
-                  __float_as_uint(p0.z) == __float_as_uint(p1.z) && __float_as_uint(q0.x) == __float_as_uint(q1.x) &&
-                  __float_as_uint(q0.y) == __float_as_uint(q1.y) && __float_as_uint(q0.z) == __float_as_uint(q1.z);
-          break;
-        }
-        same = found;
+    unsigned long long rem = 0xffffffffffffffffull;
+    bool any = false;
+    for (int k = 0; k < c1; k++) {
+      const unsigned long long key = v.tl_key[dst][(size_t)b * kTimeline + k];
+      bool found = false;
+      for (int m = 0; m < c0; m++) {
+        if (v.tl_key[src][(size_t)b * kTimeline + m] != key) continue;
+        found = same_state(v.tl_pos[src][(size_t)b * kTimeline + m], v.tl_vel[src][(size_t)b * kTimeline + m],
+                           v.tl_pos[dst][(size_t)b * kTimeline + k], v.tl_vel[dst][(size_t)b * kTimeline + k]);
+        break;
       }
+      v.tl_pos[dst][(size_t)b * kTimeline + k].w = found ? 0.0f : 1.0f;      // new or changed entry
+      any = any || !found;
     }
-    v.tl_dirty[dst][b] = same ? 0 : 1;
-    if (!same) v.flags->changed = 1;
+    for (int m = 0; m < c0; m++) {
+      const unsigned long long key = v.tl_key[src][(size_t)b * kTimeline + m];
+      bool found = false;
+      for (int k = 0; k < c1; k++) if (v.tl_key[dst][(size_t)b * kTimeline + k] == key) { found = true; break; }
+      if (!found && key < rem) rem = key;
+    }
+    if (v.tl_cnt[src][b] != v.tl_cnt[dst][b] && rem == 0xffffffffffffffffull && !any) rem = 0ull;      // overflowed counts: be safe
+    v.tl_chg[dst][b] = rem;
+    if (any || rem != 0xffffffffffffffffull) v.flags->changed = 1;
     // envelope validation on the new timeline: every state the body takes must stay inside env[b]
     const float4 p = v.pos_rest[b], q = v.vel_rad[b];
     float need = 0.0f;
@@ -512,18 +556,25 @@ __global__ void k_check(LargeView v, int src, int dst, float dt) {
     }
   }
 }
+// reset the destination timelines of the touched bodies before an iteration refills them
+__global__ void k_clear(LargeView v, int dst) {
+  const int nt = (int)v.flags->n_touched;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) v.tl_cnt[dst][v.touched[t]] = 0;
+}
 
 // Envelopes of a few bodies grew (a contact sped them up).  Find the candidate pairs they gain --
 // touching under the new envelopes but not under the ones the list was built with -- through the
-// existing grid, append them, and mark the grown bodies dirty so that the next iteration evaluates
-// everything they are part of.  If both bodies of a pair grew, the lower index appends it.
+// existing grid and append them marked as fresh, so that the next iteration evaluates them (pairs
+// that were already listed keep their recorded outcomes).  If both bodies of a pair grew, the lower
+// index appends it.
 __global__ void k_requery(LargeView v, int src) {
   const GridParams g = *v.grid;
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < v.n; b += gridDim.x * blockDim.x) {
+  const int nt = (int)v.flags->n_touched;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    const int b = v.touched[t];
     if (!v.grown[b]) continue;
     const float4 p = v.pos_rest[b];
     const float eb = v.env[b], eb_old = v.env_prev[b];
-    v.tl_dirty[src][b] = 1;
     // a partner x can be up to eb + env_x <= eb + emax away: search that many cells in every direction
     const float emax = o2f(v.bbox[6]);
     const int R = (int)ceilf((eb + emax) * g.inv_h * 1.001f);
@@ -545,14 +596,16 @@ __global__ void k_requery(LargeView v, int src) {
         if (!(d2 <= Tn * Tn) || d2 <= To * To) continue;          // not a candidate, or already listed
         if (v.grown[x] && x < b) continue;                        // the other grown body appends it
         const unsigned long long slot = atomicAdd(&v.flags->n_pairs, 1ull);
-        if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2(min(b, x), max(b, x));
+        if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2(~min(b, x), max(b, x));   // ~i marks it fresh
         else atomicExch(&v.flags->overflow_pairs, 1);
       }
     }
   }
 }
 __global__ void k_requery_done(LargeView v) {
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < v.n; b += gridDim.x * blockDim.x) {
+  const int nt = (int)v.flags->n_touched;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    const int b = v.touched[t];
     if (v.grown[b]) { v.grown[b] = 0; v.env_prev[b] = v.env[b]; }
   }
 }
@@ -713,13 +766,15 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   bool converged = false;
   int requeries = 0;
   for (int it = 0; it < kMaxIter; it++) {
-    PG_CUDA(cudaMemsetAsync(v.tl_cnt[dst], 0, (size_t)v.n + 4, w->stream));
+    const int nt_grid = lw_grid(w, std::max((int)f.n_touched, 1), 256);
+    k_clear<<<nt_grid, 256, 0, w->stream>>>(v, dst);
+    w->launches++;
     PG_CUDA(cudaMemsetAsync(&v.flags->changed, 0, sizeof(int), w->stream));
     PG_CUDA(cudaMemsetAsync(&v.flags->grew, 0, sizeof(int), w->stream));
     PG_CUDA(cudaMemsetAsync(&v.flags->n_hits, 0, sizeof(unsigned long long), w->stream));
     const int np = (int)std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
     LW_LAUNCH(w, K_EVAL, k_eval, lw_grid(w, std::max(np, 1), 128), 128, v, src, dst, it, dt);
-    LW_LAUNCH(w, K_CHECK, k_check, lw_grid(w, v.n, 256), 256, v, src, dst, dt);
+    LW_LAUNCH(w, K_CHECK, k_check, lw_grid(w, std::max(np, 1), 256), 256, v, src, dst, dt);
     rc = lw_read_flags(w, &f);
     if (rc) return rc;
     lw_accumulate(w, K_EVAL); lw_accumulate(w, K_CHECK);
@@ -737,8 +792,8 @@ static int lw_step_once(PgLarge *w, float dt_in) {
     if (f.grew) {
       // candidates the grown envelopes add; their bodies are marked dirty so the next iteration
       // re-evaluates them on top of the current timelines (warm start)
-      LW_LAUNCH(w, K_BOUNDS, k_requery, lw_grid(w, v.n, 256), 256, v, src);
-      k_requery_done<<<lw_grid(w, v.n, 256), 256, 0, w->stream>>>(v);
+      LW_LAUNCH(w, K_BOUNDS, k_requery, lw_grid(w, std::max((int)f.n_touched, 1), 128), 128, v, src);
+      k_requery_done<<<lw_grid(w, std::max((int)f.n_touched, 1), 256), 256, 0, w->stream>>>(v);
       w->launches++;
       rc = lw_read_flags(w, &f);
       if (rc) return rc;
@@ -798,9 +853,11 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   PG_CUDA_NULL(cudaMalloc(&v.grown, n + 8));
   PG_CUDA_NULL(cudaMemset(v.grown, 0, n + 8));
   PG_CUDA_NULL(cudaMalloc(&v.env_prev, sizeof(float) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.seen, sizeof(int) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.touched, sizeof(int) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.cell_rank, sizeof(unsigned) * n));
   for (int k = 0; k < 2; k++) {
-    PG_CUDA_NULL(cudaMalloc(&v.tl_dirty[k], n + 8));
-    PG_CUDA_NULL(cudaMemset(v.tl_dirty[k], 0, n + 8));
+    PG_CUDA_NULL(cudaMalloc(&v.tl_chg[k], sizeof(unsigned long long) * n));
     PG_CUDA_NULL(cudaMalloc(&v.tl_cnt[k], n + 8));
     PG_CUDA_NULL(cudaMemset(v.tl_cnt[k], 0, n + 8));
     PG_CUDA_NULL(cudaMalloc(&v.tl_key[k], sizeof(unsigned long long) * n * kTimeline));
@@ -824,7 +881,7 @@ void pg_large_destroy(PgLarge *w) {
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
   void *ptrs[] = {v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.cell_fill, v.block_sums, v.sorted_idx,
-                  v.sorted_cenv, v.pairs, v.grown, v.env_prev, v.tl_dirty[0], v.tl_dirty[1], v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
+                  v.sorted_cenv, v.pairs, v.grown, v.env_prev, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
                   v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);
   cudaEventDestroy(w->ev0); cudaEventDestroy(w->ev1);
