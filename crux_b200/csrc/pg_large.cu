@@ -72,8 +72,17 @@ struct Flags {
 struct LargeView {
   int n, ns;
   float4 *pos_rest, *vel_rad;        // state (in/out), body order = reference array order
-  float4 *planes;
+  float4 *planes;                    // the static PLANES, array order
+  int *plane_sidx;                   // their index in the static array
   float restitution;
+  // level geometry: static AABBs (world boxes precomputed on the host) in a uniform grid
+  int n_static_total, n_boxes;
+  float4 *box_c, *box_e;             // [n_static_total] world centre / extents (boxes only)
+  unsigned char *static_type;        // [n_static_total] PG_AABB / PG_PLANE
+  float sg_org[3], sg_inv_h, sg_reach;   // cell(p) = floor((p - org) * inv_h); boxes inserted inflated by sg_reach
+  int sg_dim[3];
+  unsigned *sg_start;                // [cells + 1]
+  int *sg_items;                     // static indices, ascending inside a cell
   float *env;                        // envelope radius per body
   // reductions
   unsigned *bbox;                    // 6 ordered-uint encodings: min xyz, max xyz ; [6] = max env
@@ -149,18 +158,63 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes) {
     float4 p = v.pos_rest[i], q = v.vel_rad[i];
     if (do_planes) {
       bool touched = false;
-      for (int k = 0; k < v.ns; k++) {
+      const V3 p0 = v3(p.x, p.y, p.z);        // scene-node translation: the position at step start
+      auto do_plane = [&](int k) {
         const float4 pl = s_pl[k];
         const float rho = pgs::reach(q.w, q.x, q.y, q.z, dt);
         const float s0 = __fmaf_rn(p.x, pl.x, __fmaf_rn(p.y, pl.y, p.z * pl.z)) - pl.w;
-        if (gate_ok && fabsf(s0) > rho * 1.0001f + 1.0e-5f * (fabsf(s0) + fabsf(pl.w) + 1.0f)) continue;
+        if (gate_ok && fabsf(s0) > rho * 1.0001f + 1.0e-5f * (fabsf(s0) + fabsf(pl.w) + 1.0f)) return;
         Sphere A;
         A.px = p.x; A.py = p.y; A.pz = p.z; A.vx = q.x; A.vy = q.y; A.vz = q.z; A.r = q.w; A.rest = 0;
         if (pgs::sphere_plane_exact(A, pl, v.restitution, dt, leaf)) {
           p.x = A.px; p.y = A.py; p.z = A.pz; q.x = A.vx; q.y = A.vy; q.z = A.vz;
           if (A.rest) p.w = 1.0f;
           touched = true;
-          emit_event(v, step, 3, PG_CLASS_DYNAMIC, i, PG_CLASS_STATIC, k);
+          emit_event(v, step, 3, PG_CLASS_DYNAMIC, i, PG_CLASS_STATIC, v.plane_sidx[k]);
+        }
+      };
+      auto do_box = [&](int j) {
+        pgm::BoxS bx;
+        const float4 bc = v.box_c[j], be = v.box_e[j];
+        bx.c = v3(bc.x, bc.y, bc.z); bx.e = v3(be.x, be.y, be.z);
+        const V3 vel = v3(q.x, q.y, q.z);
+        const float nv = pgm::norm(vel);
+        // cheap gate on the root test: distance at t=0 must not exceed r + |v| dt
+        const float rho = __fmaf_rn(nv, dt, q.w) * 1.0001f + 1.0e-6f;
+        const float d2 = pgm::bb_d2(v3(0.0f + p0.x, 0.0f + p0.y, 0.0f + p0.z), bx);
+        if (gate_ok && d2 > rho * rho * 1.0001f) return;
+        if (!pgm::bb_interval(p0, vel, nv, q.w, bx, 0.0f, dt, leaf)) return;
+        const pgm::Contact c = pgm::bb_narrow(p0, vel, q.w, bx, dt);
+        if (!(c.hit && c.t >= 0)) return;
+        V3 pos = v3(p.x, p.y, p.z), vv = vel;
+        pgm::bb_resolve(pos, vv, p0, q.w, v.restitution, bx, c.t);
+        p.x = pos.x; p.y = pos.y; p.z = pos.z; q.x = vv.x; q.y = vv.y; q.z = vv.z;
+        touched = true;
+        emit_event(v, step, 3, PG_CLASS_STATIC, j, PG_CLASS_DYNAMIC, i);      // the box is body_A (lower collider type)
+      };
+      if (v.n_boxes == 0) {
+        for (int k = 0; k < v.ns; k++) do_plane(k);
+      } else {
+        // planes and the boxes registered in this sphere's level-grid cell, merged in static-array order
+        const float rho0 = pgs::reach(q.w, q.x, q.y, q.z, dt);
+        int cx = (int)floorf((p0.x - v.sg_org[0]) * v.sg_inv_h), cy = (int)floorf((p0.y - v.sg_org[1]) * v.sg_inv_h),
+            cz = (int)floorf((p0.z - v.sg_org[2]) * v.sg_inv_h);
+        const bool inside = cx >= 0 && cy >= 0 && cz >= 0 && cx < v.sg_dim[0] && cy < v.sg_dim[1] && cz < v.sg_dim[2];
+        if (rho0 * 1.01f + 1.0e-3f <= v.sg_reach) {
+          unsigned ib = 0, ie = 0;
+          if (inside) { const int cell = (cz * v.sg_dim[1] + cy) * v.sg_dim[0] + cx; ib = v.sg_start[cell]; ie = v.sg_start[cell + 1]; }
+          int ip = 0;
+          while (ip < v.ns || ib < ie) {
+            const int jp = ip < v.ns ? v.plane_sidx[ip] : 0x7fffffff;
+            const int jb = ib < ie ? v.sg_items[ib] : 0x7fffffff;
+            if (jp < jb) { do_plane(ip); ip++; } else { do_box(jb); ib++; }
+          }
+        } else {
+          // faster than the level grid was built for: walk the whole static array
+          int ip = 0;
+          for (int j = 0; j < v.n_static_total; j++) {
+            if (v.static_type[j] == PG_PLANE) { do_plane(ip); ip++; } else do_box(j);
+          }
         }
       }
       if (touched) { v.pos_rest[i] = p; v.vel_rad[i] = q; }
@@ -690,6 +744,9 @@ struct PgLarge {
   float *d_stage_pos, *d_stage_vel;
   unsigned char *d_stage_rest;
   int last_iterations, last_proven;
+  PgWorlds *player_world;        // players x level geometry (passes 1-2) run through the any-collider kernel
+  int n_players;
+  int cap_static_total;
   long long last_candidates, last_hits;
   int step_in_call;
 };
@@ -815,10 +872,36 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   return PG_OK;
 }
 
+// World-space box of a static AABB body: node_decompose + AABB_update (distance.c:27-36, aabb.c:59-78)
+// in host arithmetic -- IEEE float/double like the device, so the bits equal what the device
+// functions of pg_math.cuh would produce for the same record.
+static void host_world_box(const PgBody &b, float *c, float *e) {
+  for (int k = 0; k < 3; k++) { c[k] = 0.0f; e[k] = 0.0f; }
+  if (!b.has_node) return;
+  const float *m = b.node_xform;
+  float pos[3], scl[3], rot[9];
+  for (int k = 0; k < 3; k++) pos[k] = m[0 + k] * 0.0f + m[4 + k] * 0.0f + m[8 + k] * 0.0f + m[12 + k] * 1.0f;
+  for (int col = 0; col < 3; col++) {
+    const float *q = m + col * 4;
+    scl[col] = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+  }
+  for (int col = 0; col < 3; col++) for (int r = 0; r < 3; r++) rot[col * 3 + r] = m[col * 4 + r];
+  if (scl[0] != 0.0f) { const float inv = 1.0f / scl[0]; for (int k = 0; k < 9; k++) rot[k] *= inv; }
+  for (int k = 0; k < 3; k++) pos[k] += b.velocity[k] * 0.0f;            // muladds(velocity, time, pos) with a static body
+  for (int i = 0; i < 3; i++) {
+    float cc = pos[i], ee = 0.0f;
+    for (int j = 0; j < 3; j++) {
+      cc += rot[j * 3 + i] * b.shape[j];
+      ee = (float)((double)ee + fabs((double)rot[j * 3 + i]) * (double)b.shape[3 + j] * fabs((double)scl[i]));
+    }
+    c[i] = cc; e[i] = ee;
+  }
+}
+
 extern "C" {
 
 PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
-  if (max_spheres <= 0 || max_static < 0 || max_static > kMaxPlanesL) { pg_set_error("pg_large_create: bad argument (at most %d static planes)", kMaxPlanesL); return nullptr; }
+  if (max_spheres <= 0 || max_static < 0 || max_static > (1 << 22)) { pg_set_error("pg_large_create: bad argument"); return nullptr; }
   PG_CUDA_NULL(cudaSetDevice(device));
   PgLarge *w = new PgLarge();
   memset(w, 0, sizeof(*w));
@@ -840,6 +923,11 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   PG_CUDA_NULL(cudaMalloc(&v.pos_rest, sizeof(float4) * n));
   PG_CUDA_NULL(cudaMalloc(&v.vel_rad, sizeof(float4) * n));
   PG_CUDA_NULL(cudaMalloc(&v.planes, sizeof(float4) * kMaxPlanesL));
+  PG_CUDA_NULL(cudaMalloc(&v.plane_sidx, sizeof(int) * kMaxPlanesL));
+  w->cap_static_total = std::max(max_static, kMaxPlanesL);
+  PG_CUDA_NULL(cudaMalloc(&v.box_c, sizeof(float4) * (size_t)w->cap_static_total));
+  PG_CUDA_NULL(cudaMalloc(&v.box_e, sizeof(float4) * (size_t)w->cap_static_total));
+  PG_CUDA_NULL(cudaMalloc(&v.static_type, (size_t)w->cap_static_total));
   PG_CUDA_NULL(cudaMalloc(&v.env, sizeof(float) * n));
   PG_CUDA_NULL(cudaMalloc(&v.bbox, sizeof(unsigned) * 8));
   PG_CUDA_NULL(cudaMalloc(&v.grid, sizeof(GridParams)));
@@ -880,7 +968,8 @@ void pg_large_destroy(PgLarge *w) {
   cudaSetDevice(w->device);
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
-  void *ptrs[] = {v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.cell_fill, v.block_sums, v.sorted_idx,
+  if (w->player_world) pg_worlds_destroy(w->player_world);
+  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.cell_fill, v.block_sums, v.sorted_idx,
                   v.sorted_cenv, v.pairs, v.grown, v.env_prev, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
                   v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);
@@ -934,16 +1023,103 @@ extern "C" {
 
 int pg_large_set(PgLarge *w, const PgBody *statics, int n_static, int n_spheres, const float *pos, const float *vel,
                  const float *radius_or_null, float radius, float restitution) {
-  if (!w || n_spheres < 0 || n_spheres > w->cap_n || n_static < 0 || n_static > kMaxPlanesL || !pos || !vel) { pg_set_error("pg_large_set: bad argument"); return PG_ERR_ARG; }
-  for (int i = 0; i < n_static; i++)
-    if (statics[i].collider_type != PG_PLANE) { pg_set_error("pg_large_set: static bodies must be planes"); return PG_ERR_UNSUPPORTED; }
+  if (!w || n_spheres < 0 || n_spheres > w->cap_n || n_static < 0 || n_static > w->cap_static_total || !pos || !vel) { pg_set_error("pg_large_set: bad argument"); return PG_ERR_ARG; }
   PG_CUDA(cudaSetDevice(w->device));
   PG_CUDA(cudaStreamSynchronize(w->stream));
   LargeView &v = w->v;
-  v.n = n_spheres; v.ns = n_static; v.restitution = restitution;
-  float4 pl[kMaxPlanesL];
-  for (int i = 0; i < n_static; i++) pl[i] = make_float4(statics[i].shape[0], statics[i].shape[1], statics[i].shape[2], statics[i].shape[3]);
-  if (n_static) PG_CUDA(cudaMemcpy(v.planes, pl, sizeof(float4) * n_static, cudaMemcpyHostToDevice));
+  // statics: planes (visited against body->position) and AABBs (visited through scene nodes), array order kept
+  std::vector<float4> pl, bc((size_t)std::max(n_static, 1)), be((size_t)std::max(n_static, 1));
+  std::vector<int> pidx;
+  std::vector<unsigned char> types((size_t)std::max(n_static, 1));
+  int n_boxes = 0;
+  float blo[3] = {3e38f, 3e38f, 3e38f}, bhi[3] = {-3e38f, -3e38f, -3e38f};
+  for (int i = 0; i < n_static; i++) {
+    types[i] = (unsigned char)statics[i].collider_type;
+    bc[i] = make_float4(0, 0, 0, 0); be[i] = make_float4(0, 0, 0, 0);
+    if (statics[i].collider_type == PG_PLANE) {
+      if ((int)pl.size() >= kMaxPlanesL) { pg_set_error("pg_large_set: at most %d static planes", kMaxPlanesL); return PG_ERR_CAPACITY; }
+      pl.push_back(make_float4(statics[i].shape[0], statics[i].shape[1], statics[i].shape[2], statics[i].shape[3]));
+      pidx.push_back(i);
+    } else if (statics[i].collider_type == PG_AABB) {
+      if (!statics[i].has_node) { pg_set_error("pg_large_set: static AABB %d has no scene node (the reference reads boxes through scene_node->world_transform)", i); return PG_ERR_UNSUPPORTED; }
+      float c[3], e[3];
+      host_world_box(statics[i], c, e);
+      bc[i] = make_float4(c[0], c[1], c[2], 0.0f); be[i] = make_float4(e[0], e[1], e[2], 0.0f);
+      for (int k = 0; k < 3; k++) { blo[k] = std::min(blo[k], c[k] - e[k]); bhi[k] = std::max(bhi[k], c[k] + e[k]); }
+      n_boxes++;
+    } else {
+      pg_set_error("pg_large_set: static bodies must be planes or AABBs");
+      return PG_ERR_UNSUPPORTED;
+    }
+  }
+  v.n = n_spheres; v.ns = (int)pl.size(); v.restitution = restitution;
+  v.n_static_total = n_static; v.n_boxes = n_boxes;
+  if (!pl.empty()) {
+    PG_CUDA(cudaMemcpy(v.planes, pl.data(), sizeof(float4) * pl.size(), cudaMemcpyHostToDevice));
+    PG_CUDA(cudaMemcpy(v.plane_sidx, pidx.data(), sizeof(int) * pidx.size(), cudaMemcpyHostToDevice));
+  }
+  if (n_static) {
+    PG_CUDA(cudaMemcpy(v.box_c, bc.data(), sizeof(float4) * (size_t)n_static, cudaMemcpyHostToDevice));
+    PG_CUDA(cudaMemcpy(v.box_e, be.data(), sizeof(float4) * (size_t)n_static, cudaMemcpyHostToDevice));
+    PG_CUDA(cudaMemcpy(v.static_type, types.data(), (size_t)n_static, cudaMemcpyHostToDevice));
+  }
+  if (v.sg_start) { cudaFree(v.sg_start); v.sg_start = nullptr; }
+  if (v.sg_items) { cudaFree(v.sg_items); v.sg_items = nullptr; }
+  if (n_boxes) {
+    // level grid: every box is registered in the cells its bounds, inflated by sg_reach, overlap.  A
+    // sphere whose reach r + |v| dt is below sg_reach only needs the list of the cell its centre is in.
+    const float reach = 1.0f;
+    double vol = 1.0;
+    for (int k = 0; k < 3; k++) vol *= std::max(1.0, (double)bhi[k] - (double)blo[k] + 2.0 * reach);
+    float h = std::max(2.0f, (float)cbrt(vol / (8.0 * (double)n_boxes)));
+    int dim[3];
+    for (;;) {
+      double cells = 1.0;
+      for (int k = 0; k < 3; k++) { dim[k] = (int)floor(((double)bhi[k] - (double)blo[k] + 2.0 * reach) / h) + 1; cells *= dim[k]; }
+      if (cells <= 4.0e6) break;
+      h *= 1.26f;
+    }
+    v.sg_reach = reach; v.sg_inv_h = 1.0f / h;
+    for (int k = 0; k < 3; k++) { v.sg_org[k] = blo[k] - reach; v.sg_dim[k] = dim[k]; }
+    const size_t ncell = (size_t)dim[0] * dim[1] * dim[2];
+    std::vector<unsigned> start(ncell + 1, 0u);
+    auto cell_range = [&](int i, int *lo3, int *hi3) {
+      const float c[3] = {bc[i].x, bc[i].y, bc[i].z}, e[3] = {be[i].x, be[i].y, be[i].z};
+      for (int k = 0; k < 3; k++) {
+        // one extra cell of slack on each side: the device computes floor((p - org) * inv_h) in float
+        lo3[k] = std::max(0, (int)floorf((c[k] - e[k] - reach - v.sg_org[k]) * v.sg_inv_h) - 1);
+        hi3[k] = std::min(dim[k] - 1, (int)floorf((c[k] + e[k] + reach - v.sg_org[k]) * v.sg_inv_h) + 1);
+      }
+    };
+    for (int i = 0; i < n_static; i++) {
+      if (types[i] != PG_AABB) continue;
+      int lo3[3], hi3[3]; cell_range(i, lo3, hi3);
+      for (int z = lo3[2]; z <= hi3[2]; z++) for (int y = lo3[1]; y <= hi3[1]; y++) for (int x = lo3[0]; x <= hi3[0]; x++)
+        start[((size_t)z * dim[1] + y) * dim[0] + x + 1]++;
+    }
+    for (size_t c = 0; c < ncell; c++) start[c + 1] += start[c];
+    std::vector<int> items(start[ncell]);
+    std::vector<unsigned> fill(start.begin(), start.end() - 1);
+    for (int i = 0; i < n_static; i++) {          // ascending i: every cell list ends up sorted by static index
+      if (types[i] != PG_AABB) continue;
+      int lo3[3], hi3[3]; cell_range(i, lo3, hi3);
+      for (int z = lo3[2]; z <= hi3[2]; z++) for (int y = lo3[1]; y <= hi3[1]; y++) for (int x = lo3[0]; x <= hi3[0]; x++)
+        items[fill[((size_t)z * dim[1] + y) * dim[0] + x]++] = i;
+    }
+    PG_CUDA(cudaMalloc(&v.sg_start, sizeof(unsigned) * (ncell + 1)));
+    PG_CUDA(cudaMalloc(&v.sg_items, sizeof(int) * std::max<size_t>(items.size(), 1)));
+    PG_CUDA(cudaMemcpy(v.sg_start, start.data(), sizeof(unsigned) * (ncell + 1), cudaMemcpyHostToDevice));
+    if (!items.empty()) PG_CUDA(cudaMemcpy(v.sg_items, items.data(), sizeof(int) * items.size(), cudaMemcpyHostToDevice));
+  }
+  // players x level geometry run through the any-collider kernel on a private one-world handle
+  if (w->player_world) { pg_worlds_destroy(w->player_world); w->player_world = nullptr; }
+  w->n_players = 0;
+  if (n_static) {
+    w->player_world = pg_worlds_create(1, n_static, 1, 8, 65536, w->device);
+    if (!w->player_world) return PG_ERR_CUDA;
+    int rc = pg_worlds_set_bodies(w->player_world, 0, PG_CLASS_STATIC, statics, n_static);
+    if (rc) return rc;
+  }
   const size_t n = (size_t)n_spheres;
   PG_CUDA(cudaMemcpyAsync(w->d_stage_pos, pos, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, w->stream));
   PG_CUDA(cudaMemcpyAsync(w->d_stage_vel, vel, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, w->stream));
@@ -994,6 +1170,13 @@ int pg_large_step(PgLarge *w, float dt, int n_steps) {
   for (int k = 0; k < K_COUNT; k++) w->kms[k] = 0.0f;
   PG_CUDA(cudaEventRecord(w->ev0, w->stream));
   int rc = PG_OK;
+  // passes 1-2 (players x statics, players x dynamics): independent of the spheres, because the
+  // sphere-capsule table entries never fire (undefined upstream) -- all steps at once
+  if (w->player_world && w->n_players > 0 && n_steps > 0) {
+    rc = pg_worlds_step(w->player_world, dt, n_steps, 1);
+    if (rc) return rc;
+    w->launches++;
+  }
   for (int s = 0; s < n_steps && rc == PG_OK; s++) { w->step_in_call = s; rc = lw_step_once(w, dt); }
   PG_CUDA(cudaEventRecord(w->ev1, w->stream));
   PG_CUDA(cudaStreamSynchronize(w->stream));
@@ -1051,18 +1234,52 @@ long long pg_large_events(PgLarge *w, PgEvent *out, long long cap, int *overflow
   if (cudaMemcpy(&n, w->v.n_events, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return PG_ERR_CUDA;
   int over = 0;
   if (n > w->v.max_events) { over = 1; n = w->v.max_events; }
-  if (overflowed) *overflowed = over;
-  if (!out || n == 0) return n;
   std::vector<PgEvent> buf((size_t)n);
-  if (cudaMemcpy(buf.data(), w->v.events, sizeof(PgEvent) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) return PG_ERR_CUDA;
-  std::sort(buf.begin(), buf.end(), [](const PgEvent &a, const PgEvent &b) {
+  if (n && cudaMemcpy(buf.data(), w->v.events, sizeof(PgEvent) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) return PG_ERR_CUDA;
+  for (auto &e : buf) e.pad_ >>= 8;                       // device tag -> pass number
+  if (w->player_world && w->n_players > 0) {
+    int pover = 0;
+    long long np = pg_worlds_events(w->player_world, nullptr, 0, &pover);
+    if (np > 0) {
+      std::vector<PgEvent> pe((size_t)np);
+      np = pg_worlds_events(w->player_world, pe.data(), np, &pover);
+      buf.insert(buf.end(), pe.begin(), pe.begin() + np);   // pad_ already holds the pass (1 or 2)
+    }
+    over |= pover;
+  }
+  if (overflowed) *overflowed = over;
+  // solve order: step, pass, row body, column body.  Rows: player (1-2), dynamic sphere (3-4).
+  auto row_col = [](const PgEvent &e, int *row, int *col) {
+    const int row_class = e.pad_ <= 2 ? PG_CLASS_PLAYER : PG_CLASS_DYNAMIC;
+    if (e.pad_ == 4) { *row = e.a_index; *col = e.b_index; return; }
+    if (e.a_class == row_class) { *row = e.a_index; *col = e.b_index; } else { *row = e.b_index; *col = e.a_index; }
+  };
+  std::stable_sort(buf.begin(), buf.end(), [&](const PgEvent &a, const PgEvent &b) {
     if (a.step != b.step) return a.step < b.step;
     if (a.pad_ != b.pad_) return a.pad_ < b.pad_;
-    if (a.a_index != b.a_index) return a.a_index < b.a_index;      // row body: the dynamic sphere (A in both passes)
-    return a.b_index < b.b_index;
+    int ra, ca, rb, cb;
+    row_col(a, &ra, &ca); row_col(b, &rb, &cb);
+    if (ra != rb) return ra < rb;
+    return ca < cb;
   });
-  for (long long i = 0; i < n && i < cap; i++) { out[i] = buf[(size_t)i]; out[i].pad_ = buf[(size_t)i].pad_ >> 8; }
-  return n;
+  const long long total = (long long)buf.size();
+  if (out) for (long long i = 0; i < total && i < cap; i++) out[i] = buf[(size_t)i];
+  return total;
+}
+
+int pg_large_set_players(PgLarge *w, const PgBody *players, int n) {
+  if (!w || n < 0 || n > 8 || (n > 0 && !players)) { pg_set_error("pg_large_set_players: bad argument (at most 8 players)"); return PG_ERR_ARG; }
+  if (!w->player_world) { pg_set_error("pg_large_set_players: set the level (pg_large_set with static bodies) first"); return PG_ERR_ARG; }
+  int rc = pg_worlds_set_bodies(w->player_world, 0, PG_CLASS_PLAYER, players, n);
+  if (rc) return rc;
+  w->n_players = n;
+  return PG_OK;
+}
+
+int pg_large_get_players(PgLarge *w, PgBody *out, int cap) {
+  if (!w || !out) return PG_ERR_ARG;
+  if (!w->player_world || w->n_players == 0) return 0;
+  return pg_worlds_get_bodies(w->player_world, 0, PG_CLASS_PLAYER, out, cap);
 }
 
 int pg_large_stats(PgLarge *w, PgStats *host_out, void *dev_out8) {

@@ -485,6 +485,112 @@ __device__ inline bool sp_resolve(V3 &p, V3 &v, V3 o, float r, float restitution
   return false;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Static AABB x dynamic sphere on scalars (large-world pass 3 against level geometry).  The box is
+// the world-space AABB of a static body (host-computed once with AABB_update's arithmetic); the
+// sphere is taken THROUGH ITS SCENE NODE, as the reference does (distance.c:113-125): its centre is
+// the node translation p0 (the body position at the last scene_node_update, i.e. at step start),
+// advanced by the CURRENT velocity, never by position changes made earlier in the step.
+// ---------------------------------------------------------------------------------------------
+struct BoxS { V3 c, e; };
+
+// squared point-box distance, distance.c:146-154
+__device__ __forceinline__ float bb_d2(V3 p, const BoxS &bx) {
+  float d2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float v = get(p, i), lo = get(bx.c, i) - get(bx.e, i), hi = get(bx.c, i) + get(bx.e, i);
+    if (v < lo) d2 += (lo - v) * (lo - v);
+    if (v > hi) d2 += (v - hi) * (v - hi);
+  }
+  return d2;
+}
+// sphere centre as min_dist_at_time_AABB_sphere builds it: (p0 + v t), then local centre (0) + that
+__device__ __forceinline__ V3 bb_centre(V3 p0, V3 v, float t) {
+  const V3 q = muladds(v, t, p0);
+  return v3(0.0f + q.x, 0.0f + q.y, 0.0f + q.z);
+}
+// interval_collision(box, sphere): mm = |v_box| len + |v_sphere| len with |v_box| = 0.  Same guided,
+// enclosure-pruned walk as ss_interval: the distance of a moving point to a convex set is convex in
+// t and |v|-Lipschitz.
+__device__ inline bool bb_interval(V3 p0, V3 v, float nv, float r, const BoxS &bx, float t_begin, float t_end,
+                                   LeafLen leaf = default_leaf_len()) {
+  const float tmax = fmaxf(fabsf(t_begin), fabsf(t_end));
+  const float c1 = fabsf(p0.x) + fabsf(p0.y) + fabsf(p0.z);
+  const float b1 = fabsf(bx.c.x) + fabsf(bx.c.y) + fabsf(bx.c.z) + fabsf(bx.e.x) + fabsf(bx.e.y) + fabsf(bx.e.z);
+  const float v1 = fabsf(v.x) + fabsf(v.y) + fabsf(v.z);
+  const float E0 = 1.25f * kU * (c1 + 2.0f * v1 * tmax + 3.0f * b1) + 1.0e-30f;
+  const float L = nv * 1.0001f;
+  const float mm_hi = (0.0f * leaf.hi + nv * leaf.hi) * 1.000001f;
+  const float mm_lo = (0.0f * leaf.lo + nv * leaf.lo) * 0.999999f;
+  const bool finite_ok = (nv < 1.0e30f) && (c1 < 1.0e30f) && (b1 < 1.0e30f) && (r < 1.0e30f);
+  // closest approach to the box centre as the preferred time (a heuristic only)
+  const V3 s0 = sub(p0, bx.c);
+  const float vv = __fmaf_rn(v.x, v.x, __fmaf_rn(v.y, v.y, v.z * v.z));
+  const float sv = __fmaf_rn(s0.x, v.x, __fmaf_rn(s0.y, v.y, s0.z * v.z));
+  const float t_pref = vv > 0.0f ? fminf(fmaxf(-sv / vv, t_begin), t_end) : t_begin;
+  return interval_walk_guided<float>(t_begin, t_end, t_pref,
+    [&](float t) { return bb_d2(bb_centre(p0, v, t), bx); },
+    [&](float t0, float t1, float d2a, float d2b) -> int {
+      const float len = t1 - t0;
+      const float mm = 0.0f * len + nv * len;
+      if (ss_dist_exceeds(d2a, r, mm) || ss_dist_exceeds(d2b, r, mm)) return kDead;   // same tail as sphere-sphere: d2 < r^2 ? 0 : sqrt(d2) - r
+      if (len < kIntervalEps || !finite_ok) return kOpen;
+      const float Da = sqrtf(d2a), Db = sqrtf(d2b);
+      const float Dmax = fmaxf(Da, Db);
+      const float E = E0 + 8.0f * kU * Dmax;
+      const float lower = 0.5f * (Da + Db) * 0.9999999f - 0.5f * L * len - 2.0f * E - r;
+      if (lower * 0.999999f > mm_hi) return kDead;
+      const float upper = fmaxf((Dmax + 2.0f * E) * 1.0000001f - r, 0.0f) * 1.000001f;
+      if (upper <= mm_lo) return kSure;
+      return kOpen;
+    });
+}
+// narrow_phase_AABB_sphere, narrow_phase.c:143-196 + ray_intersect_AABB :702-739 (static box: rel_v = v - 0)
+__device__ inline Contact bb_narrow(V3 p0, V3 v, float r, const BoxS &bx, float dt) {
+  const V3 c = v3(0.0f + p0.x, 0.0f + p0.y, 0.0f + p0.z);
+  const V3 e = v3(bx.e.x + r, bx.e.y + r, bx.e.z + r);
+  const V3 rv = sub(v, v3(0.0f, 0.0f, 0.0f));
+  float hit = 0.0f, t_max = dt;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float lo = get(bx.c, i) - get(e, i), hi = get(bx.c, i) + get(e, i), pi = get(c, i), di = get(rv, i);
+    if ((double)fabsf(di) < kNpEps) {
+      if (pi < lo || pi > hi) return contact(-1.0f, false);
+    } else {
+      float t1 = (lo - pi) / di;
+      float t2 = (hi - pi) / di;
+      if (t1 > t2) { const float tmp = t1; t1 = t2; t2 = tmp; }
+      if (t1 > hit) hit = t1;
+      if (t2 < t_max) t_max = t2;
+      if (hit > t_max) return contact(-1.0f, false);
+    }
+  }
+  if (hit > dt) return contact(-1.0f, false);
+  return contact(hit, true);
+}
+// resolve_collision_AABB_sphere with a static box and a dynamic sphere, resolution.c:152-241.
+// pos/vel = the body's CURRENT position and velocity (updated in place); p0 = node translation.
+__device__ inline void bb_resolve(V3 &pos, V3 &vel, V3 p0, float r, float restitution, const BoxS &bx, float t) {
+  V3 vb;
+  advance_to_hit(pos, vel, t, vb);
+  const V3 q = muladds(vb, t, p0);                         // node position advanced by velocity_before (resolution.c:190)
+  const V3 c = v3(0.0f + q.x, 0.0f + q.y, 0.0f + q.z);
+  V3 closest;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float lo = get(bx.c, i) - get(bx.e, i), hi = get(bx.c, i) + get(bx.e, i), ci = get(c, i);
+    set(closest, i, lo > ci ? lo : (hi > ci ? ci : hi));
+  }
+  const V3 diff = sub(c, closest);
+  const float d = norm(diff);
+  const float pen = (d < r) ? (float)((double)(r - d) + 0.001) : 0.0f;   // [f64]
+  if (pen <= 0) return;
+  const V3 n = normalize(diff);
+  pos = muladds(n, pen * 0.5f, pos);
+  vel = reflect(vb, n, restitution);
+}
+
 // =====================================================================================
 // General path: all collider pairs, on PgBody records.
 // =====================================================================================

@@ -50,6 +50,8 @@ API = [
     ("pg_large_create", _vp, [_i, _i, _i]),
     ("pg_large_destroy", None, [_vp]),
     ("pg_large_set", _i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _f, _f]),
+    ("pg_large_set_players", _i, [_vp, _vp, _i]),
+    ("pg_large_get_players", _i, [_vp, _vp, _i]),
     ("pg_large_upload_state", _i, [_vp, _vp, _vp, _vp]),
     ("pg_large_download_state", _i, [_vp, _vp, _vp, _vp]),
     ("pg_large_step", _i, [_vp, _f, _i]),
@@ -312,6 +314,16 @@ class GpuLargeWorld:
         self.n = len(pos)
         _check(self.L.pg_large_set(self.h, _ptr(st), len(st), self.n, _ptr(pos), _ptr(vel), _ptr(rad_arr),
                                    np.float32(r_uniform), np.float32(restitution)), "pg_large_set")
+
+    def set_players(self, players: np.ndarray):
+        p = prepare(players)
+        _check(self.L.pg_large_set_players(self.h, _ptr(p), len(p)), "pg_large_set_players")
+        self.n_players = len(p)
+
+    def get_players(self) -> np.ndarray:
+        out = np.zeros(8, dtype=BODY_DTYPE)
+        n = _check(self.L.pg_large_get_players(self.h, _ptr(out), len(out)), "pg_large_get_players")
+        return out[:n]
 
     def upload_state(self, pos, vel, at_rest=None):
         _check(self.L.pg_large_upload_state(self.h, _ptr(pos), _ptr(vel), _ptr(at_rest)), "pg_large_upload_state")

@@ -155,3 +155,73 @@ CONFIGS = {
     "c2": dict(n_worlds=1, n_spheres=65536, L=64.0),
     "c4": dict(n_worlds=1, n_spheres=4194304, L=256.0),
 }
+
+
+def translate16(pos) -> np.ndarray:
+    m = np.eye(4, dtype=np.float32)
+    m[3, :3] = np.asarray(pos, np.float32)        # cglm column-major: translation in column 3
+    return m.reshape(16)
+
+
+def level_slabs(L: float, spacing: float = 8.0, extents=(4.0, 0.25, 4.0)) -> np.ndarray:
+    """Static level geometry of config C5: axis-aligned AABB slabs on an
+    `spacing`-unit lattice inside the L-box, checkerboard so that spheres can pass between floors;
+    identity-rotation scene nodes under an identity parent."""
+    n = int(L // spacing)
+    out = []
+    for j in range(1, n):
+        for i in range(n):
+            for k in range(n):
+                if (i + j + k) % 2:
+                    continue
+                out.append((-L / 2 + spacing * (i + 0.5), spacing * j, -L / 2 + spacing * (k + 0.5)))
+    b = new_bodies(len(out))
+    b["collider_type"] = COLLIDER_AABB
+    b["position"] = np.asarray(out, np.float32).reshape(-1, 3)
+    b["shape"][:, 3:6] = np.asarray(extents, np.float32)
+    b["has_node"] = 1
+    b["has_parent"] = 1
+    for r in b:
+        r["node_xform"] = translate16(r["position"])
+    return b
+
+
+def player_capsule(pos=(0.0, 0.0, 2.0), rot=(0.0, 180.0, 0.0), vel=(0.0, 0.0, 0.0)) -> np.ndarray:
+    """The player body scene_load creates (scene.c:303-332): capsule A=(0,.25,0) B=(0,1.75,0) r=.25."""
+    b = new_bodies(1)
+    b["collider_type"] = COLLIDER_CAPSULE
+    b["entity_type"] = ENTITY_PLAYER
+    b["shape"][0, :3] = [0.0, 0.25, 0.0]
+    b["shape"][0, 3:6] = [0.0, 1.75, 0.0]
+    b["shape"][0, 6] = 0.25
+    b["position"] = np.asarray(pos, np.float32)
+    b["rotation"] = np.asarray(rot, np.float32)
+    b["velocity"] = np.asarray(vel, np.float32)
+    b["has_node"] = 1
+    b["has_parent"] = 1
+    return b
+
+
+def level_world(n_spheres: int, L: float, seed_world: int = 0, with_player: bool = True):
+    """Config C5: (statics, sphere pos, sphere vel, players).  Statics = the six box planes followed
+    by the slab level; spheres as in C2."""
+    planes = plane_bodies(box_planes(L))
+    planes["has_node"] = 1
+    planes["has_parent"] = 1
+    statics = np.concatenate([planes, level_slabs(L)])
+    pos, vel = sphere_worlds(1, n_spheres, L, first_world=seed_world)
+    players = player_capsule() if with_player else np.zeros(0, dtype=BODY_DTYPE)
+    return statics, pos[0], vel[0], players
+
+
+def sphere_bodies_with_nodes(pos, vel, radius: float = 0.15, restitution: float = 1.0) -> np.ndarray:
+    """Dynamic spheres carrying a scene node (translation = position), as a loaded scene has them."""
+    b = sphere_bodies(pos, vel, radius, restitution)
+    b["has_node"] = 1
+    m = np.tile(np.eye(4, dtype=np.float32).reshape(16), (len(b), 1))
+    m[:, 12:15] = b["position"]
+    b["node_xform"] = m
+    return b
+
+
+CONFIGS["c5"] = dict(n_worlds=1, n_spheres=1048576, L=160.0)

@@ -174,11 +174,19 @@ void *pg_worlds_stream(PgWorlds *w);   /* cudaStream_t as void* */
  * ------------------------------------------------------------------------------------------ */
 typedef struct PgLarge PgLarge;
 
+/* Static bodies may be planes (at most 16) and AABBs with scene nodes (level geometry, any number
+ * up to max_static); their array order is the reference's visit order.  When AABBs are present the
+ * spheres are visited THROUGH SCENE NODES like the reference does (distance.c:113-125): node
+ * translation = body position at the start of the step (refreshed by the per-frame
+ * scene_node_update), identity rotation, unit scale.  Player bodies (capsules) run passes 1-2
+ * against the level; sphere-capsule visits never fire (undefined upstream). */
 PgLarge *pg_large_create(int max_spheres, int max_static, int device);
 void pg_large_destroy(PgLarge *w);
 int  pg_large_set(PgLarge *w, const PgBody *statics, int n_static, int n_spheres,
                   const float *pos, const float *vel, const float *radius_or_null, float radius,
                   float restitution);
+int  pg_large_set_players(PgLarge *w, const PgBody *players, int n);
+int  pg_large_get_players(PgLarge *w, PgBody *out, int cap);
 int  pg_large_upload_state(PgLarge *w, const float *pos, const float *vel, const uint8_t *at_rest_or_null);
 int  pg_large_download_state(PgLarge *w, float *pos, float *vel, uint8_t *at_rest_or_null);
 int  pg_large_step(PgLarge *w, float dt, int n_steps);

@@ -77,3 +77,38 @@ def test_broadphase_pair_set_bit_exact(gpu_lib, oracle_lib, n, L):
     cnt = oracle_lib.dll.ora_world_pairs(o.h, DT, 1, buf.ctypes.data_as(C.c_void_p), len(buf))
     assert np.array_equal(got, buf[:cnt])
     g.close()
+
+
+@pytest.mark.parametrize("with_player", [False, True])
+def test_level_geometry_world_c5_style(gpu_lib, oracle_lib, with_player):
+    """Config C5 in small: box planes + static AABB slabs (scene nodes) + spheres visited through their
+    scene nodes + the player capsule against the level; state, node semantics and event order."""
+    n, L = 2500, 32.0
+    statics, pos, vel, players = scenes.level_world(n, L, seed_world=3, with_player=with_player)
+    # make sure spheres are actually moving into slabs: a denser, faster subset near the floors
+    vel = (vel * np.float32(1.5)).astype(np.float32)
+    g = gpu_lib.GpuLargeWorld(n, len(statics))
+    g.set(gpu_lib.prepare(statics), pos, vel)
+    if with_player:
+        pl = gpu_lib.prepare(players)
+        pl["node_xform"][0] = gpu_lib.node_transform(pl["position"][0], pl["rotation"][0], pl["scale"][0], pl["parent_xform"][0])
+        g.set_players(pl)
+        players = pl
+    o = ora.World(oracle_lib, statics, scenes.sphere_bodies_with_nodes(pos, vel), players if with_player else None)
+    box_events = 0
+    for s in range(25):
+        g.step(DT, 1)
+        o.step(DT, 1, 1)
+        assert g.exactness()["proven_exact"], s
+        P, V, R = g.download_state()
+        r = o.read(1)
+        assert gen.same_bits(P, r["position"]) and gen.same_bits(V, r["velocity"]) and np.array_equal(R != 0, r["at_rest"] != 0), s
+        ge, oe = g.events(), o.events()
+        key = lambda e: [(int(x["a_class"]), int(x["a_index"]), int(x["b_class"]), int(x["b_index"])) for x in e]
+        assert key(ge) == key(oe), (s, len(ge), len(oe))
+        box_events += int(((oe["a_class"] == 0) & (oe["b_class"] == 1)).sum())
+        if with_player:
+            gp, op = g.get_players(), o.read(2)
+            assert gen.state_equal(gp, op), s
+    assert box_events > 0          # AABB-sphere contacts really happened
+    g.close()
