@@ -44,6 +44,8 @@ WORKLOADS = {
     # single large worlds (uniform-grid path); under N > 1 every rank runs an independent replica
     "c2": dict(n_worlds=1, n_spheres=65536, L=64.0, desc="one world, 65,536 spheres in a closed box", large=True),
     "c4": dict(n_worlds=1, n_spheres=4194304, L=256.0, desc="one world, 4,194,304 spheres in a closed box", large=True),
+    "c5": dict(n_worlds=1, n_spheres=1048576, L=160.0, large=True, level=True,
+               desc="static AABB slab level (8-unit lattice) + 1,048,576 spheres + player capsule"),
 }
 # algorithmic bytes per body-step of the streaming kernels of the large-world path
 LARGE_KERNEL_BYTES = {"k_pass3": 52, "k_cell_count": 20, "k_scan": 12, "k_scatter": 56, "k_pairs": 28, "k_finalize": 52}
@@ -212,10 +214,18 @@ def run_large_arm(args, cfg):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, L = cfg["n_spheres"], cfg["L"]
-    pos, vel = scenes.sphere_worlds(1, n, L, first_world=rank)
-    statics = scenes.plane_bodies(scenes.box_planes(L))
-    world = gpu.GpuLargeWorld(n, len(statics), device=local_rank)
-    world.set(statics, pos[0], vel[0])
+    if cfg.get("level"):
+        statics, p0, v0, players = scenes.level_world(n, L, seed_world=rank, with_player=True)
+        world = gpu.GpuLargeWorld(n, len(statics), device=local_rank)
+        world.set(gpu.prepare(statics), p0, v0)
+        pl = gpu.prepare(players)
+        pl["node_xform"][0] = gpu.node_transform(pl["position"][0], pl["rotation"][0], pl["scale"][0], pl["parent_xform"][0])
+        world.set_players(pl)
+    else:
+        pos, vel = scenes.sphere_worlds(1, n, L, first_world=rank)
+        statics = scenes.plane_bodies(scenes.box_planes(L))
+        world = gpu.GpuLargeWorld(n, len(statics), device=local_rank)
+        world.set(statics, pos[0], vel[0])
     dt = float(scenes.DT_60HZ)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -281,7 +291,7 @@ def run_large_arm(args, cfg):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "desc": cfg["desc"], "n_spheres": n, "n_planes": 6, "dt": float(scenes.MAX_DELTA_TIME),
+            "config": {"workload": args.workload, "desc": cfg["desc"], "n_spheres": n, "n_static": int(len(statics)), "dt": float(scenes.MAX_DELTA_TIME),
                        "parallelism": "replicas only" if world_size > 1 else "single world, 1 GPU",
                        "l2": "256 MiB flush between steps, outside the CUDA-event pairs"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
