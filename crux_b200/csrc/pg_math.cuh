@@ -368,7 +368,7 @@ __device__ __forceinline__ float sp_dist_from_s(float s, float r) {
 __device__ __forceinline__ float sp_dist(V3 c, V3 n, float d, float r) { return sp_dist_from_s(sp_signed(c, n, d), r); }
 // Same enclosure idea as ss_interval.  The real signed distance s(t) = n.(c + v t) - d is linear in
 // t, the computed one differs from it by at most
-//   Es = 1.5 u (5 (|c|_1 + |v|_1 t_max) + |d|)          (|n_k| <= 1; rigorous bound has factor 1.0)
+//   Es = 1.5 u (sum_k |n_k| (4|c_k| + 4|v_k| t_max) + |s|_max)   (|n_k| <= 1; rigorous bound has factor 1.0)
 // and is EXACTLY constant in t when every product v_k n_k vanishes (a body at rest that was
 // pushed sideways along an axis-aligned plane: the case that otherwise costs 2^depth nodes every
 // step, for ever, because a resting body is never integrated).
@@ -378,7 +378,14 @@ __device__ inline bool sp_interval(V3 c, V3 v, float nv, V3 n, float d, float r,
   const float c1 = fabsf(c.x) + fabsf(c.y) + fabsf(c.z), v1 = fabsf(v.x) + fabsf(v.y) + fabsf(v.z);
   const bool constant_s = (v.x == 0.0f || n.x == 0.0f) && (v.y == 0.0f || n.y == 0.0f) && (v.z == 0.0f || n.z == 0.0f);
   const bool unit_n = fabsf(n.x) <= 1.0000001f && fabsf(n.y) <= 1.0000001f && fabsf(n.z) <= 1.0000001f;
-  const float Es = constant_s ? 0.0f : 1.5f * kU * (5.0f * (c1 + v1 * tmax) + fabsf(d)) + 1.0e-30f;
+  // every rounding on the way to s carries a factor |n_k|: c_k = fl(p_k + fl(v_k t)) errs by
+  // u(2|v_k|t + |c_k|), the product by u|c_k n_k| more, the two sums by u x partial sums, the final
+  // subtraction by u|s|:  |s_computed - s_real| <= u (sum_k |n_k| (4|c_k| + 2|v_k| t) + |s|).  For an
+  // axis-aligned wall only the coordinate along the normal counts.
+  const float w1 = fabsf(n.x) * (4.0f * fabsf(c.x) + 4.0f * fabsf(v.x) * tmax) + fabsf(n.y) * (4.0f * fabsf(c.y) + 4.0f * fabsf(v.y) * tmax) +
+                   fabsf(n.z) * (4.0f * fabsf(c.z) + 4.0f * fabsf(v.z) * tmax);
+  const float s_mag = fabsf(c.x * n.x) + fabsf(c.y * n.y) + fabsf(c.z * n.z) + fabsf(d) + v1 * tmax;
+  const float Es = constant_s ? 0.0f : 1.5f * kU * (w1 + s_mag) + 1.0e-30f;
   const float mm_hi = (nv * leaf.hi + 0.0f * leaf.hi) * 1.000001f;
   const float mm_lo = (nv * leaf.lo + 0.0f * leaf.lo) * 0.999999f;
   const bool finite_ok = unit_n && (nv < 1.0e30f) && (c1 < 1.0e30f) && (fabsf(d) < 1.0e30f) && (r < 1.0e30f) && (r >= 0.0f);
