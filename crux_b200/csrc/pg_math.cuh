@@ -268,13 +268,34 @@ __device__ __forceinline__ bool interval_walk(float t_begin, float t_end, float 
 // bits, so each level costs one new sample.  path bit = 1 means "the non-preferred child".
 //   eval(t)                       -> Sample   (the computed quantity at time t)
 //   probe(t0, t1, Sample, Sample) -> kDead / kOpen / kSure
-template <typename Sample, typename Eval, typename Probe>
-__device__ __forceinline__ bool interval_walk_guided(float t_begin, float t_end, float t_pref, Eval eval, Probe probe) {
+#ifdef PG_WALK_STATS
+// debug build only (crux_b200/lib/alt): nodes visited per walk kind -- [kind][calls, nodes, max nodes, walks > 256 nodes]
+static __device__ unsigned long long pg_walk_stats[4][4];
+struct WalkCount {
+  int kind; unsigned long long n; unsigned long long *out;
+  __device__ WalkCount(int k, unsigned long long *o) : kind(k), n(0), out(o) {}
+  __device__ ~WalkCount() {
+    if (out) *out = n;
+    atomicAdd(&pg_walk_stats[kind][0], 1ull); atomicAdd(&pg_walk_stats[kind][1], n); atomicMax(&pg_walk_stats[kind][2], n);
+    if (n > 256) atomicAdd(&pg_walk_stats[kind][3], 1ull);
+  }
+};
+#define PG_WALK_BEGIN(kind) WalkCount wc_(kind, dbg_nodes)
+#define PG_WALK_NODE() (wc_.n++)
+#else
+#define PG_WALK_BEGIN(kind)
+#define PG_WALK_NODE()
+#endif
+
+template <typename Sample, int Kind = 0, typename Eval, typename Probe>
+__device__ __forceinline__ bool interval_walk_guided(float t_begin, float t_end, float t_pref, Eval eval, Probe probe, unsigned long long *dbg_nodes = nullptr) {
   unsigned long long path = 0;
   int depth = 0;
   float t0 = t_begin, t1 = t_end;
   Sample Sa = eval(t0), Sb = eval(t1);
+  PG_WALK_BEGIN(Kind);
   for (;;) {
+    PG_WALK_NODE();
     const int st = probe(t0, t1, Sa, Sb);
     if (st == kSure) return true;
     if (st == kOpen) {
@@ -314,16 +335,18 @@ constexpr float kU = 5.9604645e-8f;                  // 2^-24, unit roundoff of 
 // points, and mm is monotone in len.  For any float t in a node [a,b] the computed centre distance
 // Dc(t) differs from the real D(t) = |s + u t| (real arithmetic on the float inputs) by at most
 //   E = 1.25 u (|cA|_1 + |cB|_1 + 2 (|vA|_1 + |vB|_1) t_max) + 8 u D     (u = 2^-24)
-// (roundings of v t, c + v t, the difference, the dot product and the square root).  D is convex
-// and |u|-Lipschitz, so on the node  D <= max(D(a), D(b))  and  D >= (D(a)+D(b))/2 - |u| len/2.
+// (roundings of v t, c + v t, the difference, the dot product and the square root).  D is convex,
+// so on the node  D <= max(D(a), D(b)),  and D^2 is a parabola whose minimum over the node is known
+// in closed form (vertex clamped into the node, evaluated in binary64).
 //   lower bound of dist > mm(longest leaf)   -> no leaf below can survive          -> kDead
 //   upper bound of dist <= mm(shortest leaf) -> every node below passes            -> kSure
-// Fast bodies moving almost in parallel (|u| << nA+nB) would otherwise make the recursion visit
-// O(2^depth) nodes; with the enclosures it is O(depth) except inside a ~1e-6-wide band.
+// Fast bodies moving almost in parallel (|u| << nA+nB), and near misses of bodies moving head-on
+// (|u| ~ nA+nB, where the reach shrinks as fast as the gap), would otherwise make the recursion
+// visit hundreds to O(2^depth) nodes; with the enclosures it is O(depth) unless the closest
+// approach lies inside a band of a few 1e-6 around mm(leaf).
 __device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float nB, float rs,
                                    float t_begin, float t_end, LeafLen leaf = default_leaf_len()) {
   const V3 u = sub(vA, vB);
-  const float L = sqrtf(__fmaf_rn(u.x, u.x, __fmaf_rn(u.y, u.y, u.z * u.z))) * 1.0001f;
   const float tmax = fmaxf(fabsf(t_begin), fabsf(t_end));
   const float c1 = fabsf(cA.x) + fabsf(cA.y) + fabsf(cA.z) + fabsf(cB.x) + fabsf(cB.y) + fabsf(cB.z);
   const float v1 = fabsf(vA.x) + fabsf(vA.y) + fabsf(vA.z) + fabsf(vB.x) + fabsf(vB.y) + fabsf(vB.z);
@@ -336,6 +359,26 @@ __device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float n
   const float uu = __fmaf_rn(u.x, u.x, __fmaf_rn(u.y, u.y, u.z * u.z));
   const float su = __fmaf_rn(s0.x, u.x, __fmaf_rn(s0.y, u.y, s0.z * u.z));
   const float t_pref = uu > 0.0f ? fminf(fmaxf(-su / uu, t_begin), t_end) : t_begin;
+#ifdef PG_WALK_STATS
+  unsigned long long dbg_n = 0;
+  struct Dump { const V3 &cA, &vA, &cB, &vB; float rs, t0, t1; unsigned long long &n;
+    __device__ ~Dump() { if (n > 256) printf("SS %llu nodes cA %.9g %.9g %.9g vA %.9g %.9g %.9g cB %.9g %.9g %.9g vB %.9g %.9g %.9g rs %.9g t %.9g %.9g\n",
+      n, cA.x, cA.y, cA.z, vA.x, vA.y, vA.z, cB.x, cB.y, cB.z, vB.x, vB.y, vB.z, rs, t0, t1); } } dump_{cA, vA, cB, vB, rs, t_begin, t_end, dbg_n};
+#define PG_DBG_ARG , &dbg_n
+#else
+#define PG_DBG_ARG
+#endif
+  // The same parabola in binary64 (inputs are binary32, so s and u are exact and the three
+  // coefficients carry a relative error of a few 2^-53): D^2(t) = ss + 2 su t + uu t^2.  A node is
+  // dead as soon as the real minimum over it clears the longest leaf's reach:
+  //   computed dist(t) >= (D(t)(1 - 8u) - E0 - rs)(1 - u) > mm_hi   <=   D_min > thr.
+  const double sx = (double)cA.x - (double)cB.x, sy = (double)cA.y - (double)cB.y, sz = (double)cA.z - (double)cB.z;
+  const double ux = (double)vA.x - (double)vB.x, uy = (double)vA.y - (double)vB.y, uz = (double)vA.z - (double)vB.z;
+  const double ss_d = sx * sx + sy * sy + sz * sz, su_d = sx * ux + sy * uy + sz * uz, uu_d = ux * ux + uy * uy + uz * uz;
+  const double t_star = uu_d > 0.0 ? -su_d / uu_d : (double)t_begin;
+  const double d2_slack = 1.0e-13 * (ss_d + 2.0 * fabs(su_d) * (double)tmax + uu_d * (double)tmax * (double)tmax);
+  const double dead_thr = ((double)mm_hi + (double)rs + (double)E0) * 1.00001;
+  const double dead_thr2 = dead_thr * dead_thr;
   return interval_walk_guided<float>(t_begin, t_end, t_pref,
     [&](float t) { return ss_d2_at(cA, vA, cB, vB, t); },
     [&](float t0, float t1, float d2a, float d2b) -> int {
@@ -343,16 +386,17 @@ __device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float n
       const float mm = nA * len + nB * len;
       if (ss_dist_exceeds(d2a, rs, mm) || ss_dist_exceeds(d2b, rs, mm)) return kDead;
       if (len < kIntervalEps || !finite_ok) return kOpen;       // leaves are decided by the tests above
+      // real minimum of |s + u t|^2 over the node, in closed form: the parabola's vertex clamped into it
+      const double tc = fmin(fmax(t_star, (double)t0), (double)t1);
+      const double D2min = fma(tc, fma(uu_d, tc, 2.0 * su_d), ss_d) - d2_slack;
+      if (D2min > dead_thr2) return kDead;
       const float Da = sqrtf(d2a), Db = sqrtf(d2b);
       const float Dmax = fmaxf(Da, Db);
       const float E = E0 + 8.0f * kU * Dmax;       // |computed - real| at any t of the node
-      // computed end points -> real end points (E) -> real interior (convexity/Lipschitz) -> computed interior (E)
-      const float lower = 0.5f * (Da + Db) * 0.9999999f - 0.5f * L * len - 2.0f * E - rs;   // <= dist anywhere in the node
-      if (lower * 0.999999f > mm_hi) return kDead;
       const float upper = fmaxf((Dmax + 2.0f * E) * 1.0000001f - rs, 0.0f) * 1.000001f;     // >= dist anywhere in the node
       if (upper <= mm_lo) return kSure;
       return kOpen;
-    });
+    } PG_DBG_ARG);
 }
 
 // min_dist_at_time_sphere_plane, distance.c:305-321: max(|s| - r, 0), |s|-r in double.
@@ -393,7 +437,7 @@ __device__ inline bool sp_interval(V3 c, V3 v, float nv, V3 n, float d, float r,
   const float s_begin = __fmaf_rn(c.x, n.x, __fmaf_rn(c.y, n.y, c.z * n.z)) - d;
   const float ndv = __fmaf_rn(v.x, n.x, __fmaf_rn(v.y, n.y, v.z * n.z));
   const float t_pref = ndv != 0.0f ? fminf(fmaxf(-s_begin / ndv, t_begin), t_end) : t_begin;
-  return interval_walk_guided<float>(t_begin, t_end, t_pref,
+  return interval_walk_guided<float, 1>(t_begin, t_end, t_pref,
     [&](float t) { return sp_signed(muladds(v, t, c), n, d); },
     [&](float t0, float t1, float sa, float sb) -> int {
       const float len = t1 - t0;
@@ -536,7 +580,7 @@ __device__ inline bool bb_interval(V3 p0, V3 v, float nv, float r, const BoxS &b
   const float vv = __fmaf_rn(v.x, v.x, __fmaf_rn(v.y, v.y, v.z * v.z));
   const float sv = __fmaf_rn(s0.x, v.x, __fmaf_rn(s0.y, v.y, s0.z * v.z));
   const float t_pref = vv > 0.0f ? fminf(fmaxf(-sv / vv, t_begin), t_end) : t_begin;
-  return interval_walk_guided<float>(t_begin, t_end, t_pref,
+  return interval_walk_guided<float, 2>(t_begin, t_end, t_pref,
     [&](float t) { return bb_d2(bb_centre(p0, v, t), bx); },
     [&](float t0, float t1, float d2a, float d2b) -> int {
       const float len = t1 - t0;

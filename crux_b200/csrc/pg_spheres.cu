@@ -541,3 +541,12 @@ int pg_launch_worlds_stats(PgWorlds *w, void *dev_out8) {
   w->launches++;
   return PG_OK;
 }
+
+#ifdef PG_WALK_STATS
+// debug build only: read (and optionally clear) this translation unit's interval-walk counters
+extern "C" int pg_debug_walk_stats(unsigned long long *out16, int reset) {
+  if (cudaMemcpyFromSymbol(out16, pgm::pg_walk_stats, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(pgm::pg_walk_stats, z, sizeof z); }
+  return 0;
+}
+#endif
