@@ -39,15 +39,41 @@ static __device__ __forceinline__ bool pair_gate_rejects(V3 cA, V3 vA, V3 cB, V3
   return dmin2 > lim * lim && dmin2 < 3.0e38f;
 }
 
+// Reach filter + closest-approach gate of bodies r and c of a shared-memory world image
+// (P4 = position + reach, V4 = velocity + radius); `integrate_c`: body c as it will be once its own
+// row has integrated it.  True = the pair cannot fire.  One out-of-line copy for every caller.
+static __device__ __noinline__ bool pair_gate_far(const float4 *P4, const float4 *V4, int r, int c, bool integrate_c, float dt) {
+  const float4 ap = P4[r], av = V4[r];
+  const float4 bp = P4[c], bv = V4[c];
+  V3 p = v3(bp.x, bp.y, bp.z), vel = v3(bv.x, bv.y, bv.z);
+  float rho = bp.w;
+  const float na2 = __fmaf_rn(av.x, av.x, __fmaf_rn(av.y, av.y, av.z * av.z));
+  float nb2 = __fmaf_rn(vel.x, vel.x, __fmaf_rn(vel.y, vel.y, vel.z * vel.z));
+  if (integrate_c) {
+    pgm::integrate(p, vel, dt);
+    nb2 = __fmaf_rn(vel.x, vel.x, __fmaf_rn(vel.y, vel.y, vel.z * vel.z));
+    rho = __fmaf_rn(sqrtf(nb2), dt, bv.w) * 1.0001f + 1.0e-6f;         // == reach()
+  }
+  const float dx = ap.x - p.x, dy = ap.y - p.y, dz = ap.z - p.z;
+  const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
+  const float T = ap.w + rho;
+  if (!(d2 <= T * T)) return true;                                     // root test of the interval search fails
+  if (dt <= 1.0e-9f) return false;
+  const float vsum = sqrtf(2.0f * (na2 + nb2)) * 1.0001f;              // >= |vA| + |vB|
+  return pair_gate_rejects(v3(ap.x, ap.y, ap.z), v3(av.x, av.y, av.z), p, vel, av.w + bv.w, vsum, dt);
+}
+
 // Exact visit of two spheres (world.c:481-541 with the sphere-sphere table entries).
 // All lanes call it with identical arguments.  Returns true if an event fires; A and B updated.
-static __device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
+// Gate = false: the caller already applied pair_gate_rejects to this very state.
+template <bool Gate>
+static __device__ __forceinline__ bool sphere_pair_exact_impl(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
   V3 cA = v3(0.0f + A.px, 0.0f + A.py, 0.0f + A.pz);     // centre (0,0,0) + position, distance.c:283
   V3 cB = v3(0.0f + B.px, 0.0f + B.py, 0.0f + B.pz);
   V3 vA = v3(A.vx, A.vy, A.vz), vB = v3(B.vx, B.vy, B.vz);
   float rs = A.r + B.r;
   float nA = pgm::norm(vA), nB = pgm::norm(vB);
-  if (pair_gate_rejects(cA, vA, cB, vB, rs, nA + nB, dt)) return false;
+  if (Gate && pair_gate_rejects(cA, vA, cB, vB, rs, nA + nB, dt)) return false;
   if (!pgm::ss_interval(cA, vA, nA, cB, vB, nB, rs, 0.0f, dt, leaf)) return false;
   pgm::Contact c = pgm::ss_narrow(cA, vA, cB, vB, rs);
   if (!(c.hit && c.t >= 0)) return false;
@@ -56,6 +82,12 @@ static __device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, floa
   A.px = pA.x; A.py = pA.y; A.pz = pA.z; A.vx = vA.x; A.vy = vA.y; A.vz = vA.z;
   B.px = pB.x; B.py = pB.y; B.pz = pB.z; B.vx = vB.x; B.vy = vB.y; B.vz = vB.z;
   return true;
+}
+static __device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
+  return sphere_pair_exact_impl<true>(A, B, dt, leaf);
+}
+static __device__ __noinline__ bool sphere_pair_exact_gated(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
+  return sphere_pair_exact_impl<false>(A, B, dt, leaf);
 }
 
 // Exact visit sphere x plane (per lane, divergent).  Returns true if an event fires.

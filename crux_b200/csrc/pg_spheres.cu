@@ -25,15 +25,22 @@
 #include "pg_sphere_exact.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
 using pgm::V3;
 using pgm::v3;
 
-#ifndef PG_SPH_WARPS
-#define PG_SPH_WARPS 12   // resident warps (worlds) per SM the register budget is sized for (measured best: 8 -> 0.41, 12 -> 0.28, 16 -> 0.44 ms/step)
+#ifndef PG_SPH_WPB
+#define PG_SPH_WPB 8      // warps (= worlds) per block for worlds of up to 256 spheres: two blocks per SM
 #endif
+#ifndef PG_SPH_WARPS
+#define PG_SPH_WARPS 16   // resident warps per SM the register budget is sized for (128 registers per thread)
+#endif
+#ifndef PG_SPH_SYNC
+#define PG_SPH_SYNC 1     // 1: one block barrier per step keeps the block's warps in phase, so that an instruction
+#endif                    //    line fetched once serves all of them (the kernel is instruction-fetch bound); 0: none
 constexpr int kMaxPlanes = 16;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr float kHuge = 1.0e8f;      // padding bodies: far from everything, squares still finite
@@ -43,7 +50,7 @@ using pgs::reach;
 using pgs::sphere_pair_exact;
 using pgs::sphere_plane_exact;
 
-__device__ __forceinline__ void emit_event(const WorldsView &v, int w, int step, int pass, int ac, int ai, int bc, int bi) {
+__device__ __noinline__ void emit_event(const WorldsView &v, int w, int step, int pass, int ac, int ai, int bc, int bi) {
   int slot = atomicAdd(v.n_events + w, 1);
   if (slot >= v.max_events) return;
   PgEvent e;
@@ -57,70 +64,6 @@ __device__ __forceinline__ void emit_event(const WorldsView &v, int w, int step,
 //   P4[i] = (px, py, pz, rho)   rho = conservative reach (r + |v| dt)(1+1e-4), refreshed with v
 //   V4[i] = (vx, vy, vz, r)
 // Lanes additionally cache (px,py,pz,rho) of their own CPT bodies in registers for the hot filter.
-
-// Slow half of one pass-4 row: candidates of row i (bit s of `mask` = this lane's column s*32+lane
-// passed the reach filter) are evaluated in increasing column order with the exact predicate.
-// Warp-uniform control flow; state is read from / written to shared memory.  Returns true if any
-// body changed (callers then reload their register caches).
-__device__ __noinline__ bool row_slow_path(float4 *P4, float4 *V4, int i, unsigned mask, int lane, int ncols_slots,
-                                           float dt, const WorldsView &v, int w, int step, bool record) {
-  __syncwarp();
-  pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
-  bool dirty = false;
-  int j0 = 0;
-  // Lane-parallel refinement: every lane runs the closest-approach gate on its own candidate
-  // columns, so the serial part below only sees pairs that really come within contact range.
-  auto refine = [&](unsigned m, float4 ap, float4 av) {
-    unsigned keep = 0;
-    const float na2 = __fmaf_rn(av.x, av.x, __fmaf_rn(av.y, av.y, av.z * av.z));
-    for (; m; m &= m - 1) {
-      const int s = __ffs((int)m) - 1;
-      const float4 bp = P4[s * 32 + lane], bv = V4[s * 32 + lane];
-      const float nb2 = __fmaf_rn(bv.x, bv.x, __fmaf_rn(bv.y, bv.y, bv.z * bv.z));
-      const float vsum = sqrtf(2.0f * (na2 + nb2)) * 1.0001f;            // >= |vA| + |vB|
-      if (!pgs::pair_gate_rejects(v3(ap.x, ap.y, ap.z), v3(av.x, av.y, av.z), v3(bp.x, bp.y, bp.z), v3(bv.x, bv.y, bv.z),
-                                  av.w + bv.w, vsum, dt)) keep |= 1u << s;
-    }
-    return keep;
-  };
-  if (dt > 1.0e-9f) mask = refine(mask, P4[i], V4[i]);
-  for (;;) {
-    // lowest candidate column >= j0 of this lane: slot bits below the first admissible slot are dropped
-    const int smin = (j0 >> 5) + ((lane < (j0 & 31)) ? 1 : 0);
-    const unsigned m = smin < 32 ? (mask >> smin) << smin : 0u;
-    const int jl = m ? (__ffs((int)m) - 1) * 32 + lane : 0x7fffffff;
-    const int j = __reduce_min_sync(kFull, jl);
-    if (j == 0x7fffffff) break;
-    const float4 ap = P4[i], av = V4[i], bp = P4[j], bv = V4[j];
-    Sphere A, B;
-    A.px = ap.x; A.py = ap.y; A.pz = ap.z; A.vx = av.x; A.vy = av.y; A.vz = av.z; A.r = av.w; A.rest = 0;
-    B.px = bp.x; B.py = bp.y; B.pz = bp.z; B.vx = bv.x; B.vy = bv.y; B.vz = bv.z; B.r = bv.w; B.rest = 0;
-    if (sphere_pair_exact(A, B, dt, leaf)) {
-      const float rhoA = reach(A.r, A.vx, A.vy, A.vz, dt), rhoB = reach(B.r, B.vx, B.vy, B.vz, dt);
-      __syncwarp();
-      if (lane == 0) {
-        P4[i] = make_float4(A.px, A.py, A.pz, rhoA); V4[i] = make_float4(A.vx, A.vy, A.vz, A.r);
-        P4[j] = make_float4(B.px, B.py, B.pz, rhoB); V4[j] = make_float4(B.vx, B.vy, B.vz, B.r);
-        if (record) emit_event(v, w, step, 4, PG_CLASS_DYNAMIC, i, PG_CLASS_DYNAMIC, j);
-      }
-      __syncwarp();
-      dirty = true;
-      // the row body changed: re-filter this lane's columns against its new state
-      mask = 0;
-      for (int s = 0; s < ncols_slots; s++) {
-        const int c = s * 32 + lane;
-        const float4 q = P4[c];
-        const float dx = A.px - q.x, dy = A.py - q.y, dz = A.pz - q.z;
-        const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
-        const float T = rhoA + q.w;
-        if (d2 <= T * T && c != i) mask |= 1u << s;
-      }
-      if (dt > 1.0e-9f) mask = refine(mask, P4[i], V4[i]);
-    }
-    j0 = j + 1;
-  }
-  return dirty;
-}
 
 // Slow half of pass 3 for one body against one plane (per lane, divergent): refined gate, then the
 // exact visit.  Returns true if the body changed; *rest is set when it came to rest.
@@ -147,39 +90,147 @@ __device__ __noinline__ bool plane_slow_path(float4 *P4, float4 *V4, int i, floa
   return true;
 }
 
+// ---- pass 4 helpers -------------------------------------------------------------------------------
+// packed binary32 pairs (Blackwell FFMA2 / FADD2): two columns of the reach filter per instruction
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long x, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(x));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+
+constexpr int kMaxRowChanges = 8;
+constexpr int kGateList = 96;         // candidate bits of one 32-row block gated in one go
+
+// All visits of row i, in increasing column order.  `mask` bit s = this lane's column s*32+lane is a
+// candidate that already passed the reach filter AND the closest-approach gate for the state the
+// row sees; with `fresh` the row body changed since those ran and the candidates are rebuilt here
+// from shared memory, which holds the TRUE current state (rows < i integrated).  Columns changed by
+// a contact are appended to chg[]; returns their number (> kMaxRowChanges: list overflowed).
+__device__ __noinline__ int row_visits(float4 *P4, float4 *V4, int i, unsigned mask, bool fresh, int lane, int ncols_slots,
+                                       float dt, const WorldsView &v, int w, int step, bool record, int *chg) {
+  __syncwarp();
+  pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
+  int n_chg = 0;
+  int j0 = 0;
+  for (;;) {
+    if (fresh) {
+      // reach filter + closest-approach gate of this lane's remaining columns against the row body
+      mask = 0;
+      for (int s = j0 >> 5; s < ncols_slots; s++) {
+        const int c = s * 32 + lane;
+        if (c != i && c >= j0 && !pgs::pair_gate_far(P4, V4, i, c, false, dt)) mask |= 1u << s;
+      }
+      fresh = false;
+    }
+    // lowest candidate column >= j0 of this lane: slot bits below the first admissible slot are dropped
+    const int smin = (j0 >> 5) + ((lane < (j0 & 31)) ? 1 : 0);
+    const unsigned m = smin < 32 ? (mask >> smin) << smin : 0u;
+    const int jl = m ? (__ffs((int)m) - 1) * 32 + lane : 0x7fffffff;
+    const int j = __reduce_min_sync(kFull, jl);
+    if (j == 0x7fffffff) break;
+    const float4 ap = P4[i], av = V4[i], bp = P4[j], bv = V4[j];
+    Sphere A, B;
+    A.px = ap.x; A.py = ap.y; A.pz = ap.z; A.vx = av.x; A.vy = av.y; A.vz = av.z; A.r = av.w; A.rest = 0;
+    B.px = bp.x; B.py = bp.y; B.pz = bp.z; B.vx = bv.x; B.vy = bv.y; B.vz = bv.z; B.r = bv.w; B.rest = 0;
+    if (pgs::sphere_pair_exact_gated(A, B, dt, leaf)) {
+      __syncwarp();
+      if (lane == 0) {
+        P4[i] = make_float4(A.px, A.py, A.pz, reach(A.r, A.vx, A.vy, A.vz, dt)); V4[i] = make_float4(A.vx, A.vy, A.vz, A.r);
+        P4[j] = make_float4(B.px, B.py, B.pz, reach(B.r, B.vx, B.vy, B.vz, dt)); V4[j] = make_float4(B.vx, B.vy, B.vz, B.r);
+        if (record) emit_event(v, w, step, 4, PG_CLASS_DYNAMIC, i, PG_CLASS_DYNAMIC, j);
+        if (n_chg < kMaxRowChanges) chg[n_chg] = j;
+      }
+      n_chg++;
+      __syncwarp();
+      fresh = true;                                  // the row body changed: rebuild the remaining candidates
+    }
+    j0 = j + 1;
+  }
+  return n_chg;
+}
+
+// Column c changed (contact) while row row0+rl was being swept: which of the block's LATER rows
+// (bit l, l > rl) now have it as a candidate?  A later row r sees column c integrated iff c < r;
+// shared memory already holds it integrated iff c < done.
+__device__ __noinline__ unsigned recheck_column(const float4 *P4, const float4 *V4, int row0, int rl, int c, bool c_rest, int done,
+                                                int n, float dt, int lane) {
+  const int r = row0 + lane;
+  bool pass = false;
+  if (lane > rl && r < n && r != c) {
+    const bool integ = c >= done && c < r && !c_rest;
+    pass = !pgs::pair_gate_far(P4, V4, r, c, integ, dt);
+  }
+  return __ballot_sync(kFull, pass);
+}
+
 // The register cache is kept ROTATED: while row block `rb` (rows rb*32 .. rb*32+31) is swept,
 // static slot k of the cache holds the body of actual slot (rb + k) mod CPT, so the block's own
 // bodies always sit in static slot 0.  That keeps every register index a compile-time constant
 // with ONE copy of the row loop in the instruction stream (a fully unrolled variant was 9.5k SASS
 // instructions and spent most of its time in instruction-cache misses).
+// Shared-memory image of one world (one warp).
+template <int CPT>
+struct WarpSmem {
+  float4 P4[CPT * 32];
+  float4 V4[CPT * 32];
+  float4 planes[kMaxPlanes];
+  ulonglong2 RA[64];                               // filter coefficients of the 32 rows being swept, as duplicated pairs for FFMA2
+  unsigned long long RB[32];
+  unsigned W[CPT * 32];                       // candidate bits: [static slot][lane], bit = row of the block
+  unsigned list[kGateList];
+  unsigned rest[CPT];                       // at-rest flags by actual slot, bit = lane
+  int chg[kMaxRowChanges];
+};
+
 template <int CPT, int WPB>
-__global__ void __launch_bounds__(WPB * 32, (CPT <= 8) ? PG_SPH_WARPS / WPB : 2)
+__global__ void __launch_bounds__(WPB * 32, (CPT <= 8) ? PG_SPH_WARPS / WPB : 1)
 k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int first_world, int end_world) {
-  __shared__ float4 s_planes[WPB][kMaxPlanes];
-  __shared__ float4 s_P4[WPB][CPT * 32];
-  __shared__ float4 s_V4[WPB][CPT * 32];
+  // per-warp shared memory (dynamic: a block of 16 worlds needs more than the 48 KB static limit)
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  WarpSmem<CPT> &S = reinterpret_cast<WarpSmem<CPT> *>(s_raw)[threadIdx.x >> 5];
 
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   // Worlds are handed out through an atomic counter: the grid holds exactly the warps that fit on
   // the GPU, each warp keeps pulling worlds until none are left, so there is no partial last wave.
+  __shared__ int s_base;
   for (;;) {
   int w = 0;
-  if (lane == 0) w = first_world + atomicAdd(work_counter, 1);
-  w = __shfl_sync(kFull, w, 0);
-  if (w >= end_world) return;
+  bool valid = true;
+  if constexpr (PG_SPH_SYNC > 0) {
+    // the block takes WPB worlds at a time and its warps move through the step in phase (block
+    // barriers below), so that an instruction line fetched once serves every warp of the block
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = first_world + atomicAdd(work_counter, WPB);
+    __syncthreads();
+    if (s_base >= end_world) return;
+    w = s_base + wib;
+    valid = w < end_world;
+    if (!valid) w = end_world - 1;
+  } else {
+    if (lane == 0) w = first_world + atomicAdd(work_counter, 1);
+    w = __shfl_sync(kFull, w, 0);
+    if (w >= end_world) return;
+  }
   __syncwarp();
-  const int n = v.counts[w * 3 + 1];
+  const int n = valid ? v.counts[w * 3 + 1] : 0;
   const int ns = min(v.counts[w * 3 + 0], kMaxPlanes);
   const int n_blocks = (n + 31) >> 5;
   const float dt = pgm::clamp_dt(dt_in);
   const float restitution = v.restitution;
   const bool record = v.max_events > 0;
   const bool gate_ok = dt > 1.0e-9f;
-  float4 *P4 = s_P4[wib], *V4 = s_V4[wib];
+  float4 *P4 = S.P4, *V4 = S.V4;
   pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
 
-  if (lane < ns) s_planes[wib][lane] = v.planes[(size_t)w * v.cap[0] + lane];
+  if (lane < ns) S.planes[lane] = v.planes[(size_t)w * v.cap[0] + lane];
 
   unsigned rest = 0;                       // bit s: this lane's body of actual slot s is at rest
   const size_t base = (size_t)w * v.cap[1];
@@ -200,174 +251,261 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
   }
   __syncwarp();
 
-  // Register cache of this lane's CPT bodies for the reach filter, in coordinates relative to the
-  // world's centre: q = p - centre, qr = rho, qc = |q|^2 - rho^2.  With them
-  //   |ci - ck|^2 <= (rho_i + rho_k)^2   <=>   qc_k - 2 q_i.q_k - 2 rho_i rho_k <= rho_i^2 - |q_i|^2
-  // is four FMAs and a compare per pair; the rounding of the expanded form is covered by `slack`
-  // (>= 60 eps of the largest term), which keeps the filter a superset of the exact root test.
-  float qx[CPT], qy[CPT], qz[CPT], qr[CPT], qc[CPT];
   float cx0 = 0.0f, cy0 = 0.0f, cz0 = 0.0f;
-  auto cache_slot = [&](int k, const float4 a) {
-    qx[k] = a.x - cx0; qy[k] = a.y - cy0; qz[k] = a.z - cz0; qr[k] = a.w;
-    qc[k] = __fmaf_rn(qx[k], qx[k], __fmaf_rn(qy[k], qy[k], qz[k] * qz[k])) - a.w * a.w;
-  };
 
   for (int step = 0; step < n_steps; step++) {
+    if constexpr (PG_SPH_SYNC == 1) __syncthreads();
     // ---------------- pass 3: every sphere against the planes, in plane order (world.c:369-471)
-    float bl[3] = {3.0e38f, 3.0e38f, 3.0e38f}, bh[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
     // cheap gate: |signed distance| beyond the reach -> the root test of the interval search fails
     auto plane_near = [&](const float4 a, const float4 pl) {
       const float s0 = __fmaf_rn(a.x, pl.x, __fmaf_rn(a.y, pl.y, a.z * pl.z)) - pl.w;
       return !(gate_ok && fabsf(s0) > a.w * 1.0001f + 1.0e-5f * (fabsf(s0) + fabsf(pl.w) + 1.0f));
     };
-    if (ns <= 8 && n_blocks <= 8) {
-      // Every lane first lists its (body, plane) visits that pass the cheap gate, then all lanes
-      // work through their own lists TOGETHER: the exact evaluations of different bodies run in
-      // the same SIMT pass instead of one after the other.  Per body the planes stay in order, and
-      // a contact re-gates that body's remaining planes against its new state.
-      unsigned long long pend = 0;
+    // Every lane first lists its (body, plane) visits that pass the cheap gate -- 8 slots x 8 planes
+    // at a time in one 64-bit word -- then all lanes work through their own lists TOGETHER: the
+    // exact evaluations of different bodies run in the same SIMT pass instead of one after the
+    // other.  Per body the planes stay in order, and a contact re-gates that body's remaining planes
+    // against its new state.
 #pragma unroll 1
-      for (int s = 0; s < n_blocks; s++) {
-        const int i = s * 32 + lane;
-        if (i < n) {
-          const float4 a = P4[i];
-          for (int k = 0; k < ns; k++) if (plane_near(a, s_planes[wib][k])) pend |= 1ull << (s * 8 + k);
-        }
-      }
-      while (__any_sync(kFull, pend != 0ull)) {
-        if (pend) {
-          const int bit = __ffsll((long long)pend) - 1;
-          pend &= pend - 1ull;
-          const int s = bit >> 3, k = bit & 7, i = s * 32 + lane;
-          int came_to_rest = 0;
-          if (plane_slow_path(P4, V4, i, s_planes[wib][k], restitution, dt, gate_ok, &came_to_rest, leaf)) {
-            if (came_to_rest) rest |= 1u << s;
-            if (record) emit_event(v, w, step, 3, PG_CLASS_DYNAMIC, i, PG_CLASS_STATIC, k);
+    for (int g = 0; g < ns; g += 8) {
+      const int g_end = min(g + 8, ns);
+#pragma unroll 1
+      for (int sg = 0; sg < n_blocks; sg += 8) {
+        unsigned long long pend = 0;
+#pragma unroll 1
+        for (int s = sg; s < min(sg + 8, n_blocks); s++) {
+          const int i = s * 32 + lane;
+          if (i < n) {
             const float4 a = P4[i];
-            for (int k2 = k + 1; k2 < ns; k2++) {
-              const unsigned long long b2 = 1ull << (s * 8 + k2);
-              if (plane_near(a, s_planes[wib][k2])) pend |= b2; else pend &= ~b2;
-            }
+#pragma unroll 1
+            for (int k = g; k < g_end; k++) if (plane_near(a, S.planes[k])) pend |= 1ull << ((s - sg) * 8 + (k - g));
           }
         }
-      }
-    } else {
-#pragma unroll 1
-      for (int s = 0; s < n_blocks; s++) {
-        const int i = s * 32 + lane;
-        if (i < n) {
-          float4 a = P4[i];
-#pragma unroll 1
-          for (int k = 0; k < ns; k++) {
-            const float4 pl = s_planes[wib][k];
-            if (!plane_near(a, pl)) continue;
+        while (__any_sync(kFull, pend != 0ull)) {
+          if (pend) {
+            const int bit = __ffsll((long long)pend) - 1;
+            pend &= pend - 1ull;
+            const int s = sg + (bit >> 3), k = g + (bit & 7), i = s * 32 + lane;
             int came_to_rest = 0;
-            if (plane_slow_path(P4, V4, i, pl, restitution, dt, gate_ok, &came_to_rest, leaf)) {
-              a = P4[i];
+            if (plane_slow_path(P4, V4, i, S.planes[k], restitution, dt, gate_ok, &came_to_rest, leaf)) {
               if (came_to_rest) rest |= 1u << s;
               if (record) emit_event(v, w, step, 3, PG_CLASS_DYNAMIC, i, PG_CLASS_STATIC, k);
+              const float4 a = P4[i];
+#pragma unroll 1
+              for (int k2 = k + 1; k2 < g_end; k2++) {
+                const unsigned long long b2 = 1ull << ((bit & ~7) + (k2 - g));
+                if (plane_near(a, S.planes[k2])) pend |= b2; else pend &= ~b2;
+              }
             }
           }
         }
       }
     }
+    // bounding box of the world: min / max through an order-preserving float -> int map and one
+    // warp reduction each
+    int ol[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, oh[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
+    auto ordered = [](float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); };
+    auto unordered = [](int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); };
 #pragma unroll 1
     for (int s = 0; s < n_blocks; s++) {
       const int i = s * 32 + lane;
       if (i < n) {
         const float4 a = P4[i];
-        bl[0] = fminf(bl[0], a.x); bl[1] = fminf(bl[1], a.y); bl[2] = fminf(bl[2], a.z);
-        bh[0] = fmaxf(bh[0], a.x); bh[1] = fmaxf(bh[1], a.y); bh[2] = fmaxf(bh[2], a.z);
+        const int ox = ordered(a.x), oy = ordered(a.y), oz = ordered(a.z);
+        ol[0] = min(ol[0], ox); ol[1] = min(ol[1], oy); ol[2] = min(ol[2], oz);
+        oh[0] = max(oh[0], ox); oh[1] = max(oh[1], oy); oh[2] = max(oh[2], oz);
       }
+    }
+    float bl[3], bh[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      bl[k] = unordered(__reduce_min_sync(kFull, ol[k]));
+      bh[k] = unordered(__reduce_max_sync(kFull, oh[k]));
     }
     // world centre and the magnitude the filter's rounding slack is scaled with
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        bl[k] = fminf(bl[k], __shfl_xor_sync(kFull, bl[k], o));
-        bh[k] = fmaxf(bh[k], __shfl_xor_sync(kFull, bh[k], o));
-      }
-    }
     cx0 = 0.5f * (bl[0] + bh[0]); cy0 = 0.5f * (bl[1] + bh[1]); cz0 = 0.5f * (bl[2] + bh[2]);
     if (!(fabsf(cx0) < 1.0e30f && fabsf(cy0) < 1.0e30f && fabsf(cz0) < 1.0e30f)) { cx0 = cy0 = cz0 = 0.0f; }
     const float hx = bh[0] - cx0 + 2.0f, hy = bh[1] - cy0 + 2.0f, hz = bh[2] - cz0 + 2.0f;   // + room to move within the step
     const float maxn2 = hx * hx + hy * hy + hz * hz;
+    const bool wild = !(maxn2 < 1.0e30f);          // non-finite or astronomically spread world: the expanded filter is not trusted
     __syncwarp();
 
-    // ---------------- pass 4: rows in order (world.c:473-554)
+    {
+    // ---------------- pass 4, batched filter: rows in order (world.c:473-554)
+    // Per block of 32 rows: (1) the reach filter of all 32 rows against all columns in one
+    // branch-free loop (bit rl of W[k] = row rl x this lane's column of static slot k), using the
+    // state every row WILL see if no contact intervenes (columns of the block's own slot: not yet
+    // integrated for earlier rows, speculatively integrated for later ones); (2) only rows with a
+    // candidate are visited, in order; (3) a contact rewrites the bits of the bodies it changed.
+    int done = 0;                                  // rows [0, done) are integrated in shared memory
 #pragma unroll
-    for (int k = 0; k < CPT; k++) cache_slot(k, P4[k * 32 + lane]);
-
+    for (int sl = 0; sl < CPT; sl++) {
+      const unsigned b = __ballot_sync(kFull, (rest >> sl) & 1u);
+      if (lane == 0) S.rest[sl] = b;
+    }
 #pragma unroll 1
-    for (int rb = 0; rb < n_blocks; rb++) {
-      // speculative integration of this lane's row body (committed to the register cache when its
-      // row completes, written back to shared memory lazily; recomputed if a contact intervenes)
-      float ipx, ipy, ipz, ivx, ivy, ivz, irho, irad;
-      auto speculate = [&]() {
-        const float4 a = P4[rb * 32 + lane], b = V4[rb * 32 + lane];
-        V3 p = v3(a.x, a.y, a.z), vel = v3(b.x, b.y, b.z);
-        irho = a.w; irad = b.w;
-        if (!((rest >> rb) & 1u)) { pgm::integrate(p, vel, dt); irho = reach(b.w, vel.x, vel.y, vel.z, dt); }
-        ipx = p.x; ipy = p.y; ipz = p.z; ivx = vel.x; ivy = vel.y; ivz = vel.z;
-      };
-      speculate();
-      const int rows_here = min(32, n - rb * 32);
-      int flushed = 0;                              // rows [0, flushed) of this block are committed in shared memory
-#pragma unroll 1
-      for (int rl = 0; rl < rows_here; rl++) {
-        const int i = rb * 32 + rl;
-        const float4 rp = P4[i];
-        const float rx = rp.x - cx0, ry = rp.y - cy0, rz = rp.z - cz0;
-        const float n2 = __fmaf_rn(rx, rx, __fmaf_rn(ry, ry, rz * rz));
-        const float ea = -2.0f * rx, eb = -2.0f * ry, ec = -2.0f * rz, ed = -2.0f * rp.w;
-        const float ee = __fmaf_rn(rp.w, rp.w, -n2) + (8.0e-6f * (n2 + maxn2) + 1.0e-6f);
-        unsigned mask = 0;
+    for (int rb = 0; rb < (PG_SPH_SYNC == 2 ? CPT : n_blocks); rb++) {
+      if constexpr (PG_SPH_SYNC == 2) { __syncthreads(); if (rb >= n_blocks) continue; }
+      const int row0 = rb * 32;
+      const int rows_here = min(32, n - row0);
+      constexpr int NP = (CPT + 2) / 2;            // column pairs: CPT slots + the integrated own column (+ padding)
+      unsigned long long cx2[NP], cy2[NP], cz2[NP], cr2[NP], cc2[NP];
+      {
+        float fx[2 * NP], fy[2 * NP], fz[2 * NP], fr[2 * NP], fc[2 * NP];
+        auto put = [&](int m, float px, float py, float pz, float rho) {
+          fx[m] = px - cx0; fy[m] = py - cy0; fz[m] = pz - cz0; fr[m] = rho;
+          fc[m] = __fmaf_rn(fx[m], fx[m], __fmaf_rn(fy[m], fy[m], fz[m] * fz[m])) - rho * rho;
+        };
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
-          const float t = __fmaf_rn(ea, qx[k], __fmaf_rn(eb, qy[k], __fmaf_rn(ec, qz[k], __fmaf_rn(ed, qr[k], qc[k]))));
-          mask |= (t <= ee ? 1u : 0u) << k;
+          int sa = rb + k; if (sa >= CPT) sa -= CPT;
+          const float4 a = P4[sa * 32 + lane];
+          put(k, a.x, a.y, a.z, a.w);
         }
-        if (lane == rl) mask &= ~1u;                 // the row body itself lives in static slot 0
-        if (__any_sync(kFull, mask != 0)) {
-          // bring shared memory up to date with the rows committed so far in this block
-          if (lane >= flushed && lane < rl) {
-            P4[rb * 32 + lane] = make_float4(ipx, ipy, ipz, irho);
-            V4[rb * 32 + lane] = make_float4(ivx, ivy, ivz, irad);
-          }
-          flushed = rl;
-          // static slot k is actual slot (rb + k) mod CPT: rotate the bits into column order
-          const unsigned full = (CPT == 32) ? 0xffffffffu : ((1u << CPT) - 1u);
-          const unsigned amask = ((mask << rb) | (mask >> ((CPT - rb) & 31))) & full;
-          if (row_slow_path(P4, V4, i, rb == 0 ? mask : amask, lane, CPT, dt, v, w, step, record)) {
+        // own body: filter coefficients of its row, and the state later rows of the block will see
+        const float4 a = P4[row0 + lane], b = V4[row0 + lane];
+        {
+          const float rx = a.x - cx0, ry = a.y - cy0, rz = a.z - cz0;
+          const float n2 = __fmaf_rn(rx, rx, __fmaf_rn(ry, ry, rz * rz));
+          const float ea = -2.0f * rx, eb = -2.0f * ry, ec = -2.0f * rz, ed = -2.0f * a.w;
+          const float ne = -(__fmaf_rn(a.w, a.w, -n2) + (8.0e-6f * (n2 + maxn2) + 1.0e-6f));
+          S.RA[2 * lane] = make_ulonglong2(pack2(ea, ea), pack2(eb, eb));
+          S.RA[2 * lane + 1] = make_ulonglong2(pack2(ec, ec), pack2(ed, ed));
+          S.RB[lane] = pack2(ne, ne);
+        }
+        V3 p = v3(a.x, a.y, a.z), vel = v3(b.x, b.y, b.z);
+        float irho = a.w;
+        if (!((rest >> rb) & 1u)) { pgm::integrate(p, vel, dt); irho = reach(b.w, vel.x, vel.y, vel.z, dt); }
+        put(CPT, p.x, p.y, p.z, irho);
 #pragma unroll
-            for (int k = 0; k < CPT; k++) {
-              int sa = rb + k; if (sa >= CPT) sa -= CPT;
-              cache_slot(k, P4[sa * 32 + lane]);
-            }
-            if (lane >= rl) speculate();
-            else {                                   // already integrated: keep what shared memory now holds
-              const float4 a = P4[rb * 32 + lane], b = V4[rb * 32 + lane];
-              ipx = a.x; ipy = a.y; ipz = a.z; irho = a.w; ivx = b.x; ivy = b.y; ivz = b.z; irad = b.w;
-            }
-          }
+        for (int m = CPT + 1; m < 2 * NP; m++) put(m, p.x, p.y, p.z, irho);
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+          cx2[q] = pack2(fx[2 * q], fx[2 * q + 1]); cy2[q] = pack2(fy[2 * q], fy[2 * q + 1]); cz2[q] = pack2(fz[2 * q], fz[2 * q + 1]);
+          cr2[q] = pack2(fr[2 * q], fr[2 * q + 1]); cc2[q] = pack2(fc[2 * q], fc[2 * q + 1]);
         }
-        // integrate row i (world.c:549-553): the owner lane's cache takes the speculative state
-        if (lane == rl) cache_slot(0, make_float4(ipx, ipy, ipz, irho));
       }
       __syncwarp();
-      if (lane >= flushed && lane < rows_here) {
-        P4[rb * 32 + lane] = make_float4(ipx, ipy, ipz, irho);
-        V4[rb * 32 + lane] = make_float4(ivx, ivy, ivz, irad);
-      }
-      __syncwarp();
-      // rotate the cache: the next block's bodies move into static slot 0
-      {
-        const float t0 = qx[0], t1 = qy[0], t2 = qz[0], t3 = qr[0], t4 = qc[0];
+      unsigned W[2 * NP];
 #pragma unroll
-        for (int k = 0; k + 1 < CPT; k++) { qx[k] = qx[k + 1]; qy[k] = qy[k + 1]; qz[k] = qz[k + 1]; qr[k] = qr[k + 1]; qc[k] = qc[k + 1]; }
-        qx[CPT - 1] = t0; qy[CPT - 1] = t1; qz[CPT - 1] = t2; qr[CPT - 1] = t3; qc[CPT - 1] = t4;
+      for (int m = 0; m < 2 * NP; m++) W[m] = 0;
+#pragma unroll 2
+      for (int rl = 0; rl < rows_here; rl++) {
+        const ulonglong2 e0 = S.RA[2 * rl], e1 = S.RA[2 * rl + 1];
+        const unsigned long long ne = S.RB[rl];
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+          // (|q_c|^2 - rho_c^2) - 2 rho_r rho_c - 2 q_r.q_c - (rho_r^2 - |q_r|^2 + slack): negative <=> candidate
+          unsigned long long x = fadd2(cc2[q], ne);
+          x = ffma2(e1.y, cr2[q], x); x = ffma2(e1.x, cz2[q], x); x = ffma2(e0.y, cy2[q], x); x = ffma2(e0.x, cx2[q], x);
+          float lo, hi; unpack2(x, lo, hi);
+          W[2 * q] = __funnelshift_l(__float_as_uint(lo), W[2 * q], 1);        // shift the sign bit in
+          W[2 * q + 1] = __funnelshift_l(__float_as_uint(hi), W[2 * q + 1], 1);
+        }
       }
+#pragma unroll
+      for (int m = 0; m <= CPT; m++) W[m] = __brev(W[m]) >> (32 - rows_here);   // bit rl = row rl
+      // own slot: rows before this lane's body see it as it is, rows after it see it integrated
+      W[0] = (W[0] & ((1u << lane) - 1u)) | (W[CPT] & (0xfffffffeu << lane));
+      if (wild) {                                  // every pair is a candidate; the rows filter for themselves
+#pragma unroll
+        for (int k = 0; k < CPT; k++) W[k] = 0xffffffffu >> (32 - rows_here);
+      }
+      unsigned *WS = S.W;                     // WS[k * 32 + lane]: the bit matrix, in shared memory from here on
+#pragma unroll
+      for (int k = 0; k < CPT; k++) WS[k * 32 + lane] = W[k];
+      __syncwarp();
+      // --- closest-approach gate of every surviving (row, column) bit, one pair per lane: the bits
+      // are compacted into a list (k, lane, rl) and gated 32 at a time.  More than kGateList bits in
+      // one block (a dense pile): the rows gate their own candidates instead (`fresh` below).
+      bool gated = false;
+      int cnt = 0;
+#pragma unroll
+      for (int k = 0; k < CPT; k++) cnt += __popc(W[k]);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
+      const int total = __shfl_sync(kFull, incl, 31);
+      if (dt > 1.0e-9f && total <= kGateList) {
+        gated = true;
+        if (total > 0) {
+          unsigned *list = S.list;
+          int off = incl - cnt;
+#pragma unroll 1
+          for (int k = 0; k < CPT; k++) {
+            for (unsigned word = WS[k * 32 + lane]; word; word &= word - 1u)
+              list[off++] = (unsigned)k | ((unsigned)lane << 8) | ((unsigned)(__ffs((int)word) - 1) << 16);
+          }
+          __syncwarp();
+#pragma unroll 1
+          for (int idx = lane; idx < total; idx += 32) {
+            const unsigned e = list[idx];
+            const int ek = e & 0xff, el = (e >> 8) & 0xff, erl = e >> 16;
+            int sa = rb + ek; if (sa >= CPT) sa -= CPT;
+            // a column of the block's own slot that comes before the row is integrated by then
+            const bool integ = ek == 0 && el < erl && !((S.rest[sa] >> el) & 1u);
+            if (pgs::pair_gate_far(P4, V4, row0 + erl, sa * 32 + el, integ, dt)) atomicAnd(&WS[ek * 32 + el], ~(1u << erl));
+          }
+          __syncwarp();
+        }
+      }
+      unsigned rows_any = 0;
+      if (total > 0) {
+        unsigned any = 0;
+#pragma unroll 1
+        for (int k = 0; k < CPT; k++) any |= WS[k * 32 + lane];
+        rows_any = __reduce_or_sync(kFull, any);
+      }
+      unsigned dirty_rows = 0;
+      auto commit_to = [&](int upto) {             // integrate rows [done, upto) of this block (world.c:549-553)
+        const int r = row0 + lane;
+        if (r >= done && r < upto && !((rest >> rb) & 1u)) {
+          const float4 a = P4[r], b = V4[r];
+          V3 p = v3(a.x, a.y, a.z), vel = v3(b.x, b.y, b.z);
+          pgm::integrate(p, vel, dt);
+          P4[r] = make_float4(p.x, p.y, p.z, reach(b.w, vel.x, vel.y, vel.z, dt));
+          V4[r] = make_float4(vel.x, vel.y, vel.z, b.w);
+        }
+        done = upto;
+        __syncwarp();
+      };
+      const unsigned full = (CPT == 32) ? 0xffffffffu : ((1u << CPT) - 1u);
+      while (rows_any) {
+        const int rl = __ffs((int)rows_any) - 1;
+        const int i = row0 + rl;
+        commit_to(i);
+        unsigned mask = 0;
+#pragma unroll 1
+        for (int k = 0; k < CPT; k++) mask |= ((WS[k * 32 + lane] >> rl) & 1u) << k;
+        // static slot k is actual slot (rb + k) mod CPT: rotate the bits into column order
+        const unsigned amask = ((mask << rb) | (mask >> ((CPT - rb) & 31))) & full;
+        const int n_chg = row_visits(P4, V4, i, rb == 0 ? mask : amask, !gated || ((dirty_rows >> rl) & 1u), lane, CPT, dt, v, w, step, record, S.chg);
+        const unsigned later = 0xfffffffeu << rl;  // rows after rl
+        if (n_chg) {
+          if (n_chg > kMaxRowChanges) {
+            dirty_rows |= later;                   // too many to track: every later row re-filters itself
+          } else {
+#pragma unroll 1
+            for (int e = 0; e <= n_chg; e++) {
+              const int c = e < n_chg ? S.chg[e] : i;       // the changed columns, then the row body itself
+              const bool c_rest = (S.rest[c >> 5] >> (c & 31)) & 1u;
+              const unsigned word = recheck_column(P4, V4, row0, rl, c, c_rest, done, n, dt, lane);
+              int kc = (c >> 5) - rb; if (kc < 0) kc += CPT;
+              if (lane == 0) WS[kc * 32 + (c & 31)] = (WS[kc * 32 + (c & 31)] & ~later) | word;
+              if (c > i && c < row0 + 32) dirty_rows |= 1u << (c - row0);   // a later row of this block changed
+            }
+            __syncwarp();
+          }
+          unsigned any = 0;
+#pragma unroll 1
+          for (int k = 0; k < CPT; k++) any |= WS[k * 32 + lane];
+          rows_any = (__reduce_or_sync(kFull, any) | dirty_rows) & later;
+        } else {
+          rows_any &= rows_any - 1u;
+        }
+      }
+      commit_to(row0 + rows_here);
+    }
     }
   }
 
@@ -498,17 +636,18 @@ template <int CPT, int WPB>
 static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter) {
   static bool configured = false;
   static int resident_blocks = 0;
+  constexpr size_t smem_bytes = sizeof(WarpSmem<CPT>) * WPB;
   if (!configured) {
-    // all shared memory the SM has: the kernel wants an 8 KB world image per resident warp
     cudaFuncSetAttribute(k_step_spheres<CPT, WPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_step_spheres<CPT, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_spheres<CPT, WPB>, WPB * 32, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_spheres<CPT, WPB>, WPB * 32, smem_bytes);
     resident_blocks = std::max(1, per_sm) * w->sm_count;
     configured = true;
   }
   const int blocks = std::min((count + WPB - 1) / WPB, resident_blocks);
   cudaMemsetAsync(counter, 0, sizeof(int), stream);
-  k_step_spheres<CPT, WPB><<<blocks, WPB * 32, 0, stream>>>(w->v, dt, n_steps, counter, first, first + count);
+  k_step_spheres<CPT, WPB><<<blocks, WPB * 32, smem_bytes, stream>>>(w->v, dt, n_steps, counter, first, first + count);
   return PG_OK;
 }
 
@@ -516,11 +655,11 @@ static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int cou
 int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter) {
   const int cap = w->v.cap[1];
   if (w->v.cap[0] > kMaxPlanes) { pg_set_error("sphere mode supports at most %d static planes", kMaxPlanes); return PG_ERR_CAPACITY; }
-  if (cap <= 32) launch_spheres<1, 4>(w, dt, n_steps, first, count, stream, counter);
-  else if (cap <= 64) launch_spheres<2, 4>(w, dt, n_steps, first, count, stream, counter);
-  else if (cap <= 128) launch_spheres<4, 4>(w, dt, n_steps, first, count, stream, counter);
-  else if (cap <= 256) launch_spheres<8, 4>(w, dt, n_steps, first, count, stream, counter);
-  else if (cap <= 512) launch_spheres<16, 2>(w, dt, n_steps, first, count, stream, counter);
+  if (cap <= 32) launch_spheres<1, PG_SPH_WPB>(w, dt, n_steps, first, count, stream, counter);
+  else if (cap <= 64) launch_spheres<2, PG_SPH_WPB>(w, dt, n_steps, first, count, stream, counter);
+  else if (cap <= 128) launch_spheres<4, PG_SPH_WPB>(w, dt, n_steps, first, count, stream, counter);
+  else if (cap <= 256) launch_spheres<8, PG_SPH_WPB>(w, dt, n_steps, first, count, stream, counter);
+  else if (cap <= 512) launch_spheres<16, 8>(w, dt, n_steps, first, count, stream, counter);
   else { pg_set_error("sphere mode supports at most 512 spheres per world (got capacity %d)", cap); return PG_ERR_CAPACITY; }
   PG_CUDA(cudaGetLastError());
   w->launches++;
