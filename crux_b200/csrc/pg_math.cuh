@@ -287,8 +287,12 @@ struct WalkCount {
 #define PG_WALK_NODE()
 #endif
 
+// `budget`: give up (return kWalkGaveUp) after that many nodes; the caller then decides the pair
+// another way (ss_interval: leaf scan).
+enum { kWalkFalse = 0, kWalkTrue = 1, kWalkGaveUp = 2 };
 template <typename Sample, int Kind = 0, typename Eval, typename Probe>
-__device__ __forceinline__ bool interval_walk_guided(float t_begin, float t_end, float t_pref, Eval eval, Probe probe, unsigned long long *dbg_nodes = nullptr) {
+__device__ __forceinline__ int interval_walk_guided(float t_begin, float t_end, float t_pref, Eval eval, Probe probe,
+                                                    int budget = 0x7fffffff, unsigned long long *dbg_nodes = nullptr) {
   unsigned long long path = 0;
   int depth = 0;
   float t0 = t_begin, t1 = t_end;
@@ -296,11 +300,12 @@ __device__ __forceinline__ bool interval_walk_guided(float t_begin, float t_end,
   PG_WALK_BEGIN(Kind);
   for (;;) {
     PG_WALK_NODE();
+    if (--budget < 0) return kWalkGaveUp;
     const int st = probe(t0, t1, Sa, Sb);
-    if (st == kSure) return true;
+    if (st == kSure) return kWalkTrue;
     if (st == kOpen) {
-      if (t1 - t0 < kIntervalEps) return true;
-      if (depth >= 62) return false;
+      if (t1 - t0 < kIntervalEps) return kWalkTrue;
+      if (depth >= 62) return kWalkFalse;
       const float mid = (t0 + t1) * 0.5f;
       const Sample Sm = eval(mid);
       path <<= 1; depth++;
@@ -308,7 +313,7 @@ __device__ __forceinline__ bool interval_walk_guided(float t_begin, float t_end,
       continue;
     }
     while (depth > 0 && (path & 1ull)) { path >>= 1; depth--; }
-    if (depth == 0) return false;
+    if (depth == 0) return kWalkFalse;
     path |= 1ull;
     t0 = t_begin; t1 = t_end;
     for (int k = depth - 1; k >= 0; k--) {
@@ -326,6 +331,69 @@ __device__ __forceinline__ bool interval_walk_guided(float t_begin, float t_end,
 struct LeafLen { float lo, hi; };
 __host__ __device__ __forceinline__ LeafLen default_leaf_len() { LeafLen l; l.lo = 0.4990e-6f; l.hi = 1.0e-6f; return l; }
 constexpr float kU = 5.9604645e-8f;                  // 2^-24, unit roundoff of binary32
+constexpr int kWalkBudget = 48;                      // nodes before a sphere-sphere walk switches to the leaf scan
+constexpr int kScanMax = 8192;                       // widest leaf window the scan takes on
+
+// Leaf scan behind ss_interval (see there); out of line and self-contained so that the common path
+// keeps its registers.  Returns kWalkTrue / kWalkFalse, or kWalkGaveUp if the window is too wide or
+// the halving tree is not uniform there (the caller then finishes the plain walk).
+template <bool Coop>
+__device__ __noinline__ int ss_leaf_scan(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float nB, float rs,
+                                         float t_begin, float t_end, LeafLen leaf) {
+  const float tmax = fmaxf(fabsf(t_begin), fabsf(t_end));
+  const float c1 = fabsf(cA.x) + fabsf(cA.y) + fabsf(cA.z) + fabsf(cB.x) + fabsf(cB.y) + fabsf(cB.z);
+  const float v1 = fabsf(vA.x) + fabsf(vA.y) + fabsf(vA.z) + fabsf(vB.x) + fabsf(vB.y) + fabsf(vB.z);
+  const float E0 = 1.25f * kU * (c1 + 2.0f * v1 * tmax) + 1.0e-30f;
+  const float mm_hi = (nA * leaf.hi + nB * leaf.hi) * 1.000001f;
+  if (!((nA + nB < 1.0e30f) && (c1 < 1.0e30f) && (rs < 1.0e30f) && (v1 < 1.0e30f))) return kWalkGaveUp;
+  const double sx = (double)cA.x - (double)cB.x, sy = (double)cA.y - (double)cB.y, sz = (double)cA.z - (double)cB.z;
+  const double ux = (double)vA.x - (double)vB.x, uy = (double)vA.y - (double)vB.y, uz = (double)vA.z - (double)vB.z;
+  const double ss_d = sx * sx + sy * sy + sz * sz, su_d = sx * ux + sy * uy + sz * uz, uu_d = ux * ux + uy * uy + uz * uz;
+  const double d2_slack = 1.0e-13 * (ss_d + 2.0 * fabs(su_d) * (double)tmax + uu_d * (double)tmax * (double)tmax);
+  const double dead_thr = ((double)mm_hi + (double)rs + (double)E0) * 1.00001;
+  const double dead_thr2 = dead_thr * dead_thr;
+  auto eval = [&](float t) { return ss_d2_at(cA, vA, cB, vB, t); };
+  {
+    const double cq = ss_d - d2_slack - dead_thr2;            // uu t^2 + 2 su t + cq <= 0 inside the window
+    double tL = (double)t_begin, tR = (double)t_end;
+    if (uu_d > 0.0) {
+      const double disc = su_d * su_d - uu_d * cq;
+      if (disc < 0.0) return kWalkFalse;
+      const double sq = sqrt(disc) * (1.0 + 1.0e-12);
+      tL = (-su_d - sq) / uu_d; tR = (-su_d + sq) / uu_d;
+    } else if (cq > 0.0) {
+      return kWalkFalse;
+    }
+    int D = 0;                                                // depth of the leaves along the leftmost path
+    for (float a = t_begin, b = t_end; b - a >= kIntervalEps && D < 40; D++) b = (a + b) * 0.5f;
+    const double per_t = ldexp(1.0, D) / ((double)t_end - (double)t_begin);
+    const double last = ldexp(1.0, D) - 1.0;
+    const double k0d = fmax(floor((tL - (double)t_begin) * per_t) - 1.0, 0.0), k1d = fmin(floor((tR - (double)t_begin) * per_t) + 1.0, last);
+    if (k0d > k1d) return kWalkFalse;                         // the window misses the interval
+    if (k1d - k0d >= (double)kScanMax || D >= 40) return kWalkGaveUp;   // too wide to scan
+    const long long k0 = (long long)k0d, k1 = (long long)k1d;
+    bool found = false, unknown = false;
+    long long k = k0;
+    if (Coop) k += threadIdx.x & 31;
+    for (; k <= k1 && !found; k += Coop ? 32 : 1) {
+      float t0 = t_begin, t1 = t_end;
+      float Sa = eval(t0), Sb = eval(t1);
+      for (int level = D - 1;; level--) {
+        const float len = t1 - t0;
+        const float mm = nA * len + nB * len;
+        if (ss_dist_exceeds(Sa, rs, mm) || ss_dist_exceeds(Sb, rs, mm)) break;        // this ancestor (or leaf) fails
+        if (len < kIntervalEps) { found = true; break; }
+        if (level < 0) { unknown = true; break; }             // deeper than the leftmost path: not a uniform tree
+        const float mid = (t0 + t1) * 0.5f;
+        const float Sm = eval(mid);
+        if ((k >> level) & 1ll) { t0 = mid; Sa = Sm; } else { t1 = mid; Sb = Sm; }
+      }
+    }
+    if (Coop) { found = __any_sync(0xffffffffu, found); unknown = __any_sync(0xffffffffu, unknown); }
+    if (found) return kWalkTrue;
+    return unknown ? kWalkGaveUp : kWalkFalse;
+  }
+}
 
 // interval_collision for two spheres, world.c:557-582 with distance.c:278-299 inlined.
 // cA/cB = centre + position at t=0, nA/nB = |v| (glm_vec3_norm), rs = rA + rB.
@@ -344,6 +412,8 @@ constexpr float kU = 5.9604645e-8f;                  // 2^-24, unit roundoff of 
 // (|u| ~ nA+nB, where the reach shrinks as fast as the gap), would otherwise make the recursion
 // visit hundreds to O(2^depth) nodes; with the enclosures it is O(depth) unless the closest
 // approach lies inside a band of a few 1e-6 around mm(leaf).
+// Coop: all 32 lanes of the warp call with identical arguments (pg_spheres.cu) and share the leaf scan.
+template <bool Coop = false>
 __device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float nB, float rs,
                                    float t_begin, float t_end, LeafLen leaf = default_leaf_len()) {
   const V3 u = sub(vA, vB);
@@ -379,24 +449,35 @@ __device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float n
   const double d2_slack = 1.0e-13 * (ss_d + 2.0 * fabs(su_d) * (double)tmax + uu_d * (double)tmax * (double)tmax);
   const double dead_thr = ((double)mm_hi + (double)rs + (double)E0) * 1.00001;
   const double dead_thr2 = dead_thr * dead_thr;
-  return interval_walk_guided<float>(t_begin, t_end, t_pref,
-    [&](float t) { return ss_d2_at(cA, vA, cB, vB, t); },
-    [&](float t0, float t1, float d2a, float d2b) -> int {
-      const float len = t1 - t0;
-      const float mm = nA * len + nB * len;
-      if (ss_dist_exceeds(d2a, rs, mm) || ss_dist_exceeds(d2b, rs, mm)) return kDead;
-      if (len < kIntervalEps || !finite_ok) return kOpen;       // leaves are decided by the tests above
-      // real minimum of |s + u t|^2 over the node, in closed form: the parabola's vertex clamped into it
-      const double tc = fmin(fmax(t_star, (double)t0), (double)t1);
-      const double D2min = fma(tc, fma(uu_d, tc, 2.0 * su_d), ss_d) - d2_slack;
-      if (D2min > dead_thr2) return kDead;
-      const float Da = sqrtf(d2a), Db = sqrtf(d2b);
-      const float Dmax = fmaxf(Da, Db);
-      const float E = E0 + 8.0f * kU * Dmax;       // |computed - real| at any t of the node
-      const float upper = fmaxf((Dmax + 2.0f * E) * 1.0000001f - rs, 0.0f) * 1.000001f;     // >= dist anywhere in the node
-      if (upper <= mm_lo) return kSure;
-      return kOpen;
-    } PG_DBG_ARG);
+  auto eval = [&](float t) { return ss_d2_at(cA, vA, cB, vB, t); };
+  auto probe = [&](float t0, float t1, float d2a, float d2b) -> int {
+    const float len = t1 - t0;
+    const float mm = nA * len + nB * len;
+    if (ss_dist_exceeds(d2a, rs, mm) || ss_dist_exceeds(d2b, rs, mm)) return kDead;
+    if (len < kIntervalEps || !finite_ok) return kOpen;       // leaves are decided by the tests above
+    // real minimum of |s + u t|^2 over the node, in closed form: the parabola's vertex clamped into it
+    const double tc = fmin(fmax(t_star, (double)t0), (double)t1);
+    const double D2min = fma(tc, fma(uu_d, tc, 2.0 * su_d), ss_d) - d2_slack;
+    if (D2min > dead_thr2) return kDead;
+    const float Da = sqrtf(d2a), Db = sqrtf(d2b);
+    const float Dmax = fmaxf(Da, Db);
+    const float E = E0 + 8.0f * kU * Dmax;       // |computed - real| at any t of the node
+    const float upper = fmaxf((Dmax + 2.0f * E) * 1.0000001f - rs, 0.0f) * 1.000001f;     // >= dist anywhere in the node
+    if (upper <= mm_lo) return kSure;
+    return kOpen;
+  };
+  // A grazing pair (closest approach within a few 1e-6 of the leaf reach -- typically the step after
+  // a contact left the two spheres touching) keeps thousands of nodes around the vertex open.  After
+  // kWalkBudget nodes the walk is abandoned for a LEAF SCAN: only leaves inside the window where
+  // the real distance is below the dead threshold can pass their own test; each of them is reached
+  // from the root by its own halving sequence, testing every ancestor on the way exactly as the
+  // recursion would.  The candidates are independent, so a warp scans 32 at a time.
+  for (int budget = kWalkBudget;; budget = 0x7fffffff) {
+    const int r = interval_walk_guided<float>(t_begin, t_end, t_pref, eval, probe, budget PG_DBG_ARG);
+    if (r != kWalkGaveUp) return r == kWalkTrue;
+    const int q = ss_leaf_scan<Coop>(cA, vA, nA, cB, vB, nB, rs, t_begin, t_end, leaf);
+    if (q != kWalkGaveUp) return q == kWalkTrue;
+  }
 }
 
 // min_dist_at_time_sphere_plane, distance.c:305-321: max(|s| - r, 0), |s|-r in double.

@@ -66,7 +66,7 @@ static __device__ __noinline__ bool pair_gate_far(const float4 *P4, const float4
 // Exact visit of two spheres (world.c:481-541 with the sphere-sphere table entries).
 // All lanes call it with identical arguments.  Returns true if an event fires; A and B updated.
 // Gate = false: the caller already applied pair_gate_rejects to this very state.
-template <bool Gate>
+template <bool Gate, bool Coop>
 static __device__ __forceinline__ bool sphere_pair_exact_impl(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
   V3 cA = v3(0.0f + A.px, 0.0f + A.py, 0.0f + A.pz);     // centre (0,0,0) + position, distance.c:283
   V3 cB = v3(0.0f + B.px, 0.0f + B.py, 0.0f + B.pz);
@@ -74,7 +74,7 @@ static __device__ __forceinline__ bool sphere_pair_exact_impl(Sphere &A, Sphere 
   float rs = A.r + B.r;
   float nA = pgm::norm(vA), nB = pgm::norm(vB);
   if (Gate && pair_gate_rejects(cA, vA, cB, vB, rs, nA + nB, dt)) return false;
-  if (!pgm::ss_interval(cA, vA, nA, cB, vB, nB, rs, 0.0f, dt, leaf)) return false;
+  if (!pgm::ss_interval<Coop>(cA, vA, nA, cB, vB, nB, rs, 0.0f, dt, leaf)) return false;
   pgm::Contact c = pgm::ss_narrow(cA, vA, cB, vB, rs);
   if (!(c.hit && c.t >= 0)) return false;
   V3 pA = v3(A.px, A.py, A.pz), pB = v3(B.px, B.py, B.pz);
@@ -84,10 +84,11 @@ static __device__ __forceinline__ bool sphere_pair_exact_impl(Sphere &A, Sphere 
   return true;
 }
 static __device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
-  return sphere_pair_exact_impl<true>(A, B, dt, leaf);
+  return sphere_pair_exact_impl<true, false>(A, B, dt, leaf);
 }
+// Warp-uniform variant (all 32 lanes, identical arguments, already gated): the lanes share the leaf scan.
 static __device__ __noinline__ bool sphere_pair_exact_gated(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
-  return sphere_pair_exact_impl<false>(A, B, dt, leaf);
+  return sphere_pair_exact_impl<false, true>(A, B, dt, leaf);
 }
 
 // Exact visit sphere x plane (per lane, divergent).  Returns true if an event fires.

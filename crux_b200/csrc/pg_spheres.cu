@@ -39,7 +39,7 @@ using pgm::v3;
 #define PG_SPH_WARPS 16   // resident warps per SM the register budget is sized for (128 registers per thread)
 #endif
 #ifndef PG_SPH_SYNC
-#define PG_SPH_SYNC 1     // 1: one block barrier per step keeps the block's warps in phase, so that an instruction
+#define PG_SPH_SYNC 1     // P > 0: a block barrier every P steps keeps the block's warps in phase, so that an instruction
 #endif                    //    line fetched once serves all of them (the kernel is instruction-fetch bound); 0: none
 constexpr int kMaxPlanes = 16;
 constexpr unsigned kFull = 0xffffffffu;
@@ -47,7 +47,7 @@ constexpr float kHuge = 1.0e8f;      // padding bodies: far from everything, squ
 
 using pgs::Sphere;
 using pgs::reach;
-using pgs::sphere_pair_exact;
+
 using pgs::sphere_plane_exact;
 
 __device__ __noinline__ void emit_event(const WorldsView &v, int w, int step, int pass, int ac, int ai, int bc, int bi) {
@@ -254,7 +254,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
   float cx0 = 0.0f, cy0 = 0.0f, cz0 = 0.0f;
 
   for (int step = 0; step < n_steps; step++) {
-    if constexpr (PG_SPH_SYNC == 1) __syncthreads();
+    if constexpr (PG_SPH_SYNC >= 1) { if (step % PG_SPH_SYNC == 0) __syncthreads(); }
     // ---------------- pass 3: every sphere against the planes, in plane order (world.c:369-471)
     // cheap gate: |signed distance| beyond the reach -> the root test of the interval search fails
     auto plane_near = [&](const float4 a, const float4 pl) {
@@ -344,8 +344,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
       if (lane == 0) S.rest[sl] = b;
     }
 #pragma unroll 1
-    for (int rb = 0; rb < (PG_SPH_SYNC == 2 ? CPT : n_blocks); rb++) {
-      if constexpr (PG_SPH_SYNC == 2) { __syncthreads(); if (rb >= n_blocks) continue; }
+    for (int rb = 0; rb < n_blocks; rb++) {
       const int row0 = rb * 32;
       const int rows_here = min(32, n - row0);
       constexpr int NP = (CPT + 2) / 2;            // column pairs: CPT slots + the integrated own column (+ padding)
