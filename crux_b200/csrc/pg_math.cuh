@@ -372,6 +372,9 @@ __device__ __noinline__ int ss_leaf_scan(V3 cA, V3 vA, float nA, V3 cB, V3 vB, f
     if (k0d > k1d) return kWalkFalse;                         // the window misses the interval
     if (k1d - k0d >= (double)kScanMax || D >= 40) return kWalkGaveUp;   // too wide to scan
     const long long k0 = (long long)k0d, k1 = (long long)k1d;
+#ifdef PG_WALK_STATS
+    atomicAdd(&pg_walk_stats[3][0], 1ull); atomicAdd(&pg_walk_stats[3][1], (unsigned long long)(k1 - k0 + 1)); atomicMax(&pg_walk_stats[3][2], (unsigned long long)(k1 - k0 + 1));
+#endif
     bool found = false, unknown = false;
     long long k = k0;
     if (Coop) k += threadIdx.x & 31;
@@ -445,20 +448,26 @@ __device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float n
   const double sx = (double)cA.x - (double)cB.x, sy = (double)cA.y - (double)cB.y, sz = (double)cA.z - (double)cB.z;
   const double ux = (double)vA.x - (double)vB.x, uy = (double)vA.y - (double)vB.y, uz = (double)vA.z - (double)vB.z;
   const double ss_d = sx * sx + sy * sy + sz * sz, su_d = sx * ux + sy * uy + sz * uz, uu_d = ux * ux + uy * uy + uz * uz;
-  const double t_star = uu_d > 0.0 ? -su_d / uu_d : (double)t_begin;
+  const double nsu_d = -su_d;
   const double d2_slack = 1.0e-13 * (ss_d + 2.0 * fabs(su_d) * (double)tmax + uu_d * (double)tmax * (double)tmax);
   const double dead_thr = ((double)mm_hi + (double)rs + (double)E0) * 1.00001;
-  const double dead_thr2 = dead_thr * dead_thr;
+  const double dead_c2 = dead_thr * dead_thr + d2_slack;      // D^2 > dead_c2  =>  dead
+  const double dead_c = ss_d - dead_c2;
   auto eval = [&](float t) { return ss_d2_at(cA, vA, cB, vB, t); };
   auto probe = [&](float t0, float t1, float d2a, float d2b) -> int {
     const float len = t1 - t0;
     const float mm = nA * len + nB * len;
     if (ss_dist_exceeds(d2a, rs, mm) || ss_dist_exceeds(d2b, rs, mm)) return kDead;
     if (len < kIntervalEps || !finite_ok) return kOpen;       // leaves are decided by the tests above
-    // real minimum of |s + u t|^2 over the node, in closed form: the parabola's vertex clamped into it
-    const double tc = fmin(fmax(t_star, (double)t0), (double)t1);
-    const double D2min = fma(tc, fma(uu_d, tc, 2.0 * su_d), ss_d) - d2_slack;
-    if (D2min > dead_thr2) return kDead;
+    // real minimum of |s + u t|^2 over the node, in closed form (no division: the vertex -su/uu lies
+    // left of, right of, or inside the node; inside, the minimum is ss - su^2/uu)
+    const double a0 = (double)t0 * uu_d, a1 = (double)t1 * uu_d;
+    if (nsu_d > a0 && nsu_d < a1) {
+      if (dead_c * uu_d > su_d * su_d) return kDead;
+    } else {
+      const double tc = nsu_d <= a0 ? (double)t0 : (double)t1;
+      if (fma(tc, fma(uu_d, tc, 2.0 * su_d), ss_d) > dead_c2) return kDead;
+    }
     const float Da = sqrtf(d2a), Db = sqrtf(d2b);
     const float Dmax = fmaxf(Da, Db);
     const float E = E0 + 8.0f * kU * Dmax;       // |computed - real| at any t of the node

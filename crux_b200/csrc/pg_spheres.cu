@@ -106,7 +106,7 @@ __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsign
 }
 
 constexpr int kMaxRowChanges = 8;
-constexpr int kGateList = 96;         // candidate bits of one 32-row block gated in one go
+constexpr int kGateList = 128;        // candidate bits of one 32-row block gated per pass
 
 // All visits of row i, in increasing column order.  `mask` bit s = this lane's column s*32+lane is a
 // candidate that already passed the reach filter AND the closest-approach gate for the state the
@@ -123,9 +123,14 @@ __device__ __noinline__ int row_visits(float4 *P4, float4 *V4, int i, unsigned m
     if (fresh) {
       // reach filter + closest-approach gate of this lane's remaining columns against the row body
       mask = 0;
+      const float4 ap = P4[i];
       for (int s = j0 >> 5; s < ncols_slots; s++) {
         const int c = s * 32 + lane;
-        if (c != i && c >= j0 && !pgs::pair_gate_far(P4, V4, i, c, false, dt)) mask |= 1u << s;
+        const float4 q = P4[c];
+        const float dx = ap.x - q.x, dy = ap.y - q.y, dz = ap.z - q.z;
+        const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
+        const float T = ap.w + q.w;
+        if (d2 <= T * T && c != i && c >= j0 && !pgs::pair_gate_far(P4, V4, i, c, false, dt)) mask |= 1u << s;
       }
       fresh = false;
     }
@@ -183,6 +188,7 @@ struct WarpSmem {
   float4 planes[kMaxPlanes];
   ulonglong2 RA[64];                               // filter coefficients of the 32 rows being swept, as duplicated pairs for FFMA2
   unsigned long long RB[32];
+  unsigned W0[CPT * 32];                           // the filter's bits as they came out (enumeration order of the gate)
   unsigned W[CPT * 32];                       // candidate bits: [static slot][lane], bit = row of the block
   unsigned list[kGateList];
   unsigned rest[CPT];                       // at-rest flags by actual slot, bit = lane
@@ -412,7 +418,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
       }
       unsigned *WS = S.W;                     // WS[k * 32 + lane]: the bit matrix, in shared memory from here on
 #pragma unroll
-      for (int k = 0; k < CPT; k++) WS[k * 32 + lane] = W[k];
+      for (int k = 0; k < CPT; k++) { WS[k * 32 + lane] = W[k]; S.W0[k * 32 + lane] = W[k]; }
       __syncwarp();
       // --- closest-approach gate of every surviving (row, column) bit, one pair per lane: the bits
       // are compacted into a list (k, lane, rl) and gated 32 at a time.  More than kGateList bits in
@@ -425,19 +431,22 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
       const int total = __shfl_sync(kFull, incl, 31);
-      if (dt > 1.0e-9f && total <= kGateList) {
+      if (dt > 1.0e-9f) {
         gated = true;
-        if (total > 0) {
-          unsigned *list = S.list;
-          int off = incl - cnt;
+        unsigned *list = S.list;
+        // list windows of kGateList bits: each lane knows the global index of its first bit (prefix sum)
 #pragma unroll 1
-          for (int k = 0; k < CPT; k++) {
-            for (unsigned word = WS[k * 32 + lane]; word; word &= word - 1u)
-              list[off++] = (unsigned)k | ((unsigned)lane << 8) | ((unsigned)(__ffs((int)word) - 1) << 16);
+        for (int base = 0; base < total; base += kGateList) {
+          int pos = incl - cnt - base;
+#pragma unroll 1
+          for (int k = 0; k < CPT && pos < kGateList; k++) {
+            for (unsigned word = S.W0[k * 32 + lane]; word; word &= word - 1u, pos++)
+              if (pos >= 0 && pos < kGateList) list[pos] = (unsigned)k | ((unsigned)lane << 8) | ((unsigned)(__ffs((int)word) - 1) << 16);
           }
           __syncwarp();
+          const int m = min(kGateList, total - base);
 #pragma unroll 1
-          for (int idx = lane; idx < total; idx += 32) {
+          for (int idx = lane; idx < m; idx += 32) {
             const unsigned e = list[idx];
             const int ek = e & 0xff, el = (e >> 8) & 0xff, erl = e >> 16;
             int sa = rb + ek; if (sa >= CPT) sa -= CPT;
