@@ -61,6 +61,9 @@ struct PgWorlds {
   int last_steps;
   double *d_stats;            // 8 doubles
   int *d_work_counter;        // world hand-out counter of the sphere kernel
+  unsigned *d_cost;           // sphere kernel: clocks/1024 each world took in the last full launch
+  int *d_order;               // sphere kernel: worlds sorted by that cost, dearest first (hand-out order)
+  bool cost_valid;
   int sm_count;
   bool static_pass_parallel_ok;   // recomputed on upload (general mode)
   // device staging for packed [body][3] state exchange (sphere mode)

@@ -105,6 +105,10 @@ __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsign
   unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
 }
 
+// The expanded reach test |q_r - q_c|^2 - (rho_r + rho_c)^2 < 0 is evaluated with ~10 roundings on terms of
+// magnitude <= 2 (|q_r|^2 + |q_c|^2): error <= 1.2e-6 (|q_r|^2 + |q_c|^2).  The slack kFilterSlack (|q_r|^2 + |q_c|^2) + 1e-6
+// covers it six times over, per PAIR, so that one far-away body does not blunt the filter for the others.
+constexpr float kFilterSlack = 8.0e-6f;
 constexpr int kMaxRowChanges = 8;
 constexpr int kGateList = 128;        // candidate bits of one 32-row block gated per pass
 
@@ -197,7 +201,8 @@ struct WarpSmem {
 
 template <int CPT, int WPB>
 __global__ void __launch_bounds__(WPB * 32, (CPT <= 8) ? PG_SPH_WARPS / WPB : 1)
-k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int first_world, int end_world) {
+k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int first_world, int end_world,
+               const int *order, unsigned *cost) {
   // per-warp shared memory (dynamic: a block of 16 worlds needs more than the 48 KB static limit)
   extern __shared__ __align__(16) unsigned char s_raw[];
   WarpSmem<CPT> &S = reinterpret_cast<WarpSmem<CPT> *>(s_raw)[threadIdx.x >> 5];
@@ -225,6 +230,8 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
     w = __shfl_sync(kFull, w, 0);
     if (w >= end_world) return;
   }
+  if (order) w = order[w];                 // dearest worlds first (see k_order_worlds)
+  const long long t_start = clock64();
   __syncwarp();
   const int n = valid ? v.counts[w * 3 + 1] : 0;
   const int ns = min(v.counts[w * 3 + 0], kMaxPlanes);
@@ -307,33 +314,44 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
         }
       }
     }
-    // bounding box of the world: min / max through an order-preserving float -> int map and one
-    // warp reduction each
-    int ol[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, oh[3] = {(int)0x80000000, (int)0x80000000, (int)0x80000000};
-    auto ordered = [](float f) { const int i = __float_as_int(f); return i ^ ((i >> 31) & 0x7fffffff); };
-    auto unordered = [](int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); };
+    // Centre the filter's coordinates are taken relative to.  It must sit among the bulk of the
+    // bodies whatever a few stragglers do (a sphere that tunnelled through the floor keeps falling
+    // for ever): mean of all bodies, then the mean of those within twice the mean L1 distance of it.
+    auto warp_sum = [&](float x) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+      return x;
+    };
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+#pragma unroll 1
+    for (int s = 0; s < n_blocks; s++) {
+      const int i = s * 32 + lane;
+      if (i < n) { const float4 a = P4[i]; ax += a.x; ay += a.y; az += a.z; }
+    }
+    const float inv_n = 1.0f / (float)max(n, 1);
+    const float mx = warp_sum(ax) * inv_n, my = warp_sum(ay) * inv_n, mz = warp_sum(az) * inv_n;
+    float ad = 0.0f, dmax = 0.0f;
+#pragma unroll 1
+    for (int s = 0; s < n_blocks; s++) {
+      const int i = s * 32 + lane;
+      if (i < n) { const float4 a = P4[i]; const float d = fabsf(a.x - mx) + fabsf(a.y - my) + fabsf(a.z - mz); ad += d; dmax = fmaxf(dmax, d); if (!(d == d)) dmax = 3.0e38f; }
+    }
+    const float lim = 2.0f * warp_sum(ad) * inv_n + 1.0f;
+    const bool wild = !(__uint_as_float(__reduce_max_sync(kFull, __float_as_uint(dmax))) < 1.0e15f);   // non-finite or astronomically spread: the expanded filter is not trusted
+    ax = ay = az = 0.0f;
+    float cntf = 0.0f;
 #pragma unroll 1
     for (int s = 0; s < n_blocks; s++) {
       const int i = s * 32 + lane;
       if (i < n) {
         const float4 a = P4[i];
-        const int ox = ordered(a.x), oy = ordered(a.y), oz = ordered(a.z);
-        ol[0] = min(ol[0], ox); ol[1] = min(ol[1], oy); ol[2] = min(ol[2], oz);
-        oh[0] = max(oh[0], ox); oh[1] = max(oh[1], oy); oh[2] = max(oh[2], oz);
+        if (fabsf(a.x - mx) + fabsf(a.y - my) + fabsf(a.z - mz) <= lim) { ax += a.x; ay += a.y; az += a.z; cntf += 1.0f; }
       }
     }
-    float bl[3], bh[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      bl[k] = unordered(__reduce_min_sync(kFull, ol[k]));
-      bh[k] = unordered(__reduce_max_sync(kFull, oh[k]));
-    }
-    // world centre and the magnitude the filter's rounding slack is scaled with
-    cx0 = 0.5f * (bl[0] + bh[0]); cy0 = 0.5f * (bl[1] + bh[1]); cz0 = 0.5f * (bl[2] + bh[2]);
+    cntf = warp_sum(cntf);
+    cx0 = mx; cy0 = my; cz0 = mz;
+    if (cntf >= 1.0f) { cx0 = warp_sum(ax) / cntf; cy0 = warp_sum(ay) / cntf; cz0 = warp_sum(az) / cntf; }
     if (!(fabsf(cx0) < 1.0e30f && fabsf(cy0) < 1.0e30f && fabsf(cz0) < 1.0e30f)) { cx0 = cy0 = cz0 = 0.0f; }
-    const float hx = bh[0] - cx0 + 2.0f, hy = bh[1] - cy0 + 2.0f, hz = bh[2] - cz0 + 2.0f;   // + room to move within the step
-    const float maxn2 = hx * hx + hy * hy + hz * hz;
-    const bool wild = !(maxn2 < 1.0e30f);          // non-finite or astronomically spread world: the expanded filter is not trusted
     __syncwarp();
 
     {
@@ -359,7 +377,8 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
         float fx[2 * NP], fy[2 * NP], fz[2 * NP], fr[2 * NP], fc[2 * NP];
         auto put = [&](int m, float px, float py, float pz, float rho) {
           fx[m] = px - cx0; fy[m] = py - cy0; fz[m] = pz - cz0; fr[m] = rho;
-          fc[m] = __fmaf_rn(fx[m], fx[m], __fmaf_rn(fy[m], fy[m], fz[m] * fz[m])) - rho * rho;
+          const float n2c = __fmaf_rn(fx[m], fx[m], __fmaf_rn(fy[m], fy[m], fz[m] * fz[m]));
+          fc[m] = __fmaf_rn(n2c, -kFilterSlack, n2c) - rho * rho;           // |q|^2 (1 - slack) - rho^2: the column's share of the slack
         };
 #pragma unroll
         for (int k = 0; k < CPT; k++) {
@@ -373,7 +392,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
           const float rx = a.x - cx0, ry = a.y - cy0, rz = a.z - cz0;
           const float n2 = __fmaf_rn(rx, rx, __fmaf_rn(ry, ry, rz * rz));
           const float ea = -2.0f * rx, eb = -2.0f * ry, ec = -2.0f * rz, ed = -2.0f * a.w;
-          const float ne = -(__fmaf_rn(a.w, a.w, -n2) + (8.0e-6f * (n2 + maxn2) + 1.0e-6f));
+          const float ne = -(__fmaf_rn(a.w, a.w, -n2) + (kFilterSlack * n2 + 1.0e-6f));   // the row's share of the slack
           S.RA[2 * lane] = make_ulonglong2(pack2(ea, ea), pack2(eb, eb));
           S.RA[2 * lane + 1] = make_ulonglong2(pack2(ec, ec), pack2(ed, ed));
           S.RB[lane] = pack2(ne, ne);
@@ -527,6 +546,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
       v.vel_rad[base + i] = V4[i];
     }
   }
+  if (cost && valid && lane == 0) cost[w] = (unsigned)min((clock64() - t_start) >> 10, 0x7fffffffll);
   __syncwarp();
   }   // next world
 }
@@ -640,6 +660,26 @@ int pg_launch_unpack_state(PgWorlds *w, int first, int count, int n, float *pos,
   return PG_OK;
 }
 
+// Hand-out order for the next launch: worlds sorted by what they cost in the last one, dearest first
+// (counting sort on a log-scale key, one block).  A launch ends when its slowest world ends, so the
+// slow ones must start first; and a block keeps its worlds in phase with barriers, so worlds of
+// similar cost belong in the same block.  Worlds are independent: the order never changes a result.
+__global__ void k_order_worlds(const unsigned *cost, int n_worlds, int *order) {
+  __shared__ int hist[256], cursor[256];
+  auto key = [](unsigned c) {               // 5 exponent bits + 3 mantissa bits, larger cost -> smaller key
+    if (c < 8u) return 255 - (int)c;
+    const int e = 31 - __clz(c);
+    return 255 - min(255, ((e - 2) << 3) | (int)((c >> (e - 3)) & 7u));
+  };
+  for (int k = threadIdx.x; k < 256; k += blockDim.x) hist[k] = 0;
+  __syncthreads();
+  for (int w = threadIdx.x; w < n_worlds; w += blockDim.x) atomicAdd(&hist[key(cost[w])], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) { int acc = 0; for (int k = 0; k < 256; k++) { cursor[k] = acc; acc += hist[k]; } }
+  __syncthreads();
+  for (int w = threadIdx.x; w < n_worlds; w += blockDim.x) order[atomicAdd(&cursor[key(cost[w])], 1)] = w;
+}
+
 template <int CPT, int WPB>
 static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter) {
   static bool configured = false;
@@ -654,8 +694,18 @@ static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int cou
     configured = true;
   }
   const int blocks = std::min((count + WPB - 1) / WPB, resident_blocks);
+  // cost-ordered hand-out only for launches over the whole batch (the chunked host pipeline keeps index order)
+  const bool whole = first == 0 && count == w->v.n_worlds && count > resident_blocks * WPB;
+  const int *order = nullptr;
+  if (whole && w->cost_valid) {
+    k_order_worlds<<<1, 1024, 0, stream>>>(w->d_cost, count, w->d_order);
+    w->launches++;
+    order = w->d_order;
+  }
   cudaMemsetAsync(counter, 0, sizeof(int), stream);
-  k_step_spheres<CPT, WPB><<<blocks, WPB * 32, smem_bytes, stream>>>(w->v, dt, n_steps, counter, first, first + count);
+  k_step_spheres<CPT, WPB><<<blocks, WPB * 32, smem_bytes, stream>>>(w->v, dt, n_steps, counter, first, first + count, order,
+                                                                    whole ? w->d_cost : nullptr);
+  w->cost_valid = whole;
   return PG_OK;
 }
 

@@ -170,6 +170,9 @@ PgWorlds *pg_worlds_create(int n_worlds, int max_static, int max_dynamic, int ma
     PG_CUDA_NULL(cudaMalloc(&w->v.events, sizeof(PgEvent) * (size_t)n_worlds * max_events_per_world));
   PG_CUDA_NULL(cudaMalloc(&w->d_stats, 8 * sizeof(double)));
   PG_CUDA_NULL(cudaMalloc(&w->d_work_counter, sizeof(int)));
+  PG_CUDA_NULL(cudaMalloc(&w->d_cost, sizeof(unsigned) * (size_t)n_worlds));
+  PG_CUDA_NULL(cudaMalloc(&w->d_order, sizeof(int) * (size_t)n_worlds));
+  w->cost_valid = false;
   w->h_counts = (int *)calloc((size_t)n_worlds * 3, sizeof(int));
   return w;
 }
@@ -187,6 +190,8 @@ void pg_worlds_destroy(PgWorlds *w) {
   if (w->v.planes) cudaFree(w->v.planes);
   if (w->d_stats) cudaFree(w->d_stats);
   if (w->d_work_counter) cudaFree(w->d_work_counter);
+  if (w->d_cost) cudaFree(w->d_cost);
+  if (w->d_order) cudaFree(w->d_order);
   if (w->pipe_ready) {
     for (int k = 0; k < 3; k++) { cudaStreamDestroy(w->pipe_stream[k]); cudaEventDestroy(w->pipe_done[k]); }
     cudaFree(w->d_pipe_counters);
