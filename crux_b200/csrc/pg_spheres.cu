@@ -264,7 +264,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
   }
   __syncwarp();
 
-  float cx0 = 0.0f, cy0 = 0.0f, cz0 = 0.0f;
+  float cx0 = 0.0f, cy0 = 0.0f, cz0 = 0.0f, trim = 3.0e38f;   // filter centre and trimming radius, carried from step to step
 
   for (int step = 0; step < n_steps; step++) {
     if constexpr (PG_SPH_SYNC >= 1) { if (step % PG_SPH_SYNC == 0) __syncthreads(); }
@@ -316,41 +316,36 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
     }
     // Centre the filter's coordinates are taken relative to.  It must sit among the bulk of the
     // bodies whatever a few stragglers do (a sphere that tunnelled through the floor keeps falling
-    // for ever): mean of all bodies, then the mean of those within twice the mean L1 distance of it.
+    // for ever): the mean of the bodies within `trim` (twice the mean L1 distance, as of the
+    // previous step) of the previous centre.  One pass over the world per step.
     auto warp_sum = [&](float x) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
       return x;
     };
-    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+    bool wild = false;
 #pragma unroll 1
-    for (int s = 0; s < n_blocks; s++) {
-      const int i = s * 32 + lane;
-      if (i < n) { const float4 a = P4[i]; ax += a.x; ay += a.y; az += a.z; }
-    }
-    const float inv_n = 1.0f / (float)max(n, 1);
-    const float mx = warp_sum(ax) * inv_n, my = warp_sum(ay) * inv_n, mz = warp_sum(az) * inv_n;
-    float ad = 0.0f, dmax = 0.0f;
-#pragma unroll 1
-    for (int s = 0; s < n_blocks; s++) {
-      const int i = s * 32 + lane;
-      if (i < n) { const float4 a = P4[i]; const float d = fabsf(a.x - mx) + fabsf(a.y - my) + fabsf(a.z - mz); ad += d; dmax = fmaxf(dmax, d); if (!(d == d)) dmax = 3.0e38f; }
-    }
-    const float lim = 2.0f * warp_sum(ad) * inv_n + 1.0f;
-    const bool wild = !(__uint_as_float(__reduce_max_sync(kFull, __float_as_uint(dmax))) < 1.0e15f);   // non-finite or astronomically spread: the expanded filter is not trusted
-    ax = ay = az = 0.0f;
-    float cntf = 0.0f;
+    for (int pass = (trim > 1.0e38f) ? 0 : 1; pass < 2; pass++) {      // a fresh start takes two passes
+    float ax = 0.0f, ay = 0.0f, az = 0.0f, cntf = 0.0f, ad = 0.0f, dmax = 0.0f;
 #pragma unroll 1
     for (int s = 0; s < n_blocks; s++) {
       const int i = s * 32 + lane;
       if (i < n) {
         const float4 a = P4[i];
-        if (fabsf(a.x - mx) + fabsf(a.y - my) + fabsf(a.z - mz) <= lim) { ax += a.x; ay += a.y; az += a.z; cntf += 1.0f; }
+        const float d = fabsf(a.x - cx0) + fabsf(a.y - cy0) + fabsf(a.z - cz0);
+        dmax = fmaxf(dmax, d); if (!(d == d)) dmax = 3.0e38f;
+        if (d <= trim) { ax += a.x; ay += a.y; az += a.z; cntf += 1.0f; ad += d; }
       }
     }
+    wild = !(__uint_as_float(__reduce_max_sync(kFull, __float_as_uint(dmax))) < 1.0e15f);   // non-finite or astronomically spread: the expanded filter is not trusted
     cntf = warp_sum(cntf);
-    cx0 = mx; cy0 = my; cz0 = mz;
-    if (cntf >= 1.0f) { cx0 = warp_sum(ax) / cntf; cy0 = warp_sum(ay) / cntf; cz0 = warp_sum(az) / cntf; }
+    if (cntf >= 1.0f) {
+      cx0 = warp_sum(ax) / cntf; cy0 = warp_sum(ay) / cntf; cz0 = warp_sum(az) / cntf;
+      trim = 2.0f * warp_sum(ad) / cntf + 2.0f;              // + room for the shift of the centre itself
+    } else {
+      trim = 3.0e38f;                                        // lost the bulk: start over from the plain mean
+    }
+    }
     if (!(fabsf(cx0) < 1.0e30f && fabsf(cy0) < 1.0e30f && fabsf(cz0) < 1.0e30f)) { cx0 = cy0 = cz0 = 0.0f; }
     __syncwarp();
 
