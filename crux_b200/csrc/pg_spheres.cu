@@ -32,12 +32,9 @@ namespace {
 using pgm::V3;
 using pgm::v3;
 
-#ifndef PG_SPH_WPB
-#define PG_SPH_WPB 8      // warps (= worlds) per block for worlds of up to 256 spheres: two blocks per SM
-#endif
 #ifndef PG_SPH_WARPS
-#define PG_SPH_WARPS 16   // resident warps per SM the register budget is sized for (128 registers per thread)
-#endif
+#define PG_SPH_WARPS 16   // most warps (= worlds) per block, one block per SM (128 registers per thread); the launcher
+#endif                    // picks the actual number per launch so that the batch fills whole waves of blocks
 #ifndef PG_SPH_SYNC
 #define PG_SPH_SYNC 1     // P > 0: a block barrier every P steps keeps the block's warps in phase, so that an instruction
 #endif                    //    line fetched once serves all of them (the kernel is instruction-fetch bound); 0: none
@@ -199,8 +196,8 @@ struct WarpSmem {
   int chg[kMaxRowChanges];
 };
 
-template <int CPT, int WPB>
-__global__ void __launch_bounds__(WPB * 32, (CPT <= 8) ? PG_SPH_WARPS / WPB : 1)
+template <int CPT, int MAXW>
+__global__ void __launch_bounds__(MAXW * 32, 1)
 k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int first_world, int end_world,
                const int *order, unsigned *cost) {
   // per-warp shared memory (dynamic: a block of 16 worlds needs more than the 48 KB static limit)
@@ -216,10 +213,10 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
   int w = 0;
   bool valid = true;
   if constexpr (PG_SPH_SYNC > 0) {
-    // the block takes WPB worlds at a time and its warps move through the step in phase (block
+    // the block takes one world per warp at a time and its warps move through the step in phase (block
     // barriers below), so that an instruction line fetched once serves every warp of the block
     __syncthreads();
-    if (threadIdx.x == 0) s_base = first_world + atomicAdd(work_counter, WPB);
+    if (threadIdx.x == 0) s_base = first_world + atomicAdd(work_counter, (int)(blockDim.x >> 5));
     __syncthreads();
     if (s_base >= end_world) return;
     w = s_base + wib;
@@ -675,22 +672,24 @@ __global__ void k_order_worlds(const unsigned *cost, int n_worlds, int *order) {
   for (int w = threadIdx.x; w < n_worlds; w += blockDim.x) order[atomicAdd(&cursor[key(cost[w])], 1)] = w;
 }
 
-template <int CPT, int WPB>
+template <int CPT, int MAXW>
 static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter) {
   static bool configured = false;
-  static int resident_blocks = 0;
-  constexpr size_t smem_bytes = sizeof(WarpSmem<CPT>) * WPB;
+  constexpr size_t warp_bytes = sizeof(WarpSmem<CPT>);
   if (!configured) {
-    cudaFuncSetAttribute(k_step_spheres<CPT, WPB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(k_step_spheres<CPT, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    int per_sm = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_spheres<CPT, WPB>, WPB * 32, smem_bytes);
-    resident_blocks = std::max(1, per_sm) * w->sm_count;
+    cudaFuncSetAttribute(k_step_spheres<CPT, MAXW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_step_spheres<CPT, MAXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(warp_bytes * MAXW));
     configured = true;
   }
-  const int blocks = std::min((count + WPB - 1) / WPB, resident_blocks);
+  // One block per SM.  The fewest waves of (SMs x MAXW) worlds that hold the batch, then the fewest
+  // warps per block that still do it in that many waves: 4096 worlds on 148 SMs run as 2 waves of
+  // 148 x 14 instead of 1.73 waves of 148 x 16.
+  const int sms = w->sm_count;
+  const int waves = (count + sms * MAXW - 1) / (sms * MAXW);
+  const int wpb = std::max(1, std::min(MAXW, (count + waves * sms - 1) / (waves * sms)));
+  const int blocks = std::min((count + wpb - 1) / wpb, sms);
   // cost-ordered hand-out only for launches over the whole batch (the chunked host pipeline keeps index order)
-  const bool whole = first == 0 && count == w->v.n_worlds && count > resident_blocks * WPB;
+  const bool whole = first == 0 && count == w->v.n_worlds && count > sms * wpb;
   const int *order = nullptr;
   if (whole && w->cost_valid) {
     k_order_worlds<<<1, 1024, 0, stream>>>(w->d_cost, count, w->d_order);
@@ -698,7 +697,7 @@ static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int cou
     order = w->d_order;
   }
   cudaMemsetAsync(counter, 0, sizeof(int), stream);
-  k_step_spheres<CPT, WPB><<<blocks, WPB * 32, smem_bytes, stream>>>(w->v, dt, n_steps, counter, first, first + count, order,
+  k_step_spheres<CPT, MAXW><<<blocks, wpb * 32, warp_bytes * wpb, stream>>>(w->v, dt, n_steps, counter, first, first + count, order,
                                                                     whole ? w->d_cost : nullptr);
   w->cost_valid = whole;
   return PG_OK;
@@ -708,10 +707,10 @@ static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int cou
 int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter) {
   const int cap = w->v.cap[1];
   if (w->v.cap[0] > kMaxPlanes) { pg_set_error("sphere mode supports at most %d static planes", kMaxPlanes); return PG_ERR_CAPACITY; }
-  if (cap <= 32) launch_spheres<1, PG_SPH_WPB>(w, dt, n_steps, first, count, stream, counter);
-  else if (cap <= 64) launch_spheres<2, PG_SPH_WPB>(w, dt, n_steps, first, count, stream, counter);
-  else if (cap <= 128) launch_spheres<4, PG_SPH_WPB>(w, dt, n_steps, first, count, stream, counter);
-  else if (cap <= 256) launch_spheres<8, PG_SPH_WPB>(w, dt, n_steps, first, count, stream, counter);
+  if (cap <= 32) launch_spheres<1, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter);
+  else if (cap <= 64) launch_spheres<2, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter);
+  else if (cap <= 128) launch_spheres<4, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter);
+  else if (cap <= 256) launch_spheres<8, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter);
   else if (cap <= 512) launch_spheres<16, 8>(w, dt, n_steps, first, count, stream, counter);
   else { pg_set_error("sphere mode supports at most 512 spheres per world (got capacity %d)", cap); return PG_ERR_CAPACITY; }
   PG_CUDA(cudaGetLastError());
