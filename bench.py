@@ -465,8 +465,8 @@ def run_gpu_arm(args, cfg):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 1000 for c3, 24 for the large-world workloads)")
+    ap.add_argument("--warmup", type=int, default=None, help="untimed steps first (default: 20 for c3, 4 for the large-world workloads)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--steps-per-launch", type=int, default=10)
@@ -474,6 +474,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
+    if args.steps is None:
+        args.steps = 24 if cfg.get("large") else 1000
+    if args.warmup is None:
+        args.warmup = 4 if cfg.get("large") else 20
     if args.impl == "reference":
         run_reference_arm(args, cfg)
     elif cfg.get("large"):

@@ -798,6 +798,28 @@ static int lw_read_flags(PgLarge *w, Flags *f) {
   return PG_OK;
 }
 
+// The candidate list outgrew its buffer (dense piles: every sphere touches a dozen neighbours).
+// Reallocate for `needed` pairs, keeping the first `keep` entries, and clear the overflow mark.
+static int lw_grow_pairs(PgLarge *w, unsigned long long needed, unsigned long long keep) {
+  LargeView &v = w->v;
+  const long long cap = (long long)(needed + needed / 4 + 65536);
+  int2 *bigger = nullptr;
+  if (cudaMalloc(&bigger, sizeof(int2) * (size_t)cap) != cudaSuccess) {
+    cudaGetLastError();
+    pg_set_error("large world: cannot grow the candidate pair buffer to %lld pairs", cap);
+    return PG_ERR_CAPACITY;
+  }
+  if (keep) PG_CUDA(cudaMemcpyAsync(bigger, v.pairs, sizeof(int2) * (size_t)keep, cudaMemcpyDeviceToDevice, w->stream));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  cudaFree(v.pairs);
+  v.pairs = bigger;
+  v.pairs_cap = cap;
+  PG_CUDA(cudaMemsetAsync(&v.flags->overflow_pairs, 0, sizeof(int), w->stream));
+  PG_CUDA(cudaMemcpyAsync(&v.flags->n_pairs, &keep, sizeof(keep), cudaMemcpyHostToDevice, w->stream));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  return PG_OK;
+}
+
 static int lw_step_once(PgLarge *w, float dt_in) {
   LargeView &v = w->v;
   float dt = dt_in;
@@ -816,7 +838,16 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   rc = lw_read_flags(w, &f);            // pair count: sizes the eval grid, detects overflow
   if (rc) return rc;
   lw_accumulate(w, K_PASS3); lw_accumulate(w, K_SCAN); lw_accumulate(w, K_SCATTER); lw_accumulate(w, K_PAIRS);
-  if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
+  if (f.overflow_pairs) {
+    // k_pairs is a pure function of the grid: grow the buffer and run it again
+    rc = lw_grow_pairs(w, f.n_pairs, 0);
+    if (rc) return rc;
+    LW_LAUNCH(w, K_PAIRS, k_pairs, lw_grid(w, v.n, 128), 128, v);
+    rc = lw_read_flags(w, &f);
+    if (rc) return rc;
+    lw_accumulate(w, K_PAIRS);
+    if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
+  }
   if (f.unsafe) { pg_set_error("large world: non-finite body state"); return PG_ERR_ARG; }
   w->last_candidates = (long long)f.n_pairs;
   const bool debug = getenv("PG_LARGE_DEBUG") != nullptr;
@@ -849,13 +880,24 @@ static int lw_step_once(PgLarge *w, float dt_in) {
     if (f.grew) {
       // candidates the grown envelopes add; their bodies are marked dirty so the next iteration
       // re-evaluates them on top of the current timelines (warm start)
-      LW_LAUNCH(w, K_BOUNDS, k_requery, lw_grid(w, std::max((int)f.n_touched, 1), 128), 128, v, src);
-      k_requery_done<<<lw_grid(w, std::max((int)f.n_touched, 1), 256), 256, 0, w->stream>>>(v);
-      w->launches++;
+      const unsigned long long pairs_before = std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
+      const int touched_now = std::max((int)f.n_touched, 1);
+      LW_LAUNCH(w, K_BOUNDS, k_requery, lw_grid(w, touched_now, 128), 128, v, src);
       rc = lw_read_flags(w, &f);
       if (rc) return rc;
       lw_accumulate(w, K_BOUNDS);
-      if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
+      if (f.overflow_pairs) {
+        // k_requery only appends: keep the list as it was, make room, and let it append again
+        rc = lw_grow_pairs(w, f.n_pairs, pairs_before);
+        if (rc) return rc;
+        LW_LAUNCH(w, K_BOUNDS, k_requery, lw_grid(w, touched_now, 128), 128, v, src);
+        rc = lw_read_flags(w, &f);
+        if (rc) return rc;
+        lw_accumulate(w, K_BOUNDS);
+        if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
+      }
+      k_requery_done<<<lw_grid(w, touched_now, 256), 256, 0, w->stream>>>(v);
+      w->launches++;
       if (f.unsafe) { w->last_proven = 0; if (debug) fprintf(stderr, "  [pg_large] envelope outgrew the grid: result not proven\n"); }
       w->last_candidates = (long long)f.n_pairs;
       requeries++;

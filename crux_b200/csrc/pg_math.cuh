@@ -480,8 +480,9 @@ __device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float n
   // kWalkBudget nodes the walk is abandoned for a LEAF SCAN: only leaves inside the window where
   // the real distance is below the dead threshold can pass their own test; each of them is reached
   // from the root by its own halving sequence, testing every ancestor on the way exactly as the
-  // recursion would.  The candidates are independent, so a warp scans 32 at a time.
-  for (int budget = kWalkBudget;; budget = 0x7fffffff) {
+  // recursion would.  The candidates are independent, so a warp scans 32 at a time (Coop callers
+  // only: a single thread scanning a window of hundreds of leaves is slower than its walk).
+  for (int budget = Coop ? kWalkBudget : 0x7fffffff;; budget = 0x7fffffff) {     // one thread alone is better off walking
     const int r = interval_walk_guided<float>(t_begin, t_end, t_pref, eval, probe, budget PG_DBG_ARG);
     if (r != kWalkGaveUp) return r == kWalkTrue;
     const int q = ss_leaf_scan<Coop>(cA, vA, nA, cB, vB, nB, rs, t_begin, t_end, leaf);
@@ -506,8 +507,8 @@ __device__ __forceinline__ float sp_dist(V3 c, V3 n, float d, float r) { return 
 // and is EXACTLY constant in t when every product v_k n_k vanishes (a body at rest that was
 // pushed sideways along an axis-aligned plane: the case that otherwise costs 2^depth nodes every
 // step, for ever, because a resting body is never integrated).
-__device__ inline bool sp_interval(V3 c, V3 v, float nv, V3 n, float d, float r, float t_begin, float t_end,
-                                   LeafLen leaf = default_leaf_len()) {
+template <bool Hard>
+__device__ __forceinline__ int sp_interval_impl(V3 c, V3 v, float nv, V3 n, float d, float r, float t_begin, float t_end, LeafLen leaf) {
   const float tmax = fmaxf(fabsf(t_begin), fabsf(t_end));
   const float c1 = fabsf(c.x) + fabsf(c.y) + fabsf(c.z), v1 = fabsf(v.x) + fabsf(v.y) + fabsf(v.z);
   const bool constant_s = (v.x == 0.0f || n.x == 0.0f) && (v.y == 0.0f || n.y == 0.0f) && (v.z == 0.0f || n.z == 0.0f);
@@ -527,9 +528,17 @@ __device__ inline bool sp_interval(V3 c, V3 v, float nv, V3 n, float d, float r,
   const float s_begin = __fmaf_rn(c.x, n.x, __fmaf_rn(c.y, n.y, c.z * n.z)) - d;
   const float ndv = __fmaf_rn(v.x, n.x, __fmaf_rn(v.y, n.y, v.z * n.z));
   const float t_pref = ndv != 0.0f ? fminf(fmaxf(-s_begin / ndv, t_begin), t_end) : t_begin;
-  return interval_walk_guided<float, 1>(t_begin, t_end, t_pref,
-    [&](float t) { return sp_signed(muladds(v, t, c), n, d); },
-    [&](float t0, float t1, float sa, float sb) -> int {
+#ifdef PG_WALK_STATS
+  unsigned long long dbg_sp = 0;
+  struct DumpSp { const V3 &c, &v, &n; float d, r, t1, Es; unsigned long long &k;
+    __device__ ~DumpSp() { if (k > 1000) printf("SP %llu nodes c %.9g %.9g %.9g v %.9g %.9g %.9g n %.9g %.9g %.9g d %.9g r %.9g dt %.9g Es %.9g\n",
+      k, c.x, c.y, c.z, v.x, v.y, v.z, n.x, n.y, n.z, d, r, t1, Es); } } dump_sp{c, v, n, d, r, t_end, Es, dbg_sp};
+#define PG_DBG_SP , 0x7fffffff, &dbg_sp
+#else
+#define PG_DBG_SP
+#endif
+  auto eval = [&](float t) { return sp_signed(muladds(v, t, c), n, d); };
+  auto probe = [&](float t0, float t1, float sa, float sb) -> int {
       const float len = t1 - t0;
       const float mm = nv * len + 0.0f * len;      // the plane's |v| is 0 (world.c:51): 0*len, then the sum
       if (sp_dist_from_s(sa, r) > mm || sp_dist_from_s(sb, r) > mm) return kDead;
@@ -541,7 +550,37 @@ __device__ inline bool sp_interval(V3 c, V3 v, float nv, V3 n, float d, float r,
       if ((amin - r) * 0.999999f > mm_hi) return kDead;
       if (fmaxf(amax - r, 0.0f) * 1.000001f <= mm_lo) return kSure;
       return kOpen;
-    });
+    };
+  if (!Hard) return interval_walk_guided<float, 1>(t_begin, t_end, t_pref, eval, probe, kWalkBudget);
+  // Monotone signed distance (see bb_interval): the products fl(c_k(t) n_k) are monotone in t; if the
+  // ones that move all move the same way, so does the computed s(t), exactly, and while it keeps its
+  // sign so does the computed distance.  Its extremes over the interval are then the end values.
+  if (finite_ok) {
+    bool up = true, down = true;
+    if (v.x != 0.0f && n.x != 0.0f) { const bool inc = (v.x > 0.0f) == (n.x > 0.0f); up = up && inc; down = down && !inc; }
+    if (v.y != 0.0f && n.y != 0.0f) { const bool inc = (v.y > 0.0f) == (n.y > 0.0f); up = up && inc; down = down && !inc; }
+    if (v.z != 0.0f && n.z != 0.0f) { const bool inc = (v.z > 0.0f) == (n.z > 0.0f); up = up && inc; down = down && !inc; }
+    if (up || down) {
+      const float sb = sp_signed(muladds(v, t_begin, c), n, d), se = sp_signed(muladds(v, t_end, c), n, d);
+      if ((sb > 0.0f && se > 0.0f) || (sb < 0.0f && se < 0.0f)) {
+        const float da = sp_dist_from_s(sb, r), db = sp_dist_from_s(se, r);
+        if (fminf(da, db) > nv * leaf.hi + 0.0f * leaf.hi) return kWalkFalse;
+        if (fmaxf(da, db) <= nv * leaf.lo + 0.0f * leaf.lo) return kWalkTrue;
+      }
+    }
+  }
+  return interval_walk_guided<float, 1>(t_begin, t_end, t_pref, eval, probe PG_DBG_SP);
+}
+// A walk still going after kWalkBudget nodes is one of the rare band cases: out of line, first the
+// exact monotone decision, then the plain walk to the end.
+static __device__ __noinline__ bool sp_interval_hard(V3 c, V3 v, float nv, V3 n, float d, float r, float t_begin, float t_end, LeafLen leaf) {
+  return sp_interval_impl<true>(c, v, nv, n, d, r, t_begin, t_end, leaf) == kWalkTrue;
+}
+__device__ inline bool sp_interval(V3 c, V3 v, float nv, V3 n, float d, float r, float t_begin, float t_end,
+                                   LeafLen leaf = default_leaf_len()) {
+  const int r0 = sp_interval_impl<false>(c, v, nv, n, d, r, t_begin, t_end, leaf);
+  if (r0 != kWalkGaveUp) return r0 == kWalkTrue;
+  return sp_interval_hard(c, v, nv, n, d, r, t_begin, t_end, leaf);
 }
 
 struct Contact { float t; bool hit; };
@@ -654,8 +693,8 @@ __device__ __forceinline__ V3 bb_centre(V3 p0, V3 v, float t) {
 // interval_collision(box, sphere): mm = |v_box| len + |v_sphere| len with |v_box| = 0.  Same guided,
 // enclosure-pruned walk as ss_interval: the distance of a moving point to a convex set is convex in
 // t and |v|-Lipschitz.
-__device__ inline bool bb_interval(V3 p0, V3 v, float nv, float r, const BoxS &bx, float t_begin, float t_end,
-                                   LeafLen leaf = default_leaf_len()) {
+template <bool Hard>
+__device__ __forceinline__ int bb_interval_impl(V3 p0, V3 v, float nv, float r, const BoxS &bx, float t_begin, float t_end, LeafLen leaf) {
   const float tmax = fmaxf(fabsf(t_begin), fabsf(t_end));
   const float c1 = fabsf(p0.x) + fabsf(p0.y) + fabsf(p0.z);
   const float b1 = fabsf(bx.c.x) + fabsf(bx.c.y) + fabsf(bx.c.z) + fabsf(bx.e.x) + fabsf(bx.e.y) + fabsf(bx.e.z);
@@ -670,9 +709,17 @@ __device__ inline bool bb_interval(V3 p0, V3 v, float nv, float r, const BoxS &b
   const float vv = __fmaf_rn(v.x, v.x, __fmaf_rn(v.y, v.y, v.z * v.z));
   const float sv = __fmaf_rn(s0.x, v.x, __fmaf_rn(s0.y, v.y, s0.z * v.z));
   const float t_pref = vv > 0.0f ? fminf(fmaxf(-sv / vv, t_begin), t_end) : t_begin;
-  return interval_walk_guided<float, 2>(t_begin, t_end, t_pref,
-    [&](float t) { return bb_d2(bb_centre(p0, v, t), bx); },
-    [&](float t0, float t1, float d2a, float d2b) -> int {
+#ifdef PG_WALK_STATS
+  unsigned long long dbg_bb = 0;
+  struct DumpBb { const V3 &p, &v; const BoxS &b; float r, t1; unsigned long long &k;
+    __device__ ~DumpBb() { if (k > 1000) printf("BB %llu nodes p %.9g %.9g %.9g v %.9g %.9g %.9g bc %.9g %.9g %.9g be %.9g %.9g %.9g r %.9g dt %.9g\n",
+      k, p.x, p.y, p.z, v.x, v.y, v.z, b.c.x, b.c.y, b.c.z, b.e.x, b.e.y, b.e.z, r, t1); } } dump_bb{p0, v, bx, r, t_end, dbg_bb};
+#define PG_DBG_BB , 0x7fffffff, &dbg_bb
+#else
+#define PG_DBG_BB
+#endif
+  auto eval = [&](float t) { return bb_d2(bb_centre(p0, v, t), bx); };
+  auto probe = [&](float t0, float t1, float d2a, float d2b) -> int {
       const float len = t1 - t0;
       const float mm = 0.0f * len + nv * len;
       if (ss_dist_exceeds(d2a, r, mm) || ss_dist_exceeds(d2b, r, mm)) return kDead;   // same tail as sphere-sphere: d2 < r^2 ? 0 : sqrt(d2) - r
@@ -685,7 +732,48 @@ __device__ inline bool bb_interval(V3 p0, V3 v, float nv, float r, const BoxS &b
       const float upper = fmaxf((Dmax + 2.0f * E) * 1.0000001f - r, 0.0f) * 1.000001f;
       if (upper <= mm_lo) return kSure;
       return kOpen;
-    });
+    };
+  if (!Hard) return interval_walk_guided<float, 2>(t_begin, t_end, t_pref, eval, probe, kWalkBudget);
+  // Monotone distance.  Each computed coordinate fl(p + fl(v t)) is monotone in t, and an axis'
+  // contribution to the squared point-box distance -- (lo-p)^2 below the extent, 0 inside, (p-hi)^2
+  // above -- is monotone in p on either side, roundings included.  Unless some axis crosses the
+  // whole extent, every contribution therefore runs monotonically from its value at t_begin to its
+  // value at t_end; if they all run the same way, so does the computed distance, EXACTLY, and its
+  // extremes over every float t of the interval are the two end values.  Then
+  //   smallest > mm(longest leaf)  -> no leaf can pass            -> false
+  //   largest <= mm(shortest leaf) -> every node passes           -> true
+  // with no rounding allowance at all.  This settles the sphere that rolls along a slab with a
+  // vertical velocity of 1e-4: its height moves by less than an ulp per step, the distance sits a
+  // few 1e-6 from the leaf reach, and the enclosures (ulp(72) = 7.6e-6) cannot tell.
+  if (finite_ok) {
+    const V3 pb = bb_centre(p0, v, t_begin), pe = bb_centre(p0, v, t_end);
+    bool falling = true, rising = true;               // all contributions non-increasing / non-decreasing in t
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float lo = get(bx.c, i) - get(bx.e, i), hi = get(bx.c, i) + get(bx.e, i);
+      const float a = get(pb, i), b = get(pe, i);
+      const float fa = a < lo ? (lo - a) * (lo - a) : (a > hi ? (a - hi) * (a - hi) : 0.0f);
+      const float fb = b < lo ? (lo - b) * (lo - b) : (b > hi ? (b - hi) * (b - hi) : 0.0f);
+      const bool crosses = (a < lo && b > hi) || (a > hi && b < lo);
+      falling = falling && !crosses && fa >= fb;
+      rising = rising && !crosses && fa <= fb;
+    }
+    if (falling || rising) {
+      const float da = ss_dist_from_d2(bb_d2(pb, bx), r), db = ss_dist_from_d2(bb_d2(pe, bx), r);
+      if (fminf(da, db) > 0.0f * leaf.hi + nv * leaf.hi) return kWalkFalse;
+      if (fmaxf(da, db) <= 0.0f * leaf.lo + nv * leaf.lo) return kWalkTrue;
+    }
+  }
+  return interval_walk_guided<float, 2>(t_begin, t_end, t_pref, eval, probe PG_DBG_BB);
+}
+static __device__ __noinline__ bool bb_interval_hard(V3 p0, V3 v, float nv, float r, const BoxS &bx, float t_begin, float t_end, LeafLen leaf) {
+  return bb_interval_impl<true>(p0, v, nv, r, bx, t_begin, t_end, leaf) == kWalkTrue;
+}
+__device__ inline bool bb_interval(V3 p0, V3 v, float nv, float r, const BoxS &bx, float t_begin, float t_end,
+                                   LeafLen leaf = default_leaf_len()) {
+  const int r0 = bb_interval_impl<false>(p0, v, nv, r, bx, t_begin, t_end, leaf);
+  if (r0 != kWalkGaveUp) return r0 == kWalkTrue;
+  return bb_interval_hard(p0, v, nv, r, bx, t_begin, t_end, leaf);
 }
 // narrow_phase_AABB_sphere, narrow_phase.c:143-196 + ray_intersect_AABB :702-739 (static box: rel_v = v - 0)
 __device__ inline Contact bb_narrow(V3 p0, V3 v, float r, const BoxS &bx, float dt) {
