@@ -501,6 +501,13 @@ __device__ __forceinline__ float sp_dist_from_s(float s, float r) {
   return glm_max(dist, 0);
 }
 __device__ __forceinline__ float sp_dist(V3 c, V3 n, float d, float r) { return sp_dist_from_s(sp_signed(c, n, d), r); }
+// End points of the leaf at the very end (toward_end) or the very beginning of the halving tree of
+// [t_begin, t_end]: the same (t0+t1)*0.5f sequence the recursion performs along that edge.
+__device__ __forceinline__ void extreme_leaf(float t_begin, float t_end, bool toward_end, float &a, float &b) {
+  a = t_begin; b = t_end;
+  for (int k = 0; k < 64 && b - a >= kIntervalEps; k++) { const float m = (a + b) * 0.5f; if (toward_end) a = m; else b = m; }
+}
+
 // Same enclosure idea as ss_interval.  The real signed distance s(t) = n.(c + v t) - d is linear in
 // t, the computed one differs from it by at most
 //   Es = 1.5 u (sum_k |n_k| (4|c_k| + 4|v_k| t_max) + |s|_max)   (|n_k| <= 1; rigorous bound has factor 1.0)
@@ -552,6 +559,7 @@ __device__ __forceinline__ int sp_interval_impl(V3 c, V3 v, float nv, V3 n, floa
       return kOpen;
     };
   if (!Hard) return interval_walk_guided<float, 1>(t_begin, t_end, t_pref, eval, probe, kWalkBudget);
+  float t_pref_hard = t_pref;
   // Monotone signed distance (see bb_interval): the products fl(c_k(t) n_k) are monotone in t; if the
   // ones that move all move the same way, so does the computed s(t), exactly, and while it keeps its
   // sign so does the computed distance.  Its extremes over the interval are then the end values.
@@ -566,10 +574,16 @@ __device__ __forceinline__ int sp_interval_impl(V3 c, V3 v, float nv, V3 n, floa
         const float da = sp_dist_from_s(sb, r), db = sp_dist_from_s(se, r);
         if (fminf(da, db) > nv * leaf.hi + 0.0f * leaf.hi) return kWalkFalse;
         if (fmaxf(da, db) <= nv * leaf.lo + 0.0f * leaf.lo) return kWalkTrue;
+        const bool near_end = db <= da;                    // see bb_interval
+        float la, lb;
+        extreme_leaf(t_begin, t_end, near_end, la, lb);
+        const float far_d = sp_dist_from_s(eval(near_end ? la : lb), r);
+        if (far_d > nv * leaf.hi + 0.0f * leaf.hi) return kWalkFalse;
+        t_pref_hard = near_end ? t_end : t_begin;
       }
     }
   }
-  return interval_walk_guided<float, 1>(t_begin, t_end, t_pref, eval, probe PG_DBG_SP);
+  return interval_walk_guided<float, 1>(t_begin, t_end, t_pref_hard, eval, probe PG_DBG_SP);
 }
 // A walk still going after kWalkBudget nodes is one of the rare band cases: out of line, first the
 // exact monotone decision, then the plain walk to the end.
@@ -734,6 +748,7 @@ __device__ __forceinline__ int bb_interval_impl(V3 p0, V3 v, float nv, float r, 
       return kOpen;
     };
   if (!Hard) return interval_walk_guided<float, 2>(t_begin, t_end, t_pref, eval, probe, kWalkBudget);
+  float t_pref_hard = t_pref;
   // Monotone distance.  Each computed coordinate fl(p + fl(v t)) is monotone in t, and an axis'
   // contribution to the squared point-box distance -- (lo-p)^2 below the extent, 0 inside, (p-hi)^2
   // above -- is monotone in p on either side, roundings included.  Unless some axis crosses the
@@ -762,9 +777,17 @@ __device__ __forceinline__ int bb_interval_impl(V3 p0, V3 v, float nv, float r, 
       const float da = ss_dist_from_d2(bb_d2(pb, bx), r), db = ss_dist_from_d2(bb_d2(pe, bx), r);
       if (fminf(da, db) > 0.0f * leaf.hi + nv * leaf.hi) return kWalkFalse;
       if (fmaxf(da, db) <= 0.0f * leaf.lo + nv * leaf.lo) return kWalkTrue;
+      // Of all leaves the one at the near end has the smallest distances; a leaf passes iff the
+      // larger of its two end values is within mm(its length) <= mm(longest leaf).
+      const bool near_end = db <= da;
+      float la, lb;
+      extreme_leaf(t_begin, t_end, near_end, la, lb);
+      const float far_d = ss_dist_from_d2(eval(near_end ? la : lb), r);
+      if (far_d > 0.0f * leaf.hi + nv * leaf.hi) return kWalkFalse;
+      t_pref_hard = near_end ? t_end : t_begin;            // and if a leaf passes, it is found there
     }
   }
-  return interval_walk_guided<float, 2>(t_begin, t_end, t_pref, eval, probe PG_DBG_BB);
+  return interval_walk_guided<float, 2>(t_begin, t_end, t_pref_hard, eval, probe PG_DBG_BB);
 }
 static __device__ __noinline__ bool bb_interval_hard(V3 p0, V3 v, float nv, float r, const BoxS &bx, float t_begin, float t_end, LeafLen leaf) {
   return bb_interval_impl<true>(p0, v, nv, r, bx, t_begin, t_end, leaf) == kWalkTrue;
