@@ -40,7 +40,7 @@ using pgm::v3;
 using pgs::Sphere;
 
 constexpr int kMaxPlanesL = 16;
-constexpr int kTimeline = 8;            // contacts per body per step the timelines can hold
+constexpr int kTimeline = 24;           // contacts per body per step the timelines can hold (a sphere buried in a pile: 12 neighbours, each pair visited twice)
 constexpr int kMaxIter = 24;
 constexpr int kMaxRounds = 4;
 constexpr unsigned kFullMask = 0xffffffffu;
