@@ -432,7 +432,7 @@ def run_gpu_arm(args, cfg):
             "config": {"workload": args.workload, "desc": cfg["desc"], "worlds_per_gpu": nw, "n_spheres": n, "n_planes": 6,
                        "dt": float(scenes.MAX_DELTA_TIME), "steps_per_launch": spl, "parallelism": f"worlds-sharded x{world_size}",
                        "l2": "256 MiB flush between launches, outside the CUDA-event pairs"},
-            "roofline": {"bound": "hbm", "kernel": "k_step_spheres<8,4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_step_spheres<8,16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes,
                          "note": "state lives in registers/shared memory for the whole launch; the kernel is "
