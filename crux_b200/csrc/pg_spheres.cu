@@ -426,6 +426,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
       if (wild) {                                  // every pair is a candidate; the rows filter for themselves
 #pragma unroll
         for (int k = 0; k < CPT; k++) W[k] = 0xffffffffu >> (32 - rows_here);
+        W[0] &= ~(1u << lane);                     // ... except a body with itself
       }
       unsigned *WS = S.W;                     // WS[k * 32 + lane]: the bit matrix, in shared memory from here on
 #pragma unroll

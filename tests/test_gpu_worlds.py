@@ -139,6 +139,72 @@ def test_sphere_kernel_ragged_sizes(gpu_lib, oracle_lib, n):
     w.close()
 
 
+def _hard_worlds():
+    """Worlds that drive the sphere kernel's rare paths: a dense pile (hundreds of candidate bits per
+    row block, several contacts per row, dirty rows), far-away stragglers (filter centre / per-pair
+    slack), a carpet of touching spheres with tiny velocities (grazing pairs: walk budget, leaf
+    scan, monotone plane decisions), and an astronomically large coordinate (the `wild` path)."""
+    n = 256
+    out = {}
+    pos, vel = scenes.sphere_worlds(1, n, 2.6, first_world=501)
+    out["dense"] = (2.6, pos[0].copy(), vel[0].copy())
+    pos, vel = scenes.sphere_worlds(1, n, 1.7, first_world=504)     # spheres overlap by the dozen: > 8 contacts in one row
+    out["crush"] = (1.7, pos[0].copy(), vel[0].copy())
+    pos, vel = scenes.sphere_worlds(1, n, 10.0, first_world=502)
+    p, v = pos[0].copy(), vel[0].copy()
+    p[7] = (0.5, -1500.0, 0.25); v[7] = (0.0, -170.0, 0.0)
+    p[100] = (3.0e4, 5.0, -2.0); v[100] = (40.0, 0.0, 0.0)
+    p[255] = (-0.75, 2.0e5, 1.0); v[255] = (0.0, 900.0, 0.0)
+    out["stragglers"] = (10.0, p, v)
+    g = np.arange(16, dtype=np.float32)
+    gx, gz = np.meshgrid(g, g)
+    p = np.stack([(gx.ravel() - 7.5) * np.float32(0.3000001), np.full(n, 0.151, np.float32) + (np.arange(n) % 3) * np.float32(1.0e-6),
+                  (gz.ravel() - 7.5) * np.float32(0.3000001)], axis=1).astype(np.float32)
+    rng = np.random.default_rng(5)
+    v = (rng.standard_normal((n, 3)) * np.float32(0.02)).astype(np.float32)
+    v[::5] *= np.float32(100.0)
+    out["carpet"] = (10.0, p, v)
+    pos, vel = scenes.sphere_worlds(1, n, 10.0, first_world=503)
+    p, v = pos[0].copy(), vel[0].copy()
+    p[33] = (1.0e18, 3.0, 0.0)
+    out["wild"] = (10.0, p, v)
+    return out
+
+
+@pytest.mark.parametrize("name", ["dense", "crush", "stragglers", "carpet", "wild"])
+def test_sphere_kernel_hard_worlds(gpu_lib, oracle_lib, name):
+    L, p, v = _hard_worlds()[name]
+    st = scenes.plane_bodies(scenes.box_planes(L))
+    w = gpu_lib.GpuWorlds(1, len(st), len(p), 0, max_events_per_world=65536)
+    w.set_spheres(0, st, p[None], v[None])
+    o = ora.World(oracle_lib, st, scenes.sphere_bodies(p, v))
+    total = 0
+    for chunk in range(4):
+        w.step(DT, 15)
+        o.step(DT, 15)
+        assert gen.state_equal(w.get_bodies(0, scenes.CLASS_DYNAMIC), o.read(1)), (name, chunk)
+        ge, oe = _events_tuple(w.events()), _events_tuple(o.events())
+        assert ge == oe, (name, chunk, len(ge), len(oe))
+        total += len(ge)
+    assert total > (500 if name in ("dense", "crush", "carpet") else 20), (name, total)
+    w.close()
+
+
+def test_sphere_kernel_tiny_dt(gpu_lib, oracle_lib):
+    """dt below 1e-9: the closest-approach gates are switched off, the exact path alone decides."""
+    pos, vel = scenes.sphere_worlds(1, 256, 4.0, first_world=77)
+    st = scenes.plane_bodies(scenes.box_planes(4.0))
+    w = gpu_lib.GpuWorlds(1, len(st), 256, 0, max_events_per_world=16384)
+    w.set_spheres(0, st, pos, vel)
+    o = ora.World(oracle_lib, st, scenes.sphere_bodies(pos[0], vel[0]))
+    for dt in (np.float32(5.0e-10), DT, np.float32(5.0e-10)):
+        w.step(dt, 5)
+        o.step(dt, 5)
+        assert gen.state_equal(w.get_bodies(0, scenes.CLASS_DYNAMIC), o.read(1)), float(dt)
+        assert _events_tuple(w.events()) == _events_tuple(o.events()), float(dt)
+    w.close()
+
+
 def test_no_gpu_fallback_is_an_error(gpu_lib):
     """Capacity and mode errors surface as exceptions, never as silent CPU work."""
     w = gpu_lib.GpuWorlds(1, 2, 4, 0)
