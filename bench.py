@@ -439,7 +439,7 @@ def run_gpu_arm(args, cfg):
                                  "SM-issue-bound, not HBM-bound (SURVEY.md section 8d), see profiles/"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "pg_worlds_step_host(dt, 1, pos, vel, at_rest): pinned host arrays in and out every step, 8 world chunks pipelined over 3 streams"},
+                    "steps": e2e_steps, "api": "pg_worlds_step_host(dt, 1, pos, vel, at_rest): pinned host arrays in and out every step; 4 world chunks over separate upload, compute and download queues, replayed as one CUDA graph"},
             "gpu_launches": int(gpu_launches),
             "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
             "launch_ms_per_step_min_max": [min(launch_ms), max(launch_ms)],

@@ -71,10 +71,17 @@ struct PgWorlds {
   unsigned char *d_stage_rest;
   size_t stage_bodies;
   // chunked host pipeline (pg_worlds_step_host)
-  cudaStream_t pipe_stream[3];
-  cudaEvent_t pipe_done[3];
+  cudaStream_t pipe_stream[3];    // compute: pack / step / unpack of chunk c on stream c % 3
+  cudaStream_t pipe_up, pipe_down;   // one queue per copy engine, so that a download never waits behind an upload
+  cudaEvent_t pipe_up_ev[8], pipe_k_ev[8], pipe_done[2], pipe_join[3], pipe_fork;
   int *d_pipe_counters;       // one hand-out counter per chunk
   bool pipe_ready;
+  // the whole chunk pipeline as one CUDA graph, re-captured when the host buffers or the step change
+  cudaGraphExec_t pipe_graph;
+  const void *pipe_key_ptr[3];
+  float pipe_key_dt;
+  int pipe_key_steps, pipe_key_chunks;
+  long long pipe_graph_kernels;
 };
 
 // pg_general.cu

@@ -682,6 +682,7 @@ static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int cou
     cudaFuncSetAttribute(k_step_spheres<CPT, MAXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(warp_bytes * MAXW));
     configured = true;
   }
+  if (count <= 0) return PG_OK;              // configuration only (callers about to capture a graph)
   // One block per SM.  The fewest waves of (SMs x MAXW) worlds that hold the batch, then the fewest
   // warps per block that still do it in that many waves: 4096 worlds on 148 SMs run as 2 waves of
   // 148 x 14 instead of 1.73 waves of 148 x 16.
@@ -715,7 +716,7 @@ int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int co
   else if (cap <= 512) launch_spheres<16, 8>(w, dt, n_steps, first, count, stream, counter);
   else { pg_set_error("sphere mode supports at most 512 spheres per world (got capacity %d)", cap); return PG_ERR_CAPACITY; }
   PG_CUDA(cudaGetLastError());
-  w->launches++;
+  if (count > 0) w->launches++;
   return PG_OK;
 }
 

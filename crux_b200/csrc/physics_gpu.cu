@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <vector>
 
 static thread_local char g_err[512] = "";
@@ -193,7 +194,13 @@ void pg_worlds_destroy(PgWorlds *w) {
   if (w->d_cost) cudaFree(w->d_cost);
   if (w->d_order) cudaFree(w->d_order);
   if (w->pipe_ready) {
-    for (int k = 0; k < 3; k++) { cudaStreamDestroy(w->pipe_stream[k]); cudaEventDestroy(w->pipe_done[k]); }
+    for (int k = 0; k < 3; k++) cudaStreamDestroy(w->pipe_stream[k]);
+    cudaStreamDestroy(w->pipe_up); cudaStreamDestroy(w->pipe_down);
+    for (int k = 0; k < 8; k++) { cudaEventDestroy(w->pipe_up_ev[k]); cudaEventDestroy(w->pipe_k_ev[k]); }
+    for (int k = 0; k < 2; k++) cudaEventDestroy(w->pipe_done[k]);
+    for (int k = 0; k < 3; k++) cudaEventDestroy(w->pipe_join[k]);
+    cudaEventDestroy(w->pipe_fork);
+    if (w->pipe_graph) cudaGraphExecDestroy(w->pipe_graph);
     cudaFree(w->d_pipe_counters);
   }
   if (w->d_stage_pos) { cudaFree(w->d_stage_pos); cudaFree(w->d_stage_vel); cudaFree(w->d_stage_rest); }
@@ -489,13 +496,20 @@ int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *v
   if (rc) return rc;
   rc = ensure_stage(w, (size_t)nw * n);
   if (rc) return rc;
-  constexpr int kChunks = 8;
+  static const int kChunksEnv = getenv("PG_HOST_CHUNKS") ? atoi(getenv("PG_HOST_CHUNKS")) : 4;   // measured: 2 -> 0.99, 4 -> 0.94, 8 -> 0.96 ms per 1 M-body step
+  const int kChunks = std::max(1, std::min(8, kChunksEnv));
   if (!w->pipe_ready) {
-    for (int k = 0; k < 3; k++) {
-      PG_CUDA(cudaStreamCreateWithFlags(&w->pipe_stream[k], cudaStreamNonBlocking));
-      PG_CUDA(cudaEventCreateWithFlags(&w->pipe_done[k], cudaEventDisableTiming));
+    for (int k = 0; k < 3; k++) PG_CUDA(cudaStreamCreateWithFlags(&w->pipe_stream[k], cudaStreamNonBlocking));
+    PG_CUDA(cudaStreamCreateWithFlags(&w->pipe_up, cudaStreamNonBlocking));
+    PG_CUDA(cudaStreamCreateWithFlags(&w->pipe_down, cudaStreamNonBlocking));
+    for (int k = 0; k < 8; k++) {
+      PG_CUDA(cudaEventCreateWithFlags(&w->pipe_up_ev[k], cudaEventDisableTiming));
+      PG_CUDA(cudaEventCreateWithFlags(&w->pipe_k_ev[k], cudaEventDisableTiming));
     }
-    PG_CUDA(cudaMalloc(&w->d_pipe_counters, sizeof(int) * kChunks));
+    for (int k = 0; k < 2; k++) PG_CUDA(cudaEventCreateWithFlags(&w->pipe_done[k], cudaEventDisableTiming));
+    for (int k = 0; k < 3; k++) PG_CUDA(cudaEventCreateWithFlags(&w->pipe_join[k], cudaEventDisableTiming));
+    PG_CUDA(cudaEventCreateWithFlags(&w->pipe_fork, cudaEventDisableTiming));
+    PG_CUDA(cudaMalloc(&w->d_pipe_counters, sizeof(int) * 8));
     w->pipe_ready = true;
   }
   {
@@ -503,38 +517,82 @@ int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *v
     if ((double)cdt > 0.01666) cdt = (float)0.01666;
     pg_leaf_lengths(0.0f, cdt, &w->v.leaf_lo, &w->v.leaf_hi);
   }
+  // One graph launch per call instead of ~60 stream operations (the cost that remains is per-copy
+  // overhead on the GPU side: the copies alone take 0.80 ms against 0.55 ms of pure PCIe time; SMs
+  // reading and writing the pinned arrays directly -- tried -- are no faster than the copy engines).
+  const bool same = w->pipe_graph && w->pipe_key_ptr[0] == pos && w->pipe_key_ptr[1] == vel && w->pipe_key_ptr[2] == at_rest &&
+                    w->pipe_key_dt == dt && w->pipe_key_steps == n_steps && w->pipe_key_chunks == kChunks;
+  static const bool use_graph = getenv("PG_HOST_NO_GRAPH") == nullptr;
+  if (use_graph && same) {
+    PG_CUDA(cudaEventRecord(w->ev0, w->stream));
+    PG_CUDA(cudaGraphLaunch(w->pipe_graph, w->stream));
+    PG_CUDA(cudaEventRecord(w->ev1, w->stream));
+    w->launches += w->pipe_graph_kernels;
+    w->last_steps = n_steps;
+    w->cost_valid = false;
+    PG_CUDA(cudaStreamSynchronize(w->stream));
+    return PG_OK;
+  }
+  if (w->pipe_graph) { cudaGraphExecDestroy(w->pipe_graph); w->pipe_graph = nullptr; }
+  const long long launches_before = w->launches;
+  if (use_graph) {
+    rc = pg_launch_sphere_range(w, dt, 0, 0, 0, w->stream, w->d_work_counter);      // kernel attributes are not capturable
+    if (rc) return rc;
+    PG_CUDA(cudaStreamSynchronize(w->stream));
+    PG_CUDA(cudaEventRecord(w->ev0, w->stream));
+    PG_CUDA(cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal));
+  } else {
+    PG_CUDA(cudaEventRecord(w->ev0, w->stream));
+  }
   PG_CUDA(cudaMemsetAsync(w->v.n_events, 0, sizeof(int) * (size_t)nw, w->stream));
-  PG_CUDA(cudaEventRecord(w->ev0, w->stream));
-  for (int k = 0; k < 3; k++) PG_CUDA(cudaStreamWaitEvent(w->pipe_stream[k], w->ev0, 0));
+  PG_CUDA(cudaEventRecord(w->pipe_fork, w->stream));
+  for (int k = 0; k < 3; k++) PG_CUDA(cudaStreamWaitEvent(w->pipe_stream[k], w->pipe_fork, 0));
   const int per = (nw + kChunks - 1) / kChunks;
+  {
+  PG_CUDA(cudaStreamWaitEvent(w->pipe_up, w->pipe_fork, 0));
+  // Three queues: uploads (H2D engine), compute (pack / step / unpack, three streams round robin),
+  // downloads (D2H engine).  Chunk c's kernels wait for its upload, its download waits for its
+  // kernels; a download never sits behind an upload in the same stream, so both copy engines and
+  // the SMs run at the same time (PCIe is full duplex: 26 MB each way take 0.55 ms together).
   for (int c = 0; c < kChunks; c++) {
     const int first = c * per, count = std::min(per, nw - first);
     if (count <= 0) break;
     cudaStream_t st = w->pipe_stream[c % 3];
     const size_t off = (size_t)first * n, bodies = (size_t)count * n;
-    PG_CUDA(cudaMemcpyAsync(w->d_stage_pos + 3 * off, pos + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyHostToDevice, st));
-    PG_CUDA(cudaMemcpyAsync(w->d_stage_vel + 3 * off, vel + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyHostToDevice, st));
-    if (at_rest) PG_CUDA(cudaMemcpyAsync(w->d_stage_rest + off, at_rest + off, bodies, cudaMemcpyHostToDevice, st));
+    PG_CUDA(cudaMemcpyAsync(w->d_stage_pos + 3 * off, pos + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyHostToDevice, w->pipe_up));
+    PG_CUDA(cudaMemcpyAsync(w->d_stage_vel + 3 * off, vel + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyHostToDevice, w->pipe_up));
+    if (at_rest) PG_CUDA(cudaMemcpyAsync(w->d_stage_rest + off, at_rest + off, bodies, cudaMemcpyHostToDevice, w->pipe_up));
+    PG_CUDA(cudaEventRecord(w->pipe_up_ev[c], w->pipe_up));
+    PG_CUDA(cudaStreamWaitEvent(st, w->pipe_up_ev[c], 0));
     rc = pg_launch_pack_state_on(w, st, first, count, n, w->d_stage_pos + 3 * off, w->d_stage_vel + 3 * off, at_rest ? w->d_stage_rest + off : nullptr);
     if (rc) return rc;
     if (n_steps > 0) { rc = pg_launch_sphere_range(w, dt, n_steps, first, count, st, w->d_pipe_counters + c); if (rc) return rc; }
     rc = pg_launch_unpack_state_on(w, st, first, count, n, w->d_stage_pos + 3 * off, w->d_stage_vel + 3 * off, at_rest ? w->d_stage_rest + off : nullptr);
     if (rc) return rc;
+    PG_CUDA(cudaEventRecord(w->pipe_k_ev[c], st));
+    PG_CUDA(cudaStreamWaitEvent(w->pipe_down, w->pipe_k_ev[c], 0));
+    PG_CUDA(cudaMemcpyAsync(pos + 3 * off, w->d_stage_pos + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyDeviceToHost, w->pipe_down));
+    PG_CUDA(cudaMemcpyAsync(vel + 3 * off, w->d_stage_vel + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyDeviceToHost, w->pipe_down));
+    if (at_rest) PG_CUDA(cudaMemcpyAsync(at_rest + off, w->d_stage_rest + off, bodies, cudaMemcpyDeviceToHost, w->pipe_down));
   }
-  // downloads are issued after ALL uploads: a copy engine serves its queue in order, and a D2H that
-  // waits for its chunk's kernels must not sit in front of the next chunk's H2D
-  for (int c = 0; c < kChunks; c++) {
-    const int first = c * per, count = std::min(per, nw - first);
-    if (count <= 0) break;
-    cudaStream_t st = w->pipe_stream[c % 3];
-    const size_t off = (size_t)first * n, bodies = (size_t)count * n;
-    PG_CUDA(cudaMemcpyAsync(pos + 3 * off, w->d_stage_pos + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyDeviceToHost, st));
-    PG_CUDA(cudaMemcpyAsync(vel + 3 * off, w->d_stage_vel + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyDeviceToHost, st));
-    if (at_rest) PG_CUDA(cudaMemcpyAsync(at_rest + off, w->d_stage_rest + off, bodies, cudaMemcpyDeviceToHost, st));
+  PG_CUDA(cudaEventRecord(w->pipe_done[0], w->pipe_down));
+  PG_CUDA(cudaStreamWaitEvent(w->stream, w->pipe_done[0], 0));
+  PG_CUDA(cudaEventRecord(w->pipe_done[1], w->pipe_up));
+  PG_CUDA(cudaStreamWaitEvent(w->stream, w->pipe_done[1], 0));
   }
-  for (int k = 0; k < 3; k++) {
-    PG_CUDA(cudaEventRecord(w->pipe_done[k], w->pipe_stream[k]));
-    PG_CUDA(cudaStreamWaitEvent(w->stream, w->pipe_done[k], 0));
+  for (int k = 0; k < 3; k++) {                  // every forked stream joins (chunks < 3 leave some idle)
+    PG_CUDA(cudaEventRecord(w->pipe_join[k], w->pipe_stream[k]));
+    PG_CUDA(cudaStreamWaitEvent(w->stream, w->pipe_join[k], 0));
+  }
+  if (use_graph) {
+    cudaGraph_t graph = nullptr;
+    PG_CUDA(cudaStreamEndCapture(w->stream, &graph));
+    PG_CUDA(cudaGraphInstantiate(&w->pipe_graph, graph, 0));
+    cudaGraphDestroy(graph);
+    w->pipe_key_ptr[0] = pos; w->pipe_key_ptr[1] = vel; w->pipe_key_ptr[2] = at_rest;
+    w->pipe_key_dt = dt; w->pipe_key_steps = n_steps; w->pipe_key_chunks = kChunks;
+    w->pipe_graph_kernels = w->launches - launches_before;
+    PG_CUDA(cudaGraphLaunch(w->pipe_graph, w->stream));
   }
   PG_CUDA(cudaEventRecord(w->ev1, w->stream));
   w->last_steps = n_steps;
