@@ -1,5 +1,7 @@
+"""Developer tool: per-step timing of the C5 level world (1 M spheres): step, k_pass3, k_eval, event counts."""
+import os
 import sys, time
-sys.path.insert(0, ".")
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
 from crux_b200 import scenes, gpu
 n, L = 1048576, 160.0
