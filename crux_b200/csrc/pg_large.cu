@@ -42,7 +42,6 @@ using pgs::Sphere;
 constexpr int kMaxPlanesL = 16;
 constexpr int kTimeline = 24;           // contacts per body per step the timelines can hold (a sphere buried in a pile: 12 neighbours, each pair visited twice)
 constexpr int kMaxIter = 24;
-constexpr int kMaxRounds = 4;
 constexpr unsigned kFullMask = 0xffffffffu;
 
 enum { K_PASS3 = 0, K_BOUNDS, K_CELLS, K_SCAN, K_SCATTER, K_PAIRS, K_EVAL, K_CHECK, K_FINAL, K_COUNT };
@@ -90,7 +89,6 @@ struct LargeView {
   // grid
   unsigned *cell_of;                 // [n]
   unsigned *cell_cnt;                // [cells_cap + 1]  counts -> exclusive starts
-  unsigned *cell_fill;               // [cells_cap]
   unsigned *block_sums;              // scan scratch
   int cells_cap;
   unsigned *sorted_idx;              // [n]
@@ -975,7 +973,6 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   PG_CUDA_NULL(cudaMalloc(&v.grid, sizeof(GridParams)));
   PG_CUDA_NULL(cudaMalloc(&v.cell_of, sizeof(unsigned) * n));
   PG_CUDA_NULL(cudaMalloc(&v.cell_cnt, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
-  PG_CUDA_NULL(cudaMalloc(&v.cell_fill, sizeof(unsigned) * (size_t)v.cells_cap));
   PG_CUDA_NULL(cudaMalloc(&v.block_sums, sizeof(unsigned) * ((size_t)v.cells_cap / (kScanBlock * kScanItems) + 2)));
   PG_CUDA_NULL(cudaMalloc(&v.sorted_idx, sizeof(unsigned) * n));
   PG_CUDA_NULL(cudaMalloc(&v.sorted_cenv, sizeof(float4) * n));
@@ -1011,7 +1008,7 @@ void pg_large_destroy(PgLarge *w) {
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
   if (w->player_world) pg_worlds_destroy(w->player_world);
-  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.cell_fill, v.block_sums, v.sorted_idx,
+  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.block_sums, v.sorted_idx,
                   v.sorted_cenv, v.pairs, v.grown, v.env_prev, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
                   v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);
