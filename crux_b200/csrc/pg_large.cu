@@ -53,6 +53,15 @@ struct GridParams {
   int dim[3];
   int n_cells;
   int ok;
+  float e_cap;            // envelope the cell edge is sized for; bodies beyond it are "fast" (few) and search wider
+};
+
+// Running statistics that keep the grid sized for the BULK of the bodies whatever a few stragglers do
+// (a sphere that tunnelled out of the level falls for ever, faster and faster): centre and accepted
+// half-widths carried from step to step; only bodies inside them contribute to the next ones.
+struct Robust {
+  float centre[3], half[3];
+  int valid;
 };
 
 struct Flags {
@@ -64,7 +73,7 @@ struct Flags {
   unsigned long long n_pairs;
   unsigned long long n_hits;
   unsigned n_touched;
-  unsigned pad0;
+  unsigned n_fast;        // bodies on the fast list
   float max_env_bits_pad;
 };
 
@@ -85,6 +94,9 @@ struct LargeView {
   float *env;                        // envelope radius per body
   // reductions
   unsigned *bbox;                    // 6 ordered-uint encodings: min xyz, max xyz ; [6] = max env
+  float *rstat;                      // [8] sums over the bodies inside the previous robust box: x y z |dx| |dy| |dz| env count
+  Robust *robust;
+  int *fast_list;                    // [n] bodies whose envelope exceeds grid->e_cap
   GridParams *grid;
   // grid
   unsigned *cell_of;                 // [n]
@@ -151,6 +163,8 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes) {
   pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
   const bool gate_ok = dt > 1.0e-9f;
   float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f}, emax = 0.0f;
+  float rs[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  const Robust rb = *v.robust;
   bool bad = false;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
     float4 p = v.pos_rest[i], q = v.vel_rad[i];
@@ -230,6 +244,10 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes) {
     lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
     hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
     emax = fmaxf(emax, e);
+    const float dx = fabsf(p.x - rb.centre[0]), dy = fabsf(p.y - rb.centre[1]), dz = fabsf(p.z - rb.centre[2]);
+    if (dx <= rb.half[0] && dy <= rb.half[1] && dz <= rb.half[2]) {
+      rs[0] += p.x; rs[1] += p.y; rs[2] += p.z; rs[3] += dx; rs[4] += dy; rs[5] += dz; rs[6] += e; rs[7] += 1.0f;
+    }
   }
   for (int o = 16; o > 0; o >>= 1) {
     for (int k = 0; k < 3; k++) {
@@ -237,10 +255,12 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes) {
       hi[k] = fmaxf(hi[k], __shfl_xor_sync(kFullMask, hi[k], o));
     }
     emax = fmaxf(emax, __shfl_xor_sync(kFullMask, emax, o));
+    for (int k = 0; k < 8; k++) rs[k] += __shfl_xor_sync(kFullMask, rs[k], o);
   }
   if ((threadIdx.x & 31) == 0) {
     for (int k = 0; k < 3; k++) { atomicMin(v.bbox + k, f2o(lo[k])); atomicMax(v.bbox + 3 + k, f2o(hi[k])); }
     atomicMax(v.bbox + 6, f2o(emax));
+    if (rs[7] > 0.0f) for (int k = 0; k < 8; k++) atomicAdd(v.rstat + k, rs[k]);
   }
   if (bad) atomicExch(&v.flags->unsafe, 1);
 }
@@ -250,9 +270,32 @@ __global__ void k_grid_params(LargeView v) {
   float lo[3], hi[3];
   for (int k = 0; k < 3; k++) { lo[k] = o2f(v.bbox[k]); hi[k] = o2f(v.bbox[3 + k]); }
   const float emax = o2f(v.bbox[6]);
-  // cell edge: two envelopes (one per body of a pair) with 25 % head room for envelopes that grow
-  float h = 2.0f * emax * 1.25f + 1.0e-6f;
   g.ok = 1;
+  // The bulk: mean position, mean absolute deviation and mean envelope of the bodies that were inside
+  // last step's accepted box.  The grid covers mean +- (6 deviations + room) -- a uniform box spans
+  // +-2 deviations -- and its cells are sized for 4 mean envelopes; bodies outside are clamped into
+  // the border cells, bodies with a larger envelope search more cells (k_pairs).
+  float e_cap = emax;
+  Robust rb = *v.robust;
+  const float cnt = v.rstat[7];
+  if (cnt >= 0.5f * (float)v.n && cnt >= 1.0f) {
+    for (int k = 0; k < 3; k++) {
+      const float mean = v.rstat[k] / cnt, dev = v.rstat[3 + k] / cnt;
+      const float half = 6.0f * dev + 32.0f * (v.rstat[6] / cnt) + 4.0f;   // dev is about last step's centre: never too small
+      if (rb.valid) { lo[k] = fmaxf(lo[k], mean - half); hi[k] = fminf(hi[k], mean + half); }
+      rb.centre[k] = mean; rb.half[k] = half;
+    }
+    if (rb.valid) e_cap = fminf(emax, 4.0f * (v.rstat[6] / cnt) + 1.0e-3f);
+    rb.valid = 1;
+  } else {
+    // lost the bulk (or first step, or a frozen-state query): accept everything, start over
+    for (int k = 0; k < 3; k++) { rb.centre[k] = 0.0f; rb.half[k] = 3.0e38f; }
+    rb.valid = 0;
+  }
+  for (int k = 0; k < 3; k++) if (!(lo[k] <= hi[k])) { const float m = 0.5f * (o2f(v.bbox[k]) + o2f(v.bbox[3 + k])); lo[k] = hi[k] = m; }
+  *v.robust = rb;
+  // cell edge: two envelopes (one per body of a pair) with 25 % head room for envelopes that grow
+  float h = 2.0f * e_cap * 1.25f + 1.0e-6f;
   if (!(h > 0.0f) || !(h < 1.0e15f) || !(lo[0] <= hi[0])) { g.ok = 0; h = 1.0f; lo[0] = lo[1] = lo[2] = 0.0f; hi[0] = hi[1] = hi[2] = 0.0f; }
   for (;;) {
     double cells = 1.0;
@@ -266,6 +309,7 @@ __global__ void k_grid_params(LargeView v) {
   }
   for (int k = 0; k < 3; k++) g.org[k] = lo[k] - 0.5f * h * 0.001f;
   g.inv_h = 1.0f / h;
+  g.e_cap = 0.5f * h;                          // the largest envelope the 27-cell search serves: 2 env <= h (25 % above the sizing envelope)
   *v.grid = g;
 }
 
@@ -286,6 +330,7 @@ __global__ void k_cell_count(LargeView v) {
     const unsigned cell = (unsigned)((c.z * g.dim[1] + c.y) * g.dim[0] + c.x);
     v.cell_of[i] = cell;
     v.cell_rank[i] = atomicAdd(v.cell_cnt + cell, 1u);
+    if (v.env[i] > g.e_cap) v.fast_list[atomicAdd(&v.flags->n_fast, 1u)] = i;
   }
 }
 
@@ -357,7 +402,12 @@ __global__ void k_scatter(LargeView v) {
   }
 }
 
-// ---------------------------------------------------------------- candidate pairs (27 cells = 9 x-runs)
+// ---------------------------------------------------------------- candidate pairs
+// A pair is listed by its body with the LARGER envelope (ties: lower index), which therefore only has
+// to find partners within 2 env of itself: R = ceil(2 env / h) cells each way -- 1 for everybody the
+// grid was sized for (27 cells = 9 contiguous x-runs), more for the few fast bodies, and the whole
+// sorted array for a body so fast that its search would cover most of the grid anyway.
+constexpr int kMaxSearch = 12;
 __global__ void k_pairs(LargeView v) {
   const GridParams g = *v.grid;
   const int lane = threadIdx.x & 31;
@@ -366,17 +416,26 @@ __global__ void k_pairs(LargeView v) {
     float4 ca = make_float4(0, 0, 0, 0);
     unsigned ia = 0;
     int3 c = make_int3(0, 0, 0);
-    if (live) { ca = v.sorted_cenv[a]; ia = v.sorted_idx[a]; c = cell_coords(g, ca.x, ca.y, ca.z); }
-    for (int dz = -1; dz <= 1; dz++) {
-      for (int dy = -1; dy <= 1; dy++) {
+    int R = 0;
+    bool everything = false;
+    if (live) {
+      ca = v.sorted_cenv[a]; ia = v.sorted_idx[a]; c = cell_coords(g, ca.x, ca.y, ca.z);
+      const float need = 2.0f * ca.w * g.inv_h * 1.001f;
+      R = need <= 1.0f ? 1 : (need <= (float)kMaxSearch ? (int)ceilf(need) : 0);
+      everything = !(need <= (float)kMaxSearch);
+    }
+    const int Rw = __reduce_max_sync(kFullMask, R);
+    for (int dz = -Rw; dz <= Rw; dz++) {
+      for (int dy = -Rw; dy <= Rw; dy++) {
         unsigned b0 = 0, b1 = 0;
         const int y = c.y + dy, z = c.z + dz;
-        if (live && y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
-          const int x0 = max(c.x - 1, 0), x1 = min(c.x + 1, g.dim[0] - 1);
+        if (live && !everything && abs(dy) <= R && abs(dz) <= R && y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
+          const int x0 = max(c.x - R, 0), x1 = min(c.x + R, g.dim[0] - 1);
           const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
           b0 = v.cell_cnt[row + x0];
           b1 = v.cell_cnt[row + x1 + 1];
         }
+        if (everything && dz == -Rw && dy == -Rw) { b0 = 0; b1 = (unsigned)v.n; }
         // lanes walk their runs together; appends are warp-aggregated
         for (unsigned b = b0; __any_sync(kFullMask, b < b1); b++) {
           bool hit = false;
@@ -387,7 +446,7 @@ __global__ void k_pairs(LargeView v) {
             const float dx = ca.x - cb.x, dyy = ca.y - cb.y, dzz = ca.z - cb.z;
             const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
             const float T = ca.w + cb.w;
-            hit = (ia < ib) && (d2 <= T * T);
+            hit = (ca.w > cb.w || (ca.w == cb.w && ia < ib)) && ia != ib && (d2 <= T * T);
           }
           const unsigned m = __ballot_sync(kFullMask, hit);
           if (m) {
@@ -396,7 +455,7 @@ __global__ void k_pairs(LargeView v) {
             base = __shfl_sync(kFullMask, base, __ffs(m) - 1);
             if (hit) {
               const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
-              if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2((int)ia, (int)ib);
+              if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2((int)min(ia, ib), (int)max(ia, ib));
               else atomicExch(&v.flags->overflow_pairs, 1);
             }
           }
@@ -600,9 +659,11 @@ __global__ void k_check(LargeView v, int src, int dst, float dt) {
       need = fmaxf(need, (q.w + dev + reach) * 1.0002f + 2.0e-6f);
     }
     if (need > v.env[b]) {
+      const float e_cap = v.grid->e_cap;
+      if (!(v.env[b] > e_cap) && need * 1.05f > e_cap) v.fast_list[atomicAdd(&v.flags->n_fast, 1u)] = b;   // joins the fast bodies
       v.env[b] = need * 1.05f;
       v.grown[b] = 1;
-      v.flags->grew = 1;
+      atomicAdd(&v.flags->grew, 1);
       atomicMax(v.bbox + 6, f2o(need * 1.05f));      // largest envelope in the world, for k_requery's search radius
       if (!(need < 1.0e15f)) v.flags->unsafe = 1;
     }
@@ -622,35 +683,56 @@ __global__ void k_clear(LargeView v, int dst) {
 __global__ void k_requery(LargeView v, int src) {
   const GridParams g = *v.grid;
   const int nt = (int)v.flags->n_touched;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  // one warp per touched body: the lanes share its cell runs, the fast list and -- for a body whose
+  // search would cover most of the grid -- the whole sorted array
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nt; t += warps) {
     const int b = v.touched[t];
     if (!v.grown[b]) continue;
     const float4 p = v.pos_rest[b];
     const float eb = v.env[b], eb_old = v.env_prev[b];
-    // a partner x can be up to eb + env_x <= eb + emax away: search that many cells in every direction
-    const float emax = o2f(v.bbox[6]);
-    const int R = (int)ceilf((eb + emax) * g.inv_h * 1.001f);
-    if (!(R >= 1) || R > 8) { v.flags->unsafe = 2; continue; }
-    const int3 c = cell_coords(g, p.x, p.y, p.z);
-    for (int dz = -R; dz <= R; dz++) for (int dy = -R; dy <= R; dy++) {
-      const int y = c.y + dy, z = c.z + dz;
-      if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
-      const int x0 = max(c.x - R, 0), x1 = min(c.x + R, g.dim[0] - 1);
-      const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
-      for (unsigned a = v.cell_cnt[row + x0]; a < v.cell_cnt[row + x1 + 1]; a++) {
+    auto consider = [&](int x, float4 cx) {
+      const float dx = p.x - cx.x, dyy = p.y - cx.y, dzz = p.z - cx.z;
+      const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
+      const float ex = v.env[x], ex_old = v.env_prev[x];
+      const float Tn = eb + ex, To = eb_old + ex_old;
+      if (!(d2 <= Tn * Tn) || d2 <= To * To) return;            // not a candidate, or already listed
+      if (v.grown[x] && x < b) return;                          // the other grown body appends it
+      const unsigned long long slot = atomicAdd(&v.flags->n_pairs, 1ull);
+      if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2(~min(b, x), max(b, x));   // ~i marks it fresh
+      else atomicExch(&v.flags->overflow_pairs, 1);
+    };
+    // Partners the grid was sized for (envelope <= e_cap) can be up to eb + e_cap away: search that many
+    // cells in every direction.  Fast partners are few and are checked one by one from their list
+    // (which also holds bodies that outgrew e_cap this step).
+    const float need = (eb + g.e_cap) * g.inv_h * 1.001f;
+    if (!(need <= (float)kMaxSearch)) {
+      for (int a = lane; a < v.n; a += 32) {
         const int x = (int)v.sorted_idx[a];
-        if (x == b) continue;
-        const float4 cx = v.sorted_cenv[a];
-        const float dx = p.x - cx.x, dyy = p.y - cx.y, dzz = p.z - cx.z;
-        const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
-        const float ex = v.env[x], ex_old = v.env_prev[x];
-        const float Tn = eb + ex, To = eb_old + ex_old;
-        if (!(d2 <= Tn * Tn) || d2 <= To * To) continue;          // not a candidate, or already listed
-        if (v.grown[x] && x < b) continue;                        // the other grown body appends it
-        const unsigned long long slot = atomicAdd(&v.flags->n_pairs, 1ull);
-        if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2(~min(b, x), max(b, x));   // ~i marks it fresh
-        else atomicExch(&v.flags->overflow_pairs, 1);
+        if (x != b && !(v.env[x] > g.e_cap)) consider(x, v.sorted_cenv[a]);
       }
+    } else {
+      const int R = max((int)ceilf(need), 1);
+      const int3 c = cell_coords(g, p.x, p.y, p.z);
+      for (int dz = -R; dz <= R; dz++) for (int dy = -R; dy <= R; dy++) {
+        const int y = c.y + dy, z = c.z + dz;
+        if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
+        const int x0 = max(c.x - R, 0), x1 = min(c.x + R, g.dim[0] - 1);
+        const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+        const unsigned a1 = v.cell_cnt[row + x1 + 1];
+        for (unsigned a = v.cell_cnt[row + x0] + lane; a < a1; a += 32) {
+          const int x = (int)v.sorted_idx[a];
+          if (x != b && !(v.env[x] > g.e_cap)) consider(x, v.sorted_cenv[a]);
+        }
+      }
+    }
+    const int nf = (int)v.flags->n_fast;
+    for (int f = lane; f < nf; f += 32) {
+      const int x = v.fast_list[f];
+      if (x == b || !(v.env[x] > g.e_cap)) continue;
+      const float4 px = v.pos_rest[x];
+      consider(x, make_float4(px.x, px.y, px.z, 0.0f));
     }
   }
 }
@@ -826,6 +908,7 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   const unsigned bbox_init[7] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u};
   PG_CUDA(cudaMemcpyAsync(v.bbox, bbox_init, sizeof(bbox_init), cudaMemcpyHostToDevice, w->stream));
   PG_CUDA(cudaMemsetAsync(v.flags, 0, sizeof(Flags), w->stream));
+  PG_CUDA(cudaMemsetAsync(v.rstat, 0, sizeof(float) * 8, w->stream));
   LW_LAUNCH(w, K_PASS3, k_pass3, lw_grid(w, v.n, 256), 256, v, dt, w->step_in_call, 1);
   w->last_proven = 1;
   w->last_iterations = 0;
@@ -868,8 +951,8 @@ static int lw_step_once(PgLarge *w, float dt_in) {
       float e = 0, c = 0;
       cudaEventElapsedTime(&e, w->kev[K_EVAL][0], w->kev[K_EVAL][1]);
       cudaEventElapsedTime(&c, w->kev[K_CHECK][0], w->kev[K_CHECK][1]);
-      fprintf(stderr, "  [pg_large] iter %d: eval %.3f ms check %.3f ms hits %llu changed %d grew %d pairs %llu\n", it, e, c,
-              (unsigned long long)f.n_hits, f.changed, f.grew, (unsigned long long)f.n_pairs);
+      fprintf(stderr, "  [pg_large] iter %d: eval %.3f ms check %.3f ms hits %llu changed %d grew %d pairs %llu touched %u fast %u\n", it, e, c,
+              (unsigned long long)f.n_hits, f.changed, f.grew, (unsigned long long)f.n_pairs, f.n_touched, f.n_fast);
     }
     w->last_iterations++;
     w->last_hits = (long long)f.n_hits;
@@ -880,7 +963,7 @@ static int lw_step_once(PgLarge *w, float dt_in) {
       // re-evaluates them on top of the current timelines (warm start)
       const unsigned long long pairs_before = std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
       const int touched_now = std::max((int)f.n_touched, 1);
-      LW_LAUNCH(w, K_BOUNDS, k_requery, lw_grid(w, touched_now, 128), 128, v, src);
+      LW_LAUNCH(w, K_BOUNDS, k_requery, lw_grid(w, std::min(touched_now, 1 << 24) * 32, 128), 128, v, src);
       rc = lw_read_flags(w, &f);
       if (rc) return rc;
       lw_accumulate(w, K_BOUNDS);
@@ -888,11 +971,16 @@ static int lw_step_once(PgLarge *w, float dt_in) {
         // k_requery only appends: keep the list as it was, make room, and let it append again
         rc = lw_grow_pairs(w, f.n_pairs, pairs_before);
         if (rc) return rc;
-        LW_LAUNCH(w, K_BOUNDS, k_requery, lw_grid(w, touched_now, 128), 128, v, src);
+        LW_LAUNCH(w, K_BOUNDS, k_requery, lw_grid(w, std::min(touched_now, 1 << 24) * 32, 128), 128, v, src);
         rc = lw_read_flags(w, &f);
         if (rc) return rc;
         lw_accumulate(w, K_BOUNDS);
         if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
+      }
+      if (debug) {
+        float rq = 0;
+        cudaEventElapsedTime(&rq, w->kev[K_BOUNDS][0], w->kev[K_BOUNDS][1]);
+        fprintf(stderr, "  [pg_large] requery %.3f ms: pairs %llu -> %llu, fast %u\n", rq, pairs_before, (unsigned long long)f.n_pairs, f.n_fast);
       }
       k_requery_done<<<lw_grid(w, touched_now, 256), 256, 0, w->stream>>>(v);
       w->launches++;
@@ -971,6 +1059,15 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   PG_CUDA_NULL(cudaMalloc(&v.env, sizeof(float) * n));
   PG_CUDA_NULL(cudaMalloc(&v.bbox, sizeof(unsigned) * 8));
   PG_CUDA_NULL(cudaMalloc(&v.grid, sizeof(GridParams)));
+  PG_CUDA_NULL(cudaMalloc(&v.rstat, sizeof(float) * 8));
+  PG_CUDA_NULL(cudaMalloc(&v.robust, sizeof(Robust)));
+  {
+    Robust r0;
+    for (int k = 0; k < 3; k++) { r0.centre[k] = 0.0f; r0.half[k] = 3.0e38f; }
+    r0.valid = 0;
+    PG_CUDA_NULL(cudaMemcpy(v.robust, &r0, sizeof(r0), cudaMemcpyHostToDevice));
+  }
+  PG_CUDA_NULL(cudaMalloc(&v.fast_list, sizeof(int) * n));
   PG_CUDA_NULL(cudaMalloc(&v.cell_of, sizeof(unsigned) * n));
   PG_CUDA_NULL(cudaMalloc(&v.cell_cnt, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.block_sums, sizeof(unsigned) * ((size_t)v.cells_cap / (kScanBlock * kScanItems) + 2)));
@@ -1008,7 +1105,7 @@ void pg_large_destroy(PgLarge *w) {
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
   if (w->player_world) pg_worlds_destroy(w->player_world);
-  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.block_sums, v.sorted_idx,
+  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.fast_list, v.block_sums, v.sorted_idx,
                   v.sorted_cenv, v.pairs, v.grown, v.env_prev, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
                   v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);
@@ -1239,6 +1336,7 @@ long long pg_large_pairs(PgLarge *w, float dt_in, int32_t *out_ij, long long cap
   const unsigned bbox_init[7] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u};
   PG_CUDA(cudaMemcpyAsync(v.bbox, bbox_init, sizeof(bbox_init), cudaMemcpyHostToDevice, w->stream));
   PG_CUDA(cudaMemsetAsync(v.flags, 0, sizeof(Flags), w->stream));
+  PG_CUDA(cudaMemsetAsync(v.rstat, 0, sizeof(float) * 8, w->stream));       // no running statistics here: plain bounding box
   k_env_frozen<<<lw_grid(w, v.n, 256), 256, 0, w->stream>>>(v, dt);
   w->launches++;
   int rc = lw_build_pairs(w);

@@ -44,6 +44,43 @@ def test_large_world_equals_sequential_sweep(gpu_lib, oracle_lib, n, L, steps):
     g.close()
 
 
+def test_large_world_with_stragglers_and_fast_bodies(gpu_lib, oracle_lib):
+    """Bodies far outside the bulk (tunnelled through the floor and falling, or simply far away) and
+    bodies much faster than the rest: the grid is sized for the bulk, the odd ones search wider or are
+    checked from the fast list -- and the result is still the sequential sweep's, bit for bit."""
+    n, L = 3000, 16.0
+    pos, vel = scenes.sphere_worlds(1, n, L, first_world=4242)
+    pos, vel = pos[0].copy(), vel[0].copy()
+    rng = np.random.default_rng(9)
+    fall = rng.choice(n, 40, replace=False)
+    pos[fall, 1] = -rng.uniform(50.0, 900.0, 40).astype(np.float32)
+    vel[fall, 1] = -rng.uniform(30.0, 170.0, 40).astype(np.float32)
+    pos[fall[:6], 0] = pos[fall[6:12], 0] + np.float32(0.31)          # some of them close enough to meet on the way down
+    pos[fall[:6], 1] = pos[fall[6:12], 1] + np.float32(0.05)
+    pos[fall[:6], 2] = pos[fall[6:12], 2]
+    far = rng.choice(np.setdiff1d(np.arange(n), fall), 5, replace=False)
+    pos[far, 0] = np.float32(1.0e4) + np.arange(5, dtype=np.float32)
+    fast = rng.choice(np.setdiff1d(np.arange(n), np.concatenate([fall, far])), 25, replace=False)
+    vel[fast] *= np.float32(20.0)                                       # up to 80 m/s inside the box
+    st = scenes.plane_bodies(scenes.box_planes(L))
+    o = ora.World(oracle_lib, st, scenes.sphere_bodies(pos, vel))
+    g = gpu_lib.GpuLargeWorld(n, len(st))
+    g.set(st, pos, vel)
+    total = 0
+    for s in range(30):
+        g.step(DT, 1)
+        oracle_lib.dll.ora_world_step_grid(o.h, DT, 1, 0)
+        assert g.exactness()["proven_exact"], s
+        P, V, R = g.download_state()
+        r = o.read(1)
+        assert gen.same_bits(P, r["position"]) and gen.same_bits(V, r["velocity"]) and np.array_equal(R != 0, r["at_rest"] != 0), s
+        ge, oe = _ev(g.events()), _ev(o.events())
+        assert ge == oe, (s, len(ge), len(oe))
+        total += len(ge)
+    assert total > 500
+    g.close()
+
+
 def test_large_world_multi_step_call(gpu_lib, oracle_lib):
     n, L = 5000, 24.0
     pos, vel, st, o = _world(oracle_lib, n, L, 31)
