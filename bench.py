@@ -418,11 +418,15 @@ def run_gpu_arm(args, cfg):
         algo_bytes = ALGO_BYTES_PER_BODY_STEP * bodies * spl
         achieved = algo_bytes / (avg_launch_ms * 1e-3) / 1e9
         traffic = None
+        issue = {}
         rj = os.path.join(ROOT, "profiles", "roofline_r01.json")
         if os.path.exists(rj):
             try:
-                traffic = json.load(open(rj)).get("dram_bytes_per_step")
+                prof = json.load(open(rj))
+                traffic = prof.get("dram_bytes_per_step")
                 traffic = traffic * spl if traffic else None
+                issue = {k: prof[k] for k in ("sm_issue_utilisation", "warp_instructions_per_world_step", "icache_hit_rate",
+                                              "gcc_instruction_request_rate_of_peak") if k in prof}
             except Exception:
                 traffic = None
         line = {
@@ -435,8 +439,9 @@ def run_gpu_arm(args, cfg):
             "roofline": {"bound": "hbm", "kernel": "k_step_spheres<8,16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes,
-                         "note": "state lives in registers/shared memory for the whole launch; the kernel is "
-                                 "SM-issue-bound, not HBM-bound (SURVEY.md section 8d), see profiles/"},
+                         "sm_issue": issue,     # from the ncu capture in profiles/ (not measured live)
+                         "note": "state lives in shared memory for the whole launch; the kernel is bound by SM issue "
+                                 "slots and instruction fetch, not by HBM (SURVEY.md section 8d), see profiles/k_step_spheres_r01.md"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "pg_worlds_step_host(dt, 1, pos, vel, at_rest): pinned host arrays in and out every step; 4 world chunks over separate upload, compute and download queues, replayed as one CUDA graph"},
