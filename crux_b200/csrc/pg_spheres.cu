@@ -1,22 +1,29 @@
 // pg_spheres.cu -- batched sphere worlds (config C3: 4096 x 256-sphere bouncehouse worlds).
 //
-// ONE WARP PER WORLD, state in registers, reference solve order preserved exactly.
+// ONE WARP PER WORLD, state in shared memory, reference solve order preserved exactly.
 //
-// Body i of a world lives in lane (i & 31), register slot (i >> 5); a world holds up to 32*CPT
-// spheres.  The whole n_steps loop runs inside one launch: positions/velocities are read from HBM
-// once and written once per launch (32 B + 32 B per body), everything in between is register and
-// shuffle traffic.  There are no block barriers -- a world's sequential sweep only ever needs
-// warp-level votes.
+// Body i of a world belongs to lane (i & 31), slot (i >> 5); a world holds up to 32*CPT spheres.
+// The whole n_steps loop runs inside one launch: positions/velocities are read from HBM once and
+// written once per launch (32 B + 32 B per body), everything in between is shared-memory, register
+// and shuffle traffic.  A world's sequential sweep only ever needs warp-level votes; the one block
+// barrier per step exists for the instruction cache (see PG_SPH_SYNC).
 //
 // Pass 4 of physics_step (world.c:473-554) is N rows; row i visits every column j != i, mutating
-// i and j in place, then integrates i.  Per row every lane runs a CONSERVATIVE reach test on its CPT
-// columns (float, |ci-cj|^2 against (rho_i+rho_j)^2 with rho = (r + |v| dt)(1+1e-4)): a pair that
-// fails it cannot pass the root test of interval_collision (world.c:559-565), so skipping it is
-// exact.  Survivors are taken in increasing j (warp min-reduce), gated by a second conservative
-// test (closest approach of the two linear paths over [0,dt] against rs + delta), and only then
-// evaluated with the exact predicate + narrowphase + resolver of pg_math.cuh, redundantly on all
-// lanes (warp-uniform control flow).  After any evaluated candidate the remaining columns are
-// re-filtered against the row body's current state, which is what the sequential loop would see.
+// i and j in place, then integrates i.  Rows are processed 32 at a time:
+//   filter   every lane tests its CPT columns against the 32 rows with a CONSERVATIVE reach test
+//            (|ci-cj|^2 against (rho_i+rho_j)^2, rho = (r + |v| dt)(1+1e-4), expanded form, two
+//            columns per FFMA2): a pair that fails it cannot pass the root test of
+//            interval_collision (world.c:559-565), so skipping it is exact.  It runs on the state
+//            each row WILL see if no contact intervenes (earlier rows of the block integrated).
+//   gate     the surviving (row, column) bits of the block are gated one pair per lane by the
+//            closest approach of the two linear paths over [0,dt] against rs + delta.
+//   visits   rows that still hold a bit are visited in order, their columns in increasing j
+//            (warp min-reduce), with the exact predicate + narrowphase + resolver of pg_math.cuh,
+//            redundantly on all lanes (warp-uniform control flow); rows in between are integrated
+//            in bulk.
+//   repair   a contact rewrites the bits of the two bodies it changed: the row re-filters its
+//            remaining columns, later rows of the block re-test the changed columns (one lane per
+//            row, a ballot is the new word), a changed later row rebuilds itself when its turn comes.
 //
 // Pass 3 (dynamic x static planes, world.c:369-471) touches only the dynamic body, so each lane
 // runs it for its own bodies, planes in array order.
@@ -60,7 +67,6 @@ __device__ __noinline__ void emit_event(const WorldsView &v, int w, int step, in
 // Shared-memory image of one world: every body as two float4.
 //   P4[i] = (px, py, pz, rho)   rho = conservative reach (r + |v| dt)(1+1e-4), refreshed with v
 //   V4[i] = (vx, vy, vz, r)
-// Lanes additionally cache (px,py,pz,rho) of their own CPT bodies in registers for the hot filter.
 
 // Slow half of pass 3 for one body against one plane (per lane, divergent): refined gate, then the
 // exact visit.  Returns true if the body changed; *rest is set when it came to rest.
@@ -176,11 +182,11 @@ __device__ __noinline__ unsigned recheck_column(const float4 *P4, const float4 *
   return __ballot_sync(kFull, pass);
 }
 
-// The register cache is kept ROTATED: while row block `rb` (rows rb*32 .. rb*32+31) is swept,
-// static slot k of the cache holds the body of actual slot (rb + k) mod CPT, so the block's own
-// bodies always sit in static slot 0.  That keeps every register index a compile-time constant
-// with ONE copy of the row loop in the instruction stream (a fully unrolled variant was 9.5k SASS
-// instructions and spent most of its time in instruction-cache misses).
+// The filter's column registers are ROTATED: while row block `rb` (rows rb*32 .. rb*32+31) is swept,
+// static slot k holds the body of actual slot (rb + k) mod CPT, so the block's own bodies always sit
+// in static slot 0.  That keeps every register index a compile-time constant with ONE copy of the
+// filter loop in the instruction stream.
+//
 // Shared-memory image of one world (one warp).
 template <int CPT>
 struct WarpSmem {
