@@ -91,7 +91,7 @@ def build_host(force: bool = False) -> str | None:
             raise RuntimeError("gcc failed on the host layer")
     main_c = os.path.join(CSRC, "host", "crux_headless.c")
     if os.path.exists(main_c) and (force or _newer(HEADLESS, [main_c, HOST_SO] + _headers())):
-        cmd = ["gcc", "-std=gnu11", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-rdynamic",
+        cmd = ["gcc", "-std=gnu11", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-rdynamic", "-DCRUX_HAVE_UPLOAD_STATS",
                "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(CSRC, "host"),
                "-o", HEADLESS, main_c, "-L" + LIB, "-lcrux_physics", "-lphysics_gpu", "-Wl,-rpath,$ORIGIN", "-lm"]
         r = subprocess.run(cmd, capture_output=True, text=True)

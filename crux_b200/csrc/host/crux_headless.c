@@ -66,6 +66,10 @@ int main(int argc, char **argv) {
   fclose(f);
   printf("%s: generation %d, %d static %d dynamic %d player bodies, %d steps, %d events\n", argv[1], s->schema_generation, hdr[0], hdr[1], hdr[2],
          steps, g_nev);
+#ifdef CRUX_HAVE_UPLOAD_STATS
+  /* the GPU drop-in only: how many body records travelled host -> device (dirty ranges, crux_world.c) */
+  printf("uploaded body records: %llu\n", physics_world_uploaded_records(s->world));
+#endif
   crux_scene_free(s);
   return 0;
 }

@@ -166,5 +166,8 @@ void physics_world_release_gpu(struct PhysicsWorld *world);
 /* Step `n_steps` frames on the device without the per-frame host round trip; scene-node matrices
  * are refreshed on the device after every step like scene_update does (scene.c:401-408). */
 void physics_step_n(struct PhysicsWorld *world, float delta_time, int n_steps);
+/* How many body records physics_step has sent to the device so far.  Only records that differ from the
+ * device's copy travel (dirty ranges): a frame in which only the player was poked sends one. */
+unsigned long long physics_world_uploaded_records(struct PhysicsWorld *world);
 
 #endif /* CRUX_PHYSICS_COMPAT_H */

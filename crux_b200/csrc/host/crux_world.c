@@ -28,8 +28,11 @@ typedef struct Shadow {
   struct PhysicsWorld *world;
   PgWorlds *gpu;
   int cap[3];
-  PgBody *rec[3];
+  PgBody *rec[3];             /* scratch: this frame's flattened mirror / the downloaded records */
+  PgBody *dev[3];             /* what the device holds (as of the last upload or download) */
+  int dev_n[3];               /* ... and how many records of each class; -1 = unknown, upload everything */
   int rec_cap[3];
+  unsigned long long uploaded_records;   /* statistics: body records sent to the device so far */
   PgEvent *events;
   struct Shadow *next;
 } Shadow;
@@ -130,7 +133,7 @@ void physics_world_release_gpu(struct PhysicsWorld *world) {
     if (s->world == world) {
       *pp = s->next;
       if (s->gpu) pg_worlds_destroy(s->gpu);
-      for (int c = 0; c < 3; c++) free(s->rec[c]);
+      for (int c = 0; c < 3; c++) { free(s->rec[c]); free(s->dev[c]); }
       free(s->events);
       free(s);
       return;
@@ -231,6 +234,7 @@ static int ensure_gpu(Shadow *s) {
     if (s->gpu) pg_worlds_destroy(s->gpu);
     for (int c = 0; c < 3; c++) { s->cap[c] = need[c] > MAX_PHYSICS_BODIES ? need[c] * 2 : MAX_PHYSICS_BODIES; }
     s->gpu = pg_worlds_create(1, s->cap[0], s->cap[1], s->cap[2], CRUX_MAX_EVENTS, 0);
+    for (int c = 0; c < 3; c++) s->dev_n[c] = -1;
     if (!s->gpu) {
       fprintf(stderr, "Error: physics_step: no usable CUDA device (%s); the step is skipped\n", pg_last_error());
       return -1;
@@ -241,6 +245,8 @@ static int ensure_gpu(Shadow *s) {
     if (need[c] > s->rec_cap[c]) {
       s->rec_cap[c] = need[c] > MAX_PHYSICS_BODIES ? need[c] * 2 : MAX_PHYSICS_BODIES;
       s->rec[c] = (PgBody *)realloc(s->rec[c], sizeof(PgBody) * (size_t)s->rec_cap[c]);
+      s->dev[c] = (PgBody *)realloc(s->dev[c], sizeof(PgBody) * (size_t)s->rec_cap[c]);
+      s->dev_n[c] = -1;
     }
   }
   return 0;
@@ -285,10 +291,30 @@ static void step_impl(struct PhysicsWorld *physics_world, float delta_time, int 
     unsigned int n;
     struct PhysicsBody *arr = class_array(physics_world, c, &n);
     for (unsigned int i = 0; i < n; i++) crux_flatten_body(&arr[i], &s->rec[c][i]);
-    if (pg_worlds_set_bodies(s->gpu, 0, c, s->rec[c], (int)n) != PG_OK) {
+    /* The host arrays are the truth (player.c and the scene poke them between frames), the device keeps
+     * a copy: send only the records that differ from what it holds, as contiguous dirty ranges.  A class
+     * whose length changed (physics_add_body / physics_remove_body) is sent whole. */
+    int rc = PG_OK;
+    if (s->dev_n[c] != (int)n) {
+      rc = pg_worlds_set_bodies(s->gpu, 0, c, s->rec[c], (int)n);
+      s->uploaded_records += n;
+    } else {
+      unsigned int i = 0;
+      while (i < n && rc == PG_OK) {
+        if (memcmp(&s->rec[c][i], &s->dev[c][i], sizeof(PgBody)) == 0) { i++; continue; }
+        unsigned int j = i + 1;
+        while (j < n && memcmp(&s->rec[c][j], &s->dev[c][j], sizeof(PgBody)) != 0) j++;
+        rc = pg_worlds_update_bodies(s->gpu, 0, c, (int)i, &s->rec[c][i], (int)(j - i));
+        s->uploaded_records += j - i;
+        i = j;
+      }
+    }
+    if (rc != PG_OK) {
       fprintf(stderr, "Error: physics_step: upload failed (%s)\n", pg_last_error());
+      s->dev_n[c] = -1;
       return;
     }
+    s->dev_n[c] = (int)n;
   }
   if (pg_worlds_step(s->gpu, delta_time, n_steps, refresh_nodes) != PG_OK) {
     fprintf(stderr, "Error: physics_step: launch failed (%s)\n", pg_last_error());
@@ -300,8 +326,10 @@ static void step_impl(struct PhysicsWorld *physics_world, float delta_time, int 
     if (n == 0) continue;
     if (pg_worlds_get_bodies(s->gpu, 0, c, s->rec[c], s->rec_cap[c]) != (int)n) {
       fprintf(stderr, "Error: physics_step: download failed (%s)\n", pg_last_error());
+      s->dev_n[c] = -1;
       return;
     }
+    memcpy(s->dev[c], s->rec[c], sizeof(PgBody) * (size_t)n);
     for (unsigned int i = 0; i < n; i++) {
       unflatten_state(&s->rec[c][i], &arr[i]);
       if (refresh_nodes && arr[i].scene_node) {
@@ -319,6 +347,11 @@ static void step_impl(struct PhysicsWorld *physics_world, float delta_time, int 
   if (n_events > CRUX_MAX_EVENTS) n_events = CRUX_MAX_EVENTS;
   if (overflow) fprintf(stderr, "Error: physics_step: more than %d contacts in one call, the rest are dropped\n", CRUX_MAX_EVENTS);
   if (n_events > 0) replay_events(s, n_events);
+}
+
+unsigned long long physics_world_uploaded_records(struct PhysicsWorld *world) {
+  Shadow *s = shadow_find(world, 0);
+  return s ? s->uploaded_records : 0ull;
 }
 
 /* world.c:174-555 */

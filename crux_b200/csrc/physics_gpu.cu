@@ -246,6 +246,20 @@ int pg_worlds_set_bodies(PgWorlds *w, int world, int cls, const PgBody *bodies, 
   return refresh_parallel_flag(w);
 }
 
+int pg_worlds_update_bodies(PgWorlds *w, int world, int cls, int first, const PgBody *bodies, int n) {
+  if (!valid_world(w, world) || cls < 0 || cls > 2 || first < 0 || n < 0 || (n > 0 && !bodies)) { pg_set_error("pg_worlds_update_bodies: bad argument"); return PG_ERR_ARG; }
+  if (w->mode != PG_MODE_GENERAL) { pg_set_error("handle is in sphere mode"); return PG_ERR_ARG; }
+  if (first + n > w->h_counts[world * 3 + cls]) { pg_set_error("pg_worlds_update_bodies: range [%d,%d) exceeds the class length %d", first, first + n, w->h_counts[world * 3 + cls]); return PG_ERR_ARG; }
+  if (n == 0) return PG_OK;
+  PG_CUDA(cudaSetDevice(w->device));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  PG_CUDA(cudaMemcpy(w->v.bodies[cls] + (size_t)world * w->v.cap[cls] + first, bodies, sizeof(PgBody) * (size_t)n, cudaMemcpyHostToDevice));
+  // the uploaded records can only withdraw the "statics are read-only in pass 3" licence, never grant it
+  if (cls == PG_CLASS_STATIC && !statics_read_only(bodies, n)) w->static_pass_parallel_ok = false;
+  if (cls == PG_CLASS_DYNAMIC) for (int i = 0; i < n; i++) if (bodies[i].collider_type == PG_PLANE) w->static_pass_parallel_ok = false;
+  return PG_OK;
+}
+
 int pg_worlds_add_body(PgWorlds *w, int world, const PgBody *body, int as_player) {
   if (!valid_world(w, world) || !body) { pg_set_error("pg_worlds_add_body: bad argument"); return PG_ERR_ARG; }
   if (w->mode != PG_MODE_GENERAL) { pg_set_error("handle is in sphere mode"); return PG_ERR_ARG; }

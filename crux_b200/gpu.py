@@ -32,6 +32,7 @@ API = [
     ("pg_worlds_destroy", None, [_vp]),
     ("pg_worlds_count", _i, [_vp]),
     ("pg_worlds_set_bodies", _i, [_vp, _i, _i, _vp, _i]),
+    ("pg_worlds_update_bodies", _i, [_vp, _i, _i, _i, _vp, _i]),
     ("pg_worlds_add_body", _i, [_vp, _i, _vp, _i]),
     ("pg_worlds_remove_body", _i, [_vp, _i, _i, _i]),
     ("pg_worlds_body_count", _i, [_vp, _i, _i]),
@@ -161,6 +162,11 @@ class GpuWorlds:
     def set_bodies(self, world: int, cls: int, bodies: np.ndarray):
         b = prepare(bodies)
         _check(self.L.pg_worlds_set_bodies(self.h, world, cls, _ptr(b), len(b)), "pg_worlds_set_bodies")
+
+    def update_bodies(self, world: int, cls: int, first: int, bodies: np.ndarray):
+        """Dirty-range upload: overwrite records [first, first+len(bodies)) of a class, verbatim."""
+        b = np.ascontiguousarray(bodies, dtype=BODY_DTYPE)
+        _check(self.L.pg_worlds_update_bodies(self.h, world, cls, first, _ptr(b), len(b)), "pg_worlds_update_bodies")
 
     def add_body(self, world: int, body: np.ndarray, as_player: bool = False) -> int:
         b = prepare(np.atleast_1d(body))

@@ -125,6 +125,10 @@ int  pg_worlds_count(const PgWorlds *w);
 /* Replace the bodies of one class of one world (n may be 0), records taken VERBATIM (the caller's
  * mirror is the truth, as it is for the reference's physics_step).  Order = reference array order. */
 int  pg_worlds_set_bodies(PgWorlds *w, int world, int cls, const PgBody *bodies, int n);
+/* Dirty-range upload: overwrite records [first, first+n) of one class of one world, verbatim; the
+ * class keeps its length.  This is the per-frame player write path (player.c:11-65,160-173 pokes
+ * position / rotation / velocity / at_rest of a handful of bodies between two steps). */
+int  pg_worlds_update_bodies(PgWorlds *w, int world, int cls, int first, const PgBody *bodies, int n);
 /* physics_add_body / physics_add_player: append one record applying the reference's add-time rules
  * (static velocity forced to 0, world.c:51; player restitution 0 and dynamic=false, world.c:137);
  * returns its index or <0. */

@@ -37,6 +37,17 @@ def test_scene_file_through_reference_api(tmp_path, gpu_lib, name, player, steps
         cmd.append("--device-steps")
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+    # dirty-range upload: only records the HOST changed since the device last saw
+    # them travel.  Frame by frame the scene rewrites the node matrix of every body that moved
+    # (scene_node_update), so those go up again and the static level never does; with the frames run on
+    # the device there is exactly one upload.
+    up = [int(l.split(":")[1]) for l in r.stdout.splitlines() if l.startswith("uploaded body records")]
+    assert up, r.stdout
+    ns, nd, npl = (int(x) for x in np.frombuffer(open(out, "rb").read()[:12], np.int32))
+    if device_steps:
+        assert up[0] == ns + nd + npl, (up, ns, nd, npl)
+    else:
+        assert ns + nd + npl <= up[0] <= ns + steps * (nd + npl), (up, ns, nd, npl)
     got = open(out, "rb").read()
     want = open(os.path.join(SC, f"{name}_{steps}.bin"), "rb").read()
     if got != want:
