@@ -190,6 +190,42 @@ def test_sphere_kernel_hard_worlds(gpu_lib, oracle_lib, name):
     w.close()
 
 
+def _random_world_campaign(gpu_lib, oracle_lib, n_cases, seed, steps):
+    """Random size, box, speed, radius, restitution and time step per case; bit-exact state and contact
+    order against the oracle.  Worlds of one capacity class share a handle (one kernel instance)."""
+    rng = np.random.default_rng(seed)
+    total = 0
+    for case in range(n_cases):
+        n = int(rng.choice([2, 5, 17, 32, 33, 64, 65, 100, 128, 129, 200, 256]))
+        radius = float(rng.choice([0.05, 0.15, 0.3]))
+        L = float(rng.uniform(max(1.5, 12 * radius), 12.0))
+        speed = float(rng.choice([1.0, 8.0, 40.0]))
+        restitution = float(rng.choice([1.0, 0.8, 0.3, 0.0]))
+        dt = np.float32(rng.choice([1.0 / 60.0, 0.004, 1.0e-4]))
+        pos, vel = scenes.sphere_worlds(1, n, L, first_world=10_000 * seed + case, radius=radius, speed=speed)
+        st = scenes.plane_bodies(scenes.box_planes(L))
+        w = gpu_lib.GpuWorlds(1, len(st), n, 0, max_events_per_world=65536)
+        w.set_spheres(0, st, pos, vel, radius=radius, restitution=restitution)
+        dyn = scenes.sphere_bodies(pos[0], vel[0], radius=radius, restitution=restitution)
+        o = ora.World(oracle_lib, st, dyn)
+        w.step(dt, steps)
+        o.step(dt, steps)
+        tag = (case, n, L, speed, radius, restitution, float(dt))
+        assert gen.state_equal(w.get_bodies(0, scenes.CLASS_DYNAMIC), o.read(1)), tag
+        ge, oe = _events_tuple(w.events()), _events_tuple(o.events())
+        if len(oe) > 65536:                      # more contacts than the event buffer holds: the first 65536 are kept, in order
+            assert w.events_overflowed and ge == oe[:65536], tag + (len(ge), len(oe))
+        else:
+            assert ge == oe, tag + (len(ge), len(oe))
+        total += len(ge)
+        w.close()
+    return total
+
+
+def test_sphere_kernel_random_campaign(gpu_lib, oracle_lib):
+    assert _random_world_campaign(gpu_lib, oracle_lib, n_cases=40, seed=1, steps=60) > 1000
+
+
 def test_sphere_kernel_tiny_dt(gpu_lib, oracle_lib):
     """dt below 1e-9: the closest-approach gates are switched off, the exact path alone decides."""
     pos, vel = scenes.sphere_worlds(1, 256, 4.0, first_world=77)
