@@ -327,6 +327,7 @@ int pg_worlds_set_spheres(PgWorlds *w, int first, int count, const PgBody *stati
   }
   w->mode = PG_MODE_SPHERES;
   w->v.restitution = restitution;
+  if (w->pipe_graph) { cudaGraphExecDestroy(w->pipe_graph); w->pipe_graph = nullptr; }   // the captured kernels carry the old view by value
   std::vector<float4> hp((size_t)count * w->v.cap[1]), hv((size_t)count * w->v.cap[1]), pl((size_t)count * w->v.cap[0]);
   for (int wd = 0; wd < count; wd++) {
     for (int i = 0; i < n_spheres; i++) {
