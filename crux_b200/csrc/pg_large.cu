@@ -113,6 +113,7 @@ struct LargeView {
   unsigned long long *tl_chg[2];      // smallest key of an entry that DISAPPEARED since the previous iteration (~0 = none);
                                       // new / changed entries carry a flag in tl_pos[..].w
   int *seen;                          // body already on the touched list (this step)
+  unsigned *touched_bits;             // the same as a bitmap (n/32 words): the cheap test k_eval makes for every pair
   int *touched;                       // bodies that ever received a timeline entry this step
   unsigned *cell_rank;                // rank of a body inside its cell (returned by the counting atomic)
   unsigned char *grown;               // envelope grew during the current fixed point
@@ -521,7 +522,7 @@ __device__ __forceinline__ void timeline_push(const LargeView &v, int dst, int b
     old = atomicCAS(word, assumed, assumed + (1u << sh));
   } while (old != assumed);
   if (slot >= kTimeline) { atomicExch(&v.flags->overflow_timeline, 1); return; }
-  if (slot == 0 && atomicExch(&v.seen[b], 1) == 0) v.touched[atomicAdd(&v.flags->n_touched, 1u)] = b;
+  if (slot == 0 && atomicExch(&v.seen[b], 1) == 0) { v.touched[atomicAdd(&v.flags->n_touched, 1u)] = b; atomicOr(&v.touched_bits[b >> 5], 1u << (b & 31)); }
   v.tl_key[dst][(size_t)b * kTimeline + slot] = key;
   v.tl_pos[dst][(size_t)b * kTimeline + slot] = make_float4(s.px, s.py, s.pz, 0.0f);
   v.tl_vel[dst][(size_t)b * kTimeline + slot] = make_float4(s.vx, s.vy, s.vz, 0.0f);
@@ -584,6 +585,8 @@ __global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) {
     const unsigned long long key1 = ((unsigned long long)(unsigned)i << 32) | (unsigned)j;
     const unsigned long long key2 = ((unsigned long long)(unsigned)j << 32) | (unsigned)i;
     if (iter > 0 && !fresh) {
+      // neither body has a timeline: nothing to carry, nothing that could have changed
+      if (!((v.touched_bits[i >> 5] >> (i & 31)) & 1u) && !((v.touched_bits[j >> 5] >> (j & 31)) & 1u)) continue;
       // A visit depends only on the entries with SMALLER keys of its two bodies.  If none of those
       // appeared, changed or disappeared since the previous iteration, its outcome is the recorded
       // one: carry it over instead of re-evaluating.  The second visit saw the first one's outcome
@@ -909,6 +912,7 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   PG_CUDA(cudaMemcpyAsync(v.bbox, bbox_init, sizeof(bbox_init), cudaMemcpyHostToDevice, w->stream));
   PG_CUDA(cudaMemsetAsync(v.flags, 0, sizeof(Flags), w->stream));
   PG_CUDA(cudaMemsetAsync(v.rstat, 0, sizeof(float) * 8, w->stream));
+  PG_CUDA(cudaMemsetAsync(v.touched_bits, 0, sizeof(unsigned) * ((size_t)v.n / 32 + 1), w->stream));
   LW_LAUNCH(w, K_PASS3, k_pass3, lw_grid(w, v.n, 256), 256, v, dt, w->step_in_call, 1);
   w->last_proven = 1;
   w->last_iterations = 0;
@@ -1078,6 +1082,7 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   PG_CUDA_NULL(cudaMemset(v.grown, 0, n + 8));
   PG_CUDA_NULL(cudaMalloc(&v.env_prev, sizeof(float) * n));
   PG_CUDA_NULL(cudaMalloc(&v.seen, sizeof(int) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.touched_bits, sizeof(unsigned) * (n / 32 + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.touched, sizeof(int) * n));
   PG_CUDA_NULL(cudaMalloc(&v.cell_rank, sizeof(unsigned) * n));
   for (int k = 0; k < 2; k++) {
@@ -1105,7 +1110,7 @@ void pg_large_destroy(PgLarge *w) {
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
   if (w->player_world) pg_worlds_destroy(w->player_world);
-  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.fast_list, v.block_sums, v.sorted_idx,
+  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.fast_list, v.touched_bits, v.block_sums, v.sorted_idx,
                   v.sorted_cenv, v.pairs, v.grown, v.env_prev, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
                   v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);
