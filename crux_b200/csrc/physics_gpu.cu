@@ -562,7 +562,19 @@ int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *v
   PG_CUDA(cudaMemsetAsync(w->v.n_events, 0, sizeof(int) * (size_t)nw, w->stream));
   PG_CUDA(cudaEventRecord(w->pipe_fork, w->stream));
   for (int k = 0; k < 3; k++) PG_CUDA(cudaStreamWaitEvent(w->pipe_stream[k], w->pipe_fork, 0));
-  const int per = (nw + kChunks - 1) / kChunks;
+  // Chunks shrink towards the end (weights kChunks, kChunks-1, ..., 1): what cannot overlap is the last
+  // chunk's kernels and download, after the uploads are through
+  int chunk_first[9];
+  {
+    static const bool even = getenv("PG_HOST_EVEN_CHUNKS") != nullptr;
+    const int wsum = kChunks * (kChunks + 1) / 2;
+    long long acc = 0;
+    for (int c = 0; c < kChunks; c++) {
+      chunk_first[c] = even ? (int)((long long)nw * c / kChunks) : (int)((long long)nw * acc / wsum);
+      acc += kChunks - c;
+    }
+    chunk_first[kChunks] = nw;
+  }
   {
   PG_CUDA(cudaStreamWaitEvent(w->pipe_up, w->pipe_fork, 0));
   // Three queues: uploads (H2D engine), compute (pack / step / unpack, three streams round robin),
@@ -570,8 +582,8 @@ int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *v
   // kernels; a download never sits behind an upload in the same stream, so both copy engines and
   // the SMs run at the same time (PCIe is full duplex: 26 MB each way take 0.55 ms together).
   for (int c = 0; c < kChunks; c++) {
-    const int first = c * per, count = std::min(per, nw - first);
-    if (count <= 0) break;
+    const int first = chunk_first[c], count = chunk_first[c + 1] - first;
+    if (count <= 0) continue;
     cudaStream_t st = w->pipe_stream[c % 3];
     const size_t off = (size_t)first * n, bodies = (size_t)count * n;
     PG_CUDA(cudaMemcpyAsync(w->d_stage_pos + 3 * off, pos + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyHostToDevice, w->pipe_up));
