@@ -297,7 +297,7 @@ __global__ void k_grid_params(LargeView v) {
   *v.robust = rb;
   // cell edge: two envelopes (one per body of a pair) with 25 % head room for envelopes that grow
   float h = 2.0f * e_cap * 1.25f + 1.0e-6f;
-  if (!(h > 0.0f) || !(h < 1.0e15f) || !(lo[0] <= hi[0])) { g.ok = 0; h = 1.0f; lo[0] = lo[1] = lo[2] = 0.0f; hi[0] = hi[1] = hi[2] = 0.0f; }
+  if (!(h > 0.0f) || !(h < 1.0e15f) || !(lo[0] <= hi[0])) { g.ok = 0; v.flags->unsafe = 1; h = 1.0f; lo[0] = lo[1] = lo[2] = 0.0f; hi[0] = hi[1] = hi[2] = 0.0f; }
   for (;;) {
     double cells = 1.0;
     for (int k = 0; k < 3; k++) {
@@ -857,12 +857,9 @@ static int lw_build_pairs(PgLarge *w) {
   PG_CUDA(cudaMemsetAsync(v.cell_cnt, 0, sizeof(unsigned) * ((size_t)v.cells_cap + 1), w->stream));
   PG_CUDA(cudaMemsetAsync(&v.flags->n_pairs, 0, sizeof(unsigned long long), w->stream));
   LW_LAUNCH(w, K_CELLS, k_cell_count, lw_grid(w, v.n, 256), 256, v);
-  GridParams g;
-  PG_CUDA(cudaMemcpyAsync(&g, v.grid, sizeof(g), cudaMemcpyDeviceToHost, w->stream));
-  PG_CUDA(cudaStreamSynchronize(w->stream));
-  lw_accumulate(w, K_CELLS);
-  if (!g.ok) { pg_set_error("large world: non-finite state, grid cannot be built"); return PG_ERR_ARG; }
-  const int scan_blocks = (g.n_cells + 1 + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems);
+  // no read-back of the grid: the scan is launched for the largest table the buffers hold (blocks past
+  // n_cells see zeros), and a grid that could not be built raises flags->unsafe for the next read-back
+  const int scan_blocks = (v.cells_cap + 1 + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems);
   cudaEventRecord(w->kev[K_SCAN][0], w->stream);
   k_scan_local<<<scan_blocks, kScanBlock, 0, w->stream>>>(v);
   k_scan_sums<<<1, 1024, 0, w->stream>>>(v, scan_blocks);
@@ -922,7 +919,7 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   Flags f;
   rc = lw_read_flags(w, &f);            // pair count: sizes the eval grid, detects overflow
   if (rc) return rc;
-  lw_accumulate(w, K_PASS3); lw_accumulate(w, K_SCAN); lw_accumulate(w, K_SCATTER); lw_accumulate(w, K_PAIRS);
+  lw_accumulate(w, K_PASS3); lw_accumulate(w, K_CELLS); lw_accumulate(w, K_SCAN); lw_accumulate(w, K_SCATTER); lw_accumulate(w, K_PAIRS);
   if (f.overflow_pairs) {
     // k_pairs is a pure function of the grid: grow the buffer and run it again
     rc = lw_grow_pairs(w, f.n_pairs, 0);
@@ -938,62 +935,66 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   const bool debug = getenv("PG_LARGE_DEBUG") != nullptr;
   bool converged = false;
   int requeries = 0;
+  // One host read-back per iteration: k_requery always rides along (it returns at once for bodies whose
+  // envelope did not grow), its bookkeeping kernel is deferred to the start of the next iteration so
+  // that an overflowing candidate list can still be grown and the append repeated.
+  bool requery_pending = false;
+  const int wide_grid = w->sm_count * 8;
   for (int it = 0; it < kMaxIter; it++) {
-    const int nt_grid = lw_grid(w, std::max((int)f.n_touched, 1), 256);
-    k_clear<<<nt_grid, 256, 0, w->stream>>>(v, dst);
+    if (requery_pending) {
+      k_requery_done<<<wide_grid, 256, 0, w->stream>>>(v);
+      w->launches++;
+      requery_pending = false;
+    }
+    k_clear<<<wide_grid, 256, 0, w->stream>>>(v, dst);
     w->launches++;
     PG_CUDA(cudaMemsetAsync(&v.flags->changed, 0, sizeof(int), w->stream));
     PG_CUDA(cudaMemsetAsync(&v.flags->grew, 0, sizeof(int), w->stream));
     PG_CUDA(cudaMemsetAsync(&v.flags->n_hits, 0, sizeof(unsigned long long), w->stream));
-    const int np = (int)std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
+    const unsigned long long pairs_before = std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
+    const int np = (int)std::min<unsigned long long>(pairs_before, 0x7fffffffull);
     LW_LAUNCH(w, K_EVAL, k_eval, lw_grid(w, std::max(np, 1), 128), 128, v, src, dst, it, dt);
-    LW_LAUNCH(w, K_CHECK, k_check, lw_grid(w, std::max(np, 1), 256), 256, v, src, dst, dt);
+    LW_LAUNCH(w, K_CHECK, k_check, wide_grid, 256, v, src, dst, dt);
+    // candidates the grown envelopes add (on top of the NEW timelines); their bodies are marked dirty so
+    // the next iteration re-evaluates them (warm start)
+    LW_LAUNCH(w, K_BOUNDS, k_requery, wide_grid, 128, v, dst);
     rc = lw_read_flags(w, &f);
     if (rc) return rc;
-    lw_accumulate(w, K_EVAL); lw_accumulate(w, K_CHECK);
+    lw_accumulate(w, K_EVAL); lw_accumulate(w, K_CHECK); lw_accumulate(w, K_BOUNDS);
     if (debug) {
-      float e = 0, c = 0;
+      float e = 0, c = 0, rq = 0;
       cudaEventElapsedTime(&e, w->kev[K_EVAL][0], w->kev[K_EVAL][1]);
       cudaEventElapsedTime(&c, w->kev[K_CHECK][0], w->kev[K_CHECK][1]);
-      fprintf(stderr, "  [pg_large] iter %d: eval %.3f ms check %.3f ms hits %llu changed %d grew %d pairs %llu touched %u fast %u\n", it, e, c,
-              (unsigned long long)f.n_hits, f.changed, f.grew, (unsigned long long)f.n_pairs, f.n_touched, f.n_fast);
+      cudaEventElapsedTime(&rq, w->kev[K_BOUNDS][0], w->kev[K_BOUNDS][1]);
+      fprintf(stderr, "  [pg_large] iter %d: eval %.3f ms check %.3f ms requery %.3f ms hits %llu changed %d grew %d pairs %llu -> %llu touched %u fast %u\n",
+              it, e, c, rq, (unsigned long long)f.n_hits, f.changed, f.grew, pairs_before, (unsigned long long)f.n_pairs, f.n_touched, f.n_fast);
     }
     w->last_iterations++;
     w->last_hits = (long long)f.n_hits;
     if (f.overflow_timeline) { pg_set_error("large world: more than %d contacts on one body in one step", kTimeline); return PG_ERR_CAPACITY; }
     std::swap(src, dst);
     if (f.grew) {
-      // candidates the grown envelopes add; their bodies are marked dirty so the next iteration
-      // re-evaluates them on top of the current timelines (warm start)
-      const unsigned long long pairs_before = std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
-      const int touched_now = std::max((int)f.n_touched, 1);
-      LW_LAUNCH(w, K_BOUNDS, k_requery, lw_grid(w, std::min(touched_now, 1 << 24) * 32, 128), 128, v, src);
-      rc = lw_read_flags(w, &f);
-      if (rc) return rc;
-      lw_accumulate(w, K_BOUNDS);
       if (f.overflow_pairs) {
         // k_requery only appends: keep the list as it was, make room, and let it append again
         rc = lw_grow_pairs(w, f.n_pairs, pairs_before);
         if (rc) return rc;
-        LW_LAUNCH(w, K_BOUNDS, k_requery, lw_grid(w, std::min(touched_now, 1 << 24) * 32, 128), 128, v, src);
+        LW_LAUNCH(w, K_BOUNDS, k_requery, wide_grid, 128, v, src);
         rc = lw_read_flags(w, &f);
         if (rc) return rc;
         lw_accumulate(w, K_BOUNDS);
         if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
       }
-      if (debug) {
-        float rq = 0;
-        cudaEventElapsedTime(&rq, w->kev[K_BOUNDS][0], w->kev[K_BOUNDS][1]);
-        fprintf(stderr, "  [pg_large] requery %.3f ms: pairs %llu -> %llu, fast %u\n", rq, pairs_before, (unsigned long long)f.n_pairs, f.n_fast);
-      }
-      k_requery_done<<<lw_grid(w, touched_now, 256), 256, 0, w->stream>>>(v);
-      w->launches++;
+      requery_pending = true;
       if (f.unsafe) { w->last_proven = 0; if (debug) fprintf(stderr, "  [pg_large] envelope outgrew the grid: result not proven\n"); }
       w->last_candidates = (long long)f.n_pairs;
       requeries++;
       continue;                           // at least one more iteration with the new pairs
     }
     if (!f.changed) { converged = true; break; }
+  }
+  if (requery_pending) {
+    k_requery_done<<<wide_grid, 256, 0, w->stream>>>(v);
+    w->launches++;
   }
   if (!converged) w->last_proven = 0;
   (void)requeries;
@@ -1349,6 +1350,7 @@ long long pg_large_pairs(PgLarge *w, float dt_in, int32_t *out_ij, long long cap
   Flags f;
   rc = lw_read_flags(w, &f);
   if (rc) return rc;
+  if (f.unsafe) { pg_set_error("large world: non-finite state, grid cannot be built"); return PG_ERR_ARG; }
   if (f.overflow_pairs) { pg_set_error("pg_large_pairs: candidate buffer too small"); return PG_ERR_CAPACITY; }
   const long long np = (long long)f.n_pairs;
   if (np == 0) return 0;
