@@ -439,8 +439,8 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
       for (int k = 0; k < CPT; k++) { WS[k * 32 + lane] = W[k]; S.W0[k * 32 + lane] = W[k]; }
       __syncwarp();
       // --- closest-approach gate of every surviving (row, column) bit, one pair per lane: the bits
-      // are compacted into a list (k, lane, rl) and gated 32 at a time.  More than kGateList bits in
-      // one block (a dense pile): the rows gate their own candidates instead (`fresh` below).
+      // are compacted into a list (k, lane, rl), kGateList at a time, and gated 32 at a time.  With a
+      // time step too small for the gate to mean anything the rows filter for themselves (`fresh`).
       bool gated = false;
       int cnt = 0;
 #pragma unroll
