@@ -200,6 +200,7 @@ struct WarpSmem {
   unsigned list[kGateList];
   unsigned rest[CPT];                       // at-rest flags by actual slot, bit = lane
   int chg[kMaxRowChanges];
+  int n_list;                                      // gate list allocation counter (zero between uses)
 };
 
 template <int CPT, int MAXW>
@@ -247,6 +248,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
   pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
 
   if (lane < ns) S.planes[lane] = v.planes[(size_t)w * v.cap[0] + lane];
+  if (lane == 0) S.n_list = 0;
 
   unsigned rest = 0;                       // bit s: this lane's body of actual slot s is at rest
   const size_t base = (size_t)w * v.cap[1];
@@ -445,21 +447,26 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
       int cnt = 0;
 #pragma unroll
       for (int k = 0; k < CPT; k++) cnt += __popc(W[k]);
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(kFull, incl, o); if (lane >= o) incl += t; }
-      const int total = __shfl_sync(kFull, incl, 31);
+      // list positions are handed out by a shared-memory counter (the order of the list is irrelevant)
+      int first = 0;
+      if (cnt) first = atomicAdd(&S.n_list, cnt);
+      __syncwarp();
+      const int total = S.n_list;
+      __syncwarp();
+      if (lane == 0) S.n_list = 0;
       if (dt > 1.0e-9f) {
         gated = true;
         unsigned *list = S.list;
-        // list windows of kGateList bits: each lane knows the global index of its first bit (prefix sum)
+        // windows of kGateList bits (one, unless the block sits in a pile)
 #pragma unroll 1
         for (int base = 0; base < total; base += kGateList) {
-          int pos = incl - cnt - base;
+          if (cnt) {
+            int pos = first - base;
 #pragma unroll 1
-          for (int k = 0; k < CPT && pos < kGateList; k++) {
-            for (unsigned word = S.W0[k * 32 + lane]; word; word &= word - 1u, pos++)
-              if (pos >= 0 && pos < kGateList) list[pos] = (unsigned)k | ((unsigned)lane << 8) | ((unsigned)(__ffs((int)word) - 1) << 16);
+            for (int k = 0; k < CPT && pos < kGateList; k++) {
+              for (unsigned word = S.W0[k * 32 + lane]; word; word &= word - 1u, pos++)
+                if (pos >= 0 && pos < kGateList) list[pos] = (unsigned)k | ((unsigned)lane << 8) | ((unsigned)(__ffs((int)word) - 1) << 16);
+            }
           }
           __syncwarp();
           const int m = min(kGateList, total - base);
@@ -478,7 +485,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
       unsigned rows_any = 0;
       if (total > 0) {
         unsigned any = 0;
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < CPT; k++) any |= WS[k * 32 + lane];
         rows_any = __reduce_or_sync(kFull, any);
       }
@@ -501,7 +508,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
         const int i = row0 + rl;
         commit_to(i);
         unsigned mask = 0;
-#pragma unroll 1
+#pragma unroll
         for (int k = 0; k < CPT; k++) mask |= ((WS[k * 32 + lane] >> rl) & 1u) << k;
         // static slot k is actual slot (rb + k) mod CPT: rotate the bits into column order
         const unsigned amask = ((mask << rb) | (mask >> ((CPT - rb) & 31))) & full;
@@ -523,7 +530,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
             __syncwarp();
           }
           unsigned any = 0;
-#pragma unroll 1
+#pragma unroll
           for (int k = 0; k < CPT; k++) any |= WS[k * 32 + lane];
           rows_any = (__reduce_or_sync(kFull, any) | dirty_rows) & later;
         } else {
