@@ -358,7 +358,12 @@ unsigned long long physics_world_uploaded_records(struct PhysicsWorld *world) {
 void physics_step(struct PhysicsWorld *physics_world, float delta_time) { step_impl(physics_world, delta_time, 1, 0); }
 
 void physics_step_n(struct PhysicsWorld *physics_world, float delta_time, int n_steps) {
-  if (n_steps > 0) step_impl(physics_world, delta_time, n_steps, 1);
+  /* in chunks, so that the contact list of one device call (CRUX_MAX_EVENTS) is replayed before it can fill up */
+  while (n_steps > 0) {
+    const int k = n_steps < 16 ? n_steps : 16;
+    step_impl(physics_world, delta_time, k, 1);
+    n_steps -= k;
+  }
 }
 
 /* ------------------------------------------------------------------ public predicates (world.h:47-50) */
