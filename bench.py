@@ -249,14 +249,22 @@ def run_large_arm(args, cfg):
         torch.cuda.synchronize()
         world.step(dt, 1)
         ev_ms += world.last_step_ms()
-        for k, v in world.kernel_ms().items():
-            kms[k] = kms.get(k, 0.0) + v
         ex = world.exactness()
         iters.append(ex["iterations"])
         proven = proven and ex["proven_exact"]
     barrier()
     clocks = sampler.stop()
     gpu_launches = world.launches - launches0
+    # per-kernel breakdown: a few more steps AFTER the timed region with the library's per-kernel event pairs
+    # switched on (they are off by default: they double the API calls of a launch-bound pipeline)
+    breakdown_steps = min(8, args.steps)
+    world.set_timing(True)
+    for _ in range(breakdown_steps):
+        world.step(dt, 1)
+        for k, v in world.kernel_ms().items():
+            kms[k] = kms.get(k, 0.0) + v
+    world.set_timing(False)
+    kms = {k: v * args.steps / breakdown_steps for k, v in kms.items()}      # scaled to the timed region's step count
     t = torch.tensor([ev_ms], dtype=torch.float64, device="cuda")
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

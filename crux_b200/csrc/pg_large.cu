@@ -675,6 +675,7 @@ __global__ void k_check(LargeView v, int src, int dst, float dt) {
 // reset the destination timelines of the touched bodies before an iteration refills them
 __global__ void k_clear(LargeView v, int dst) {
   const int nt = (int)v.flags->n_touched;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { v.flags->changed = 0; v.flags->grew = 0; v.flags->n_hits = 0ull; }
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) v.tl_cnt[dst][v.touched[t]] = 0;
 }
 
@@ -832,19 +833,22 @@ struct PgLarge {
   int cap_static_total;
   long long last_candidates, last_hits;
   int step_in_call;
+  int timing;                    // record a CUDA event pair around every kernel (pg_large_kernel_ms); off by default:
+                                 // the pipeline of a small world is launch-bound and the events double its API calls
 };
 
 #define LW_LAUNCH(w, kid, kern, grid, block, ...)                                 \
   do {                                                                            \
-    cudaEventRecord((w)->kev[kid][0], (w)->stream);                               \
+    if ((w)->timing) cudaEventRecord((w)->kev[kid][0], (w)->stream);              \
     kern<<<(grid), (block), 0, (w)->stream>>>(__VA_ARGS__);                       \
-    cudaEventRecord((w)->kev[kid][1], (w)->stream);                               \
+    if ((w)->timing) cudaEventRecord((w)->kev[kid][1], (w)->stream);              \
     (w)->launches++;                                                              \
   } while (0)
 
 static int lw_grid(const PgLarge *w, int n, int block) { return std::max(1, std::min((n + block - 1) / block, w->sm_count * 8)); }
 
 static void lw_accumulate(PgLarge *w, int kid) {
+  if (!w->timing) return;
   float ms = 0.0f;
   if (cudaEventElapsedTime(&ms, w->kev[kid][0], w->kev[kid][1]) == cudaSuccess) w->kms[kid] += ms;
 }
@@ -860,11 +864,11 @@ static int lw_build_pairs(PgLarge *w) {
   // no read-back of the grid: the scan is launched for the largest table the buffers hold (blocks past
   // n_cells see zeros), and a grid that could not be built raises flags->unsafe for the next read-back
   const int scan_blocks = (v.cells_cap + 1 + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems);
-  cudaEventRecord(w->kev[K_SCAN][0], w->stream);
+  if (w->timing) cudaEventRecord(w->kev[K_SCAN][0], w->stream);
   k_scan_local<<<scan_blocks, kScanBlock, 0, w->stream>>>(v);
   k_scan_sums<<<1, 1024, 0, w->stream>>>(v, scan_blocks);
   k_scan_add<<<scan_blocks, kScanBlock, 0, w->stream>>>(v);
-  cudaEventRecord(w->kev[K_SCAN][1], w->stream);
+  if (w->timing) cudaEventRecord(w->kev[K_SCAN][1], w->stream);
   w->launches += 3;
   LW_LAUNCH(w, K_SCATTER, k_scatter, lw_grid(w, v.n, 256), 256, v);
   LW_LAUNCH(w, K_PAIRS, k_pairs, lw_grid(w, v.n, 128), 128, v);
@@ -932,7 +936,7 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   }
   if (f.unsafe) { pg_set_error("large world: non-finite body state"); return PG_ERR_ARG; }
   w->last_candidates = (long long)f.n_pairs;
-  const bool debug = getenv("PG_LARGE_DEBUG") != nullptr;
+  const bool debug = getenv("PG_LARGE_DEBUG") != nullptr && w->timing;
   bool converged = false;
   int requeries = 0;
   // One host read-back per iteration: k_requery always rides along (it returns at once for bodies whose
@@ -946,11 +950,8 @@ static int lw_step_once(PgLarge *w, float dt_in) {
       w->launches++;
       requery_pending = false;
     }
-    k_clear<<<wide_grid, 256, 0, w->stream>>>(v, dst);
+    k_clear<<<wide_grid, 256, 0, w->stream>>>(v, dst);      // also resets the per-iteration flags
     w->launches++;
-    PG_CUDA(cudaMemsetAsync(&v.flags->changed, 0, sizeof(int), w->stream));
-    PG_CUDA(cudaMemsetAsync(&v.flags->grew, 0, sizeof(int), w->stream));
-    PG_CUDA(cudaMemsetAsync(&v.flags->n_hits, 0, sizeof(unsigned long long), w->stream));
     const unsigned long long pairs_before = std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
     const int np = (int)std::min<unsigned long long>(pairs_before, 0x7fffffffull);
     LW_LAUNCH(w, K_EVAL, k_eval, lw_grid(w, std::max(np, 1), 128), 128, v, src, dst, it, dt);
@@ -1037,6 +1038,7 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   if (max_spheres <= 0 || max_static < 0 || max_static > (1 << 22)) { pg_set_error("pg_large_create: bad argument"); return nullptr; }
   PG_CUDA_NULL(cudaSetDevice(device));
   PgLarge *w = new PgLarge();
+  w->timing = getenv("PG_LARGE_TIMING") != nullptr || getenv("PG_LARGE_DEBUG") != nullptr;
   memset(w, 0, sizeof(*w));
   w->device = device;
   w->cap_n = max_spheres;
@@ -1457,6 +1459,11 @@ float pg_large_last_step_ms(PgLarge *w) {
 int pg_large_kernel_count(void) { return K_COUNT; }
 const char *pg_large_kernel_name(int k) { return (k >= 0 && k < K_COUNT) ? kKernelNames[k] : ""; }
 float pg_large_kernel_ms(PgLarge *w, int k) { return (w && k >= 0 && k < K_COUNT) ? w->kms[k] : -1.0f; }
+int pg_large_set_timing(PgLarge *w, int on) {
+  if (!w) return PG_ERR_ARG;
+  w->timing = on ? 1 : 0;
+  return PG_OK;
+}
 
 int pg_large_exactness(PgLarge *w, int *iterations, int *proven_exact, long long *candidates, long long *hits) {
   if (!w) return PG_ERR_ARG;

@@ -65,6 +65,7 @@ API = [
     ("pg_large_kernel_count", _i, []),
     ("pg_large_kernel_name", C.c_char_p, [_i]),
     ("pg_large_kernel_ms", _f, [_vp, _i]),
+    ("pg_large_set_timing", _i, [_vp, _i]),
     ("pg_large_exactness", _i, [_vp, _vp, _vp, _vp, _vp]),
     ("pg_pair_max_move", _i, [_vp, _i, _f, _f, _vp]),
     ("pg_pair_min_dist", _i, [_vp, _vp, _i, _vp, _vp]),
@@ -368,6 +369,10 @@ class GpuLargeWorld:
         ca, hi = C.c_longlong(0), C.c_longlong(0)
         _check(self.L.pg_large_exactness(self.h, C.byref(it), C.byref(pr), C.byref(ca), C.byref(hi)), "pg_large_exactness")
         return {"iterations": it.value, "proven_exact": bool(pr.value), "candidates": ca.value, "hits": hi.value}
+
+    def set_timing(self, on: bool):
+        """Per-kernel CUDA-event timing (kernel_ms) is off by default; it costs an event pair per launch."""
+        _check(self.L.pg_large_set_timing(self.h, int(on)), "pg_large_set_timing")
 
     def kernel_ms(self) -> dict:
         return {self.L.pg_large_kernel_name(k).decode(): float(self.L.pg_large_kernel_ms(self.h, k))

@@ -207,6 +207,9 @@ float pg_large_last_step_ms(PgLarge *w);
 int  pg_large_kernel_count(void);
 const char *pg_large_kernel_name(int k);
 float pg_large_kernel_ms(PgLarge *w, int k);
+/* Per-kernel timing costs a CUDA event pair around every launch and is OFF by default (a small world's
+ * pipeline is launch-bound); switch it on before the steps whose pg_large_kernel_ms you want. */
+int  pg_large_set_timing(PgLarge *w, int on);
 /* Fixed-point statistics of the last step: iterations used, 1 if the step is proven identical to
  * the sequential reference order, candidate-visit and hit counts. */
 int  pg_large_exactness(PgLarge *w, int *iterations, int *proven_exact, long long *candidates, long long *hits);

@@ -8,6 +8,7 @@ n, L = 1048576, 160.0
 statics, p0, v0, players = scenes.level_world(n, L, seed_world=0, with_player=False)
 g = gpu.GpuLargeWorld(n, len(statics))
 g.set(gpu.prepare(statics), p0, v0)
+g.set_timing(True)
 for s in range(24):
     g.step(scenes.DT_60HZ, 1)
     km = g.kernel_ms()

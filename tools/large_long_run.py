@@ -16,6 +16,7 @@ P, V, R = g.download_state()
 print("after", skip, "steps: at rest", int((R != 0).sum()), "y range", float(P[:, 1].min()), float(P[:, 1].max()),
       "max speed", float(np.linalg.norm(V, axis=1).max()), "bodies below the floor", int((P[:, 1] < -1).sum()))
 os.environ["PG_LARGE_DEBUG"] = "1"
+g.set_timing(True)
 for s in range(2):
     g.step(scenes.DT_60HZ, 1)
     print("step", skip + s, "ms", round(g.last_step_ms(), 3), {k: round(v, 3) for k, v in g.kernel_ms().items()}, g.exactness())
