@@ -1,9 +1,10 @@
-"""Developer tool: a long random parity campaign of the sphere kernel against the oracle (the committed test
-runs 40 cases; this runs as many as asked: `python tools/random_campaign.py 800 80`)."""
+"""Test infrastructure (not collected by pytest): a long random parity campaign of the sphere kernel against the
+oracle.  The suite runs 40 cases (test_gpu_worlds.py); this runs as many as asked on a GPU box:
+`python tests/random_campaign.py 800 80`."""
 import os
 import sys
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..")); sys.path.insert(0, HERE)
 import ora
 from crux_b200 import gpu
 import test_gpu_worlds as t
