@@ -542,7 +542,6 @@ __device__ __forceinline__ bool eval_visit(const LargeView &v, int src, int dst,
   if (!pgs::sphere_pair_exact(A, B, dt, leaf)) return false;
   timeline_push(v, dst, row, key, A);
   timeline_push(v, dst, col, key, B);
-  atomicAdd(&v.flags->n_hits, 1ull);
   if (out_row) { out_row->key = key; out_row->present = true; out_row->px = A.px; out_row->py = A.py; out_row->pz = A.pz; out_row->vx = A.vx; out_row->vy = A.vy; out_row->vz = A.vz; }
   if (out_col) { out_col->key = key; out_col->present = true; out_col->px = B.px; out_col->py = B.py; out_col->pz = B.pz; out_col->vx = B.vx; out_col->vy = B.vy; out_col->vz = B.vz; }
   return true;
@@ -577,6 +576,7 @@ __device__ __forceinline__ bool affected(const LargeView &v, int src, int b, uns
 __global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) {
   pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
   const long long np = (long long)min((unsigned long long)v.pairs_cap, v.flags->n_pairs);
+  unsigned my_hits = 0;
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < np; k += (long long)gridDim.x * blockDim.x) {
     const int2 pr = v.pairs[k];
     const bool fresh = pr.x < 0;                     // appended by k_requery: never evaluated yet
@@ -594,12 +594,12 @@ __global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) {
       const bool need1 = affected(v, src, i, key1, 0ull) || affected(v, src, j, key1, 0ull);
       if (!need1) {
         const bool have_i = v.tl_cnt[src][i] != 0, have_j = v.tl_cnt[src][j] != 0;
-        if (have_i && have_j && carry_entry(v, src, dst, i, key1)) { carry_entry(v, src, dst, j, key1); atomicAdd(&v.flags->n_hits, 1ull); }
+        if (have_i && have_j && carry_entry(v, src, dst, i, key1)) { carry_entry(v, src, dst, j, key1); my_hits++; }
         const bool need2 = affected(v, src, i, key2, key1) || affected(v, src, j, key2, key1);
         if (!need2) {
-          if (have_i && have_j && carry_entry(v, src, dst, i, key2)) { carry_entry(v, src, dst, j, key2); atomicAdd(&v.flags->n_hits, 1ull); }
+          if (have_i && have_j && carry_entry(v, src, dst, i, key2)) { carry_entry(v, src, dst, j, key2); my_hits++; }
         } else {
-          eval_visit(v, src, dst, j, i, dt, leaf, 0ull, nullptr, nullptr, nullptr, nullptr);
+          my_hits += eval_visit(v, src, dst, j, i, dt, leaf, 0ull, nullptr, nullptr, nullptr, nullptr) ? 1u : 0u;
         }
         continue;
       }
@@ -607,9 +607,12 @@ __global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) {
     // visit (i, j) of row i, then visit (j, i) of row j on top of the first one's fresh outcome
     Override oi, oj;
     oi.present = false; oj.present = false; oi.key = key1; oj.key = key1;
-    eval_visit(v, src, dst, i, j, dt, leaf, 0ull, nullptr, nullptr, &oi, &oj);
-    eval_visit(v, src, dst, j, i, dt, leaf, key1, &oj, &oi, nullptr, nullptr);
+    my_hits += eval_visit(v, src, dst, i, j, dt, leaf, 0ull, nullptr, nullptr, &oi, &oj) ? 1u : 0u;
+    my_hits += eval_visit(v, src, dst, j, i, dt, leaf, key1, &oj, &oi, nullptr, nullptr) ? 1u : 0u;
   }
+  // one atomic per warp for the hit statistic (a single hot address otherwise)
+  my_hits = __reduce_add_sync(kFullMask, my_hits);
+  if ((threadIdx.x & 31) == 0 && my_hits) atomicAdd(&v.flags->n_hits, (unsigned long long)my_hits);
 }
 
 // Compare the timelines of two iterations (as sets keyed by visit) and validate envelopes, for the

@@ -688,12 +688,13 @@ __global__ void k_order_worlds(const unsigned *cost, int n_worlds, int *order) {
 
 template <int CPT, int MAXW>
 static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter) {
-  static bool configured = false;
+  static bool configured[64] = {false};      // function attributes are per device
   constexpr size_t warp_bytes = sizeof(WarpSmem<CPT>);
-  if (!configured) {
+  const int dev = w->device >= 0 && w->device < 64 ? w->device : 0;
+  if (!configured[dev] || w->device >= 64) {
     cudaFuncSetAttribute(k_step_spheres<CPT, MAXW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_step_spheres<CPT, MAXW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(warp_bytes * MAXW));
-    configured = true;
+    configured[dev] = true;
   }
   if (count <= 0) return PG_OK;              // configuration only (callers about to capture a graph)
   // One block per SM.  The fewest waves of (SMs x MAXW) worlds that hold the batch, then the fewest
