@@ -574,11 +574,8 @@ __global__ void k_stats_spheres(WorldsView v, double *out, double *out2) {
     const bool fin = isfinite(a.x) && isfinite(a.y) && isfinite(a.z) && isfinite(b.x) && isfinite(b.y) && isfinite(b.z);
     acc[7] += fin ? 0.0 : 1.0;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    long long ev = 0;
-    for (int w = 0; w < v.n_worlds; w++) ev += v.n_events[w];
-    acc[5] += (double)ev;
-  }
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < v.n_worlds; w += (long long)gridDim.x * blockDim.x)
+    acc[5] += (double)v.n_events[w];
 #pragma unroll
   for (int q = 0; q < 8; q++) {
     double x = acc[q];
@@ -602,11 +599,8 @@ __global__ void k_stats_general(WorldsView v, double *out, double *out2) {
     for (int q = 0; q < 3; q++) fin = fin && isfinite(b.position[q]) && isfinite(b.velocity[q]);
     acc[7] += fin ? 0.0 : 1.0;
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    long long ev = 0;
-    for (int w = 0; w < v.n_worlds; w++) ev += v.n_events[w];
-    acc[5] += (double)ev;
-  }
+  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < v.n_worlds; w += (long long)gridDim.x * blockDim.x)
+    acc[5] += (double)v.n_events[w];
 #pragma unroll
   for (int q = 0; q < 8; q++) {
     double x = acc[q];
