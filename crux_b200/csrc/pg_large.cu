@@ -30,6 +30,8 @@
 #include "pg_math.cuh"
 #include "pg_sphere_exact.cuh"
 
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -74,8 +76,14 @@ struct Flags {
   unsigned long long n_hits;
   unsigned n_touched;
   unsigned n_fast;        // bodies on the fast list
-  float max_env_bits_pad;
+  unsigned n_active;      // candidate pairs k_select handed to k_eval this iteration
+  unsigned n_hard;        // of those, pairs k_eval passed on to k_eval_hard (long interval searches)
 };
+
+// One body of the cell-ordered copy.  A whole 32-byte sector per body: the counting sort's scattered
+// store then never leaves a partial sector behind (16 B + 4 B stores into shared sectors made the L2
+// fetch the rest from DRAM: 2.6x the algorithmic traffic), and a reader gets the index with the centre.
+struct __align__(32) SortedBody { float4 cenv; unsigned idx, pad0, pad1, pad2; };
 
 struct LargeView {
   int n, ns;
@@ -103,11 +111,12 @@ struct LargeView {
   unsigned *cell_cnt;                // [cells_cap + 1]  counts -> exclusive starts
   unsigned *block_sums;              // scan scratch
   int cells_cap;
-  unsigned *sorted_idx;              // [n]
-  float4 *sorted_cenv;               // [n]  centre xyz, env
+  SortedBody *sorted;                // [n]  bodies in cell order: centre xyz, env, body index -- one 32-byte sector each
   // candidates
   int2 *pairs;
   long long pairs_cap;
+  unsigned *active;                  // [2 pairs_cap] indices into pairs[]: the ones this iteration has to look at (k_select), and from
+                                     // pairs_cap on the ones k_eval deferred to k_eval_hard
   // timelines, double buffered
   unsigned char *tl_cnt[2];
   unsigned long long *tl_chg[2];      // smallest key of an entry that DISAPPEARED since the previous iteration (~0 = none);
@@ -398,8 +407,9 @@ __global__ void k_scatter(LargeView v) {
     const unsigned cell = v.cell_of[i];
     const unsigned slot = v.cell_cnt[cell] + v.cell_rank[i];
     const float4 p = v.pos_rest[i];
-    v.sorted_idx[slot] = (unsigned)i;
-    v.sorted_cenv[slot] = make_float4(p.x, p.y, p.z, v.env[i]);
+    const float e = v.env[i];
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(v.sorted + slot), "r"(__float_as_uint(p.x)), "r"(__float_as_uint(p.y)),
+                 "r"(__float_as_uint(p.z)), "r"(__float_as_uint(e)), "r"((unsigned)i), "r"(0u), "r"(0u), "r"(0u) : "memory");
   }
 }
 
@@ -409,60 +419,104 @@ __global__ void k_scatter(LargeView v) {
 // grid was sized for (27 cells = 9 contiguous x-runs), more for the few fast bodies, and the whole
 // sorted array for a body so fast that its search would cover most of the grid anyway.
 constexpr int kMaxSearch = 12;
-__global__ void k_pairs(LargeView v) {
+constexpr int kPairsBlock = 128;
+constexpr int kPairsStage = 1024;       // pairs a block collects in shared memory between two flushes
+// One thread per body (in cell order, so neighbouring threads read neighbouring cells); every thread
+// walks its own cell runs without warp votes.  Two bodies the grid was sized for (R = 1 both) lie in the
+// same or in adjacent cells, so each of them searches only the HALF shell of cells that follow its own
+// in cell order (the rest of its own x-run, the next y-row, the three rows of the next z-layer: 5 runs,
+// 13.5 cells instead of 27) and lists whatever it finds there; a body with a larger envelope searches
+// its whole neighbourhood and lists the partners whose envelope is smaller (ties: lower index), and an
+// R = 1 body leaves such partners to them.  Pairs are staged in shared memory and appended to the global
+// list once per tile of kPairsBlock bodies; a tile that finds more than kPairsStage pairs (a dense pile)
+// appends the surplus directly.
+__global__ void __launch_bounds__(kPairsBlock) k_pairs(LargeView v) {
+  __shared__ int2 s_pairs[kPairsStage];
+  __shared__ unsigned s_cnt;
+  __shared__ unsigned long long s_base;
   const GridParams g = *v.grid;
-  const int lane = threadIdx.x & 31;
-  for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < ((v.n + 31) & ~31); a += gridDim.x * blockDim.x) {
-    const bool live = a < v.n;
-    float4 ca = make_float4(0, 0, 0, 0);
-    unsigned ia = 0;
-    int3 c = make_int3(0, 0, 0);
-    int R = 0;
-    bool everything = false;
-    if (live) {
-      ca = v.sorted_cenv[a]; ia = v.sorted_idx[a]; c = cell_coords(g, ca.x, ca.y, ca.z);
+  const int n_tiles = (v.n + kPairsBlock - 1) / kPairsBlock;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int a = tile * kPairsBlock + threadIdx.x;
+    if (a < v.n) {
+      const float4 ca = v.sorted[a].cenv;
+      const unsigned ia = v.sorted[a].idx;
+      const int3 c = cell_coords(g, ca.x, ca.y, ca.z);
       const float need = 2.0f * ca.w * g.inv_h * 1.001f;
-      R = need <= 1.0f ? 1 : (need <= (float)kMaxSearch ? (int)ceilf(need) : 0);
-      everything = !(need <= (float)kMaxSearch);
-    }
-    const int Rw = __reduce_max_sync(kFullMask, R);
-    for (int dz = -Rw; dz <= Rw; dz++) {
-      for (int dy = -Rw; dy <= Rw; dy++) {
-        unsigned b0 = 0, b1 = 0;
-        const int y = c.y + dy, z = c.z + dz;
-        if (live && !everything && abs(dy) <= R && abs(dz) <= R && y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
-          const int x0 = max(c.x - R, 0), x1 = min(c.x + R, g.dim[0] - 1);
-          const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
-          b0 = v.cell_cnt[row + x0];
-          b1 = v.cell_cnt[row + x1 + 1];
-        }
-        if (everything && dz == -Rw && dy == -Rw) { b0 = 0; b1 = (unsigned)v.n; }
-        // lanes walk their runs together; appends are warp-aggregated
-        for (unsigned b = b0; __any_sync(kFullMask, b < b1); b++) {
-          bool hit = false;
-          unsigned ib = 0;
-          if (b < b1) {
-            const float4 cb = v.sorted_cenv[b];
-            ib = v.sorted_idx[b];
-            const float dx = ca.x - cb.x, dyy = ca.y - cb.y, dzz = ca.z - cb.z;
-            const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
-            const float T = ca.w + cb.w;
-            hit = (ca.w > cb.w || (ca.w == cb.w && ia < ib)) && ia != ib && (d2 <= T * T);
+      const int R = need <= 1.0f ? 1 : (need <= (float)kMaxSearch ? (int)ceilf(need) : 0);
+      const bool everything = !(need <= (float)kMaxSearch);
+      const bool half = need <= 1.0f;
+      auto run = [&](unsigned b0, unsigned b1) {
+        // (the loads of up to four partners are issued before the first is looked at: the kernel is bound by
+        // the latency of its dependent loads, not by instructions or bytes)
+        float4 nb[4];
+        for (unsigned bb = b0; bb < b1; bb += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) nb[u] = v.sorted[min(bb + u, b1 - 1)].cenv;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const unsigned b = bb + u;
+          if (b >= b1) break;
+          const float4 cb = nb[u];
+          const float dx = ca.x - cb.x, dyy = ca.y - cb.y, dzz = ca.z - cb.z;
+          const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
+          const float T = ca.w + cb.w;
+          if (!(d2 <= T * T)) continue;
+          const unsigned ib = v.sorted[b].idx;
+          if (half) {
+            if (!(2.0f * cb.w * g.inv_h * 1.001f <= 1.0f)) continue;          // a wider-searching partner lists the pair itself
+          } else {
+            if (ca.w < cb.w || ia == ib || (ca.w == cb.w && !(ia < ib))) continue;
           }
-          const unsigned m = __ballot_sync(kFullMask, hit);
-          if (m) {
-            unsigned long long base = 0;
-            if (lane == __ffs(m) - 1) base = atomicAdd(&v.flags->n_pairs, (unsigned long long)__popc(m));
-            base = __shfl_sync(kFullMask, base, __ffs(m) - 1);
-            if (hit) {
-              const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
-              if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2((int)min(ia, ib), (int)max(ia, ib));
-              else atomicExch(&v.flags->overflow_pairs, 1);
-            }
-          }
+          const int2 pr = make_int2((int)min(ia, ib), (int)max(ia, ib));
+          const unsigned slot = atomicAdd(&s_cnt, 1u);
+          if (slot < (unsigned)kPairsStage) { s_pairs[slot] = pr; continue; }
+          const unsigned long long gs = atomicAdd(&v.flags->n_pairs, 1ull);
+          if ((long long)gs < v.pairs_cap) v.pairs[gs] = pr;
+          else atomicExch(&v.flags->overflow_pairs, 1);
         }
+        }
+      };
+      if (everything) {
+        run(0u, (unsigned)v.n);
+      } else if (half) {
+        const int x0 = max(c.x - 1, 0), x1 = min(c.x + 1, g.dim[0] - 1);
+        const unsigned row = (unsigned)((c.z * g.dim[1] + c.y) * g.dim[0]);
+        // the bounds of all five runs first (independent loads), then the runs
+        unsigned lo[5], hi[5];
+        lo[0] = (unsigned)a + 1u; hi[0] = v.cell_cnt[row + x1 + 1];            // rest of the own cell, then cell x+1
+        const bool up = c.y + 1 < g.dim[1];
+        lo[1] = up ? v.cell_cnt[row + g.dim[0] + x0] : 0u; hi[1] = up ? v.cell_cnt[row + g.dim[0] + x1 + 1] : 0u;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          const int y = c.y - 1 + q;
+          const bool ok = c.z + 1 < g.dim[2] && y >= 0 && y < g.dim[1];
+          const unsigned r2 = (unsigned)(((c.z + 1) * g.dim[1] + y) * g.dim[0]);
+          lo[2 + q] = ok ? v.cell_cnt[r2 + x0] : 0u; hi[2 + q] = ok ? v.cell_cnt[r2 + x1 + 1] : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 5; q++) run(lo[q], hi[q]);
+      } else {
+        const int x0 = max(c.x - R, 0), x1 = min(c.x + R, g.dim[0] - 1);
+        for (int z = max(c.z - R, 0); z <= min(c.z + R, g.dim[2] - 1); z++)
+          for (int y = max(c.y - R, 0); y <= min(c.y + R, g.dim[1] - 1); y++) {
+            const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+            run(v.cell_cnt[row + x0], v.cell_cnt[row + x1 + 1]);
+          }
       }
     }
+    __syncthreads();
+    const unsigned staged = min(s_cnt, (unsigned)kPairsStage);
+    if (threadIdx.x == 0 && staged) s_base = atomicAdd(&v.flags->n_pairs, (unsigned long long)staged);
+    __syncthreads();
+    for (unsigned e = threadIdx.x; e < staged; e += kPairsBlock) {
+      const unsigned long long gs = s_base + e;
+      if ((long long)gs < v.pairs_cap) v.pairs[gs] = s_pairs[e];
+      else atomicExch(&v.flags->overflow_pairs, 1);
+    }
+    __syncthreads();
   }
 }
 
@@ -509,6 +563,36 @@ __device__ __forceinline__ BodyState state_at(const LargeView &v, int src, int b
   return s;
 }
 
+// Bodies that receive their first timeline entry join the touched list.  Tens of thousands do in the
+// first iteration of a step, and one atomic each on the list's counter serialises them; they are staged
+// per block instead and appended with one atomic when the block is through (kTouchInit / kTouchFlush:
+// called by ALL threads of the block at the start / end of every phase that pushes timeline entries).
+constexpr int kTouchStage = 512;
+enum { kTouchAdd = 0, kTouchFlush = 1, kTouchInit = 2 };
+__device__ __noinline__ void touched_stage(const LargeView &v, int b, int mode) {
+  __shared__ int s_list[kTouchStage];
+  __shared__ unsigned s_cnt, s_base;
+  if (mode == kTouchInit) {
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    return;
+  }
+  if (mode == kTouchAdd) {
+    const unsigned slot = atomicAdd(&s_cnt, 1u);
+    if (slot < (unsigned)kTouchStage) s_list[slot] = b;
+    else v.touched[atomicAdd(&v.flags->n_touched, 1u)] = b;
+    return;
+  }
+  __syncthreads();
+  const unsigned staged = min(s_cnt, (unsigned)kTouchStage);
+  if (threadIdx.x == 0 && staged) s_base = atomicAdd(&v.flags->n_touched, staged);
+  __syncthreads();
+  for (unsigned e = threadIdx.x; e < staged; e += blockDim.x) v.touched[s_base + e] = s_list[e];
+  __syncthreads();
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+}
+
 __device__ __forceinline__ void timeline_push(const LargeView &v, int dst, int b, unsigned long long key, const Sphere &s) {
   // tl_cnt is a byte array; claim a slot with a 32-bit CAS on the containing word
   unsigned *word = (unsigned *)(v.tl_cnt[dst] + (b & ~3));
@@ -522,29 +606,29 @@ __device__ __forceinline__ void timeline_push(const LargeView &v, int dst, int b
     old = atomicCAS(word, assumed, assumed + (1u << sh));
   } while (old != assumed);
   if (slot >= kTimeline) { atomicExch(&v.flags->overflow_timeline, 1); return; }
-  if (slot == 0 && atomicExch(&v.seen[b], 1) == 0) { v.touched[atomicAdd(&v.flags->n_touched, 1u)] = b; atomicOr(&v.touched_bits[b >> 5], 1u << (b & 31)); }
+  if (slot == 0 && atomicExch(&v.seen[b], 1) == 0) { touched_stage(v, b, kTouchAdd); atomicOr(&v.touched_bits[b >> 5], 1u << (b & 31)); }
   v.tl_key[dst][(size_t)b * kTimeline + slot] = key;
   v.tl_pos[dst][(size_t)b * kTimeline + slot] = make_float4(s.px, s.py, s.pz, 0.0f);
   v.tl_vel[dst][(size_t)b * kTimeline + slot] = make_float4(s.vx, s.vy, s.vz, 0.0f);
 }
 
-// Evaluate one visit on the hypothesis `src`; on a hit append the outcome to both bodies' `dst`
-// timelines and report it through ovr_row / ovr_col.
-__device__ __forceinline__ bool eval_visit(const LargeView &v, int src, int dst, int row, int col, float dt, pgm::LeafLen leaf,
-                                           unsigned long long skip_key, const Override *in_row, const Override *in_col,
-                                           Override *out_row, Override *out_col) {
+// Evaluate one visit on the hypothesis `src` WITHOUT touching the timelines: 0 = no event, 1 = event
+// (A = row body, B = column body after it), 2 = deferred (one thread per pair only: the interval search
+// is a long one, the pair goes to a block).  Warp: all threads of the block, identical arguments.
+template <bool Warp>
+__device__ __forceinline__ int visit_compute(const LargeView &v, int src, int row, int col, float dt, pgm::LeafLen leaf,
+                                             unsigned long long skip_key, const Override *in_row, const Override *in_col,
+                                             Sphere &A, Sphere &B) {
   const unsigned long long key = ((unsigned long long)(unsigned)row << 32) | (unsigned)col;
   float ra, rb;
   const BodyState a = state_at(v, src, row, key, dt, &ra, skip_key, in_row), b = state_at(v, src, col, key, dt, &rb, skip_key, in_col);
-  Sphere A, B;
   A.px = a.px; A.py = a.py; A.pz = a.pz; A.vx = a.vx; A.vy = a.vy; A.vz = a.vz; A.r = ra; A.rest = 0;
   B.px = b.px; B.py = b.py; B.pz = b.pz; B.vx = b.vx; B.vy = b.vy; B.vz = b.vz; B.r = rb; B.rest = 0;
-  if (!pgs::sphere_pair_exact(A, B, dt, leaf)) return false;
-  timeline_push(v, dst, row, key, A);
-  timeline_push(v, dst, col, key, B);
-  if (out_row) { out_row->key = key; out_row->present = true; out_row->px = A.px; out_row->py = A.py; out_row->pz = A.pz; out_row->vx = A.vx; out_row->vy = A.vy; out_row->vz = A.vz; }
-  if (out_col) { out_col->key = key; out_col->present = true; out_col->px = B.px; out_col->py = B.py; out_col->pz = B.pz; out_col->vx = B.vx; out_col->vy = B.vy; out_col->vz = B.vz; }
-  return true;
+  if (Warp) return pgs::sphere_pair_exact_block(A, B, dt, leaf) ? 1 : 0;
+  return pgs::sphere_pair_exact_try(A, B, dt, leaf);
+}
+__device__ __forceinline__ void set_override(Override *o, unsigned long long key, const Sphere &S) {
+  o->key = key; o->present = true; o->px = S.px; o->py = S.py; o->pz = S.pz; o->vx = S.vx; o->vy = S.vy; o->vz = S.vz;
 }
 
 // Copy the entry with `key` (if any) of body b from the src to the dst timeline.
@@ -573,46 +657,157 @@ __device__ __forceinline__ bool affected(const LargeView &v, int src, int b, uns
   return false;
 }
 
-__global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) {
-  pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
+// Which candidate pairs does this iteration have to look at?  A light, fully occupied pass over the
+// whole list so that k_eval (122 registers, long divergent evaluations) runs on dense warps only.
+//   iteration 0   the timelines are empty, so both visits of a pair see the post-pass-3 states (the
+//                 second one its column body integrated): a pair both of whose closest-approach gates
+//                 -- the very gate sphere_pair_exact opens with -- reject cannot fire and is dropped.
+//                 If the first gate passes the pair is kept whatever the second says (a hit would
+//                 change what the second visit sees).
+//   later         pairs with a body that has a timeline (or appended by k_requery): the rest has
+//                 nothing to carry and nothing that could have changed.
+// The order of the active list is irrelevant (timeline slots are claimed atomically anyway).
+constexpr int kSelItems = 4;
+__device__ __forceinline__ void d_select(const LargeView &v, int iter, float dt) {
+  __shared__ unsigned s_cnt, s_base;
+  const int kSelBlock = (int)blockDim.x;
   const long long np = (long long)min((unsigned long long)v.pairs_cap, v.flags->n_pairs);
-  unsigned my_hits = 0;
-  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < np; k += (long long)gridDim.x * blockDim.x) {
-    const int2 pr = v.pairs[k];
-    const bool fresh = pr.x < 0;                     // appended by k_requery: never evaluated yet
-    const int i = fresh ? ~pr.x : pr.x, j = pr.y;
-    if (fresh) v.pairs[k].x = i;
-    const unsigned long long key1 = ((unsigned long long)(unsigned)i << 32) | (unsigned)j;
-    const unsigned long long key2 = ((unsigned long long)(unsigned)j << 32) | (unsigned)i;
-    if (iter > 0 && !fresh) {
-      // neither body has a timeline: nothing to carry, nothing that could have changed
-      if (!((v.touched_bits[i >> 5] >> (i & 31)) & 1u) && !((v.touched_bits[j >> 5] >> (j & 31)) & 1u)) continue;
-      // A visit depends only on the entries with SMALLER keys of its two bodies.  If none of those
-      // appeared, changed or disappeared since the previous iteration, its outcome is the recorded
-      // one: carry it over instead of re-evaluating.  The second visit saw the first one's outcome
-      // directly (Gauss-Seidel), so that entry is excluded from its test.
-      const bool need1 = affected(v, src, i, key1, 0ull) || affected(v, src, j, key1, 0ull);
-      if (!need1) {
-        const bool have_i = v.tl_cnt[src][i] != 0, have_j = v.tl_cnt[src][j] != 0;
-        if (have_i && have_j && carry_entry(v, src, dst, i, key1)) { carry_entry(v, src, dst, j, key1); my_hits++; }
-        const bool need2 = affected(v, src, i, key2, key1) || affected(v, src, j, key2, key1);
-        if (!need2) {
-          if (have_i && have_j && carry_entry(v, src, dst, i, key2)) { carry_entry(v, src, dst, j, key2); my_hits++; }
-        } else {
-          my_hits += eval_visit(v, src, dst, j, i, dt, leaf, 0ull, nullptr, nullptr, nullptr, nullptr) ? 1u : 0u;
+  const long long tile = (long long)kSelBlock * kSelItems;
+  for (long long k0 = blockIdx.x * tile; k0 < np; k0 += (long long)gridDim.x * tile) {
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    unsigned need_bits = 0;
+#pragma unroll
+    for (int q = 0; q < kSelItems; q++) {
+      const long long k = k0 + q * kSelBlock + threadIdx.x;
+      if (k >= np) continue;
+      const int2 pr = v.pairs[k];
+      const bool fresh = pr.x < 0;
+      const int i = fresh ? ~pr.x : pr.x, j = pr.y;
+      bool need = fresh;
+      if (!need && iter > 0) {
+        need = ((v.touched_bits[i >> 5] >> (i & 31)) & 1u) || ((v.touched_bits[j >> 5] >> (j & 31)) & 1u);
+      } else if (!need) {
+        const float4 pi = v.pos_rest[i], qi = v.vel_rad[i], pj = v.pos_rest[j], qj = v.vel_rad[j];
+        // visit (i, j) of row i (i < j): neither body integrated yet
+        const V3 cI = v3(0.0f + pi.x, 0.0f + pi.y, 0.0f + pi.z), cJ = v3(0.0f + pj.x, 0.0f + pj.y, 0.0f + pj.z);
+        const V3 vI = v3(qi.x, qi.y, qi.z), vJ = v3(qj.x, qj.y, qj.z);
+        const float rs = qi.w + qj.w, rs2 = qj.w + qi.w;
+        const float nI = pgm::norm(vI), nJ = pgm::norm(vJ);
+        need = !pgs::pair_gate_rejects(cI, vI, cJ, vJ, rs, nI + nJ, dt);
+        if (!need) {
+          // visit (j, i) of row j: body i has been integrated by its own row unless it rests (state_at)
+          V3 p2 = v3(pi.x, pi.y, pi.z), v2 = vI;
+          if (pi.w == 0.0f) pgm::integrate(p2, v2, dt);
+          const V3 c2 = v3(0.0f + p2.x, 0.0f + p2.y, 0.0f + p2.z);
+          need = !pgs::pair_gate_rejects(cJ, vJ, c2, v2, rs2, nJ + pgm::norm(v2), dt);
         }
-        continue;
       }
+      if (need) need_bits |= 1u << q;
     }
-    // visit (i, j) of row i, then visit (j, i) of row j on top of the first one's fresh outcome
-    Override oi, oj;
-    oi.present = false; oj.present = false; oi.key = key1; oj.key = key1;
-    my_hits += eval_visit(v, src, dst, i, j, dt, leaf, 0ull, nullptr, nullptr, &oi, &oj) ? 1u : 0u;
-    my_hits += eval_visit(v, src, dst, j, i, dt, leaf, key1, &oj, &oi, nullptr, nullptr) ? 1u : 0u;
+    unsigned slot = 0;
+    const int mine = __popc(need_bits);
+    if (mine) slot = atomicAdd(&s_cnt, (unsigned)mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) s_base = atomicAdd(&v.flags->n_active, s_cnt);
+    __syncthreads();
+    if (mine) {
+      slot += s_base;
+#pragma unroll
+      for (int q = 0; q < kSelItems; q++)
+        if ((need_bits >> q) & 1u) v.active[slot++] = (unsigned)(k0 + q * kSelBlock + threadIdx.x);
+    }
+    __syncthreads();                               // s_base is rewritten by the next tile
+  }
+}
+__global__ void __launch_bounds__(256) k_select(LargeView v, int iter, float dt) { d_select(v, iter, dt); }
+
+// Both visits of candidate pair k on the hypothesis `src`; hits go to the `dst` timelines.  Returns the
+// number of hits, or -1 when a one-thread evaluation met a long interval search: nothing has been
+// written then and the pair is to be repeated by a whole block (Warp = true: all its threads run this
+// with the same k, `writer` = thread 0 does the writes).
+template <bool Warp>
+__device__ __forceinline__ int eval_pair(const LargeView &v, int src, int dst, int iter, float dt, pgm::LeafLen leaf, long long k, bool writer) {
+  const int2 pr = v.pairs[k];
+  const bool fresh = pr.x < 0;                     // appended by k_requery: never evaluated yet
+  const int i = fresh ? ~pr.x : pr.x, j = pr.y;
+  const unsigned long long key1 = ((unsigned long long)(unsigned)i << 32) | (unsigned)j;
+  const unsigned long long key2 = ((unsigned long long)(unsigned)j << 32) | (unsigned)i;
+  Sphere A1, B1, A2, B2;
+  if (iter > 0 && !fresh) {
+    // neither body has a timeline: nothing to carry, nothing that could have changed
+    if (!((v.touched_bits[i >> 5] >> (i & 31)) & 1u) && !((v.touched_bits[j >> 5] >> (j & 31)) & 1u)) return 0;
+    // A visit depends only on the entries with SMALLER keys of its two bodies.  If none of those
+    // appeared, changed or disappeared since the previous iteration, its outcome is the recorded
+    // one: carry it over instead of re-evaluating.  The second visit saw the first one's outcome
+    // directly (Gauss-Seidel), so that entry is excluded from its test.
+    const bool need1 = affected(v, src, i, key1, 0ull) || affected(v, src, j, key1, 0ull);
+    if (!need1) {
+      const bool need2 = affected(v, src, i, key2, key1) || affected(v, src, j, key2, key1);
+      int h2 = 0;
+      if (need2) {
+        h2 = visit_compute<Warp>(v, src, j, i, dt, leaf, 0ull, nullptr, nullptr, A2, B2);
+        if (h2 == 2) return -1;
+      }
+      int hits = 0;
+      if (writer) {
+        const bool have_i = v.tl_cnt[src][i] != 0, have_j = v.tl_cnt[src][j] != 0;
+        if (have_i && have_j && carry_entry(v, src, dst, i, key1)) { carry_entry(v, src, dst, j, key1); hits++; }
+        if (!need2) {
+          if (have_i && have_j && carry_entry(v, src, dst, i, key2)) { carry_entry(v, src, dst, j, key2); hits++; }
+        } else if (h2) {
+          timeline_push(v, dst, j, key2, A2); timeline_push(v, dst, i, key2, B2); hits++;
+        }
+      }
+      return hits;
+    }
+  }
+  // visit (i, j) of row i, then visit (j, i) of row j on top of the first one's fresh outcome
+  Override oi, oj;
+  oi.present = false; oj.present = false; oi.key = key1; oj.key = key1;
+  const int h1 = visit_compute<Warp>(v, src, i, j, dt, leaf, 0ull, nullptr, nullptr, A1, B1);
+  if (h1 == 2) return -1;
+  if (h1) { set_override(&oi, key1, A1); set_override(&oj, key1, B1); }
+  const int h2 = visit_compute<Warp>(v, src, j, i, dt, leaf, key1, &oj, &oi, A2, B2);
+  if (h2 == 2) return -1;
+  if (writer) {
+    if (fresh) v.pairs[k].x = i;
+    if (h1) { timeline_push(v, dst, i, key1, A1); timeline_push(v, dst, j, key1, B1); }
+    if (h2) { timeline_push(v, dst, j, key2, A2); timeline_push(v, dst, i, key2, B2); }
+  }
+  return h1 + h2;
+}
+
+__device__ __forceinline__ void d_eval(const LargeView &v, int src, int dst, int iter, float dt) {
+  pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
+  const long long na = (long long)v.flags->n_active;
+  unsigned my_hits = 0;
+  touched_stage(v, 0, kTouchInit);
+  for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < na; a += (long long)gridDim.x * blockDim.x) {
+    const unsigned k = v.active[a];
+    const int h = eval_pair<false>(v, src, dst, iter, dt, leaf, (long long)k, true);
+    if (h >= 0) my_hits += (unsigned)h;
+    else v.active[v.pairs_cap + atomicAdd(&v.flags->n_hard, 1u)] = k;      // the hard list: second half of active[]
   }
   // one atomic per warp for the hit statistic (a single hot address otherwise)
   my_hits = __reduce_add_sync(kFullMask, my_hits);
   if ((threadIdx.x & 31) == 0 && my_hits) atomicAdd(&v.flags->n_hits, (unsigned long long)my_hits);
+  touched_stage(v, 0, kTouchFlush);
+}
+// The pairs k_eval deferred (grazing pairs: an interval search of hundreds to thousands of nodes that a
+// single thread would walk for up to a millisecond while the rest of the GPU waits; a handful per step):
+// one BLOCK per pair, all threads evaluate it redundantly and share the leaf scan of pgm::ss_interval.
+__device__ __forceinline__ void d_eval_hard(const LargeView &v, int src, int dst, int iter, float dt) {
+  pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
+  const int nh = (int)v.flags->n_hard;
+  touched_stage(v, 0, kTouchInit);
+  for (int t = blockIdx.x; t < nh; t += gridDim.x) {
+    const long long k = (long long)v.active[v.pairs_cap + t];
+    const int h = eval_pair<true>(v, src, dst, iter, dt, leaf, k, threadIdx.x == 0);
+    if (threadIdx.x == 0 && h > 0) atomicAdd(&v.flags->n_hits, (unsigned long long)h);
+    __syncthreads();
+  }
+  touched_stage(v, 0, kTouchFlush);
 }
 
 // Compare the timelines of two iterations (as sets keyed by visit) and validate envelopes, for the
@@ -622,7 +817,7 @@ __device__ __forceinline__ bool same_state(float4 p0, float4 q0, float4 p1, floa
          __float_as_uint(p0.z) == __float_as_uint(p1.z) && __float_as_uint(q0.x) == __float_as_uint(q1.x) &&
          __float_as_uint(q0.y) == __float_as_uint(q1.y) && __float_as_uint(q0.z) == __float_as_uint(q1.z);
 }
-__global__ void k_check(LargeView v, int src, int dst, float dt) {
+__device__ __forceinline__ void d_check(const LargeView &v, int src, int dst, float dt) {
   const int nt = (int)v.flags->n_touched;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     const int b = v.touched[t];
@@ -676,9 +871,9 @@ __global__ void k_check(LargeView v, int src, int dst, float dt) {
   }
 }
 // reset the destination timelines of the touched bodies before an iteration refills them
-__global__ void k_clear(LargeView v, int dst) {
+__device__ __forceinline__ void d_clear(const LargeView &v, int dst) {
   const int nt = (int)v.flags->n_touched;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { v.flags->changed = 0; v.flags->grew = 0; v.flags->n_hits = 0ull; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { v.flags->changed = 0; v.flags->grew = 0; v.flags->n_hits = 0ull; v.flags->n_active = 0u; v.flags->n_hard = 0u; }
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) v.tl_cnt[dst][v.touched[t]] = 0;
 }
 
@@ -687,14 +882,16 @@ __global__ void k_clear(LargeView v, int dst) {
 // existing grid and append them marked as fresh, so that the next iteration evaluates them (pairs
 // that were already listed keep their recorded outcomes).  If both bodies of a pair grew, the lower
 // index appends it.
-__global__ void k_requery(LargeView v, int src) {
+__device__ __forceinline__ void d_requery(const LargeView &v, int src) {
   const GridParams g = *v.grid;
   const int nt = (int)v.flags->n_touched;
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  // one warp per touched body: the lanes share its cell runs, the fast list and -- for a body whose
-  // search would cover most of the grid -- the whole sorted array
-  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < nt; t += warps) {
+  // Eight lanes per touched body (a search is 9 short cell runs, each a chain of dependent loads: more
+  // bodies in flight beat more lanes per body): the lanes share its cell runs, the fast list and -- for a
+  // body whose search would cover most of the grid -- the whole sorted array.  No warp-level primitives.
+  constexpr int kGroup = 8;
+  const int lane = threadIdx.x & (kGroup - 1);
+  const int warps = (gridDim.x * blockDim.x) / kGroup;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) / kGroup; t < nt; t += warps) {
     const int b = v.touched[t];
     if (!v.grown[b]) continue;
     const float4 p = v.pos_rest[b];
@@ -715,27 +912,30 @@ __global__ void k_requery(LargeView v, int src) {
     // (which also holds bodies that outgrew e_cap this step).
     const float need = (eb + g.e_cap) * g.inv_h * 1.001f;
     if (!(need <= (float)kMaxSearch)) {
-      for (int a = lane; a < v.n; a += 32) {
-        const int x = (int)v.sorted_idx[a];
-        if (x != b && !(v.env[x] > g.e_cap)) consider(x, v.sorted_cenv[a]);
+      for (int a = lane; a < v.n; a += kGroup) {
+        const int x = (int)v.sorted[a].idx;
+        if (x != b && !(v.env[x] > g.e_cap)) consider(x, v.sorted[a].cenv);
       }
     } else {
+      // every lane takes whole x-runs of the (2R+1)^2 the search covers (9 for a body the grid was sized
+      // for), so their dependent loads -- cell table, cell contents, envelopes -- are in flight together
       const int R = max((int)ceilf(need), 1);
       const int3 c = cell_coords(g, p.x, p.y, p.z);
-      for (int dz = -R; dz <= R; dz++) for (int dy = -R; dy <= R; dy++) {
-        const int y = c.y + dy, z = c.z + dz;
+      const int side = 2 * R + 1;
+      const int x0 = max(c.x - R, 0), x1 = min(c.x + R, g.dim[0] - 1);
+      for (int r = lane; r < side * side; r += kGroup) {
+        const int y = c.y + r % side - R, z = c.z + r / side - R;
         if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
-        const int x0 = max(c.x - R, 0), x1 = min(c.x + R, g.dim[0] - 1);
         const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
         const unsigned a1 = v.cell_cnt[row + x1 + 1];
-        for (unsigned a = v.cell_cnt[row + x0] + lane; a < a1; a += 32) {
-          const int x = (int)v.sorted_idx[a];
-          if (x != b && !(v.env[x] > g.e_cap)) consider(x, v.sorted_cenv[a]);
+        for (unsigned a = v.cell_cnt[row + x0]; a < a1; a++) {
+          const int x = (int)v.sorted[a].idx;
+          if (x != b && !(v.env[x] > g.e_cap)) consider(x, v.sorted[a].cenv);
         }
       }
     }
     const int nf = (int)v.flags->n_fast;
-    for (int f = lane; f < nf; f += 32) {
+    for (int f = lane; f < nf; f += kGroup) {
       const int x = v.fast_list[f];
       if (x == b || !(v.env[x] > g.e_cap)) continue;
       const float4 px = v.pos_rest[x];
@@ -743,7 +943,7 @@ __global__ void k_requery(LargeView v, int src) {
     }
   }
 }
-__global__ void k_requery_done(LargeView v) {
+__device__ __forceinline__ void d_requery_done(const LargeView &v) {
   const int nt = (int)v.flags->n_touched;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     const int b = v.touched[t];
@@ -751,11 +951,94 @@ __global__ void k_requery_done(LargeView v) {
   }
 }
 
+
+// ---------------------------------------------------------------- the whole fixed point in ONE launch
+// A cooperative kernel (every block resident, grid-wide barriers between the phases) runs the
+// iterations that lw_step_once otherwise drives from the host with seven launches and one read-back
+// each.  It stops when the fixed point is reached, after kMaxIter iterations, or when something only
+// the host can do is needed (a buffer has to grow); `FpStatus` says where it stopped.
+struct FpStatus {
+  int iterations;          // iterations run by this launch
+  int src;                 // timeline buffer that holds the latest hypothesis
+  int converged;
+  int requery_pending;     // k_requery_done still owed (only when stopped for the host)
+  int stop;                // 0 = loop finished, 1 = timeline overflow, 2 = candidate list overflowed while k_requery appended
+  int unsafe_seen;
+  unsigned long long pairs_before;   // list length before the iteration that stopped (stop == 2)
+  unsigned long long phase_ns[8];    // time per phase, summed over the iterations: clear, select, eval, hard, check, requery, control; [7] = pairs sent to k_eval_hard
+};
+__global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) { d_eval(v, src, dst, iter, dt); }
+__global__ void __launch_bounds__(512) k_eval_hard(LargeView v, int src, int dst, int iter, float dt) { d_eval_hard(v, src, dst, iter, dt); }
+__global__ void k_check(LargeView v, int src, int dst, float dt) { d_check(v, src, dst, dt); }
+__global__ void k_clear(LargeView v, int dst) { d_clear(v, dst); }
+__global__ void k_requery(LargeView v, int src) { d_requery(v, src); }
+__global__ void k_requery_done(LargeView v) { d_requery_done(v); }
+
+__global__ void __launch_bounds__(128, 4) k_fixed_point(LargeView v, int it_start, int src, int requery_pending, float dt, FpStatus *status) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const volatile Flags *vf = v.flags;
+  int dst = src ^ 1;
+  int converged = 0, stop = 0, unsafe_seen = 0, iterations = 0;
+  unsigned long long pairs_before = 0;
+  const bool clerk = blockIdx.x == 0 && threadIdx.x == 0;
+  unsigned long long t_prev = 0, ns[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
+  auto lap = [&](int k) { if (clerk) { const unsigned long long t = now(); ns[k] += t - t_prev; t_prev = t; } };
+  if (clerk) t_prev = now();
+  for (int it = it_start; it < kMaxIter; it++) {
+    pairs_before = min(vf->n_pairs, (unsigned long long)v.pairs_cap);
+    grid.sync();                                   // everybody has read the flags of the previous iteration
+    if (requery_pending) { d_requery_done(v); requery_pending = 0; }
+    d_clear(v, dst);                               // also resets the per-iteration flags
+    grid.sync(); lap(0);
+    d_select(v, it, dt);
+    grid.sync(); lap(1);
+    d_eval(v, src, dst, it, dt);
+    grid.sync(); lap(2);
+    if (vf->n_hard) d_eval_hard(v, src, dst, it, dt);
+    if (clerk) ns[7] += vf->n_hard;
+    grid.sync(); lap(3);
+    d_check(v, src, dst, dt);
+    grid.sync(); lap(4);
+    d_requery(v, dst);
+    grid.sync(); lap(5);
+    iterations++;
+    const int grew = vf->grew, changed = vf->changed;
+    if (vf->overflow_timeline) { stop = 1; break; }
+    src ^= 1; dst ^= 1;
+    if (grew) {
+      requery_pending = 1;
+      if (vf->overflow_pairs) { stop = 2; break; }
+      if (vf->unsafe) unsafe_seen = 1;
+      continue;                                    // at least one more iteration with the new pairs
+    }
+    if (!changed) { converged = 1; break; }
+  }
+  if (!stop && requery_pending) {
+    grid.sync();
+    d_requery_done(v);
+    requery_pending = 0;
+  }
+  lap(6);
+  if (clerk) {
+    status->iterations = iterations; status->src = src; status->converged = converged; status->requery_pending = requery_pending;
+    status->stop = stop; status->unsafe_seen = unsafe_seen; status->pairs_before = pairs_before;
+    for (int k = 0; k < 8; k++) status->phase_ns[k] = ns[k];
+  }
+}
+
 // ---------------------------------------------------------------- 5. final state + pass-4 events
 __global__ void k_finalize(LargeView v, int src, float dt, int step) {
-  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < v.n; b += gridDim.x * blockDim.x) {
-    float4 p = v.pos_rest[b], q = v.vel_rad[b];
-    const int cnt = min((int)v.tl_cnt[src][b], kTimeline);
+  const int stride = gridDim.x * blockDim.x;
+  // two bodies per trip: the second one's loads are issued before the first one's stores
+  float4 p_next = make_float4(0, 0, 0, 0), q_next = p_next;
+  int cnt_next = 0;
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < v.n) { p_next = v.pos_rest[b]; q_next = v.vel_rad[b]; cnt_next = v.tl_cnt[src][b]; }
+  for (; b < v.n; b += stride) {
+    float4 p = p_next, q = q_next;
+    const int cnt = min(cnt_next, kTimeline);
+    if (b + stride < v.n) { p_next = v.pos_rest[b + stride]; q_next = v.vel_rad[b + stride]; cnt_next = v.tl_cnt[src][b + stride]; }
     long long last_row = -1;
     if (cnt > 0) {
       unsigned long long best = 0; int best_k = -1;
@@ -836,6 +1119,10 @@ struct PgLarge {
   int cap_static_total;
   long long last_candidates, last_hits;
   int step_in_call;
+  int fp_blocks;                 // grid of the cooperative fixed-point kernel (every block resident); 0 = not available
+  int fused;                     // PG_LARGE_FUSED was set when the world was created
+  FpStatus *d_fp_status;
+  unsigned long long fp_phase_ns[8];
   int timing;                    // record a CUDA event pair around every kernel (pg_large_kernel_ms); off by default:
                                  // the pipeline of a small world is launch-bound and the events double its API calls
 };
@@ -874,7 +1161,7 @@ static int lw_build_pairs(PgLarge *w) {
   if (w->timing) cudaEventRecord(w->kev[K_SCAN][1], w->stream);
   w->launches += 3;
   LW_LAUNCH(w, K_SCATTER, k_scatter, lw_grid(w, v.n, 256), 256, v);
-  LW_LAUNCH(w, K_PAIRS, k_pairs, lw_grid(w, v.n, 128), 128, v);
+  LW_LAUNCH(w, K_PAIRS, k_pairs, lw_grid(w, v.n, kPairsBlock), kPairsBlock, v);
   PG_CUDA(cudaGetLastError());
   return PG_OK;
 }
@@ -901,6 +1188,13 @@ static int lw_grow_pairs(PgLarge *w, unsigned long long needed, unsigned long lo
   cudaFree(v.pairs);
   v.pairs = bigger;
   v.pairs_cap = cap;
+  cudaFree(v.active);
+  v.active = nullptr;
+  if (cudaMalloc(&v.active, sizeof(unsigned) * 2 * (size_t)cap) != cudaSuccess) {
+    cudaGetLastError();
+    pg_set_error("large world: cannot grow the active pair list to %lld entries", cap);
+    return PG_ERR_CAPACITY;
+  }
   PG_CUDA(cudaMemsetAsync(&v.flags->overflow_pairs, 0, sizeof(int), w->stream));
   PG_CUDA(cudaMemcpyAsync(&v.flags->n_pairs, &keep, sizeof(keep), cudaMemcpyHostToDevice, w->stream));
   PG_CUDA(cudaStreamSynchronize(w->stream));
@@ -920,7 +1214,6 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   LW_LAUNCH(w, K_PASS3, k_pass3, lw_grid(w, v.n, 256), 256, v, dt, w->step_in_call, 1);
   w->last_proven = 1;
   w->last_iterations = 0;
-  int src = 0, dst = 1;
   int rc = lw_build_pairs(w);
   if (rc) return rc;
   Flags f;
@@ -931,7 +1224,7 @@ static int lw_step_once(PgLarge *w, float dt_in) {
     // k_pairs is a pure function of the grid: grow the buffer and run it again
     rc = lw_grow_pairs(w, f.n_pairs, 0);
     if (rc) return rc;
-    LW_LAUNCH(w, K_PAIRS, k_pairs, lw_grid(w, v.n, 128), 128, v);
+    LW_LAUNCH(w, K_PAIRS, k_pairs, lw_grid(w, v.n, kPairsBlock), kPairsBlock, v);
     rc = lw_read_flags(w, &f);
     if (rc) return rc;
     lw_accumulate(w, K_PAIRS);
@@ -942,10 +1235,62 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   const bool debug = getenv("PG_LARGE_DEBUG") != nullptr && w->timing;
   bool converged = false;
   int requeries = 0;
+  // PG_LARGE_FUSED=1 (read at pg_large_create): the fixed point runs inside ONE cooperative launch
+  // (k_fixed_point) with one read-back at the end instead of the launch-per-kernel loop below.  Measured
+  //  it saves 4/5 of the launches but is 2 % faster only for a 65 k world and 3-7 %
+  // slower from 1 M bodies up (a resident grid is smaller than the grids the phases get on their own), so
+  // it is opt-in; it also reports the time per phase (pg_large_fixed_point_ns).
+  const bool fused_ok = w->fused != 0;
+  int src = 0, dst = 1;
+  int it0 = 0;
+  bool requery_pending = false;
+  if (fused_ok && !w->timing && w->fp_blocks > 0) {
+    for (;;) {
+      int a_it = it0, a_src = src, a_pending = requery_pending ? 1 : 0;
+      float a_dt = dt;
+      FpStatus *a_status = w->d_fp_status;
+      void *args[] = {&v, &a_it, &a_src, &a_pending, &a_dt, &a_status};
+      PG_CUDA(cudaLaunchCooperativeKernel((const void *)k_fixed_point, dim3(w->fp_blocks), dim3(128), args, 0, w->stream));
+      w->launches++;
+      FpStatus st;
+      PG_CUDA(cudaMemcpyAsync(&st, w->d_fp_status, sizeof(st), cudaMemcpyDeviceToHost, w->stream));
+      rc = lw_read_flags(w, &f);
+      if (rc) return rc;
+      for (int k = 0; k < 8; k++) w->fp_phase_ns[k] += st.phase_ns[k];
+      w->last_iterations += st.iterations;
+      w->last_hits = (long long)f.n_hits;
+      w->last_candidates = (long long)f.n_pairs;
+      src = st.src; dst = src ^ 1;
+      if (st.unsafe_seen) w->last_proven = 0;
+      if (st.stop == 1) { pg_set_error("large world: more than %d contacts on one body in one step", kTimeline); return PG_ERR_CAPACITY; }
+      if (st.stop == 2) {
+        // k_requery only appends: keep the list as it was, make room, let it append again, then carry on
+        rc = lw_grow_pairs(w, f.n_pairs, st.pairs_before);
+        if (rc) return rc;
+        LW_LAUNCH(w, K_BOUNDS, k_requery, w->sm_count * 8, 128, v, src);
+        rc = lw_read_flags(w, &f);
+        if (rc) return rc;
+        if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
+        if (f.unsafe) w->last_proven = 0;
+        w->last_candidates = (long long)f.n_pairs;
+        requery_pending = true;
+        it0 += st.iterations;
+        if (it0 < kMaxIter) continue;
+        k_requery_done<<<w->sm_count * 8, 256, 0, w->stream>>>(v);
+        w->launches++;
+      }
+      converged = st.converged != 0;
+      break;
+    }
+    if (!converged) w->last_proven = 0;
+    LW_LAUNCH(w, K_FINAL, k_finalize, lw_grid(w, v.n, 256), 256, v, src, dt, w->step_in_call);
+    PG_CUDA(cudaGetLastError());
+    PG_CUDA(cudaStreamSynchronize(w->stream));
+    return PG_OK;
+  }
   // One host read-back per iteration: k_requery always rides along (it returns at once for bodies whose
   // envelope did not grow), its bookkeeping kernel is deferred to the start of the next iteration so
   // that an overflowing candidate list can still be grown and the append repeated.
-  bool requery_pending = false;
   const int wide_grid = w->sm_count * 8;
   for (int it = 0; it < kMaxIter; it++) {
     if (requery_pending) {
@@ -957,7 +1302,13 @@ static int lw_step_once(PgLarge *w, float dt_in) {
     w->launches++;
     const unsigned long long pairs_before = std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
     const int np = (int)std::min<unsigned long long>(pairs_before, 0x7fffffffull);
-    LW_LAUNCH(w, K_EVAL, k_eval, lw_grid(w, std::max(np, 1), 128), 128, v, src, dst, it, dt);
+    // the active list's length stays on the device: k_eval runs as many blocks as fit at once and strides
+    if (w->timing) cudaEventRecord(w->kev[K_EVAL][0], w->stream);
+    k_select<<<std::max(1, std::min((np + 256 * kSelItems - 1) / (256 * kSelItems), w->sm_count * 8)), 256, 0, w->stream>>>(v, it, dt);
+    k_eval<<<w->sm_count * 4, 128, 0, w->stream>>>(v, src, dst, it, dt);
+    k_eval_hard<<<w->sm_count, 512, 0, w->stream>>>(v, src, dst, it, dt);
+    if (w->timing) cudaEventRecord(w->kev[K_EVAL][1], w->stream);
+    w->launches += 3;
     LW_LAUNCH(w, K_CHECK, k_check, wide_grid, 256, v, src, dst, dt);
     // candidates the grown envelopes add (on top of the NEW timelines); their bodies are marked dirty so
     // the next iteration re-evaluates them (warm start)
@@ -1081,9 +1432,9 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   PG_CUDA_NULL(cudaMalloc(&v.cell_of, sizeof(unsigned) * n));
   PG_CUDA_NULL(cudaMalloc(&v.cell_cnt, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.block_sums, sizeof(unsigned) * ((size_t)v.cells_cap / (kScanBlock * kScanItems) + 2)));
-  PG_CUDA_NULL(cudaMalloc(&v.sorted_idx, sizeof(unsigned) * n));
-  PG_CUDA_NULL(cudaMalloc(&v.sorted_cenv, sizeof(float4) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.sorted, sizeof(SortedBody) * n));
   PG_CUDA_NULL(cudaMalloc(&v.pairs, sizeof(int2) * (size_t)v.pairs_cap));
+  PG_CUDA_NULL(cudaMalloc(&v.active, sizeof(unsigned) * 2 * (size_t)v.pairs_cap));
   PG_CUDA_NULL(cudaMalloc(&v.grown, n + 8));
   PG_CUDA_NULL(cudaMemset(v.grown, 0, n + 8));
   PG_CUDA_NULL(cudaMalloc(&v.env_prev, sizeof(float) * n));
@@ -1104,6 +1455,15 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   PG_CUDA_NULL(cudaMalloc(&v.n_events, sizeof(int)));
   PG_CUDA_NULL(cudaMemset(v.n_events, 0, sizeof(int)));
   PG_CUDA_NULL(cudaMalloc(&w->d_stats, 8 * sizeof(double)));
+  PG_CUDA_NULL(cudaMalloc(&w->d_fp_status, sizeof(FpStatus)));
+  {
+    int coop = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fixed_point, 128, 0) == cudaSuccess && per_sm > 0)
+      w->fp_blocks = per_sm * w->sm_count;
+    w->fused = getenv("PG_LARGE_FUSED") != nullptr;
+    cudaGetLastError();
+  }
   PG_CUDA_NULL(cudaMalloc(&w->d_stage_pos, sizeof(float) * 3 * n));
   PG_CUDA_NULL(cudaMalloc(&w->d_stage_vel, sizeof(float) * 3 * n));
   PG_CUDA_NULL(cudaMalloc(&w->d_stage_rest, n));
@@ -1116,9 +1476,9 @@ void pg_large_destroy(PgLarge *w) {
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
   if (w->player_world) pg_worlds_destroy(w->player_world);
-  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.fast_list, v.touched_bits, v.block_sums, v.sorted_idx,
-                  v.sorted_cenv, v.pairs, v.grown, v.env_prev, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
-                  v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
+  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.fast_list, v.touched_bits, v.block_sums, v.sorted,
+                  v.pairs, v.active, v.grown, v.env_prev, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
+                  v.flags, v.events, v.n_events, w->d_stats, w->d_fp_status, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);
   cudaEventDestroy(w->ev0); cudaEventDestroy(w->ev1);
   for (int k = 0; k < K_COUNT; k++) { cudaEventDestroy(w->kev[k][0]); cudaEventDestroy(w->kev[k][1]); }
@@ -1462,6 +1822,14 @@ float pg_large_last_step_ms(PgLarge *w) {
 int pg_large_kernel_count(void) { return K_COUNT; }
 const char *pg_large_kernel_name(int k) { return (k >= 0 && k < K_COUNT) ? kKernelNames[k] : ""; }
 float pg_large_kernel_ms(PgLarge *w, int k) { return (w && k >= 0 && k < K_COUNT) ? w->kms[k] : -1.0f; }
+// Time the cooperative fixed-point kernel spent per phase (ns, summed over the steps since the last reset):
+// clear, select, eval, hard, check, requery, control.  Read from %globaltimer by one thread between
+// the grid barriers; costs nothing to leave on.
+int pg_large_fixed_point_ns(PgLarge *w, unsigned long long *out8, int reset) {
+  if (!w || !out8) return PG_ERR_ARG;
+  for (int k = 0; k < 8; k++) { out8[k] = w->fp_phase_ns[k]; if (reset) w->fp_phase_ns[k] = 0; }
+  return PG_OK;
+}
 int pg_large_set_timing(PgLarge *w, int on) {
   if (!w) return PG_ERR_ARG;
   w->timing = on ? 1 : 0;

@@ -337,7 +337,10 @@ constexpr int kScanMax = 8192;                       // widest leaf window the s
 // Leaf scan behind ss_interval (see there); out of line and self-contained so that the common path
 // keeps its registers.  Returns kWalkTrue / kWalkFalse, or kWalkGaveUp if the window is too wide or
 // the halving tree is not uniform there (the caller then finishes the plain walk).
-template <bool Coop>
+// Coop: 0 = the calling thread scans alone; 1 = all 32 lanes of the warp call with identical arguments
+// and take every 32nd candidate; 2 = all threads of the BLOCK do (every blockDim.x-th candidate, one
+// __syncthreads_or at the end).
+template <int Coop>
 __device__ __noinline__ int ss_leaf_scan(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float nB, float rs,
                                          float t_begin, float t_end, LeafLen leaf) {
   const float tmax = fmaxf(fabsf(t_begin), fabsf(t_end));
@@ -377,8 +380,10 @@ __device__ __noinline__ int ss_leaf_scan(V3 cA, V3 vA, float nA, V3 cB, V3 vB, f
 #endif
     bool found = false, unknown = false;
     long long k = k0;
-    if (Coop) k += threadIdx.x & 31;
-    for (; k <= k1 && !found; k += Coop ? 32 : 1) {
+    if (Coop == 1) k += threadIdx.x & 31;
+    if (Coop == 2) k += threadIdx.x;
+    const int k_step = Coop == 1 ? 32 : (Coop == 2 ? (int)blockDim.x : 1);
+    for (; k <= k1 && !found; k += k_step) {
       float t0 = t_begin, t1 = t_end;
       float Sa = eval(t0), Sb = eval(t1);
       for (int level = D - 1;; level--) {
@@ -392,7 +397,8 @@ __device__ __noinline__ int ss_leaf_scan(V3 cA, V3 vA, float nA, V3 cB, V3 vB, f
         if ((k >> level) & 1ll) { t0 = mid; Sa = Sm; } else { t1 = mid; Sb = Sm; }
       }
     }
-    if (Coop) { found = __any_sync(0xffffffffu, found); unknown = __any_sync(0xffffffffu, unknown); }
+    if (Coop == 1) { found = __any_sync(0xffffffffu, found); unknown = __any_sync(0xffffffffu, unknown); }
+    if (Coop == 2) { found = __syncthreads_or(found) != 0; unknown = __syncthreads_or(unknown) != 0; }
     if (found) return kWalkTrue;
     return unknown ? kWalkGaveUp : kWalkFalse;
   }
@@ -415,10 +421,13 @@ __device__ __noinline__ int ss_leaf_scan(V3 cA, V3 vA, float nA, V3 cB, V3 vB, f
 // (|u| ~ nA+nB, where the reach shrinks as fast as the gap), would otherwise make the recursion
 // visit hundreds to O(2^depth) nodes; with the enclosures it is O(depth) unless the closest
 // approach lies inside a band of a few 1e-6 around mm(leaf).
-// Coop: all 32 lanes of the warp call with identical arguments (pg_spheres.cu) and share the leaf scan.
-template <bool Coop = false>
-__device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float nB, float rs,
-                                   float t_begin, float t_end, LeafLen leaf = default_leaf_len()) {
+// Coop = 1: all 32 lanes of the warp call with identical arguments (pg_spheres.cu) and share the leaf scan;
+// Coop = 2: all threads of the block do (pg_large.cu, k_eval_hard).
+// Defer (one thread per pair, pg_large.cu): a walk still going after kWalkBudget nodes returns
+// kWalkGaveUp instead of being finished alone; the caller hands the pair to a warp (Coop).
+template <int Coop, bool Defer>
+__device__ inline int ss_interval_impl(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float nB, float rs,
+                                       float t_begin, float t_end, LeafLen leaf) {
   const V3 u = sub(vA, vB);
   const float tmax = fmaxf(fabsf(t_begin), fabsf(t_end));
   const float c1 = fabsf(cA.x) + fabsf(cA.y) + fabsf(cA.z) + fabsf(cB.x) + fabsf(cB.y) + fabsf(cB.z);
@@ -482,12 +491,17 @@ __device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float n
   // from the root by its own halving sequence, testing every ancestor on the way exactly as the
   // recursion would.  The candidates are independent, so a warp scans 32 at a time (Coop callers
   // only: a single thread scanning a window of hundreds of leaves is slower than its walk).
-  for (int budget = Coop ? kWalkBudget : 0x7fffffff;; budget = 0x7fffffff) {     // one thread alone is better off walking
+  for (int budget = (Coop || Defer) ? kWalkBudget : 0x7fffffff;; budget = 0x7fffffff) {     // one thread alone is better off walking
     const int r = interval_walk_guided<float>(t_begin, t_end, t_pref, eval, probe, budget PG_DBG_ARG);
-    if (r != kWalkGaveUp) return r == kWalkTrue;
+    if (r != kWalkGaveUp || Defer) return r;
     const int q = ss_leaf_scan<Coop>(cA, vA, nA, cB, vB, nB, rs, t_begin, t_end, leaf);
-    if (q != kWalkGaveUp) return q == kWalkTrue;
+    if (q != kWalkGaveUp) return q;
   }
+}
+template <int Coop = 0>
+__device__ inline bool ss_interval(V3 cA, V3 vA, float nA, V3 cB, V3 vB, float nB, float rs,
+                                   float t_begin, float t_end, LeafLen leaf = default_leaf_len()) {
+  return ss_interval_impl<Coop, false>(cA, vA, nA, cB, vB, nB, rs, t_begin, t_end, leaf) == kWalkTrue;
 }
 
 // min_dist_at_time_sphere_plane, distance.c:305-321: max(|s| - r, 0), |s|-r in double.

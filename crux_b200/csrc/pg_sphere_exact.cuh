@@ -66,7 +66,7 @@ static __device__ __noinline__ bool pair_gate_far(const float4 *P4, const float4
 // Exact visit of two spheres (world.c:481-541 with the sphere-sphere table entries).
 // All lanes call it with identical arguments.  Returns true if an event fires; A and B updated.
 // Gate = false: the caller already applied pair_gate_rejects to this very state.
-template <bool Gate, bool Coop>
+template <bool Gate, int Coop>
 static __device__ __forceinline__ bool sphere_pair_exact_impl(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
   V3 cA = v3(0.0f + A.px, 0.0f + A.py, 0.0f + A.pz);     // centre (0,0,0) + position, distance.c:283
   V3 cB = v3(0.0f + B.px, 0.0f + B.py, 0.0f + B.pz);
@@ -84,11 +84,36 @@ static __device__ __forceinline__ bool sphere_pair_exact_impl(Sphere &A, Sphere 
   return true;
 }
 static __device__ __noinline__ bool sphere_pair_exact(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
-  return sphere_pair_exact_impl<true, false>(A, B, dt, leaf);
+  return sphere_pair_exact_impl<true, 0>(A, B, dt, leaf);
 }
 // Warp-uniform variant (all 32 lanes, identical arguments, already gated): the lanes share the leaf scan.
 static __device__ __noinline__ bool sphere_pair_exact_gated(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
-  return sphere_pair_exact_impl<false, true>(A, B, dt, leaf);
+  return sphere_pair_exact_impl<false, 1>(A, B, dt, leaf);
+}
+
+// One thread per pair with a bounded walk: 0 = no event, 1 = event (A, B updated), 2 = the interval
+// search is one of the rare long ones (a grazing pair): nothing changed, evaluate the visit with a
+// whole block instead (sphere_pair_exact_block).
+static __device__ __noinline__ int sphere_pair_exact_try(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
+  V3 cA = v3(0.0f + A.px, 0.0f + A.py, 0.0f + A.pz);
+  V3 cB = v3(0.0f + B.px, 0.0f + B.py, 0.0f + B.pz);
+  V3 vA = v3(A.vx, A.vy, A.vz), vB = v3(B.vx, B.vy, B.vz);
+  float rs = A.r + B.r;
+  float nA = pgm::norm(vA), nB = pgm::norm(vB);
+  if (pair_gate_rejects(cA, vA, cB, vB, rs, nA + nB, dt)) return 0;
+  const int r = pgm::ss_interval_impl<0, true>(cA, vA, nA, cB, vB, nB, rs, 0.0f, dt, leaf);
+  if (r != pgm::kWalkTrue) return r == pgm::kWalkGaveUp ? 2 : 0;
+  pgm::Contact c = pgm::ss_narrow(cA, vA, cB, vB, rs);
+  if (!(c.hit && c.t >= 0)) return 0;
+  V3 pA = v3(A.px, A.py, A.pz), pB = v3(B.px, B.py, B.pz);
+  pgm::ss_resolve(pA, vA, v3(0.0f, 0.0f, 0.0f), pB, vB, v3(0.0f, 0.0f, 0.0f), rs, c.t);
+  A.px = pA.x; A.py = pA.y; A.pz = pA.z; A.vx = vA.x; A.vy = vA.y; A.vz = vA.z;
+  B.px = pB.x; B.py = pB.y; B.pz = pB.z; B.vx = vB.x; B.vy = vB.y; B.vz = vB.z;
+  return 1;
+}
+// All threads of the block, identical arguments (gate included): they share the leaf scan.
+static __device__ __noinline__ bool sphere_pair_exact_block(Sphere &A, Sphere &B, float dt, pgm::LeafLen leaf) {
+  return sphere_pair_exact_impl<true, 2>(A, B, dt, leaf);
 }
 
 // Exact visit sphere x plane (per lane, divergent).  Returns true if an event fires.
