@@ -236,7 +236,6 @@ def run_large_arm(args, cfg):
         torch.cuda.synchronize()
 
     world.step(dt, args.warmup)
-    world.fixed_point_ns(reset=True)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -256,7 +255,6 @@ def run_large_arm(args, cfg):
     barrier()
     clocks = sampler.stop()
     gpu_launches = world.launches - launches0
-    fp_ns = world.fixed_point_ns(reset=True)           # phases of the cooperative fixed-point kernel over the timed steps
     # per-kernel breakdown: a few more steps AFTER the timed region with the library's per-kernel event pairs
     # switched on (they are off by default: they double the API calls of a launch-bound pipeline)
     breakdown_steps = min(8, args.steps)
@@ -315,10 +313,7 @@ def run_large_arm(args, cfg):
             "gpu_launches": int(gpu_launches),
             "fixed_point": {"iterations_mean": float(np.mean(iters)), "iterations_max": int(max(iters)), "proven_exact_every_step": bool(proven)},
             "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
-            "kernel_ms_note": "per-kernel CUDA-event pairs from extra steps driven launch by launch (pg_large_set_timing); the timed steps "
-                              "run the fixed point (k_eval, k_check, k_requery) inside one cooperative launch, see fixed_point_ms_per_step",
-            "fixed_point_ms_per_step": {k: v * 1e-6 / args.steps for k, v in fp_ns.items() if k != "hard_pairs"},
-            "hard_pairs_per_step": fp_ns.get("hard_pairs", 0) / args.steps,
+            "kernel_ms_note": "per-kernel CUDA-event pairs from extra steps after the timed region (pg_large_set_timing)",
             "stats": stats,
         }
         print(json.dumps(line), flush=True)

@@ -30,8 +30,6 @@
 #include "pg_math.cuh"
 #include "pg_sphere_exact.cuh"
 
-#include <cooperative_groups.h>
-
 #include <algorithm>
 #include <vector>
 
@@ -74,9 +72,10 @@ struct Flags {
   int unsafe;             // non-finite state or an envelope the grid cannot hold
   unsigned long long n_pairs;
   unsigned long long n_hits;
+  unsigned long long n_carried;   // hits d_clear_carry copied this iteration; folded into n_hits by k_check
   unsigned n_touched;
   unsigned n_fast;        // bodies on the fast list
-  unsigned n_active;      // candidate pairs k_select handed to k_eval this iteration
+  unsigned n_active;      // candidate pairs the selection (k_begin) handed to k_eval this iteration
   unsigned n_hard;        // of those, pairs k_eval passed on to k_eval_hard (long interval searches)
 };
 
@@ -115,7 +114,7 @@ struct LargeView {
   // candidates
   int2 *pairs;
   long long pairs_cap;
-  unsigned *active;                  // [2 pairs_cap] indices into pairs[]: the ones this iteration has to look at (k_select), and from
+  unsigned *active;                  // [2 pairs_cap] indices into pairs[]: the ones this iteration has to look at (k_begin), and from
                                      // pairs_cap on the ones k_eval deferred to k_eval_hard
   // timelines, double buffered
   unsigned char *tl_cnt[2];
@@ -123,6 +122,9 @@ struct LargeView {
                                       // new / changed entries carry a flag in tl_pos[..].w
   int *seen;                          // body already on the touched list (this step)
   unsigned *touched_bits;             // the same as a bitmap (n/32 words): the cheap test k_eval makes for every pair
+  unsigned *dirty_bits[2];            // per timeline buffer: the body's timeline differs from the previous iteration's (k_check)
+  unsigned *pushed_bits;              // the body received an entry from k_eval in the current iteration, or had one that k_eval
+                                      // was to decide about again: k_check must compare its timelines
   int *touched;                       // bodies that ever received a timeline entry this step
   unsigned *cell_rank;                // rank of a body inside its cell (returned by the counting atomic)
   unsigned char *grown;               // envelope grew during the current fixed point
@@ -148,15 +150,51 @@ __host__ __device__ __forceinline__ float o2f(unsigned o) {
 #endif
 }
 
+// Contact events of the streaming kernels (k_pass3, k_finalize).  Tens of thousands per step used to take
+// one atomic each on the single event counter, which serialised them for about as long as the kernel needs
+// to stream the whole state; a block now stages its events in shared memory and appends them with one
+// atomic when it is through (kEventInit / kEventFlush: called by ALL threads of the block).  The order in
+// the buffer is irrelevant: the host restores solve order at read-back.
+constexpr int kEventStage = 192;
+enum { kEventAdd = 0, kEventFlush = 1, kEventInit = 2 };
+// (the view's fields are passed by value: a reference to the kernel parameter would make every thread copy
+// the whole 400-byte struct to its local stack)
+__device__ __noinline__ void event_stage_impl(PgEvent *events, int *n_events, int max_events, int mode, int step, int pass, int ac, int ai, int bc, int bi) {
+  __shared__ PgEvent s_ev[kEventStage];
+  __shared__ unsigned s_cnt;
+  __shared__ int s_base;
+  if (mode == kEventInit) {
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    return;
+  }
+  if (mode == kEventAdd) {
+    if (max_events <= 0) return;
+    PgEvent e;
+    e.world = 0; e.step = step; e.event_type = 0;
+    e.a_class = ac; e.a_index = ai; e.b_class = bc; e.b_index = bi;
+    e.pad_ = pass << 8;
+    const unsigned st = atomicAdd(&s_cnt, 1u);
+    if (st < (unsigned)kEventStage) { s_ev[st] = e; return; }
+    const int slot = atomicAdd(n_events, 1);
+    if (slot < max_events) events[slot] = e;
+    return;
+  }
+  __syncthreads();
+  const int staged = (int)min(s_cnt, (unsigned)kEventStage);
+  if (threadIdx.x == 0 && staged) s_base = atomicAdd(n_events, staged);
+  __syncthreads();
+  for (int e = threadIdx.x; e < staged; e += blockDim.x)
+    if (s_base + e < max_events) events[s_base + e] = s_ev[e];
+  __syncthreads();
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+}
+__device__ __forceinline__ void event_stage(const LargeView &v, int mode, int step, int pass, int ac, int ai, int bc, int bi) {
+  event_stage_impl(v.events, v.n_events, v.max_events, mode, step, pass, ac, ai, bc, bi);
+}
 __device__ __forceinline__ void emit_event(const LargeView &v, int step, int pass, int ac, int ai, int bc, int bi) {
-  if (v.max_events <= 0) return;
-  int slot = atomicAdd(v.n_events, 1);
-  if (slot >= v.max_events) return;
-  PgEvent e;
-  e.world = 0; e.step = step; e.event_type = 0;
-  e.a_class = ac; e.a_index = ai; e.b_class = bc; e.b_index = bi;
-  e.pad_ = pass << 8;
-  v.events[slot] = e;
+  event_stage(v, kEventAdd, step, pass, ac, ai, bc, bi);
 }
 
 __device__ __forceinline__ float envelope(float r, float vx, float vy, float vz, float dt) {
@@ -166,10 +204,11 @@ __device__ __forceinline__ float envelope(float r, float vx, float vy, float vz,
 }
 
 // ---------------------------------------------------------------- 1. pass 3 + envelope + bounds
-__global__ void k_pass3(LargeView v, float dt, int step, int do_planes) {
+__global__ void k_pass3(LargeView v, float dt, int step, int do_planes, int full_reset) {
   __shared__ float4 s_pl[kMaxPlanesL];
+  __shared__ float s_red[8][15];                   // per-warp partials of the bounds and the running statistics
   if (threadIdx.x < v.ns) s_pl[threadIdx.x] = v.planes[threadIdx.x];
-  __syncthreads();
+  event_stage(v, kEventInit, 0, 0, 0, 0, 0, 0);     // (includes the block barrier)
   pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
   const bool gate_ok = dt > 1.0e-9f;
   float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f}, emax = 0.0f;
@@ -244,12 +283,16 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes) {
     const float e = envelope(q.w, q.x, q.y, q.z, dt);
     v.env[i] = e;
     v.env_prev[i] = e;
-    v.grown[i] = 0;
-    v.tl_cnt[0][i] = 0;
-    v.tl_cnt[1][i] = 0;
-    v.tl_chg[0][i] = 0xffffffffffffffffull;
-    v.tl_chg[1][i] = 0xffffffffffffffffull;
-    v.seen[i] = 0;
+    if (full_reset) {
+      // per-step bookkeeping of the fixed point: only bodies that get a timeline entry ever change it, and
+      // k_reset_touched puts those back at the end of the step (23 B per body and step not written here)
+      v.grown[i] = 0;
+      v.tl_cnt[0][i] = 0;
+      v.tl_cnt[1][i] = 0;
+      v.tl_chg[0][i] = 0xffffffffffffffffull;
+      v.tl_chg[1][i] = 0xffffffffffffffffull;
+      v.seen[i] = 0;
+    }
     if (!(fabsf(p.x) < 1.0e15f && fabsf(p.y) < 1.0e15f && fabsf(p.z) < 1.0e15f && e < 1.0e15f)) { bad = true; continue; }
     lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
     hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
@@ -267,12 +310,24 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes) {
     emax = fmaxf(emax, __shfl_xor_sync(kFullMask, emax, o));
     for (int k = 0; k < 8; k++) rs[k] += __shfl_xor_sync(kFullMask, rs[k], o);
   }
-  if ((threadIdx.x & 31) == 0) {
-    for (int k = 0; k < 3; k++) { atomicMin(v.bbox + k, f2o(lo[k])); atomicMax(v.bbox + 3 + k, f2o(hi[k])); }
-    atomicMax(v.bbox + 6, f2o(emax));
-    if (rs[7] > 0.0f) for (int k = 0; k < 8; k++) atomicAdd(v.rstat + k, rs[k]);
+  // one set of global atomics per BLOCK (the 15 addresses are shared by every warp of the grid)
+  const int wib = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0 && wib < 8) {
+    for (int k = 0; k < 3; k++) { s_red[wib][k] = lo[k]; s_red[wib][3 + k] = hi[k]; }
+    s_red[wib][6] = emax;
+    for (int k = 0; k < 8; k++) s_red[wib][7 + k] = rs[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 15) {
+    const int k = threadIdx.x, nw = min((int)(blockDim.x >> 5), 8);
+    float x = s_red[0][k];
+    for (int q = 1; q < nw; q++) x = k < 3 ? fminf(x, s_red[q][k]) : (k < 7 ? fmaxf(x, s_red[q][k]) : x + s_red[q][k]);
+    if (k < 3) atomicMin(v.bbox + k, f2o(x));
+    else if (k < 7) atomicMax(v.bbox + k, f2o(x));
+    else if (x != 0.0f) atomicAdd(v.rstat + (k - 7), x);
   }
   if (bad) atomicExch(&v.flags->unsafe, 1);
+  event_stage(v, kEventFlush, 0, 0, 0, 0, 0, 0);
 }
 
 __global__ void k_grid_params(LargeView v) {
@@ -569,7 +624,7 @@ __device__ __forceinline__ BodyState state_at(const LargeView &v, int src, int b
 // called by ALL threads of the block at the start / end of every phase that pushes timeline entries).
 constexpr int kTouchStage = 512;
 enum { kTouchAdd = 0, kTouchFlush = 1, kTouchInit = 2 };
-__device__ __noinline__ void touched_stage(const LargeView &v, int b, int mode) {
+__device__ __noinline__ void touched_stage_impl(int *touched, unsigned *n_touched, int b, int mode) {
   __shared__ int s_list[kTouchStage];
   __shared__ unsigned s_cnt, s_base;
   if (mode == kTouchInit) {
@@ -580,19 +635,20 @@ __device__ __noinline__ void touched_stage(const LargeView &v, int b, int mode) 
   if (mode == kTouchAdd) {
     const unsigned slot = atomicAdd(&s_cnt, 1u);
     if (slot < (unsigned)kTouchStage) s_list[slot] = b;
-    else v.touched[atomicAdd(&v.flags->n_touched, 1u)] = b;
+    else touched[atomicAdd(n_touched, 1u)] = b;
     return;
   }
   __syncthreads();
   const unsigned staged = min(s_cnt, (unsigned)kTouchStage);
-  if (threadIdx.x == 0 && staged) s_base = atomicAdd(&v.flags->n_touched, staged);
+  if (threadIdx.x == 0 && staged) s_base = atomicAdd(n_touched, staged);
   __syncthreads();
-  for (unsigned e = threadIdx.x; e < staged; e += blockDim.x) v.touched[s_base + e] = s_list[e];
+  for (unsigned e = threadIdx.x; e < staged; e += blockDim.x) touched[s_base + e] = s_list[e];
   __syncthreads();
   if (threadIdx.x == 0) s_cnt = 0;
   __syncthreads();
 }
 
+__device__ __forceinline__ void touched_stage(const LargeView &v, int b, int mode) { touched_stage_impl(v.touched, &v.flags->n_touched, b, mode); }
 __device__ __forceinline__ void timeline_push(const LargeView &v, int dst, int b, unsigned long long key, const Sphere &s) {
   // tl_cnt is a byte array; claim a slot with a 32-bit CAS on the containing word
   unsigned *word = (unsigned *)(v.tl_cnt[dst] + (b & ~3));
@@ -606,6 +662,7 @@ __device__ __forceinline__ void timeline_push(const LargeView &v, int dst, int b
     old = atomicCAS(word, assumed, assumed + (1u << sh));
   } while (old != assumed);
   if (slot >= kTimeline) { atomicExch(&v.flags->overflow_timeline, 1); return; }
+  atomicOr(&v.pushed_bits[b >> 5], 1u << (b & 31));
   if (slot == 0 && atomicExch(&v.seen[b], 1) == 0) { touched_stage(v, b, kTouchAdd); atomicOr(&v.touched_bits[b >> 5], 1u << (b & 31)); }
   v.tl_key[dst][(size_t)b * kTimeline + slot] = key;
   v.tl_pos[dst][(size_t)b * kTimeline + slot] = make_float4(s.px, s.py, s.pz, 0.0f);
@@ -664,11 +721,12 @@ __device__ __forceinline__ bool affected(const LargeView &v, int src, int b, uns
 //                 -- the very gate sphere_pair_exact opens with -- reject cannot fire and is dropped.
 //                 If the first gate passes the pair is kept whatever the second says (a hit would
 //                 change what the second visit sees).
-//   later         pairs with a body that has a timeline (or appended by k_requery): the rest has
-//                 nothing to carry and nothing that could have changed.
+//   later         pairs with a DIRTY body -- one whose timeline changed in the previous iteration (k_check)
+//                 -- or appended by k_requery.  Every visit of two clean bodies would come out as
+//                 recorded; d_clear_carry has copied those entries already.
 // The order of the active list is irrelevant (timeline slots are claimed atomically anyway).
 constexpr int kSelItems = 4;
-__device__ __forceinline__ void d_select(const LargeView &v, int iter, float dt) {
+__device__ __forceinline__ void d_select(const LargeView &v, int src, int iter, float dt) {
   __shared__ unsigned s_cnt, s_base;
   const int kSelBlock = (int)blockDim.x;
   const long long np = (long long)min((unsigned long long)v.pairs_cap, v.flags->n_pairs);
@@ -686,7 +744,7 @@ __device__ __forceinline__ void d_select(const LargeView &v, int iter, float dt)
       const int i = fresh ? ~pr.x : pr.x, j = pr.y;
       bool need = fresh;
       if (!need && iter > 0) {
-        need = ((v.touched_bits[i >> 5] >> (i & 31)) & 1u) || ((v.touched_bits[j >> 5] >> (j & 31)) & 1u);
+        need = ((v.dirty_bits[src][i >> 5] >> (i & 31)) & 1u) || ((v.dirty_bits[src][j >> 5] >> (j & 31)) & 1u);
       } else if (!need) {
         const float4 pi = v.pos_rest[i], qi = v.vel_rad[i], pj = v.pos_rest[j], qj = v.vel_rad[j];
         // visit (i, j) of row i (i < j): neither body integrated yet
@@ -720,7 +778,6 @@ __device__ __forceinline__ void d_select(const LargeView &v, int iter, float dt)
     __syncthreads();                               // s_base is rewritten by the next tile
   }
 }
-__global__ void __launch_bounds__(256) k_select(LargeView v, int iter, float dt) { d_select(v, iter, dt); }
 
 // Both visits of candidate pair k on the hypothesis `src`; hits go to the `dst` timelines.  Returns the
 // number of hits, or -1 when a one-thread evaluation met a long interval search: nothing has been
@@ -817,10 +874,17 @@ __device__ __forceinline__ bool same_state(float4 p0, float4 q0, float4 p1, floa
          __float_as_uint(p0.z) == __float_as_uint(p1.z) && __float_as_uint(q0.x) == __float_as_uint(q1.x) &&
          __float_as_uint(q0.y) == __float_as_uint(q1.y) && __float_as_uint(q0.z) == __float_as_uint(q1.z);
 }
-__device__ __forceinline__ void d_check(const LargeView &v, int src, int dst, float dt) {
+__device__ __forceinline__ void d_check(const LargeView &v, int src, int dst, int iter, float dt) {
   const int nt = (int)v.flags->n_touched;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    v.flags->n_hits += v.flags->n_carried; v.flags->n_carried = 0ull;
+    v.flags->n_active = 0u; v.flags->n_hard = 0u;      // for the next iteration's k_begin (zero at step start)
+  }
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     const int b = v.touched[t];
+    // a clean body that k_eval gave nothing holds exactly the entries d_clear_carry copied: same timeline,
+    // flags already in their rest state, envelope validated when the entries were new
+    if (iter > 0 && !((v.dirty_bits[src][b >> 5] >> (b & 31)) & 1u) && !((v.pushed_bits[b >> 5] >> (b & 31)) & 1u)) continue;
     const int c0 = min((int)v.tl_cnt[src][b], kTimeline), c1 = min((int)v.tl_cnt[dst][b], kTimeline);
     unsigned long long rem = 0xffffffffffffffffull;
     bool any = false;
@@ -844,7 +908,7 @@ __device__ __forceinline__ void d_check(const LargeView &v, int src, int dst, fl
     }
     if (v.tl_cnt[src][b] != v.tl_cnt[dst][b] && rem == 0xffffffffffffffffull && !any) rem = 0ull;      // overflowed counts: be safe
     v.tl_chg[dst][b] = rem;
-    if (any || rem != 0xffffffffffffffffull) v.flags->changed = 1;
+    if (any || rem != 0xffffffffffffffffull) { v.flags->changed = 1; atomicOr(&v.dirty_bits[dst][b >> 5], 1u << (b & 31)); }
     // envelope validation on the new timeline: every state the body takes must stay inside env[b]
     const float4 p = v.pos_rest[b], q = v.vel_rad[b];
     float need = 0.0f;
@@ -870,11 +934,45 @@ __device__ __forceinline__ void d_check(const LargeView &v, int src, int dst, fl
     }
   }
 }
-// reset the destination timelines of the touched bodies before an iteration refills them
-__device__ __forceinline__ void d_clear(const LargeView &v, int dst) {
+// Start of an iteration: the destination timelines of the touched bodies.  A DIRTY body (its timeline
+// changed in the previous iteration) starts empty: every pair it belongs to is on the selection's list and
+// k_eval rebuilds its entries.  A clean body keeps, by plain copy, the entries whose partner is clean as
+// well -- visits nothing has changed for; its entries with a dirty partner come back through k_eval.
+// From the third iteration on almost everybody is clean, and an iteration costs what its few changes cost.
+__device__ __forceinline__ void d_clear_carry(const LargeView &v, int src, int dst, int iter) {
   const int nt = (int)v.flags->n_touched;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { v.flags->changed = 0; v.flags->grew = 0; v.flags->n_hits = 0ull; v.flags->n_active = 0u; v.flags->n_hard = 0u; }
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) v.tl_cnt[dst][v.touched[t]] = 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { v.flags->changed = 0; v.flags->grew = 0; v.flags->n_hits = 0ull; }      // (n_active, n_hard: k_check)
+  unsigned carried = 0;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    const int b = v.touched[t];
+    const unsigned bit = 1u << (b & 31);
+    atomicAnd(&v.dirty_bits[dst][b >> 5], ~bit);
+    atomicAnd(&v.pushed_bits[b >> 5], ~bit);
+    int m = 0;
+    if (iter > 0 && !(v.dirty_bits[src][b >> 5] & bit)) {
+      const int cnt = min((int)v.tl_cnt[src][b], kTimeline);
+      for (int k = 0; k < cnt; k++) {
+        const unsigned long long key = v.tl_key[src][(size_t)b * kTimeline + k];
+        const int row = (int)(key >> 32), col = (int)(key & 0xffffffffu);
+        const int partner = row == b ? col : row;
+        if ((v.dirty_bits[src][partner >> 5] >> (partner & 31)) & 1u) {
+          // k_eval decides about this entry (it may not come back): k_check has to look at this body
+          atomicOr(&v.pushed_bits[b >> 5], bit);
+          continue;
+        }
+        const float4 tp = v.tl_pos[src][(size_t)b * kTimeline + k];
+        v.tl_key[dst][(size_t)b * kTimeline + m] = key;
+        v.tl_pos[dst][(size_t)b * kTimeline + m] = make_float4(tp.x, tp.y, tp.z, 0.0f);
+        v.tl_vel[dst][(size_t)b * kTimeline + m] = v.tl_vel[src][(size_t)b * kTimeline + k];
+        m++;
+        if (row == b) carried++;                   // one hit per visit: counted by its row body
+      }
+      v.tl_chg[dst][b] = 0xffffffffffffffffull;
+    }
+    v.tl_cnt[dst][b] = (unsigned char)m;
+  }
+  carried = __reduce_add_sync(kFullMask, carried);
+  if ((threadIdx.x & 31) == 0 && carried) atomicAdd(&v.flags->n_carried, (unsigned long long)carried);   // (n_hits is being reset by this very kernel)
 }
 
 // Envelopes of a few bodies grew (a contact sped them up).  Find the candidate pairs they gain --
@@ -952,84 +1050,22 @@ __device__ __forceinline__ void d_requery_done(const LargeView &v) {
 }
 
 
-// ---------------------------------------------------------------- the whole fixed point in ONE launch
-// A cooperative kernel (every block resident, grid-wide barriers between the phases) runs the
-// iterations that lw_step_once otherwise drives from the host with seven launches and one read-back
-// each.  It stops when the fixed point is reached, after kMaxIter iterations, or when something only
-// the host can do is needed (a buffer has to grow); `FpStatus` says where it stopped.
-struct FpStatus {
-  int iterations;          // iterations run by this launch
-  int src;                 // timeline buffer that holds the latest hypothesis
-  int converged;
-  int requery_pending;     // k_requery_done still owed (only when stopped for the host)
-  int stop;                // 0 = loop finished, 1 = timeline overflow, 2 = candidate list overflowed while k_requery appended
-  int unsafe_seen;
-  unsigned long long pairs_before;   // list length before the iteration that stopped (stop == 2)
-  unsigned long long phase_ns[8];    // time per phase, summed over the iterations: clear, select, eval, hard, check, requery, control; [7] = pairs sent to k_eval_hard
-};
 __global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) { d_eval(v, src, dst, iter, dt); }
 __global__ void __launch_bounds__(512) k_eval_hard(LargeView v, int src, int dst, int iter, float dt) { d_eval_hard(v, src, dst, iter, dt); }
-__global__ void k_check(LargeView v, int src, int dst, float dt) { d_check(v, src, dst, dt); }
-__global__ void k_clear(LargeView v, int dst) { d_clear(v, dst); }
+__global__ void k_check(LargeView v, int src, int dst, int iter, float dt) { d_check(v, src, dst, iter, dt); }
+// One launch opens an iteration: the carry (per touched body) and the selection (per candidate pair) read the
+// same source hypothesis and write disjoint things.
+__global__ void __launch_bounds__(256) k_begin(LargeView v, int src, int dst, int iter, float dt) {
+  d_clear_carry(v, src, dst, iter);
+  d_select(v, src, iter, dt);
+}
 __global__ void k_requery(LargeView v, int src) { d_requery(v, src); }
 __global__ void k_requery_done(LargeView v) { d_requery_done(v); }
-
-__global__ void __launch_bounds__(128, 4) k_fixed_point(LargeView v, int it_start, int src, int requery_pending, float dt, FpStatus *status) {
-  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
-  const volatile Flags *vf = v.flags;
-  int dst = src ^ 1;
-  int converged = 0, stop = 0, unsafe_seen = 0, iterations = 0;
-  unsigned long long pairs_before = 0;
-  const bool clerk = blockIdx.x == 0 && threadIdx.x == 0;
-  unsigned long long t_prev = 0, ns[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  auto now = [] { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; };
-  auto lap = [&](int k) { if (clerk) { const unsigned long long t = now(); ns[k] += t - t_prev; t_prev = t; } };
-  if (clerk) t_prev = now();
-  for (int it = it_start; it < kMaxIter; it++) {
-    pairs_before = min(vf->n_pairs, (unsigned long long)v.pairs_cap);
-    grid.sync();                                   // everybody has read the flags of the previous iteration
-    if (requery_pending) { d_requery_done(v); requery_pending = 0; }
-    d_clear(v, dst);                               // also resets the per-iteration flags
-    grid.sync(); lap(0);
-    d_select(v, it, dt);
-    grid.sync(); lap(1);
-    d_eval(v, src, dst, it, dt);
-    grid.sync(); lap(2);
-    if (vf->n_hard) d_eval_hard(v, src, dst, it, dt);
-    if (clerk) ns[7] += vf->n_hard;
-    grid.sync(); lap(3);
-    d_check(v, src, dst, dt);
-    grid.sync(); lap(4);
-    d_requery(v, dst);
-    grid.sync(); lap(5);
-    iterations++;
-    const int grew = vf->grew, changed = vf->changed;
-    if (vf->overflow_timeline) { stop = 1; break; }
-    src ^= 1; dst ^= 1;
-    if (grew) {
-      requery_pending = 1;
-      if (vf->overflow_pairs) { stop = 2; break; }
-      if (vf->unsafe) unsafe_seen = 1;
-      continue;                                    // at least one more iteration with the new pairs
-    }
-    if (!changed) { converged = 1; break; }
-  }
-  if (!stop && requery_pending) {
-    grid.sync();
-    d_requery_done(v);
-    requery_pending = 0;
-  }
-  lap(6);
-  if (clerk) {
-    status->iterations = iterations; status->src = src; status->converged = converged; status->requery_pending = requery_pending;
-    status->stop = stop; status->unsafe_seen = unsafe_seen; status->pairs_before = pairs_before;
-    for (int k = 0; k < 8; k++) status->phase_ns[k] = ns[k];
-  }
-}
 
 // ---------------------------------------------------------------- 5. final state + pass-4 events
 __global__ void k_finalize(LargeView v, int src, float dt, int step) {
   const int stride = gridDim.x * blockDim.x;
+  event_stage(v, kEventInit, 0, 0, 0, 0, 0, 0);
   // two bodies per trip: the second one's loads are issued before the first one's stores
   float4 p_next = make_float4(0, 0, 0, 0), q_next = p_next;
   int cnt_next = 0;
@@ -1058,6 +1094,26 @@ __global__ void k_finalize(LargeView v, int src, float dt, int step) {
     }
     v.pos_rest[b] = p;
     v.vel_rad[b] = q;
+  }
+  event_stage(v, kEventFlush, 0, 0, 0, 0, 0, 0);
+}
+
+// End of step: the bodies on the touched list are the only ones whose fixed-point bookkeeping left its
+// rest state; put it back so that the next k_pass3 does not have to rewrite it for every body.
+__global__ void k_reset_touched(LargeView v) {
+  const int nt = (int)v.flags->n_touched;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
+    const int b = v.touched[t];
+    v.grown[b] = 0;
+    v.tl_cnt[0][b] = 0;
+    v.tl_cnt[1][b] = 0;
+    v.tl_chg[0][b] = 0xffffffffffffffffull;
+    v.tl_chg[1][b] = 0xffffffffffffffffull;
+    v.seen[b] = 0;
+    const unsigned bit = 1u << (b & 31);
+    atomicAnd(&v.dirty_bits[0][b >> 5], ~bit);
+    atomicAnd(&v.dirty_bits[1][b >> 5], ~bit);
+    atomicAnd(&v.pushed_bits[b >> 5], ~bit);
   }
 }
 
@@ -1119,10 +1175,7 @@ struct PgLarge {
   int cap_static_total;
   long long last_candidates, last_hits;
   int step_in_call;
-  int fp_blocks;                 // grid of the cooperative fixed-point kernel (every block resident); 0 = not available
-  int fused;                     // PG_LARGE_FUSED was set when the world was created
-  FpStatus *d_fp_status;
-  unsigned long long fp_phase_ns[8];
+  int bookkeeping_clean;         // the last step ended with k_reset_touched: k_pass3 may skip the per-body resets
   int timing;                    // record a CUDA event pair around every kernel (pg_large_kernel_ms); off by default:
                                  // the pipeline of a small world is launch-bound and the events double its API calls
 };
@@ -1211,7 +1264,15 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   PG_CUDA(cudaMemsetAsync(v.flags, 0, sizeof(Flags), w->stream));
   PG_CUDA(cudaMemsetAsync(v.rstat, 0, sizeof(float) * 8, w->stream));
   PG_CUDA(cudaMemsetAsync(v.touched_bits, 0, sizeof(unsigned) * ((size_t)v.n / 32 + 1), w->stream));
-  LW_LAUNCH(w, K_PASS3, k_pass3, lw_grid(w, v.n, 256), 256, v, dt, w->step_in_call, 1);
+  const int full_reset = w->bookkeeping_clean ? 0 : 1;
+  if (full_reset) {
+    const size_t words = (size_t)w->cap_n / 32 + 1;
+    PG_CUDA(cudaMemsetAsync(v.dirty_bits[0], 0, sizeof(unsigned) * words, w->stream));
+    PG_CUDA(cudaMemsetAsync(v.dirty_bits[1], 0, sizeof(unsigned) * words, w->stream));
+    PG_CUDA(cudaMemsetAsync(v.pushed_bits, 0, sizeof(unsigned) * words, w->stream));
+  }
+  w->bookkeeping_clean = 0;                     // until this step's k_reset_touched is in the stream
+  LW_LAUNCH(w, K_PASS3, k_pass3, lw_grid(w, v.n, 256), 256, v, dt, w->step_in_call, 1, full_reset);
   w->last_proven = 1;
   w->last_iterations = 0;
   int rc = lw_build_pairs(w);
@@ -1235,59 +1296,8 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   const bool debug = getenv("PG_LARGE_DEBUG") != nullptr && w->timing;
   bool converged = false;
   int requeries = 0;
-  // PG_LARGE_FUSED=1 (read at pg_large_create): the fixed point runs inside ONE cooperative launch
-  // (k_fixed_point) with one read-back at the end instead of the launch-per-kernel loop below.  Measured
-  //  it saves 4/5 of the launches but is 2 % faster only for a 65 k world and 3-7 %
-  // slower from 1 M bodies up (a resident grid is smaller than the grids the phases get on their own), so
-  // it is opt-in; it also reports the time per phase (pg_large_fixed_point_ns).
-  const bool fused_ok = w->fused != 0;
   int src = 0, dst = 1;
-  int it0 = 0;
   bool requery_pending = false;
-  if (fused_ok && !w->timing && w->fp_blocks > 0) {
-    for (;;) {
-      int a_it = it0, a_src = src, a_pending = requery_pending ? 1 : 0;
-      float a_dt = dt;
-      FpStatus *a_status = w->d_fp_status;
-      void *args[] = {&v, &a_it, &a_src, &a_pending, &a_dt, &a_status};
-      PG_CUDA(cudaLaunchCooperativeKernel((const void *)k_fixed_point, dim3(w->fp_blocks), dim3(128), args, 0, w->stream));
-      w->launches++;
-      FpStatus st;
-      PG_CUDA(cudaMemcpyAsync(&st, w->d_fp_status, sizeof(st), cudaMemcpyDeviceToHost, w->stream));
-      rc = lw_read_flags(w, &f);
-      if (rc) return rc;
-      for (int k = 0; k < 8; k++) w->fp_phase_ns[k] += st.phase_ns[k];
-      w->last_iterations += st.iterations;
-      w->last_hits = (long long)f.n_hits;
-      w->last_candidates = (long long)f.n_pairs;
-      src = st.src; dst = src ^ 1;
-      if (st.unsafe_seen) w->last_proven = 0;
-      if (st.stop == 1) { pg_set_error("large world: more than %d contacts on one body in one step", kTimeline); return PG_ERR_CAPACITY; }
-      if (st.stop == 2) {
-        // k_requery only appends: keep the list as it was, make room, let it append again, then carry on
-        rc = lw_grow_pairs(w, f.n_pairs, st.pairs_before);
-        if (rc) return rc;
-        LW_LAUNCH(w, K_BOUNDS, k_requery, w->sm_count * 8, 128, v, src);
-        rc = lw_read_flags(w, &f);
-        if (rc) return rc;
-        if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
-        if (f.unsafe) w->last_proven = 0;
-        w->last_candidates = (long long)f.n_pairs;
-        requery_pending = true;
-        it0 += st.iterations;
-        if (it0 < kMaxIter) continue;
-        k_requery_done<<<w->sm_count * 8, 256, 0, w->stream>>>(v);
-        w->launches++;
-      }
-      converged = st.converged != 0;
-      break;
-    }
-    if (!converged) w->last_proven = 0;
-    LW_LAUNCH(w, K_FINAL, k_finalize, lw_grid(w, v.n, 256), 256, v, src, dt, w->step_in_call);
-    PG_CUDA(cudaGetLastError());
-    PG_CUDA(cudaStreamSynchronize(w->stream));
-    return PG_OK;
-  }
   // One host read-back per iteration: k_requery always rides along (it returns at once for bodies whose
   // envelope did not grow), its bookkeeping kernel is deferred to the start of the next iteration so
   // that an overflowing candidate list can still be grown and the append repeated.
@@ -1298,18 +1308,17 @@ static int lw_step_once(PgLarge *w, float dt_in) {
       w->launches++;
       requery_pending = false;
     }
-    k_clear<<<wide_grid, 256, 0, w->stream>>>(v, dst);      // also resets the per-iteration flags
-    w->launches++;
     const unsigned long long pairs_before = std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
     const int np = (int)std::min<unsigned long long>(pairs_before, 0x7fffffffull);
     // the active list's length stays on the device: k_eval runs as many blocks as fit at once and strides
     if (w->timing) cudaEventRecord(w->kev[K_EVAL][0], w->stream);
-    k_select<<<std::max(1, std::min((np + 256 * kSelItems - 1) / (256 * kSelItems), w->sm_count * 8)), 256, 0, w->stream>>>(v, it, dt);
+    (void)np;
+    k_begin<<<wide_grid, 256, 0, w->stream>>>(v, src, dst, it, dt);      // carry + selection; also resets the per-iteration flags
     k_eval<<<w->sm_count * 4, 128, 0, w->stream>>>(v, src, dst, it, dt);
     k_eval_hard<<<w->sm_count, 512, 0, w->stream>>>(v, src, dst, it, dt);
     if (w->timing) cudaEventRecord(w->kev[K_EVAL][1], w->stream);
     w->launches += 3;
-    LW_LAUNCH(w, K_CHECK, k_check, wide_grid, 256, v, src, dst, dt);
+    LW_LAUNCH(w, K_CHECK, k_check, wide_grid, 256, v, src, dst, it, dt);
     // candidates the grown envelopes add (on top of the NEW timelines); their bodies are marked dirty so
     // the next iteration re-evaluates them (warm start)
     LW_LAUNCH(w, K_BOUNDS, k_requery, wide_grid, 128, v, dst);
@@ -1354,6 +1363,9 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   if (!converged) w->last_proven = 0;
   (void)requeries;
   LW_LAUNCH(w, K_FINAL, k_finalize, lw_grid(w, v.n, 256), 256, v, src, dt, w->step_in_call);
+  k_reset_touched<<<w->sm_count * 4, 256, 0, w->stream>>>(v);
+  w->launches++;
+  w->bookkeeping_clean = 1;
   PG_CUDA(cudaGetLastError());
   PG_CUDA(cudaStreamSynchronize(w->stream));
   lw_accumulate(w, K_FINAL);
@@ -1440,6 +1452,9 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   PG_CUDA_NULL(cudaMalloc(&v.env_prev, sizeof(float) * n));
   PG_CUDA_NULL(cudaMalloc(&v.seen, sizeof(int) * n));
   PG_CUDA_NULL(cudaMalloc(&v.touched_bits, sizeof(unsigned) * (n / 32 + 1)));
+  PG_CUDA_NULL(cudaMalloc(&v.dirty_bits[0], sizeof(unsigned) * (n / 32 + 1)));
+  PG_CUDA_NULL(cudaMalloc(&v.dirty_bits[1], sizeof(unsigned) * (n / 32 + 1)));
+  PG_CUDA_NULL(cudaMalloc(&v.pushed_bits, sizeof(unsigned) * (n / 32 + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.touched, sizeof(int) * n));
   PG_CUDA_NULL(cudaMalloc(&v.cell_rank, sizeof(unsigned) * n));
   for (int k = 0; k < 2; k++) {
@@ -1455,15 +1470,6 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   PG_CUDA_NULL(cudaMalloc(&v.n_events, sizeof(int)));
   PG_CUDA_NULL(cudaMemset(v.n_events, 0, sizeof(int)));
   PG_CUDA_NULL(cudaMalloc(&w->d_stats, 8 * sizeof(double)));
-  PG_CUDA_NULL(cudaMalloc(&w->d_fp_status, sizeof(FpStatus)));
-  {
-    int coop = 0, per_sm = 0;
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-    if (coop && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fixed_point, 128, 0) == cudaSuccess && per_sm > 0)
-      w->fp_blocks = per_sm * w->sm_count;
-    w->fused = getenv("PG_LARGE_FUSED") != nullptr;
-    cudaGetLastError();
-  }
   PG_CUDA_NULL(cudaMalloc(&w->d_stage_pos, sizeof(float) * 3 * n));
   PG_CUDA_NULL(cudaMalloc(&w->d_stage_vel, sizeof(float) * 3 * n));
   PG_CUDA_NULL(cudaMalloc(&w->d_stage_rest, n));
@@ -1476,9 +1482,9 @@ void pg_large_destroy(PgLarge *w) {
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
   if (w->player_world) pg_worlds_destroy(w->player_world);
-  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.fast_list, v.touched_bits, v.block_sums, v.sorted,
+  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.fast_list, v.touched_bits, v.dirty_bits[0], v.dirty_bits[1], v.pushed_bits, v.block_sums, v.sorted,
                   v.pairs, v.active, v.grown, v.env_prev, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
-                  v.flags, v.events, v.n_events, w->d_stats, w->d_fp_status, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
+                  v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);
   cudaEventDestroy(w->ev0); cudaEventDestroy(w->ev1);
   for (int k = 0; k < K_COUNT; k++) { cudaEventDestroy(w->kev[k][0]); cudaEventDestroy(w->kev[k][1]); }
@@ -1533,6 +1539,7 @@ int pg_large_set(PgLarge *w, const PgBody *statics, int n_static, int n_spheres,
   if (!w || n_spheres < 0 || n_spheres > w->cap_n || n_static < 0 || n_static > w->cap_static_total || !pos || !vel) { pg_set_error("pg_large_set: bad argument"); return PG_ERR_ARG; }
   PG_CUDA(cudaSetDevice(w->device));
   PG_CUDA(cudaStreamSynchronize(w->stream));
+  w->bookkeeping_clean = 0;                     // the body count may grow: the next step resets every body
   LargeView &v = w->v;
   // statics: planes (visited against body->position) and AABBs (visited through scene nodes), array order kept
   std::vector<float4> pl, bc((size_t)std::max(n_static, 1)), be((size_t)std::max(n_static, 1));
@@ -1822,14 +1829,6 @@ float pg_large_last_step_ms(PgLarge *w) {
 int pg_large_kernel_count(void) { return K_COUNT; }
 const char *pg_large_kernel_name(int k) { return (k >= 0 && k < K_COUNT) ? kKernelNames[k] : ""; }
 float pg_large_kernel_ms(PgLarge *w, int k) { return (w && k >= 0 && k < K_COUNT) ? w->kms[k] : -1.0f; }
-// Time the cooperative fixed-point kernel spent per phase (ns, summed over the steps since the last reset):
-// clear, select, eval, hard, check, requery, control.  Read from %globaltimer by one thread between
-// the grid barriers; costs nothing to leave on.
-int pg_large_fixed_point_ns(PgLarge *w, unsigned long long *out8, int reset) {
-  if (!w || !out8) return PG_ERR_ARG;
-  for (int k = 0; k < 8; k++) { out8[k] = w->fp_phase_ns[k]; if (reset) w->fp_phase_ns[k] = 0; }
-  return PG_OK;
-}
 int pg_large_set_timing(PgLarge *w, int on) {
   if (!w) return PG_ERR_ARG;
   w->timing = on ? 1 : 0;

@@ -66,7 +66,6 @@ API = [
     ("pg_large_kernel_name", C.c_char_p, [_i]),
     ("pg_large_kernel_ms", _f, [_vp, _i]),
     ("pg_large_set_timing", _i, [_vp, _i]),
-    ("pg_large_fixed_point_ns", _i, [_vp, _vp, _i]),
     ("pg_large_exactness", _i, [_vp, _vp, _vp, _vp, _vp]),
     ("pg_pair_max_move", _i, [_vp, _i, _f, _f, _vp]),
     ("pg_pair_min_dist", _i, [_vp, _vp, _i, _vp, _vp]),
@@ -374,12 +373,6 @@ class GpuLargeWorld:
     def set_timing(self, on: bool):
         """Per-kernel CUDA-event timing (kernel_ms) is off by default; it costs an event pair per launch."""
         _check(self.L.pg_large_set_timing(self.h, int(on)), "pg_large_set_timing")
-
-    def fixed_point_ns(self, reset: bool = True) -> dict:
-        """ns the cooperative fixed-point kernel spent per phase since the last reset."""
-        out = (C.c_ulonglong * 8)()
-        _check(self.L.pg_large_fixed_point_ns(self.h, out, int(reset)), "pg_large_fixed_point_ns")
-        return dict(zip(("clear", "select", "eval", "hard", "check", "requery", "control", "hard_pairs"), [int(x) for x in out]))
 
     def kernel_ms(self) -> dict:
         return {self.L.pg_large_kernel_name(k).decode(): float(self.L.pg_large_kernel_ms(self.h, k))

@@ -210,11 +210,6 @@ float pg_large_kernel_ms(PgLarge *w, int k);
 /* Per-kernel timing costs a CUDA event pair around every launch and is OFF by default (a small world's
  * pipeline is launch-bound); switch it on before the steps whose pg_large_kernel_ms you want. */
 int  pg_large_set_timing(PgLarge *w, int on);
-/* The fixed point of a step runs inside one cooperative kernel; this reads the
- * nanoseconds it spent per phase since the last reset: clear, select, eval, hard pairs, check,
- * requery, loop control, (unused).  With pg_large_set_timing on, the step is driven launch by launch
- * instead and these stay zero. */
-int  pg_large_fixed_point_ns(PgLarge *w, unsigned long long *out8, int reset);
 /* Fixed-point statistics of the last step: iterations used, 1 if the step is proven identical to
  * the sequential reference order, candidate-visit and hit counts. */
 int  pg_large_exactness(PgLarge *w, int *iterations, int *proven_exact, long long *candidates, long long *hits);

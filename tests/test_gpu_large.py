@@ -23,15 +23,8 @@ def _ev(e):
     return [(int(x["step"]), int(x["a_class"]), int(x["a_index"]), int(x["b_class"]), int(x["b_index"])) for x in e]
 
 
-@pytest.mark.parametrize("n,L,steps,fused", [(256, 10.0, 120, False), (3000, 16.0, 40, False), (20000, 40.0, 12, False),
-                                             (3000, 16.0, 40, True), (20000, 40.0, 12, True)])
-def test_large_world_equals_sequential_sweep(gpu_lib, oracle_lib, monkeypatch, n, L, steps, fused):
-    """fused: the fixed point inside one cooperative launch (PG_LARGE_FUSED, read when the world is created)
-    instead of the launch-per-kernel loop; both must reproduce the sequential sweep bit for bit."""
-    if fused:
-        monkeypatch.setenv("PG_LARGE_FUSED", "1")
-    else:
-        monkeypatch.delenv("PG_LARGE_FUSED", raising=False)
+@pytest.mark.parametrize("n,L,steps", [(256, 10.0, 120), (3000, 16.0, 40), (20000, 40.0, 12)])
+def test_large_world_equals_sequential_sweep(gpu_lib, oracle_lib, n, L, steps):
     pos, vel, st, o = _world(oracle_lib, n, L, 900 + n)
     g = gpu_lib.GpuLargeWorld(n, len(st))
     g.set(st, pos, vel)
