@@ -41,7 +41,7 @@ using pgs::Sphere;
 
 constexpr int kMaxPlanesL = 16;
 constexpr int kTimeline = 24;           // contacts per body per step the timelines can hold (a sphere buried in a pile: 12 neighbours, each pair visited twice)
-constexpr int kMaxIter = 24;
+constexpr int kMaxIter = 256;       // a dependency chain of the sweep is resolved one link per iteration; later iterations only touch what changed
 constexpr unsigned kFullMask = 0xffffffffu;
 
 enum { K_PASS3 = 0, K_BOUNDS, K_CELLS, K_SCAN, K_SCATTER, K_PAIRS, K_EVAL, K_CHECK, K_FINAL, K_COUNT };
