@@ -77,6 +77,7 @@ struct Flags {
   unsigned n_fast;        // bodies on the fast list
   unsigned n_active;      // candidate pairs the selection (k_begin) handed to k_eval this iteration
   unsigned n_hard;        // of those, pairs k_eval passed on to k_eval_hard (long interval searches)
+  unsigned n_wide;        // grown bodies k_requery passed on to k_requery_wide
 };
 
 // One body of the cell-ordered copy.  A whole 32-byte sector per body: the counting sort's scattered
@@ -104,6 +105,7 @@ struct LargeView {
   float *rstat;                      // [8] sums over the bodies inside the previous robust box: x y z |dx| |dy| |dz| env count
   Robust *robust;
   int *fast_list;                    // [n] bodies whose envelope exceeds grid->e_cap
+  int *wide_list;                    // [n] grown bodies whose search is wider than 27 cells (k_requery_wide)
   GridParams *grid;
   // grid
   unsigned *cell_of;                 // [n]
@@ -879,6 +881,7 @@ __device__ __forceinline__ void d_check(const LargeView &v, int src, int dst, in
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     v.flags->n_hits += v.flags->n_carried; v.flags->n_carried = 0ull;
     v.flags->n_active = 0u; v.flags->n_hard = 0u;      // for the next iteration's k_begin (zero at step start)
+    v.flags->n_wide = 0u;                               // for this iteration's k_requery
   }
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     const int b = v.touched[t];
@@ -980,66 +983,91 @@ __device__ __forceinline__ void d_clear_carry(const LargeView &v, int src, int d
 // existing grid and append them marked as fresh, so that the next iteration evaluates them (pairs
 // that were already listed keep their recorded outcomes).  If both bodies of a pair grew, the lower
 // index appends it.
-__device__ __forceinline__ void d_requery(const LargeView &v, int src) {
-  const GridParams g = *v.grid;
-  const int nt = (int)v.flags->n_touched;
-  // Eight lanes per touched body (a search is 9 short cell runs, each a chain of dependent loads: more
-  // bodies in flight beat more lanes per body): the lanes share its cell runs, the fast list and -- for a
-  // body whose search would cover most of the grid -- the whole sorted array.  No warp-level primitives.
-  constexpr int kGroup = 8;
-  const int lane = threadIdx.x & (kGroup - 1);
-  const int warps = (gridDim.x * blockDim.x) / kGroup;
-  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) / kGroup; t < nt; t += warps) {
-    const int b = v.touched[t];
-    if (!v.grown[b]) continue;
-    const float4 p = v.pos_rest[b];
-    const float eb = v.env[b], eb_old = v.env_prev[b];
-    auto consider = [&](int x, float4 cx) {
-      const float dx = p.x - cx.x, dyy = p.y - cx.y, dzz = p.z - cx.z;
-      const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
-      const float ex = v.env[x], ex_old = v.env_prev[x];
-      const float Tn = eb + ex, To = eb_old + ex_old;
-      if (!(d2 <= Tn * Tn) || d2 <= To * To) return;            // not a candidate, or already listed
-      if (v.grown[x] && x < b) return;                          // the other grown body appends it
-      const unsigned long long slot = atomicAdd(&v.flags->n_pairs, 1ull);
-      if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2(~min(b, x), max(b, x));   // ~i marks it fresh
-      else atomicExch(&v.flags->overflow_pairs, 1);
-    };
-    // Partners the grid was sized for (envelope <= e_cap) can be up to eb + e_cap away: search that many
-    // cells in every direction.  Fast partners are few and are checked one by one from their list
-    // (which also holds bodies that outgrew e_cap this step).
-    const float need = (eb + g.e_cap) * g.inv_h * 1.001f;
-    if (!(need <= (float)kMaxSearch)) {
-      for (int a = lane; a < v.n; a += kGroup) {
+// The search of one grown body b, shared by `stride` threads (this one is number `lane` of them).
+// ByEntry = false: every thread takes whole cell runs (8 lanes, sparse cells: the runs' dependent loads are
+// in flight together); true (a block): the warps take the runs, the lanes of a warp the bodies inside a run --
+// for wide searches and for dense cells (a settled world has dozens of bodies per floor cell).
+template <bool ByEntry>
+__device__ __forceinline__ void requery_body(const LargeView &v, const GridParams &g, int b, int lane, int stride) {
+  const float4 p = v.pos_rest[b];
+  const float eb = v.env[b], eb_old = v.env_prev[b];
+  auto consider = [&](int x, float4 cx) {
+    const float dx = p.x - cx.x, dyy = p.y - cx.y, dzz = p.z - cx.z;
+    const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
+    const float ex = v.env[x], ex_old = v.env_prev[x];
+    const float Tn = eb + ex, To = eb_old + ex_old;
+    if (!(d2 <= Tn * Tn) || d2 <= To * To) return;            // not a candidate, or already listed
+    if (v.grown[x] && x < b) return;                          // the other grown body appends it
+    const unsigned long long slot = atomicAdd(&v.flags->n_pairs, 1ull);
+    if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2(~min(b, x), max(b, x));   // ~i marks it fresh
+    else atomicExch(&v.flags->overflow_pairs, 1);
+  };
+  // Partners the grid was sized for (envelope <= e_cap) can be up to eb + e_cap away: search that many
+  // cells in every direction.  Fast partners are few and are checked one by one from their list
+  // (which also holds bodies that outgrew e_cap this step).
+  const float need = (eb + g.e_cap) * g.inv_h * 1.001f;
+  if (!(need <= (float)kMaxSearch)) {
+    for (int a = lane; a < v.n; a += stride) {
+      const int x = (int)v.sorted[a].idx;
+      if (x != b && !(v.env[x] > g.e_cap)) consider(x, v.sorted[a].cenv);
+    }
+  } else {
+    // every thread takes whole x-runs of the (2R+1)^2 the search covers (9 for a body the grid was sized
+    // for), so their dependent loads -- cell table, cell contents, envelopes -- are in flight together
+    const int R = max((int)ceilf(need), 1);
+    const int3 c = cell_coords(g, p.x, p.y, p.z);
+    const int side = 2 * R + 1;
+    const int x0 = max(c.x - R, 0), x1 = min(c.x + R, g.dim[0] - 1);
+    const int r_first = ByEntry ? (lane >> 5) : lane, r_step = ByEntry ? max(stride >> 5, 1) : stride;
+    const unsigned a_first = ByEntry ? (unsigned)(lane & 31) : 0u, a_step = ByEntry ? 32u : 1u;
+    for (int r = r_first; r < side * side; r += r_step) {
+      const int y = c.y + r % side - R, z = c.z + r / side - R;
+      if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
+      const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+      const unsigned a1 = v.cell_cnt[row + x1 + 1];
+      for (unsigned a = v.cell_cnt[row + x0] + a_first; a < a1; a += a_step) {
         const int x = (int)v.sorted[a].idx;
         if (x != b && !(v.env[x] > g.e_cap)) consider(x, v.sorted[a].cenv);
       }
-    } else {
-      // every lane takes whole x-runs of the (2R+1)^2 the search covers (9 for a body the grid was sized
-      // for), so their dependent loads -- cell table, cell contents, envelopes -- are in flight together
-      const int R = max((int)ceilf(need), 1);
-      const int3 c = cell_coords(g, p.x, p.y, p.z);
-      const int side = 2 * R + 1;
-      const int x0 = max(c.x - R, 0), x1 = min(c.x + R, g.dim[0] - 1);
-      for (int r = lane; r < side * side; r += kGroup) {
-        const int y = c.y + r % side - R, z = c.z + r / side - R;
-        if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
-        const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
-        const unsigned a1 = v.cell_cnt[row + x1 + 1];
-        for (unsigned a = v.cell_cnt[row + x0]; a < a1; a++) {
-          const int x = (int)v.sorted[a].idx;
-          if (x != b && !(v.env[x] > g.e_cap)) consider(x, v.sorted[a].cenv);
-        }
-      }
-    }
-    const int nf = (int)v.flags->n_fast;
-    for (int f = lane; f < nf; f += kGroup) {
-      const int x = v.fast_list[f];
-      if (x == b || !(v.env[x] > g.e_cap)) continue;
-      const float4 px = v.pos_rest[x];
-      consider(x, make_float4(px.x, px.y, px.z, 0.0f));
     }
   }
+  const int nf = (int)v.flags->n_fast;
+  for (int f = lane; f < nf; f += stride) {
+    const int x = v.fast_list[f];
+    if (x == b || !(v.env[x] > g.e_cap)) continue;
+    const float4 px = v.pos_rest[x];
+    consider(x, make_float4(px.x, px.y, px.z, 0.0f));
+  }
+}
+__device__ __forceinline__ void d_requery(const LargeView &v, int src) {
+  const GridParams g = *v.grid;
+  const int nt = (int)v.flags->n_touched;
+  // Eight lanes per touched body whose search is the usual 9 short cell runs (each a chain of dependent
+  // loads: more bodies in flight beat more lanes per body).  A body that searches wider -- a fast one, or a
+  // straggler whose search covers most of the grid and falls back to the whole sorted array -- goes on a
+  // list and gets a whole block (k_requery_wide): eight lanes walking 65 k bodies held the step up for 0.7 ms.
+  constexpr int kGroup = 8;
+  const int lane = threadIdx.x & (kGroup - 1);
+  const int groups = (gridDim.x * blockDim.x) / kGroup;
+  // when only a few bodies grew (every iteration but the first) there is a block to spare for each of them
+  const bool few = v.flags->grew < 4096;
+  // ... and in a settled world (dozens of bodies per floor cell) a lane would walk its runs for too long
+  const bool dense = (float)v.n > 1.5f * (float)g.n_cells;
+  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) / kGroup; t < nt; t += groups) {
+    const int b = v.touched[t];
+    if (!v.grown[b]) continue;
+    const float need = (v.env[b] + g.e_cap) * g.inv_h * 1.001f;
+    if (few || dense || !(need <= 1.0f)) {
+      if (lane == 0) v.wide_list[atomicAdd(&v.flags->n_wide, 1u)] = b;
+      continue;
+    }
+    requery_body<false>(v, g, b, lane, kGroup);
+  }
+}
+__device__ __forceinline__ void d_requery_wide(const LargeView &v) {
+  const GridParams g = *v.grid;
+  const int nw = (int)v.flags->n_wide;
+  for (int t = blockIdx.x; t < nw; t += gridDim.x) requery_body<true>(v, g, v.wide_list[t], (int)threadIdx.x, (int)blockDim.x);
 }
 __device__ __forceinline__ void d_requery_done(const LargeView &v) {
   const int nt = (int)v.flags->n_touched;
@@ -1060,6 +1088,7 @@ __global__ void __launch_bounds__(256) k_begin(LargeView v, int src, int dst, in
   d_select(v, src, iter, dt);
 }
 __global__ void k_requery(LargeView v, int src) { d_requery(v, src); }
+__global__ void k_requery_wide(LargeView v) { d_requery_wide(v); }
 __global__ void k_requery_done(LargeView v) { d_requery_done(v); }
 
 // ---------------------------------------------------------------- 5. final state + pass-4 events
@@ -1321,7 +1350,11 @@ static int lw_step_once(PgLarge *w, float dt_in) {
     LW_LAUNCH(w, K_CHECK, k_check, wide_grid, 256, v, src, dst, it, dt);
     // candidates the grown envelopes add (on top of the NEW timelines); their bodies are marked dirty so
     // the next iteration re-evaluates them (warm start)
-    LW_LAUNCH(w, K_BOUNDS, k_requery, wide_grid, 128, v, dst);
+    if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][0], w->stream);
+    k_requery<<<wide_grid, 128, 0, w->stream>>>(v, dst);
+    k_requery_wide<<<wide_grid, 256, 0, w->stream>>>(v);
+    if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][1], w->stream);
+    w->launches += 2;
     rc = lw_read_flags(w, &f);
     if (rc) return rc;
     lw_accumulate(w, K_EVAL); lw_accumulate(w, K_CHECK); lw_accumulate(w, K_BOUNDS);
@@ -1330,8 +1363,8 @@ static int lw_step_once(PgLarge *w, float dt_in) {
       cudaEventElapsedTime(&e, w->kev[K_EVAL][0], w->kev[K_EVAL][1]);
       cudaEventElapsedTime(&c, w->kev[K_CHECK][0], w->kev[K_CHECK][1]);
       cudaEventElapsedTime(&rq, w->kev[K_BOUNDS][0], w->kev[K_BOUNDS][1]);
-      fprintf(stderr, "  [pg_large] iter %d: eval %.3f ms check %.3f ms requery %.3f ms hits %llu changed %d grew %d pairs %llu -> %llu touched %u fast %u\n",
-              it, e, c, rq, (unsigned long long)f.n_hits, f.changed, f.grew, pairs_before, (unsigned long long)f.n_pairs, f.n_touched, f.n_fast);
+      fprintf(stderr, "  [pg_large] iter %d: eval %.3f ms check %.3f ms requery %.3f ms hits %llu changed %d grew %d pairs %llu -> %llu touched %u fast %u wide %u\n",
+              it, e, c, rq, (unsigned long long)f.n_hits, f.changed, f.grew, pairs_before, (unsigned long long)f.n_pairs, f.n_touched, f.n_fast, f.n_wide);
     }
     w->last_iterations++;
     w->last_hits = (long long)f.n_hits;
@@ -1342,7 +1375,12 @@ static int lw_step_once(PgLarge *w, float dt_in) {
         // k_requery only appends: keep the list as it was, make room, and let it append again
         rc = lw_grow_pairs(w, f.n_pairs, pairs_before);
         if (rc) return rc;
-        LW_LAUNCH(w, K_BOUNDS, k_requery, wide_grid, 128, v, src);
+        PG_CUDA(cudaMemsetAsync(&v.flags->n_wide, 0, sizeof(unsigned), w->stream));
+        if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][0], w->stream);
+        k_requery<<<wide_grid, 128, 0, w->stream>>>(v, src);
+        k_requery_wide<<<wide_grid, 256, 0, w->stream>>>(v);
+        if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][1], w->stream);
+        w->launches += 2;
         rc = lw_read_flags(w, &f);
         if (rc) return rc;
         lw_accumulate(w, K_BOUNDS);
@@ -1441,6 +1479,7 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
     PG_CUDA_NULL(cudaMemcpy(v.robust, &r0, sizeof(r0), cudaMemcpyHostToDevice));
   }
   PG_CUDA_NULL(cudaMalloc(&v.fast_list, sizeof(int) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.wide_list, sizeof(int) * n));
   PG_CUDA_NULL(cudaMalloc(&v.cell_of, sizeof(unsigned) * n));
   PG_CUDA_NULL(cudaMalloc(&v.cell_cnt, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.block_sums, sizeof(unsigned) * ((size_t)v.cells_cap / (kScanBlock * kScanItems) + 2)));
@@ -1482,7 +1521,7 @@ void pg_large_destroy(PgLarge *w) {
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
   if (w->player_world) pg_worlds_destroy(w->player_world);
-  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.fast_list, v.touched_bits, v.dirty_bits[0], v.dirty_bits[1], v.pushed_bits, v.block_sums, v.sorted,
+  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.fast_list, v.wide_list, v.touched_bits, v.dirty_bits[0], v.dirty_bits[1], v.pushed_bits, v.block_sums, v.sorted,
                   v.pairs, v.active, v.grown, v.env_prev, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
                   v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);
