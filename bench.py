@@ -288,10 +288,17 @@ def run_large_arm(args, cfg):
     if rank == 0:
         peak, peak_src = read_peaks()
         per_kernel = {}
+        traffic = {}
+        rj = os.path.join(ROOT, "profiles", "roofline_large_r01.json")
+        if os.path.exists(rj) and n == 4194304:             # the capture is of the 4 M-body world
+            try:
+                traffic = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in json.load(open(rj))["kernels"].items()}
+            except Exception:
+                traffic = {}
         for k, b in LARGE_KERNEL_BYTES.items():
             ms = kms.get(k, 0.0) / args.steps
             if ms > 0:
-                per_kernel[k] = {"ms": ms, "GBps": b * n / (ms * 1e-3) / 1e9, "frac": b * n / (ms * 1e-3) / 1e9 / peak}
+                per_kernel[k] = {"ms": ms, "GBps": b * n / (ms * 1e-3) / 1e9, "frac": b * n / (ms * 1e-3) / 1e9 / peak, "traffic": traffic.get(k)}
         dom = max(kms, key=kms.get)
         dom_ms = kms[dom] / args.steps
         dom_bytes = LARGE_KERNEL_BYTES.get(dom, 96) * n      # k_eval / k_check: 96 B per contact is the survey figure; per body as an upper bound

@@ -87,6 +87,8 @@ struct __align__(32) SortedBody { float4 cenv; unsigned idx, pad0, pad1, pad2; }
 
 struct LargeView {
   int n, ns;
+  int stage_limit;                   // entries the per-block shared-memory stages may hold (tests shrink it to reach the overflow paths)
+  int requery_few;                   // k_requery: below this many grown bodies each gets a block
   float4 *pos_rest, *vel_rad;        // state (in/out), body order = reference array order
   float4 *planes;                    // the static PLANES, array order
   int *plane_sidx;                   // their index in the static array
@@ -161,7 +163,7 @@ constexpr int kEventStage = 192;
 enum { kEventAdd = 0, kEventFlush = 1, kEventInit = 2 };
 // (the view's fields are passed by value: a reference to the kernel parameter would make every thread copy
 // the whole 400-byte struct to its local stack)
-__device__ __noinline__ void event_stage_impl(PgEvent *events, int *n_events, int max_events, int mode, int step, int pass, int ac, int ai, int bc, int bi) {
+__device__ __noinline__ void event_stage_impl(PgEvent *events, int *n_events, int max_events, int cap, int mode, int step, int pass, int ac, int ai, int bc, int bi) {
   __shared__ PgEvent s_ev[kEventStage];
   __shared__ unsigned s_cnt;
   __shared__ int s_base;
@@ -177,13 +179,13 @@ __device__ __noinline__ void event_stage_impl(PgEvent *events, int *n_events, in
     e.a_class = ac; e.a_index = ai; e.b_class = bc; e.b_index = bi;
     e.pad_ = pass << 8;
     const unsigned st = atomicAdd(&s_cnt, 1u);
-    if (st < (unsigned)kEventStage) { s_ev[st] = e; return; }
+    if (st < (unsigned)cap) { s_ev[st] = e; return; }
     const int slot = atomicAdd(n_events, 1);
     if (slot < max_events) events[slot] = e;
     return;
   }
   __syncthreads();
-  const int staged = (int)min(s_cnt, (unsigned)kEventStage);
+  const int staged = (int)min(s_cnt, (unsigned)cap);
   if (threadIdx.x == 0 && staged) s_base = atomicAdd(n_events, staged);
   __syncthreads();
   for (int e = threadIdx.x; e < staged; e += blockDim.x)
@@ -193,7 +195,7 @@ __device__ __noinline__ void event_stage_impl(PgEvent *events, int *n_events, in
   __syncthreads();
 }
 __device__ __forceinline__ void event_stage(const LargeView &v, int mode, int step, int pass, int ac, int ai, int bc, int bi) {
-  event_stage_impl(v.events, v.n_events, v.max_events, mode, step, pass, ac, ai, bc, bi);
+  event_stage_impl(v.events, v.n_events, v.max_events, min(v.stage_limit, kEventStage), mode, step, pass, ac, ai, bc, bi);
 }
 __device__ __forceinline__ void emit_event(const LargeView &v, int step, int pass, int ac, int ai, int bc, int bi) {
   event_stage(v, kEventAdd, step, pass, ac, ai, bc, bi);
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs(LargeView v) {
           }
           const int2 pr = make_int2((int)min(ia, ib), (int)max(ia, ib));
           const unsigned slot = atomicAdd(&s_cnt, 1u);
-          if (slot < (unsigned)kPairsStage) { s_pairs[slot] = pr; continue; }
+          if (slot < (unsigned)min(v.stage_limit, kPairsStage)) { s_pairs[slot] = pr; continue; }
           const unsigned long long gs = atomicAdd(&v.flags->n_pairs, 1ull);
           if ((long long)gs < v.pairs_cap) v.pairs[gs] = pr;
           else atomicExch(&v.flags->overflow_pairs, 1);
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs(LargeView v) {
       }
     }
     __syncthreads();
-    const unsigned staged = min(s_cnt, (unsigned)kPairsStage);
+    const unsigned staged = min(s_cnt, (unsigned)min(v.stage_limit, kPairsStage));
     if (threadIdx.x == 0 && staged) s_base = atomicAdd(&v.flags->n_pairs, (unsigned long long)staged);
     __syncthreads();
     for (unsigned e = threadIdx.x; e < staged; e += kPairsBlock) {
@@ -626,7 +628,7 @@ __device__ __forceinline__ BodyState state_at(const LargeView &v, int src, int b
 // called by ALL threads of the block at the start / end of every phase that pushes timeline entries).
 constexpr int kTouchStage = 512;
 enum { kTouchAdd = 0, kTouchFlush = 1, kTouchInit = 2 };
-__device__ __noinline__ void touched_stage_impl(int *touched, unsigned *n_touched, int b, int mode) {
+__device__ __noinline__ void touched_stage_impl(int *touched, unsigned *n_touched, int cap, int b, int mode) {
   __shared__ int s_list[kTouchStage];
   __shared__ unsigned s_cnt, s_base;
   if (mode == kTouchInit) {
@@ -636,12 +638,12 @@ __device__ __noinline__ void touched_stage_impl(int *touched, unsigned *n_touche
   }
   if (mode == kTouchAdd) {
     const unsigned slot = atomicAdd(&s_cnt, 1u);
-    if (slot < (unsigned)kTouchStage) s_list[slot] = b;
+    if (slot < (unsigned)cap) s_list[slot] = b;
     else touched[atomicAdd(n_touched, 1u)] = b;
     return;
   }
   __syncthreads();
-  const unsigned staged = min(s_cnt, (unsigned)kTouchStage);
+  const unsigned staged = min(s_cnt, (unsigned)cap);
   if (threadIdx.x == 0 && staged) s_base = atomicAdd(n_touched, staged);
   __syncthreads();
   for (unsigned e = threadIdx.x; e < staged; e += blockDim.x) touched[s_base + e] = s_list[e];
@@ -650,7 +652,7 @@ __device__ __noinline__ void touched_stage_impl(int *touched, unsigned *n_touche
   __syncthreads();
 }
 
-__device__ __forceinline__ void touched_stage(const LargeView &v, int b, int mode) { touched_stage_impl(v.touched, &v.flags->n_touched, b, mode); }
+__device__ __forceinline__ void touched_stage(const LargeView &v, int b, int mode) { touched_stage_impl(v.touched, &v.flags->n_touched, min(v.stage_limit, kTouchStage), b, mode); }
 __device__ __forceinline__ void timeline_push(const LargeView &v, int dst, int b, unsigned long long key, const Sphere &s) {
   // tl_cnt is a byte array; claim a slot with a 32-bit CAS on the containing word
   unsigned *word = (unsigned *)(v.tl_cnt[dst] + (b & ~3));
@@ -1050,14 +1052,30 @@ __device__ __forceinline__ void d_requery(const LargeView &v, int src) {
   const int lane = threadIdx.x & (kGroup - 1);
   const int groups = (gridDim.x * blockDim.x) / kGroup;
   // when only a few bodies grew (every iteration but the first) there is a block to spare for each of them
-  const bool few = v.flags->grew < 4096;
-  // ... and in a settled world (dozens of bodies per floor cell) a lane would walk its runs for too long
-  const bool dense = (float)v.n > 1.5f * (float)g.n_cells;
+  const bool few = v.flags->grew < v.requery_few;
+  const unsigned group_mask = 0xffu << (threadIdx.x & 24);
   for (int t = (blockIdx.x * blockDim.x + threadIdx.x) / kGroup; t < nt; t += groups) {
     const int b = v.touched[t];
     if (!v.grown[b]) continue;
     const float need = (v.env[b] + g.e_cap) * g.inv_h * 1.001f;
-    if (few || dense || !(need <= 1.0f)) {
+    bool wide = few || !(need <= 1.0f);
+    if (!wide) {
+      // ... and so does a body whose 27 cells hold many bodies (a settled world has dozens per floor cell):
+      // a lane would walk its runs for too long.  The lanes add up the lengths of their runs first.
+      const float4 p = v.pos_rest[b];
+      const int3 c = cell_coords(g, p.x, p.y, p.z);
+      const int x0 = max(c.x - 1, 0), x1 = min(c.x + 1, g.dim[0] - 1);
+      unsigned work = 0;
+      for (int r = lane; r < 9; r += kGroup) {
+        const int y = c.y + r % 3 - 1, z = c.z + r / 3 - 1;
+        if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
+        const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+        work += v.cell_cnt[row + x1 + 1] - v.cell_cnt[row + x0];
+      }
+      for (int o = 4; o > 0; o >>= 1) work += __shfl_xor_sync(group_mask, work, o);
+      wide = work > 96u;                        // (measured: C4 at step 110 and the settled C2 are both slower with 512)
+    }
+    if (wide) {
       if (lane == 0) v.wide_list[atomicAdd(&v.flags->n_wide, 1u)] = b;
       continue;
     }
@@ -1456,6 +1474,10 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   for (int k = 0; k < K_COUNT; k++) { PG_CUDA_NULL(cudaEventCreate(&w->kev[k][0])); PG_CUDA_NULL(cudaEventCreate(&w->kev[k][1])); }
   LargeView &v = w->v;
   const size_t n = (size_t)max_spheres;
+  // test hooks (read once per handle): tiny shared-memory stages reach their overflow paths, and a zero
+  // threshold keeps k_requery on its eight-lane path in worlds where few bodies grow
+  v.stage_limit = getenv("PG_LARGE_SMALL_STAGES") ? 3 : (1 << 20);
+  v.requery_few = getenv("PG_LARGE_REQUERY_FEW") ? atoi(getenv("PG_LARGE_REQUERY_FEW")) : 4096;
   v.cells_cap = (int)std::min<size_t>(4 * n + 4096, (size_t)1 << 28);
   v.pairs_cap = (long long)(4 * n + 65536);
   v.max_events = (int)std::max<size_t>(n / 4, 65536);

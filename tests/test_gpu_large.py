@@ -23,8 +23,14 @@ def _ev(e):
     return [(int(x["step"]), int(x["a_class"]), int(x["a_index"]), int(x["b_class"]), int(x["b_index"])) for x in e]
 
 
-@pytest.mark.parametrize("n,L,steps", [(256, 10.0, 120), (3000, 16.0, 40), (20000, 40.0, 12)])
-def test_large_world_equals_sequential_sweep(gpu_lib, oracle_lib, n, L, steps):
+@pytest.mark.parametrize("n,L,steps,env", [(256, 10.0, 120, {}), (3000, 16.0, 40, {}), (20000, 40.0, 12, {}),
+                                           (3000, 16.0, 40, {"PG_LARGE_REQUERY_FEW": "0"}),      # k_requery's eight-lane path
+                                           (3000, 12.0, 30, {"PG_LARGE_SMALL_STAGES": "1"})])    # overflow paths of the block stages
+def test_large_world_equals_sequential_sweep(gpu_lib, oracle_lib, monkeypatch, n, L, steps, env):
+    for k in ("PG_LARGE_REQUERY_FEW", "PG_LARGE_SMALL_STAGES"):
+        monkeypatch.delenv(k, raising=False)
+    for k, val in env.items():
+        monkeypatch.setenv(k, val)                 # read by pg_large_create
     pos, vel, st, o = _world(oracle_lib, n, L, 900 + n)
     g = gpu_lib.GpuLargeWorld(n, len(st))
     g.set(st, pos, vel)
@@ -78,6 +84,39 @@ def test_large_world_with_stragglers_and_fast_bodies(gpu_lib, oracle_lib):
         assert ge == oe, (s, len(ge), len(oe))
         total += len(ge)
     assert total > 500
+    g.close()
+
+
+def test_large_world_grazing_carpet(gpu_lib, oracle_lib):
+    """A carpet of touching spheres with tiny velocities: grazing pairs whose interval search runs to hundreds
+    or thousands of nodes.  One thread per pair gives them up after 48 nodes; a block per pair shares the leaf
+    scan (k_eval_hard) -- and the result is still the sequential sweep's, bit for bit."""
+    side = 32
+    n = side * side
+    g1 = np.arange(side, dtype=np.float32)
+    gx, gz = np.meshgrid(g1, g1)
+    pos = np.stack([(gx.ravel() - 15.5) * np.float32(0.3000001), np.full(n, 0.151, np.float32) + (np.arange(n) % 3) * np.float32(1.0e-6),
+                    (gz.ravel() - 15.5) * np.float32(0.3000001)], axis=1).astype(np.float32)
+    rng = np.random.default_rng(5)
+    vel = (rng.standard_normal((n, 3)) * np.float32(0.02)).astype(np.float32)
+    vel[::5] *= np.float32(100.0)
+    st = scenes.plane_bodies(scenes.box_planes(12.0))
+    o = ora.World(oracle_lib, st, scenes.sphere_bodies(pos, vel))
+    g = gpu_lib.GpuLargeWorld(n, len(st))
+    g.set(st, pos, vel)
+    total = 0
+    for s in range(24):
+        g.step(DT, 1)
+        oracle_lib.dll.ora_world_step_grid(o.h, DT, 1, 0)
+        ex = g.exactness()
+        assert ex["proven_exact"], (s, ex)
+        P, V, R = g.download_state()
+        r = o.read(1)
+        assert gen.same_bits(P, r["position"]) and gen.same_bits(V, r["velocity"]) and np.array_equal(R != 0, r["at_rest"] != 0), (s, ex)
+        ge, oe = _ev(g.events()), _ev(o.events())
+        assert ge == oe, (s, len(ge), len(oe))
+        total += len(ge)
+    assert total > 1000, total
     g.close()
 
 

@@ -1,12 +1,12 @@
-"""Developer tool: run the C2 world (65,536 spheres) for many steps, then print the per-iteration trace of a
+"""Developer tool: run the C2 world (65,536 spheres; `large_long_run.py STEPS c4` for the 4 M one) for many steps, then print the per-iteration trace of a
 few steps (PG_LARGE_DEBUG=1) and the per-kernel times.  Shows what a settled, piled-up world costs."""
 import os
 import sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
 from crux_b200 import scenes, gpu
-n, L = 65536, 64.0
 skip = int(sys.argv[1]) if len(sys.argv) > 1 else 900
+n, L = {"c2": (65536, 64.0), "c4": (4194304, 256.0)}[sys.argv[2] if len(sys.argv) > 2 else "c2"]
 pos, vel = scenes.sphere_worlds(1, n, L)
 st = scenes.plane_bodies(scenes.box_planes(L))
 g = gpu.GpuLargeWorld(n, len(st))
