@@ -78,6 +78,7 @@ struct Flags {
   unsigned n_active;      // candidate pairs the selection (k_begin) handed to k_eval this iteration
   unsigned n_hard;        // of those, pairs k_eval passed on to k_eval_hard (long interval searches)
   unsigned n_wide;        // grown bodies k_requery passed on to k_requery_wide
+  unsigned n_pass3;       // bodies k_pass3 passed on to k_pass3_exact
 };
 
 // One body of the cell-ordered copy.  A whole 32-byte sector per body: the counting sort's scattered
@@ -89,6 +90,7 @@ struct LargeView {
   int n, ns;
   int stage_limit;                   // entries the per-block shared-memory stages may hold (tests shrink it to reach the overflow paths)
   int requery_few;                   // k_requery: below this many grown bodies each gets a block
+  int pass3_split_min;               // worlds of at least this many bodies run pass 3 as probe + dense exact kernel
   float4 *pos_rest, *vel_rad;        // state (in/out), body order = reference array order
   float4 *planes;                    // the static PLANES, array order
   int *plane_sidx;                   // their index in the static array
@@ -208,19 +210,63 @@ __device__ __forceinline__ float envelope(float r, float vx, float vy, float vz,
 }
 
 // ---------------------------------------------------------------- 1. pass 3 + envelope + bounds
-__global__ void k_pass3(LargeView v, float dt, int step, int do_planes, int full_reset) {
+// Bodies that receive their first timeline entry join the touched list.  Tens of thousands do in the
+// first iteration of a step, and one atomic each on the list's counter serialises them; they are staged
+// per block instead and appended with one atomic when the block is through (kTouchInit / kTouchFlush:
+// called by ALL threads of the block at the start / end of every phase that pushes timeline entries).
+constexpr int kTouchStage = 512;
+enum { kTouchAdd = 0, kTouchFlush = 1, kTouchInit = 2 };
+__device__ __noinline__ void touched_stage_impl(int *touched, unsigned *n_touched, int cap, int b, int mode) {
+  __shared__ int s_list[kTouchStage];
+  __shared__ unsigned s_cnt, s_base;
+  if (mode == kTouchInit) {
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    return;
+  }
+  if (mode == kTouchAdd) {
+    const unsigned slot = atomicAdd(&s_cnt, 1u);
+    if (slot < (unsigned)cap) s_list[slot] = b;
+    else touched[atomicAdd(n_touched, 1u)] = b;
+    return;
+  }
+  __syncthreads();
+  const unsigned staged = min(s_cnt, (unsigned)cap);
+  if (threadIdx.x == 0 && staged) s_base = atomicAdd(n_touched, staged);
+  __syncthreads();
+  for (unsigned e = threadIdx.x; e < staged; e += blockDim.x) touched[s_base + e] = s_list[e];
+  __syncthreads();
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+}
+
+__device__ __forceinline__ void touched_stage(const LargeView &v, int b, int mode) { touched_stage_impl(v.touched, &v.flags->n_touched, min(v.stage_limit, kTouchStage), b, mode); }
+// Pass 3 runs as two kernels.  Probe = true (k_pass3, one thread per body, few registers, streaming): the
+// cheap gates only; a body none of whose statics passes its gate is left as it is and gets its envelope,
+// bookkeeping and bounds here, the others (a few per cent; 15 % in a level full of slabs) go on a list.
+// Probe = false (k_pass3_exact, dense over that list): the whole visit sequence of the body -- gates again,
+// exact predicate, narrowphase, resolver, statics in array order -- then the same envelope / bounds code.
+// One kernel doing both ran every warp through the 124-register exact path with a few lanes alive.
+// All = true (with Probe = false): the exact kernel over every body, in one launch -- for worlds small enough
+// to be bound by their launches.
+template <bool Probe, bool All = false>
+__device__ __forceinline__ void pass3_impl(const LargeView &v, float dt, int step, int do_planes, int full_reset) {
   __shared__ float4 s_pl[kMaxPlanesL];
   __shared__ float s_red[8][15];                   // per-warp partials of the bounds and the running statistics
   if (threadIdx.x < v.ns) s_pl[threadIdx.x] = v.planes[threadIdx.x];
   event_stage(v, kEventInit, 0, 0, 0, 0, 0, 0);     // (includes the block barrier)
+  touched_stage_impl(v.touched, &v.flags->n_pass3, kTouchStage, 0, kTouchInit);
   pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
   const bool gate_ok = dt > 1.0e-9f;
   float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f}, emax = 0.0f;
   float rs[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
   const Robust rb = *v.robust;
   bool bad = false;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
+  const int n_items = (Probe || All) ? v.n : (int)v.flags->n_pass3;
+  for (int item = blockIdx.x * blockDim.x + threadIdx.x; item < n_items; item += gridDim.x * blockDim.x) {
+    const int i = (Probe || All) ? item : v.touched[item];   // (the touched list's storage is free until k_eval)
     float4 p = v.pos_rest[i], q = v.vel_rad[i];
+    bool needs = false;                                    // Probe: some static passed its gate
     if (do_planes) {
       bool touched = false;
       const V3 p0 = v3(p.x, p.y, p.z);        // scene-node translation: the position at step start
@@ -229,6 +275,7 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes, int full
         const float rho = pgs::reach(q.w, q.x, q.y, q.z, dt);
         const float s0 = __fmaf_rn(p.x, pl.x, __fmaf_rn(p.y, pl.y, p.z * pl.z)) - pl.w;
         if (gate_ok && fabsf(s0) > rho * 1.0001f + 1.0e-5f * (fabsf(s0) + fabsf(pl.w) + 1.0f)) return;
+        if (Probe) { needs = true; return; }
         Sphere A;
         A.px = p.x; A.py = p.y; A.pz = p.z; A.vx = q.x; A.vy = q.y; A.vz = q.z; A.r = q.w; A.rest = 0;
         if (pgs::sphere_plane_exact(A, pl, v.restitution, dt, leaf)) {
@@ -248,6 +295,7 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes, int full
         const float rho = __fmaf_rn(nv, dt, q.w) * 1.0001f + 1.0e-6f;
         const float d2 = pgm::bb_d2(v3(0.0f + p0.x, 0.0f + p0.y, 0.0f + p0.z), bx);
         if (gate_ok && d2 > rho * rho * 1.0001f) return;
+        if (Probe) { needs = true; return; }
         if (!pgm::bb_interval(p0, vel, nv, q.w, bx, 0.0f, dt, leaf)) return;
         const pgm::Contact c = pgm::bb_narrow(p0, vel, q.w, bx, dt);
         if (!(c.hit && c.t >= 0)) return;
@@ -258,7 +306,7 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes, int full
         emit_event(v, step, 3, PG_CLASS_STATIC, j, PG_CLASS_DYNAMIC, i);      // the box is body_A (lower collider type)
       };
       if (v.n_boxes == 0) {
-        for (int k = 0; k < v.ns; k++) do_plane(k);
+        for (int k = 0; k < v.ns && !needs; k++) do_plane(k);
       } else {
         // planes and the boxes registered in this sphere's level-grid cell, merged in static-array order
         const float rho0 = pgs::reach(q.w, q.x, q.y, q.z, dt);
@@ -269,7 +317,7 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes, int full
           unsigned ib = 0, ie = 0;
           if (inside) { const int cell = (cz * v.sg_dim[1] + cy) * v.sg_dim[0] + cx; ib = v.sg_start[cell]; ie = v.sg_start[cell + 1]; }
           int ip = 0;
-          while (ip < v.ns || ib < ie) {
+          while ((ip < v.ns || ib < ie) && !needs) {
             const int jp = ip < v.ns ? v.plane_sidx[ip] : 0x7fffffff;
             const int jb = ib < ie ? v.sg_items[ib] : 0x7fffffff;
             if (jp < jb) { do_plane(ip); ip++; } else { do_box(jb); ib++; }
@@ -277,13 +325,14 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes, int full
         } else {
           // faster than the level grid was built for: walk the whole static array
           int ip = 0;
-          for (int j = 0; j < v.n_static_total; j++) {
+          for (int j = 0; j < v.n_static_total && !needs; j++) {
             if (v.static_type[j] == PG_PLANE) { do_plane(ip); ip++; } else do_box(j);
           }
         }
       }
       if (touched) { v.pos_rest[i] = p; v.vel_rad[i] = q; }
     }
+    if (Probe && needs) { touched_stage_impl(v.touched, &v.flags->n_pass3, kTouchStage, i, kTouchAdd); continue; }
     const float e = envelope(q.w, q.x, q.y, q.z, dt);
     v.env[i] = e;
     v.env_prev[i] = e;
@@ -332,7 +381,11 @@ __global__ void k_pass3(LargeView v, float dt, int step, int do_planes, int full
   }
   if (bad) atomicExch(&v.flags->unsafe, 1);
   event_stage(v, kEventFlush, 0, 0, 0, 0, 0, 0);
+  touched_stage_impl(v.touched, &v.flags->n_pass3, kTouchStage, 0, kTouchFlush);
 }
+__global__ void k_pass3(LargeView v, float dt, int step, int do_planes, int full_reset) { pass3_impl<true>(v, dt, step, do_planes, full_reset); }
+__global__ void k_pass3_exact(LargeView v, float dt, int step, int do_planes, int full_reset) { pass3_impl<false>(v, dt, step, do_planes, full_reset); }
+__global__ void k_pass3_all(LargeView v, float dt, int step, int do_planes, int full_reset) { pass3_impl<false, true>(v, dt, step, do_planes, full_reset); }
 
 __global__ void k_grid_params(LargeView v) {
   GridParams g;
@@ -622,37 +675,6 @@ __device__ __forceinline__ BodyState state_at(const LargeView &v, int src, int b
   return s;
 }
 
-// Bodies that receive their first timeline entry join the touched list.  Tens of thousands do in the
-// first iteration of a step, and one atomic each on the list's counter serialises them; they are staged
-// per block instead and appended with one atomic when the block is through (kTouchInit / kTouchFlush:
-// called by ALL threads of the block at the start / end of every phase that pushes timeline entries).
-constexpr int kTouchStage = 512;
-enum { kTouchAdd = 0, kTouchFlush = 1, kTouchInit = 2 };
-__device__ __noinline__ void touched_stage_impl(int *touched, unsigned *n_touched, int cap, int b, int mode) {
-  __shared__ int s_list[kTouchStage];
-  __shared__ unsigned s_cnt, s_base;
-  if (mode == kTouchInit) {
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    return;
-  }
-  if (mode == kTouchAdd) {
-    const unsigned slot = atomicAdd(&s_cnt, 1u);
-    if (slot < (unsigned)cap) s_list[slot] = b;
-    else touched[atomicAdd(n_touched, 1u)] = b;
-    return;
-  }
-  __syncthreads();
-  const unsigned staged = min(s_cnt, (unsigned)cap);
-  if (threadIdx.x == 0 && staged) s_base = atomicAdd(n_touched, staged);
-  __syncthreads();
-  for (unsigned e = threadIdx.x; e < staged; e += blockDim.x) touched[s_base + e] = s_list[e];
-  __syncthreads();
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
-}
-
-__device__ __forceinline__ void touched_stage(const LargeView &v, int b, int mode) { touched_stage_impl(v.touched, &v.flags->n_touched, min(v.stage_limit, kTouchStage), b, mode); }
 __device__ __forceinline__ void timeline_push(const LargeView &v, int dst, int b, unsigned long long key, const Sphere &s) {
   // tl_cnt is a byte array; claim a slot with a 32-bit CAS on the containing word
   unsigned *word = (unsigned *)(v.tl_cnt[dst] + (b & ~3));
@@ -1319,7 +1341,16 @@ static int lw_step_once(PgLarge *w, float dt_in) {
     PG_CUDA(cudaMemsetAsync(v.pushed_bits, 0, sizeof(unsigned) * words, w->stream));
   }
   w->bookkeeping_clean = 0;                     // until this step's k_reset_touched is in the stream
-  LW_LAUNCH(w, K_PASS3, k_pass3, lw_grid(w, v.n, 256), 256, v, dt, w->step_in_call, 1, full_reset);
+  if (w->timing) cudaEventRecord(w->kev[K_PASS3][0], w->stream);
+  if (v.n >= v.pass3_split_min) {
+    k_pass3<<<lw_grid(w, v.n, 256), 256, 0, w->stream>>>(v, dt, w->step_in_call, 1, full_reset);
+    k_pass3_exact<<<w->sm_count * 8, 128, 0, w->stream>>>(v, dt, w->step_in_call, 1, full_reset);
+    w->launches += 2;
+  } else {
+    k_pass3_all<<<lw_grid(w, v.n, 256), 256, 0, w->stream>>>(v, dt, w->step_in_call, 1, full_reset);
+    w->launches++;
+  }
+  if (w->timing) cudaEventRecord(w->kev[K_PASS3][1], w->stream);
   w->last_proven = 1;
   w->last_iterations = 0;
   int rc = lw_build_pairs(w);
@@ -1478,6 +1509,7 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   // threshold keeps k_requery on its eight-lane path in worlds where few bodies grow
   v.stage_limit = getenv("PG_LARGE_SMALL_STAGES") ? 3 : (1 << 20);
   v.requery_few = getenv("PG_LARGE_REQUERY_FEW") ? atoi(getenv("PG_LARGE_REQUERY_FEW")) : 4096;
+  v.pass3_split_min = getenv("PG_LARGE_PASS3_SPLIT_MIN") ? atoi(getenv("PG_LARGE_PASS3_SPLIT_MIN")) : 262144;
   v.cells_cap = (int)std::min<size_t>(4 * n + 4096, (size_t)1 << 28);
   v.pairs_cap = (long long)(4 * n + 65536);
   v.max_events = (int)std::max<size_t>(n / 4, 65536);

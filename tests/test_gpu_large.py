@@ -25,9 +25,10 @@ def _ev(e):
 
 @pytest.mark.parametrize("n,L,steps,env", [(256, 10.0, 120, {}), (3000, 16.0, 40, {}), (20000, 40.0, 12, {}),
                                            (3000, 16.0, 40, {"PG_LARGE_REQUERY_FEW": "0"}),      # k_requery's eight-lane path
-                                           (3000, 12.0, 30, {"PG_LARGE_SMALL_STAGES": "1"})])    # overflow paths of the block stages
+                                           (3000, 12.0, 30, {"PG_LARGE_SMALL_STAGES": "1"}),     # overflow paths of the block stages
+                                           (3000, 12.0, 30, {"PG_LARGE_PASS3_SPLIT_MIN": "0"})]) # pass 3 as probe + dense exact kernel (large worlds)
 def test_large_world_equals_sequential_sweep(gpu_lib, oracle_lib, monkeypatch, n, L, steps, env):
-    for k in ("PG_LARGE_REQUERY_FEW", "PG_LARGE_SMALL_STAGES"):
+    for k in ("PG_LARGE_REQUERY_FEW", "PG_LARGE_SMALL_STAGES", "PG_LARGE_PASS3_SPLIT_MIN"):
         monkeypatch.delenv(k, raising=False)
     for k, val in env.items():
         monkeypatch.setenv(k, val)                 # read by pg_large_create
@@ -197,10 +198,15 @@ def test_broadphase_pair_set_bit_exact(gpu_lib, oracle_lib, n, L):
     g.close()
 
 
-@pytest.mark.parametrize("with_player", [False, True])
-def test_level_geometry_world_c5_style(gpu_lib, oracle_lib, with_player):
+@pytest.mark.parametrize("with_player,split", [(False, False), (True, False), (False, True)])
+def test_level_geometry_world_c5_style(gpu_lib, oracle_lib, monkeypatch, with_player, split):
     """Config C5 in small: box planes + static AABB slabs (scene nodes) + spheres visited through their
-    scene nodes + the player capsule against the level; state, node semantics and event order."""
+    scene nodes + the player capsule against the level; state, node semantics and event order.
+    split: pass 3 as probe kernel + dense exact kernel, as worlds of 262144 bodies and more run it."""
+    if split:
+        monkeypatch.setenv("PG_LARGE_PASS3_SPLIT_MIN", "0")
+    else:
+        monkeypatch.delenv("PG_LARGE_PASS3_SPLIT_MIN", raising=False)
     n, L = 2500, 32.0
     statics, pos, vel, players = scenes.level_world(n, L, seed_world=3, with_player=with_player)
     # make sure spheres are actually moving into slabs: a denser, faster subset near the floors
