@@ -4,7 +4,9 @@
 // (world.c:473-554).  Here the same RESULT is produced without the quadratic sweep and without
 // giving up the solve order:
 //
-//   1. pass 3 (spheres x planes) touches only the sphere -> one thread per sphere           [k_pass3]
+//   1. pass 3 (spheres x statics) touches only the sphere -> one thread per sphere: a streaming probe
+//      kernel with the cheap gates, then the exact visits of the few bodies that pass one
+//                                                                        [k_pass3, k_pass3_exact]
 //   2. uniform grid over the post-pass-3 centres; every body carries an envelope
 //        env = r + 2 (|v| + g dt) dt (1+eps)
 //      that bounds where it can be, plus how far interval_collision can reach from there, at ANY
@@ -14,16 +16,24 @@
 //                                           [k_cell_count, scan, k_scatter (counting sort), k_pairs]
 //   3. ORDER-PRESERVING FIXED POINT.  Each body keeps a timeline: the contacts it has suffered so
 //      far, keyed by (row, column) = the position of the visit in the reference's sweep, with the
-//      state they left behind.  Every candidate pair is evaluated as its two visits (i,j) and (j,i)
+//      state they left behind.  A candidate pair is evaluated as its two visits (i,j) and (j,i)
 //      on the states the timelines imply AT THAT KEY (including whether the body's own row, hence
 //      its integration, lies before the key).  The hits found form the next timelines; iterate
 //      until nothing changes.  The earliest event of the true sequential sweep is found in the
 //      first iteration and never changes again; by induction iteration k fixes the k-th link of
 //      every dependency chain, so the fixed point IS the sequential result -- bit for bit, since
-//      every visit runs the exact arithmetic of pg_math.cuh.               [k_eval, k_check]
-//   4. envelopes are re-validated against the final timelines (a contact may have sped a body
-//      up); if one grew, candidates are regenerated and the fixed point repeated.  [k_check, host loop]
-//   5. final state = timeline tail, integrated if the body's own row came after it.        [k_finalize]
+//      every visit runs the exact arithmetic of pg_math.cuh.  An iteration only looks at what can
+//      have changed: k_begin copies the entries of bodies whose timeline did not change (with
+//      partners that did not either) and lists the pairs that need a look; k_eval evaluates them,
+//      one thread per pair, and hands the rare long interval searches to k_eval_hard (a block per
+//      pair); k_check compares the timelines of the bodies involved.
+//                                                          [k_begin, k_eval, k_eval_hard, k_check]
+//   4. envelopes are re-validated against the new timelines (a contact may have sped a body
+//      up); if one grew, the pairs it adds are appended and the iteration continues warm.
+//                                                       [k_check, k_requery, k_requery_wide]
+//   5. final state = timeline tail, integrated if the body's own row came after it; the fixed
+//      point's per-body bookkeeping is put back for the bodies that used it.
+//                                                                    [k_finalize, k_reset_touched]
 //
 // Steps 2 and 5 are the streaming, HBM-bound kernels of SURVEY.md section 8(d).
 #include "pg_common.cuh"
@@ -1387,10 +1397,8 @@ static int lw_step_once(PgLarge *w, float dt_in) {
       requery_pending = false;
     }
     const unsigned long long pairs_before = std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
-    const int np = (int)std::min<unsigned long long>(pairs_before, 0x7fffffffull);
     // the active list's length stays on the device: k_eval runs as many blocks as fit at once and strides
     if (w->timing) cudaEventRecord(w->kev[K_EVAL][0], w->stream);
-    (void)np;
     k_begin<<<wide_grid, 256, 0, w->stream>>>(v, src, dst, it, dt);      // carry + selection; also resets the per-iteration flags
     k_eval<<<w->sm_count * 4, 128, 0, w->stream>>>(v, src, dst, it, dt);
     k_eval_hard<<<w->sm_count, 512, 0, w->stream>>>(v, src, dst, it, dt);
