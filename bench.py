@@ -168,9 +168,13 @@ def run_reference_arm(args, cfg):
         return
     cores = os.cpu_count() or 1
     threads = min(cores, 64)
-    n_sample = threads * 2
-    # bound the run: ~1.2 ms per world-step on one core
+    # Size the sample so that the TIMED region lasts >= ~1.5 s whatever K is (a 40 ms region moved the ratio by
+    # +-50 % between boxes): one world-step of 256 spheres costs ~1.3 ms on one core, so every thread gets
+    # ceil(1.5 s / (K x 1.3 ms)) worlds, at least 2 and at most 64; a "step" is one physics_step of every
+    # sample world.  K = 20 -> 58 worlds per thread, K = 1000 -> 2.
     steps = args.steps
+    per_thread = int(min(64, max(2, -(-1.5 // (max(steps, 1) * 1.3e-3)))))
+    n_sample = threads * per_thread
     if cfg.get("large"):
         # the reference sweep is O(N^2): ~1 minute per step at 65,536 bodies.  One world, one thread
         # (the reference is single-threaded), capped at 3 steps for c2; c4 is not runnable at all.

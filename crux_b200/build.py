@@ -28,6 +28,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math",
     "-Xptxas", "-v",
 ]
+EXTRA_INCLUDES: list[str] = []
 CU_SOURCES = ["physics_gpu.cu", "pg_general.cu", "pg_spheres.cu", "pg_large.cu"]
 HOST_SOURCES = ["host/crux_world.c", "host/crux_colliders.c", "host/crux_scene.c"]
 HEADLESS = os.path.join(LIB, "crux_headless")
@@ -57,12 +58,15 @@ def build_gpu(force: bool = False, verbose: bool = False) -> str:
         logs = []
         for s in srcs:
             o = os.path.join(LIB, os.path.basename(s).replace(".cu", ".o"))
-            if force or _newer(o, [s] + _headers() + [os.path.abspath(__file__)]):
-                r = subprocess.run([NVCC, *NVCC_FLAGS, "-c", s, "-o", o], capture_output=True, text=True)
-                logs.append(r.stderr)
+            tu_log = o[:-2] + ".ptxas.log"         # per translation unit, so that ptxas.log always covers all of them
+            if force or _newer(o, [s] + _headers() + [os.path.abspath(__file__)]) or not os.path.exists(tu_log):
+                r = subprocess.run([NVCC, *NVCC_FLAGS, *EXTRA_INCLUDES, "-c", s, "-o", o], capture_output=True, text=True)
                 if r.returncode != 0:
                     sys.stderr.write(r.stdout + r.stderr)
                     raise RuntimeError(f"nvcc failed on {s}")
+                with open(tu_log, "w") as f:
+                    f.write(f"==== {os.path.basename(s)} ====\n" + r.stderr)
+            logs.append(open(tu_log).read())
             objs.append(o)
         r = subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", GPU_SO, *objs],
                            capture_output=True, text=True)

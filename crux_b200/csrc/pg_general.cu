@@ -188,6 +188,22 @@ __global__ void k_pair_visit(PgBody *a, PgBody *b, int n, float dt, int *ev) {
   ev[k] = pgm::visit_ordered(A, B, dt) ? 1 : 0;
 }
 
+// The two collider pairs the reference leaves as empty functions (distance.c:301-303,323-325;
+// narrow_phase.c:522-524,590-592; resolution.c:572-574,624-626): their table entries return undefined values
+// upstream, so a direct table-level query is rejected at the boundary.  Inside a step such
+// a visit never fires (pgm::visit_ordered), which pg_pair_visit reports as "no event".
+bool undefined_pair(const PgBody *a, const PgBody *b, int n) {
+  if (!a || !b) return false;
+  for (int k = 0; k < n; k++) {
+    const int ta = a[k].collider_type, tb = b[k].collider_type;
+    if ((ta == PG_CAPSULE && (tb == PG_SPHERE || tb == PG_CAPSULE)) || (ta == PG_SPHERE && tb == PG_CAPSULE)) {
+      pg_set_error("pair %d: sphere-capsule / capsule-capsule is undefined in the reference (empty functions)", k);
+      return true;
+    }
+  }
+  return false;
+}
+
 template <typename F>
 int with_pairs(const PgBody *a, const PgBody *b, int n, PgBody **da, PgBody **db, F &&body) {
   *da = nullptr; *db = nullptr;
@@ -234,6 +250,7 @@ int pg_pair_max_move(const PgBody *a, int n, float t0, float t1, float *out) {
 }
 
 int pg_pair_min_dist(const PgBody *a, const PgBody *b, int n, const float *t, float *out) {
+  if (n > 0 && undefined_pair(a, b, n)) return PG_ERR_UNSUPPORTED;
   PgBody *da, *db;
   return with_pairs(a, b, n, &da, &db, [&]() -> int {
     DevBuf<float> o, dt_; if (o.alloc(n) || dt_.alloc(n)) return PG_ERR_CUDA;
@@ -246,6 +263,7 @@ int pg_pair_min_dist(const PgBody *a, const PgBody *b, int n, const float *t, fl
 
 int pg_pair_interval_collision(const PgBody *a, const PgBody *b, int n, float t0, float t1,
                                int32_t *out_hit, float *out_hit_time) {
+  if (n > 0 && undefined_pair(a, b, n)) return PG_ERR_UNSUPPORTED;
   PgBody *da, *db;
   return with_pairs(a, b, n, &da, &db, [&]() -> int {
     DevBuf<int> h; DevBuf<float> t; if (h.alloc(n) || t.alloc(n)) return PG_ERR_CUDA;
@@ -258,6 +276,7 @@ int pg_pair_interval_collision(const PgBody *a, const PgBody *b, int n, float t0
 
 int pg_pair_narrow_phase(const PgBody *a, const PgBody *b, int n, float dt, int32_t *out_colliding,
                          float *out_hit_time) {
+  if (n > 0 && undefined_pair(a, b, n)) return PG_ERR_UNSUPPORTED;
   PgBody *da, *db;
   return with_pairs(a, b, n, &da, &db, [&]() -> int {
     DevBuf<int> h; DevBuf<float> t; if (h.alloc(n) || t.alloc(n)) return PG_ERR_CUDA;
@@ -269,6 +288,7 @@ int pg_pair_narrow_phase(const PgBody *a, const PgBody *b, int n, float dt, int3
 }
 
 int pg_pair_resolve(PgBody *a, PgBody *b, int n, const float *hit_time, float dt) {
+  if (n > 0 && undefined_pair(a, b, n)) return PG_ERR_UNSUPPORTED;
   PgBody *da, *db;
   return with_pairs(a, b, n, &da, &db, [&]() -> int {
     DevBuf<float> t; if (t.alloc(n)) return PG_ERR_CUDA;

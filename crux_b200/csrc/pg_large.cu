@@ -1499,8 +1499,8 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   if (max_spheres <= 0 || max_static < 0 || max_static > (1 << 22)) { pg_set_error("pg_large_create: bad argument"); return nullptr; }
   PG_CUDA_NULL(cudaSetDevice(device));
   PgLarge *w = new PgLarge();
-  w->timing = getenv("PG_LARGE_TIMING") != nullptr || getenv("PG_LARGE_DEBUG") != nullptr;
   memset(w, 0, sizeof(*w));
+  w->timing = getenv("PG_LARGE_TIMING") != nullptr || getenv("PG_LARGE_DEBUG") != nullptr;
   w->device = device;
   w->cap_n = max_spheres;
   w->cap_static = std::max(max_static, 1);
@@ -1792,9 +1792,21 @@ int pg_large_step(PgLarge *w, float dt, int n_steps) {
     if (rc) return rc;
     w->launches++;
   }
-  for (int s = 0; s < n_steps && rc == PG_OK; s++) { w->step_in_call = s; rc = lw_step_once(w, dt); }
+  int unproven = 0, first_unproven = -1;
+  for (int s = 0; s < n_steps && rc == PG_OK; s++) {
+    w->step_in_call = s;
+    rc = lw_step_once(w, dt);
+    if (rc == PG_OK && !w->last_proven) { if (!unproven) first_unproven = s; unproven++; }
+  }
   PG_CUDA(cudaEventRecord(w->ev1, w->stream));
   PG_CUDA(cudaStreamSynchronize(w->stream));
+  if (rc == PG_OK && unproven) {
+    // loud, not silent: the state HAS been advanced (all n_steps ran), but at least one step's fixed point did
+    // not converge or an envelope outgrew the grid, so equality with the sequential sweep is not established
+    w->last_proven = 0;
+    pg_set_error("pg_large_step: %d of %d steps not proven identical to the sequential reference order (first: step %d)", unproven, n_steps, first_unproven);
+    return PG_ERR_UNPROVEN;
+  }
   return rc;
 }
 
@@ -1887,6 +1899,15 @@ long long pg_large_events(PgLarge *w, PgEvent *out, long long cap, int *overflow
 int pg_large_set_players(PgLarge *w, const PgBody *players, int n) {
   if (!w || n < 0 || n > 8 || (n > 0 && !players)) { pg_set_error("pg_large_set_players: bad argument (at most 8 players)"); return PG_ERR_ARG; }
   if (!w->player_world) { pg_set_error("pg_large_set_players: set the level (pg_large_set with static bodies) first"); return PG_ERR_ARG; }
+  // Passes 1-2 run the players against the LEVEL only: that is the whole of the reference's result when every
+  // player is a capsule (scene.c:311-318), because the sphere-capsule table entries are empty functions
+  // upstream and never fire.  A sphere or AABB player has live entries against the dynamic spheres
+  // (world.c:277-367) which this path does not evaluate -- refuse it instead of silently dropping contacts.
+  for (int i = 0; i < n; i++)
+    if (players[i].collider_type != PG_CAPSULE) {
+      pg_set_error("pg_large_set_players: player %d is not a capsule (collider type %d); only capsule players are supported in a large world", i, players[i].collider_type);
+      return PG_ERR_UNSUPPORTED;
+    }
   int rc = pg_worlds_set_bodies(w->player_world, 0, PG_CLASS_PLAYER, players, n);
   if (rc) return rc;
   w->n_players = n;

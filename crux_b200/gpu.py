@@ -80,6 +80,14 @@ class PgError(RuntimeError):
     pass
 
 
+class PgUnproven(PgError):
+    """pg_large_step returned PG_ERR_UNPROVEN: the steps ran, but equality with the reference's sequential
+    sweep is not established for at least one of them."""
+
+
+PG_ERR_UNPROVEN = -5
+
+
 _lib = None
 
 
@@ -108,8 +116,29 @@ def _ptr(a):
 def _check(rc, what: str):
     if rc is None or (isinstance(rc, int) and rc < 0):
         msg = lib().pg_last_error()
-        raise PgError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+        cls = PgUnproven if rc == PG_ERR_UNPROVEN else PgError
+        raise cls(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
     return rc
+
+
+def _state_array(a, shape, dtype, what: str, writable: bool = False, optional: bool = False):
+    """The library copies exactly prod(shape) items of `dtype` through the raw pointer: refuse anything else
+    (a float64, sliced, short or read-only array would corrupt the heap silently)."""
+    if a is None:
+        if optional:
+            return None
+        raise PgError(f"{what}: array required")
+    if not isinstance(a, np.ndarray):
+        raise PgError(f"{what}: numpy array expected, got {type(a).__name__}")
+    if a.dtype != np.dtype(dtype):
+        raise PgError(f"{what}: dtype {a.dtype} (need {np.dtype(dtype)})")
+    if tuple(a.shape) != tuple(shape):
+        raise PgError(f"{what}: shape {tuple(a.shape)} (need {tuple(shape)})")
+    if not a.flags["C_CONTIGUOUS"]:
+        raise PgError(f"{what}: array must be C-contiguous")
+    if writable and not a.flags["WRITEABLE"]:
+        raise PgError(f"{what}: array must be writable")
+    return a
 
 
 def prepare(bodies: np.ndarray) -> np.ndarray:
@@ -193,12 +222,32 @@ class GpuWorlds:
         st = prepare(statics)
         _check(self.L.pg_worlds_set_spheres(self.h, first, count, _ptr(st), len(st), n, _ptr(pos), _ptr(vel),
                                             np.float32(radius), np.float32(restitution)), "pg_worlds_set_spheres")
+        self._sphere_n = n
+
+    def _state_args(self, first, count, pos, vel, at_rest, what, writable):
+        if first < 0 or count <= 0 or first + count > self.n_worlds:
+            raise PgError(f"{what}: world range [{first}, {first + count}) outside 0..{self.n_worlds}")
+        if getattr(self, "_sphere_n", None) is not None:      # sphere mode: every world holds the same count
+            total = count * self._sphere_n
+        else:
+            total = sum(self.body_count(k, CLASS_DYNAMIC) for k in range(first, first + count))
+        for a, per, dt_, name, opt in ((pos, 3, np.float32, "pos", False), (vel, 3, np.float32, "vel", False),
+                                       (at_rest, 1, np.uint8, "at_rest", True)):
+            if a is None and opt:
+                continue
+            if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dt_) or not a.flags["C_CONTIGUOUS"] or a.size != total * per \
+                    or (writable and not a.flags["WRITEABLE"]):
+                raise PgError(f"{what} {name}: need a C-contiguous {'writable ' if writable else ''}{np.dtype(dt_)} array of "
+                              f"{total} x {per} items, got {type(a).__name__}"
+                              + (f" dtype {a.dtype} shape {a.shape} contiguous {a.flags['C_CONTIGUOUS']}" if isinstance(a, np.ndarray) else ""))
 
     def upload_state(self, first: int, count: int, pos: np.ndarray, vel: np.ndarray, at_rest=None):
+        self._state_args(first, count, pos, vel, at_rest, "upload_state", False)
         _check(self.L.pg_worlds_upload_state(self.h, first, count, _ptr(pos), _ptr(vel), _ptr(at_rest)),
                "pg_worlds_upload_state")
 
     def download_state(self, first: int, count: int, pos: np.ndarray, vel: np.ndarray, at_rest=None):
+        self._state_args(first, count, pos, vel, at_rest, "download_state", True)
         _check(self.L.pg_worlds_download_state(self.h, first, count, _ptr(pos), _ptr(vel), _ptr(at_rest)),
                "pg_worlds_download_state")
 
@@ -211,6 +260,7 @@ class GpuWorlds:
 
     def step_host(self, dt: float, n_steps: int, pos: np.ndarray, vel: np.ndarray, at_rest=None):
         """Host arrays in, n_steps steps, host arrays out (in place); chunk-pipelined inside the library."""
+        self._state_args(0, self.n_worlds, pos, vel, at_rest, "step_host", True)
         _check(self.L.pg_worlds_step_host(self.h, np.float32(dt), n_steps, _ptr(pos), _ptr(vel), _ptr(at_rest)),
                "pg_worlds_step_host")
 
@@ -333,12 +383,18 @@ class GpuLargeWorld:
         return out[:n]
 
     def upload_state(self, pos, vel, at_rest=None):
+        _state_array(pos, (self.n, 3), np.float32, "upload_state pos")
+        _state_array(vel, (self.n, 3), np.float32, "upload_state vel")
+        _state_array(at_rest, (self.n,), np.uint8, "upload_state at_rest", optional=True)
         _check(self.L.pg_large_upload_state(self.h, _ptr(pos), _ptr(vel), _ptr(at_rest)), "pg_large_upload_state")
 
     def download_state(self, pos=None, vel=None, at_rest=None):
         pos = np.zeros((self.n, 3), np.float32) if pos is None else pos
         vel = np.zeros((self.n, 3), np.float32) if vel is None else vel
         at_rest = np.zeros(self.n, np.uint8) if at_rest is None else at_rest
+        _state_array(pos, (self.n, 3), np.float32, "download_state pos", writable=True)
+        _state_array(vel, (self.n, 3), np.float32, "download_state vel", writable=True)
+        _state_array(at_rest, (self.n,), np.uint8, "download_state at_rest", writable=True)
         _check(self.L.pg_large_download_state(self.h, _ptr(pos), _ptr(vel), _ptr(at_rest)), "pg_large_download_state")
         return pos, vel, at_rest
 

@@ -46,8 +46,11 @@ enum {
   PG_ERR_CUDA = -1,       /* a CUDA runtime call failed (pg_last_error() has the text) */
   PG_ERR_ARG = -2,        /* bad handle / index / count */
   PG_ERR_CAPACITY = -3,   /* more bodies than the handle was created for */
-  PG_ERR_UNSUPPORTED = -4 /* collider pair the reference leaves undefined (sphere-capsule,
-                             capsule-capsule: distance.c:301-303,323-325; narrow_phase.c:522-524,590-592) */
+  PG_ERR_UNSUPPORTED = -4,/* collider pair the reference leaves undefined (sphere-capsule,
+                             capsule-capsule: distance.c:301-303,323-325; narrow_phase.c:522-524,590-592),
+                             or a body mix an entry point does not serve */
+  PG_ERR_UNPROVEN = -5    /* pg_large_step: the step ran, but its result is NOT proven identical to the
+                             reference's sequential sweep (see pg_large_exactness); the state was advanced */
 };
 
 /*
@@ -217,7 +220,10 @@ int  pg_large_exactness(PgLarge *w, int *iterations, int *proven_exact, long lon
 /* ------------------------------------------------------------------------------------------
  * Per-pair entry points: the reference's public predicate/table functions evaluated on the GPU
  * for n independent pairs (records in host memory; results in host memory).  A[k] must already be
- * the lower collider type, as the tables require (world.c:482-488).
+ * the lower collider type, as the tables require (world.c:482-488).  The table-level queries (min_dist,
+ * interval_collision, narrow_phase, resolve) return PG_ERR_UNSUPPORTED for a sphere-capsule or
+ * capsule-capsule pair -- empty functions with undefined results upstream; pg_pair_visit,
+ * which is what the step does with such a pair, reports "no event" and leaves both bodies alone.
  * ------------------------------------------------------------------------------------------ */
 int  pg_pair_max_move(const PgBody *a, int n, float t0, float t1, float *out);
 int  pg_pair_min_dist(const PgBody *a, const PgBody *b, int n, const float *t, float *out);

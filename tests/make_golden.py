@@ -159,6 +159,8 @@ if __name__ == "__main__":
 # ---- scene-file fixtures (config C1): reduced copies of the reference's scene DATA + dumps of the
 # reference-linked headless driver (oracle/_ref/crux_headless_ref)
 SCENES = [("bouncehouse", True, 1000), ("bouncehouse3", False, 600), ("scene_sphere", False, 600)]
+# the game layer's write paths (crux_headless --script): item pickup -> physics_remove_body, player pokes
+SCRIPTED = [("bouncehouse", "pickup", 400), ("bouncehouse", "jump", 400), ("plates_only", "jump", 400)]
 
 
 def _reduce(node):
@@ -193,6 +195,20 @@ def make_scene_fixtures():
         subprocess.run([exe, dst, str(steps), os.path.join(out_dir, f"{name}_{steps}.bin")] + args, check=True)
         assert open(full, "rb").read() == open(os.path.join(out_dir, f"{name}_{steps}.bin"), "rb").read(), "reduction changed the workload"
         os.remove(full)
+    # our own reduced scene: the six plates of bouncehouse.json and nothing that moves but the player
+    doc = json.load(open(os.path.join(out_dir, "bouncehouse.json")))
+
+    def _static_only(node):
+        kids = [_static_only(c) for c in node.get("children", [])
+                if not (c.get("collider") and c["collider"].get("dynamic"))]
+        out = {k: v for k, v in node.items() if k != "children"}
+        if kids:
+            out["children"] = kids
+        return out
+    json.dump({"nodes": _static_only(doc["nodes"])}, open(os.path.join(out_dir, "plates_only.json"), "w"), indent=1)
+    for name, script, steps in SCRIPTED:
+        subprocess.run([exe, os.path.join(out_dir, name + ".json"), str(steps), os.path.join(out_dir, f"{name}_{script}_{steps}.bin"),
+                        "--player", "--script", script], check=True)
 
 
 if __name__ == "__main__":

@@ -58,3 +58,56 @@ def test_scene_file_through_reference_api(tmp_path, gpu_lib, name, player, steps
         assert len(bad) == 0, f"first differing (body, field): {bad[:5].tolist()} got {bg[bad[0][0]]} want {bw[bad[0][0]]}"
         assert np.array_equal(eg, ew)
     assert got == want
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def _assert_same_dump(got, want):
+    if got != want:
+        hg, bg, eg = parse_dump(got)
+        hw, bw, ew = parse_dump(want)
+        assert list(hg) == list(hw), (list(hg), list(hw))
+        bad = np.argwhere(bg.view(np.uint32) != bw.view(np.uint32))
+        assert len(bad) == 0, f"first differing (body, field): {bad[:5].tolist()} got {bg[bad[0][0]]} want {bw[bad[0][0]]}"
+        assert np.array_equal(eg, ew)
+    assert got == want
+
+
+def test_item_pickup_removes_bodies_mid_game(tmp_path, gpu_lib):
+    """three dynamic bodies are ITEM entities; the player (walked under them by position
+    writes) triggers EVENT_PLAYER_ITEM_PICKUP, whose handling removes the item's body with physics_remove_body
+    (event.c:118-125 -> scene.c:1203 -> world.c:147-172, swap-and-pop: the solve order of the frames that
+    follow changes); two more removals hit the first and the last dynamic slot.  400 frames, byte-identical to
+    the same driver linked with the unmodified reference physics."""
+    out = tmp_path / "gpu.bin"
+    text = _run([EXE, os.path.join(SC, "bouncehouse.json"), "400", str(out), "--player", "--script", "pickup"])
+    assert "script pickup: 5 bodies removed" in text, text
+    got = open(out, "rb").read()
+    hdr, bodies, events = parse_dump(got)
+    assert list(hdr[:3]) == [6, 3, 1] and int((events[:, 0] == 1).sum()) == 3      # three pickups happened
+    _assert_same_dump(got, open(os.path.join(SC, "bouncehouse_pickup_400.bin"), "rb").read())
+
+
+@pytest.mark.parametrize("scene", ["bouncehouse", "plates_only"])
+def test_player_pokes_between_frames(tmp_path, gpu_lib, scene):
+    """SURVEY.md 8(f)3: the player write path of player.c -- jump (at_rest = false, velocity[1] = 3;
+    player.c:160-173), walking (position writes + scene_node_update; player.c:11-50), turning (rotation write;
+    player.c:155-157) -- between physics_step calls, 400 frames, byte-identical to the reference-linked twin.
+    In the scene where nothing but the player moves the dirty-range upload must send exactly the player's
+    record in a frame that poked (or moved) it, and nothing at all once it rests unpoked."""
+    out = tmp_path / "gpu.bin"
+    text = _run([EXE, os.path.join(SC, scene + ".json"), "400", str(out), "--player", "--script", "jump"])
+    assert "4 jumps" in text, text
+    _assert_same_dump(open(out, "rb").read(), open(os.path.join(SC, f"{scene}_jump_400.bin"), "rb").read())
+    up = {int(l.split()[1]): int(l.split()[3]) for l in text.splitlines() if l.startswith("frame ")}
+    assert len(up) == 400
+    if scene == "plates_only":
+        assert up[0] == 7                                   # first frame: the six plates and the player
+        assert all(v <= 1 for k, v in up.items() if k > 0), [kv for kv in up.items() if kv[1] > 1][:5]
+        for k in (30, 120, 121, 300, 60, 75, 200):          # frames whose script poked the player record
+            assert up[k] == 1, (k, up[k])
+        assert sum(1 for k, v in up.items() if k > 0 and v == 0) > 100      # resting and unpoked: nothing travels

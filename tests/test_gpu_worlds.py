@@ -351,3 +351,101 @@ def test_step_host_pipeline_matches_resident_path(gpu_lib, oracle_lib):
         r = o.read(1)
         assert gen.same_bits(P[k], r["position"]) and gen.same_bits(V[k], r["velocity"])
     a.close(); b.close()
+
+
+def test_remove_add_and_poke_between_steps(gpu_lib, oracle_lib):
+    """pg_worlds_remove_body (world.c:147-172 swap-and-pop, changes the solve order), pg_worlds_add_body
+    (world.c:41-142 add-time rules) and the dirty-range poke of the player record (player.c:160-173:
+    at_rest = false, velocity[1] = 3, plus a position write) between step calls, against the oracle's
+    world_remove / world_add_many / world_poke: state, node matrices and event order stay bit-exact."""
+    rng = np.random.default_rng(11)
+    st, dy, pl = gen.mixed_world(rng, gpu_lib.node_transform, with_player=True, n_dyn=20)
+    w = gpu_lib.GpuWorlds(1, len(st) + 2, len(dy) + 2, len(pl), max_events_per_world=4096)
+    w.set_bodies(0, scenes.CLASS_STATIC, st)
+    w.set_bodies(0, scenes.CLASS_DYNAMIC, dy)
+    w.set_bodies(0, scenes.CLASS_PLAYER, pl)
+    o = ora.World(oracle_lib, st, dy, pl)
+    total = 0
+
+    def run_and_compare(tag, frames=30):
+        nonlocal total
+        w.step(DT, frames, refresh_nodes=True)
+        o.step(DT, frames, refresh_nodes=1)
+        for cls in (0, 1, 2):
+            g, r = w.get_bodies(0, cls), o.read(cls)
+            assert len(g) == len(r), (tag, cls, len(g), len(r))
+            assert gen.state_equal(g, r), (tag, cls)
+            assert gen.same_bits(g["node_xform"], r["node_xform"]), (tag, cls)
+        eg, eo = _events_tuple(w.events()), _events_tuple(o.events())
+        assert eg == eo, tag
+        total += len(eg)
+
+    run_and_compare("start")
+    # remove from the middle (the last record moves into the hole), then the last, then the first
+    for step, index in enumerate((3, len(dy) - 2, 0)):
+        w.remove_body(0, scenes.CLASS_DYNAMIC, index)
+        o.remove(scenes.CLASS_DYNAMIC, index)
+        assert w.body_count(0, scenes.CLASS_DYNAMIC) == o.counts()[1]
+        run_and_compare(("remove", step))
+    # a static box disappears as well (pass 1 and pass 3 lose a column)
+    w.remove_body(0, scenes.CLASS_STATIC, 7)
+    o.remove(scenes.CLASS_STATIC, 7)
+    run_and_compare("remove static")
+    # physics_add_body: a new dynamic AABB (its velocity kept) and a new static one (velocity forced to 0)
+    nb = dy[5:6].copy()
+    nb["position"] = [[0.3, 2.5, -0.4]]; nb["velocity"] = [[1.5, -2.0, 0.5]]
+    nb["node_xform"] = gen.node_xform(gpu_lib.node_transform, nb["position"][0], [0, 0, 0], [1, 1, 1], np.eye(4, dtype=np.float32).reshape(16))
+    ns = st[7:8].copy()
+    ns["velocity"] = [[9.0, 9.0, 9.0]]
+    assert w.add_body(0, nb[0]) == o.counts()[1]
+    o.add(nb)
+    assert w.add_body(0, ns[0]) == o.counts()[0]
+    o.add(ns)
+    assert np.all(w.get_bodies(0, scenes.CLASS_STATIC)["velocity"][-1] == 0.0)
+    run_and_compare("add")
+    # the player write path: jump + walk, several times
+    for k in range(4):
+        rec = w.get_bodies(0, scenes.CLASS_PLAYER)[0:1].copy()
+        rec["at_rest"] = 0
+        rec["velocity"][0, 1] = 3.0
+        rec["position"][0, 0] += np.float32(0.25)
+        rec["position"][0, 2] -= np.float32(0.125)
+        rec["rotation"][0, 1] = np.float32(-35.0 + 90.0 + 10.0 * k)
+        rec = gpu_lib.prepare(rec)                            # rotation changed: refresh the host-computed Euler matrices
+        w.update_bodies(0, scenes.CLASS_PLAYER, 0, rec)
+        o.poke(scenes.CLASS_PLAYER, 0, rec)
+        run_and_compare(("poke", k), frames=20)
+    assert total > 100, total
+    w.close()
+
+
+def test_undefined_pairs_never_fire_and_are_rejected_at_the_boundary(gpu_lib):
+    """sphere-capsule and capsule-capsule are empty functions upstream.  Table-level queries are
+    refused with PG_ERR_UNSUPPORTED; inside a step such a visit never fires: a sphere flies straight through a
+    capsule player, neither is touched, no event."""
+    from crux_b200.gpu import PgError
+    sph = scenes.sphere_bodies(np.array([[0.0, 1.0, 0.6]], np.float32), np.array([[0.0, 0.0, -3.0]], np.float32))
+    cap = gen.new_bodies(1)
+    cap["collider_type"] = scenes.COLLIDER_CAPSULE if hasattr(scenes, "COLLIDER_CAPSULE") else 2
+    cap["entity_type"] = 3
+    cap["shape"][0, :3] = [0, 0.25, 0]; cap["shape"][0, 3:6] = [0, 1.75, 0]; cap["shape"][0, 6] = 0.25
+    cap["has_node"] = 1; cap["has_parent"] = 1
+    cap["node_xform"] = gen.node_xform(gpu_lib.node_transform, [0, 0, 0], [0, 0, 0], [1, 1, 1], np.eye(4, dtype=np.float32).reshape(16))
+    for a, b in ((sph, cap), (cap, cap)):
+        for call in (lambda: gpu_lib.pair_min_dist(a, b, 0.0), lambda: gpu_lib.pair_interval_collision(a, b, 0.0, DT),
+                     lambda: gpu_lib.pair_narrow_phase(a, b, DT), lambda: gpu_lib.pair_resolve(a, b, 0.0, DT)):
+            with pytest.raises(PgError, match="-4"):
+                call()
+        ev, a2, b2 = gpu_lib.pair_visit(a, b, DT)
+        assert ev[0] == 0 and gen.same_bits(a2["position"], gpu_lib.prepare(a.copy())["position"]) and gen.same_bits(b2["velocity"], b["velocity"])
+    # in a world: the sphere crosses the capsule's volume in ~20 frames; only gravity acts on it
+    w = gpu_lib.GpuWorlds(1, 1, 1, 1, max_events_per_world=64)
+    floor = scenes.plane_bodies(np.array([[0.0, 1.0, 0.0, -50.0]], np.float32))
+    w.set_bodies(0, scenes.CLASS_STATIC, floor)
+    w.set_bodies(0, scenes.CLASS_DYNAMIC, sph)
+    w.set_bodies(0, scenes.CLASS_PLAYER, cap)
+    w.step(DT, 30, refresh_nodes=True)
+    assert len(w.events()) == 0
+    d = w.get_bodies(0, scenes.CLASS_DYNAMIC)
+    assert d["position"][0, 2] < -0.8 and d["velocity"][0, 0] == 0.0 and d["velocity"][0, 2] == -3.0
+    w.close()
