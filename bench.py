@@ -202,6 +202,23 @@ def run_reference_arm(args, cfg):
 # the CUDA path
 # ------------------------------------------------------------------------------------------------
 
+E2E_API_NOTE = ("pg_worlds_step_host(dt, 1, pos, vel, at_rest): pinned host arrays in and out every step; world chunks over separate "
+                "upload, compute and download queues, replayed as one CUDA graph")
+
+
+def _set_affinity(local_rank: int):
+    """Bind the rank to the CPUs NVML reports as closest to its GPU, so that its pinned host buffers are
+    allocated (first touch) and copied NUMA-local; a no-op where NVML or the topology says nothing."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+    except Exception:
+        pass
+
+
 def run_large_arm(args, cfg):
     """One large world per rank (replicas under N > 1: the slab decomposition is not built yet)."""
     import torch
@@ -337,7 +354,7 @@ def run_large_arm(args, cfg):
 def run_gpu_arm(args, cfg):
     import torch
     import torch.distributed as dist
-    from crux_b200 import gpu
+    from crux_b200 import gpu, shard
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -345,20 +362,18 @@ def run_gpu_arm(args, cfg):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    _set_affinity(local_rank)
+    comm = None
     if world_size > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # the path's one collective lives in the library: its own NCCL communicator, bootstrapped with a 128-byte
+        # id that torch.distributed carries from rank 0 to the others (plumbing only)
+        comm = gpu.Comm.from_torch_distributed(local_rank)
 
     nw, n, L = cfg["n_worlds"], cfg["n_spheres"], cfg["L"]
-    bodies = nw * n
-    first_world = rank * nw                                 # weak scaling: every rank owns nw worlds
-    pos, vel = scenes.sphere_worlds(nw, n, L, first_world=first_world)
     statics = scenes.plane_bodies(scenes.box_planes(L))
-    worlds = gpu.GpuWorlds(nw, len(statics), n, 0, max_events_per_world=0, device=local_rank)
-    worlds.set_spheres(0, statics, pos, vel)
-
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
-    stats_dev = torch.zeros(8, dtype=torch.float64, device="cuda")
     spl = max(1, min(args.steps_per_launch, args.steps))
     dt = float(scenes.DT_60HZ)
 
@@ -368,65 +383,94 @@ def run_gpu_arm(args, cfg):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def launch(k):
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def make_worlds(first_world, count):
+        pos, vel = scenes.sphere_worlds(count, n, L, first_world=first_world)
+        w = gpu.GpuWorlds(count, len(statics), n, 0, max_events_per_world=0, device=local_rank)
+        w.set_spheres(0, statics, pos, vel)
+        return w
+
+    def launch(worlds, k):
+        """One timed unit: L2 flush (outside the clock), then k steps in one launch + the statistics all-reduce,
+        both on the library's stream inside ONE CUDA-event pair (pg_worlds_last_step_ms)."""
         flush.zero_()
         torch.cuda.synchronize()
         worlds.step(dt, k)
-        worlds.stats(dev_out_ptr=stats_dev.data_ptr(), want_host=False)     # fused partials -> device vector
+        worlds.stats_allreduce(comm)                                        # NCCL inside the library, no host sync
         worlds.sync()
-        ms = worlds.last_step_ms()
-        if world_size > 1:
-            dist.all_reduce(stats_dev)                                      # NCCL, 64 bytes
-        return ms
+        return worlds.last_step_ms()
 
-    # warm-up
-    done = 0
-    while done < args.warmup:
-        k = min(spl, args.warmup - done)
-        launch(k)
-        done += k
-    barrier()
+    def timed(worlds, steps, warmup):
+        done = 0
+        while done < warmup:
+            k = min(spl, warmup - done)
+            launch(worlds, k)
+            done += k
+        barrier()
+        ev_ms, per = 0.0, []
+        t0 = time.perf_counter()
+        done = 0
+        while done < steps:
+            k = min(spl, steps - done)
+            ms = launch(worlds, k)
+            ev_ms += ms
+            per.append(ms / k)
+            done += k
+        barrier()
+        return max_over_ranks(ev_ms), per, time.perf_counter() - t0
 
+    # ---- weak scaling (the driver's line): every rank owns nw worlds
+    bodies = nw * n
+    worlds = make_worlds(rank * nw, nw)
     sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = worlds.launches
-    ev_ms = 0.0
-    launch_ms = []
-    t_wall0 = time.perf_counter()
-    done = 0
-    while done < args.steps:
-        k = min(spl, args.steps - done)
-        ms = launch(k)
-        ev_ms += ms
-        launch_ms.append(ms / k)
-        done += k
-    barrier()
-    wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    sampler.start()
+    ev_ms_max, launch_ms, wall = timed(worlds, args.steps, args.warmup)
     gpu_launches = worlds.launches - launches0
-    stats_host = stats_dev.cpu().numpy().copy()
-
-    t = torch.tensor([ev_ms], dtype=torch.float64, device="cuda")
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ev_ms_max = float(t.item())
+    stats_sum = worlds.stats_allreduce(comm, want_host=True)                # summed over all ranks
     value = bodies * world_size * args.steps / (ev_ms_max * 1e-3)
 
+    # ---- the hard regime: the same batch after its worlds have thermalised (pre-advanced, untimed)
+    therm = None
+    if args.thermalise_steps > 0:
+        worlds.step(dt, args.thermalise_steps)
+        worlds.sync()
+        ev2, per2, _ = timed(worlds, args.steps, 0)
+        therm = {"value": bodies * world_size * args.steps / (ev2 * 1e-3), "ms_per_step": ev2 / args.steps,
+                 "pre_advanced_steps": args.thermalise_steps + args.warmup + args.steps}
+    clocks = sampler.stop()
+    worlds.close()
+
+    # ---- strong scaling: BASELINE's named batch (4096 worlds in total) split over the ranks
+    strong = None
+    if world_size > 1:
+        first, count = shard.shard_range(cfg["n_worlds"], rank, world_size)
+        sw = make_worlds(first, count)
+        ev3, _, _ = timed(sw, args.steps, args.warmup)
+        strong = {"value": cfg["n_worlds"] * n * args.steps / (ev3 * 1e-3), "ms_per_step": ev3 / args.steps,
+                  "worlds_total": cfg["n_worlds"], "worlds_per_gpu": count, "scaling": "strong"}
+        sw.close()
+
     # ---- end to end through the host-buffer API: H2D state, one step, D2H state, every step
+    worlds = make_worlds(rank * nw, nw)
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     hp = gpu.PinnedArray((nw, n, 3), np.float32); hv = gpu.PinnedArray((nw, n, 3), np.float32)
     hr = gpu.PinnedArray((nw, n), np.uint8)
     worlds.download_state(0, nw, hp.array, hv.array, hr.array)
+    for _ in range(3):
+        worlds.step_host(dt, 1, hp.array, hv.array, hr.array)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         worlds.step_host(dt, 1, hp.array, hv.array, hr.array)           # H2D + step + D2H, synchronous
     barrier()
-    e2e_wall = time.perf_counter() - t0
-    t = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = bodies * world_size * e2e_steps / float(t.item())
+    e2e_wall = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = bodies * world_size * e2e_steps / e2e_wall
     h2d = bodies * (12 + 12 + 1)
     d2h = bodies * (12 + 12 + 1)
     checksum = float(np.abs(hp.array).sum())
@@ -439,14 +483,18 @@ def run_gpu_arm(args, cfg):
         achieved = algo_bytes / (avg_launch_ms * 1e-3) / 1e9
         traffic = None
         issue = {}
-        rj = os.path.join(ROOT, "profiles", "roofline_r01.json")
-        if os.path.exists(rj):
+        for name in ("roofline_r02.json", "roofline_r01.json"):
+            rj = os.path.join(ROOT, "profiles", name)
+            if not os.path.exists(rj):
+                continue
             try:
                 prof = json.load(open(rj))
                 traffic = prof.get("dram_bytes_per_step")
                 traffic = traffic * spl if traffic else None
                 issue = {k: prof[k] for k in ("sm_issue_utilisation", "warp_instructions_per_world_step", "icache_hit_rate",
                                               "gcc_instruction_request_rate_of_peak") if k in prof}
+                issue["source"] = "profiles/" + name + " (ncu capture, not measured live)"
+                break
             except Exception:
                 traffic = None
         line = {
@@ -455,22 +503,29 @@ def run_gpu_arm(args, cfg):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "desc": cfg["desc"], "worlds_per_gpu": nw, "n_spheres": n, "n_planes": 6,
                        "dt": float(scenes.MAX_DELTA_TIME), "steps_per_launch": spl, "parallelism": f"worlds-sharded x{world_size}",
+                       "collective": "8-double statistics all-reduce (NCCL, inside libphysics_gpu.so) once per launch, inside the timed CUDA-event pair",
                        "l2": "256 MiB flush between launches, outside the CUDA-event pairs"},
-            "roofline": {"bound": "hbm", "kernel": "k_step_spheres<8,16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "sm_issue", "kernel": "k_step_spheres<8,16>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes,
-                         "sm_issue": issue,     # from the ncu capture in profiles/ (not measured live)
-                         "note": "state lives in shared memory for the whole launch; the kernel is bound by SM issue "
-                                 "slots and instruction fetch, not by HBM (SURVEY.md section 8d), see profiles/k_step_spheres_r01.md"},
+                         "issue": issue,
+                         "note": "achieved/peak/frac are the LIVE HBM figures (algorithmic 52 B per body-step over the measured launch time); "
+                                 "they are a secondary reading: state lives in shared memory for the whole launch and the kernel is bound by SM "
+                                 "issue slots and instruction fetch (SURVEY.md section 8d), see profiles/k_step_spheres_r02.md"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "pg_worlds_step_host(dt, 1, pos, vel, at_rest): pinned host arrays in and out every step; 4 world chunks over separate upload, compute and download queues, replayed as one CUDA graph"},
+                    "steps": e2e_steps, "api": E2E_API_NOTE},
             "gpu_launches": int(gpu_launches),
             "wall_ms_per_step_incl_flush": wall / args.steps * 1e3,
             "launch_ms_per_step_min_max": [min(launch_ms), max(launch_ms)],
-            "stats": {"bodies": stats_host[0], "kinetic": stats_host[1], "at_rest": stats_host[6], "nonfinite": stats_host[7]},
+            "stats": {k: stats_sum[k] for k in ("bodies", "kinetic", "contacts", "at_rest", "nonfinite")},
             "state_checksum": checksum,
         }
+        if therm:
+            line["value_thermalised"] = therm["value"]
+            line["thermalised"] = therm
+        if strong:
+            line["strong"] = strong
         if world_size == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             threads = min(cores, 64)
@@ -482,6 +537,8 @@ def run_gpu_arm(args, cfg):
         print(json.dumps(line), flush=True)
 
     worlds.close()
+    if comm:
+        comm.close()
     if world_size > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -497,6 +554,9 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=10)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--thermalise-steps", type=int, default=1000,
+                    help="c3: after the timed region, pre-advance the batch this many steps (untimed) and time K steps again "
+                         "(value_thermalised); 0 to skip")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
     if args.steps is None:

@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
 ]
 EXTRA_INCLUDES: list[str] = []
-CU_SOURCES = ["physics_gpu.cu", "pg_general.cu", "pg_spheres.cu", "pg_large.cu"]
+CU_SOURCES = ["physics_gpu.cu", "pg_general.cu", "pg_spheres.cu", "pg_large.cu", "pg_comm.cu"]
 HOST_SOURCES = ["host/crux_world.c", "host/crux_colliders.c", "host/crux_scene.c"]
 HEADLESS = os.path.join(LIB, "crux_headless")
 
@@ -68,7 +68,7 @@ def build_gpu(force: bool = False, verbose: bool = False) -> str:
                     f.write(f"==== {os.path.basename(s)} ====\n" + r.stderr)
             logs.append(open(tu_log).read())
             objs.append(o)
-        r = subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", GPU_SO, *objs],
+        r = subprocess.run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", GPU_SO, *objs, "-ldl"],
                            capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -59,7 +59,9 @@ struct PgWorlds {
   cudaEvent_t ev0, ev1;
   long long launches;
   int last_steps;
-  double *d_stats;            // 8 doubles
+  double *d_stats;            // 8 doubles: aggregate statistics of this handle's bodies (sphere mode: written by the step launch's epilogue)
+  double *d_stats_sum;        // 8 doubles: the same summed over all ranks of a communicator (pg_worlds_stats_allreduce)
+  bool stats_valid;           // d_stats describes the current state
   int *d_work_counter;        // world hand-out counter of the sphere kernel
   unsigned *d_cost;           // sphere kernel: clocks/1024 each world took in the last full launch
   int *d_order;               // sphere kernel: worlds sorted by that cost, dearest first (hand-out order)
@@ -88,9 +90,9 @@ struct PgWorlds {
 int pg_launch_general_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes);
 // pg_spheres.cu
 int pg_launch_sphere_step(PgWorlds *w, float dt, int n_steps);
-int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter);
+int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter, double *stats);
 int pg_launch_pack_state_on(PgWorlds *w, cudaStream_t st, int first, int count, int n, const float *pos, const float *vel, const unsigned char *rest);
 int pg_launch_unpack_state_on(PgWorlds *w, cudaStream_t st, int first, int count, int n, float *pos, float *vel, unsigned char *rest);
-int pg_launch_worlds_stats(PgWorlds *w, void *dev_out8);
+int pg_launch_worlds_stats(PgWorlds *w);
 int pg_launch_pack_state(PgWorlds *w, int first, int count, int n, const float *pos, const float *vel, const unsigned char *rest);
 int pg_launch_unpack_state(PgWorlds *w, int first, int count, int n, float *pos, float *vel, unsigned char *rest);

@@ -121,7 +121,7 @@ constexpr int kGateList = 128;        // candidate bits of one 32-row block gate
 // from shared memory, which holds the TRUE current state (rows < i integrated).  Columns changed by
 // a contact are appended to chg[]; returns their number (> kMaxRowChanges: list overflowed).
 __device__ __noinline__ int row_visits(float4 *P4, float4 *V4, int i, unsigned mask, bool fresh, int lane, int ncols_slots,
-                                       float dt, const WorldsView &v, int w, int step, bool record, int *chg) {
+                                       float dt, const WorldsView &v, int w, int step, bool record, int *chg, int *contacts) {
   __syncwarp();
   pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
   int n_chg = 0;
@@ -157,6 +157,7 @@ __device__ __noinline__ int row_visits(float4 *P4, float4 *V4, int i, unsigned m
         P4[i] = make_float4(A.px, A.py, A.pz, reach(A.r, A.vx, A.vy, A.vz, dt)); V4[i] = make_float4(A.vx, A.vy, A.vz, A.r);
         P4[j] = make_float4(B.px, B.py, B.pz, reach(B.r, B.vx, B.vy, B.vz, dt)); V4[j] = make_float4(B.vx, B.vy, B.vz, B.r);
         if (record) emit_event(v, w, step, 4, PG_CLASS_DYNAMIC, i, PG_CLASS_DYNAMIC, j);
+        *contacts += 1;
         if (n_chg < kMaxRowChanges) chg[n_chg] = j;
       }
       n_chg++;
@@ -201,12 +202,13 @@ struct WarpSmem {
   unsigned rest[CPT];                       // at-rest flags by actual slot, bit = lane
   int chg[kMaxRowChanges];
   int n_list;                                      // gate list allocation counter (zero between uses)
+  int contacts;                                    // contacts (events) of this world in this launch, for the statistics
 };
 
 template <int CPT, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
 k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int first_world, int end_world,
-               const int *order, unsigned *cost) {
+               const int *order, unsigned *cost, double *stats) {
   // per-warp shared memory (dynamic: a block of 16 worlds needs more than the 48 KB static limit)
   extern __shared__ __align__(16) unsigned char s_raw[];
   WarpSmem<CPT> &S = reinterpret_cast<WarpSmem<CPT> *>(s_raw)[threadIdx.x >> 5];
@@ -216,6 +218,26 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
   // Worlds are handed out through an atomic counter: the grid holds exactly the warps that fit on
   // the GPU, each warp keeps pulling worlds until none are left, so there is no partial last wave.
   __shared__ int s_base;
+  // Aggregate statistics (PgStats: the 8 doubles a multi-GPU run all-reduces) are taken in the launch's
+  // epilogue, while a world's final state is still in shared memory: lane q < 8 of every warp carries
+  // statistic q summed over the worlds the warp has stepped; when the block runs out of worlds its warps
+  // add up in shared memory and 8 atomics per block reach the device vector.  No separate pass over HBM.
+  __shared__ double s_stats[MAXW][8];
+  double stat_acc = 0.0;
+  auto flush_stats = [&]() {                        // on the way out (PG_SPH_SYNC > 0: all threads of the block together)
+    if (!stats) return;
+    if constexpr (PG_SPH_SYNC > 0) {
+      if (lane < 8) s_stats[wib][lane] = stat_acc;
+      __syncthreads();
+      if (threadIdx.x < 8) {
+        double x = 0.0;
+        for (int q = 0; q < (int)(blockDim.x >> 5); q++) x += s_stats[q][threadIdx.x];
+        if (x != 0.0) atomicAdd(stats + threadIdx.x, x);
+      }
+    } else {
+      if (lane < 8 && stat_acc != 0.0) atomicAdd(stats + lane, stat_acc);
+    }
+  };
   for (;;) {
   int w = 0;
   bool valid = true;
@@ -225,14 +247,14 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
     __syncthreads();
     if (threadIdx.x == 0) s_base = first_world + atomicAdd(work_counter, (int)(blockDim.x >> 5));
     __syncthreads();
-    if (s_base >= end_world) return;
+    if (s_base >= end_world) { flush_stats(); return; }
     w = s_base + wib;
     valid = w < end_world;
     if (!valid) w = end_world - 1;
   } else {
     if (lane == 0) w = first_world + atomicAdd(work_counter, 1);
     w = __shfl_sync(kFull, w, 0);
-    if (w >= end_world) return;
+    if (w >= end_world) { flush_stats(); return; }
   }
   if (order) w = order[w];                 // dearest worlds first (see k_order_worlds)
   const long long t_start = clock64();
@@ -248,7 +270,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
   pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
 
   if (lane < ns) S.planes[lane] = v.planes[(size_t)w * v.cap[0] + lane];
-  if (lane == 0) S.n_list = 0;
+  if (lane == 0) { S.n_list = 0; S.contacts = 0; }
 
   unsigned rest = 0;                       // bit s: this lane's body of actual slot s is at rest
   const size_t base = (size_t)w * v.cap[1];
@@ -308,6 +330,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
             if (plane_slow_path(P4, V4, i, S.planes[k], restitution, dt, gate_ok, &came_to_rest, leaf)) {
               if (came_to_rest) rest |= 1u << s;
               if (record) emit_event(v, w, step, 3, PG_CLASS_DYNAMIC, i, PG_CLASS_STATIC, k);
+              atomicAdd(&S.contacts, 1);
               const float4 a = P4[i];
 #pragma unroll 1
               for (int k2 = k + 1; k2 < g_end; k2++) {
@@ -512,7 +535,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
         for (int k = 0; k < CPT; k++) mask |= ((WS[k * 32 + lane] >> rl) & 1u) << k;
         // static slot k is actual slot (rb + k) mod CPT: rotate the bits into column order
         const unsigned amask = ((mask << rb) | (mask >> ((CPT - rb) & 31))) & full;
-        const int n_chg = row_visits(P4, V4, i, rb == 0 ? mask : amask, !gated || ((dirty_rows >> rl) & 1u), lane, CPT, dt, v, w, step, record, S.chg);
+        const int n_chg = row_visits(P4, V4, i, rb == 0 ? mask : amask, !gated || ((dirty_rows >> rl) & 1u), lane, CPT, dt, v, w, step, record, S.chg, &S.contacts);
         const unsigned later = 0xfffffffeu << rl;  // rows after rl
         if (n_chg) {
           if (n_chg > kMaxRowChanges) {
@@ -553,38 +576,37 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
     }
   }
   if (cost && valid && lane == 0) cost[w] = (unsigned)min((clock64() - t_start) >> 10, 0x7fffffffll);
+  if (stats && valid) {
+    double a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 1
+    for (int s = 0; s < n_blocks; s++) {
+      const int i = s * 32 + lane;
+      if (i < n) {
+        const float4 p = P4[i], b = V4[i];
+        a[0] += 1.0;
+        a[1] += 0.5 * ((double)b.x * b.x + (double)b.y * b.y + (double)b.z * b.z);
+        a[2] += b.x; a[3] += b.y; a[4] += b.z;
+        a[6] += ((rest >> s) & 1u) ? 1.0 : 0.0;
+        const bool fin = isfinite(p.x) && isfinite(p.y) && isfinite(p.z) && isfinite(b.x) && isfinite(b.y) && isfinite(b.z);
+        a[7] += fin ? 0.0 : 1.0;
+      }
+    }
+    if (lane == 0) a[5] = (double)S.contacts;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      double x = a[q];
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+      if (lane == q) stat_acc += x;
+    }
+  }
   __syncwarp();
   }   // next world
 }
 
-// ---------------------------------------------------------------- aggregate statistics
-// One pass over the hot state; block partials -> 8 double atomics.  The same 8 doubles are what a
-// multi-GPU run all-reduces (SUM), so the kernel can write straight into the caller's buffer.
-__global__ void k_stats_spheres(WorldsView v, double *out, double *out2) {
-  double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const long long total = (long long)v.n_worlds * v.cap[1];
-  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-    const int w = (int)(k / v.cap[1]), i = (int)(k % v.cap[1]);
-    if (i >= v.counts[w * 3 + 1]) continue;
-    const float4 a = v.pos_rest[k], b = v.vel_rad[k];
-    acc[0] += 1.0;
-    acc[1] += 0.5 * ((double)b.x * b.x + (double)b.y * b.y + (double)b.z * b.z);
-    acc[2] += b.x; acc[3] += b.y; acc[4] += b.z;
-    acc[6] += a.w != 0.0f ? 1.0 : 0.0;
-    const bool fin = isfinite(a.x) && isfinite(a.y) && isfinite(a.z) && isfinite(b.x) && isfinite(b.y) && isfinite(b.z);
-    acc[7] += fin ? 0.0 : 1.0;
-  }
-  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < v.n_worlds; w += (long long)gridDim.x * blockDim.x)
-    acc[5] += (double)v.n_events[w];
-#pragma unroll
-  for (int q = 0; q < 8; q++) {
-    double x = acc[q];
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
-    if ((threadIdx.x & 31) == 0 && x != 0.0) { atomicAdd(out + q, x); if (out2) atomicAdd(out2 + q, x); }
-  }
-}
-
-__global__ void k_stats_general(WorldsView v, double *out, double *out2) {
+// ---------------------------------------------------------------- aggregate statistics (any-collider worlds)
+// Sphere batches take their statistics in k_step_spheres' epilogue; game-sized general worlds use this
+// one pass over the records: block partials -> 8 double atomics.
+__global__ void k_stats_general(WorldsView v, double *out) {
   double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long total = (long long)v.n_worlds * v.cap[1];
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
@@ -605,7 +627,7 @@ __global__ void k_stats_general(WorldsView v, double *out, double *out2) {
   for (int q = 0; q < 8; q++) {
     double x = acc[q];
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
-    if ((threadIdx.x & 31) == 0 && x != 0.0) { atomicAdd(out + q, x); if (out2) atomicAdd(out2 + q, x); }
+    if ((threadIdx.x & 31) == 0 && x != 0.0) atomicAdd(out + q, x);
   }
 }
 
@@ -681,7 +703,7 @@ __global__ void k_order_worlds(const unsigned *cost, int n_worlds, int *order) {
 }
 
 template <int CPT, int MAXW>
-static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter) {
+static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter, double *stats) {
   static bool configured[64] = {false};      // function attributes are per device
   constexpr size_t warp_bytes = sizeof(WarpSmem<CPT>);
   const int dev = w->device >= 0 && w->device < 64 ? w->device : 0;
@@ -708,36 +730,44 @@ static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int cou
   }
   cudaMemsetAsync(counter, 0, sizeof(int), stream);
   k_step_spheres<CPT, MAXW><<<blocks, wpb * 32, warp_bytes * wpb, stream>>>(w->v, dt, n_steps, counter, first, first + count, order,
-                                                                    whole ? w->d_cost : nullptr);
-  w->cost_valid = whole;
+                                                                    (whole && n_steps > 0) ? w->d_cost : nullptr, stats);
+  if (n_steps > 0) w->cost_valid = whole;
   return PG_OK;
 }
 
 // Step worlds [first, first+count) on `stream` (the whole batch on the handle's stream by default).
-int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter) {
+int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter, double *stats) {
   const int cap = w->v.cap[1];
   if (w->v.cap[0] > kMaxPlanes) { pg_set_error("sphere mode supports at most %d static planes", kMaxPlanes); return PG_ERR_CAPACITY; }
-  if (cap <= 32) launch_spheres<1, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter);
-  else if (cap <= 64) launch_spheres<2, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter);
-  else if (cap <= 128) launch_spheres<4, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter);
-  else if (cap <= 256) launch_spheres<8, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter);
-  else if (cap <= 512) launch_spheres<16, 8>(w, dt, n_steps, first, count, stream, counter);
+  if (cap <= 32) launch_spheres<1, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter, stats);
+  else if (cap <= 64) launch_spheres<2, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter, stats);
+  else if (cap <= 128) launch_spheres<4, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter, stats);
+  else if (cap <= 256) launch_spheres<8, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter, stats);
+  else if (cap <= 512) launch_spheres<16, 8>(w, dt, n_steps, first, count, stream, counter, stats);
   else { pg_set_error("sphere mode supports at most 512 spheres per world (got capacity %d)", cap); return PG_ERR_CAPACITY; }
   PG_CUDA(cudaGetLastError());
   if (count > 0) w->launches++;
   return PG_OK;
 }
 
+// The whole batch on the handle's stream; the launch's epilogue leaves the aggregate statistics in d_stats.
+// n_steps == 0 is the statistics-only pass (state in, state out unchanged) for a state that was uploaded,
+// not stepped.
 int pg_launch_sphere_step(PgWorlds *w, float dt, int n_steps) {
-  return pg_launch_sphere_range(w, dt, n_steps, 0, w->v.n_worlds, w->stream, w->d_work_counter);
+  PG_CUDA(cudaMemsetAsync(w->d_stats, 0, 8 * sizeof(double), w->stream));
+  int rc = pg_launch_sphere_range(w, dt, n_steps, 0, w->v.n_worlds, w->stream, w->d_work_counter, w->d_stats);
+  w->stats_valid = rc == PG_OK;
+  return rc;
 }
 
-int pg_launch_worlds_stats(PgWorlds *w, void *dev_out8) {
+// Make d_stats describe the current state (on the handle's stream, no host sync).
+int pg_launch_worlds_stats(PgWorlds *w) {
+  if (w->mode == PG_MODE_SPHERES) {
+    if (w->stats_valid) return PG_OK;              // the last step launch's epilogue already did it
+    return pg_launch_sphere_step(w, 0.0f, 0);
+  }
   PG_CUDA(cudaMemsetAsync(w->d_stats, 0, 8 * sizeof(double), w->stream));
-  if (dev_out8) PG_CUDA(cudaMemsetAsync(dev_out8, 0, 8 * sizeof(double), w->stream));
-  const int blocks = w->sm_count * 4;
-  if (w->mode == PG_MODE_SPHERES) k_stats_spheres<<<blocks, 256, 0, w->stream>>>(w->v, w->d_stats, (double *)dev_out8);
-  else k_stats_general<<<blocks, 256, 0, w->stream>>>(w->v, w->d_stats, (double *)dev_out8);
+  k_stats_general<<<w->sm_count * 4, 256, 0, w->stream>>>(w->v, w->d_stats);
   PG_CUDA(cudaGetLastError());
   w->launches++;
   return PG_OK;

@@ -170,6 +170,9 @@ PgWorlds *pg_worlds_create(int n_worlds, int max_static, int max_dynamic, int ma
   if (max_events_per_world > 0)
     PG_CUDA_NULL(cudaMalloc(&w->v.events, sizeof(PgEvent) * (size_t)n_worlds * max_events_per_world));
   PG_CUDA_NULL(cudaMalloc(&w->d_stats, 8 * sizeof(double)));
+  PG_CUDA_NULL(cudaMalloc(&w->d_stats_sum, 8 * sizeof(double)));
+  PG_CUDA_NULL(cudaMemset(w->d_stats, 0, 8 * sizeof(double)));
+  PG_CUDA_NULL(cudaMemset(w->d_stats_sum, 0, 8 * sizeof(double)));
   PG_CUDA_NULL(cudaMalloc(&w->d_work_counter, sizeof(int)));
   PG_CUDA_NULL(cudaMalloc(&w->d_cost, sizeof(unsigned) * (size_t)n_worlds));
   PG_CUDA_NULL(cudaMalloc(&w->d_order, sizeof(int) * (size_t)n_worlds));
@@ -190,6 +193,7 @@ void pg_worlds_destroy(PgWorlds *w) {
   if (w->v.vel_rad) cudaFree(w->v.vel_rad);
   if (w->v.planes) cudaFree(w->v.planes);
   if (w->d_stats) cudaFree(w->d_stats);
+  if (w->d_stats_sum) cudaFree(w->d_stats_sum);
   if (w->d_work_counter) cudaFree(w->d_work_counter);
   if (w->d_cost) cudaFree(w->d_cost);
   if (w->d_order) cudaFree(w->d_order);
@@ -326,6 +330,7 @@ int pg_worlds_set_spheres(PgWorlds *w, int first, int count, const PgBody *stati
     PG_CUDA(cudaMemset(w->v.vel_rad, 0, sizeof(float4) * nd_all));
   }
   w->mode = PG_MODE_SPHERES;
+  w->stats_valid = false;
   w->v.restitution = restitution;
   if (w->pipe_graph) { cudaGraphExecDestroy(w->pipe_graph); w->pipe_graph = nullptr; }   // the captured kernels carry the old view by value
   std::vector<float4> hp((size_t)count * w->v.cap[1]), hv((size_t)count * w->v.cap[1]), pl((size_t)count * w->v.cap[0]);
@@ -418,6 +423,7 @@ int pg_worlds_upload_state(PgWorlds *w, int first, int count, const float *pos, 
     const size_t total = (size_t)count * n;
     rc = ensure_stage(w, total);
     if (rc) return rc;
+    w->stats_valid = false;
     // one H2D copy per array (async when the caller's buffers are pinned), then a pack kernel
     PG_CUDA(cudaMemcpyAsync(w->d_stage_pos, pos, sizeof(float) * 3 * total, cudaMemcpyHostToDevice, w->stream));
     PG_CUDA(cudaMemcpyAsync(w->d_stage_vel, vel, sizeof(float) * 3 * total, cudaMemcpyHostToDevice, w->stream));
@@ -545,13 +551,14 @@ int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *v
     w->launches += w->pipe_graph_kernels;
     w->last_steps = n_steps;
     w->cost_valid = false;
+    w->stats_valid = n_steps > 0;
     PG_CUDA(cudaStreamSynchronize(w->stream));
     return PG_OK;
   }
   if (w->pipe_graph) { cudaGraphExecDestroy(w->pipe_graph); w->pipe_graph = nullptr; }
   const long long launches_before = w->launches;
   if (use_graph) {
-    rc = pg_launch_sphere_range(w, dt, 0, 0, 0, w->stream, w->d_work_counter);      // kernel attributes are not capturable
+    rc = pg_launch_sphere_range(w, dt, 0, 0, 0, w->stream, w->d_work_counter, nullptr);      // kernel attributes are not capturable
     if (rc) return rc;
     PG_CUDA(cudaStreamSynchronize(w->stream));
     PG_CUDA(cudaEventRecord(w->ev0, w->stream));
@@ -560,6 +567,7 @@ int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *v
     PG_CUDA(cudaEventRecord(w->ev0, w->stream));
   }
   PG_CUDA(cudaMemsetAsync(w->v.n_events, 0, sizeof(int) * (size_t)nw, w->stream));
+  PG_CUDA(cudaMemsetAsync(w->d_stats, 0, 8 * sizeof(double), w->stream));      // every chunk's launch adds its partials
   PG_CUDA(cudaEventRecord(w->pipe_fork, w->stream));
   for (int k = 0; k < 3; k++) PG_CUDA(cudaStreamWaitEvent(w->pipe_stream[k], w->pipe_fork, 0));
   // Chunks shrink towards the end (weights kChunks, kChunks-1, ..., 1): what cannot overlap is the last
@@ -593,7 +601,7 @@ int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *v
     PG_CUDA(cudaStreamWaitEvent(st, w->pipe_up_ev[c], 0));
     rc = pg_launch_pack_state_on(w, st, first, count, n, w->d_stage_pos + 3 * off, w->d_stage_vel + 3 * off, at_rest ? w->d_stage_rest + off : nullptr);
     if (rc) return rc;
-    if (n_steps > 0) { rc = pg_launch_sphere_range(w, dt, n_steps, first, count, st, w->d_pipe_counters + c); if (rc) return rc; }
+    if (n_steps > 0) { rc = pg_launch_sphere_range(w, dt, n_steps, first, count, st, w->d_pipe_counters + c, w->d_stats); if (rc) return rc; }
     rc = pg_launch_unpack_state_on(w, st, first, count, n, w->d_stage_pos + 3 * off, w->d_stage_vel + 3 * off, at_rest ? w->d_stage_rest + off : nullptr);
     if (rc) return rc;
     PG_CUDA(cudaEventRecord(w->pipe_k_ev[c], st));
@@ -623,6 +631,7 @@ int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *v
   }
   PG_CUDA(cudaEventRecord(w->ev1, w->stream));
   w->last_steps = n_steps;
+  w->stats_valid = n_steps > 0;
   PG_CUDA(cudaStreamSynchronize(w->stream));
   return PG_OK;
 }
@@ -680,8 +689,9 @@ int pg_worlds_stats(PgWorlds *w, PgStats *host_out, void *dev_out8) {
   if (!w) return PG_ERR_ARG;
   PG_CUDA(cudaSetDevice(w->device));
   if (w->mode == PG_MODE_GENERAL) { int rc = ensure_records(w); if (rc) return rc; }
-  int rc = pg_launch_worlds_stats(w, dev_out8);
+  int rc = pg_launch_worlds_stats(w);
   if (rc) return rc;
+  if (dev_out8) PG_CUDA(cudaMemcpyAsync(dev_out8, w->d_stats, 8 * sizeof(double), cudaMemcpyDeviceToDevice, w->stream));
   if (host_out) {
     double h[8];
     PG_CUDA(cudaMemcpyAsync(h, w->d_stats, sizeof(h), cudaMemcpyDeviceToHost, w->stream));

@@ -45,6 +45,13 @@ API = [
     ("pg_worlds_step_host", _i, [_vp, _f, _i, _vp, _vp, _vp]),
     ("pg_worlds_events", _ll, [_vp, _vp, _ll, _vp]),
     ("pg_worlds_stats", _i, [_vp, _vp, _vp]),
+    ("pg_comm_unique_id", _i, [_vp]),
+    ("pg_comm_init", _vp, [_vp, _i, _i, _i]),
+    ("pg_comm_destroy", None, [_vp]),
+    ("pg_comm_rank", _i, [_vp]),
+    ("pg_comm_size", _i, [_vp]),
+    ("pg_comm_nccl_version", _i, []),
+    ("pg_worlds_stats_allreduce", _i, [_vp, _vp, _vp, _vp]),
     ("pg_worlds_launches", _ll, [_vp]),
     ("pg_worlds_last_step_ms", _f, [_vp]),
     ("pg_worlds_stream", _vp, [_vp]),
@@ -175,6 +182,41 @@ class PinnedArray:
             self.ptr = None
 
 
+class Comm:
+    """An NCCL communicator owned by the library (PgComm): one per process/GPU."""
+
+    def __init__(self, unique_id: bytes, rank: int, n_ranks: int, device: int):
+        if len(unique_id) != 128:
+            raise PgError("Comm: the NCCL unique id is 128 bytes")
+        self.L = lib()
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self.h = self.L.pg_comm_init(buf, rank, n_ranks, device)
+        if not self.h:
+            raise PgError("pg_comm_init failed: " + self.L.pg_last_error().decode())
+        self.rank, self.n_ranks = rank, n_ranks
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(lib().pg_comm_unique_id(buf), "pg_comm_unique_id")
+        return buf.raw
+
+    @staticmethod
+    def from_torch_distributed(device: int) -> "Comm":
+        """Rank 0 makes the id, torch.distributed (any backend) carries the 128 bytes to the others."""
+        import torch
+        import torch.distributed as dist
+        rank, n = dist.get_rank(), dist.get_world_size()
+        box = [Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return Comm(box[0], rank, n, device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pg_comm_destroy(self.h)
+            self.h = None
+
+
 class GpuWorlds:
     """A batch of physics worlds resident on one GPU (PgWorlds handle)."""
 
@@ -276,6 +318,13 @@ class GpuWorlds:
         h = np.zeros(8, np.float64) if want_host else None
         _check(self.L.pg_worlds_stats(self.h, _ptr(h), C.c_void_p(dev_out_ptr) if dev_out_ptr else None),
                "pg_worlds_stats")
+        return dict(zip(PG_STATS_FIELDS, h.tolist())) if want_host else None
+
+    def stats_allreduce(self, comm: "Comm | None" = None, dev_out_ptr: int | None = None, want_host: bool = False) -> dict | None:
+        """Statistics summed over every rank of `comm`, enqueued on the handle's stream (a collective)."""
+        h = np.zeros(8, np.float64) if want_host else None
+        _check(self.L.pg_worlds_stats_allreduce(self.h, comm.h if comm else None, _ptr(h),
+                                                C.c_void_p(dev_out_ptr) if dev_out_ptr else None), "pg_worlds_stats_allreduce")
         return dict(zip(PG_STATS_FIELDS, h.tolist())) if want_host else None
 
     @property

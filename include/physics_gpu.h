@@ -166,10 +166,31 @@ int  pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *
  * number produced (may exceed cap; a world that overflowed max_events_per_world is reported
  * through *overflowed). */
 long long pg_worlds_events(PgWorlds *w, PgEvent *out, long long cap, int *overflowed);
-/* Aggregate statistics.  If dev_out8 != NULL the 8 doubles are ALSO written (by the reducing
- * kernel, on the handle's stream) to that device address -- the buffer a caller hands to
- * ncclAllReduce / torch.distributed.all_reduce; host_out may be NULL to stay asynchronous. */
+/* Aggregate statistics of THIS handle's bodies.  Sphere batches: the step launch itself leaves them behind
+ * (its epilogue reduces them while the final state is still in shared memory), so this call only copies 8
+ * doubles; for a state that was uploaded and not stepped it runs the same kernel with zero steps.  `contacts`
+ * counts the events of the last step call (0 if the state was replaced since).  If dev_out8 != NULL the 8
+ * doubles are ALSO copied to that device address on the handle's stream; host_out may be NULL to stay
+ * asynchronous. */
 int  pg_worlds_stats(PgWorlds *w, PgStats *host_out, void *dev_out8);
+
+/* ---- multi-GPU: worlds shard across GPUs as independent units (no body data ever crosses GPUs); the only
+ * exchange of the path is the SUM all-reduce of the PgStats vector, done HERE over NCCL (NVLink / NVSwitch).
+ * One process (or thread) per GPU:  rank 0 calls pg_comm_unique_id and hands the 128 bytes to the other ranks by
+ * any means (file, pipe, MPI, torch.distributed broadcast); every rank then calls pg_comm_init.  NCCL is bound
+ * at run time (libnccl.so.2); without it these calls return PG_ERR_UNSUPPORTED / NULL and pg_last_error says so. */
+typedef struct PgComm PgComm;
+int  pg_comm_unique_id(void *out128);
+PgComm *pg_comm_init(const void *unique_id128, int rank, int n_ranks, int device);
+void pg_comm_destroy(PgComm *c);
+int  pg_comm_rank(const PgComm *c);
+int  pg_comm_size(const PgComm *c);
+int  pg_comm_nccl_version(void);      /* e.g. 22809; 0 if NCCL is not available */
+/* Statistics summed over ALL ranks of `comm` (NULL: this GPU alone).  Enqueued on the handle's stream behind the
+ * step launch that produced the partials -- no host synchronisation unless host_out != NULL -- and the end mark
+ * of the step's CUDA-event pair moves behind the collective: pg_worlds_last_step_ms then covers launch +
+ * all-reduce.  Every rank of the communicator must make the call (it is a collective). */
+int  pg_worlds_stats_allreduce(PgWorlds *w, PgComm *comm, PgStats *host_out, void *dev_out8);
 /* Number of kernel launches this handle has issued (bench.py's gpu_launches) and the device
  * time, in ms, of the last pg_worlds_step call measured with CUDA events on the handle's stream. */
 long long pg_worlds_launches(const PgWorlds *w);

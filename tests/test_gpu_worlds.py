@@ -449,3 +449,57 @@ def test_undefined_pairs_never_fire_and_are_rejected_at_the_boundary(gpu_lib):
     d = w.get_bodies(0, scenes.CLASS_DYNAMIC)
     assert d["position"][0, 2] < -0.8 and d["velocity"][0, 0] == 0.0 and d["velocity"][0, 2] == -3.0
     w.close()
+
+
+def test_statistics_come_from_the_step_epilogue_and_the_library_allreduce(gpu_lib, oracle_lib):
+    """PgStats of a sphere batch are reduced in k_step_spheres' epilogue (no separate pass): compare them with
+    the same aggregates taken from the downloaded state, after a step launch, after a chunked host step and for
+    a state that was uploaded but not stepped (zero-step launch).  The library's own NCCL communicator (one
+    rank here; bench.py runs it over 2-8 GPUs) must return the same vector."""
+    from crux_b200 import shard
+    nw, n, L = 37, 200, 9.0
+    pos, vel = scenes.sphere_worlds(nw, n, L, first_world=900)
+    st = scenes.plane_bodies(scenes.box_planes(L))
+    w = gpu_lib.GpuWorlds(nw, len(st), n, 0, max_events_per_world=4096)
+    w.set_spheres(0, st, pos, vel)
+
+    def check(tag, contacts=None):
+        s = w.stats()
+        P = np.zeros((nw, n, 3), np.float32); V = np.zeros((nw, n, 3), np.float32); R = np.zeros((nw, n), np.uint8)
+        w.download_state(0, nw, P, V, R)
+        want = shard.stats_from_state(V, R)
+        got = np.array([s[k] for k in gpu_lib.PG_STATS_FIELDS])
+        assert got[0] == nw * n and got[7] == 0, tag
+        assert np.allclose(got[[1, 2, 3, 4, 6]], want[[1, 2, 3, 4, 6]], rtol=1e-12, atol=1e-9), (tag, got, want)
+        if contacts is not None:
+            assert got[5] == contacts, (tag, got[5], contacts)
+        return got
+
+    check("fresh upload (zero-step launch)", contacts=0)
+    w.step(DT, 40)
+    got = check("after a step launch", contacts=len(w.events()))
+    assert got[5] > 100
+    launches = w.launches
+    w.stats(); w.stats()
+    assert w.launches == launches, "statistics of a stepped batch must not launch anything"
+    s1 = w.stats_allreduce(None, want_host=True)
+    assert np.array_equal(np.array(list(s1.values())), got)
+    if gpu_lib.lib().pg_comm_nccl_version() > 0:
+        comm = gpu_lib.Comm(gpu_lib.Comm.unique_id(), 0, 1, 0)
+        s2 = w.stats_allreduce(comm, want_host=True)
+        assert np.array_equal(np.array(list(s2.values())), got)
+        assert w.last_step_ms() > 0.0
+        comm.close()
+    # chunked host pipeline: every chunk's launch adds its partials
+    P = gpu_lib.PinnedArray((nw, n, 3), np.float32); V = gpu_lib.PinnedArray((nw, n, 3), np.float32); R = gpu_lib.PinnedArray((nw, n), np.uint8)
+    w.download_state(0, nw, P.array, V.array, R.array)
+    w.step_host(DT, 3, P.array, V.array, R.array)
+    check("after step_host")
+    # replace the state without stepping: the statistics follow
+    V.array[:] = 0.0
+    w.upload_state(0, nw, P.array, V.array, R.array)
+    s = w.stats()
+    assert s["kinetic"] == 0.0 and s["bodies"] == nw * n
+    for a in (P, V, R):
+        a.free()
+    w.close()
