@@ -202,8 +202,9 @@ def run_reference_arm(args, cfg):
 # the CUDA path
 # ------------------------------------------------------------------------------------------------
 
-E2E_API_NOTE = ("pg_worlds_step_host(dt, 1, pos, vel, at_rest): pinned host arrays in and out every step; world chunks over separate "
-                "upload, compute and download queues, replayed as one CUDA graph")
+E2E_API_NOTE = ("pg_worlds_step_host_packed(dt, 1, state) [--e2e-layout split: pg_worlds_step_host(dt, 1, pos, vel, at_rest)]: pinned host "
+                "state in and out every step; 4 world chunks (small first and last), two DMA queues per direction, the step kernel reads and writes the staging "
+                "buffers itself, replayed as one CUDA graph")
 
 
 def _set_affinity(local_rank: int):
@@ -462,18 +463,33 @@ def run_gpu_arm(args, cfg):
     hp = gpu.PinnedArray((nw, n, 3), np.float32); hv = gpu.PinnedArray((nw, n, 3), np.float32)
     hr = gpu.PinnedArray((nw, n), np.uint8)
     worlds.download_state(0, nw, hp.array, hv.array, hr.array)
+    packed = args.e2e_layout == "packed"
+    if packed:
+        # one pinned buffer, one record per world (pos | vel | at_rest): a chunk of worlds is one DMA each way
+        rec = worlds.packed_dtype()
+        hs = gpu.PinnedArray((nw,), rec)
+        hs.array["pos"][:] = hp.array; hs.array["vel"][:] = hv.array; hs.array["at_rest"][:] = hr.array
+
+        def host_step():
+            worlds.step_host_packed(dt, 1, hs.array)
+    else:
+        def host_step():
+            worlds.step_host(dt, 1, hp.array, hv.array, hr.array)
     for _ in range(3):
-        worlds.step_host(dt, 1, hp.array, hv.array, hr.array)
+        host_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        worlds.step_host(dt, 1, hp.array, hv.array, hr.array)           # H2D + step + D2H, synchronous
+        host_step()                                                      # H2D + step + D2H, synchronous
     barrier()
     e2e_wall = max_over_ranks(time.perf_counter() - t0)
     e2e_value = bodies * world_size * e2e_steps / e2e_wall
-    h2d = bodies * (12 + 12 + 1)
-    d2h = bodies * (12 + 12 + 1)
-    checksum = float(np.abs(hp.array).sum())
+    bytes_per_body = (rec.itemsize / n) if packed else 25
+    h2d = int(bodies * bytes_per_body)
+    d2h = int(bodies * bytes_per_body)
+    checksum = float(np.abs(hs.array["pos"]).sum()) if packed else float(np.abs(hp.array).sum())
+    if packed:
+        hs.free()
     hp.free(); hv.free(); hr.free()
 
     if rank == 0:
@@ -554,6 +570,8 @@ def main():
     ap.add_argument("--steps-per-launch", type=int, default=10)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-layout", default="packed", choices=["packed", "split"],
+                    help="host layout of the end-to-end leg: one packed record per world, or three split arrays")
     ap.add_argument("--thermalise-steps", type=int, default=1000,
                     help="c3: after the timed region, pre-advance the batch this many steps (untimed) and time K steps again "
                          "(value_thermalised); 0 to skip")

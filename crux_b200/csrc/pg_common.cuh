@@ -31,6 +31,9 @@ void pg_leaf_lengths(float t0, float t1, float *lo, float *hi);
     }                                                                                         \
   } while (0)
 
+#define PG_PIPE_MAX_CHUNKS 16
+#define PG_PIPE_DMA 2
+
 enum PgMode { PG_MODE_GENERAL = 0, PG_MODE_SPHERES = 1 };
 
 // Device-side view of a batch of worlds (passed by value to kernels).
@@ -48,6 +51,16 @@ struct WorldsView {
   float4 *planes;             // [n_worlds * cap[0]]  nx, ny, nz, d    (statics are planes in sphere mode)
   float restitution;          // uniform in sphere mode
   float leaf_lo, leaf_hi;     // extreme leaf lengths of the interval walk for (0, clamp(dt)); set per step call
+};
+
+// Host-exchange staging of a sphere batch, as the step kernel itself reads and writes it (no separate pack /
+// unpack launches): body i of world w (absolute index) has its position at pos + w*stride + 12 i, its velocity
+// at vel + w*stride + 12 i and its at_rest byte at rest + w*rest_stride + i.  That covers both host layouts:
+// three split arrays ([world][body][3] floats, [world][body] bytes) and one packed record per world.
+struct StageView {
+  unsigned char *pos, *vel, *rest;     // device addresses (rest may be null)
+  size_t stride, rest_stride;
+  int load, store;                     // read the initial state from the stage / also write the final state to it
 };
 
 struct PgWorlds {
@@ -73,16 +86,19 @@ struct PgWorlds {
   unsigned char *d_stage_rest;
   size_t stage_bodies;
   // chunked host pipeline (pg_worlds_step_host)
-  cudaStream_t pipe_stream[3];    // compute: pack / step / unpack of chunk c on stream c % 3
-  cudaStream_t pipe_up, pipe_down;   // one queue per copy engine, so that a download never waits behind an upload
-  cudaEvent_t pipe_up_ev[8], pipe_k_ev[8], pipe_done[2], pipe_join[3], pipe_fork;
+  cudaStream_t pipe_stream[3];    // compute: the step kernel of chunk c on stream c % 3
+  cudaStream_t pipe_up[PG_PIPE_DMA], pipe_down[PG_PIPE_DMA];   // DMA queues per direction: a download never waits behind an upload,
+                                                               // and one copy's set-up hides behind another's transfer
+  cudaEvent_t pipe_up_ev[PG_PIPE_MAX_CHUNKS], pipe_k_ev[PG_PIPE_MAX_CHUNKS], pipe_done[2 * PG_PIPE_DMA], pipe_join[3], pipe_fork;
+  unsigned char *d_stage_packed;  // device staging for the packed host layout (pg_worlds_step_host_packed)
+  size_t stage_packed_bytes;
   int *d_pipe_counters;       // one hand-out counter per chunk
   bool pipe_ready;
   // the whole chunk pipeline as one CUDA graph, re-captured when the host buffers or the step change
   cudaGraphExec_t pipe_graph;
   const void *pipe_key_ptr[3];
   float pipe_key_dt;
-  int pipe_key_steps, pipe_key_chunks;
+  int pipe_key_steps, pipe_key_chunks, pipe_key_packed;
   long long pipe_graph_kernels;
 };
 
@@ -90,7 +106,8 @@ struct PgWorlds {
 int pg_launch_general_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes);
 // pg_spheres.cu
 int pg_launch_sphere_step(PgWorlds *w, float dt, int n_steps);
-int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter, double *stats);
+int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter, double *stats,
+                           const StageView *stage = nullptr);
 int pg_launch_pack_state_on(PgWorlds *w, cudaStream_t st, int first, int count, int n, const float *pos, const float *vel, const unsigned char *rest);
 int pg_launch_unpack_state_on(PgWorlds *w, cudaStream_t st, int first, int count, int n, float *pos, float *vel, unsigned char *rest);
 int pg_launch_worlds_stats(PgWorlds *w);

@@ -208,7 +208,7 @@ struct WarpSmem {
 template <int CPT, int MAXW>
 __global__ void __launch_bounds__(MAXW * 32, 1)
 k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int first_world, int end_world,
-               const int *order, unsigned *cost, double *stats) {
+               const int *order, unsigned *cost, double *stats, StageView stage) {
   // per-warp shared memory (dynamic: a block of 16 worlds needs more than the 48 KB static limit)
   extern __shared__ __align__(16) unsigned char s_raw[];
   WarpSmem<CPT> &S = reinterpret_cast<WarpSmem<CPT> *>(s_raw)[threadIdx.x >> 5];
@@ -279,7 +279,15 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
     const int i = s * 32 + lane;
     float4 a, b;
     if (i < n) {
-      a = v.pos_rest[base + i]; b = v.vel_rad[base + i];
+      if (stage.load) {
+        // the host's packed [body][3] floats straight from the staging buffer the upload landed in
+        const float *sp = reinterpret_cast<const float *>(stage.pos + (size_t)w * stage.stride) + 3 * i;
+        const float *sv = reinterpret_cast<const float *>(stage.vel + (size_t)w * stage.stride) + 3 * i;
+        a = make_float4(sp[0], sp[1], sp[2], (stage.rest && stage.rest[(size_t)w * stage.rest_stride + i]) ? 1.0f : 0.0f);
+        b = make_float4(sv[0], sv[1], sv[2], v.vel_rad[base + i].w);
+      } else {
+        a = v.pos_rest[base + i]; b = v.vel_rad[base + i];
+      }
       if (a.w != 0.0f) rest |= 1u << s;
       a.w = reach(b.w, b.x, b.y, b.z, dt);
     } else {
@@ -570,9 +578,16 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
   for (int s = 0; s < n_blocks; s++) {
     const int i = s * 32 + lane;
     if (i < n) {
-      const float4 a = P4[i];
+      const float4 a = P4[i], b = V4[i];
       v.pos_rest[base + i] = make_float4(a.x, a.y, a.z, ((rest >> s) & 1u) ? 1.0f : 0.0f);
-      v.vel_rad[base + i] = V4[i];
+      v.vel_rad[base + i] = b;
+      if (stage.store) {
+        float *sp = reinterpret_cast<float *>(stage.pos + (size_t)w * stage.stride) + 3 * i;
+        float *sv = reinterpret_cast<float *>(stage.vel + (size_t)w * stage.stride) + 3 * i;
+        sp[0] = a.x; sp[1] = a.y; sp[2] = a.z;
+        sv[0] = b.x; sv[1] = b.y; sv[2] = b.z;
+        if (stage.rest) stage.rest[(size_t)w * stage.rest_stride + i] = ((rest >> s) & 1u) ? 1 : 0;
+      }
     }
   }
   if (cost && valid && lane == 0) cost[w] = (unsigned)min((clock64() - t_start) >> 10, 0x7fffffffll);
@@ -703,7 +718,8 @@ __global__ void k_order_worlds(const unsigned *cost, int n_worlds, int *order) {
 }
 
 template <int CPT, int MAXW>
-static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter, double *stats) {
+static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter, double *stats,
+                          const StageView &stage) {
   static bool configured[64] = {false};      // function attributes are per device
   constexpr size_t warp_bytes = sizeof(WarpSmem<CPT>);
   const int dev = w->device >= 0 && w->device < 64 ? w->device : 0;
@@ -730,20 +746,24 @@ static int launch_spheres(PgWorlds *w, float dt, int n_steps, int first, int cou
   }
   cudaMemsetAsync(counter, 0, sizeof(int), stream);
   k_step_spheres<CPT, MAXW><<<blocks, wpb * 32, warp_bytes * wpb, stream>>>(w->v, dt, n_steps, counter, first, first + count, order,
-                                                                    (whole && n_steps > 0) ? w->d_cost : nullptr, stats);
+                                                                    (whole && n_steps > 0) ? w->d_cost : nullptr, stats, stage);
   if (n_steps > 0) w->cost_valid = whole;
   return PG_OK;
 }
 
 // Step worlds [first, first+count) on `stream` (the whole batch on the handle's stream by default).
-int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter, double *stats) {
+int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter, double *stats,
+                           const StageView *stage_or_null) {
   const int cap = w->v.cap[1];
+  StageView stage;
+  memset(&stage, 0, sizeof(stage));
+  if (stage_or_null) stage = *stage_or_null;
   if (w->v.cap[0] > kMaxPlanes) { pg_set_error("sphere mode supports at most %d static planes", kMaxPlanes); return PG_ERR_CAPACITY; }
-  if (cap <= 32) launch_spheres<1, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter, stats);
-  else if (cap <= 64) launch_spheres<2, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter, stats);
-  else if (cap <= 128) launch_spheres<4, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter, stats);
-  else if (cap <= 256) launch_spheres<8, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter, stats);
-  else if (cap <= 512) launch_spheres<16, 8>(w, dt, n_steps, first, count, stream, counter, stats);
+  if (cap <= 32) launch_spheres<1, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter, stats, stage);
+  else if (cap <= 64) launch_spheres<2, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter, stats, stage);
+  else if (cap <= 128) launch_spheres<4, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter, stats, stage);
+  else if (cap <= 256) launch_spheres<8, PG_SPH_WARPS>(w, dt, n_steps, first, count, stream, counter, stats, stage);
+  else if (cap <= 512) launch_spheres<16, 8>(w, dt, n_steps, first, count, stream, counter, stats, stage);
   else { pg_set_error("sphere mode supports at most 512 spheres per world (got capacity %d)", cap); return PG_ERR_CAPACITY; }
   PG_CUDA(cudaGetLastError());
   if (count > 0) w->launches++;

@@ -199,15 +199,16 @@ void pg_worlds_destroy(PgWorlds *w) {
   if (w->d_order) cudaFree(w->d_order);
   if (w->pipe_ready) {
     for (int k = 0; k < 3; k++) cudaStreamDestroy(w->pipe_stream[k]);
-    cudaStreamDestroy(w->pipe_up); cudaStreamDestroy(w->pipe_down);
-    for (int k = 0; k < 8; k++) { cudaEventDestroy(w->pipe_up_ev[k]); cudaEventDestroy(w->pipe_k_ev[k]); }
-    for (int k = 0; k < 2; k++) cudaEventDestroy(w->pipe_done[k]);
+    for (int k = 0; k < PG_PIPE_DMA; k++) { cudaStreamDestroy(w->pipe_up[k]); cudaStreamDestroy(w->pipe_down[k]); }
+    for (int k = 0; k < PG_PIPE_MAX_CHUNKS; k++) { cudaEventDestroy(w->pipe_up_ev[k]); cudaEventDestroy(w->pipe_k_ev[k]); }
+    for (int k = 0; k < 2 * PG_PIPE_DMA; k++) cudaEventDestroy(w->pipe_done[k]);
     for (int k = 0; k < 3; k++) cudaEventDestroy(w->pipe_join[k]);
     cudaEventDestroy(w->pipe_fork);
     if (w->pipe_graph) cudaGraphExecDestroy(w->pipe_graph);
     cudaFree(w->d_pipe_counters);
   }
   if (w->d_stage_pos) { cudaFree(w->d_stage_pos); cudaFree(w->d_stage_vel); cudaFree(w->d_stage_rest); }
+  if (w->d_stage_packed) cudaFree(w->d_stage_packed);
   cudaEventDestroy(w->ev0);
   cudaEventDestroy(w->ev1);
   cudaStreamDestroy(w->stream);
@@ -504,45 +505,69 @@ int pg_worlds_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes) {
   return rc;
 }
 
-// Host-to-host step: state in from `pos/vel/at_rest`, n_steps steps, state back out into the same
-// arrays.  The batch is cut into chunks of worlds that flow through three streams, so the H2D copy
-// of chunk c+1, the kernels of chunk c and the D2H copy of chunk c-1 overlap (PCIe is full duplex).
-int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *vel, uint8_t *at_rest) {
-  if (!w || n_steps < 0 || !pos || !vel) { pg_set_error("pg_worlds_step_host: bad argument"); return PG_ERR_ARG; }
-  if (w->mode != PG_MODE_SPHERES) { pg_set_error("pg_worlds_step_host: handle must be in sphere mode"); return PG_ERR_UNSUPPORTED; }
-  PG_CUDA(cudaSetDevice(w->device));
+// Host-to-host step: state in from the caller's (pinned) arrays, n_steps steps, state back out into the same
+// arrays.  The batch is cut into chunks of worlds; chunk c's upload, chunk c-1's kernel and chunk c-2's download
+// overlap (PCIe is full duplex).  The step kernel itself reads the staging buffer the upload landed in and writes
+// the one the download leaves from (StageView): no pack / unpack launches, one kernel per chunk.  Uploads and
+// downloads are spread over two queues per direction, so that the set-up latency of one DMA hides behind the
+// transfer of another.  The whole pipeline is captured once and replayed as one CUDA graph.
+struct HostState {
+  unsigned char *pos, *vel, *rest;     // host addresses (rest may be null; packed: vel/rest lie inside the record pos points to)
+  size_t stride, rest_stride;          // bytes per world
+  bool packed;                         // one contiguous record per world: a chunk is ONE copy each way
+};
+
+static int step_host_impl(PgWorlds *w, float dt, int n_steps, const HostState &h, int n) {
   const int nw = w->v.n_worlds;
-  int n = 0;
-  int rc = sphere_range_count(w, 0, nw, &n);
-  if (rc) return rc;
-  rc = ensure_stage(w, (size_t)nw * n);
-  if (rc) return rc;
-  static const int kChunksEnv = getenv("PG_HOST_CHUNKS") ? atoi(getenv("PG_HOST_CHUNKS")) : 4;   // measured: 2 -> 0.99, 4 -> 0.94, 8 -> 0.96 ms per 1 M-body step
-  const int kChunks = std::max(1, std::min(8, kChunksEnv));
+  static const int kChunksEnv = getenv("PG_HOST_CHUNKS") ? atoi(getenv("PG_HOST_CHUNKS")) : 4;      // measured (1 M bodies, packed): 4 -> 0.847, 6 -> 0.860, 8 -> 0.853, 16 -> 0.946 ms
+  static const int kDmaEnv = getenv("PG_HOST_DMA_QUEUES") ? atoi(getenv("PG_HOST_DMA_QUEUES")) : 2;
+  const int kChunks = std::max(1, std::min(PG_PIPE_MAX_CHUNKS, std::min(kChunksEnv, nw)));
+  const int kDma = std::max(1, std::min(PG_PIPE_DMA, kDmaEnv));
   if (!w->pipe_ready) {
     for (int k = 0; k < 3; k++) PG_CUDA(cudaStreamCreateWithFlags(&w->pipe_stream[k], cudaStreamNonBlocking));
-    PG_CUDA(cudaStreamCreateWithFlags(&w->pipe_up, cudaStreamNonBlocking));
-    PG_CUDA(cudaStreamCreateWithFlags(&w->pipe_down, cudaStreamNonBlocking));
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < PG_PIPE_DMA; k++) {
+      PG_CUDA(cudaStreamCreateWithFlags(&w->pipe_up[k], cudaStreamNonBlocking));
+      PG_CUDA(cudaStreamCreateWithFlags(&w->pipe_down[k], cudaStreamNonBlocking));
+      PG_CUDA(cudaEventCreateWithFlags(&w->pipe_done[2 * k], cudaEventDisableTiming));
+      PG_CUDA(cudaEventCreateWithFlags(&w->pipe_done[2 * k + 1], cudaEventDisableTiming));
+    }
+    for (int k = 0; k < PG_PIPE_MAX_CHUNKS; k++) {
       PG_CUDA(cudaEventCreateWithFlags(&w->pipe_up_ev[k], cudaEventDisableTiming));
       PG_CUDA(cudaEventCreateWithFlags(&w->pipe_k_ev[k], cudaEventDisableTiming));
     }
-    for (int k = 0; k < 2; k++) PG_CUDA(cudaEventCreateWithFlags(&w->pipe_done[k], cudaEventDisableTiming));
     for (int k = 0; k < 3; k++) PG_CUDA(cudaEventCreateWithFlags(&w->pipe_join[k], cudaEventDisableTiming));
     PG_CUDA(cudaEventCreateWithFlags(&w->pipe_fork, cudaEventDisableTiming));
-    PG_CUDA(cudaMalloc(&w->d_pipe_counters, sizeof(int) * 8));
+    PG_CUDA(cudaMalloc(&w->d_pipe_counters, sizeof(int) * PG_PIPE_MAX_CHUNKS));
     w->pipe_ready = true;
+  }
+  // device staging mirrors the host layout byte for byte
+  StageView sv;
+  memset(&sv, 0, sizeof(sv));
+  sv.stride = h.stride; sv.rest_stride = h.rest_stride; sv.load = 1; sv.store = 1;
+  if (h.packed) {
+    const size_t bytes = (size_t)nw * h.stride;
+    if (bytes > w->stage_packed_bytes) {
+      if (w->d_stage_packed) cudaFree(w->d_stage_packed);
+      w->d_stage_packed = nullptr; w->stage_packed_bytes = 0;
+      PG_CUDA(cudaMalloc(&w->d_stage_packed, bytes));
+      w->stage_packed_bytes = bytes;
+    }
+    sv.pos = w->d_stage_packed;
+    sv.vel = w->d_stage_packed + (h.vel - h.pos);
+    sv.rest = w->d_stage_packed + (h.rest - h.pos);
+  } else {
+    int rc = ensure_stage(w, (size_t)nw * n);
+    if (rc) return rc;
+    sv.pos = (unsigned char *)w->d_stage_pos; sv.vel = (unsigned char *)w->d_stage_vel;
+    sv.rest = h.rest ? w->d_stage_rest : nullptr;
   }
   {
     float cdt = dt;
     if ((double)cdt > 0.01666) cdt = (float)0.01666;
     pg_leaf_lengths(0.0f, cdt, &w->v.leaf_lo, &w->v.leaf_hi);
   }
-  // One graph launch per call instead of ~60 stream operations (the cost that remains is per-copy
-  // overhead on the GPU side: the copies alone take 0.80 ms against 0.55 ms of pure PCIe time; SMs
-  // reading and writing the pinned arrays directly -- tried -- are no faster than the copy engines).
-  const bool same = w->pipe_graph && w->pipe_key_ptr[0] == pos && w->pipe_key_ptr[1] == vel && w->pipe_key_ptr[2] == at_rest &&
-                    w->pipe_key_dt == dt && w->pipe_key_steps == n_steps && w->pipe_key_chunks == kChunks;
+  const bool same = w->pipe_graph && w->pipe_key_ptr[0] == h.pos && w->pipe_key_ptr[1] == h.vel && w->pipe_key_ptr[2] == h.rest &&
+                    w->pipe_key_dt == dt && w->pipe_key_steps == n_steps && w->pipe_key_chunks == kChunks && w->pipe_key_packed == (h.packed ? 1 : 0);
   static const bool use_graph = getenv("PG_HOST_NO_GRAPH") == nullptr;
   if (use_graph && same) {
     PG_CUDA(cudaEventRecord(w->ev0, w->stream));
@@ -551,12 +576,13 @@ int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *v
     w->launches += w->pipe_graph_kernels;
     w->last_steps = n_steps;
     w->cost_valid = false;
-    w->stats_valid = n_steps > 0;
+    w->stats_valid = true;
     PG_CUDA(cudaStreamSynchronize(w->stream));
     return PG_OK;
   }
   if (w->pipe_graph) { cudaGraphExecDestroy(w->pipe_graph); w->pipe_graph = nullptr; }
   const long long launches_before = w->launches;
+  int rc = PG_OK;
   if (use_graph) {
     rc = pg_launch_sphere_range(w, dt, 0, 0, 0, w->stream, w->d_work_counter, nullptr);      // kernel attributes are not capturable
     if (rc) return rc;
@@ -570,52 +596,56 @@ int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *v
   PG_CUDA(cudaMemsetAsync(w->d_stats, 0, 8 * sizeof(double), w->stream));      // every chunk's launch adds its partials
   PG_CUDA(cudaEventRecord(w->pipe_fork, w->stream));
   for (int k = 0; k < 3; k++) PG_CUDA(cudaStreamWaitEvent(w->pipe_stream[k], w->pipe_fork, 0));
-  // Chunks shrink towards the end (weights kChunks, kChunks-1, ..., 1): what cannot overlap is the last
-  // chunk's kernels and download, after the uploads are through
-  int chunk_first[9];
+  for (int k = 0; k < kDma; k++) {
+    PG_CUDA(cudaStreamWaitEvent(w->pipe_up[k], w->pipe_fork, 0));
+    PG_CUDA(cudaStreamWaitEvent(w->pipe_down[k], w->pipe_fork, 0));
+  }
+  // Chunk sizes: what cannot overlap is the first chunk's upload (nothing to download yet) and the last
+  // chunk's kernel + download (nothing left to upload), so both ends are small and the middle is large
+  // (weights 1, 2, 3, ... up to the middle and back down; PG_HOST_EVEN_CHUNKS for equal sizes).
+  int chunk_first[PG_PIPE_MAX_CHUNKS + 1];
   {
     static const bool even = getenv("PG_HOST_EVEN_CHUNKS") != nullptr;
-    const int wsum = kChunks * (kChunks + 1) / 2;
-    long long acc = 0;
-    for (int c = 0; c < kChunks; c++) {
-      chunk_first[c] = even ? (int)((long long)nw * c / kChunks) : (int)((long long)nw * acc / wsum);
-      acc += kChunks - c;
-    }
+    long long wsum = 0, acc = 0;
+    auto weight = [&](int c) { return even ? 2 : 1 + 2 * std::min(c, kChunks - 1 - c); };
+    for (int c = 0; c < kChunks; c++) wsum += weight(c);
+    for (int c = 0; c < kChunks; c++) { chunk_first[c] = (int)((long long)nw * acc / wsum); acc += weight(c); }
     chunk_first[kChunks] = nw;
   }
-  {
-  PG_CUDA(cudaStreamWaitEvent(w->pipe_up, w->pipe_fork, 0));
-  // Three queues: uploads (H2D engine), compute (pack / step / unpack, three streams round robin),
-  // downloads (D2H engine).  Chunk c's kernels wait for its upload, its download waits for its
-  // kernels; a download never sits behind an upload in the same stream, so both copy engines and
-  // the SMs run at the same time (PCIe is full duplex: 26 MB each way take 0.55 ms together).
   for (int c = 0; c < kChunks; c++) {
     const int first = chunk_first[c], count = chunk_first[c + 1] - first;
     if (count <= 0) continue;
-    cudaStream_t st = w->pipe_stream[c % 3];
-    const size_t off = (size_t)first * n, bodies = (size_t)count * n;
-    PG_CUDA(cudaMemcpyAsync(w->d_stage_pos + 3 * off, pos + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyHostToDevice, w->pipe_up));
-    PG_CUDA(cudaMemcpyAsync(w->d_stage_vel + 3 * off, vel + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyHostToDevice, w->pipe_up));
-    if (at_rest) PG_CUDA(cudaMemcpyAsync(w->d_stage_rest + off, at_rest + off, bodies, cudaMemcpyHostToDevice, w->pipe_up));
-    PG_CUDA(cudaEventRecord(w->pipe_up_ev[c], w->pipe_up));
+    cudaStream_t st = w->pipe_stream[c % 3], up = w->pipe_up[c % kDma], down = w->pipe_down[c % kDma];
+    const size_t off = (size_t)first * h.stride, bytes = (size_t)count * h.stride;
+    const size_t roff = (size_t)first * h.rest_stride, rbytes = (size_t)count * h.rest_stride;
+    if (h.packed) {
+      PG_CUDA(cudaMemcpyAsync(sv.pos + off, h.pos + off, bytes, cudaMemcpyHostToDevice, up));
+    } else {
+      PG_CUDA(cudaMemcpyAsync(sv.pos + off, h.pos + off, bytes, cudaMemcpyHostToDevice, up));
+      PG_CUDA(cudaMemcpyAsync(sv.vel + off, h.vel + off, bytes, cudaMemcpyHostToDevice, up));
+      if (h.rest) PG_CUDA(cudaMemcpyAsync(sv.rest + roff, h.rest + roff, rbytes, cudaMemcpyHostToDevice, up));
+    }
+    PG_CUDA(cudaEventRecord(w->pipe_up_ev[c], up));
     PG_CUDA(cudaStreamWaitEvent(st, w->pipe_up_ev[c], 0));
-    rc = pg_launch_pack_state_on(w, st, first, count, n, w->d_stage_pos + 3 * off, w->d_stage_vel + 3 * off, at_rest ? w->d_stage_rest + off : nullptr);
-    if (rc) return rc;
-    if (n_steps > 0) { rc = pg_launch_sphere_range(w, dt, n_steps, first, count, st, w->d_pipe_counters + c, w->d_stats); if (rc) return rc; }
-    rc = pg_launch_unpack_state_on(w, st, first, count, n, w->d_stage_pos + 3 * off, w->d_stage_vel + 3 * off, at_rest ? w->d_stage_rest + off : nullptr);
+    rc = pg_launch_sphere_range(w, dt, n_steps, first, count, st, w->d_pipe_counters + c, w->d_stats, &sv);
     if (rc) return rc;
     PG_CUDA(cudaEventRecord(w->pipe_k_ev[c], st));
-    PG_CUDA(cudaStreamWaitEvent(w->pipe_down, w->pipe_k_ev[c], 0));
-    PG_CUDA(cudaMemcpyAsync(pos + 3 * off, w->d_stage_pos + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyDeviceToHost, w->pipe_down));
-    PG_CUDA(cudaMemcpyAsync(vel + 3 * off, w->d_stage_vel + 3 * off, sizeof(float) * 3 * bodies, cudaMemcpyDeviceToHost, w->pipe_down));
-    if (at_rest) PG_CUDA(cudaMemcpyAsync(at_rest + off, w->d_stage_rest + off, bodies, cudaMemcpyDeviceToHost, w->pipe_down));
+    PG_CUDA(cudaStreamWaitEvent(down, w->pipe_k_ev[c], 0));
+    if (h.packed) {
+      PG_CUDA(cudaMemcpyAsync(h.pos + off, sv.pos + off, bytes, cudaMemcpyDeviceToHost, down));
+    } else {
+      PG_CUDA(cudaMemcpyAsync(h.pos + off, sv.pos + off, bytes, cudaMemcpyDeviceToHost, down));
+      PG_CUDA(cudaMemcpyAsync(h.vel + off, sv.vel + off, bytes, cudaMemcpyDeviceToHost, down));
+      if (h.rest) PG_CUDA(cudaMemcpyAsync(h.rest + roff, sv.rest + roff, rbytes, cudaMemcpyDeviceToHost, down));
+    }
   }
-  PG_CUDA(cudaEventRecord(w->pipe_done[0], w->pipe_down));
-  PG_CUDA(cudaStreamWaitEvent(w->stream, w->pipe_done[0], 0));
-  PG_CUDA(cudaEventRecord(w->pipe_done[1], w->pipe_up));
-  PG_CUDA(cudaStreamWaitEvent(w->stream, w->pipe_done[1], 0));
+  for (int k = 0; k < kDma; k++) {               // every forked queue joins
+    PG_CUDA(cudaEventRecord(w->pipe_done[2 * k], w->pipe_down[k]));
+    PG_CUDA(cudaStreamWaitEvent(w->stream, w->pipe_done[2 * k], 0));
+    PG_CUDA(cudaEventRecord(w->pipe_done[2 * k + 1], w->pipe_up[k]));
+    PG_CUDA(cudaStreamWaitEvent(w->stream, w->pipe_done[2 * k + 1], 0));
   }
-  for (int k = 0; k < 3; k++) {                  // every forked stream joins (chunks < 3 leave some idle)
+  for (int k = 0; k < 3; k++) {
     PG_CUDA(cudaEventRecord(w->pipe_join[k], w->pipe_stream[k]));
     PG_CUDA(cudaStreamWaitEvent(w->stream, w->pipe_join[k], 0));
   }
@@ -624,16 +654,49 @@ int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *v
     PG_CUDA(cudaStreamEndCapture(w->stream, &graph));
     PG_CUDA(cudaGraphInstantiate(&w->pipe_graph, graph, 0));
     cudaGraphDestroy(graph);
-    w->pipe_key_ptr[0] = pos; w->pipe_key_ptr[1] = vel; w->pipe_key_ptr[2] = at_rest;
-    w->pipe_key_dt = dt; w->pipe_key_steps = n_steps; w->pipe_key_chunks = kChunks;
+    w->pipe_key_ptr[0] = h.pos; w->pipe_key_ptr[1] = h.vel; w->pipe_key_ptr[2] = h.rest;
+    w->pipe_key_dt = dt; w->pipe_key_steps = n_steps; w->pipe_key_chunks = kChunks; w->pipe_key_packed = h.packed ? 1 : 0;
     w->pipe_graph_kernels = w->launches - launches_before;
     PG_CUDA(cudaGraphLaunch(w->pipe_graph, w->stream));
   }
   PG_CUDA(cudaEventRecord(w->ev1, w->stream));
   w->last_steps = n_steps;
-  w->stats_valid = n_steps > 0;
+  w->cost_valid = false;
+  w->stats_valid = true;
   PG_CUDA(cudaStreamSynchronize(w->stream));
   return PG_OK;
+}
+
+int pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *vel, uint8_t *at_rest) {
+  if (!w || n_steps < 0 || !pos || !vel) { pg_set_error("pg_worlds_step_host: bad argument"); return PG_ERR_ARG; }
+  if (w->mode != PG_MODE_SPHERES) { pg_set_error("pg_worlds_step_host: handle must be in sphere mode"); return PG_ERR_UNSUPPORTED; }
+  PG_CUDA(cudaSetDevice(w->device));
+  int n = 0;
+  int rc = sphere_range_count(w, 0, w->v.n_worlds, &n);
+  if (rc) return rc;
+  HostState h;
+  h.pos = (unsigned char *)pos; h.vel = (unsigned char *)vel; h.rest = at_rest;
+  h.stride = (size_t)n * 12; h.rest_stride = (size_t)n; h.packed = false;
+  return step_host_impl(w, dt, n_steps, h, n);
+}
+
+size_t pg_worlds_packed_world_bytes(const PgWorlds *w) {
+  if (!w || w->mode != PG_MODE_SPHERES) return 0;
+  const size_t n = (size_t)w->h_counts[1];
+  return (n * 25 + 15) & ~(size_t)15;
+}
+
+int pg_worlds_step_host_packed(PgWorlds *w, float dt, int n_steps, void *state) {
+  if (!w || n_steps < 0 || !state) { pg_set_error("pg_worlds_step_host_packed: bad argument"); return PG_ERR_ARG; }
+  if (w->mode != PG_MODE_SPHERES) { pg_set_error("pg_worlds_step_host_packed: handle must be in sphere mode"); return PG_ERR_UNSUPPORTED; }
+  PG_CUDA(cudaSetDevice(w->device));
+  int n = 0;
+  int rc = sphere_range_count(w, 0, w->v.n_worlds, &n);
+  if (rc) return rc;
+  HostState h;
+  h.pos = (unsigned char *)state; h.vel = h.pos + (size_t)n * 12; h.rest = h.pos + (size_t)n * 24;
+  h.stride = pg_worlds_packed_world_bytes(w); h.rest_stride = h.stride; h.packed = true;
+  return step_host_impl(w, dt, n_steps, h, n);
 }
 
 int pg_worlds_sync(PgWorlds *w) {

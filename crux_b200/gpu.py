@@ -43,6 +43,8 @@ API = [
     ("pg_worlds_step", _i, [_vp, _f, _i, _i]),
     ("pg_worlds_sync", _i, [_vp]),
     ("pg_worlds_step_host", _i, [_vp, _f, _i, _vp, _vp, _vp]),
+    ("pg_worlds_packed_world_bytes", C.c_size_t, [_vp]),
+    ("pg_worlds_step_host_packed", _i, [_vp, _f, _i, _vp]),
     ("pg_worlds_events", _ll, [_vp, _vp, _ll, _vp]),
     ("pg_worlds_stats", _i, [_vp, _vp, _vp]),
     ("pg_comm_unique_id", _i, [_vp]),
@@ -305,6 +307,21 @@ class GpuWorlds:
         self._state_args(0, self.n_worlds, pos, vel, at_rest, "step_host", True)
         _check(self.L.pg_worlds_step_host(self.h, np.float32(dt), n_steps, _ptr(pos), _ptr(vel), _ptr(at_rest)),
                "pg_worlds_step_host")
+
+    def packed_dtype(self) -> np.dtype:
+        """Record of one world in the packed host layout of step_host_packed (include/physics_gpu.h)."""
+        n = self._sphere_n
+        size = int(self.L.pg_worlds_packed_world_bytes(self.h))
+        return np.dtype({"names": ["pos", "vel", "at_rest"], "formats": [("<f4", (n, 3)), ("<f4", (n, 3)), ("u1", (n,))],
+                         "offsets": [0, 12 * n, 24 * n], "itemsize": size})
+
+    def step_host_packed(self, dt: float, n_steps: int, state: np.ndarray):
+        """`state`: C-contiguous array of n_worlds packed_dtype() records (ideally over pinned memory), stepped in place."""
+        dtp = self.packed_dtype()
+        if not isinstance(state, np.ndarray) or state.dtype != dtp or state.size != self.n_worlds or not state.flags["C_CONTIGUOUS"] \
+                or not state.flags["WRITEABLE"]:
+            raise PgError(f"step_host_packed: need a writable C-contiguous array of {self.n_worlds} packed_dtype() records")
+        _check(self.L.pg_worlds_step_host_packed(self.h, np.float32(dt), n_steps, _ptr(state)), "pg_worlds_step_host_packed")
 
     def events(self) -> np.ndarray:
         over = C.c_int(0)

@@ -162,6 +162,11 @@ int  pg_worlds_sync(PgWorlds *w);
  * run n_steps steps, download into the same arrays -- one call, internally pipelined over chunks of
  * worlds so that both PCIe directions and the kernels overlap.  Synchronous. */
 int  pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *vel, uint8_t *at_rest_or_null);
+/* The same with ONE host buffer in a packed layout, one record per world:
+ *     float pos[n][3]; float vel[n][3]; uint8_t at_rest[n]; padding up to pg_worlds_packed_world_bytes()
+ * A chunk of worlds is then one contiguous range: one DMA per chunk and direction instead of three. */
+size_t pg_worlds_packed_world_bytes(const PgWorlds *w);
+int  pg_worlds_step_host_packed(PgWorlds *w, float dt, int n_steps, void *state);
 /* Events of the last pg_worlds_step call, world-major then solve order.  Returns the total
  * number produced (may exceed cap; a world that overflowed max_events_per_world is reported
  * through *overflowed). */

@@ -350,6 +350,29 @@ def test_step_host_pipeline_matches_resident_path(gpu_lib, oracle_lib):
         o.step(DT, 30)
         r = o.read(1)
         assert gen.same_bits(P[k], r["position"]) and gen.same_bits(V[k], r["velocity"])
+    # the packed host layout (one record per world, one DMA per chunk and direction): same bits again, with a
+    # ragged sphere count (n = 100: the record is padded to 16 bytes) and n_steps = 0 as the identity
+    for nn in (256, 100):
+        pos2, vel2 = scenes.sphere_worlds(nw, nn, 10.0, first_world=500)
+        c = gpu_lib.GpuWorlds(nw, len(st), nn, 0); c.set_spheres(0, st, pos2, vel2)
+        d = gpu_lib.GpuWorlds(nw, len(st), nn, 0); d.set_spheres(0, st, pos2, vel2)
+        rec = c.packed_dtype()
+        assert rec.itemsize % 16 == 0 and rec.itemsize >= 25 * nn
+        S = np.zeros(nw, rec)
+        S["pos"] = pos2; S["vel"] = vel2
+        c.step_host_packed(DT, 0, S)
+        assert gen.same_bits(S["pos"], pos2) and gen.same_bits(S["vel"], vel2) and not S["at_rest"].any()
+        for _ in range(6):
+            c.step_host_packed(DT, 5, S)
+        d.step(DT, 30)
+        P3 = np.zeros_like(pos2); V3 = np.zeros_like(vel2); R3 = np.zeros((nw, nn), np.uint8)
+        d.download_state(0, nw, P3, V3, R3)
+        assert gen.same_bits(S["pos"], P3) and gen.same_bits(S["vel"], V3) and np.array_equal(S["at_rest"], R3)
+        if nn == 256:
+            assert gen.same_bits(S["pos"], P)
+        with pytest.raises(gpu_lib.PgError):
+            c.step_host_packed(DT, 1, S[:-1])
+        c.close(); d.close()
     a.close(); b.close()
 
 
