@@ -7,30 +7,39 @@
 //   1. pass 3 (spheres x statics) touches only the sphere -> one thread per sphere: a streaming probe
 //      kernel with the cheap gates, then the exact visits of the few bodies that pass one
 //                                                                        [k_pass3, k_pass3_exact]
-//   2. uniform grid over the post-pass-3 centres; every body carries an envelope
-//        env = r + 2 (|v| + g dt) dt (1+eps)
-//      that bounds where it can be, plus how far interval_collision can reach from there, at ANY
-//      moment of pass 4 as long as no contact changes it.  Two bodies whose envelopes do not
-//      touch can never pass the root test of interval_collision (world.c:559-565), so only pairs
-//      from the 27-cell neighbourhood with touching envelopes are candidates.
+//   2. BROADPHASE OVER PHASE ENTRIES.  During pass 4 a body is seen in two phases: before its own row has
+//      integrated it (phase A: by the visits of rows <= its own) and after (phase B: by the rows that follow;
+//      a body at rest has no phase B).  A visit (row, col) pairs phase A of `row` with phase A of `col` when
+//      col > row and with phase B of `col` when col < row -- never B with B.  In either phase the body moves
+//      on a straight line for the length of the visit, x(t) = c + v t, t in [0, dt], so it stays inside the
+//      ball around the MIDPOINT of that segment
+//            mid = c + v dt/2,   rho = r + |v| dt/2   (+ rounding slack)
+//      and a visit can only fire -- the closest approach of the two segments must come within r_a + r_b plus
+//      what the interval search can still bridge, pgs::pair_gate_rejects -- if the two balls touch.  The
+//      balls are what goes into the uniform grid: two entries per body, binned by midpoint.  Compared with one
+//      ball per body that covers both phases and the predicate's own sum-of-speeds reach
+//      (r + 2 (|v| + g dt) dt: the previous scheme) the search radius of a fast body drops by 4x, and a gas
+//      that falls in parallel at 50 m/s lists a handful of candidates per body instead of hundreds.
+//      Candidates are VISITS (row, col): entry pair (A_i, A_j), i < j -> visit (i, j) [and (j, i) too when i
+//      rests]; (B_i, A_j), i < j -> visit (j, i).  Each carries the verdict of the closest-approach gate on
+//      the untouched states, so the first iteration only evaluates the few that pass it.
 //                                           [k_cell_count, scan, k_scatter (counting sort), k_pairs]
 //   3. ORDER-PRESERVING FIXED POINT.  Each body keeps a timeline: the contacts it has suffered so
 //      far, keyed by (row, column) = the position of the visit in the reference's sweep, with the
-//      state they left behind.  A candidate pair is evaluated as its two visits (i,j) and (j,i)
-//      on the states the timelines imply AT THAT KEY (including whether the body's own row, hence
-//      its integration, lies before the key).  The hits found form the next timelines; iterate
-//      until nothing changes.  The earliest event of the true sequential sweep is found in the
-//      first iteration and never changes again; by induction iteration k fixes the k-th link of
-//      every dependency chain, so the fixed point IS the sequential result -- bit for bit, since
-//      every visit runs the exact arithmetic of pg_math.cuh.  An iteration only looks at what can
+//      state they left behind.  A candidate visit is evaluated on the states the timelines imply AT THAT KEY
+//      (including whether the body's own row, hence its integration, lies before the key).  The hits found
+//      form the next timelines; iterate until nothing changes.  The earliest event of the true sequential
+//      sweep is found in the first iteration and never changes again; by induction iteration k fixes the
+//      k-th link of every dependency chain, so the fixed point IS the sequential result -- bit for bit,
+//      since every visit runs the exact arithmetic of pg_math.cuh.  An iteration only looks at what can
 //      have changed: k_begin copies the entries of bodies whose timeline did not change (with
-//      partners that did not either) and lists the pairs that need a look; k_eval evaluates them,
-//      one thread per pair, and hands the rare long interval searches to k_eval_hard (a block per
-//      pair); k_check compares the timelines of the bodies involved.
+//      partners that did not either) and lists the visits that need a look; k_eval evaluates them,
+//      one thread per visit, and hands the rare long interval searches to k_eval_hard (a block per
+//      visit); k_check compares the timelines of the bodies involved.
 //                                                          [k_begin, k_eval, k_eval_hard, k_check]
-//   4. envelopes are re-validated against the new timelines (a contact may have sped a body
-//      up); if one grew, the pairs it adds are appended and the iteration continues warm.
-//                                                       [k_check, k_requery, k_requery_wide]
+//   4. a contact gives a body states its phase balls were not sized for; k_check re-validates the two radii
+//      against the new timelines, and if one grew, the visits it adds are appended and the iteration continues
+//      warm.                                              [k_check, k_requery, k_requery_wide]
 //   5. final state = timeline tail, integrated if the body's own row came after it; the fixed
 //      point's per-body bookkeeping is put back for the bodies that used it.
 //                                                                    [k_finalize, k_reset_touched]
@@ -63,7 +72,7 @@ struct GridParams {
   int dim[3];
   int n_cells;
   int ok;
-  float e_cap;            // envelope the cell edge is sized for; bodies beyond it are "fast" (few) and search wider
+  float e_cap;            // ball radius the cell edge is sized for; entries beyond it are "fast" (few) and search wider
 };
 
 // Running statistics that keep the grid sized for the BULK of the bodies whatever a few stragglers do
@@ -91,10 +100,33 @@ struct Flags {
   unsigned n_pass3;       // bodies k_pass3 passed on to k_pass3_exact
 };
 
-// One body of the cell-ordered copy.  A whole 32-byte sector per body: the counting sort's scattered
+// One phase entry of the cell-ordered copy.  A whole 32-byte sector per entry: the counting sort's scattered
 // store then never leaves a partial sector behind (16 B + 4 B stores into shared sectors made the L2
-// fetch the rest from DRAM: 2.6x the algorithmic traffic), and a reader gets the index with the centre.
-struct __align__(32) SortedBody { float4 cenv; unsigned idx, pad0, pad1, pad2; };
+// fetch the rest from DRAM: 2.6x the algorithmic traffic), and a reader gets everything a candidate test
+// needs -- the exact centre and velocity the phase's visits see (the gate's inputs), the ball radius, and the
+// entry id (2 * body + phase) -- without a second look-up.
+struct __align__(32) SortedBody { float4 crho; float vx, vy, vz; unsigned idx; };
+
+// Phase entries.  entry id e = 2 * body + phase (0 = A: before the body's own row integrates it, 1 = B: after).
+__device__ __forceinline__ float3 entry_mid(float cx, float cy, float cz, float vx, float vy, float vz, float dt) {
+  const float h = 0.5f * dt;
+  return make_float3(__fmaf_rn(vx, h, cx), __fmaf_rn(vy, h, cy), __fmaf_rn(vz, h, cz));
+}
+// Radius of the ball around the midpoint that holds the body for the whole visit, plus the share of the gate's
+// tolerance (pgs::pair_gate_rejects: delta = 1.1e-6 vsum + 4e-6 (cmax + vsum dt) + 1e-6) this body answers for,
+// with a 5e-4 relative cushion over every rounding in here and in the float ball test.
+__device__ __forceinline__ float entry_rho(float r, float cx, float cy, float cz, float vx, float vy, float vz, float dt) {
+  const float sp = sqrtf(__fmaf_rn(vx, vx, __fmaf_rn(vy, vy, vz * vz)));
+  const float cm = fmaxf(fmaxf(fabsf(cx), fabsf(cy)), fabsf(cz));
+  return __fmaf_rn(0.5f * sp, dt, r) * 1.0005f + (2.0e-6f * sp + 8.0e-6f * (cm + sp * dt) + 4.0e-6f);
+}
+// State of an untouched body in phase `ph` from its post-pass-3 record: the record itself, or what its own
+// row's integration makes of it (world.c:549-553; the very function the real integration uses).
+__device__ __forceinline__ void entry_state(const float4 p, const float4 q, int ph, float dt, float *c, float *vel) {
+  V3 pp = v3(p.x, p.y, p.z), vv = v3(q.x, q.y, q.z);
+  if (ph) pgm::integrate(pp, vv, dt);
+  c[0] = pp.x; c[1] = pp.y; c[2] = pp.z; vel[0] = vv.x; vel[1] = vv.y; vel[2] = vv.z;
+}
 
 struct LargeView {
   int n, ns;
@@ -113,22 +145,25 @@ struct LargeView {
   int sg_dim[3];
   unsigned *sg_start;                // [cells + 1]
   int *sg_items;                     // static indices, ascending inside a cell
-  float *env;                        // envelope radius per body
+  float *env;                        // [2n] ball radius per phase entry (entry e = 2 body + phase); < 0: no such entry (body at rest has no phase B)
+  float r_uniform;                   // >= 0: every sphere has this world radius (no per-body look-up in k_pairs)
+  float ecap_factor;                 // grid sizing: cells hold balls up to ecap_factor x the mean radius
   // reductions
   unsigned *bbox;                    // 6 ordered-uint encodings: min xyz, max xyz ; [6] = max env
   float *rstat;                      // [8] sums over the bodies inside the previous robust box: x y z |dx| |dy| |dz| env count
   Robust *robust;
-  int *fast_list;                    // [n] bodies whose envelope exceeds grid->e_cap
-  int *wide_list;                    // [n] grown bodies whose search is wider than 27 cells (k_requery_wide)
+  int *fast_list;                    // [2n] entries whose radius exceeds grid->e_cap
+  int *wide_list;                    // [2n] grown entries whose search is wider than 27 cells (k_requery_wide)
   GridParams *grid;
   // grid
-  unsigned *cell_of;                 // [n]
+  unsigned *cell_of;                 // [2n] (0xffffffff: entry not in the grid)
   unsigned *cell_cnt;                // [cells_cap + 1]  counts -> exclusive starts
   unsigned *block_sums;              // scan scratch
   int cells_cap;
-  SortedBody *sorted;                // [n]  bodies in cell order: centre xyz, env, body index -- one 32-byte sector each
+  SortedBody *sorted;                // [2n] entries in cell order: centre, radius, velocity, entry id -- one 32-byte sector each
   // candidates
-  int2 *pairs;
+  int2 *pairs;                       // candidate VISITS: .x = row (~row: appended by k_requery, never evaluated yet), .y = column
+                                     // (sign bit set: the closest-approach gate rejected the visit on the untouched states)
   long long pairs_cap;
   unsigned *active;                  // [2 pairs_cap] indices into pairs[]: the ones this iteration has to look at (k_begin), and from
                                      // pairs_cap on the ones k_eval deferred to k_eval_hard
@@ -142,9 +177,9 @@ struct LargeView {
   unsigned *pushed_bits;              // the body received an entry from k_eval in the current iteration, or had one that k_eval
                                       // was to decide about again: k_check must compare its timelines
   int *touched;                       // bodies that ever received a timeline entry this step
-  unsigned *cell_rank;                // rank of a body inside its cell (returned by the counting atomic)
-  unsigned char *grown;               // envelope grew during the current fixed point
-  float *env_prev;                   // envelope the current candidate list was built with
+  unsigned *cell_rank;                // [2n] rank of an entry inside its cell (returned by the counting atomic)
+  unsigned char *grown;               // [2n] the entry's radius grew during the current fixed point
+  float *env_prev;                   // [2n] radius the current candidate list was built with
   unsigned long long *tl_key[2];
   float4 *tl_pos[2], *tl_vel[2];
   Flags *flags;
@@ -211,12 +246,6 @@ __device__ __forceinline__ void event_stage(const LargeView &v, int mode, int st
 }
 __device__ __forceinline__ void emit_event(const LargeView &v, int step, int pass, int ac, int ai, int bc, int bi) {
   event_stage(v, kEventAdd, step, pass, ac, ai, bc, bi);
-}
-
-__device__ __forceinline__ float envelope(float r, float vx, float vy, float vz, float dt) {
-  // r + 2 (|v| + g dt) dt, rounded up: displacement of one integration + the predicate's reach
-  const float sp = sqrtf(__fmaf_rn(vx, vx, __fmaf_rn(vy, vy, vz * vz)));
-  return (r + 2.0f * (sp + pgm::kGravity * dt) * dt) * 1.0002f + 2.0e-6f;
 }
 
 // ---------------------------------------------------------------- 1. pass 3 + envelope + bounds
@@ -343,26 +372,41 @@ __device__ __forceinline__ void pass3_impl(const LargeView &v, float dt, int ste
       if (touched) { v.pos_rest[i] = p; v.vel_rad[i] = q; }
     }
     if (Probe && needs) { touched_stage_impl(v.touched, &v.flags->n_pass3, kTouchStage, i, kTouchAdd); continue; }
-    const float e = envelope(q.w, q.x, q.y, q.z, dt);
-    v.env[i] = e;
-    v.env_prev[i] = e;
+    // the body's two phase entries (midpoint balls of the untouched state, see the header comment)
+    float cA[3], vA[3];
+    entry_state(p, q, 0, dt, cA, vA);
+    const float rhoA = entry_rho(q.w, cA[0], cA[1], cA[2], vA[0], vA[1], vA[2], dt);
+    const float3 mA = entry_mid(cA[0], cA[1], cA[2], vA[0], vA[1], vA[2], dt);
+    float rhoB = -1.0f;
+    float3 mB = mA;
+    if (p.w == 0.0f) {
+      float cB[3], vB[3];
+      entry_state(p, q, 1, dt, cB, vB);
+      rhoB = entry_rho(q.w, cB[0], cB[1], cB[2], vB[0], vB[1], vB[2], dt);
+      mB = entry_mid(cB[0], cB[1], cB[2], vB[0], vB[1], vB[2], dt);
+    }
+    reinterpret_cast<float2 *>(v.env)[i] = make_float2(rhoA, rhoB);
+    reinterpret_cast<float2 *>(v.env_prev)[i] = make_float2(rhoA, rhoB);
+    const float e = fmaxf(rhoA, rhoB);
     if (full_reset) {
       // per-step bookkeeping of the fixed point: only bodies that get a timeline entry ever change it, and
       // k_reset_touched puts those back at the end of the step (23 B per body and step not written here)
-      v.grown[i] = 0;
+      v.grown[2 * i] = 0;
+      v.grown[2 * i + 1] = 0;
       v.tl_cnt[0][i] = 0;
       v.tl_cnt[1][i] = 0;
       v.tl_chg[0][i] = 0xffffffffffffffffull;
       v.tl_chg[1][i] = 0xffffffffffffffffull;
       v.seen[i] = 0;
     }
-    if (!(fabsf(p.x) < 1.0e15f && fabsf(p.y) < 1.0e15f && fabsf(p.z) < 1.0e15f && e < 1.0e15f)) { bad = true; continue; }
-    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
-    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    if (!(fabsf(mA.x) < 1.0e15f && fabsf(mA.y) < 1.0e15f && fabsf(mA.z) < 1.0e15f && fabsf(mB.x) < 1.0e15f && fabsf(mB.y) < 1.0e15f &&
+          fabsf(mB.z) < 1.0e15f && e < 1.0e15f)) { bad = true; continue; }
+    lo[0] = fminf(lo[0], fminf(mA.x, mB.x)); lo[1] = fminf(lo[1], fminf(mA.y, mB.y)); lo[2] = fminf(lo[2], fminf(mA.z, mB.z));
+    hi[0] = fmaxf(hi[0], fmaxf(mA.x, mB.x)); hi[1] = fmaxf(hi[1], fmaxf(mA.y, mB.y)); hi[2] = fmaxf(hi[2], fmaxf(mA.z, mB.z));
     emax = fmaxf(emax, e);
-    const float dx = fabsf(p.x - rb.centre[0]), dy = fabsf(p.y - rb.centre[1]), dz = fabsf(p.z - rb.centre[2]);
+    const float dx = fabsf(mA.x - rb.centre[0]), dy = fabsf(mA.y - rb.centre[1]), dz = fabsf(mA.z - rb.centre[2]);
     if (dx <= rb.half[0] && dy <= rb.half[1] && dz <= rb.half[2]) {
-      rs[0] += p.x; rs[1] += p.y; rs[2] += p.z; rs[3] += dx; rs[4] += dy; rs[5] += dz; rs[6] += e; rs[7] += 1.0f;
+      rs[0] += mA.x; rs[1] += mA.y; rs[2] += mA.z; rs[3] += dx; rs[4] += dy; rs[5] += dz; rs[6] += rhoA; rs[7] += 1.0f;
     }
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -417,7 +461,7 @@ __global__ void k_grid_params(LargeView v) {
       if (rb.valid) { lo[k] = fmaxf(lo[k], mean - half); hi[k] = fminf(hi[k], mean + half); }
       rb.centre[k] = mean; rb.half[k] = half;
     }
-    if (rb.valid) e_cap = fminf(emax, 4.0f * (v.rstat[6] / cnt) + 1.0e-3f);
+    if (rb.valid) e_cap = fminf(emax, v.ecap_factor * (v.rstat[6] / cnt) + 1.0e-3f);
     rb.valid = 1;
   } else {
     // lost the bulk (or first step, or a frozen-state query): accept everything, start over
@@ -453,16 +497,22 @@ __device__ __forceinline__ int3 cell_coords(const GridParams &g, float x, float 
   return c;
 }
 
-// ---------------------------------------------------------------- 2. counting sort into cells
-__global__ void k_cell_count(LargeView v) {
+// ---------------------------------------------------------------- 2. counting sort of the phase entries into cells
+__global__ void k_cell_count(LargeView v, float dt) {
   const GridParams g = *v.grid;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
-    const float4 p = v.pos_rest[i];
-    const int3 c = cell_coords(g, p.x, p.y, p.z);
-    const unsigned cell = (unsigned)((c.z * g.dim[1] + c.y) * g.dim[0] + c.x);
-    v.cell_of[i] = cell;
-    v.cell_rank[i] = atomicAdd(v.cell_cnt + cell, 1u);
-    if (v.env[i] > g.e_cap) v.fast_list[atomicAdd(&v.flags->n_fast, 1u)] = i;
+  const int n_ent = 2 * v.n;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_ent; e += gridDim.x * blockDim.x) {
+    const float rho = v.env[e];
+    if (rho < 0.0f) { v.cell_of[e] = 0xffffffffu; continue; }      // a body at rest has no phase B
+    const int i = e >> 1;
+    float c[3], vel[3];
+    entry_state(v.pos_rest[i], v.vel_rad[i], e & 1, dt, c, vel);
+    const float3 m = entry_mid(c[0], c[1], c[2], vel[0], vel[1], vel[2], dt);
+    const int3 cc = cell_coords(g, m.x, m.y, m.z);
+    const unsigned cell = (unsigned)((cc.z * g.dim[1] + cc.y) * g.dim[0] + cc.x);
+    v.cell_of[e] = cell;
+    v.cell_rank[e] = atomicAdd(v.cell_cnt + cell, 1u);
+    if (rho > g.e_cap) v.fast_list[atomicAdd(&v.flags->n_fast, 1u)] = e;
   }
 }
 
@@ -524,48 +574,81 @@ __global__ void k_scan_add(LargeView v) {
   for (int k = 0; k < kScanItems; k++) if (base + k < n) v.cell_cnt[base + k] += add;
 }
 
-__global__ void k_scatter(LargeView v) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
-    const unsigned cell = v.cell_of[i];
-    const unsigned slot = v.cell_cnt[cell] + v.cell_rank[i];
-    const float4 p = v.pos_rest[i];
-    const float e = v.env[i];
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(v.sorted + slot), "r"(__float_as_uint(p.x)), "r"(__float_as_uint(p.y)),
-                 "r"(__float_as_uint(p.z)), "r"(__float_as_uint(e)), "r"((unsigned)i), "r"(0u), "r"(0u), "r"(0u) : "memory");
+__global__ void k_scatter(LargeView v, float dt) {
+  const int n_ent = 2 * v.n;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_ent; e += gridDim.x * blockDim.x) {
+    const unsigned cell = v.cell_of[e];
+    if (cell == 0xffffffffu) continue;
+    const unsigned slot = v.cell_cnt[cell] + v.cell_rank[e];
+    const int i = e >> 1;
+    float c[3], vel[3];
+    entry_state(v.pos_rest[i], v.vel_rad[i], e & 1, dt, c, vel);
+    const float rho = v.env[e];
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(v.sorted + slot), "r"(__float_as_uint(c[0])), "r"(__float_as_uint(c[1])),
+                 "r"(__float_as_uint(c[2])), "r"(__float_as_uint(rho)), "r"(__float_as_uint(vel[0])), "r"(__float_as_uint(vel[1])),
+                 "r"(__float_as_uint(vel[2])), "r"((unsigned)e | (v.pos_rest[i].w != 0.0f ? 0x80000000u : 0u)) : "memory");
   }
 }
 
-// ---------------------------------------------------------------- candidate pairs
-// A pair is listed by its body with the LARGER envelope (ties: lower index), which therefore only has
-// to find partners within 2 env of itself: R = ceil(2 env / h) cells each way -- 1 for everybody the
-// grid was sized for (27 cells = 9 contiguous x-runs), more for the few fast bodies, and the whole
-// sorted array for a body so fast that its search would cover most of the grid anyway.
+// ---------------------------------------------------------------- candidate visits
+// A pair of entries is listed by the one with the LARGER ball (ties: lower entry id), which therefore only has
+// to find partners within 2 rho of itself: R = ceil(2 rho / h) cells each way -- 1 for everybody the
+// grid was sized for (27 cells = 9 contiguous x-runs), more for the few fast entries, and the whole
+// sorted array for one so fast that its search would cover most of the grid anyway.
 constexpr int kMaxSearch = 12;
 constexpr int kPairsBlock = 128;
-constexpr int kPairsStage = 1024;       // pairs a block collects in shared memory between two flushes
-// One thread per body (in cell order, so neighbouring threads read neighbouring cells); every thread
-// walks its own cell runs without warp votes.  Two bodies the grid was sized for (R = 1 both) lie in the
+constexpr int kPairsStage = 1024;       // visits a block collects in shared memory between two flushes
+constexpr unsigned kRestBit = 0x80000000u;      // SortedBody::idx: the entry's body is at rest (it has no phase B)
+
+// Which visits does the touching entry pair (ea, eb) stand for?  (header comment, step 2)  Returns their number
+// and (row, col) of each; `swap[k]`: the row body of visit k is eb's.
+__device__ __forceinline__ int entry_pair_visits(unsigned ea, bool rest_a, unsigned eb, bool rest_b, int2 *out, bool *row_is_b) {
+  const int ia = (int)(ea >> 1), ib = (int)(eb >> 1);
+  const int pa = (int)(ea & 1u), pb = (int)(eb & 1u);
+  if (ia == ib || (pa & pb)) return 0;
+  if (!pa && !pb) {
+    const bool a_lo = ia < ib;
+    const int lo = a_lo ? ia : ib, hi = a_lo ? ib : ia;
+    out[0] = make_int2(lo, hi); row_is_b[0] = !a_lo;
+    if (a_lo ? rest_a : rest_b) { out[1] = make_int2(hi, lo); row_is_b[1] = a_lo; return 2; }   // lo never integrates: row hi sees it as it is
+    return 1;
+  }
+  // one phase B, one phase A: the B body must be the lower index; the visit belongs to the A body's row
+  if (pa) { if (!(ia < ib)) return 0; out[0] = make_int2(ib, ia); row_is_b[0] = true; return 1; }
+  if (!(ib < ia)) return 0;
+  out[0] = make_int2(ia, ib); row_is_b[0] = false;
+  return 1;
+}
+
+// One thread per entry (in cell order, so neighbouring threads read neighbouring cells); every thread
+// walks its own cell runs without warp votes.  Two entries the grid was sized for (R = 1 both) lie in the
 // same or in adjacent cells, so each of them searches only the HALF shell of cells that follow its own
 // in cell order (the rest of its own x-run, the next y-row, the three rows of the next z-layer: 5 runs,
-// 13.5 cells instead of 27) and lists whatever it finds there; a body with a larger envelope searches
-// its whole neighbourhood and lists the partners whose envelope is smaller (ties: lower index), and an
-// R = 1 body leaves such partners to them.  Pairs are staged in shared memory and appended to the global
-// list once per tile of kPairsBlock bodies; a tile that finds more than kPairsStage pairs (a dense pile)
+// 13.5 cells instead of 27) and lists whatever it finds there; an entry with a larger ball searches
+// its whole neighbourhood and lists the partners whose ball is smaller (ties: lower id), and an
+// R = 1 entry leaves such partners to them.  Visits are staged in shared memory and appended to the global
+// list once per tile of kPairsBlock entries; a tile that finds more than kPairsStage (a dense pile)
 // appends the surplus directly.
-__global__ void __launch_bounds__(kPairsBlock) k_pairs(LargeView v) {
+__global__ void __launch_bounds__(kPairsBlock) k_pairs(LargeView v, float dt) {
   __shared__ int2 s_pairs[kPairsStage];
   __shared__ unsigned s_cnt;
   __shared__ unsigned long long s_base;
   const GridParams g = *v.grid;
-  const int n_tiles = (v.n + kPairsBlock - 1) / kPairsBlock;
+  const int n_sorted = (int)v.cell_cnt[g.n_cells];
+  const int n_tiles = (n_sorted + kPairsBlock - 1) / kPairsBlock;
+  const bool gate_ok = dt > 1.0e-9f;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     const int a = tile * kPairsBlock + threadIdx.x;
-    if (a < v.n) {
-      const float4 ca = v.sorted[a].cenv;
-      const unsigned ia = v.sorted[a].idx;
-      const int3 c = cell_coords(g, ca.x, ca.y, ca.z);
+    if (a < n_sorted) {
+      const float4 ca = v.sorted[a].crho;
+      const float4 wa = *reinterpret_cast<const float4 *>(&v.sorted[a].vx);
+      const unsigned ea = __float_as_uint(wa.w) & ~kRestBit;
+      const bool rest_a = (__float_as_uint(wa.w) & kRestBit) != 0u;
+      const float3 ma = entry_mid(ca.x, ca.y, ca.z, wa.x, wa.y, wa.z, dt);
+      const float na2 = __fmaf_rn(wa.x, wa.x, __fmaf_rn(wa.y, wa.y, wa.z * wa.z));
+      const int3 c = cell_coords(g, ma.x, ma.y, ma.z);
       const float need = 2.0f * ca.w * g.inv_h * 1.001f;
       const int R = need <= 1.0f ? 1 : (need <= (float)kMaxSearch ? (int)ceilf(need) : 0);
       const bool everything = !(need <= (float)kMaxSearch);
@@ -573,36 +656,54 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs(LargeView v) {
       auto run = [&](unsigned b0, unsigned b1) {
         // (the loads of up to four partners are issued before the first is looked at: the kernel is bound by
         // the latency of its dependent loads, not by instructions or bytes)
-        float4 nb[4];
+        float4 nb[4], nw[4];
         for (unsigned bb = b0; bb < b1; bb += 4) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) nb[u] = v.sorted[min(bb + u, b1 - 1)].cenv;
+        for (int u = 0; u < 4; u++) {
+          const SortedBody *sb = v.sorted + min(bb + u, b1 - 1);
+          nb[u] = sb->crho; nw[u] = *reinterpret_cast<const float4 *>(&sb->vx);
+        }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const unsigned b = bb + u;
           if (b >= b1) break;
-          const float4 cb = nb[u];
-          const float dx = ca.x - cb.x, dyy = ca.y - cb.y, dzz = ca.z - cb.z;
+          const float4 cb = nb[u], wb = nw[u];
+          const float3 mb = entry_mid(cb.x, cb.y, cb.z, wb.x, wb.y, wb.z, dt);
+          const float dx = ma.x - mb.x, dyy = ma.y - mb.y, dzz = ma.z - mb.z;
           const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
           const float T = ca.w + cb.w;
           if (!(d2 <= T * T)) continue;
-          const unsigned ib = v.sorted[b].idx;
+          const unsigned eb = __float_as_uint(wb.w) & ~kRestBit;
+          const bool rest_b = (__float_as_uint(wb.w) & kRestBit) != 0u;
           if (half) {
             if (!(2.0f * cb.w * g.inv_h * 1.001f <= 1.0f)) continue;          // a wider-searching partner lists the pair itself
           } else {
-            if (ca.w < cb.w || ia == ib || (ca.w == cb.w && !(ia < ib))) continue;
+            if (ca.w < cb.w || ea == eb || (ca.w == cb.w && !(ea < eb))) continue;
           }
-          const int2 pr = make_int2((int)min(ia, ib), (int)max(ia, ib));
-          const unsigned slot = atomicAdd(&s_cnt, 1u);
-          if (slot < (unsigned)min(v.stage_limit, kPairsStage)) { s_pairs[slot] = pr; continue; }
-          const unsigned long long gs = atomicAdd(&v.flags->n_pairs, 1ull);
-          if ((long long)gs < v.pairs_cap) v.pairs[gs] = pr;
-          else atomicExch(&v.flags->overflow_pairs, 1);
+          int2 vis[2]; bool row_b[2];
+          const int nv = entry_pair_visits(ea, rest_a, eb, rest_b, vis, row_b);
+          for (int q = 0; q < nv; q++) {
+            // the closest-approach gate the exact predicate opens with, on the untouched states (row body first)
+            bool rej = false;
+            if (gate_ok) {
+              const float rs = v.r_uniform >= 0.0f ? v.r_uniform + v.r_uniform : v.vel_rad[vis[q].x].w + v.vel_rad[vis[q].y].w;
+              const float nb2 = __fmaf_rn(wb.x, wb.x, __fmaf_rn(wb.y, wb.y, wb.z * wb.z));
+              const float vsum = sqrtf(2.0f * (na2 + nb2)) * 1.0001f;          // >= |vA| + |vB|
+              const V3 pa3 = v3(ca.x, ca.y, ca.z), va3 = v3(wa.x, wa.y, wa.z), pb3 = v3(cb.x, cb.y, cb.z), vb3 = v3(wb.x, wb.y, wb.z);
+              rej = row_b[q] ? pgs::pair_gate_rejects(pb3, vb3, pa3, va3, rs, vsum, dt) : pgs::pair_gate_rejects(pa3, va3, pb3, vb3, rs, vsum, dt);
+            }
+            const int2 pr = make_int2(vis[q].x, rej ? (int)((unsigned)vis[q].y | 0x80000000u) : vis[q].y);
+            const unsigned slot = atomicAdd(&s_cnt, 1u);
+            if (slot < (unsigned)min(v.stage_limit, kPairsStage)) { s_pairs[slot] = pr; continue; }
+            const unsigned long long gs = atomicAdd(&v.flags->n_pairs, 1ull);
+            if ((long long)gs < v.pairs_cap) v.pairs[gs] = pr;
+            else atomicExch(&v.flags->overflow_pairs, 1);
+          }
         }
         }
       };
       if (everything) {
-        run(0u, (unsigned)v.n);
+        run(0u, (unsigned)n_sorted);
       } else if (half) {
         const int x0 = max(c.x - 1, 0), x1 = min(c.x + 1, g.dim[0] - 1);
         const unsigned row = (unsigned)((c.z * g.dim[1] + c.y) * g.dim[0]);
@@ -647,13 +748,7 @@ struct BodyState { float px, py, pz, vx, vy, vz; };
 
 // State of body b just before the visit with key (row, col): post-pass-3 state, then the latest
 // timeline entry with a smaller key, then the body's own integration if its row lies between.
-// `skip_key` (if non-zero) names an entry to ignore and `ovr` an entry to use in its place: the
-// fresh outcome of the pair's first visit when its second visit is evaluated (Gauss-Seidel inside
-// a pair; the fixed points are the same as without it).
-struct Override { unsigned long long key; bool present; float px, py, pz, vx, vy, vz; };
-
-__device__ __forceinline__ BodyState state_at(const LargeView &v, int src, int b, unsigned long long key, float dt, float *radius,
-                                             unsigned long long skip_key, const Override *ovr) {
+__device__ __forceinline__ BodyState state_at(const LargeView &v, int src, int b, unsigned long long key, float dt, float *radius) {
   const float4 p = v.pos_rest[b], q = v.vel_rad[b];
   BodyState s;
   s.px = p.x; s.py = p.y; s.pz = p.z; s.vx = q.x; s.vy = q.y; s.vz = q.z;
@@ -664,17 +759,12 @@ __device__ __forceinline__ BodyState state_at(const LargeView &v, int src, int b
   int best_k = -1;
   for (int k = 0; k < cnt; k++) {
     const unsigned long long kk = v.tl_key[src][(size_t)b * kTimeline + k];
-    if (kk == skip_key) continue;
     if (kk < key && (best_k < 0 || kk > best)) { best = kk; best_k = k; }
   }
   if (best_k >= 0) {
     const float4 tp = v.tl_pos[src][(size_t)b * kTimeline + best_k], tv = v.tl_vel[src][(size_t)b * kTimeline + best_k];
     s.px = tp.x; s.py = tp.y; s.pz = tp.z; s.vx = tv.x; s.vy = tv.y; s.vz = tv.z;
     last_row = (long long)(best >> 32);
-  }
-  if (ovr && ovr->present && ovr->key < key && (best_k < 0 || ovr->key > best)) {
-    s.px = ovr->px; s.py = ovr->py; s.pz = ovr->pz; s.vx = ovr->vx; s.vy = ovr->vy; s.vz = ovr->vz;
-    last_row = (long long)(ovr->key >> 32);
   }
   const long long row = (long long)(key >> 32);
   if (row > b && last_row <= b && p.w == 0.0f) {            // own row finished in between: integrate (world.c:549-553)
@@ -706,22 +796,17 @@ __device__ __forceinline__ void timeline_push(const LargeView &v, int dst, int b
 }
 
 // Evaluate one visit on the hypothesis `src` WITHOUT touching the timelines: 0 = no event, 1 = event
-// (A = row body, B = column body after it), 2 = deferred (one thread per pair only: the interval search
-// is a long one, the pair goes to a block).  Warp: all threads of the block, identical arguments.
+// (A = row body, B = column body after it), 2 = deferred (one thread per visit only: the interval search
+// is a long one, the visit goes to a block).  Warp: all threads of the block, identical arguments.
 template <bool Warp>
-__device__ __forceinline__ int visit_compute(const LargeView &v, int src, int row, int col, float dt, pgm::LeafLen leaf,
-                                             unsigned long long skip_key, const Override *in_row, const Override *in_col,
-                                             Sphere &A, Sphere &B) {
+__device__ __forceinline__ int visit_compute(const LargeView &v, int src, int row, int col, float dt, pgm::LeafLen leaf, Sphere &A, Sphere &B) {
   const unsigned long long key = ((unsigned long long)(unsigned)row << 32) | (unsigned)col;
   float ra, rb;
-  const BodyState a = state_at(v, src, row, key, dt, &ra, skip_key, in_row), b = state_at(v, src, col, key, dt, &rb, skip_key, in_col);
+  const BodyState a = state_at(v, src, row, key, dt, &ra), b = state_at(v, src, col, key, dt, &rb);
   A.px = a.px; A.py = a.py; A.pz = a.pz; A.vx = a.vx; A.vy = a.vy; A.vz = a.vz; A.r = ra; A.rest = 0;
   B.px = b.px; B.py = b.py; B.pz = b.pz; B.vx = b.vx; B.vy = b.vy; B.vz = b.vz; B.r = rb; B.rest = 0;
   if (Warp) return pgs::sphere_pair_exact_block(A, B, dt, leaf) ? 1 : 0;
   return pgs::sphere_pair_exact_try(A, B, dt, leaf);
-}
-__device__ __forceinline__ void set_override(Override *o, unsigned long long key, const Sphere &S) {
-  o->key = key; o->present = true; o->px = S.px; o->py = S.py; o->pz = S.pz; o->vx = S.vx; o->vy = S.vy; o->vz = S.vz;
 }
 
 // Copy the entry with `key` (if any) of body b from the src to the dst timeline.
@@ -738,26 +823,24 @@ __device__ __forceinline__ bool carry_entry(const LargeView &v, int src, int dst
 }
 
 // Did anything body b contributes to a visit with key K change since the previous iteration?
-// (entries with key < K other than `except`: new or different state -> flagged in .w; gone -> tl_chg)
-__device__ __forceinline__ bool affected(const LargeView &v, int src, int b, unsigned long long K, unsigned long long except) {
+// (entries with key < K: new or different state -> flagged in .w; gone -> tl_chg)
+__device__ __forceinline__ bool affected(const LargeView &v, int src, int b, unsigned long long K) {
   const unsigned long long rem = v.tl_chg[src][b];
-  if (rem < K) return true;                    // (conservative when rem == except: other removals may hide behind it)
+  if (rem < K) return true;
   const int cnt = min((int)v.tl_cnt[src][b], kTimeline);
   for (int k = 0; k < cnt; k++) {
     const unsigned long long kk = v.tl_key[src][(size_t)b * kTimeline + k];
-    if (kk < K && kk != except && v.tl_pos[src][(size_t)b * kTimeline + k].w != 0.0f) return true;
+    if (kk < K && v.tl_pos[src][(size_t)b * kTimeline + k].w != 0.0f) return true;
   }
   return false;
 }
 
-// Which candidate pairs does this iteration have to look at?  A light, fully occupied pass over the
-// whole list so that k_eval (122 registers, long divergent evaluations) runs on dense warps only.
-//   iteration 0   the timelines are empty, so both visits of a pair see the post-pass-3 states (the
-//                 second one its column body integrated): a pair both of whose closest-approach gates
-//                 -- the very gate sphere_pair_exact opens with -- reject cannot fire and is dropped.
-//                 If the first gate passes the pair is kept whatever the second says (a hit would
-//                 change what the second visit sees).
-//   later         pairs with a DIRTY body -- one whose timeline changed in the previous iteration (k_check)
+// Which candidate visits does this iteration have to look at?  A light, fully occupied pass over the
+// whole list so that k_eval (long divergent evaluations) runs on dense warps only.
+//   iteration 0   the timelines are empty: every visit sees the untouched states its two entries were listed
+//                 with, and k_pairs has already put the closest-approach gate -- the very gate
+//                 sphere_pair_exact opens with -- to those; a visit it rejected cannot fire.
+//   later         visits with a DIRTY body -- one whose timeline changed in the previous iteration (k_check)
 //                 -- or appended by k_requery.  Every visit of two clean bodies would come out as
 //                 recorded; d_clear_carry has copied those entries already.
 // The order of the active list is irrelevant (timeline slots are claimed atomically anyway).
@@ -777,26 +860,10 @@ __device__ __forceinline__ void d_select(const LargeView &v, int src, int iter, 
       if (k >= np) continue;
       const int2 pr = v.pairs[k];
       const bool fresh = pr.x < 0;
-      const int i = fresh ? ~pr.x : pr.x, j = pr.y;
+      const int i = fresh ? ~pr.x : pr.x, j = pr.y & 0x7fffffff;
       bool need = fresh;
-      if (!need && iter > 0) {
-        need = ((v.dirty_bits[src][i >> 5] >> (i & 31)) & 1u) || ((v.dirty_bits[src][j >> 5] >> (j & 31)) & 1u);
-      } else if (!need) {
-        const float4 pi = v.pos_rest[i], qi = v.vel_rad[i], pj = v.pos_rest[j], qj = v.vel_rad[j];
-        // visit (i, j) of row i (i < j): neither body integrated yet
-        const V3 cI = v3(0.0f + pi.x, 0.0f + pi.y, 0.0f + pi.z), cJ = v3(0.0f + pj.x, 0.0f + pj.y, 0.0f + pj.z);
-        const V3 vI = v3(qi.x, qi.y, qi.z), vJ = v3(qj.x, qj.y, qj.z);
-        const float rs = qi.w + qj.w, rs2 = qj.w + qi.w;
-        const float nI = pgm::norm(vI), nJ = pgm::norm(vJ);
-        need = !pgs::pair_gate_rejects(cI, vI, cJ, vJ, rs, nI + nJ, dt);
-        if (!need) {
-          // visit (j, i) of row j: body i has been integrated by its own row unless it rests (state_at)
-          V3 p2 = v3(pi.x, pi.y, pi.z), v2 = vI;
-          if (pi.w == 0.0f) pgm::integrate(p2, v2, dt);
-          const V3 c2 = v3(0.0f + p2.x, 0.0f + p2.y, 0.0f + p2.z);
-          need = !pgs::pair_gate_rejects(cJ, vJ, c2, v2, rs2, nJ + pgm::norm(v2), dt);
-        }
-      }
+      if (!need && iter > 0) need = ((v.dirty_bits[src][i >> 5] >> (i & 31)) & 1u) || ((v.dirty_bits[src][j >> 5] >> (j & 31)) & 1u);
+      else if (!need) need = pr.y >= 0;            // iteration 0: the gate's verdict from k_pairs
       if (need) need_bits |= 1u << q;
     }
     unsigned slot = 0;
@@ -815,60 +882,36 @@ __device__ __forceinline__ void d_select(const LargeView &v, int src, int iter, 
   }
 }
 
-// Both visits of candidate pair k on the hypothesis `src`; hits go to the `dst` timelines.  Returns the
-// number of hits, or -1 when a one-thread evaluation met a long interval search: nothing has been
-// written then and the pair is to be repeated by a whole block (Warp = true: all its threads run this
+// Candidate visit k on the hypothesis `src`; a hit goes to the `dst` timelines of both bodies.  Returns the
+// number of hits (0 / 1), or -1 when a one-thread evaluation met a long interval search: nothing has been
+// written then and the visit is to be repeated by a whole block (Warp = true: all its threads run this
 // with the same k, `writer` = thread 0 does the writes).
 template <bool Warp>
 __device__ __forceinline__ int eval_pair(const LargeView &v, int src, int dst, int iter, float dt, pgm::LeafLen leaf, long long k, bool writer) {
   const int2 pr = v.pairs[k];
   const bool fresh = pr.x < 0;                     // appended by k_requery: never evaluated yet
-  const int i = fresh ? ~pr.x : pr.x, j = pr.y;
-  const unsigned long long key1 = ((unsigned long long)(unsigned)i << 32) | (unsigned)j;
-  const unsigned long long key2 = ((unsigned long long)(unsigned)j << 32) | (unsigned)i;
-  Sphere A1, B1, A2, B2;
+  const int row = fresh ? ~pr.x : pr.x, col = pr.y & 0x7fffffff;
+  const unsigned long long key = ((unsigned long long)(unsigned)row << 32) | (unsigned)col;
+  Sphere A, B;
   if (iter > 0 && !fresh) {
-    // neither body has a timeline: nothing to carry, nothing that could have changed
-    if (!((v.touched_bits[i >> 5] >> (i & 31)) & 1u) && !((v.touched_bits[j >> 5] >> (j & 31)) & 1u)) return 0;
+    // neither body has a timeline: the visit sees the untouched states, like in iteration 0
+    if (!((v.touched_bits[row >> 5] >> (row & 31)) & 1u) && !((v.touched_bits[col >> 5] >> (col & 31)) & 1u)) return 0;
     // A visit depends only on the entries with SMALLER keys of its two bodies.  If none of those
     // appeared, changed or disappeared since the previous iteration, its outcome is the recorded
-    // one: carry it over instead of re-evaluating.  The second visit saw the first one's outcome
-    // directly (Gauss-Seidel), so that entry is excluded from its test.
-    const bool need1 = affected(v, src, i, key1, 0ull) || affected(v, src, j, key1, 0ull);
-    if (!need1) {
-      const bool need2 = affected(v, src, i, key2, key1) || affected(v, src, j, key2, key1);
-      int h2 = 0;
-      if (need2) {
-        h2 = visit_compute<Warp>(v, src, j, i, dt, leaf, 0ull, nullptr, nullptr, A2, B2);
-        if (h2 == 2) return -1;
-      }
+    // one: carry it over instead of re-evaluating.
+    if (!(affected(v, src, row, key) || affected(v, src, col, key))) {
       int hits = 0;
-      if (writer) {
-        const bool have_i = v.tl_cnt[src][i] != 0, have_j = v.tl_cnt[src][j] != 0;
-        if (have_i && have_j && carry_entry(v, src, dst, i, key1)) { carry_entry(v, src, dst, j, key1); hits++; }
-        if (!need2) {
-          if (have_i && have_j && carry_entry(v, src, dst, i, key2)) { carry_entry(v, src, dst, j, key2); hits++; }
-        } else if (h2) {
-          timeline_push(v, dst, j, key2, A2); timeline_push(v, dst, i, key2, B2); hits++;
-        }
-      }
+      if (writer && v.tl_cnt[src][row] != 0 && v.tl_cnt[src][col] != 0 && carry_entry(v, src, dst, row, key)) { carry_entry(v, src, dst, col, key); hits = 1; }
       return hits;
     }
   }
-  // visit (i, j) of row i, then visit (j, i) of row j on top of the first one's fresh outcome
-  Override oi, oj;
-  oi.present = false; oj.present = false; oi.key = key1; oj.key = key1;
-  const int h1 = visit_compute<Warp>(v, src, i, j, dt, leaf, 0ull, nullptr, nullptr, A1, B1);
-  if (h1 == 2) return -1;
-  if (h1) { set_override(&oi, key1, A1); set_override(&oj, key1, B1); }
-  const int h2 = visit_compute<Warp>(v, src, j, i, dt, leaf, key1, &oj, &oi, A2, B2);
-  if (h2 == 2) return -1;
+  const int h = visit_compute<Warp>(v, src, row, col, dt, leaf, A, B);
+  if (h == 2) return -1;
   if (writer) {
-    if (fresh) v.pairs[k].x = i;
-    if (h1) { timeline_push(v, dst, i, key1, A1); timeline_push(v, dst, j, key1, B1); }
-    if (h2) { timeline_push(v, dst, j, key2, A2); timeline_push(v, dst, i, key2, B2); }
+    if (fresh) v.pairs[k].x = row;
+    if (h) { timeline_push(v, dst, row, key, A); timeline_push(v, dst, col, key, B); }
   }
-  return h1 + h2;
+  return h;
 }
 
 __device__ __forceinline__ void d_eval(const LargeView &v, int src, int dst, int iter, float dt) {
@@ -946,28 +989,53 @@ __device__ __forceinline__ void d_check(const LargeView &v, int src, int dst, in
     if (v.tl_cnt[src][b] != v.tl_cnt[dst][b] && rem == 0xffffffffffffffffull && !any) rem = 0ull;      // overflowed counts: be safe
     v.tl_chg[dst][b] = rem;
     if (any || rem != 0xffffffffffffffffull) { v.flags->changed = 1; atomicOr(&v.dirty_bits[dst][b >> 5], 1u << (b & 31)); }
-    // envelope validation on the new timeline: every state the body takes must stay inside env[b]
+    // ball validation on the new timeline: every state the body takes in a phase must stay inside that phase's
+    // ball (fixed centre: the untouched state's midpoint; the radius grows).  Phase A = the states the visits of
+    // rows <= b see (the untouched state and the entries of those rows), phase B = what the later rows see (the
+    // last phase-A state once the body's own row has integrated it, and the entries of those rows).  A body at
+    // rest never integrates and has one ball only.
     const float4 p = v.pos_rest[b], q = v.vel_rad[b];
-    float need = 0.0f;
+    const bool at_rest = p.w != 0.0f;
+    float cA[3], vA[3], cB[3], vB[3];
+    entry_state(p, q, 0, dt, cA, vA);
+    const float3 mA = entry_mid(cA[0], cA[1], cA[2], vA[0], vA[1], vA[2], dt);
+    float3 mB = mA;
+    if (!at_rest) { entry_state(p, q, 1, dt, cB, vB); mB = entry_mid(cB[0], cB[1], cB[2], vB[0], vB[1], vB[2], dt); }
+    float need[2] = {0.0f, 0.0f};
+    unsigned long long lastA_key = 0ull;
+    int lastA = -1;
+    auto cover = [&](int ph, float px, float py, float pz, float vx, float vy, float vz) {
+      const float3 m = entry_mid(px, py, pz, vx, vy, vz, dt);
+      const float3 c0 = ph ? mB : mA;
+      const float dx = m.x - c0.x, dy = m.y - c0.y, dz = m.z - c0.z;
+      const float dev = sqrtf(dx * dx + dy * dy + dz * dz);
+      need[ph] = fmaxf(need[ph], (dev + entry_rho(q.w, px, py, pz, vx, vy, vz, dt)) * 1.0002f + 2.0e-6f);
+    };
     for (int k = 0; k < c1; k++) {
       const unsigned long long key = v.tl_key[dst][(size_t)b * kTimeline + k];
       const float4 tp = v.tl_pos[dst][(size_t)b * kTimeline + k], tv = v.tl_vel[dst][(size_t)b * kTimeline + k];
-      const float dx = tp.x - p.x, dy = tp.y - p.y, dz = tp.z - p.z;
-      const float dev = sqrtf(dx * dx + dy * dy + dz * dz);
-      const float sp = sqrtf(tv.x * tv.x + tv.y * tv.y + tv.z * tv.z);
-      const bool before_own_row = (long long)(key >> 32) <= (long long)b;
-      // before its own row the body will still be integrated once: one more displacement and speed bump
-      const float reach = before_own_row ? 2.0f * (sp + pgm::kGravity * dt) * dt : sp * dt;
-      need = fmaxf(need, (q.w + dev + reach) * 1.0002f + 2.0e-6f);
+      const bool phase_a = (long long)(key >> 32) <= (long long)b;
+      cover((phase_a || at_rest) ? 0 : 1, tp.x, tp.y, tp.z, tv.x, tv.y, tv.z);
+      if (phase_a && (lastA < 0 || key > lastA_key)) { lastA = k; lastA_key = key; }
     }
-    if (need > v.env[b]) {
+    if (lastA >= 0 && !at_rest) {
+      const float4 tp = v.tl_pos[dst][(size_t)b * kTimeline + lastA], tv = v.tl_vel[dst][(size_t)b * kTimeline + lastA];
+      V3 pp = v3(tp.x, tp.y, tp.z), vv = v3(tv.x, tv.y, tv.z);
+      pgm::integrate(pp, vv, dt);
+      cover(1, pp.x, pp.y, pp.z, vv.x, vv.y, vv.z);
+    }
+    for (int ph = 0; ph < 2; ph++) {
+      const int e = 2 * b + ph;
+      const float cur = v.env[e];
+      if (cur < 0.0f || !(need[ph] > cur)) continue;
       const float e_cap = v.grid->e_cap;
-      if (!(v.env[b] > e_cap) && need * 1.05f > e_cap) v.fast_list[atomicAdd(&v.flags->n_fast, 1u)] = b;   // joins the fast bodies
-      v.env[b] = need * 1.05f;
-      v.grown[b] = 1;
+      const float grown_to = need[ph] * 1.05f;
+      if (!(cur > e_cap) && grown_to > e_cap) v.fast_list[atomicAdd(&v.flags->n_fast, 1u)] = e;   // joins the fast entries
+      v.env[e] = grown_to;
+      v.grown[e] = 1;
       atomicAdd(&v.flags->grew, 1);
-      atomicMax(v.bbox + 6, f2o(need * 1.05f));      // largest envelope in the world, for k_requery's search radius
-      if (!(need < 1.0e15f)) v.flags->unsafe = 1;
+      atomicMax(v.bbox + 6, f2o(grown_to));      // largest ball in the world, for k_requery's search radius
+      if (!(need[ph] < 1.0e15f)) v.flags->unsafe = 1;
     }
   }
 }
@@ -1012,94 +1080,112 @@ __device__ __forceinline__ void d_clear_carry(const LargeView &v, int src, int d
   if ((threadIdx.x & 31) == 0 && carried) atomicAdd(&v.flags->n_carried, (unsigned long long)carried);   // (n_hits is being reset by this very kernel)
 }
 
-// Envelopes of a few bodies grew (a contact sped them up).  Find the candidate pairs they gain --
-// touching under the new envelopes but not under the ones the list was built with -- through the
-// existing grid and append them marked as fresh, so that the next iteration evaluates them (pairs
-// that were already listed keep their recorded outcomes).  If both bodies of a pair grew, the lower
-// index appends it.
-// The search of one grown body b, shared by `stride` threads (this one is number `lane` of them).
+// The balls of a few entries grew (a contact gave the body a state its phase ball was not sized for).  Find the
+// candidate visits they gain -- entry pairs touching under the new radii but not under the ones the list was
+// built with -- through the existing grid and append them marked as fresh, so that the next iteration evaluates
+// them (visits that were already listed keep their recorded outcomes).  If both entries of a pair grew, the
+// lower entry id appends it.
+// The search of one grown entry e, shared by `stride` threads (this one is number `lane` of them).
 // ByEntry = false: every thread takes whole cell runs (8 lanes, sparse cells: the runs' dependent loads are
-// in flight together); true (a block): the warps take the runs, the lanes of a warp the bodies inside a run --
+// in flight together); true (a block): the warps take the runs, the lanes of a warp the entries inside a run --
 // for wide searches and for dense cells (a settled world has dozens of bodies per floor cell).
 template <bool ByEntry>
-__device__ __forceinline__ void requery_body(const LargeView &v, const GridParams &g, int b, int lane, int stride) {
-  const float4 p = v.pos_rest[b];
-  const float eb = v.env[b], eb_old = v.env_prev[b];
-  auto consider = [&](int x, float4 cx) {
-    const float dx = p.x - cx.x, dyy = p.y - cx.y, dzz = p.z - cx.z;
+__device__ __forceinline__ void requery_entry(const LargeView &v, const GridParams &g, int e, int lane, int stride, float dt) {
+  const int b = e >> 1;
+  const float4 pb = v.pos_rest[b];
+  const bool rest_b = pb.w != 0.0f;
+  float c[3], vel[3];
+  entry_state(pb, v.vel_rad[b], e & 1, dt, c, vel);
+  const float3 m = entry_mid(c[0], c[1], c[2], vel[0], vel[1], vel[2], dt);
+  const float eb = v.env[e], eb_old = v.env_prev[e];
+  auto consider = [&](int ex, bool rest_x, float3 mx) {
+    const float dx = m.x - mx.x, dyy = m.y - mx.y, dzz = m.z - mx.z;
     const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
-    const float ex = v.env[x], ex_old = v.env_prev[x];
-    const float Tn = eb + ex, To = eb_old + ex_old;
+    const float ex_new = v.env[ex], ex_old = v.env_prev[ex];
+    const float Tn = eb + ex_new, To = eb_old + ex_old;
     if (!(d2 <= Tn * Tn) || d2 <= To * To) return;            // not a candidate, or already listed
-    if (v.grown[x] && x < b) return;                          // the other grown body appends it
-    const unsigned long long slot = atomicAdd(&v.flags->n_pairs, 1ull);
-    if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2(~min(b, x), max(b, x));   // ~i marks it fresh
-    else atomicExch(&v.flags->overflow_pairs, 1);
+    if (v.grown[ex] && ex < e) return;                        // the other grown entry appends it
+    int2 vis[2]; bool row_b[2];
+    const int nv = entry_pair_visits((unsigned)e, rest_b, (unsigned)ex, rest_x, vis, row_b);
+    for (int q = 0; q < nv; q++) {
+      const unsigned long long slot = atomicAdd(&v.flags->n_pairs, 1ull);
+      if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2(~vis[q].x, vis[q].y);   // ~row marks it fresh
+      else atomicExch(&v.flags->overflow_pairs, 1);
+    }
   };
-  // Partners the grid was sized for (envelope <= e_cap) can be up to eb + e_cap away: search that many
+  auto consider_sorted = [&](unsigned a) {
+    const float4 cx = v.sorted[a].crho;
+    const float4 wx = *reinterpret_cast<const float4 *>(&v.sorted[a].vx);
+    const unsigned idx = __float_as_uint(wx.w);
+    const int ex = (int)(idx & ~kRestBit);
+    if (ex == e || v.env[ex] > g.e_cap) return;               // (fast partners come from their list)
+    consider(ex, (idx & kRestBit) != 0u, entry_mid(cx.x, cx.y, cx.z, wx.x, wx.y, wx.z, dt));
+  };
+  // Partners the grid was sized for (radius <= e_cap) can be up to eb + e_cap away: search that many
   // cells in every direction.  Fast partners are few and are checked one by one from their list
-  // (which also holds bodies that outgrew e_cap this step).
+  // (which also holds entries that outgrew e_cap this step).
   const float need = (eb + g.e_cap) * g.inv_h * 1.001f;
   if (!(need <= (float)kMaxSearch)) {
-    for (int a = lane; a < v.n; a += stride) {
-      const int x = (int)v.sorted[a].idx;
-      if (x != b && !(v.env[x] > g.e_cap)) consider(x, v.sorted[a].cenv);
-    }
+    const int n_sorted = (int)v.cell_cnt[g.n_cells];
+    for (int a = lane; a < n_sorted; a += stride) consider_sorted((unsigned)a);
   } else {
-    // every thread takes whole x-runs of the (2R+1)^2 the search covers (9 for a body the grid was sized
-    // for), so their dependent loads -- cell table, cell contents, envelopes -- are in flight together
+    // every thread takes whole x-runs of the (2R+1)^2 the search covers (9 for an entry the grid was sized
+    // for), so their dependent loads -- cell table, cell contents, radii -- are in flight together
     const int R = max((int)ceilf(need), 1);
-    const int3 c = cell_coords(g, p.x, p.y, p.z);
+    const int3 cc = cell_coords(g, m.x, m.y, m.z);
     const int side = 2 * R + 1;
-    const int x0 = max(c.x - R, 0), x1 = min(c.x + R, g.dim[0] - 1);
+    const int x0 = max(cc.x - R, 0), x1 = min(cc.x + R, g.dim[0] - 1);
     const int r_first = ByEntry ? (lane >> 5) : lane, r_step = ByEntry ? max(stride >> 5, 1) : stride;
     const unsigned a_first = ByEntry ? (unsigned)(lane & 31) : 0u, a_step = ByEntry ? 32u : 1u;
     for (int r = r_first; r < side * side; r += r_step) {
-      const int y = c.y + r % side - R, z = c.z + r / side - R;
+      const int y = cc.y + r % side - R, z = cc.z + r / side - R;
       if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
       const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
       const unsigned a1 = v.cell_cnt[row + x1 + 1];
-      for (unsigned a = v.cell_cnt[row + x0] + a_first; a < a1; a += a_step) {
-        const int x = (int)v.sorted[a].idx;
-        if (x != b && !(v.env[x] > g.e_cap)) consider(x, v.sorted[a].cenv);
-      }
+      for (unsigned a = v.cell_cnt[row + x0] + a_first; a < a1; a += a_step) consider_sorted(a);
     }
   }
   const int nf = (int)v.flags->n_fast;
   for (int f = lane; f < nf; f += stride) {
-    const int x = v.fast_list[f];
-    if (x == b || !(v.env[x] > g.e_cap)) continue;
+    const int ex = v.fast_list[f];
+    if (ex == e || !(v.env[ex] > g.e_cap)) continue;
+    const int x = ex >> 1;
     const float4 px = v.pos_rest[x];
-    consider(x, make_float4(px.x, px.y, px.z, 0.0f));
+    float cx[3], vx[3];
+    entry_state(px, v.vel_rad[x], ex & 1, dt, cx, vx);
+    consider(ex, px.w != 0.0f, entry_mid(cx[0], cx[1], cx[2], vx[0], vx[1], vx[2], dt));
   }
 }
-__device__ __forceinline__ void d_requery(const LargeView &v, int src) {
+__device__ __forceinline__ void d_requery(const LargeView &v, int src, float dt) {
   const GridParams g = *v.grid;
-  const int nt = (int)v.flags->n_touched;
-  // Eight lanes per touched body whose search is the usual 9 short cell runs (each a chain of dependent
-  // loads: more bodies in flight beat more lanes per body).  A body that searches wider -- a fast one, or a
+  const int nt = 2 * (int)v.flags->n_touched;      // both phase entries of every touched body
+  // Eight lanes per grown entry whose search is the usual 9 short cell runs (each a chain of dependent
+  // loads: more entries in flight beat more lanes per entry).  One that searches wider -- a fast one, or a
   // straggler whose search covers most of the grid and falls back to the whole sorted array -- goes on a
   // list and gets a whole block (k_requery_wide): eight lanes walking 65 k bodies held the step up for 0.7 ms.
   constexpr int kGroup = 8;
   const int lane = threadIdx.x & (kGroup - 1);
   const int groups = (gridDim.x * blockDim.x) / kGroup;
-  // when only a few bodies grew (every iteration but the first) there is a block to spare for each of them
+  // when only a few entries grew (every iteration but the first) there is a block to spare for each of them
   const bool few = v.flags->grew < v.requery_few;
   const unsigned group_mask = 0xffu << (threadIdx.x & 24);
   for (int t = (blockIdx.x * blockDim.x + threadIdx.x) / kGroup; t < nt; t += groups) {
-    const int b = v.touched[t];
-    if (!v.grown[b]) continue;
-    const float need = (v.env[b] + g.e_cap) * g.inv_h * 1.001f;
+    const int e = 2 * v.touched[t >> 1] + (t & 1);
+    if (!v.grown[e]) continue;
+    const float need = (v.env[e] + g.e_cap) * g.inv_h * 1.001f;
     bool wide = few || !(need <= 1.0f);
     if (!wide) {
-      // ... and so does a body whose 27 cells hold many bodies (a settled world has dozens per floor cell):
+      // ... and so does one whose 27 cells hold many entries (a settled world has dozens per floor cell):
       // a lane would walk its runs for too long.  The lanes add up the lengths of their runs first.
-      const float4 p = v.pos_rest[b];
-      const int3 c = cell_coords(g, p.x, p.y, p.z);
-      const int x0 = max(c.x - 1, 0), x1 = min(c.x + 1, g.dim[0] - 1);
+      const int b = e >> 1;
+      float c[3], vel[3];
+      entry_state(v.pos_rest[b], v.vel_rad[b], e & 1, dt, c, vel);
+      const float3 m = entry_mid(c[0], c[1], c[2], vel[0], vel[1], vel[2], dt);
+      const int3 cc = cell_coords(g, m.x, m.y, m.z);
+      const int x0 = max(cc.x - 1, 0), x1 = min(cc.x + 1, g.dim[0] - 1);
       unsigned work = 0;
       for (int r = lane; r < 9; r += kGroup) {
-        const int y = c.y + r % 3 - 1, z = c.z + r / 3 - 1;
+        const int y = cc.y + r % 3 - 1, z = cc.z + r / 3 - 1;
         if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
         const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
         work += v.cell_cnt[row + x1 + 1] - v.cell_cnt[row + x0];
@@ -1108,22 +1194,22 @@ __device__ __forceinline__ void d_requery(const LargeView &v, int src) {
       wide = work > 96u;                        // (measured: C4 at step 110 and the settled C2 are both slower with 512)
     }
     if (wide) {
-      if (lane == 0) v.wide_list[atomicAdd(&v.flags->n_wide, 1u)] = b;
+      if (lane == 0) v.wide_list[atomicAdd(&v.flags->n_wide, 1u)] = e;
       continue;
     }
-    requery_body<false>(v, g, b, lane, kGroup);
+    requery_entry<false>(v, g, e, lane, kGroup, dt);
   }
 }
-__device__ __forceinline__ void d_requery_wide(const LargeView &v) {
+__device__ __forceinline__ void d_requery_wide(const LargeView &v, float dt) {
   const GridParams g = *v.grid;
   const int nw = (int)v.flags->n_wide;
-  for (int t = blockIdx.x; t < nw; t += gridDim.x) requery_body<true>(v, g, v.wide_list[t], (int)threadIdx.x, (int)blockDim.x);
+  for (int t = blockIdx.x; t < nw; t += gridDim.x) requery_entry<true>(v, g, v.wide_list[t], (int)threadIdx.x, (int)blockDim.x, dt);
 }
 __device__ __forceinline__ void d_requery_done(const LargeView &v) {
-  const int nt = (int)v.flags->n_touched;
+  const int nt = 2 * (int)v.flags->n_touched;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
-    const int b = v.touched[t];
-    if (v.grown[b]) { v.grown[b] = 0; v.env_prev[b] = v.env[b]; }
+    const int e = 2 * v.touched[t >> 1] + (t & 1);
+    if (v.grown[e]) { v.grown[e] = 0; v.env_prev[e] = v.env[e]; }
   }
 }
 
@@ -1137,8 +1223,8 @@ __global__ void __launch_bounds__(256) k_begin(LargeView v, int src, int dst, in
   d_clear_carry(v, src, dst, iter);
   d_select(v, src, iter, dt);
 }
-__global__ void k_requery(LargeView v, int src) { d_requery(v, src); }
-__global__ void k_requery_wide(LargeView v) { d_requery_wide(v); }
+__global__ void k_requery(LargeView v, int src, float dt) { d_requery(v, src, dt); }
+__global__ void k_requery_wide(LargeView v, float dt) { d_requery_wide(v, dt); }
 __global__ void k_requery_done(LargeView v) { d_requery_done(v); }
 
 // ---------------------------------------------------------------- 5. final state + pass-4 events
@@ -1183,7 +1269,8 @@ __global__ void k_reset_touched(LargeView v) {
   const int nt = (int)v.flags->n_touched;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     const int b = v.touched[t];
-    v.grown[b] = 0;
+    v.grown[2 * b] = 0;
+    v.grown[2 * b + 1] = 0;
     v.tl_cnt[0][b] = 0;
     v.tl_cnt[1][b] = 0;
     v.tl_chg[0][b] = 0xffffffffffffffffull;
@@ -1201,10 +1288,12 @@ __global__ void k_env_frozen(LargeView v, float dt) {
   float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f}, emax = 0.0f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < v.n; i += gridDim.x * blockDim.x) {
     const float4 p = v.pos_rest[i], q = v.vel_rad[i];
-    const float e = pgs::reach(q.w, q.x, q.y, q.z, dt);      // r + |v| dt: the predicate's own reach, nothing moves
-    v.env[i] = e;
-    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
-    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    // nothing moves between the visits of a frozen-state query: phase A entries only
+    const float e = entry_rho(q.w, p.x, p.y, p.z, q.x, q.y, q.z, dt);
+    const float3 m = entry_mid(p.x, p.y, p.z, q.x, q.y, q.z, dt);
+    reinterpret_cast<float2 *>(v.env)[i] = make_float2(e, -1.0f);
+    lo[0] = fminf(lo[0], m.x); lo[1] = fminf(lo[1], m.y); lo[2] = fminf(lo[2], m.z);
+    hi[0] = fmaxf(hi[0], m.x); hi[1] = fmaxf(hi[1], m.y); hi[2] = fmaxf(hi[2], m.z);
     emax = fmaxf(emax, e);
   }
   for (int o = 16; o > 0; o >>= 1) {
@@ -1223,7 +1312,8 @@ __global__ void k_pairs_exact(LargeView v, float dt, unsigned char *keep) {
   pgm::LeafLen leaf; leaf.lo = v.leaf_lo; leaf.hi = v.leaf_hi;
   const long long np = (long long)min((unsigned long long)v.pairs_cap, v.flags->n_pairs);
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < np; k += (long long)gridDim.x * blockDim.x) {
-    const int2 pr = v.pairs[k];
+    int2 pr = v.pairs[k];
+    if (pr.y < 0 || !(pr.x < pr.y)) { keep[k] = 0; continue; }      // the gate rejected it / the second visit of a pair whose lower body rests
     const float4 pa = v.pos_rest[pr.x], qa = v.vel_rad[pr.x], pb = v.pos_rest[pr.y], qb = v.vel_rad[pr.y];
     const V3 cA = v3(0.0f + pa.x, 0.0f + pa.y, 0.0f + pa.z), cB = v3(0.0f + pb.x, 0.0f + pb.y, 0.0f + pb.z);
     const V3 vA = v3(qa.x, qa.y, qa.z), vB = v3(qb.x, qb.y, qb.z);
@@ -1276,13 +1366,13 @@ static void lw_accumulate(PgLarge *w, int kid) {
 }
 
 // build grid + candidate pairs from v.env / current positions
-static int lw_build_pairs(PgLarge *w) {
+static int lw_build_pairs(PgLarge *w, float dt) {
   LargeView &v = w->v;
   k_grid_params<<<1, 1, 0, w->stream>>>(v);
   w->launches++;
   PG_CUDA(cudaMemsetAsync(v.cell_cnt, 0, sizeof(unsigned) * ((size_t)v.cells_cap + 1), w->stream));
   PG_CUDA(cudaMemsetAsync(&v.flags->n_pairs, 0, sizeof(unsigned long long), w->stream));
-  LW_LAUNCH(w, K_CELLS, k_cell_count, lw_grid(w, v.n, 256), 256, v);
+  LW_LAUNCH(w, K_CELLS, k_cell_count, lw_grid(w, 2 * v.n, 256), 256, v, dt);
   // no read-back of the grid: the scan is launched for the largest table the buffers hold (blocks past
   // n_cells see zeros), and a grid that could not be built raises flags->unsafe for the next read-back
   const int scan_blocks = (v.cells_cap + 1 + kScanBlock * kScanItems - 1) / (kScanBlock * kScanItems);
@@ -1292,8 +1382,8 @@ static int lw_build_pairs(PgLarge *w) {
   k_scan_add<<<scan_blocks, kScanBlock, 0, w->stream>>>(v);
   if (w->timing) cudaEventRecord(w->kev[K_SCAN][1], w->stream);
   w->launches += 3;
-  LW_LAUNCH(w, K_SCATTER, k_scatter, lw_grid(w, v.n, 256), 256, v);
-  LW_LAUNCH(w, K_PAIRS, k_pairs, lw_grid(w, v.n, kPairsBlock), kPairsBlock, v);
+  LW_LAUNCH(w, K_SCATTER, k_scatter, lw_grid(w, 2 * v.n, 256), 256, v, dt);
+  LW_LAUNCH(w, K_PAIRS, k_pairs, lw_grid(w, 2 * v.n, kPairsBlock), kPairsBlock, v, dt);
   PG_CUDA(cudaGetLastError());
   return PG_OK;
 }
@@ -1363,7 +1453,7 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   if (w->timing) cudaEventRecord(w->kev[K_PASS3][1], w->stream);
   w->last_proven = 1;
   w->last_iterations = 0;
-  int rc = lw_build_pairs(w);
+  int rc = lw_build_pairs(w, dt);
   if (rc) return rc;
   Flags f;
   rc = lw_read_flags(w, &f);            // pair count: sizes the eval grid, detects overflow
@@ -1373,7 +1463,7 @@ static int lw_step_once(PgLarge *w, float dt_in) {
     // k_pairs is a pure function of the grid: grow the buffer and run it again
     rc = lw_grow_pairs(w, f.n_pairs, 0);
     if (rc) return rc;
-    LW_LAUNCH(w, K_PAIRS, k_pairs, lw_grid(w, v.n, kPairsBlock), kPairsBlock, v);
+    LW_LAUNCH(w, K_PAIRS, k_pairs, lw_grid(w, 2 * v.n, kPairsBlock), kPairsBlock, v, dt);
     rc = lw_read_flags(w, &f);
     if (rc) return rc;
     lw_accumulate(w, K_PAIRS);
@@ -1408,8 +1498,8 @@ static int lw_step_once(PgLarge *w, float dt_in) {
     // candidates the grown envelopes add (on top of the NEW timelines); their bodies are marked dirty so
     // the next iteration re-evaluates them (warm start)
     if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][0], w->stream);
-    k_requery<<<wide_grid, 128, 0, w->stream>>>(v, dst);
-    k_requery_wide<<<wide_grid, 256, 0, w->stream>>>(v);
+    k_requery<<<wide_grid, 128, 0, w->stream>>>(v, dst, dt);
+    k_requery_wide<<<wide_grid, 256, 0, w->stream>>>(v, dt);
     if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][1], w->stream);
     w->launches += 2;
     rc = lw_read_flags(w, &f);
@@ -1434,8 +1524,8 @@ static int lw_step_once(PgLarge *w, float dt_in) {
         if (rc) return rc;
         PG_CUDA(cudaMemsetAsync(&v.flags->n_wide, 0, sizeof(unsigned), w->stream));
         if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][0], w->stream);
-        k_requery<<<wide_grid, 128, 0, w->stream>>>(v, src);
-        k_requery_wide<<<wide_grid, 256, 0, w->stream>>>(v);
+        k_requery<<<wide_grid, 128, 0, w->stream>>>(v, src, dt);
+        k_requery_wide<<<wide_grid, 256, 0, w->stream>>>(v, dt);
         if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][1], w->stream);
         w->launches += 2;
         rc = lw_read_flags(w, &f);
@@ -1518,8 +1608,10 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   v.stage_limit = getenv("PG_LARGE_SMALL_STAGES") ? 3 : (1 << 20);
   v.requery_few = getenv("PG_LARGE_REQUERY_FEW") ? atoi(getenv("PG_LARGE_REQUERY_FEW")) : 4096;
   v.pass3_split_min = getenv("PG_LARGE_PASS3_SPLIT_MIN") ? atoi(getenv("PG_LARGE_PASS3_SPLIT_MIN")) : 262144;
+  v.ecap_factor = getenv("PG_LARGE_ECAP_FACTOR") ? (float)atof(getenv("PG_LARGE_ECAP_FACTOR")) : 2.0f;
+  v.r_uniform = -1.0f;
   v.cells_cap = (int)std::min<size_t>(4 * n + 4096, (size_t)1 << 28);
-  v.pairs_cap = (long long)(4 * n + 65536);
+  v.pairs_cap = (long long)(8 * n + 65536);
   v.max_events = (int)std::max<size_t>(n / 4, 65536);
   PG_CUDA_NULL(cudaMalloc(&v.pos_rest, sizeof(float4) * n));
   PG_CUDA_NULL(cudaMalloc(&v.vel_rad, sizeof(float4) * n));
@@ -1529,7 +1621,7 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   PG_CUDA_NULL(cudaMalloc(&v.box_c, sizeof(float4) * (size_t)w->cap_static_total));
   PG_CUDA_NULL(cudaMalloc(&v.box_e, sizeof(float4) * (size_t)w->cap_static_total));
   PG_CUDA_NULL(cudaMalloc(&v.static_type, (size_t)w->cap_static_total));
-  PG_CUDA_NULL(cudaMalloc(&v.env, sizeof(float) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.env, sizeof(float) * 2 * n));
   PG_CUDA_NULL(cudaMalloc(&v.bbox, sizeof(unsigned) * 8));
   PG_CUDA_NULL(cudaMalloc(&v.grid, sizeof(GridParams)));
   PG_CUDA_NULL(cudaMalloc(&v.rstat, sizeof(float) * 8));
@@ -1540,24 +1632,24 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
     r0.valid = 0;
     PG_CUDA_NULL(cudaMemcpy(v.robust, &r0, sizeof(r0), cudaMemcpyHostToDevice));
   }
-  PG_CUDA_NULL(cudaMalloc(&v.fast_list, sizeof(int) * n));
-  PG_CUDA_NULL(cudaMalloc(&v.wide_list, sizeof(int) * n));
-  PG_CUDA_NULL(cudaMalloc(&v.cell_of, sizeof(unsigned) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.fast_list, sizeof(int) * 2 * n));
+  PG_CUDA_NULL(cudaMalloc(&v.wide_list, sizeof(int) * 2 * n));
+  PG_CUDA_NULL(cudaMalloc(&v.cell_of, sizeof(unsigned) * 2 * n));
   PG_CUDA_NULL(cudaMalloc(&v.cell_cnt, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.block_sums, sizeof(unsigned) * ((size_t)v.cells_cap / (kScanBlock * kScanItems) + 2)));
-  PG_CUDA_NULL(cudaMalloc(&v.sorted, sizeof(SortedBody) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.sorted, sizeof(SortedBody) * 2 * n));
   PG_CUDA_NULL(cudaMalloc(&v.pairs, sizeof(int2) * (size_t)v.pairs_cap));
   PG_CUDA_NULL(cudaMalloc(&v.active, sizeof(unsigned) * 2 * (size_t)v.pairs_cap));
-  PG_CUDA_NULL(cudaMalloc(&v.grown, n + 8));
-  PG_CUDA_NULL(cudaMemset(v.grown, 0, n + 8));
-  PG_CUDA_NULL(cudaMalloc(&v.env_prev, sizeof(float) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.grown, 2 * n + 8));
+  PG_CUDA_NULL(cudaMemset(v.grown, 0, 2 * n + 8));
+  PG_CUDA_NULL(cudaMalloc(&v.env_prev, sizeof(float) * 2 * n));
   PG_CUDA_NULL(cudaMalloc(&v.seen, sizeof(int) * n));
   PG_CUDA_NULL(cudaMalloc(&v.touched_bits, sizeof(unsigned) * (n / 32 + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.dirty_bits[0], sizeof(unsigned) * (n / 32 + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.dirty_bits[1], sizeof(unsigned) * (n / 32 + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.pushed_bits, sizeof(unsigned) * (n / 32 + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.touched, sizeof(int) * n));
-  PG_CUDA_NULL(cudaMalloc(&v.cell_rank, sizeof(unsigned) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.cell_rank, sizeof(unsigned) * 2 * n));
   for (int k = 0; k < 2; k++) {
     PG_CUDA_NULL(cudaMalloc(&v.tl_chg[k], sizeof(unsigned long long) * n));
     PG_CUDA_NULL(cudaMalloc(&v.tl_cnt[k], n + 8));
@@ -1668,6 +1760,7 @@ int pg_large_set(PgLarge *w, const PgBody *statics, int n_static, int n_spheres,
     }
   }
   v.n = n_spheres; v.ns = (int)pl.size(); v.restitution = restitution;
+  v.r_uniform = radius_or_null ? -1.0f : radius * 1.0f;
   v.n_static_total = n_static; v.n_boxes = n_boxes;
   if (!pl.empty()) {
     PG_CUDA(cudaMemcpy(v.planes, pl.data(), sizeof(float4) * pl.size(), cudaMemcpyHostToDevice));
@@ -1830,7 +1923,7 @@ long long pg_large_pairs(PgLarge *w, float dt_in, int32_t *out_ij, long long cap
   PG_CUDA(cudaMemsetAsync(v.rstat, 0, sizeof(float) * 8, w->stream));       // no running statistics here: plain bounding box
   k_env_frozen<<<lw_grid(w, v.n, 256), 256, 0, w->stream>>>(v, dt);
   w->launches++;
-  int rc = lw_build_pairs(w);
+  int rc = lw_build_pairs(w, dt);
   if (rc) return rc;
   Flags f;
   rc = lw_read_flags(w, &f);

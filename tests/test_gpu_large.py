@@ -145,14 +145,17 @@ def test_large_world_random_campaign(gpu_lib, oracle_lib):
         g.set(st, pos[0], vel[0], radius=radius, restitution=restitution)
         tag = (case, n, L, speed, restitution, float(dt))
         for s in range(12):
-            g.step(dt, 1)
+            try:
+                g.step(dt, 1)
+            except gpu_lib.PgUnproven:
+                # a crush of fast spheres can need more fixed-point iterations than the path allows; the step then
+                # returns PG_ERR_UNPROVEN -- loudly, never PG_OK -- and the case ends here
+                assert not g.exactness()["proven_exact"]
+                unproven.append(tag + (s, g.exactness()["iterations"]))
+                break
             oracle_lib.dll.ora_world_step_grid(o.h, dt, 1, 0)
             ex = g.exactness()
-            if not ex["proven_exact"]:
-                # a crush of fast spheres can need more fixed-point iterations than the path allows; it says so
-                #  and the case ends here
-                unproven.append(tag + (s, ex["iterations"]))
-                break
+            assert ex["proven_exact"], tag + (s,)
             P, V, R = g.download_state()
             r = o.read(1)
             assert gen.same_bits(P, r["position"]) and gen.same_bits(V, r["velocity"]) and np.array_equal(R != 0, r["at_rest"] != 0), tag + (s,)
@@ -160,7 +163,7 @@ def test_large_world_random_campaign(gpu_lib, oracle_lib):
             assert ge == oe, tag + (s, len(ge), len(oe))
             total += len(ge)
         g.close()
-    assert total > 2000 and len(unproven) <= 2, unproven
+    assert total > 2000 and len(unproven) == 0, unproven
 
 
 def test_large_world_multi_step_call(gpu_lib, oracle_lib):
@@ -235,4 +238,134 @@ def test_level_geometry_world_c5_style(gpu_lib, oracle_lib, monkeypatch, with_pl
             gp, op = g.get_players(), o.read(2)
             assert gen.state_equal(gp, op), s
     assert box_events > 0          # AABB-sphere contacts really happened
+    g.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# parity at the CONFIGURED sizes (BASELINE.json configs C2, C4, C5) against the oracle's grid-accelerated
+# restatement of the sequential sweep (ora_world_step_grid: same visits in the same order, proven equal to the
+# all-pairs loop in tests/test_oracle_vs_ref.py; it falls back to the all-pairs loop by itself when its bounds
+# are violated)
+# ------------------------------------------------------------------------------------------------
+
+def _compare_step(g, o, oracle_lib, tag):
+    g.step(DT, 1)
+    oracle_lib.dll.ora_world_step_grid(o.h, DT, 1, 0)
+    ex = g.exactness()
+    assert ex["proven_exact"], (tag, ex)
+    P, V, R = g.download_state()
+    r = o.read(1)
+    assert gen.same_bits(P, r["position"]) and gen.same_bits(V, r["velocity"]) and np.array_equal(R != 0, r["at_rest"] != 0), (tag, ex)
+    ge, oe = g.events(), o.events()
+    assert len(ge) == len(oe), (tag, len(ge), len(oe))
+    for f in ("a_class", "a_index", "b_class", "b_index"):
+        assert np.array_equal(ge[f], oe[f]), (tag, f)
+    return len(ge)
+
+
+def test_c2_full_size_three_steps_and_pair_set(gpu_lib, oracle_lib):
+    """Config C2 as BASELINE.json states it: one world, 65,536 spheres, L = 64.  Three steps bit for bit (state,
+    at_rest, contact events in solve order) and the broadphase pair set of the state after them."""
+    n, L = 65536, 64.0
+    pos, vel, st, o = _world(oracle_lib, n, L, 0)
+    g = gpu_lib.GpuLargeWorld(n, len(st))
+    g.set(st, pos, vel)
+    events = sum(_compare_step(g, o, oracle_lib, ("c2", s)) for s in range(3))
+    assert events > 1000
+    got = g.pairs(DT)
+    buf = np.zeros((max(4 * len(got), 1024), 2), np.int32)
+    cnt = oracle_lib.dll.ora_world_pairs(o.h, DT, 1, buf.ctypes.data_as(C.c_void_p), len(buf))
+    assert cnt == len(got) and np.array_equal(got, buf[:cnt])
+    g.close()
+
+
+def test_c2_full_size_from_a_thermalised_state(gpu_lib, oracle_lib):
+    """C2 after 300 steps on the device: spheres have fallen up to 44 m, bounced back and collide at tens of m/s
+    (the regime in which the previous candidate test listed hundreds of neighbours per body and the fixed point
+    needed 22 iterations).  The oracle is started from the downloaded state; two more steps, bit for bit."""
+    n, L = 65536, 64.0
+    pos, vel = scenes.sphere_worlds(1, n, L, first_world=0)
+    st = scenes.plane_bodies(scenes.box_planes(L))
+    g = gpu_lib.GpuLargeWorld(n, len(st))
+    g.set(st, pos[0], vel[0])
+    g.step(DT, 300)
+    P, V, R = g.download_state()
+    assert np.isfinite(P).all() and float(np.linalg.norm(V, axis=1).max()) > 20.0
+    dyn = scenes.sphere_bodies(P, V)
+    dyn["at_rest"] = R
+    o = ora.World(oracle_lib, st, dyn)
+    events = sum(_compare_step(g, o, oracle_lib, ("c2-thermal", s)) for s in range(2))
+    assert events > 1000
+    g.close()
+
+
+def test_c4_full_size_one_step(gpu_lib, oracle_lib):
+    """Config C4: one world, 4,194,304 spheres, L = 256: one step, every body and every contact event."""
+    n, L = 4194304, 256.0
+    pos, vel, st, o = _world(oracle_lib, n, L, 0)
+    g = gpu_lib.GpuLargeWorld(n, len(st))
+    g.set(st, pos, vel)
+    events = _compare_step(g, o, oracle_lib, "c4")
+    assert events > 20000
+    g.close()
+
+
+def test_c5_full_size_one_step_regions(gpu_lib, oracle_lib):
+    """Config C5: 1,048,576 spheres + the slab level (static AABBs with scene nodes) + the player capsule,
+    one step on the device at full size.  The CPU sweep over 1 M spheres x thousands of slabs takes hours, so
+    the check is regional: all spheres (array order kept) and all statics (array order kept) that reach into a
+    box are stepped by the oracle's all-pairs sweep, and the spheres well inside it -- farther from its faces
+    than any chain of contacts can carry in one step -- must come out with the same bits.  Pass 3 of EVERY
+    sphere is independent of the others and is covered by a second, random sample."""
+    n, L = 1048576, 160.0
+    statics, pos, vel, players = scenes.level_world(n, L, seed_world=0, with_player=True)
+    g = gpu_lib.GpuLargeWorld(n, len(statics))
+    g.set(gpu_lib.prepare(statics), pos, vel)
+    pl = gpu_lib.prepare(players)
+    pl["node_xform"][0] = gpu_lib.node_transform(pl["position"][0], pl["rotation"][0], pl["scale"][0], pl["parent_xform"][0])
+    g.set_players(pl)
+    g.step(DT, 1)
+    assert g.exactness()["proven_exact"]
+    P, V, R = g.download_state()
+    ev = g.events()
+    checked = 0
+    for centre, half, margin in (((0.0, 4.0, 0.0), 9.0, 3.0), ((40.0, 60.0, -30.0), 9.0, 3.0)):
+        c = np.array(centre, np.float32)
+        inside = np.all(np.abs(pos - c) <= half, axis=1)
+        deep = np.all(np.abs(pos - c) <= half - margin, axis=1)
+        idx = np.nonzero(inside)[0]
+        # statics: the six planes, and the slabs whose box comes within reach of the region
+        sc = statics["node_xform"][:, 12:15] + statics["shape"][:, 0:3]
+        se = statics["shape"][:, 3:6]
+        near = np.all(np.abs(sc - c) <= se + half + 1.0, axis=1) | (statics["collider_type"] == scenes.COLLIDER_PLANE)
+        sidx = np.nonzero(near)[0]
+        o = ora.World(oracle_lib, statics[sidx], scenes.sphere_bodies_with_nodes(pos[idx], vel[idx]), None)
+        o.step(DT, 1, 1)
+        r = o.read(1)
+        d = deep[idx]
+        assert d.sum() > 200
+        assert gen.same_bits(P[idx][d], r["position"][d]) and gen.same_bits(V[idx][d], r["velocity"][d]) and \
+            np.array_equal(R[idx][d] != 0, r["at_rest"][d] != 0), centre
+        # contact events whose spheres are all deep: the same sequence (array order is kept inside the region, so
+        # the region's solve order restricted to those bodies is the world's)
+        deep_global = set(idx[d].tolist())
+
+        def keep(cls_a, ia, cls_b, ib):
+            spheres = [i for c_, i in ((cls_a, ia), (cls_b, ib)) if c_ == 1]
+            return len(spheres) > 0 and all(i in deep_global for i in spheres)
+        want = []
+        for e in o.events():
+            ia = int(sidx[e["a_index"]]) if e["a_class"] == 0 else int(idx[e["a_index"]])
+            ib = int(sidx[e["b_index"]]) if e["b_class"] == 0 else int(idx[e["b_index"]])
+            if keep(int(e["a_class"]), ia, int(e["b_class"]), ib):
+                want.append((int(e["a_class"]), ia, int(e["b_class"]), ib))
+        got = [(int(e["a_class"]), int(e["a_index"]), int(e["b_class"]), int(e["b_index"])) for e in ev
+               if e["a_class"] != 2 and e["b_class"] != 2 and keep(int(e["a_class"]), int(e["a_index"]), int(e["b_class"]), int(e["b_index"]))]
+        assert got == want, (centre, len(got), len(want))
+        checked += int(d.sum())
+    assert checked > 500
+    # the player capsule against the level (passes 1-2): the any-collider kernel's result against the oracle's
+    o = ora.World(oracle_lib, statics, None, pl)
+    o.step(DT, 1, 1)
+    assert gen.state_equal(g.get_players(), o.read(2))
     g.close()
