@@ -37,9 +37,15 @@
 //      one thread per visit, and hands the rare long interval searches to k_eval_hard (a block per
 //      visit); k_check compares the timelines of the bodies involved.
 //                                                          [k_begin, k_eval, k_eval_hard, k_check]
-//   4. a contact gives a body states its phase balls were not sized for; k_check re-validates the two radii
-//      against the new timelines, and if one grew, the visits it adds are appended and the iteration continues
-//      warm.                                              [k_check, k_requery, k_requery_wide]
+//   4. a contact gives a body a state its phase entry does not describe (it leaves the contact point in a new
+//      direction).  Every state that appears in a timeline gets a ball of its own -- same midpoint construction,
+//      so it stays small -- which is (a) linked into a second, incremental cell structure over the same grid and
+//      (b) queried against the cell-sorted untouched entries and against the state balls linked so far; entry
+//      pairs that touch name the visits to add (deduplicated: visits the untouched entries already listed are
+//      recognised by repeating their ball test, the others go through a hash set).  Key ranges are ignored, so
+//      the list is a superset of every visit that could fire under ANY combination of the states seen so far,
+//      and at the fixed point it contains every visit the final timelines could fire.
+//                                                         [k_check, k_states_insert, k_states_query]
 //   5. final state = timeline tail, integrated if the body's own row came after it; the fixed
 //      point's per-body bookkeeping is put back for the bodies that used it.
 //                                                                    [k_finalize, k_reset_touched]
@@ -64,7 +70,7 @@ constexpr int kMaxIter = 256;       // a dependency chain of the sweep is resolv
 constexpr unsigned kFullMask = 0xffffffffu;
 
 enum { K_PASS3 = 0, K_BOUNDS, K_CELLS, K_SCAN, K_SCATTER, K_PAIRS, K_EVAL, K_CHECK, K_FINAL, K_COUNT };
-const char *kKernelNames[K_COUNT] = {"k_pass3", "k_requery", "k_cell_count", "k_scan", "k_scatter", "k_pairs", "k_eval", "k_check", "k_finalize"};
+const char *kKernelNames[K_COUNT] = {"k_pass3", "k_states", "k_cell_count", "k_scan", "k_scatter", "k_pairs", "k_eval", "k_check", "k_finalize"};
 
 struct GridParams {
   float org[3];
@@ -72,7 +78,9 @@ struct GridParams {
   int dim[3];
   int n_cells;
   int ok;
-  float e_cap;            // ball radius the cell edge is sized for; entries beyond it are "fast" (few) and search wider
+  float e_cap;            // ball radius the cell edge is sized for; entries beyond it search wider (k_pairs)
+  float e_cap2;           // radius bound of the balls linked into the second cell structure (state balls, and the untouched entries
+                          // beyond e_cap): a query searches that far; the few beyond it sit on a list every query walks
 };
 
 // Running statistics that keep the grid sized for the BULK of the bodies whatever a few stragglers do
@@ -85,7 +93,12 @@ struct Robust {
 
 struct Flags {
   int changed;            // fixed point: some timeline differs from the previous iteration
-  int grew;               // an envelope had to grow
+  int overflow_balls;     // state-ball buffer full
+  int overflow_vset;      // visit hash set full
+  unsigned n_balls;       // state balls linked so far this step
+  unsigned balls_begin;   // ... of which [balls_begin, n_balls) appeared in the current iteration
+  unsigned n_huge;        // balls beyond e_cap2 (on the list every query walks)
+  unsigned n_vset;        // visits in the hash set
   int overflow_pairs;
   int overflow_timeline;
   int unsafe;             // non-finite state or an envelope the grid cannot hold
@@ -93,10 +106,8 @@ struct Flags {
   unsigned long long n_hits;
   unsigned long long n_carried;   // hits d_clear_carry copied this iteration; folded into n_hits by k_check
   unsigned n_touched;
-  unsigned n_fast;        // bodies on the fast list
   unsigned n_active;      // candidate pairs the selection (k_begin) handed to k_eval this iteration
   unsigned n_hard;        // of those, pairs k_eval passed on to k_eval_hard (long interval searches)
-  unsigned n_wide;        // grown bodies k_requery passed on to k_requery_wide
   unsigned n_pass3;       // bodies k_pass3 passed on to k_pass3_exact
 };
 
@@ -131,7 +142,6 @@ __device__ __forceinline__ void entry_state(const float4 p, const float4 q, int 
 struct LargeView {
   int n, ns;
   int stage_limit;                   // entries the per-block shared-memory stages may hold (tests shrink it to reach the overflow paths)
-  int requery_few;                   // k_requery: below this many grown bodies each gets a block
   int pass3_split_min;               // worlds of at least this many bodies run pass 3 as probe + dense exact kernel
   float4 *pos_rest, *vel_rad;        // state (in/out), body order = reference array order
   float4 *planes;                    // the static PLANES, array order
@@ -148,12 +158,20 @@ struct LargeView {
   float *env;                        // [2n] ball radius per phase entry (entry e = 2 body + phase); < 0: no such entry (body at rest has no phase B)
   float r_uniform;                   // >= 0: every sphere has this world radius (no per-body look-up in k_pairs)
   float ecap_factor;                 // grid sizing: cells hold balls up to ecap_factor x the mean radius
+  float ecap2_factor;                // k_requery's partner bound e_cap2 = ecap2_factor x e_cap
   // reductions
   unsigned *bbox;                    // 6 ordered-uint encodings: min xyz, max xyz ; [6] = max env
   float *rstat;                      // [8] sums over the bodies inside the previous robust box: x y z |dx| |dy| |dz| env count
   Robust *robust;
-  int *fast_list;                    // [2n] entries whose radius exceeds grid->e_cap
-  int *wide_list;                    // [2n] grown entries whose search is wider than 27 cells (k_requery_wide)
+  // state balls (fixed point, step 4): append-only per step
+  float4 *ball_c;                    // [balls_cap] midpoint xyz, radius
+  uint2 *ball_e;                     // [balls_cap] .x = entry id (2 body + phase) | kRestBit, .y = next ball of its cell (0xffffffff: none)
+  int balls_cap;
+  unsigned *head2;                   // [cells_cap] first ball of every cell of the second structure (0xffffffff: empty)
+  int *huge_list;                    // [huge_cap] balls beyond grid->e_cap2
+  int huge_cap;
+  unsigned long long *vset;          // visit hash set: keys (row << 32 | col), 0xff..ff = empty slot
+  unsigned long long vset_mask;
   GridParams *grid;
   // grid
   unsigned *cell_of;                 // [2n] (0xffffffff: entry not in the grid)
@@ -178,8 +196,6 @@ struct LargeView {
                                       // was to decide about again: k_check must compare its timelines
   int *touched;                       // bodies that ever received a timeline entry this step
   unsigned *cell_rank;                // [2n] rank of an entry inside its cell (returned by the counting atomic)
-  unsigned char *grown;               // [2n] the entry's radius grew during the current fixed point
-  float *env_prev;                   // [2n] radius the current candidate list was built with
   unsigned long long *tl_key[2];
   float4 *tl_pos[2], *tl_vel[2];
   Flags *flags;
@@ -386,13 +402,10 @@ __device__ __forceinline__ void pass3_impl(const LargeView &v, float dt, int ste
       mB = entry_mid(cB[0], cB[1], cB[2], vB[0], vB[1], vB[2], dt);
     }
     reinterpret_cast<float2 *>(v.env)[i] = make_float2(rhoA, rhoB);
-    reinterpret_cast<float2 *>(v.env_prev)[i] = make_float2(rhoA, rhoB);
     const float e = fmaxf(rhoA, rhoB);
     if (full_reset) {
       // per-step bookkeeping of the fixed point: only bodies that get a timeline entry ever change it, and
       // k_reset_touched puts those back at the end of the step (23 B per body and step not written here)
-      v.grown[2 * i] = 0;
-      v.grown[2 * i + 1] = 0;
       v.tl_cnt[0][i] = 0;
       v.tl_cnt[1][i] = 0;
       v.tl_chg[0][i] = 0xffffffffffffffffull;
@@ -485,7 +498,8 @@ __global__ void k_grid_params(LargeView v) {
   }
   for (int k = 0; k < 3; k++) g.org[k] = lo[k] - 0.5f * h * 0.001f;
   g.inv_h = 1.0f / h;
-  g.e_cap = 0.5f * h;                          // the largest envelope the 27-cell search serves: 2 env <= h (25 % above the sizing envelope)
+  g.e_cap = 0.5f * h;                          // the largest ball the 27-cell search serves: 2 rho <= h (25 % above the sizing radius)
+  g.e_cap2 = v.ecap2_factor * g.e_cap;
   *v.grid = g;
 }
 
@@ -495,6 +509,63 @@ __device__ __forceinline__ int3 cell_coords(const GridParams &g, float x, float 
   c.y = min(max((int)((y - g.org[1]) * g.inv_h), 0), g.dim[1] - 1);
   c.z = min(max((int)((z - g.org[2]) * g.inv_h), 0), g.dim[2] - 1);
   return c;
+}
+
+constexpr unsigned kRestBit = 0x80000000u;      // SortedBody::idx, ball_e.x: the entry's body is at rest (it has no phase B)
+constexpr unsigned kNoBall = 0xffffffffu;
+constexpr unsigned long long kSlotEmpty = 0xffffffffffffffffull, kSlotTomb = 0xfffffffffffffffeull;
+
+// Warp-aggregated increment of a hot counter: the lanes that are here together take one atomic between them.
+__device__ __forceinline__ unsigned agg_inc(unsigned *ctr) {
+  const unsigned m = __activemask();
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs((int)m) - 1;
+  unsigned base = 0;
+  if ((int)lane == leader) base = atomicAdd(ctr, (unsigned)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + (unsigned)__popc(m & ((1u << lane) - 1u));
+}
+__device__ __forceinline__ unsigned long long agg_inc64(unsigned long long *ctr) {
+  const unsigned m = __activemask();
+  const unsigned lane = threadIdx.x & 31u;
+  const int leader = __ffs((int)m) - 1;
+  unsigned long long base = 0;
+  if ((int)lane == leader) base = atomicAdd(ctr, (unsigned long long)__popc(m));
+  base = __shfl_sync(m, base, leader);
+  return base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+}
+
+// Link a ball into the second cell structure (same cells as the sorted copy; a list per cell, pushed at the
+// head).  Insertions and queries never run in the same kernel.
+__device__ __forceinline__ void ball_insert(const LargeView &v, const GridParams &g, float3 m, float rho, unsigned ent_flags) {
+  if (!(fabsf(m.x) < 1.0e15f && fabsf(m.y) < 1.0e15f && fabsf(m.z) < 1.0e15f && rho < 1.0e15f)) { atomicExch(&v.flags->unsafe, 1); return; }
+  const unsigned idx = agg_inc(&v.flags->n_balls);
+  if (idx >= (unsigned)v.balls_cap) { atomicExch(&v.flags->overflow_balls, 1); return; }
+  v.ball_c[idx] = make_float4(m.x, m.y, m.z, rho);
+  if (rho > g.e_cap2) {                          // beyond what a query's cell search covers: the list every query walks
+    const unsigned hslot = atomicAdd(&v.flags->n_huge, 1u);
+    if (hslot < (unsigned)v.huge_cap) v.huge_list[hslot] = (int)idx; else atomicExch(&v.flags->overflow_balls, 1);
+    v.ball_e[idx] = make_uint2(ent_flags, kNoBall);
+    return;
+  }
+  const int3 c = cell_coords(g, m.x, m.y, m.z);
+  const unsigned cell = (unsigned)((c.z * g.dim[1] + c.y) * g.dim[0] + c.x);
+  v.ball_e[idx] = make_uint2(ent_flags, atomicExch(&v.head2[cell], idx));
+}
+
+// Visit hash set (open addressing, linear probing): returns the slot if `key` was inserted, -1 if it was there.
+__device__ __forceinline__ long long vset_insert(const LargeView &v, unsigned long long key) {
+  unsigned long long h = key * 0x9E3779B97F4A7C15ull;
+  h ^= h >> 29;
+  unsigned long long slot = h & v.vset_mask;
+  for (int probe = 0; probe < 256; probe++) {
+    const unsigned long long old = atomicCAS(&v.vset[slot], kSlotEmpty, key);
+    if (old == kSlotEmpty) { agg_inc(&v.flags->n_vset); return (long long)slot; }
+    if (old == key) return -1;
+    slot = (slot + 1) & v.vset_mask;
+  }
+  atomicExch(&v.flags->overflow_vset, 1);
+  return -1;
 }
 
 // ---------------------------------------------------------------- 2. counting sort of the phase entries into cells
@@ -512,7 +583,9 @@ __global__ void k_cell_count(LargeView v, float dt) {
     const unsigned cell = (unsigned)((cc.z * g.dim[1] + cc.y) * g.dim[0] + cc.x);
     v.cell_of[e] = cell;
     v.cell_rank[e] = atomicAdd(v.cell_cnt + cell, 1u);
-    if (rho > g.e_cap) v.fast_list[atomicAdd(&v.flags->n_fast, 1u)] = e;
+    // an entry whose ball exceeds what the 27-cell search of a state-ball query allows for is also linked into
+    // the second structure, where queries search wider
+    if (rho > g.e_cap) ball_insert(v, g, m, rho, (unsigned)e | (v.pos_rest[i].w != 0.0f ? kRestBit : 0u));
   }
 }
 
@@ -597,9 +670,8 @@ __global__ void k_scatter(LargeView v, float dt) {
 // sorted array for one so fast that its search would cover most of the grid anyway.
 constexpr int kMaxSearch = 12;
 constexpr int kPairsBlock = 128;
+constexpr int kPairsPrefetch = 2;      // partners whose two 16-byte halves are in flight together
 constexpr int kPairsStage = 1024;       // visits a block collects in shared memory between two flushes
-constexpr unsigned kRestBit = 0x80000000u;      // SortedBody::idx: the entry's body is at rest (it has no phase B)
-
 // Which visits does the touching entry pair (ea, eb) stand for?  (header comment, step 2)  Returns their number
 // and (row, col) of each; `swap[k]`: the row body of visit k is eb's.
 __device__ __forceinline__ int entry_pair_visits(unsigned ea, bool rest_a, unsigned eb, bool rest_b, int2 *out, bool *row_is_b) {
@@ -618,6 +690,14 @@ __device__ __forceinline__ int entry_pair_visits(unsigned ea, bool rest_a, unsig
   if (!(ib < ia)) return 0;
   out[0] = make_int2(ia, ib); row_is_b[0] = false;
   return 1;
+}
+
+// (out of line: the gate's registers stay out of the search loop, which is bound by the latency of its loads)
+__device__ __noinline__ bool listing_gate_rejects(float4 cr, float4 wr, float4 cc, float4 wc, float rs, float dt) {
+  const float na2 = __fmaf_rn(wr.x, wr.x, __fmaf_rn(wr.y, wr.y, wr.z * wr.z));
+  const float nb2 = __fmaf_rn(wc.x, wc.x, __fmaf_rn(wc.y, wc.y, wc.z * wc.z));
+  const float vsum = sqrtf(2.0f * (na2 + nb2)) * 1.0001f;          // >= |vA| + |vB|
+  return pgs::pair_gate_rejects(v3(cr.x, cr.y, cr.z), v3(wr.x, wr.y, wr.z), v3(cc.x, cc.y, cc.z), v3(wc.x, wc.y, wc.z), rs, vsum, dt);
 }
 
 // One thread per entry (in cell order, so neighbouring threads read neighbouring cells); every thread
@@ -647,7 +727,6 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs(LargeView v, float dt) {
       const unsigned ea = __float_as_uint(wa.w) & ~kRestBit;
       const bool rest_a = (__float_as_uint(wa.w) & kRestBit) != 0u;
       const float3 ma = entry_mid(ca.x, ca.y, ca.z, wa.x, wa.y, wa.z, dt);
-      const float na2 = __fmaf_rn(wa.x, wa.x, __fmaf_rn(wa.y, wa.y, wa.z * wa.z));
       const int3 c = cell_coords(g, ma.x, ma.y, ma.z);
       const float need = 2.0f * ca.w * g.inv_h * 1.001f;
       const int R = need <= 1.0f ? 1 : (need <= (float)kMaxSearch ? (int)ceilf(need) : 0);
@@ -656,15 +735,15 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs(LargeView v, float dt) {
       auto run = [&](unsigned b0, unsigned b1) {
         // (the loads of up to four partners are issued before the first is looked at: the kernel is bound by
         // the latency of its dependent loads, not by instructions or bytes)
-        float4 nb[4], nw[4];
-        for (unsigned bb = b0; bb < b1; bb += 4) {
+        float4 nb[kPairsPrefetch], nw[kPairsPrefetch];
+        for (unsigned bb = b0; bb < b1; bb += kPairsPrefetch) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < kPairsPrefetch; u++) {
           const SortedBody *sb = v.sorted + min(bb + u, b1 - 1);
           nb[u] = sb->crho; nw[u] = *reinterpret_cast<const float4 *>(&sb->vx);
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < kPairsPrefetch; u++) {
           const unsigned b = bb + u;
           if (b >= b1) break;
           const float4 cb = nb[u], wb = nw[u];
@@ -687,10 +766,7 @@ __global__ void __launch_bounds__(kPairsBlock) k_pairs(LargeView v, float dt) {
             bool rej = false;
             if (gate_ok) {
               const float rs = v.r_uniform >= 0.0f ? v.r_uniform + v.r_uniform : v.vel_rad[vis[q].x].w + v.vel_rad[vis[q].y].w;
-              const float nb2 = __fmaf_rn(wb.x, wb.x, __fmaf_rn(wb.y, wb.y, wb.z * wb.z));
-              const float vsum = sqrtf(2.0f * (na2 + nb2)) * 1.0001f;          // >= |vA| + |vB|
-              const V3 pa3 = v3(ca.x, ca.y, ca.z), va3 = v3(wa.x, wa.y, wa.z), pb3 = v3(cb.x, cb.y, cb.z), vb3 = v3(wb.x, wb.y, wb.z);
-              rej = row_b[q] ? pgs::pair_gate_rejects(pb3, vb3, pa3, va3, rs, vsum, dt) : pgs::pair_gate_rejects(pa3, va3, pb3, vb3, rs, vsum, dt);
+              rej = row_b[q] ? listing_gate_rejects(cb, wb, ca, wa, rs, dt) : listing_gate_rejects(ca, wa, cb, wb, rs, dt);
             }
             const int2 pr = make_int2(vis[q].x, rej ? (int)((unsigned)vis[q].y | 0x80000000u) : vis[q].y);
             const unsigned slot = atomicAdd(&s_cnt, 1u);
@@ -958,7 +1034,7 @@ __device__ __forceinline__ void d_check(const LargeView &v, int src, int dst, in
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     v.flags->n_hits += v.flags->n_carried; v.flags->n_carried = 0ull;
     v.flags->n_active = 0u; v.flags->n_hard = 0u;      // for the next iteration's k_begin (zero at step start)
-    v.flags->n_wide = 0u;                               // for this iteration's k_requery
+    v.flags->balls_begin = v.flags->n_balls;           // this iteration's state balls start here (k_states_insert)
   }
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     const int b = v.touched[t];
@@ -989,54 +1065,6 @@ __device__ __forceinline__ void d_check(const LargeView &v, int src, int dst, in
     if (v.tl_cnt[src][b] != v.tl_cnt[dst][b] && rem == 0xffffffffffffffffull && !any) rem = 0ull;      // overflowed counts: be safe
     v.tl_chg[dst][b] = rem;
     if (any || rem != 0xffffffffffffffffull) { v.flags->changed = 1; atomicOr(&v.dirty_bits[dst][b >> 5], 1u << (b & 31)); }
-    // ball validation on the new timeline: every state the body takes in a phase must stay inside that phase's
-    // ball (fixed centre: the untouched state's midpoint; the radius grows).  Phase A = the states the visits of
-    // rows <= b see (the untouched state and the entries of those rows), phase B = what the later rows see (the
-    // last phase-A state once the body's own row has integrated it, and the entries of those rows).  A body at
-    // rest never integrates and has one ball only.
-    const float4 p = v.pos_rest[b], q = v.vel_rad[b];
-    const bool at_rest = p.w != 0.0f;
-    float cA[3], vA[3], cB[3], vB[3];
-    entry_state(p, q, 0, dt, cA, vA);
-    const float3 mA = entry_mid(cA[0], cA[1], cA[2], vA[0], vA[1], vA[2], dt);
-    float3 mB = mA;
-    if (!at_rest) { entry_state(p, q, 1, dt, cB, vB); mB = entry_mid(cB[0], cB[1], cB[2], vB[0], vB[1], vB[2], dt); }
-    float need[2] = {0.0f, 0.0f};
-    unsigned long long lastA_key = 0ull;
-    int lastA = -1;
-    auto cover = [&](int ph, float px, float py, float pz, float vx, float vy, float vz) {
-      const float3 m = entry_mid(px, py, pz, vx, vy, vz, dt);
-      const float3 c0 = ph ? mB : mA;
-      const float dx = m.x - c0.x, dy = m.y - c0.y, dz = m.z - c0.z;
-      const float dev = sqrtf(dx * dx + dy * dy + dz * dz);
-      need[ph] = fmaxf(need[ph], (dev + entry_rho(q.w, px, py, pz, vx, vy, vz, dt)) * 1.0002f + 2.0e-6f);
-    };
-    for (int k = 0; k < c1; k++) {
-      const unsigned long long key = v.tl_key[dst][(size_t)b * kTimeline + k];
-      const float4 tp = v.tl_pos[dst][(size_t)b * kTimeline + k], tv = v.tl_vel[dst][(size_t)b * kTimeline + k];
-      const bool phase_a = (long long)(key >> 32) <= (long long)b;
-      cover((phase_a || at_rest) ? 0 : 1, tp.x, tp.y, tp.z, tv.x, tv.y, tv.z);
-      if (phase_a && (lastA < 0 || key > lastA_key)) { lastA = k; lastA_key = key; }
-    }
-    if (lastA >= 0 && !at_rest) {
-      const float4 tp = v.tl_pos[dst][(size_t)b * kTimeline + lastA], tv = v.tl_vel[dst][(size_t)b * kTimeline + lastA];
-      V3 pp = v3(tp.x, tp.y, tp.z), vv = v3(tv.x, tv.y, tv.z);
-      pgm::integrate(pp, vv, dt);
-      cover(1, pp.x, pp.y, pp.z, vv.x, vv.y, vv.z);
-    }
-    for (int ph = 0; ph < 2; ph++) {
-      const int e = 2 * b + ph;
-      const float cur = v.env[e];
-      if (cur < 0.0f || !(need[ph] > cur)) continue;
-      const float e_cap = v.grid->e_cap;
-      const float grown_to = need[ph] * 1.05f;
-      if (!(cur > e_cap) && grown_to > e_cap) v.fast_list[atomicAdd(&v.flags->n_fast, 1u)] = e;   // joins the fast entries
-      v.env[e] = grown_to;
-      v.grown[e] = 1;
-      atomicAdd(&v.flags->grew, 1);
-      atomicMax(v.bbox + 6, f2o(grown_to));      // largest ball in the world, for k_requery's search radius
-      if (!(need[ph] < 1.0e15f)) v.flags->unsafe = 1;
-    }
   }
 }
 // Start of an iteration: the destination timelines of the touched bodies.  A DIRTY body (its timeline
@@ -1046,7 +1074,7 @@ __device__ __forceinline__ void d_check(const LargeView &v, int src, int dst, in
 // From the third iteration on almost everybody is clean, and an iteration costs what its few changes cost.
 __device__ __forceinline__ void d_clear_carry(const LargeView &v, int src, int dst, int iter) {
   const int nt = (int)v.flags->n_touched;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { v.flags->changed = 0; v.flags->grew = 0; v.flags->n_hits = 0ull; }      // (n_active, n_hard: k_check)
+  if (blockIdx.x == 0 && threadIdx.x == 0) { v.flags->changed = 0; v.flags->n_hits = 0ull; }      // (n_active, n_hard: k_check)
   unsigned carried = 0;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     const int b = v.touched[t];
@@ -1080,136 +1108,184 @@ __device__ __forceinline__ void d_clear_carry(const LargeView &v, int src, int d
   if ((threadIdx.x & 31) == 0 && carried) atomicAdd(&v.flags->n_carried, (unsigned long long)carried);   // (n_hits is being reset by this very kernel)
 }
 
-// The balls of a few entries grew (a contact gave the body a state its phase ball was not sized for).  Find the
-// candidate visits they gain -- entry pairs touching under the new radii but not under the ones the list was
-// built with -- through the existing grid and append them marked as fresh, so that the next iteration evaluates
-// them (visits that were already listed keep their recorded outcomes).  If both entries of a pair grew, the
-// lower entry id appends it.
-// The search of one grown entry e, shared by `stride` threads (this one is number `lane` of them).
-// ByEntry = false: every thread takes whole cell runs (8 lanes, sparse cells: the runs' dependent loads are
-// in flight together); true (a block): the warps take the runs, the lanes of a warp the entries inside a run --
-// for wide searches and for dense cells (a settled world has dozens of bodies per floor cell).
-template <bool ByEntry>
-__device__ __forceinline__ void requery_entry(const LargeView &v, const GridParams &g, int e, int lane, int stride, float dt) {
-  const int b = e >> 1;
-  const float4 pb = v.pos_rest[b];
-  const bool rest_b = pb.w != 0.0f;
-  float c[3], vel[3];
-  entry_state(pb, v.vel_rad[b], e & 1, dt, c, vel);
-  const float3 m = entry_mid(c[0], c[1], c[2], vel[0], vel[1], vel[2], dt);
-  const float eb = v.env[e], eb_old = v.env_prev[e];
-  auto consider = [&](int ex, bool rest_x, float3 mx) {
-    const float dx = m.x - mx.x, dyy = m.y - mx.y, dzz = m.z - mx.z;
-    const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
-    const float ex_new = v.env[ex], ex_old = v.env_prev[ex];
-    const float Tn = eb + ex_new, To = eb_old + ex_old;
-    if (!(d2 <= Tn * Tn) || d2 <= To * To) return;            // not a candidate, or already listed
-    if (v.grown[ex] && ex < e) return;                        // the other grown entry appends it
-    int2 vis[2]; bool row_b[2];
-    const int nv = entry_pair_visits((unsigned)e, rest_b, (unsigned)ex, rest_x, vis, row_b);
-    for (int q = 0; q < nv; q++) {
-      const unsigned long long slot = atomicAdd(&v.flags->n_pairs, 1ull);
-      if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2(~vis[q].x, vis[q].y);   // ~row marks it fresh
-      else atomicExch(&v.flags->overflow_pairs, 1);
-    }
-  };
-  auto consider_sorted = [&](unsigned a) {
-    const float4 cx = v.sorted[a].crho;
-    const float4 wx = *reinterpret_cast<const float4 *>(&v.sorted[a].vx);
-    const unsigned idx = __float_as_uint(wx.w);
-    const int ex = (int)(idx & ~kRestBit);
-    if (ex == e || v.env[ex] > g.e_cap) return;               // (fast partners come from their list)
-    consider(ex, (idx & kRestBit) != 0u, entry_mid(cx.x, cx.y, cx.z, wx.x, wx.y, wx.z, dt));
-  };
-  // Partners the grid was sized for (radius <= e_cap) can be up to eb + e_cap away: search that many
-  // cells in every direction.  Fast partners are few and are checked one by one from their list
-  // (which also holds entries that outgrew e_cap this step).
-  const float need = (eb + g.e_cap) * g.inv_h * 1.001f;
-  if (!(need <= (float)kMaxSearch)) {
-    const int n_sorted = (int)v.cell_cnt[g.n_cells];
-    for (int a = lane; a < n_sorted; a += stride) consider_sorted((unsigned)a);
-  } else {
-    // every thread takes whole x-runs of the (2R+1)^2 the search covers (9 for an entry the grid was sized
-    // for), so their dependent loads -- cell table, cell contents, radii -- are in flight together
-    const int R = max((int)ceilf(need), 1);
-    const int3 cc = cell_coords(g, m.x, m.y, m.z);
-    const int side = 2 * R + 1;
-    const int x0 = max(cc.x - R, 0), x1 = min(cc.x + R, g.dim[0] - 1);
-    const int r_first = ByEntry ? (lane >> 5) : lane, r_step = ByEntry ? max(stride >> 5, 1) : stride;
-    const unsigned a_first = ByEntry ? (unsigned)(lane & 31) : 0u, a_step = ByEntry ? 32u : 1u;
-    for (int r = r_first; r < side * side; r += r_step) {
-      const int y = cc.y + r % side - R, z = cc.z + r / side - R;
-      if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
-      const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
-      const unsigned a1 = v.cell_cnt[row + x1 + 1];
-      for (unsigned a = v.cell_cnt[row + x0] + a_first; a < a1; a += a_step) consider_sorted(a);
-    }
-  }
-  const int nf = (int)v.flags->n_fast;
-  for (int f = lane; f < nf; f += stride) {
-    const int ex = v.fast_list[f];
-    if (ex == e || !(v.env[ex] > g.e_cap)) continue;
-    const int x = ex >> 1;
-    const float4 px = v.pos_rest[x];
-    float cx[3], vx[3];
-    entry_state(px, v.vel_rad[x], ex & 1, dt, cx, vx);
-    consider(ex, px.w != 0.0f, entry_mid(cx[0], cx[1], cx[2], vx[0], vx[1], vx[2], dt));
-  }
-}
-__device__ __forceinline__ void d_requery(const LargeView &v, int src, float dt) {
+// ---------------------------------------------------------------- 4. state balls
+// Every state that appeared (or changed) in a timeline this iteration gets its ball; so does, for a body whose
+// timeline changed at all, what its own row's integration makes of its last phase-A state.  One thread per
+// touched body.  Balls are never removed: a state that disappears again only leaves the list a superset.
+__global__ void k_states_insert(LargeView v, int src, int dst, float dt) {
   const GridParams g = *v.grid;
-  const int nt = 2 * (int)v.flags->n_touched;      // both phase entries of every touched body
-  // Eight lanes per grown entry whose search is the usual 9 short cell runs (each a chain of dependent
-  // loads: more entries in flight beat more lanes per entry).  One that searches wider -- a fast one, or a
-  // straggler whose search covers most of the grid and falls back to the whole sorted array -- goes on a
-  // list and gets a whole block (k_requery_wide): eight lanes walking 65 k bodies held the step up for 0.7 ms.
-  constexpr int kGroup = 8;
-  const int lane = threadIdx.x & (kGroup - 1);
-  const int groups = (gridDim.x * blockDim.x) / kGroup;
-  // when only a few entries grew (every iteration but the first) there is a block to spare for each of them
-  const bool few = v.flags->grew < v.requery_few;
-  const unsigned group_mask = 0xffu << (threadIdx.x & 24);
-  for (int t = (blockIdx.x * blockDim.x + threadIdx.x) / kGroup; t < nt; t += groups) {
-    const int e = 2 * v.touched[t >> 1] + (t & 1);
-    if (!v.grown[e]) continue;
-    const float need = (v.env[e] + g.e_cap) * g.inv_h * 1.001f;
-    bool wide = few || !(need <= 1.0f);
-    if (!wide) {
-      // ... and so does one whose 27 cells hold many entries (a settled world has dozens per floor cell):
-      // a lane would walk its runs for too long.  The lanes add up the lengths of their runs first.
-      const int b = e >> 1;
-      float c[3], vel[3];
-      entry_state(v.pos_rest[b], v.vel_rad[b], e & 1, dt, c, vel);
-      const float3 m = entry_mid(c[0], c[1], c[2], vel[0], vel[1], vel[2], dt);
-      const int3 cc = cell_coords(g, m.x, m.y, m.z);
-      const int x0 = max(cc.x - 1, 0), x1 = min(cc.x + 1, g.dim[0] - 1);
-      unsigned work = 0;
-      for (int r = lane; r < 9; r += kGroup) {
-        const int y = cc.y + r % 3 - 1, z = cc.z + r / 3 - 1;
-        if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
-        const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
-        work += v.cell_cnt[row + x1 + 1] - v.cell_cnt[row + x0];
-      }
-      for (int o = 4; o > 0; o >>= 1) work += __shfl_xor_sync(group_mask, work, o);
-      wide = work > 96u;                        // (measured: C4 at step 110 and the settled C2 are both slower with 512)
-    }
-    if (wide) {
-      if (lane == 0) v.wide_list[atomicAdd(&v.flags->n_wide, 1u)] = e;
-      continue;
-    }
-    requery_entry<false>(v, g, e, lane, kGroup, dt);
-  }
-}
-__device__ __forceinline__ void d_requery_wide(const LargeView &v, float dt) {
-  const GridParams g = *v.grid;
-  const int nw = (int)v.flags->n_wide;
-  for (int t = blockIdx.x; t < nw; t += gridDim.x) requery_entry<true>(v, g, v.wide_list[t], (int)threadIdx.x, (int)blockDim.x, dt);
-}
-__device__ __forceinline__ void d_requery_done(const LargeView &v) {
-  const int nt = 2 * (int)v.flags->n_touched;
+  const int nt = (int)v.flags->n_touched;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
-    const int e = 2 * v.touched[t >> 1] + (t & 1);
-    if (v.grown[e]) { v.grown[e] = 0; v.env_prev[e] = v.env[e]; }
+    const int b = v.touched[t];
+    if (!((v.dirty_bits[dst][b >> 5] >> (b & 31)) & 1u)) continue;
+    const float4 p = v.pos_rest[b];
+    const float r = v.vel_rad[b].w;
+    const bool at_rest = p.w != 0.0f;
+    const unsigned rest_flag = at_rest ? kRestBit : 0u;
+    const int cnt = min((int)v.tl_cnt[dst][b], kTimeline);
+    unsigned long long lastA_key = 0ull;
+    int lastA = -1;
+    for (int k = 0; k < cnt; k++) {
+      const unsigned long long key = v.tl_key[dst][(size_t)b * kTimeline + k];
+      const bool phase_a = (long long)(key >> 32) <= (long long)b;      // rows up to the body's own see it before its integration
+      if (phase_a && (lastA < 0 || key > lastA_key)) { lastA = k; lastA_key = key; }
+      const float4 tp = v.tl_pos[dst][(size_t)b * kTimeline + k];
+      if (tp.w == 0.0f) continue;                                        // unchanged since the previous iteration: has its ball
+      const float4 tv = v.tl_vel[dst][(size_t)b * kTimeline + k];
+      const int ph = (phase_a || at_rest) ? 0 : 1;
+      ball_insert(v, g, entry_mid(tp.x, tp.y, tp.z, tv.x, tv.y, tv.z, dt), entry_rho(r, tp.x, tp.y, tp.z, tv.x, tv.y, tv.z, dt),
+                  (unsigned)(2 * b + ph) | rest_flag);
+    }
+    if (lastA >= 0 && !at_rest) {
+      const float4 tp = v.tl_pos[dst][(size_t)b * kTimeline + lastA], tv = v.tl_vel[dst][(size_t)b * kTimeline + lastA];
+      // ... unless the previous iteration's timeline ended its phase A in the very same state (that ball exists)
+      const int cnt0 = min((int)v.tl_cnt[src][b], kTimeline);
+      unsigned long long prevA_key = 0ull;
+      int prevA = -1;
+      for (int k = 0; k < cnt0; k++) {
+        const unsigned long long key = v.tl_key[src][(size_t)b * kTimeline + k];
+        if ((long long)(key >> 32) <= (long long)b && (prevA < 0 || key > prevA_key)) { prevA = k; prevA_key = key; }
+      }
+      if (prevA >= 0 && same_state(v.tl_pos[src][(size_t)b * kTimeline + prevA], v.tl_vel[src][(size_t)b * kTimeline + prevA], tp, tv)) continue;
+      V3 pp = v3(tp.x, tp.y, tp.z), vv = v3(tv.x, tv.y, tv.z);
+      pgm::integrate(pp, vv, dt);
+      ball_insert(v, g, entry_mid(pp.x, pp.y, pp.z, vv.x, vv.y, vv.z, dt), entry_rho(r, pp.x, pp.y, pp.z, vv.x, vv.y, vv.z, dt),
+                  (unsigned)(2 * b + 1));
+    }
+  }
+}
+
+// One WARP per ball of the current iteration: which entries of other bodies does it touch, and which visits does
+// that add?  Three sources of partners: the cell-sorted untouched entries (27 cells: the lanes take the entries of
+// each x-run), the state balls and large untouched entries linked in the second structure (a lane per cell, walking
+// its list), and the few balls beyond e_cap2 (list).  A visit the untouched entries of the two bodies already listed
+// (k_pairs: the same ball test, repeated here bit for bit) is skipped; the rest go through the hash set.
+__global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
+  const GridParams g = *v.grid;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned j0 = v.flags->balls_begin, j1 = min(v.flags->n_balls, (unsigned)v.balls_cap);
+  for (unsigned j = j0 + warp; j < j1; j += n_warps) {
+    const float4 bc = v.ball_c[j];
+    const unsigned bflags = v.ball_e[j].x;
+    const int e = (int)(bflags & ~kRestBit), b = e >> 1;
+    const bool rest_b = (bflags & kRestBit) != 0u;
+    // the body's own untouched entry of the same phase (for the "already listed" test)
+    float c0[3], v0[3];
+    entry_state(v.pos_rest[b], v.vel_rad[b], e & 1, dt, c0, v0);
+    const float3 m0 = entry_mid(c0[0], c0[1], c0[2], v0[0], v0[1], v0[2], dt);
+    const float rho0 = v.env[e];
+    auto consider = [&](int ex, bool rest_x, float3 mx, float rhox, bool partner_is_untouched_entry) {
+      if ((ex >> 1) == b) return;
+      const float dx = bc.x - mx.x, dyy = bc.y - mx.y, dzz = bc.z - mx.z;
+      const float d2 = __fmaf_rn(dx, dx, __fmaf_rn(dyy, dyy, dzz * dzz));
+      const float T = bc.w + rhox;
+      if (!(d2 <= T * T)) return;
+      int2 vis[2]; bool row_b[2];
+      const int nv = entry_pair_visits((unsigned)e, rest_b, (unsigned)ex, rest_x, vis, row_b);
+      if (nv == 0) return;
+      // did k_pairs list the visits of this entry pair?  (untouched balls of both entries touch)
+      float3 ux = mx; float urho = rhox;
+      if (!partner_is_untouched_entry) {
+        const int x = ex >> 1;
+        urho = v.env[ex];
+        if (urho >= 0.0f) {
+          float cx[3], vx[3];
+          entry_state(v.pos_rest[x], v.vel_rad[x], ex & 1, dt, cx, vx);
+          ux = entry_mid(cx[0], cx[1], cx[2], vx[0], vx[1], vx[2], dt);
+        }
+      }
+      if (rho0 >= 0.0f && urho >= 0.0f) {
+        const float ex_ = m0.x - ux.x, ey_ = m0.y - ux.y, ez_ = m0.z - ux.z;
+        const float u2 = __fmaf_rn(ex_, ex_, __fmaf_rn(ey_, ey_, ez_ * ez_));
+        const float U = rho0 + urho;
+        if (u2 <= U * U) return;
+      }
+      for (int q = 0; q < nv; q++) {
+        const unsigned long long key = ((unsigned long long)(unsigned)vis[q].x << 32) | (unsigned)vis[q].y;
+        const long long hs = vset_insert(v, key);
+        if (hs < 0) continue;
+        const unsigned long long slot = agg_inc64(&v.flags->n_pairs);
+        if ((long long)slot < v.pairs_cap) v.pairs[slot] = make_int2(~vis[q].x, vis[q].y);   // ~row marks it fresh
+        else { atomicExch(&v.flags->overflow_pairs, 1); v.vset[hs] = kSlotTomb; }            // (the host makes room and repeats the query)
+      }
+    };
+    // (1) untouched entries within e_cap of the grid's sizing: rho + e_cap away at most
+    {
+      const float need = (bc.w + g.e_cap) * g.inv_h * 1.001f;
+      if (!(need <= (float)kMaxSearch)) {
+        const unsigned n_sorted = v.cell_cnt[g.n_cells];
+        for (unsigned a = lane; a < n_sorted; a += 32u) {
+          const float4 cx = v.sorted[a].crho;
+          const float4 wx = *reinterpret_cast<const float4 *>(&v.sorted[a].vx);
+          const unsigned idx = __float_as_uint(wx.w);
+          if (cx.w > g.e_cap) continue;
+          consider((int)(idx & ~kRestBit), (idx & kRestBit) != 0u, entry_mid(cx.x, cx.y, cx.z, wx.x, wx.y, wx.z, dt), cx.w, true);
+        }
+      } else {
+        const int R = max((int)ceilf(need), 1);
+        const int3 cc = cell_coords(g, bc.x, bc.y, bc.z);
+        const int side = 2 * R + 1;
+        const int x0 = max(cc.x - R, 0), x1 = min(cc.x + R, g.dim[0] - 1);
+        for (int r = 0; r < side * side; r++) {
+          const int y = cc.y + r % side - R, z = cc.z + r / side - R;
+          if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
+          const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+          const unsigned a1 = v.cell_cnt[row + x1 + 1];
+          for (unsigned a = v.cell_cnt[row + x0] + lane; a < a1; a += 32u) {
+            const float4 cx = v.sorted[a].crho;
+            if (cx.w > g.e_cap) continue;                  // (linked in the second structure as well: found there)
+            const float4 wx = *reinterpret_cast<const float4 *>(&v.sorted[a].vx);
+            const unsigned idx = __float_as_uint(wx.w);
+            consider((int)(idx & ~kRestBit), (idx & kRestBit) != 0u, entry_mid(cx.x, cx.y, cx.z, wx.x, wx.y, wx.z, dt), cx.w, true);
+          }
+        }
+      }
+    }
+    // (2) balls of the second structure (radius <= e_cap2): rho + e_cap2 away at most
+    {
+      const float need = (bc.w + g.e_cap2) * g.inv_h * 1.001f;
+      const int R = min(max((int)ceilf(need), 1), 64);
+      const int3 cc = cell_coords(g, bc.x, bc.y, bc.z);
+      const int side = 2 * R + 1;
+      const int n_cells_q = side * side * side;
+      for (int q = (int)lane; q < n_cells_q; q += 32) {
+        const int x = cc.x + q % side - R, y = cc.y + (q / side) % side - R, z = cc.z + q / (side * side) - R;
+        if (x < 0 || x >= g.dim[0] || y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
+        unsigned k = v.head2[(unsigned)((z * g.dim[1] + y) * g.dim[0] + x)];
+        while (k != kNoBall) {
+          const uint2 ke = v.ball_e[k];
+          if (k != j) {
+            const float4 kc = v.ball_c[k];
+            consider((int)(ke.x & ~kRestBit), (ke.x & kRestBit) != 0u, make_float3(kc.x, kc.y, kc.z), kc.w, false);
+          }
+          k = ke.y;
+        }
+      }
+    }
+    // (3) the few balls beyond e_cap2
+    {
+      const unsigned nh = min(v.flags->n_huge, (unsigned)v.huge_cap);
+      for (unsigned h = lane; h < nh; h += 32u) {
+        const unsigned k = (unsigned)v.huge_list[h];
+        if (k == j) continue;
+        const float4 kc = v.ball_c[k];
+        const unsigned kx = v.ball_e[k].x;
+        consider((int)(kx & ~kRestBit), (kx & kRestBit) != 0u, make_float3(kc.x, kc.y, kc.z), kc.w, false);
+      }
+    }
+  }
+}
+
+// Rehash the visit set into a larger table (host: when the load passes 1/4).
+__global__ void k_vset_rehash(LargeView v, const unsigned long long *old_tab, unsigned long long old_slots) {
+  for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s < old_slots; s += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long key = old_tab[s];
+    if (key == kSlotEmpty || key == kSlotTomb) continue;
+    unsigned long long h = key * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+    unsigned long long slot = h & v.vset_mask;
+    while (atomicCAS(&v.vset[slot], kSlotEmpty, key) != kSlotEmpty) slot = (slot + 1) & v.vset_mask;
   }
 }
 
@@ -1223,9 +1299,6 @@ __global__ void __launch_bounds__(256) k_begin(LargeView v, int src, int dst, in
   d_clear_carry(v, src, dst, iter);
   d_select(v, src, iter, dt);
 }
-__global__ void k_requery(LargeView v, int src, float dt) { d_requery(v, src, dt); }
-__global__ void k_requery_wide(LargeView v, float dt) { d_requery_wide(v, dt); }
-__global__ void k_requery_done(LargeView v) { d_requery_done(v); }
 
 // ---------------------------------------------------------------- 5. final state + pass-4 events
 __global__ void k_finalize(LargeView v, int src, float dt, int step) {
@@ -1269,8 +1342,6 @@ __global__ void k_reset_touched(LargeView v) {
   const int nt = (int)v.flags->n_touched;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
     const int b = v.touched[t];
-    v.grown[2 * b] = 0;
-    v.grown[2 * b + 1] = 0;
     v.tl_cnt[0][b] = 0;
     v.tl_cnt[1][b] = 0;
     v.tl_chg[0][b] = 0xffffffffffffffffull;
@@ -1423,6 +1494,46 @@ static int lw_grow_pairs(PgLarge *w, unsigned long long needed, unsigned long lo
   return PG_OK;
 }
 
+// Four times the slots for the visit hash set, keys carried over.
+static int lw_grow_vset(PgLarge *w) {
+  LargeView &v = w->v;
+  const unsigned long long old_slots = v.vset_mask + 1ull, new_slots = old_slots * 4ull;
+  unsigned long long *bigger = nullptr, *old = v.vset;
+  if (cudaMalloc(&bigger, sizeof(unsigned long long) * new_slots) != cudaSuccess) {
+    cudaGetLastError();
+    pg_set_error("large world: cannot grow the visit hash set to %llu slots", new_slots);
+    return PG_ERR_CAPACITY;
+  }
+  PG_CUDA(cudaMemsetAsync(bigger, 0xff, sizeof(unsigned long long) * new_slots, w->stream));
+  v.vset = bigger;
+  v.vset_mask = new_slots - 1ull;
+  k_vset_rehash<<<w->sm_count * 8, 256, 0, w->stream>>>(v, old, old_slots);
+  w->launches++;
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  cudaFree(old);
+  return PG_OK;
+}
+
+// Room for more state balls (contents kept).
+static int lw_grow_balls(PgLarge *w, unsigned used) {
+  LargeView &v = w->v;
+  const int cap = v.balls_cap * 2;
+  float4 *bc = nullptr; uint2 *be = nullptr;
+  if (cudaMalloc(&bc, sizeof(float4) * (size_t)cap) != cudaSuccess || cudaMalloc(&be, sizeof(uint2) * (size_t)cap) != cudaSuccess) {
+    cudaGetLastError();
+    if (bc) cudaFree(bc);
+    pg_set_error("large world: cannot grow the state-ball buffer to %d", cap);
+    return PG_ERR_CAPACITY;
+  }
+  const size_t keep = std::min<size_t>(used, (size_t)v.balls_cap);
+  PG_CUDA(cudaMemcpyAsync(bc, v.ball_c, sizeof(float4) * keep, cudaMemcpyDeviceToDevice, w->stream));
+  PG_CUDA(cudaMemcpyAsync(be, v.ball_e, sizeof(uint2) * keep, cudaMemcpyDeviceToDevice, w->stream));
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  cudaFree(v.ball_c); cudaFree(v.ball_e);
+  v.ball_c = bc; v.ball_e = be; v.balls_cap = cap;
+  return PG_OK;
+}
+
 static int lw_step_once(PgLarge *w, float dt_in) {
   LargeView &v = w->v;
   float dt = dt_in;
@@ -1433,6 +1544,8 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   PG_CUDA(cudaMemsetAsync(v.flags, 0, sizeof(Flags), w->stream));
   PG_CUDA(cudaMemsetAsync(v.rstat, 0, sizeof(float) * 8, w->stream));
   PG_CUDA(cudaMemsetAsync(v.touched_bits, 0, sizeof(unsigned) * ((size_t)v.n / 32 + 1), w->stream));
+  PG_CUDA(cudaMemsetAsync(v.head2, 0xff, sizeof(unsigned) * ((size_t)v.cells_cap + 1), w->stream));
+  PG_CUDA(cudaMemsetAsync(v.vset, 0xff, sizeof(unsigned long long) * (v.vset_mask + 1ull), w->stream));
   const int full_reset = w->bookkeeping_clean ? 0 : 1;
   if (full_reset) {
     const size_t words = (size_t)w->cap_n / 32 + 1;
@@ -1473,19 +1586,11 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   w->last_candidates = (long long)f.n_pairs;
   const bool debug = getenv("PG_LARGE_DEBUG") != nullptr && w->timing;
   bool converged = false;
-  int requeries = 0;
   int src = 0, dst = 1;
-  bool requery_pending = false;
-  // One host read-back per iteration: k_requery always rides along (it returns at once for bodies whose
-  // envelope did not grow), its bookkeeping kernel is deferred to the start of the next iteration so
-  // that an overflowing candidate list can still be grown and the append repeated.
+  // One host read-back per iteration.  The state-ball kernels always ride along (they return at once when no
+  // timeline changed).
   const int wide_grid = w->sm_count * 8;
   for (int it = 0; it < kMaxIter; it++) {
-    if (requery_pending) {
-      k_requery_done<<<wide_grid, 256, 0, w->stream>>>(v);
-      w->launches++;
-      requery_pending = false;
-    }
     const unsigned long long pairs_before = std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
     // the active list's length stays on the device: k_eval runs as many blocks as fit at once and strides
     if (w->timing) cudaEventRecord(w->kev[K_EVAL][0], w->stream);
@@ -1495,11 +1600,11 @@ static int lw_step_once(PgLarge *w, float dt_in) {
     if (w->timing) cudaEventRecord(w->kev[K_EVAL][1], w->stream);
     w->launches += 3;
     LW_LAUNCH(w, K_CHECK, k_check, wide_grid, 256, v, src, dst, it, dt);
-    // candidates the grown envelopes add (on top of the NEW timelines); their bodies are marked dirty so
-    // the next iteration re-evaluates them (warm start)
+    // balls of the states that appeared in the NEW timelines, and the visits they add (marked fresh: the next
+    // iteration evaluates them)
     if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][0], w->stream);
-    k_requery<<<wide_grid, 128, 0, w->stream>>>(v, dst, dt);
-    k_requery_wide<<<wide_grid, 256, 0, w->stream>>>(v, dt);
+    k_states_insert<<<wide_grid, 128, 0, w->stream>>>(v, src, dst, dt);
+    k_states_query<<<wide_grid, 256, 0, w->stream>>>(v, dt);
     if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][1], w->stream);
     w->launches += 2;
     rc = lw_read_flags(w, &f);
@@ -1510,43 +1615,39 @@ static int lw_step_once(PgLarge *w, float dt_in) {
       cudaEventElapsedTime(&e, w->kev[K_EVAL][0], w->kev[K_EVAL][1]);
       cudaEventElapsedTime(&c, w->kev[K_CHECK][0], w->kev[K_CHECK][1]);
       cudaEventElapsedTime(&rq, w->kev[K_BOUNDS][0], w->kev[K_BOUNDS][1]);
-      fprintf(stderr, "  [pg_large] iter %d: eval %.3f ms check %.3f ms requery %.3f ms hits %llu changed %d grew %d pairs %llu -> %llu touched %u fast %u wide %u\n",
-              it, e, c, rq, (unsigned long long)f.n_hits, f.changed, f.grew, pairs_before, (unsigned long long)f.n_pairs, f.n_touched, f.n_fast, f.n_wide);
+      fprintf(stderr, "  [pg_large] iter %d: eval %.3f ms check %.3f ms states %.3f ms hits %llu changed %d visits %llu -> %llu touched %u balls %u (+%u) huge %u set %u\n",
+              it, e, c, rq, (unsigned long long)f.n_hits, f.changed, pairs_before, (unsigned long long)f.n_pairs, f.n_touched, f.n_balls,
+              f.n_balls - f.balls_begin, f.n_huge, f.n_vset);
     }
     w->last_iterations++;
     w->last_hits = (long long)f.n_hits;
     if (f.overflow_timeline) { pg_set_error("large world: more than %d contacts on one body in one step", kTimeline); return PG_ERR_CAPACITY; }
-    std::swap(src, dst);
-    if (f.grew) {
-      if (f.overflow_pairs) {
-        // k_requery only appends: keep the list as it was, make room, and let it append again
-        rc = lw_grow_pairs(w, f.n_pairs, pairs_before);
-        if (rc) return rc;
-        PG_CUDA(cudaMemsetAsync(&v.flags->n_wide, 0, sizeof(unsigned), w->stream));
-        if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][0], w->stream);
-        k_requery<<<wide_grid, 128, 0, w->stream>>>(v, src, dt);
-        k_requery_wide<<<wide_grid, 256, 0, w->stream>>>(v, dt);
-        if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][1], w->stream);
-        w->launches += 2;
-        rc = lw_read_flags(w, &f);
-        if (rc) return rc;
-        lw_accumulate(w, K_BOUNDS);
-        if (f.overflow_pairs) { pg_set_error("large world: candidate pair buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
-      }
-      requery_pending = true;
-      if (f.unsafe) { w->last_proven = 0; if (debug) fprintf(stderr, "  [pg_large] envelope outgrew the grid: result not proven\n"); }
-      w->last_candidates = (long long)f.n_pairs;
-      requeries++;
-      continue;                           // at least one more iteration with the new pairs
+    if (f.overflow_balls) { pg_set_error("large world: state-ball buffer too small (%d)", v.balls_cap); return PG_ERR_CAPACITY; }
+    if (f.overflow_vset) { pg_set_error("large world: visit hash set too small (%llu slots)", (unsigned long long)v.vset_mask + 1ull); return PG_ERR_CAPACITY; }
+    if (f.unsafe) { pg_set_error("large world: non-finite body state"); return PG_ERR_ARG; }
+    int guard = 0;
+    while (f.overflow_pairs) {
+      // the query only appends (and took the visits it could not store out of the hash set again): make room
+      // and let it run again over the same balls
+      if (++guard > 8) { pg_set_error("large world: candidate visit buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
+      rc = lw_grow_pairs(w, f.n_pairs, (unsigned long long)v.pairs_cap);
+      if (rc) return rc;
+      if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][0], w->stream);
+      k_states_query<<<wide_grid, 256, 0, w->stream>>>(v, dt);
+      if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][1], w->stream);
+      w->launches++;
+      rc = lw_read_flags(w, &f);
+      if (rc) return rc;
+      lw_accumulate(w, K_BOUNDS);
     }
+    w->last_candidates = (long long)f.n_pairs;
+    // keep the hash set and the ball buffer roomy (load <= 1/4, fill <= 1/2) for the next iteration
+    if ((unsigned long long)f.n_vset * 4ull > v.vset_mask + 1ull) { rc = lw_grow_vset(w); if (rc) return rc; }
+    if ((long long)f.n_balls * 2 > (long long)v.balls_cap) { rc = lw_grow_balls(w, f.n_balls); if (rc) return rc; }
+    std::swap(src, dst);
     if (!f.changed) { converged = true; break; }
   }
-  if (requery_pending) {
-    k_requery_done<<<wide_grid, 256, 0, w->stream>>>(v);
-    w->launches++;
-  }
   if (!converged) w->last_proven = 0;
-  (void)requeries;
   LW_LAUNCH(w, K_FINAL, k_finalize, lw_grid(w, v.n, 256), 256, v, src, dt, w->step_in_call);
   k_reset_touched<<<w->sm_count * 4, 256, 0, w->stream>>>(v);
   w->launches++;
@@ -1606,9 +1707,9 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   // test hooks (read once per handle): tiny shared-memory stages reach their overflow paths, and a zero
   // threshold keeps k_requery on its eight-lane path in worlds where few bodies grow
   v.stage_limit = getenv("PG_LARGE_SMALL_STAGES") ? 3 : (1 << 20);
-  v.requery_few = getenv("PG_LARGE_REQUERY_FEW") ? atoi(getenv("PG_LARGE_REQUERY_FEW")) : 4096;
   v.pass3_split_min = getenv("PG_LARGE_PASS3_SPLIT_MIN") ? atoi(getenv("PG_LARGE_PASS3_SPLIT_MIN")) : 262144;
-  v.ecap_factor = getenv("PG_LARGE_ECAP_FACTOR") ? (float)atof(getenv("PG_LARGE_ECAP_FACTOR")) : 2.0f;
+  v.ecap_factor = getenv("PG_LARGE_ECAP_FACTOR") ? (float)atof(getenv("PG_LARGE_ECAP_FACTOR")) : 1.5f;
+  v.ecap2_factor = getenv("PG_LARGE_ECAP2_FACTOR") ? (float)atof(getenv("PG_LARGE_ECAP2_FACTOR")) : 1.0f;
   v.r_uniform = -1.0f;
   v.cells_cap = (int)std::min<size_t>(4 * n + 4096, (size_t)1 << 28);
   v.pairs_cap = (long long)(8 * n + 65536);
@@ -1632,17 +1733,24 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
     r0.valid = 0;
     PG_CUDA_NULL(cudaMemcpy(v.robust, &r0, sizeof(r0), cudaMemcpyHostToDevice));
   }
-  PG_CUDA_NULL(cudaMalloc(&v.fast_list, sizeof(int) * 2 * n));
-  PG_CUDA_NULL(cudaMalloc(&v.wide_list, sizeof(int) * 2 * n));
+  v.balls_cap = (int)std::min<size_t>(2 * n + 65536, (size_t)1 << 30);
+  PG_CUDA_NULL(cudaMalloc(&v.ball_c, sizeof(float4) * (size_t)v.balls_cap));
+  PG_CUDA_NULL(cudaMalloc(&v.ball_e, sizeof(uint2) * (size_t)v.balls_cap));
+  PG_CUDA_NULL(cudaMalloc(&v.head2, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
+  v.huge_cap = 65536;
+  PG_CUDA_NULL(cudaMalloc(&v.huge_list, sizeof(int) * (size_t)v.huge_cap));
+  {
+    unsigned long long slots = 1ull << 16;
+    while (slots < 8ull * n) slots <<= 1;
+    v.vset_mask = slots - 1ull;
+    PG_CUDA_NULL(cudaMalloc(&v.vset, sizeof(unsigned long long) * slots));
+  }
   PG_CUDA_NULL(cudaMalloc(&v.cell_of, sizeof(unsigned) * 2 * n));
   PG_CUDA_NULL(cudaMalloc(&v.cell_cnt, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.block_sums, sizeof(unsigned) * ((size_t)v.cells_cap / (kScanBlock * kScanItems) + 2)));
   PG_CUDA_NULL(cudaMalloc(&v.sorted, sizeof(SortedBody) * 2 * n));
   PG_CUDA_NULL(cudaMalloc(&v.pairs, sizeof(int2) * (size_t)v.pairs_cap));
   PG_CUDA_NULL(cudaMalloc(&v.active, sizeof(unsigned) * 2 * (size_t)v.pairs_cap));
-  PG_CUDA_NULL(cudaMalloc(&v.grown, 2 * n + 8));
-  PG_CUDA_NULL(cudaMemset(v.grown, 0, 2 * n + 8));
-  PG_CUDA_NULL(cudaMalloc(&v.env_prev, sizeof(float) * 2 * n));
   PG_CUDA_NULL(cudaMalloc(&v.seen, sizeof(int) * n));
   PG_CUDA_NULL(cudaMalloc(&v.touched_bits, sizeof(unsigned) * (n / 32 + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.dirty_bits[0], sizeof(unsigned) * (n / 32 + 1)));
@@ -1675,8 +1783,8 @@ void pg_large_destroy(PgLarge *w) {
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
   if (w->player_world) pg_worlds_destroy(w->player_world);
-  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.fast_list, v.wide_list, v.touched_bits, v.dirty_bits[0], v.dirty_bits[1], v.pushed_bits, v.block_sums, v.sorted,
-                  v.pairs, v.active, v.grown, v.env_prev, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
+  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.ball_c, v.ball_e, v.head2, v.huge_list, v.vset, v.touched_bits, v.dirty_bits[0], v.dirty_bits[1], v.pushed_bits, v.block_sums, v.sorted,
+                  v.pairs, v.active, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
                   v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);
   cudaEventDestroy(w->ev0); cudaEventDestroy(w->ev1);
@@ -1921,6 +2029,7 @@ long long pg_large_pairs(PgLarge *w, float dt_in, int32_t *out_ij, long long cap
   PG_CUDA(cudaMemcpyAsync(v.bbox, bbox_init, sizeof(bbox_init), cudaMemcpyHostToDevice, w->stream));
   PG_CUDA(cudaMemsetAsync(v.flags, 0, sizeof(Flags), w->stream));
   PG_CUDA(cudaMemsetAsync(v.rstat, 0, sizeof(float) * 8, w->stream));       // no running statistics here: plain bounding box
+  PG_CUDA(cudaMemsetAsync(v.head2, 0xff, sizeof(unsigned) * ((size_t)v.cells_cap + 1), w->stream));
   k_env_frozen<<<lw_grid(w, v.n, 256), 256, 0, w->stream>>>(v, dt);
   w->launches++;
   int rc = lw_build_pairs(w, dt);

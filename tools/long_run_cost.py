@@ -16,11 +16,16 @@ pos, vel = scenes.sphere_worlds(1, n, L)
 st = scenes.plane_bodies(scenes.box_planes(L))
 g = gpu.GpuLargeWorld(n, len(st))
 g.set(st, pos[0], vel[0])
+if os.environ.get("PG_LARGE_TIMING"):
+    g.set_timing(True)
 t_start = time.time()
 done = 0
 while done < steps and time.time() - t_start < budget_s:
     ms, proven, worst = 0.0, True, 0.0
     for _ in range(chunk):
+        if time.time() - t_start > budget_s:
+            print("time budget reached inside the chunk", flush=True)
+            break
         g.step(scenes.DT_60HZ, 1)
         m = g.last_step_ms()
         ms += m
@@ -30,4 +35,6 @@ while done < steps and time.time() - t_start < budget_s:
     done += chunk
     print(f"steps {done - chunk:5d}-{done:5d}: mean {ms / chunk:8.3f} ms/step, worst {worst:9.3f} ms, last step: {ex['iterations']} iterations, "
           f"{ex['candidates']} candidates, {ex['hits']} hits, all proven exact: {proven}", flush=True)
+    if os.environ.get("PG_LARGE_TIMING"):
+        print("      last step per kernel:", {k: round(v, 3) for k, v in g.kernel_ms().items()}, flush=True)
 g.close()
