@@ -95,6 +95,7 @@ struct Flags {
   int changed;            // fixed point: some timeline differs from the previous iteration
   int overflow_balls;     // state-ball buffer full
   int overflow_vset;      // visit hash set full
+  int overflow_huge;      // more balls beyond e_cap2 than their list holds
   unsigned n_balls;       // state balls linked so far this step
   unsigned balls_begin;   // ... of which [balls_begin, n_balls) appeared in the current iteration
   unsigned n_huge;        // balls beyond e_cap2 (on the list every query walks)
@@ -109,6 +110,9 @@ struct Flags {
   unsigned n_active;      // candidate pairs the selection (k_begin) handed to k_eval this iteration
   unsigned n_hard;        // of those, pairs k_eval passed on to k_eval_hard (long interval searches)
   unsigned n_pass3;       // bodies k_pass3 passed on to k_pass3_exact
+  int stop;               // fixed point: the iterations still queued behind this one return at once (converged, or the host must act)
+  int converged;
+  unsigned iters_done;    // iterations that really ran this step
 };
 
 // One phase entry of the cell-ordered copy.  A whole 32-byte sector per entry: the counting sort's scattered
@@ -167,7 +171,8 @@ struct LargeView {
   float4 *ball_c;                    // [balls_cap] midpoint xyz, radius
   uint2 *ball_e;                     // [balls_cap] .x = entry id (2 body + phase) | kRestBit, .y = next ball of its cell (0xffffffff: none)
   int balls_cap;
-  unsigned *head2;                   // [cells_cap] first ball of every cell of the second structure (0xffffffff: empty)
+  unsigned *head2, *head3;           // [cells_cap] first ball of every cell of the second structure (0xffffffff: empty): balls up to
+                                     // e_cap / up to e_cap2
   int *huge_list;                    // [huge_cap] balls beyond grid->e_cap2
   int huge_cap;
   unsigned long long *vset;          // visit hash set: keys (row << 32 | col), 0xff..ff = empty slot
@@ -544,13 +549,16 @@ __device__ __forceinline__ void ball_insert(const LargeView &v, const GridParams
   v.ball_c[idx] = make_float4(m.x, m.y, m.z, rho);
   if (rho > g.e_cap2) {                          // beyond what a query's cell search covers: the list every query walks
     const unsigned hslot = atomicAdd(&v.flags->n_huge, 1u);
-    if (hslot < (unsigned)v.huge_cap) v.huge_list[hslot] = (int)idx; else atomicExch(&v.flags->overflow_balls, 1);
+    if (hslot < (unsigned)v.huge_cap) v.huge_list[hslot] = (int)idx; else atomicExch(&v.flags->overflow_huge, 1);
     v.ball_e[idx] = make_uint2(ent_flags, kNoBall);
     return;
   }
+  // two levels over the same cells: the bulk (radius <= e_cap: a query looks into 27 cells), and the tail up to
+  // e_cap2 (few balls, searched wider)
   const int3 c = cell_coords(g, m.x, m.y, m.z);
   const unsigned cell = (unsigned)((c.z * g.dim[1] + c.y) * g.dim[0] + c.x);
-  v.ball_e[idx] = make_uint2(ent_flags, atomicExch(&v.head2[cell], idx));
+  unsigned *head = rho > g.e_cap ? v.head3 : v.head2;
+  v.ball_e[idx] = make_uint2(ent_flags, atomicExch(&head[cell], idx));
 }
 
 // Visit hash set (open addressing, linear probing): returns the slot if `key` was inserted, -1 if it was there.
@@ -1113,6 +1121,7 @@ __device__ __forceinline__ void d_clear_carry(const LargeView &v, int src, int d
 // timeline changed at all, what its own row's integration makes of its last phase-A state.  One thread per
 // touched body.  Balls are never removed: a state that disappears again only leaves the list a superset.
 __global__ void k_states_insert(LargeView v, int src, int dst, float dt) {
+  if (v.flags->stop) return;
   const GridParams g = *v.grid;
   const int nt = (int)v.flags->n_touched;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nt; t += gridDim.x * blockDim.x) {
@@ -1161,6 +1170,7 @@ __global__ void k_states_insert(LargeView v, int src, int dst, float dt) {
 // its list), and the few balls beyond e_cap2 (list).  A visit the untouched entries of the two bodies already listed
 // (k_pairs: the same ball test, repeated here bit for bit) is skipped; the rest go through the hash set.
 __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
+  if (v.flags->stop) return;
   const GridParams g = *v.grid;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -1242,9 +1252,11 @@ __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
         }
       }
     }
-    // (2) balls of the second structure (radius <= e_cap2): rho + e_cap2 away at most
-    {
-      const float need = (bc.w + g.e_cap2) * g.inv_h * 1.001f;
+    // (2) balls of the second structure: the bulk level (radius <= e_cap) rho + e_cap away at most, the tail level
+    // (radius <= e_cap2) rho + e_cap2; a lane per cell, walking its list
+    for (int level = 0; level < 2; level++) {
+      const unsigned *head = level ? v.head3 : v.head2;
+      const float need = (bc.w + (level ? g.e_cap2 : g.e_cap)) * g.inv_h * 1.001f;
       const int R = min(max((int)ceilf(need), 1), 64);
       const int3 cc = cell_coords(g, bc.x, bc.y, bc.z);
       const int side = 2 * R + 1;
@@ -1252,7 +1264,7 @@ __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
       for (int q = (int)lane; q < n_cells_q; q += 32) {
         const int x = cc.x + q % side - R, y = cc.y + (q / side) % side - R, z = cc.z + q / (side * side) - R;
         if (x < 0 || x >= g.dim[0] || y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
-        unsigned k = v.head2[(unsigned)((z * g.dim[1] + y) * g.dim[0] + x)];
+        unsigned k = head[(unsigned)((z * g.dim[1] + y) * g.dim[0] + x)];
         while (k != kNoBall) {
           const uint2 ke = v.ball_e[k];
           if (k != j) {
@@ -1290,12 +1302,24 @@ __global__ void k_vset_rehash(LargeView v, const unsigned long long *old_tab, un
 }
 
 
-__global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) { d_eval(v, src, dst, iter, dt); }
-__global__ void __launch_bounds__(512) k_eval_hard(LargeView v, int src, int dst, int iter, float dt) { d_eval_hard(v, src, dst, iter, dt); }
-__global__ void k_check(LargeView v, int src, int dst, int iter, float dt) { d_check(v, src, dst, iter, dt); }
+// Several iterations are queued per host read-back; this one-thread kernel opens each of them: once the fixed
+// point has converged -- or something needs the host (a buffer to grow, an error) -- it raises `stop`, and
+// every kernel queued behind it returns at once.
+__global__ void k_iter_gate(LargeView v, int first) {
+  Flags *f = v.flags;
+  if (f->stop) return;
+  if (!first && !f->changed) { f->stop = 1; f->converged = 1; return; }
+  if (f->overflow_pairs || f->overflow_timeline || f->overflow_balls || f->overflow_vset || f->overflow_huge || f->unsafe ||
+      (unsigned long long)f->n_vset * 4ull > v.vset_mask + 1ull || (long long)f->n_balls * 2 > (long long)v.balls_cap) { f->stop = 1; return; }
+  f->iters_done++;
+}
+__global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) { if (v.flags->stop) return; d_eval(v, src, dst, iter, dt); }
+__global__ void __launch_bounds__(512) k_eval_hard(LargeView v, int src, int dst, int iter, float dt) { if (v.flags->stop) return; d_eval_hard(v, src, dst, iter, dt); }
+__global__ void k_check(LargeView v, int src, int dst, int iter, float dt) { if (v.flags->stop) return; d_check(v, src, dst, iter, dt); }
 // One launch opens an iteration: the carry (per touched body) and the selection (per candidate pair) read the
 // same source hypothesis and write disjoint things.
 __global__ void __launch_bounds__(256) k_begin(LargeView v, int src, int dst, int iter, float dt) {
+  if (v.flags->stop) return;
   d_clear_carry(v, src, dst, iter);
   d_select(v, src, iter, dt);
 }
@@ -1416,6 +1440,7 @@ struct PgLarge {
   long long last_candidates, last_hits;
   int step_in_call;
   int bookkeeping_clean;         // the last step ended with k_reset_touched: k_pass3 may skip the per-body resets
+  int iter_batch;                // fixed-point iterations queued per host read-back
   int timing;                    // record a CUDA event pair around every kernel (pg_large_kernel_ms); off by default:
                                  // the pipeline of a small world is launch-bound and the events double its API calls
 };
@@ -1517,7 +1542,8 @@ static int lw_grow_vset(PgLarge *w) {
 // Room for more state balls (contents kept).
 static int lw_grow_balls(PgLarge *w, unsigned used) {
   LargeView &v = w->v;
-  const int cap = v.balls_cap * 2;
+  if (v.balls_cap > (1 << 29)) { pg_set_error("large world: state-ball buffer at its limit (%d)", v.balls_cap); return PG_ERR_CAPACITY; }
+  const int cap = std::max(v.balls_cap * 2, (int)std::min<unsigned>(used + used / 2, 1u << 30));
   float4 *bc = nullptr; uint2 *be = nullptr;
   if (cudaMalloc(&bc, sizeof(float4) * (size_t)cap) != cudaSuccess || cudaMalloc(&be, sizeof(uint2) * (size_t)cap) != cudaSuccess) {
     cudaGetLastError();
@@ -1545,6 +1571,7 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   PG_CUDA(cudaMemsetAsync(v.rstat, 0, sizeof(float) * 8, w->stream));
   PG_CUDA(cudaMemsetAsync(v.touched_bits, 0, sizeof(unsigned) * ((size_t)v.n / 32 + 1), w->stream));
   PG_CUDA(cudaMemsetAsync(v.head2, 0xff, sizeof(unsigned) * ((size_t)v.cells_cap + 1), w->stream));
+  PG_CUDA(cudaMemsetAsync(v.head3, 0xff, sizeof(unsigned) * ((size_t)v.cells_cap + 1), w->stream));
   PG_CUDA(cudaMemsetAsync(v.vset, 0xff, sizeof(unsigned long long) * (v.vset_mask + 1ull), w->stream));
   const int full_reset = w->bookkeeping_clean ? 0 : 1;
   if (full_reset) {
@@ -1586,27 +1613,31 @@ static int lw_step_once(PgLarge *w, float dt_in) {
   w->last_candidates = (long long)f.n_pairs;
   const bool debug = getenv("PG_LARGE_DEBUG") != nullptr && w->timing;
   bool converged = false;
-  int src = 0, dst = 1;
-  // One host read-back per iteration.  The state-ball kernels always ride along (they return at once when no
-  // timeline changed).
+  // Iterations are queued in batches between host read-backs (k_iter_gate stops a batch on the device when the
+  // fixed point has converged or the host has to act); with per-kernel timing on, one at a time.
   const int wide_grid = w->sm_count * 8;
-  for (int it = 0; it < kMaxIter; it++) {
+  const int batch = w->timing ? 1 : w->iter_batch;
+  int queued = 0;                       // iterations queued so far this step (== the iteration index of the next one)
+  while (queued < kMaxIter) {
     const unsigned long long pairs_before = std::min<unsigned long long>(f.n_pairs, (unsigned long long)v.pairs_cap);
-    // the active list's length stays on the device: k_eval runs as many blocks as fit at once and strides
-    if (w->timing) cudaEventRecord(w->kev[K_EVAL][0], w->stream);
-    k_begin<<<wide_grid, 256, 0, w->stream>>>(v, src, dst, it, dt);      // carry + selection; also resets the per-iteration flags
-    k_eval<<<w->sm_count * 4, 128, 0, w->stream>>>(v, src, dst, it, dt);
-    k_eval_hard<<<w->sm_count, 512, 0, w->stream>>>(v, src, dst, it, dt);
-    if (w->timing) cudaEventRecord(w->kev[K_EVAL][1], w->stream);
-    w->launches += 3;
-    LW_LAUNCH(w, K_CHECK, k_check, wide_grid, 256, v, src, dst, it, dt);
-    // balls of the states that appeared in the NEW timelines, and the visits they add (marked fresh: the next
-    // iteration evaluates them)
-    if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][0], w->stream);
-    k_states_insert<<<wide_grid, 128, 0, w->stream>>>(v, src, dst, dt);
-    k_states_query<<<wide_grid, 256, 0, w->stream>>>(v, dt);
-    if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][1], w->stream);
-    w->launches += 2;
+    const int first_of_batch = queued;
+    for (int q = 0; q < batch && queued < kMaxIter; q++, queued++) {
+      const int it = queued, src = it & 1, dst = src ^ 1;
+      k_iter_gate<<<1, 1, 0, w->stream>>>(v, it == 0 ? 1 : 0);
+      if (w->timing) cudaEventRecord(w->kev[K_EVAL][0], w->stream);
+      k_begin<<<wide_grid, 256, 0, w->stream>>>(v, src, dst, it, dt);      // carry + selection; also resets the per-iteration flags
+      k_eval<<<w->sm_count * 4, 128, 0, w->stream>>>(v, src, dst, it, dt);
+      k_eval_hard<<<w->sm_count, 512, 0, w->stream>>>(v, src, dst, it, dt);
+      if (w->timing) cudaEventRecord(w->kev[K_EVAL][1], w->stream);
+      LW_LAUNCH(w, K_CHECK, k_check, wide_grid, 256, v, src, dst, it, dt);
+      // balls of the states that appeared in the NEW timelines, and the visits they add (marked fresh: the next
+      // iteration evaluates them)
+      if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][0], w->stream);
+      k_states_insert<<<wide_grid, 128, 0, w->stream>>>(v, src, dst, dt);
+      k_states_query<<<wide_grid, 256, 0, w->stream>>>(v, dt);
+      if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][1], w->stream);
+      w->launches += 6;
+    }
     rc = lw_read_flags(w, &f);
     if (rc) return rc;
     lw_accumulate(w, K_EVAL); lw_accumulate(w, K_CHECK); lw_accumulate(w, K_BOUNDS);
@@ -1616,23 +1647,36 @@ static int lw_step_once(PgLarge *w, float dt_in) {
       cudaEventElapsedTime(&c, w->kev[K_CHECK][0], w->kev[K_CHECK][1]);
       cudaEventElapsedTime(&rq, w->kev[K_BOUNDS][0], w->kev[K_BOUNDS][1]);
       fprintf(stderr, "  [pg_large] iter %d: eval %.3f ms check %.3f ms states %.3f ms hits %llu changed %d visits %llu -> %llu touched %u balls %u (+%u) huge %u set %u\n",
-              it, e, c, rq, (unsigned long long)f.n_hits, f.changed, pairs_before, (unsigned long long)f.n_pairs, f.n_touched, f.n_balls,
+              first_of_batch, e, c, rq, (unsigned long long)f.n_hits, f.changed, pairs_before, (unsigned long long)f.n_pairs, f.n_touched, f.n_balls,
               f.n_balls - f.balls_begin, f.n_huge, f.n_vset);
     }
-    w->last_iterations++;
+    w->last_iterations = (int)f.iters_done;
     w->last_hits = (long long)f.n_hits;
+    const bool was_stopped = f.stop != 0;
     if (f.overflow_timeline) { pg_set_error("large world: more than %d contacts on one body in one step", kTimeline); return PG_ERR_CAPACITY; }
-    if (f.overflow_balls) { pg_set_error("large world: state-ball buffer too small (%d)", v.balls_cap); return PG_ERR_CAPACITY; }
     if (f.overflow_vset) { pg_set_error("large world: visit hash set too small (%llu slots)", (unsigned long long)v.vset_mask + 1ull); return PG_ERR_CAPACITY; }
     if (f.unsafe) { pg_set_error("large world: non-finite body state"); return PG_ERR_ARG; }
+    if (f.overflow_huge) { pg_set_error("large world: more than %d balls beyond the tail bound of the grid", v.huge_cap); return PG_ERR_CAPACITY; }
+    // Whatever stopped the batch, the timelines the LAST executed iteration wrote are intact; its state balls and
+    // the visits they add may be incomplete if a buffer ran full.  Make room and repeat those two kernels: balls
+    // that were stored already are linked a second time (harmless duplicates), visits that were stored already
+    // are in the hash set (the query took the ones it could not store out again).
     int guard = 0;
-    while (f.overflow_pairs) {
-      // the query only appends (and took the visits it could not store out of the hash set again): make room
-      // and let it run again over the same balls
-      if (++guard > 8) { pg_set_error("large world: candidate visit buffer too small (%lld)", v.pairs_cap); return PG_ERR_CAPACITY; }
-      rc = lw_grow_pairs(w, f.n_pairs, (unsigned long long)v.pairs_cap);
-      if (rc) return rc;
+    while (f.overflow_pairs || f.overflow_balls) {
+      if (++guard > 8) { pg_set_error("large world: candidate visit / state-ball buffers too small (%lld, %d)", v.pairs_cap, v.balls_cap); return PG_ERR_CAPACITY; }
+      const int last_it = (int)f.iters_done - 1, lsrc = last_it & 1, ldst = lsrc ^ 1;
+      if (f.overflow_pairs) { rc = lw_grow_pairs(w, f.n_pairs, (unsigned long long)v.pairs_cap); if (rc) return rc; }
+      const bool redo_insert = f.overflow_balls != 0;
+      if (redo_insert) {
+        const unsigned kept = std::min<unsigned>(f.n_balls, (unsigned)v.balls_cap);
+        rc = lw_grow_balls(w, std::max<unsigned>(f.n_balls, kept));
+        if (rc) return rc;
+        PG_CUDA(cudaMemcpyAsync(&v.flags->n_balls, &kept, sizeof(kept), cudaMemcpyHostToDevice, w->stream));
+        PG_CUDA(cudaMemsetAsync(&v.flags->overflow_balls, 0, sizeof(int), w->stream));
+      }
+      PG_CUDA(cudaMemsetAsync(&v.flags->stop, 0, sizeof(int), w->stream));
       if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][0], w->stream);
+      if (redo_insert) { k_states_insert<<<wide_grid, 128, 0, w->stream>>>(v, lsrc, ldst, dt); w->launches++; }
       k_states_query<<<wide_grid, 256, 0, w->stream>>>(v, dt);
       if (w->timing) cudaEventRecord(w->kev[K_BOUNDS][1], w->stream);
       w->launches++;
@@ -1641,12 +1685,17 @@ static int lw_step_once(PgLarge *w, float dt_in) {
       lw_accumulate(w, K_BOUNDS);
     }
     w->last_candidates = (long long)f.n_pairs;
-    // keep the hash set and the ball buffer roomy (load <= 1/4, fill <= 1/2) for the next iteration
+    if (f.converged) { converged = true; break; }
+    // keep the hash set and the ball buffer roomy (load <= 1/4, fill <= 1/2) for the iterations to come
     if ((unsigned long long)f.n_vset * 4ull > v.vset_mask + 1ull) { rc = lw_grow_vset(w); if (rc) return rc; }
     if ((long long)f.n_balls * 2 > (long long)v.balls_cap) { rc = lw_grow_balls(w, f.n_balls); if (rc) return rc; }
-    std::swap(src, dst);
-    if (!f.changed) { converged = true; break; }
+    if (was_stopped) {
+      // the batch stopped early for the host's sake: the iterations that did not run are queued again
+      PG_CUDA(cudaMemsetAsync(&v.flags->stop, 0, sizeof(int), w->stream));
+      queued = (int)f.iters_done;
+    }
   }
+  const int src = (int)(f.iters_done & 1u);       // the timelines the last executed iteration wrote
   if (!converged) w->last_proven = 0;
   LW_LAUNCH(w, K_FINAL, k_finalize, lw_grid(w, v.n, 256), 256, v, src, dt, w->step_in_call);
   k_reset_touched<<<w->sm_count * 4, 256, 0, w->stream>>>(v);
@@ -1692,6 +1741,7 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   PgLarge *w = new PgLarge();
   memset(w, 0, sizeof(*w));
   w->timing = getenv("PG_LARGE_TIMING") != nullptr || getenv("PG_LARGE_DEBUG") != nullptr;
+  w->iter_batch = getenv("PG_LARGE_ITER_BATCH") ? std::max(1, atoi(getenv("PG_LARGE_ITER_BATCH"))) : 4;
   w->device = device;
   w->cap_n = max_spheres;
   w->cap_static = std::max(max_static, 1);
@@ -1709,7 +1759,7 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   v.stage_limit = getenv("PG_LARGE_SMALL_STAGES") ? 3 : (1 << 20);
   v.pass3_split_min = getenv("PG_LARGE_PASS3_SPLIT_MIN") ? atoi(getenv("PG_LARGE_PASS3_SPLIT_MIN")) : 262144;
   v.ecap_factor = getenv("PG_LARGE_ECAP_FACTOR") ? (float)atof(getenv("PG_LARGE_ECAP_FACTOR")) : 1.5f;
-  v.ecap2_factor = getenv("PG_LARGE_ECAP2_FACTOR") ? (float)atof(getenv("PG_LARGE_ECAP2_FACTOR")) : 1.0f;
+  v.ecap2_factor = getenv("PG_LARGE_ECAP2_FACTOR") ? (float)atof(getenv("PG_LARGE_ECAP2_FACTOR")) : 4.0f;
   v.r_uniform = -1.0f;
   v.cells_cap = (int)std::min<size_t>(4 * n + 4096, (size_t)1 << 28);
   v.pairs_cap = (long long)(8 * n + 65536);
@@ -1733,10 +1783,11 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
     r0.valid = 0;
     PG_CUDA_NULL(cudaMemcpy(v.robust, &r0, sizeof(r0), cudaMemcpyHostToDevice));
   }
-  v.balls_cap = (int)std::min<size_t>(2 * n + 65536, (size_t)1 << 30);
+  v.balls_cap = (int)std::min<size_t>(4 * n + 65536, (size_t)1 << 30);
   PG_CUDA_NULL(cudaMalloc(&v.ball_c, sizeof(float4) * (size_t)v.balls_cap));
   PG_CUDA_NULL(cudaMalloc(&v.ball_e, sizeof(uint2) * (size_t)v.balls_cap));
   PG_CUDA_NULL(cudaMalloc(&v.head2, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
+  PG_CUDA_NULL(cudaMalloc(&v.head3, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
   v.huge_cap = 65536;
   PG_CUDA_NULL(cudaMalloc(&v.huge_list, sizeof(int) * (size_t)v.huge_cap));
   {
@@ -1783,7 +1834,7 @@ void pg_large_destroy(PgLarge *w) {
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
   if (w->player_world) pg_worlds_destroy(w->player_world);
-  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.ball_c, v.ball_e, v.head2, v.huge_list, v.vset, v.touched_bits, v.dirty_bits[0], v.dirty_bits[1], v.pushed_bits, v.block_sums, v.sorted,
+  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.ball_c, v.ball_e, v.head2, v.head3, v.huge_list, v.vset, v.touched_bits, v.dirty_bits[0], v.dirty_bits[1], v.pushed_bits, v.block_sums, v.sorted,
                   v.pairs, v.active, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
                   v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);
@@ -2030,6 +2081,7 @@ long long pg_large_pairs(PgLarge *w, float dt_in, int32_t *out_ij, long long cap
   PG_CUDA(cudaMemsetAsync(v.flags, 0, sizeof(Flags), w->stream));
   PG_CUDA(cudaMemsetAsync(v.rstat, 0, sizeof(float) * 8, w->stream));       // no running statistics here: plain bounding box
   PG_CUDA(cudaMemsetAsync(v.head2, 0xff, sizeof(unsigned) * ((size_t)v.cells_cap + 1), w->stream));
+  PG_CUDA(cudaMemsetAsync(v.head3, 0xff, sizeof(unsigned) * ((size_t)v.cells_cap + 1), w->stream));
   k_env_frozen<<<lw_grid(w, v.n, 256), 256, 0, w->stream>>>(v, dt);
   w->launches++;
   int rc = lw_build_pairs(w, dt);
