@@ -96,6 +96,7 @@ struct Flags {
   int overflow_balls;     // state-ball buffer full
   int overflow_vset;      // visit hash set full
   int overflow_huge;      // more balls beyond e_cap2 than their list holds
+  unsigned tail_max;      // largest radius on the tail level of the second structure (ordered-uint encoding; 0: level empty)
   unsigned n_balls;       // state balls linked so far this step
   unsigned balls_begin;   // ... of which [balls_begin, n_balls) appeared in the current iteration
   unsigned n_huge;        // balls beyond e_cap2 (on the list every query walks)
@@ -121,6 +122,9 @@ struct Flags {
 // needs -- the exact centre and velocity the phase's visits see (the gate's inputs), the ball radius, and the
 // entry id (2 * body + phase) -- without a second look-up.
 struct __align__(32) SortedBody { float4 crho; float vx, vy, vz; unsigned idx; };
+// One state ball: midpoint and radius, entry id (2 body + phase) | kRestBit, next ball of its cell (0xffffffff: none)
+// -- a whole sector, so that walking a cell's list costs one load per node.
+struct __align__(32) BallRec { float4 c; unsigned ent, next, pad0, pad1; };
 
 // Phase entries.  entry id e = 2 * body + phase (0 = A: before the body's own row integrates it, 1 = B: after).
 __device__ __forceinline__ float3 entry_mid(float cx, float cy, float cz, float vx, float vy, float vz, float dt) {
@@ -168,8 +172,7 @@ struct LargeView {
   float *rstat;                      // [8] sums over the bodies inside the previous robust box: x y z |dx| |dy| |dz| env count
   Robust *robust;
   // state balls (fixed point, step 4): append-only per step
-  float4 *ball_c;                    // [balls_cap] midpoint xyz, radius
-  uint2 *ball_e;                     // [balls_cap] .x = entry id (2 body + phase) | kRestBit, .y = next ball of its cell (0xffffffff: none)
+  struct BallRec *balls;             // [balls_cap] one 32-byte record per ball
   int balls_cap;
   unsigned *head2, *head3;           // [cells_cap] first ball of every cell of the second structure (0xffffffff: empty): balls up to
                                      // e_cap / up to e_cap2
@@ -546,19 +549,20 @@ __device__ __forceinline__ void ball_insert(const LargeView &v, const GridParams
   if (!(fabsf(m.x) < 1.0e15f && fabsf(m.y) < 1.0e15f && fabsf(m.z) < 1.0e15f && rho < 1.0e15f)) { atomicExch(&v.flags->unsafe, 1); return; }
   const unsigned idx = agg_inc(&v.flags->n_balls);
   if (idx >= (unsigned)v.balls_cap) { atomicExch(&v.flags->overflow_balls, 1); return; }
-  v.ball_c[idx] = make_float4(m.x, m.y, m.z, rho);
+  v.balls[idx].c = make_float4(m.x, m.y, m.z, rho);
   if (rho > g.e_cap2) {                          // beyond what a query's cell search covers: the list every query walks
     const unsigned hslot = atomicAdd(&v.flags->n_huge, 1u);
     if (hslot < (unsigned)v.huge_cap) v.huge_list[hslot] = (int)idx; else atomicExch(&v.flags->overflow_huge, 1);
-    v.ball_e[idx] = make_uint2(ent_flags, kNoBall);
+    *reinterpret_cast<uint2 *>(&v.balls[idx].ent) = make_uint2(ent_flags, kNoBall);
     return;
   }
   // two levels over the same cells: the bulk (radius <= e_cap: a query looks into 27 cells), and the tail up to
   // e_cap2 (few balls, searched wider)
   const int3 c = cell_coords(g, m.x, m.y, m.z);
   const unsigned cell = (unsigned)((c.z * g.dim[1] + c.y) * g.dim[0] + c.x);
-  unsigned *head = rho > g.e_cap ? v.head3 : v.head2;
-  v.ball_e[idx] = make_uint2(ent_flags, atomicExch(&head[cell], idx));
+  unsigned *head = v.head2;
+  if (rho > g.e_cap) { head = v.head3; atomicMax(&v.flags->tail_max, f2o(rho)); }
+  *reinterpret_cast<uint2 *>(&v.balls[idx].ent) = make_uint2(ent_flags, atomicExch(&head[cell], idx));
 }
 
 // Visit hash set (open addressing, linear probing): returns the slot if `key` was inserted, -1 if it was there.
@@ -1176,8 +1180,8 @@ __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
   const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
   const unsigned j0 = v.flags->balls_begin, j1 = min(v.flags->n_balls, (unsigned)v.balls_cap);
   for (unsigned j = j0 + warp; j < j1; j += n_warps) {
-    const float4 bc = v.ball_c[j];
-    const unsigned bflags = v.ball_e[j].x;
+    const float4 bc = v.balls[j].c;
+    const unsigned bflags = v.balls[j].ent;
     const int e = (int)(bflags & ~kRestBit), b = e >> 1;
     const bool rest_b = (bflags & kRestBit) != 0u;
     // the body's own untouched entry of the same phase (for the "already listed" test)
@@ -1237,26 +1241,38 @@ __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
         const int3 cc = cell_coords(g, bc.x, bc.y, bc.z);
         const int side = 2 * R + 1;
         const int x0 = max(cc.x - R, 0), x1 = min(cc.x + R, g.dim[0] - 1);
-        for (int r = 0; r < side * side; r++) {
-          const int y = cc.y + r % side - R, z = cc.z + r / side - R;
-          if (y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
-          const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
-          const unsigned a1 = v.cell_cnt[row + x1 + 1];
-          for (unsigned a = v.cell_cnt[row + x0] + lane; a < a1; a += 32u) {
-            const float4 cx = v.sorted[a].crho;
-            if (cx.w > g.e_cap) continue;                  // (linked in the second structure as well: found there)
-            const float4 wx = *reinterpret_cast<const float4 *>(&v.sorted[a].vx);
-            const unsigned idx = __float_as_uint(wx.w);
-            consider((int)(idx & ~kRestBit), (idx & kRestBit) != 0u, entry_mid(cx.x, cx.y, cx.z, wx.x, wx.y, wx.z, dt), cx.w, true);
+        // the bounds of up to 32 x-runs at a time, a lane each (independent loads), then the runs one after the
+        // other with the lanes on their entries
+        for (int r0 = 0; r0 < side * side; r0 += 32) {
+          unsigned my_a0 = 0u, my_a1 = 0u;
+          {
+            const int r = r0 + (int)lane;
+            const int y = cc.y + r % side - R, z = cc.z + r / side - R;
+            if (r < side * side && y >= 0 && y < g.dim[1] && z >= 0 && z < g.dim[2]) {
+              const unsigned row = (unsigned)((z * g.dim[1] + y) * g.dim[0]);
+              my_a0 = v.cell_cnt[row + x0]; my_a1 = v.cell_cnt[row + x1 + 1];
+            }
+          }
+          const int n_here = min(32, side * side - r0);
+          for (int q = 0; q < n_here; q++) {
+            const unsigned a0 = __shfl_sync(0xffffffffu, my_a0, q), a1 = __shfl_sync(0xffffffffu, my_a1, q);
+            for (unsigned a = a0 + lane; a < a1; a += 32u) {
+              const float4 cx = v.sorted[a].crho;
+              if (cx.w > g.e_cap) continue;                  // (linked in the second structure as well: found there)
+              const float4 wx = *reinterpret_cast<const float4 *>(&v.sorted[a].vx);
+              const unsigned idx = __float_as_uint(wx.w);
+              consider((int)(idx & ~kRestBit), (idx & kRestBit) != 0u, entry_mid(cx.x, cx.y, cx.z, wx.x, wx.y, wx.z, dt), cx.w, true);
+            }
           }
         }
       }
     }
     // (2) balls of the second structure: the bulk level (radius <= e_cap) rho + e_cap away at most, the tail level
     // (radius <= e_cap2) rho + e_cap2; a lane per cell, walking its list
-    for (int level = 0; level < 2; level++) {
+    const unsigned tail_o = v.flags->tail_max;      // (insertions and queries never share a kernel)
+    for (int level = 0; level < (tail_o ? 2 : 1); level++) {
       const unsigned *head = level ? v.head3 : v.head2;
-      const float need = (bc.w + (level ? g.e_cap2 : g.e_cap)) * g.inv_h * 1.001f;
+      const float need = (bc.w + (level ? fminf(g.e_cap2, o2f(tail_o)) : g.e_cap)) * g.inv_h * 1.001f;
       const int R = min(max((int)ceilf(need), 1), 64);
       const int3 cc = cell_coords(g, bc.x, bc.y, bc.z);
       const int side = 2 * R + 1;
@@ -1266,11 +1282,10 @@ __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
         if (x < 0 || x >= g.dim[0] || y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
         unsigned k = head[(unsigned)((z * g.dim[1] + y) * g.dim[0] + x)];
         while (k != kNoBall) {
-          const uint2 ke = v.ball_e[k];
-          if (k != j) {
-            const float4 kc = v.ball_c[k];
-            consider((int)(ke.x & ~kRestBit), (ke.x & kRestBit) != 0u, make_float3(kc.x, kc.y, kc.z), kc.w, false);
-          }
+          // both halves of the node in flight together (the walk is bound by the latency of its dependent loads)
+          const float4 kc = v.balls[k].c;
+          const uint2 ke = *reinterpret_cast<const uint2 *>(&v.balls[k].ent);
+          if (k != j) consider((int)(ke.x & ~kRestBit), (ke.x & kRestBit) != 0u, make_float3(kc.x, kc.y, kc.z), kc.w, false);
           k = ke.y;
         }
       }
@@ -1281,8 +1296,8 @@ __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
       for (unsigned h = lane; h < nh; h += 32u) {
         const unsigned k = (unsigned)v.huge_list[h];
         if (k == j) continue;
-        const float4 kc = v.ball_c[k];
-        const unsigned kx = v.ball_e[k].x;
+        const float4 kc = v.balls[k].c;
+        const unsigned kx = v.balls[k].ent;
         consider((int)(kx & ~kRestBit), (kx & kRestBit) != 0u, make_float3(kc.x, kc.y, kc.z), kc.w, false);
       }
     }
@@ -1544,19 +1559,17 @@ static int lw_grow_balls(PgLarge *w, unsigned used) {
   LargeView &v = w->v;
   if (v.balls_cap > (1 << 29)) { pg_set_error("large world: state-ball buffer at its limit (%d)", v.balls_cap); return PG_ERR_CAPACITY; }
   const int cap = std::max(v.balls_cap * 2, (int)std::min<unsigned>(used + used / 2, 1u << 30));
-  float4 *bc = nullptr; uint2 *be = nullptr;
-  if (cudaMalloc(&bc, sizeof(float4) * (size_t)cap) != cudaSuccess || cudaMalloc(&be, sizeof(uint2) * (size_t)cap) != cudaSuccess) {
+  BallRec *bigger = nullptr;
+  if (cudaMalloc(&bigger, sizeof(BallRec) * (size_t)cap) != cudaSuccess) {
     cudaGetLastError();
-    if (bc) cudaFree(bc);
     pg_set_error("large world: cannot grow the state-ball buffer to %d", cap);
     return PG_ERR_CAPACITY;
   }
   const size_t keep = std::min<size_t>(used, (size_t)v.balls_cap);
-  PG_CUDA(cudaMemcpyAsync(bc, v.ball_c, sizeof(float4) * keep, cudaMemcpyDeviceToDevice, w->stream));
-  PG_CUDA(cudaMemcpyAsync(be, v.ball_e, sizeof(uint2) * keep, cudaMemcpyDeviceToDevice, w->stream));
+  PG_CUDA(cudaMemcpyAsync(bigger, v.balls, sizeof(BallRec) * keep, cudaMemcpyDeviceToDevice, w->stream));
   PG_CUDA(cudaStreamSynchronize(w->stream));
-  cudaFree(v.ball_c); cudaFree(v.ball_e);
-  v.ball_c = bc; v.ball_e = be; v.balls_cap = cap;
+  cudaFree(v.balls);
+  v.balls = bigger; v.balls_cap = cap;
   return PG_OK;
 }
 
@@ -1784,8 +1797,7 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
     PG_CUDA_NULL(cudaMemcpy(v.robust, &r0, sizeof(r0), cudaMemcpyHostToDevice));
   }
   v.balls_cap = (int)std::min<size_t>(4 * n + 65536, (size_t)1 << 30);
-  PG_CUDA_NULL(cudaMalloc(&v.ball_c, sizeof(float4) * (size_t)v.balls_cap));
-  PG_CUDA_NULL(cudaMalloc(&v.ball_e, sizeof(uint2) * (size_t)v.balls_cap));
+  PG_CUDA_NULL(cudaMalloc(&v.balls, sizeof(BallRec) * (size_t)v.balls_cap));
   PG_CUDA_NULL(cudaMalloc(&v.head2, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.head3, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
   v.huge_cap = 65536;
@@ -1834,7 +1846,7 @@ void pg_large_destroy(PgLarge *w) {
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
   if (w->player_world) pg_worlds_destroy(w->player_world);
-  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.ball_c, v.ball_e, v.head2, v.head3, v.huge_list, v.vset, v.touched_bits, v.dirty_bits[0], v.dirty_bits[1], v.pushed_bits, v.block_sums, v.sorted,
+  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.balls, v.head2, v.head3, v.huge_list, v.vset, v.touched_bits, v.dirty_bits[0], v.dirty_bits[1], v.pushed_bits, v.block_sums, v.sorted,
                   v.pairs, v.active, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
                   v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);
