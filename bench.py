@@ -47,8 +47,11 @@ WORKLOADS = {
     "c5": dict(n_worlds=1, n_spheres=1048576, L=160.0, large=True, level=True,
                desc="static AABB slab level (8-unit lattice) + 1,048,576 spheres + player capsule"),
 }
-# algorithmic bytes per body-step of the streaming kernels of the large-world path
-LARGE_KERNEL_BYTES = {"k_pass3": 52, "k_cell_count": 20, "k_scan": 12, "k_scatter": 56, "k_pairs": 28, "k_finalize": 52}
+# algorithmic bytes per body-step of the streaming kernels of the large-world path (restated for
+# two phase entries per body -- DESIGN.md section 4.4): pass 3 reads the 32-byte state and writes the two entry radii;
+# the counting sort reads the state and the radii and writes cell + rank per entry, then writes one 32-byte record per
+# entry; the pair search reads both records of a body; the final kernel is the survey's "integrate"
+LARGE_KERNEL_BYTES = {"k_pass3": 40, "k_cell_count": 56, "k_scan": 12, "k_scatter": 120, "k_pairs": 64, "k_finalize": 52}
 
 
 def read_peaks():
@@ -311,7 +314,7 @@ def run_large_arm(args, cfg):
         peak, peak_src = read_peaks()
         per_kernel = {}
         traffic = {}
-        rj = os.path.join(ROOT, "profiles", "roofline_large_r01.json")
+        rj = os.path.join(ROOT, "profiles", "roofline_large_r02.json")
         if os.path.exists(rj) and n == 4194304:             # the capture is of the 4 M-body world
             try:
                 traffic = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in json.load(open(rj))["kernels"].items()}
