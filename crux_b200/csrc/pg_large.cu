@@ -721,7 +721,10 @@ __device__ __noinline__ bool listing_gate_rejects(float4 cr, float4 wr, float4 c
 // R = 1 entry leaves such partners to them.  Visits are staged in shared memory and appended to the global
 // list once per tile of kPairsBlock entries; a tile that finds more than kPairsStage (a dense pile)
 // appends the surplus directly.
-__global__ void __launch_bounds__(kPairsBlock) k_pairs(LargeView v, float dt) {
+#ifndef PG_PAIRS_MIN_BLOCKS
+#define PG_PAIRS_MIN_BLOCKS 8       // 64 registers: measured 1.31 -> 0.85 ms at 4 M bodies (96 registers, 5 blocks per SM before); 40 registers spill and lose 3x
+#endif
+__global__ void __launch_bounds__(kPairsBlock, PG_PAIRS_MIN_BLOCKS) k_pairs(LargeView v, float dt) {
   __shared__ int2 s_pairs[kPairsStage];
   __shared__ unsigned s_cnt;
   __shared__ unsigned long long s_base;
@@ -1328,7 +1331,10 @@ __global__ void k_iter_gate(LargeView v, int first) {
       (unsigned long long)f->n_vset * 4ull > v.vset_mask + 1ull || (long long)f->n_balls * 2 > (long long)v.balls_cap) { f->stop = 1; return; }
   f->iters_done++;
 }
-__global__ void k_eval(LargeView v, int src, int dst, int iter, float dt) { if (v.flags->stop) return; d_eval(v, src, dst, iter, dt); }
+#ifndef PG_EVAL_MIN_BLOCKS
+#define PG_EVAL_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(128, PG_EVAL_MIN_BLOCKS) k_eval(LargeView v, int src, int dst, int iter, float dt) { if (v.flags->stop) return; d_eval(v, src, dst, iter, dt); }
 __global__ void __launch_bounds__(512) k_eval_hard(LargeView v, int src, int dst, int iter, float dt) { if (v.flags->stop) return; d_eval_hard(v, src, dst, iter, dt); }
 __global__ void k_check(LargeView v, int src, int dst, int iter, float dt) { if (v.flags->stop) return; d_check(v, src, dst, iter, dt); }
 // One launch opens an iteration: the carry (per touched body) and the selection (per candidate pair) read the
