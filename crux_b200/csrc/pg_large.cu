@@ -1171,16 +1171,21 @@ __global__ void k_states_insert(LargeView v, int src, int dst, float dt) {
   }
 }
 
-// One WARP per ball of the current iteration: which entries of other bodies does it touch, and which visits does
+// One group of PG_QUERY_LANES lanes per ball of the current iteration: which entries of other bodies does it touch, and which visits does
 // that add?  Three sources of partners: the cell-sorted untouched entries (27 cells: the lanes take the entries of
 // each x-run), the state balls and large untouched entries linked in the second structure (a lane per cell, walking
 // its list), and the few balls beyond e_cap2 (list).  A visit the untouched entries of the two bodies already listed
 // (k_pairs: the same ball test, repeated here bit for bit) is skipped; the rest go through the hash set.
+#ifndef PG_QUERY_LANES
+#define PG_QUERY_LANES 8      // lanes per ball: the query is a chain of dependent loads, more balls in flight beat more lanes per ball
+#endif
 __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
   if (v.flags->stop) return;
+  constexpr unsigned G = PG_QUERY_LANES;
   const GridParams g = *v.grid;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned lane = threadIdx.x & (G - 1u);                          // lane within the ball's group
+  const unsigned gmask = G == 32u ? 0xffffffffu : (((1u << G) - 1u) << (threadIdx.x & 31u & ~(G - 1u)));
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) / G, n_warps = (gridDim.x * blockDim.x) / G;   // group index / count
   const unsigned j0 = v.flags->balls_begin, j1 = min(v.flags->n_balls, (unsigned)v.balls_cap);
   for (unsigned j = j0 + warp; j < j1; j += n_warps) {
     const float4 bc = v.balls[j].c;
@@ -1232,7 +1237,7 @@ __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
       const float need = (bc.w + g.e_cap) * g.inv_h * 1.001f;
       if (!(need <= (float)kMaxSearch)) {
         const unsigned n_sorted = v.cell_cnt[g.n_cells];
-        for (unsigned a = lane; a < n_sorted; a += 32u) {
+        for (unsigned a = lane; a < n_sorted; a += G) {
           const float4 cx = v.sorted[a].crho;
           const float4 wx = *reinterpret_cast<const float4 *>(&v.sorted[a].vx);
           const unsigned idx = __float_as_uint(wx.w);
@@ -1246,7 +1251,7 @@ __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
         const int x0 = max(cc.x - R, 0), x1 = min(cc.x + R, g.dim[0] - 1);
         // the bounds of up to 32 x-runs at a time, a lane each (independent loads), then the runs one after the
         // other with the lanes on their entries
-        for (int r0 = 0; r0 < side * side; r0 += 32) {
+        for (int r0 = 0; r0 < side * side; r0 += (int)G) {
           unsigned my_a0 = 0u, my_a1 = 0u;
           {
             const int r = r0 + (int)lane;
@@ -1256,10 +1261,10 @@ __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
               my_a0 = v.cell_cnt[row + x0]; my_a1 = v.cell_cnt[row + x1 + 1];
             }
           }
-          const int n_here = min(32, side * side - r0);
+          const int n_here = min((int)G, side * side - r0);
           for (int q = 0; q < n_here; q++) {
-            const unsigned a0 = __shfl_sync(0xffffffffu, my_a0, q), a1 = __shfl_sync(0xffffffffu, my_a1, q);
-            for (unsigned a = a0 + lane; a < a1; a += 32u) {
+            const unsigned a0 = __shfl_sync(gmask, my_a0, q, G), a1 = __shfl_sync(gmask, my_a1, q, G);
+            for (unsigned a = a0 + lane; a < a1; a += G) {
               const float4 cx = v.sorted[a].crho;
               if (cx.w > g.e_cap) continue;                  // (linked in the second structure as well: found there)
               const float4 wx = *reinterpret_cast<const float4 *>(&v.sorted[a].vx);
@@ -1280,7 +1285,7 @@ __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
       const int3 cc = cell_coords(g, bc.x, bc.y, bc.z);
       const int side = 2 * R + 1;
       const int n_cells_q = side * side * side;
-      for (int q = (int)lane; q < n_cells_q; q += 32) {
+      for (int q = (int)lane; q < n_cells_q; q += (int)G) {
         const int x = cc.x + q % side - R, y = cc.y + (q / side) % side - R, z = cc.z + q / (side * side) - R;
         if (x < 0 || x >= g.dim[0] || y < 0 || y >= g.dim[1] || z < 0 || z >= g.dim[2]) continue;
         unsigned k = head[(unsigned)((z * g.dim[1] + y) * g.dim[0] + x)];
@@ -1296,7 +1301,7 @@ __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
     // (3) the few balls beyond e_cap2
     {
       const unsigned nh = min(v.flags->n_huge, (unsigned)v.huge_cap);
-      for (unsigned h = lane; h < nh; h += 32u) {
+      for (unsigned h = lane; h < nh; h += G) {
         const unsigned k = (unsigned)v.huge_list[h];
         if (k == j) continue;
         const float4 kc = v.balls[k].c;
