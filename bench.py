@@ -317,7 +317,8 @@ def run_large_arm(args, cfg):
         rj = os.path.join(ROOT, "profiles", "roofline_large_r02.json")
         if os.path.exists(rj) and n == 4194304:             # the capture is of the 4 M-body world
             try:
-                traffic = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in json.load(open(rj))["kernels"].items()}
+                traffic = {k: v["dram_bytes_read"] + v["dram_bytes_write"] for k, v in json.load(open(rj))["kernels"].items()
+                           if v.get("dram_bytes_read") is not None}
             except Exception:
                 traffic = {}
         for k, b in LARGE_KERNEL_BYTES.items():

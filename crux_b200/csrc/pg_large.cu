@@ -1808,6 +1808,8 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
     PG_CUDA_NULL(cudaMemcpy(v.robust, &r0, sizeof(r0), cudaMemcpyHostToDevice));
   }
   v.balls_cap = (int)std::min<size_t>(4 * n + 65536, (size_t)1 << 30);
+  const bool tiny = getenv("PG_LARGE_TINY_BUFFERS") != nullptr;      // test hook: every growth / repeat path of the fixed point runs
+  if (tiny) { v.balls_cap = 256; v.pairs_cap = 4096; }
   PG_CUDA_NULL(cudaMalloc(&v.balls, sizeof(BallRec) * (size_t)v.balls_cap));
   PG_CUDA_NULL(cudaMalloc(&v.head2, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
   PG_CUDA_NULL(cudaMalloc(&v.head3, sizeof(unsigned) * ((size_t)v.cells_cap + 1)));
@@ -1816,6 +1818,7 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   {
     unsigned long long slots = 1ull << 16;
     while (slots < 8ull * n) slots <<= 1;
+    if (tiny) slots = 1ull << 12;
     v.vset_mask = slots - 1ull;
     PG_CUDA_NULL(cudaMalloc(&v.vset, sizeof(unsigned long long) * slots));
   }

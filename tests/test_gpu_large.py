@@ -24,11 +24,12 @@ def _ev(e):
 
 
 @pytest.mark.parametrize("n,L,steps,env", [(256, 10.0, 120, {}), (3000, 16.0, 40, {}), (20000, 40.0, 12, {}),
-                                           (3000, 16.0, 40, {"PG_LARGE_REQUERY_FEW": "0"}),      # k_requery's eight-lane path
+                                           (3000, 16.0, 40, {"PG_LARGE_ITER_BATCH": "1"}),       # one fixed-point iteration per host read-back
+                                           (3000, 12.0, 40, {"PG_LARGE_TINY_BUFFERS": "1"}),     # candidate list, ball buffer and hash set all have to grow
                                            (3000, 12.0, 30, {"PG_LARGE_SMALL_STAGES": "1"}),     # overflow paths of the block stages
                                            (3000, 12.0, 30, {"PG_LARGE_PASS3_SPLIT_MIN": "0"})]) # pass 3 as probe + dense exact kernel (large worlds)
 def test_large_world_equals_sequential_sweep(gpu_lib, oracle_lib, monkeypatch, n, L, steps, env):
-    for k in ("PG_LARGE_REQUERY_FEW", "PG_LARGE_SMALL_STAGES", "PG_LARGE_PASS3_SPLIT_MIN"):
+    for k in ("PG_LARGE_ITER_BATCH", "PG_LARGE_TINY_BUFFERS", "PG_LARGE_SMALL_STAGES", "PG_LARGE_PASS3_SPLIT_MIN"):
         monkeypatch.delenv(k, raising=False)
     for k, val in env.items():
         monkeypatch.setenv(k, val)                 # read by pg_large_create
