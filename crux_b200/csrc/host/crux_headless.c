@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "crux_scene.h"
 
@@ -139,8 +140,11 @@ int main(int argc, char **argv) {
   CruxScene *s = crux_scene_load(argv[1], player);
   if (!s) return 1;
   const float dt = 1.0f / 60.0f;
+  struct timespec t_begin, t_end;
+  clock_gettime(CLOCK_MONOTONIC, &t_begin);
   if (device_steps && !script) crux_scene_update_n(s, dt, steps);
   else for (int k = 0; k < steps; k++) {
+    if (k == 100) clock_gettime(CLOCK_MONOTONIC, &t_begin);      /* (device and library start-up stay out of the figure) */
     script_before_frame(s, script, k, dt);
 #ifdef CRUX_HAVE_UPLOAD_STATS
     const unsigned long long up0 = physics_world_uploaded_records(s->world);
@@ -151,7 +155,13 @@ int main(int argc, char **argv) {
 #endif
     script_after_frame(s, script);
   }
+  clock_gettime(CLOCK_MONOTONIC, &t_end);
   if (script) printf("script %s: %d bodies removed, %d jumps\n", script, g_removed, g_jumps);
+  {
+    const int timed = (device_steps && !script) ? steps : (steps > 100 ? steps - 100 : steps);
+    printf("frame loop: %.1f us per frame (%d frames timed)\n",
+           ((t_end.tv_sec - t_begin.tv_sec) * 1e6 + (t_end.tv_nsec - t_begin.tv_nsec) * 1e-3) / (timed > 0 ? timed : 1), timed);
+  }
   FILE *f = fopen(argv[3], "wb");
   if (!f) return 1;
   int hdr[4] = {(int)s->world->num_static_bodies, (int)s->world->num_dynamic_bodies, (int)s->world->num_player_bodies, g_nev};

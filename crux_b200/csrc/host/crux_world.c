@@ -23,6 +23,7 @@
 
 #define MAX_PHYSICS_BODIES 128          /* world.c:15 */
 #define CRUX_MAX_EVENTS 4096
+#define CRUX_MAX_RANGES 4               /* dirty ranges per class and frame before they are merged into one */
 
 typedef struct Shadow {
   struct PhysicsWorld *world;
@@ -33,6 +34,8 @@ typedef struct Shadow {
   int dev_n[3];               /* ... and how many records of each class; -1 = unknown, upload everything */
   int rec_cap[3];
   unsigned long long uploaded_records;   /* statistics: body records sent to the device so far */
+  PgBody *up;                 /* this frame's dirty records, back to back in range order */
+  size_t up_cap;
   PgEvent *events;
   struct Shadow *next;
 } Shadow;
@@ -134,7 +137,7 @@ void physics_world_release_gpu(struct PhysicsWorld *world) {
       *pp = s->next;
       if (s->gpu) pg_worlds_destroy(s->gpu);
       for (int c = 0; c < 3; c++) { free(s->rec[c]); free(s->dev[c]); }
-      free(s->events);
+      free(s->events); free(s->up);
       free(s);
       return;
     }
@@ -287,48 +290,63 @@ static void replay_events(Shadow *s, long long n_events) {
 static void step_impl(struct PhysicsWorld *physics_world, float delta_time, int n_steps, int refresh_nodes) {
   Shadow *s = shadow_find(physics_world, 1);
   if (!s || ensure_gpu(s)) return;
+  /* The host arrays are the truth (player.c and the scene poke them between frames), the device keeps a copy:
+   * only the records that differ from what it holds travel, as contiguous dirty ranges (a class whose length
+   * changed -- physics_add_body / physics_remove_body -- goes whole).  The whole frame is ONE call into the
+   * C-ABI and one synchronisation (pg_worlds_frame): a game-sized scene is bound by round trips, not by work. */
+  PgRange ranges[3 * CRUX_MAX_RANGES];
+  int n_ranges = 0;
+  int32_t counts[3];
+  size_t n_up = 0;
   for (int c = 0; c < 3; c++) {
     unsigned int n;
     struct PhysicsBody *arr = class_array(physics_world, c, &n);
+    counts[c] = (int32_t)n;
     for (unsigned int i = 0; i < n; i++) crux_flatten_body(&arr[i], &s->rec[c][i]);
-    /* The host arrays are the truth (player.c and the scene poke them between frames), the device keeps
-     * a copy: send only the records that differ from what it holds, as contiguous dirty ranges.  A class
-     * whose length changed (physics_add_body / physics_remove_body) is sent whole. */
-    int rc = PG_OK;
     if (s->dev_n[c] != (int)n) {
-      rc = pg_worlds_set_bodies(s->gpu, 0, c, s->rec[c], (int)n);
-      s->uploaded_records += n;
-    } else {
-      unsigned int i = 0;
-      while (i < n && rc == PG_OK) {
-        if (memcmp(&s->rec[c][i], &s->dev[c][i], sizeof(PgBody)) == 0) { i++; continue; }
-        unsigned int j = i + 1;
-        while (j < n && memcmp(&s->rec[c][j], &s->dev[c][j], sizeof(PgBody)) != 0) j++;
-        rc = pg_worlds_update_bodies(s->gpu, 0, c, (int)i, &s->rec[c][i], (int)(j - i));
-        s->uploaded_records += j - i;
-        i = j;
+      if (n) { ranges[n_ranges].cls = c; ranges[n_ranges].first = 0; ranges[n_ranges].count = (int32_t)n; n_ranges++; }
+      continue;
+    }
+    const int first_range = n_ranges;
+    unsigned int i = 0;
+    while (i < n) {
+      if (memcmp(&s->rec[c][i], &s->dev[c][i], sizeof(PgBody)) == 0) { i++; continue; }
+      unsigned int j = i + 1;
+      while (j < n && memcmp(&s->rec[c][j], &s->dev[c][j], sizeof(PgBody)) != 0) j++;
+      if (n_ranges - first_range == CRUX_MAX_RANGES) {
+        /* too fragmented: one range from the first dirty record of the class to this run's end */
+        n_ranges = first_range + 1;
+        ranges[first_range].count = (int32_t)j - ranges[first_range].first;
+      } else {
+        ranges[n_ranges].cls = c; ranges[n_ranges].first = (int32_t)i; ranges[n_ranges].count = (int32_t)(j - i); n_ranges++;
       }
+      i = j;
     }
-    if (rc != PG_OK) {
-      fprintf(stderr, "Error: physics_step: upload failed (%s)\n", pg_last_error());
-      s->dev_n[c] = -1;
-      return;
-    }
-    s->dev_n[c] = (int)n;
   }
-  if (pg_worlds_step(s->gpu, delta_time, n_steps, refresh_nodes) != PG_OK) {
-    fprintf(stderr, "Error: physics_step: launch failed (%s)\n", pg_last_error());
+  for (int r = 0; r < n_ranges; r++) n_up += (size_t)ranges[r].count;
+  if (n_up > s->up_cap) {
+    s->up_cap = n_up * 2 + 16;
+    s->up = (PgBody *)realloc(s->up, sizeof(PgBody) * s->up_cap);
+  }
+  size_t at = 0;
+  for (int r = 0; r < n_ranges; r++) {
+    memcpy(s->up + at, &s->rec[ranges[r].cls][ranges[r].first], sizeof(PgBody) * (size_t)ranges[r].count);
+    at += (size_t)ranges[r].count;
+  }
+  long long n_events = 0;
+  int overflow = 0;
+  if (pg_worlds_frame(s->gpu, 0, counts, ranges, n_ranges, s->up, delta_time, n_steps, refresh_nodes,
+                      s->rec[0], s->rec[1], s->rec[2], s->events, CRUX_MAX_EVENTS, &n_events, &overflow) != PG_OK) {
+    fprintf(stderr, "Error: physics_step: %s\n", pg_last_error());
+    for (int c = 0; c < 3; c++) s->dev_n[c] = -1;
     return;
   }
+  s->uploaded_records += n_up;
   for (int c = 0; c < 3; c++) {
     unsigned int n;
     struct PhysicsBody *arr = class_array(physics_world, c, &n);
+    s->dev_n[c] = (int)n;
     if (n == 0) continue;
-    if (pg_worlds_get_bodies(s->gpu, 0, c, s->rec[c], s->rec_cap[c]) != (int)n) {
-      fprintf(stderr, "Error: physics_step: download failed (%s)\n", pg_last_error());
-      s->dev_n[c] = -1;
-      return;
-    }
     memcpy(s->dev[c], s->rec[c], sizeof(PgBody) * (size_t)n);
     for (unsigned int i = 0; i < n; i++) {
       unflatten_state(&s->rec[c][i], &arr[i]);
@@ -342,8 +360,6 @@ static void step_impl(struct PhysicsWorld *physics_world, float delta_time, int 
       }
     }
   }
-  int overflow = 0;
-  long long n_events = pg_worlds_events(s->gpu, s->events, CRUX_MAX_EVENTS, &overflow);
   if (n_events > CRUX_MAX_EVENTS) n_events = CRUX_MAX_EVENTS;
   if (overflow) fprintf(stderr, "Error: physics_step: more than %d contacts in one call, the rest are dropped\n", CRUX_MAX_EVENTS);
   if (n_events > 0) replay_events(s, n_events);

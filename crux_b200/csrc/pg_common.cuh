@@ -94,6 +94,10 @@ struct PgWorlds {
   size_t stage_packed_bytes;
   int *d_pipe_counters;       // one hand-out counter per chunk
   bool pipe_ready;
+  // single-round-trip frame path (pg_worlds_frame): pinned staging for dirty records in, all records + events out
+  unsigned char *h_frame;         // pinned
+  size_t h_frame_bytes;
+  unsigned char *h_types[3];      // host mirror of the collider types per class of the frame path's world (licence for the parallel pass 3)
   // the whole chunk pipeline as one CUDA graph, re-captured when the host buffers or the step change
   cudaGraphExec_t pipe_graph;
   const void *pipe_key_ptr[3];

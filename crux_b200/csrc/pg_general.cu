@@ -13,7 +13,9 @@
 #include "pg_common.cuh"
 #include "pg_math.cuh"
 
+#include <algorithm>
 #include <climits>
+#include <cstdlib>
 
 namespace {
 
@@ -150,6 +152,271 @@ k_step_general(WorldsView v, float dt_in, int n_steps, int refresh_nodes, int st
   }
 }
 
+// ---------------------------------------------------------------- game-sized worlds: speculate, then commit in order
+// k_step_general walks the sweep row by row with two block barriers per row: 140 us per physics_step for the 15
+// bodies of scenes/bouncehouse.json, nearly all of it barrier and load latency.  A game-sized world has a few hundred
+// visits per step and about one contact, so: evaluate EVERY visit of the step at once, one per thread, on the state
+// it will see if no contact intervenes (a body integrated or not according to where its own row ends in the sweep);
+// then find the earliest visit that fires, bring the real state up to it (the integrations that lie before it),
+// commit it exactly as the sequential loop would, and re-evaluate only the later visits of the two bodies it
+// changed.  One round per contact; a step without contacts is one round.  Same visits, same order, same arithmetic:
+// the result is the sequential one.
+constexpr int kSmallMaxVisits = 2048;
+constexpr int kSmallBudget = 24;         // nodes of interval_collision's recursion a single thread explores before the visit goes to the block
+constexpr int kSmallStack = 2048;        // open nodes the block-wide search can hold
+
+// interval_collision (world.c:557-582) with a node budget: 0 = false, 1 = true, 2 = still undecided after
+// `budget` nodes.  Same tree, same end-point tests as pgm::interval_hit.
+__device__ int interval_hit_budget(const PgBody &A, const PgBody &B, float t_begin, float t_end, int budget) {
+  unsigned long long path = 0;
+  int depth = 0;
+  float t0 = t_begin, t1 = t_end;
+  for (;;) {
+    if (--budget < 0) return 2;
+    const float mm = pgm::max_move(A, t0, t1) + pgm::max_move(B, t0, t1);
+    const bool open = !(pgm::min_dist(A, B, t0) > mm) && !(pgm::min_dist(A, B, t1) > mm);
+    if (open) {
+      if (t1 - t0 < pgm::kIntervalEps) return 1;
+      if (depth >= 62) return 0;
+      path <<= 1; depth++;
+      t1 = (t0 + t1) * 0.5f;
+      continue;
+    }
+    while (depth > 0 && (path & 1ull)) { path >>= 1; depth--; }
+    if (depth == 0) return 0;
+    path |= 1ull;
+    t0 = t_begin; t1 = t_end;
+    for (int k = depth - 1; k >= 0; k--) {
+      const float mid = (t0 + t1) * 0.5f;
+      if ((path >> k) & 1ull) t0 = mid; else t1 = mid;
+    }
+  }
+}
+
+// The same search by the whole block (all threads, identical arguments).  Only the boolean "some leaf survives with
+// all its ancestors" is consumed (hit_time is never read, world.c:196-198), so the ORDER in which the tree is
+// explored is free: the open nodes sit on a shared stack, every round the threads take the top ones (deepest
+// first), test them exactly as the recursion would -- end points re-derived from the root by the same
+// (t0+t1)*0.5f sequence -- and push the children of those that pass.  A grazing pair's hundreds to thousands of
+// nodes take tens of rounds instead of one thread's milliseconds.
+struct BlockSearch {
+  unsigned long long stack[kSmallStack];          // node = depth << 56 | path
+  int top, found, overflow;
+};
+__device__ bool interval_hit_block(const PgBody &A, const PgBody &B, float t_begin, float t_end, BlockSearch &bs) {
+  __syncthreads();
+  if (threadIdx.x == 0) { bs.stack[0] = 0ull; bs.top = 1; bs.found = 0; bs.overflow = 0; }
+  __syncthreads();
+  for (;;) {
+    const int n = bs.top;
+    const bool stop = n == 0 || bs.found || bs.overflow;
+    __syncthreads();
+    if (stop) break;
+    const int take = min(n, (int)blockDim.x), base = n - take;
+    unsigned long long node = 0ull;
+    if ((int)threadIdx.x < take) node = bs.stack[base + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) bs.top = base;
+    __syncthreads();
+    if ((int)threadIdx.x < take) {
+      const int depth = (int)(node >> 56);
+      const unsigned long long path = node & 0x00ffffffffffffffull;
+      float t0 = t_begin, t1 = t_end;
+      for (int k = depth - 1; k >= 0; k--) {
+        const float mid = (t0 + t1) * 0.5f;
+        if ((path >> k) & 1ull) t0 = mid; else t1 = mid;
+      }
+      const float mm = pgm::max_move(A, t0, t1) + pgm::max_move(B, t0, t1);
+      if (!(pgm::min_dist(A, B, t0) > mm) && !(pgm::min_dist(A, B, t1) > mm)) {
+        if (t1 - t0 < pgm::kIntervalEps) atomicExch(&bs.found, 1);
+        else if (depth >= 55) atomicExch(&bs.overflow, 1);
+        else {
+          const int pos = atomicAdd(&bs.top, 2);
+          if (pos + 2 <= kSmallStack) {
+            bs.stack[pos] = ((unsigned long long)(depth + 1) << 56) | (path << 1) | 1ull;      // right child below,
+            bs.stack[pos + 1] = ((unsigned long long)(depth + 1) << 56) | (path << 1);        // left child on top
+          } else atomicExch(&bs.overflow, 1);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const bool overflow = bs.overflow != 0, found = bs.found != 0;
+  __syncthreads();
+  if (overflow) { float h; return pgm::interval_hit(A, B, t_begin, t_end, &h); }      // (every thread alone: slow, but the same answer)
+  return found;
+}
+
+struct SmallPlan {
+  int ns, nd, np;
+  int v1, v2, v3, v4;          // visits per pass (world.c:180, 277, 369, 473)
+  __device__ int total() const { return v1 + v2 + v3 + v4; }
+  // visit k of the sweep -> row body (class, index), column body (class, index), pass
+  __device__ void decode(int k, int &rc, int &ri, int &cc, int &ci, int &pass) const {
+    if (k < v1) { pass = 1; rc = PG_CLASS_PLAYER; ri = k / ns; cc = PG_CLASS_STATIC; ci = k % ns; return; }
+    k -= v1;
+    if (k < v2) { pass = 2; rc = PG_CLASS_PLAYER; ri = k / nd; cc = PG_CLASS_DYNAMIC; ci = k % nd; return; }
+    k -= v2;
+    if (k < v3) { pass = 3; rc = PG_CLASS_DYNAMIC; ri = k / ns; cc = PG_CLASS_STATIC; ci = k % ns; return; }
+    k -= v3;
+    pass = 4; rc = PG_CLASS_DYNAMIC; cc = PG_CLASS_DYNAMIC;
+    ri = k / (nd - 1);
+    const int jj = k % (nd - 1);
+    ci = jj + (jj >= ri ? 1 : 0);
+  }
+  // index of the first visit AFTER body (cls, i) has been integrated by its own row (world.c:362-366, 549-553);
+  // statics never are
+  __device__ int int_point(int cls, int i) const {
+    if (cls == PG_CLASS_PLAYER) return v1 + (i + 1) * nd;
+    if (cls == PG_CLASS_DYNAMIC) return v1 + v2 + v3 + (i + 1) * (nd - 1);
+    return 0x7fffffff;
+  }
+};
+
+__device__ __forceinline__ PgBody *small_body(PgBody *S, PgBody *D, PgBody *P, int cls, int i) {
+  return cls == PG_CLASS_STATIC ? S + i : (cls == PG_CLASS_DYNAMIC ? D + i : P + i);
+}
+
+// Read-only half of a visit (world.c:481-502) with the interval search either bounded (bs == nullptr: one thread,
+// 2 = undecided) or run by the whole block (bs != nullptr: all threads, identical arguments).
+__device__ int test_visit_small(const PgBody &x, const PgBody &y, float dt, float *t_hit, BlockSearch *bs) {
+  const bool swap = x.collider_type > y.collider_type;
+  const PgBody &A = swap ? y : x;
+  const PgBody &B = swap ? x : y;
+  if (bs) { if (!interval_hit_block(A, B, 0.0f, dt, *bs)) return 0; }
+  else {
+    const int r = interval_hit_budget(A, B, 0.0f, dt, kSmallBudget);
+    if (r != 1) return r;
+  }
+  bool has;
+  pgm::Contact c = pgm::narrow(A, B, dt, &has);
+  if (!has || !(c.hit && c.t >= 0)) return 0;
+  *t_hit = c.t;
+  return 1;
+}
+
+// Would visit k fire, on the real state (integrations with point <= `applied` done) plus the integrations that lie
+// between `applied` and k?  0 / 1, or 2 = undecided (bs == nullptr only).
+__device__ int small_test(const SmallPlan &pl, PgBody *S, PgBody *D, PgBody *P, int k, int applied, float dt, float *t_hit, BlockSearch *bs,
+                          PgBody *s_tmp) {
+  int rc, ri, cc, ci, pass;
+  pl.decode(k, rc, ri, cc, ci, pass);
+  const PgBody *row = small_body(S, D, P, rc, ri);        // a row body is never integrated before its own visits
+  const PgBody *col = small_body(S, D, P, cc, ci);
+  const int ip = pl.int_point(cc, ci);
+  if (ip > applied && ip <= k && !col->at_rest) {
+    // the column as its own row's integration will leave it
+    if (bs) {
+      __syncthreads();
+      if (threadIdx.x == 0) { *s_tmp = *col; integrate_body(*s_tmp, dt); }
+      __syncthreads();
+      return test_visit_small(*row, *s_tmp, dt, t_hit, bs);
+    }
+    PgBody tmp = *col;
+    integrate_body(tmp, dt);
+    return test_visit_small(*row, tmp, dt, t_hit, nullptr);
+  }
+  return test_visit_small(*row, *col, dt, t_hit, bs);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_step_small(WorldsView v, float dt_in, int n_steps, int refresh_nodes) {
+  __shared__ unsigned char s_fire[kSmallMaxVisits];      // 0 / 1, 2 = the single-thread search ran out of budget
+  __shared__ float s_t[kSmallMaxVisits];
+  __shared__ int s_min;
+  __shared__ BlockSearch s_bs;
+  __shared__ PgBody s_tmp;
+  const int w = blockIdx.x;
+  if (w >= v.n_worlds) return;
+  PgBody *S = v.bodies[0] + (size_t)w * v.cap[0];
+  PgBody *D = v.bodies[1] + (size_t)w * v.cap[1];
+  PgBody *P = v.bodies[2] + (size_t)w * v.cap[2];
+  SmallPlan pl;
+  pl.ns = v.counts[w * 3 + 0]; pl.nd = v.counts[w * 3 + 1]; pl.np = v.counts[w * 3 + 2];
+  pl.v1 = pl.np * pl.ns; pl.v2 = pl.np * pl.nd; pl.v3 = pl.nd * pl.ns; pl.v4 = pl.nd * (pl.nd - 1);
+  const int V = pl.total();
+  const float dt = pgm::clamp_dt(dt_in);
+  EventSink sink;
+  sink.buf = v.events + (size_t)w * v.max_events;
+  sink.counter = v.n_events + w;
+  sink.cap = v.max_events;
+  sink.world = w;
+  // the integrations whose point lies in (applied, to] happen for real
+  int applied = -1;
+  auto advance = [&](int to) {
+    for (int b = threadIdx.x; b < pl.np + pl.nd; b += kThreads) {
+      const int cls = b < pl.np ? PG_CLASS_PLAYER : PG_CLASS_DYNAMIC, i = b < pl.np ? b : b - pl.np;
+      const int ip = pl.int_point(cls, i);
+      if (ip > applied && ip <= to) integrate_body(*small_body(S, D, P, cls, i), dt);
+    }
+    applied = to;
+    __syncthreads();
+  };
+  for (int step = 0; step < n_steps; step++) {
+    sink.step = step;
+    int cursor = 0;
+    applied = -1;
+    for (int k = threadIdx.x; k < V; k += kThreads) {
+      float t = 0.0f;
+      s_fire[k] = (unsigned char)small_test(pl, S, D, P, k, -1, dt, &t, nullptr, nullptr);
+      s_t[k] = t;
+    }
+    __syncthreads();
+    // visits whose interval search is a long one: the whole block decides them, one after the other
+    auto settle_hard = [&](int from) {
+      for (int k = from; k < V; k++) {
+        if (s_fire[k] != 2) continue;                    // (uniform: shared memory, read between barriers)
+        float t = 0.0f;
+        const int r = small_test(pl, S, D, P, k, applied, dt, &t, &s_bs, &s_tmp);
+        __syncthreads();
+        if (threadIdx.x == 0) { s_fire[k] = (unsigned char)r; s_t[k] = t; }
+        __syncthreads();
+      }
+    };
+    settle_hard(0);
+    for (;;) {
+      if (threadIdx.x == 0) s_min = INT_MAX;
+      __syncthreads();
+      int found = INT_MAX;
+      for (int k = cursor + (int)threadIdx.x; k < V; k += kThreads) if (s_fire[k]) { found = k; break; }
+      if (found != INT_MAX) atomicMin(&s_min, found);
+      __syncthreads();
+      const int kmin = s_min;
+      __syncthreads();
+      if (kmin == INT_MAX) break;
+      advance(kmin);                            // the real state as visit kmin sees it
+      int rc, ri, cc, ci, pass;
+      pl.decode(kmin, rc, ri, cc, ci, pass);
+      if (threadIdx.x == 0)
+        commit_visit(*small_body(S, D, P, rc, ri), rc, ri, *small_body(S, D, P, cc, ci), cc, ci, s_t[kmin], sink, pass);
+      __syncthreads();
+      advance(kmin + 1);                        // a row that ended with this very visit integrates now
+      cursor = kmin + 1;
+      // the two bodies changed: their later visits are evaluated again (everything else stands)
+      for (int k = cursor + (int)threadIdx.x; k < V; k += kThreads) {
+        int rc2, ri2, cc2, ci2, p2;
+        pl.decode(k, rc2, ri2, cc2, ci2, p2);
+        const bool hit_row = (rc2 == rc && ri2 == ri) || (rc2 == cc && ri2 == ci);
+        const bool hit_col = (cc2 == rc && ci2 == ri) || (cc2 == cc && ci2 == ci);
+        if (!hit_row && !hit_col) continue;
+        float t = 0.0f;
+        s_fire[k] = (unsigned char)small_test(pl, S, D, P, k, applied, dt, &t, nullptr, nullptr);
+        s_t[k] = t;
+      }
+      __syncthreads();
+      settle_hard(cursor);
+    }
+    advance(0x7ffffffe);                        // the integrations that are left
+    // scene_node_update of every node (scene.c:1051-1079), as scene_update does after the step
+    if (refresh_nodes) {
+      for (int i = threadIdx.x; i < pl.ns; i += kThreads) if (S[i].has_node) pgm::node_refresh(S[i]);
+      for (int i = threadIdx.x; i < pl.nd; i += kThreads) if (D[i].has_node) pgm::node_refresh(D[i]);
+      for (int i = threadIdx.x; i < pl.np; i += kThreads) if (P[i].has_node) pgm::node_refresh(P[i]);
+      __syncthreads();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- per-pair kernels (pg_pair_*)
 
 __global__ void k_pair_max_move(const PgBody *a, int n, float t0, float t1, float *out) {
@@ -230,6 +497,19 @@ struct DevBuf {
 }  // namespace
 
 int pg_launch_general_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes) {
+  // game-sized worlds (every world of the handle has at most kSmallMaxVisits visits per step): speculate + commit
+  static const bool no_small = getenv("PG_GENERAL_ROW_SWEEP") != nullptr;
+  long long worst = 0;
+  for (int wd = 0; wd < w->v.n_worlds; wd++) {
+    const long long ns = w->h_counts[wd * 3 + 0], nd = w->h_counts[wd * 3 + 1], np = w->h_counts[wd * 3 + 2];
+    worst = std::max(worst, np * ns + np * nd + nd * ns + nd * (nd - 1));
+  }
+  if (!no_small && worst <= kSmallMaxVisits) {
+    k_step_small<<<w->v.n_worlds, kThreads, 0, w->stream>>>(w->v, dt, n_steps, refresh_nodes);
+    PG_CUDA(cudaGetLastError());
+    w->launches++;
+    return PG_OK;
+  }
   k_step_general<<<w->v.n_worlds, kThreads, 0, w->stream>>>(w->v, dt, n_steps, refresh_nodes,
                                                              w->static_pass_parallel_ok ? 1 : 0);
   PG_CUDA(cudaGetLastError());

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdlib>
+#include <ctime>
 #include <vector>
 
 static thread_local char g_err[512] = "";
@@ -209,6 +210,8 @@ void pg_worlds_destroy(PgWorlds *w) {
   }
   if (w->d_stage_pos) { cudaFree(w->d_stage_pos); cudaFree(w->d_stage_vel); cudaFree(w->d_stage_rest); }
   if (w->d_stage_packed) cudaFree(w->d_stage_packed);
+  if (w->h_frame) cudaFreeHost(w->h_frame);
+  for (int c = 0; c < 3; c++) free(w->h_types[c]);
   cudaEventDestroy(w->ev0);
   cudaEventDestroy(w->ev1);
   cudaStreamDestroy(w->stream);
@@ -548,6 +551,8 @@ static int step_host_impl(PgWorlds *w, float dt, int n_steps, const HostState &h
     const size_t bytes = (size_t)nw * h.stride;
     if (bytes > w->stage_packed_bytes) {
       if (w->d_stage_packed) cudaFree(w->d_stage_packed);
+  if (w->h_frame) cudaFreeHost(w->h_frame);
+  for (int c = 0; c < 3; c++) free(w->h_types[c]);
       w->d_stage_packed = nullptr; w->stage_packed_bytes = 0;
       PG_CUDA(cudaMalloc(&w->d_stage_packed, bytes));
       w->stage_packed_bytes = bytes;
@@ -717,6 +722,121 @@ static inline long long event_key_row(const PgEvent &e) {
   return ((long long)row << 32) | (unsigned)col;
 }
 
+// restore solve order: step, pass, row, column (device slots are claimed atomically); pad_ -> pass number
+static void sort_events(PgEvent *buf, int n) {
+  std::stable_sort(buf, buf + n, [](const PgEvent &a, const PgEvent &b) {
+    if (a.step != b.step) return a.step < b.step;
+    const int pa = a.pad_ >> 8, pb = b.pad_ >> 8;
+    if (pa != pb) return pa < pb;
+    return event_key_row(a) < event_key_row(b);
+  });
+  for (int i = 0; i < n; i++) buf[i].pad_ >>= 8;
+}
+
+int pg_worlds_frame(PgWorlds *w, int world, const int32_t counts[3], const PgRange *ranges, int n_ranges,
+                    const PgBody *records, float dt, int n_steps, int refresh_nodes,
+                    PgBody *out_static, PgBody *out_dynamic, PgBody *out_player,
+                    PgEvent *events, long long events_cap, long long *n_events, int *overflowed) {
+  if (!valid_world(w, world) || !counts || n_ranges < 0 || (n_ranges > 0 && (!ranges || !records)) || n_steps < 0) { pg_set_error("pg_worlds_frame: bad argument"); return PG_ERR_ARG; }
+  if (w->mode != PG_MODE_GENERAL) { pg_set_error("handle is in sphere mode"); return PG_ERR_ARG; }
+  for (int c = 0; c < 3; c++) if (counts[c] < 0 || counts[c] > w->v.cap[c]) { pg_set_error("pg_worlds_frame: class %d: %d bodies > capacity %d", c, counts[c], w->v.cap[c]); return PG_ERR_CAPACITY; }
+  size_t n_up = 0;
+  for (int r = 0; r < n_ranges; r++) {
+    const PgRange &g = ranges[r];
+    if (g.cls < 0 || g.cls > 2 || g.first < 0 || g.count < 0 || g.first + g.count > counts[g.cls]) { pg_set_error("pg_worlds_frame: bad range %d", r); return PG_ERR_ARG; }
+    n_up += (size_t)g.count;
+  }
+  static const bool frame_timing = getenv("PG_FRAME_TIMING") != nullptr;
+  static double t_acc[5] = {0, 0, 0, 0, 0};
+  static long n_acc = 0;
+  auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+  const double t0 = frame_timing ? now() : 0.0;
+  PG_CUDA(cudaSetDevice(w->device));
+  int rc = ensure_records(w);
+  if (rc) return rc;
+  // pinned staging: [ dirty records in | records of the three classes out | event counter | events out ]
+  const size_t cap_all = (size_t)w->v.cap[0] + w->v.cap[1] + w->v.cap[2];
+  const size_t off_out = sizeof(PgBody) * cap_all, off_cnt = off_out + sizeof(PgBody) * cap_all, off_ev = off_cnt + 64;
+  const size_t need = off_ev + sizeof(PgEvent) * (size_t)std::max(w->v.max_events, 1);
+  if (need > w->h_frame_bytes) {
+    if (w->h_frame) cudaFreeHost(w->h_frame);
+    w->h_frame = nullptr; w->h_frame_bytes = 0;
+    PG_CUDA(cudaHostAlloc((void **)&w->h_frame, need, cudaHostAllocDefault));
+    w->h_frame_bytes = need;
+    for (int c = 0; c < 3; c++) { free(w->h_types[c]); w->h_types[c] = (unsigned char *)calloc((size_t)w->v.cap[c], 1); }
+  }
+  if (n_up > cap_all) { pg_set_error("pg_worlds_frame: ranges overlap (more records than the world holds)"); return PG_ERR_ARG; }
+  // dirty records: one memcpy into the pinned block, one asynchronous copy per range out of it
+  PgBody *h_in = reinterpret_cast<PgBody *>(w->h_frame);
+  if (n_up) memcpy(h_in, records, sizeof(PgBody) * n_up);
+  size_t at = 0;
+  for (int r = 0; r < n_ranges; r++) {
+    const PgRange &g = ranges[r];
+    if (g.count == 0) continue;
+    PG_CUDA(cudaMemcpyAsync(w->v.bodies[g.cls] + (size_t)world * w->v.cap[g.cls] + g.first, h_in + at, sizeof(PgBody) * (size_t)g.count,
+                            cudaMemcpyHostToDevice, w->stream));
+    for (int i = 0; i < g.count; i++) w->h_types[g.cls][g.first + i] = (unsigned char)h_in[at + i].collider_type;
+    at += (size_t)g.count;
+  }
+  bool counts_changed = false;
+  for (int c = 0; c < 3; c++) if (w->h_counts[world * 3 + c] != counts[c]) { w->h_counts[world * 3 + c] = counts[c]; counts_changed = true; }
+  int *h_cnt = reinterpret_cast<int *>(w->h_frame + off_cnt);
+  if (counts_changed) {
+    for (int c = 0; c < 3; c++) h_cnt[4 + c] = counts[c];
+    PG_CUDA(cudaMemcpyAsync(w->v.counts + world * 3, h_cnt + 4, 3 * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+  }
+  // pass 3 may run one thread per dynamic body only if no resolver can write a static body (see pg_general.cu)
+  bool ok = true;
+  for (int i = 0; i < counts[0] && ok; i++) ok = w->h_types[0][i] == PG_AABB || w->h_types[0][i] == PG_PLANE;
+  for (int i = 0; i < counts[1] && ok; i++) ok = w->h_types[1][i] != PG_PLANE;
+  w->static_pass_parallel_ok = ok && w->v.n_worlds == 1;
+  if (w->v.n_worlds > 1) { rc = refresh_parallel_flag(w); if (rc) return rc; }
+  const double t1 = frame_timing ? now() : 0.0;
+  PG_CUDA(cudaMemsetAsync(w->v.n_events, 0, sizeof(int) * (size_t)w->v.n_worlds, w->stream));
+  PG_CUDA(cudaEventRecord(w->ev0, w->stream));
+  {
+    float cdt = dt;
+    if ((double)cdt > 0.01666) cdt = (float)0.01666;
+    pg_leaf_lengths(0.0f, cdt, &w->v.leaf_lo, &w->v.leaf_hi);
+  }
+  if (n_steps > 0) { rc = pg_launch_general_step(w, dt, n_steps, refresh_nodes); if (rc) return rc; }
+  PG_CUDA(cudaEventRecord(w->ev1, w->stream));
+  w->last_steps = n_steps;
+  const double t2 = frame_timing ? now() : 0.0;
+  // everything back into the pinned block, then ONE synchronisation
+  PgBody *h_out = reinterpret_cast<PgBody *>(w->h_frame + off_out);
+  PgBody *outs[3] = {out_static, out_dynamic, out_player};
+  size_t out_at[3] = {0, (size_t)w->v.cap[0], (size_t)w->v.cap[0] + w->v.cap[1]};
+  for (int c = 0; c < 3; c++)
+    if (outs[c] && counts[c] > 0)
+      PG_CUDA(cudaMemcpyAsync(h_out + out_at[c], w->v.bodies[c] + (size_t)world * w->v.cap[c], sizeof(PgBody) * (size_t)counts[c], cudaMemcpyDeviceToHost, w->stream));
+  PgEvent *h_ev = reinterpret_cast<PgEvent *>(w->h_frame + off_ev);
+  PG_CUDA(cudaMemcpyAsync(h_cnt, w->v.n_events + world, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+  if (w->v.max_events > 0 && events)
+    PG_CUDA(cudaMemcpyAsync(h_ev, w->v.events + (size_t)world * w->v.max_events, sizeof(PgEvent) * (size_t)w->v.max_events, cudaMemcpyDeviceToHost, w->stream));
+  const double t3 = frame_timing ? now() : 0.0;
+  PG_CUDA(cudaStreamSynchronize(w->stream));
+  const double t4 = frame_timing ? now() : 0.0;
+  if (frame_timing) {
+    float kms = 0.0f;
+    cudaEventElapsedTime(&kms, w->ev0, w->ev1);
+    t_acc[0] += t1 - t0; t_acc[1] += t2 - t1; t_acc[2] += t3 - t2; t_acc[3] += t4 - t3; t_acc[4] += kms * 1e3;
+    if (++n_acc % 1000 == 0)
+      fprintf(stderr, "[pg_worlds_frame] per call (us): upload issue %.1f, launch %.1f, download issue %.1f, sync wait %.1f; kernel %.1f\n",
+              t_acc[0] / n_acc, t_acc[1] / n_acc, t_acc[2] / n_acc, t_acc[3] / n_acc, t_acc[4] / n_acc);
+  }
+  for (int c = 0; c < 3; c++) if (outs[c] && counts[c] > 0) memcpy(outs[c], h_out + out_at[c], sizeof(PgBody) * (size_t)counts[c]);
+  int n = h_cnt[0], over = 0;
+  if (n > w->v.max_events) { over = 1; n = w->v.max_events; }
+  if (events && n > 0) {
+    sort_events(h_ev, n);
+    for (int i = 0; i < n && i < events_cap; i++) events[i] = h_ev[i];
+  }
+  if (n_events) *n_events = n;
+  if (overflowed) *overflowed = over;
+  return PG_OK;
+}
+
 long long pg_worlds_events(PgWorlds *w, PgEvent *out, long long cap, int *overflowed) {
   if (!w) { pg_set_error("pg_worlds_events: bad handle"); return PG_ERR_ARG; }
   if (cudaSetDevice(w->device) != cudaSuccess || cudaStreamSynchronize(w->stream) != cudaSuccess) { pg_set_error("pg_worlds_events: cuda failure"); return PG_ERR_CUDA; }
@@ -731,16 +851,8 @@ long long pg_worlds_events(PgWorlds *w, PgEvent *out, long long cap, int *overfl
     if (n > 0 && out) {
       buf.resize(n);
       if (cudaMemcpy(buf.data(), w->v.events + (size_t)wd * w->v.max_events, sizeof(PgEvent) * n, cudaMemcpyDeviceToHost) != cudaSuccess) { pg_set_error("pg_worlds_events: copy failed"); return PG_ERR_CUDA; }
-      // restore solve order: step, pass, row, column (device slots are claimed atomically)
-      std::stable_sort(buf.begin(), buf.end(), [](const PgEvent &a, const PgEvent &b) {
-        if (a.step != b.step) return a.step < b.step;
-        const int pa = a.pad_ >> 8, pb = b.pad_ >> 8;
-        if (pa != pb) return pa < pb;
-        return event_key_row(a) < event_key_row(b);
-      });
-      for (int i = 0; i < n; i++) {
-        if (total + i < cap) { out[total + i] = buf[i]; out[total + i].pad_ = buf[i].pad_ >> 8; }
-      }
+      sort_events(buf.data(), n);
+      for (int i = 0; i < n; i++) if (total + i < cap) out[total + i] = buf[i];
     }
     total += n;
   }

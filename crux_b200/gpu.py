@@ -45,6 +45,7 @@ API = [
     ("pg_worlds_step_host", _i, [_vp, _f, _i, _vp, _vp, _vp]),
     ("pg_worlds_packed_world_bytes", C.c_size_t, [_vp]),
     ("pg_worlds_step_host_packed", _i, [_vp, _f, _i, _vp]),
+    ("pg_worlds_frame", _i, [_vp, _i, _vp, _vp, _i, _vp, _f, _i, _i, _vp, _vp, _vp, _vp, _ll, _vp, _vp]),
     ("pg_worlds_events", _ll, [_vp, _vp, _ll, _vp]),
     ("pg_worlds_stats", _i, [_vp, _vp, _vp]),
     ("pg_comm_unique_id", _i, [_vp]),

@@ -167,6 +167,18 @@ int  pg_worlds_step_host(PgWorlds *w, float dt, int n_steps, float *pos, float *
  * A chunk of worlds is then one contiguous range: one DMA per chunk and direction instead of three. */
 size_t pg_worlds_packed_world_bytes(const PgWorlds *w);
 int  pg_worlds_step_host_packed(PgWorlds *w, float dt, int n_steps, void *state);
+/* One game-loop frame of ONE world in a single round trip (the latency path of the drop-in's physics_step: a
+ * game-sized scene is bound by the number of blocking CUDA calls, not by bytes or flops).  `counts` are the class
+ * lengths of this frame; `ranges` name the records the host changed since the device last saw them (a class whose
+ * length changed is passed whole) and `records` holds those records back to back, in range order, verbatim.  Then
+ * n_steps steps as pg_worlds_step does them, and everything comes back: the records of all three classes (NULL to
+ * skip a class) and the contact events in solve order.  Dirty records go up as asynchronous copies from a pinned
+ * staging block, results come down into one, and the call synchronises ONCE. */
+typedef struct PgRange { int32_t cls, first, count; } PgRange;
+int  pg_worlds_frame(PgWorlds *w, int world, const int32_t counts[3], const PgRange *ranges, int n_ranges,
+                     const PgBody *records, float dt, int n_steps, int refresh_nodes,
+                     PgBody *out_static, PgBody *out_dynamic, PgBody *out_player,
+                     PgEvent *events, long long events_cap, long long *n_events, int *overflowed);
 /* Events of the last pg_worlds_step call, world-major then solve order.  Returns the total
  * number produced (may exceed cap; a world that overflowed max_events_per_world is reported
  * through *overflowed). */

@@ -103,7 +103,7 @@ def test_player_pokes_between_frames(tmp_path, gpu_lib, scene):
     text = _run([EXE, os.path.join(SC, scene + ".json"), "400", str(out), "--player", "--script", "jump"])
     assert "4 jumps" in text, text
     _assert_same_dump(open(out, "rb").read(), open(os.path.join(SC, f"{scene}_jump_400.bin"), "rb").read())
-    up = {int(l.split()[1]): int(l.split()[3]) for l in text.splitlines() if l.startswith("frame ")}
+    up = {int(l.split()[1]): int(l.split()[3]) for l in text.splitlines() if l.startswith("frame ") and " uploaded " in l}
     assert len(up) == 400
     if scene == "plates_only":
         assert up[0] == 7                                   # first frame: the six plates and the player
