@@ -370,3 +370,38 @@ def test_c5_full_size_one_step_regions(gpu_lib, oracle_lib):
     o.step(DT, 1, 1)
     assert gen.state_equal(g.get_players(), o.read(2))
     g.close()
+
+
+def test_tall_column_through_free_fall_compression_and_hot_gas(gpu_lib, oracle_lib):
+    """The regimes the configured C4 run goes through (spheres fall for seconds, the first ones bounce back into
+    the ones still falling at a relative 100 m/s, then a hot gas), in a column small enough for the oracle: a
+    12 x 256 x 12 box at C4's number density (9216 spheres).  The device advances the world; at six points of
+    the run -- free fall, compression front, hot gas with bodies that have tunnelled through the floor -- the
+    oracle is started from the downloaded state and three steps are compared bit for bit (state, at_rest,
+    contact events in solve order).  Every step of the run must be proven exact."""
+    W, H = 12.0, 256.0
+    n = int(W * W * H * 0.25)
+    rng = np.random.default_rng(404)
+    pos = np.stack([rng.uniform(-W / 2 + 0.5, W / 2 - 0.5, n), rng.uniform(0.5, H - 0.5, n), rng.uniform(-W / 2 + 0.5, W / 2 - 0.5, n)], axis=1).astype(np.float32)
+    vel = rng.uniform(-4.0, 4.0, (n, 3)).astype(np.float32)
+    planes = np.array([[0, 1, 0, 0], [0, -1, 0, -H], [1, 0, 0, -W / 2], [-1, 0, 0, -W / 2], [0, 0, 1, -W / 2], [0, 0, -1, -W / 2]], np.float32)
+    st = scenes.plane_bodies(planes)
+    g = gpu_lib.GpuLargeWorld(n, len(st))
+    g.set(st, pos, vel)
+    done, total_events, max_iter = 0, 0, 0
+    for target in (60, 200, 300, 360, 450, 700):
+        g.step(DT, target - done)          # raises PgUnproven if any step's fixed point is not proven
+        done = target
+        P, V, R = g.download_state()
+        assert np.isfinite(P).all() and np.isfinite(V).all()
+        dyn = scenes.sphere_bodies(P, V)
+        dyn["at_rest"] = R
+        o = ora.World(oracle_lib, st, dyn)
+        for s in range(3):
+            total_events += _compare_step(g, o, oracle_lib, ("column", target, s))
+            max_iter = max(max_iter, g.exactness()["iterations"])
+        done += 3
+        o.close()
+    assert total_events > 3000 and max_iter >= 6, (total_events, max_iter)
+    assert float(np.linalg.norm(V, axis=1).max()) > 40.0 and int((P[:, 1] < -1.0).sum()) > 0      # hot, and some tunnelled out
+    g.close()
