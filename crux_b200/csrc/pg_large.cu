@@ -1176,12 +1176,11 @@ __global__ void k_states_insert(LargeView v, int src, int dst, float dt) {
 // each x-run), the state balls and large untouched entries linked in the second structure (a lane per cell, walking
 // its list), and the few balls beyond e_cap2 (list).  A visit the untouched entries of the two bodies already listed
 // (k_pairs: the same ball test, repeated here bit for bit) is skipped; the rest go through the hash set.
-#ifndef PG_QUERY_LANES
-#define PG_QUERY_LANES 8      // lanes per ball: the query is a chain of dependent loads, more balls in flight beat more lanes per ball
-#endif
-__global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
-  if (v.flags->stop) return;
-  constexpr unsigned G = PG_QUERY_LANES;
+// G lanes per ball.  The query is a chain of dependent loads: with many balls to look up (the first iterations of a
+// hot step: a million) more balls in flight beat more lanes per ball (G = 8); with few (the long tail of iterations,
+// or a small world) the kernel lasts as long as ONE query, and a whole warp per ball shortens that chain (G = 32).
+template <unsigned G>
+__device__ __forceinline__ void d_states_query(const LargeView &v, float dt) {
   const GridParams g = *v.grid;
   const unsigned lane = threadIdx.x & (G - 1u);                          // lane within the ball's group
   const unsigned gmask = G == 32u ? 0xffffffffu : (((1u << G) - 1u) << (threadIdx.x & 31u & ~(G - 1u)));
@@ -1310,6 +1309,12 @@ __global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
       }
     }
   }
+}
+__global__ void __launch_bounds__(256) k_states_query(LargeView v, float dt) {
+  if (v.flags->stop) return;
+  const unsigned n_new = min(v.flags->n_balls, (unsigned)v.balls_cap) - v.flags->balls_begin;
+  if (n_new * 8u >= gridDim.x * blockDim.x) d_states_query<8u>(v, dt);      // enough balls to fill the grid eight lanes each
+  else d_states_query<32u>(v, dt);
 }
 
 // Rehash the visit set into a larger table (host: when the load passes 1/4).
