@@ -152,6 +152,8 @@ struct LargeView {
   int stage_limit;                   // entries the per-block shared-memory stages may hold (tests shrink it to reach the overflow paths)
   int pass3_split_min;               // worlds of at least this many bodies run pass 3 as probe + dense exact kernel
   float4 *pos_rest, *vel_rad;        // state (in/out), body order = reference array order
+  float4 *snap_pos, *snap_vel;       // the state as it was when the current step began (a step that fails puts it back)
+  int *snap_n_events;
   float4 *planes;                    // the static PLANES, array order
   int *plane_sidx;                   // their index in the static array
   float restitution;
@@ -1589,7 +1591,32 @@ static int lw_grow_balls(PgLarge *w, unsigned used) {
   return PG_OK;
 }
 
+static int lw_step_body(PgLarge *w, float dt_in);
+
+// One step, all or nothing: pass 3 and the final kernel write the state in place, so the state the step began with is
+// kept aside (two device copies, 32 B per body) and put back -- events and the touched-body bookkeeping with it -- if
+// the step ends with an error (a body with more contacts than a timeline holds, a scratch buffer that cannot grow,
+// non-finite state).  A step that is merely not PROVEN (PG_ERR_UNPROVEN) has run to its end and stays.
 static int lw_step_once(PgLarge *w, float dt_in) {
+  LargeView &v = w->v;
+  const size_t bytes = sizeof(float4) * (size_t)v.n;
+  PG_CUDA(cudaMemcpyAsync(v.snap_pos, v.pos_rest, bytes, cudaMemcpyDeviceToDevice, w->stream));
+  PG_CUDA(cudaMemcpyAsync(v.snap_vel, v.vel_rad, bytes, cudaMemcpyDeviceToDevice, w->stream));
+  PG_CUDA(cudaMemcpyAsync(v.snap_n_events, v.n_events, sizeof(int), cudaMemcpyDeviceToDevice, w->stream));
+  const int rc = lw_step_body(w, dt_in);
+  if (rc == PG_OK) return PG_OK;
+  // roll back (best effort: if the device itself is gone there is nothing to restore)
+  cudaStreamSynchronize(w->stream);
+  cudaMemcpyAsync(v.pos_rest, v.snap_pos, bytes, cudaMemcpyDeviceToDevice, w->stream);
+  cudaMemcpyAsync(v.vel_rad, v.snap_vel, bytes, cudaMemcpyDeviceToDevice, w->stream);
+  cudaMemcpyAsync(v.n_events, v.snap_n_events, sizeof(int), cudaMemcpyDeviceToDevice, w->stream);
+  cudaStreamSynchronize(w->stream);
+  w->bookkeeping_clean = 0;                     // the next step resets the fixed point's per-body state for every body
+  w->last_proven = 0;
+  return rc;
+}
+
+static int lw_step_body(PgLarge *w, float dt_in) {
   LargeView &v = w->v;
   float dt = dt_in;
   if ((double)dt > 0.01666) dt = (float)0.01666;
@@ -1795,6 +1822,9 @@ PgLarge *pg_large_create(int max_spheres, int max_static, int device) {
   v.max_events = (int)std::max<size_t>(n / 4, 65536);
   PG_CUDA_NULL(cudaMalloc(&v.pos_rest, sizeof(float4) * n));
   PG_CUDA_NULL(cudaMalloc(&v.vel_rad, sizeof(float4) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.snap_pos, sizeof(float4) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.snap_vel, sizeof(float4) * n));
+  PG_CUDA_NULL(cudaMalloc(&v.snap_n_events, sizeof(int)));
   PG_CUDA_NULL(cudaMalloc(&v.planes, sizeof(float4) * kMaxPlanesL));
   PG_CUDA_NULL(cudaMalloc(&v.plane_sidx, sizeof(int) * kMaxPlanesL));
   w->cap_static_total = std::max(max_static, kMaxPlanesL);
@@ -1865,7 +1895,7 @@ void pg_large_destroy(PgLarge *w) {
   cudaStreamSynchronize(w->stream);
   LargeView &v = w->v;
   if (w->player_world) pg_worlds_destroy(w->player_world);
-  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.balls, v.head2, v.head3, v.huge_list, v.vset, v.touched_bits, v.dirty_bits[0], v.dirty_bits[1], v.pushed_bits, v.block_sums, v.sorted,
+  void *ptrs[] = {v.plane_sidx, v.box_c, v.box_e, v.static_type, v.sg_start, v.sg_items, v.pos_rest, v.vel_rad, v.snap_pos, v.snap_vel, v.snap_n_events, v.planes, v.env, v.bbox, v.grid, v.cell_of, v.cell_cnt, v.rstat, v.robust, v.balls, v.head2, v.head3, v.huge_list, v.vset, v.touched_bits, v.dirty_bits[0], v.dirty_bits[1], v.pushed_bits, v.block_sums, v.sorted,
                   v.pairs, v.active, v.tl_chg[0], v.tl_chg[1], v.seen, v.touched, v.cell_rank, v.tl_cnt[0], v.tl_cnt[1], v.tl_key[0], v.tl_key[1], v.tl_pos[0], v.tl_pos[1], v.tl_vel[0], v.tl_vel[1],
                   v.flags, v.events, v.n_events, w->d_stats, w->d_stage_pos, w->d_stage_vel, w->d_stage_rest};
   for (void *p : ptrs) if (p) cudaFree(p);

@@ -405,3 +405,49 @@ def test_tall_column_through_free_fall_compression_and_hot_gas(gpu_lib, oracle_l
     assert total_events > 3000 and max_iter >= 6, (total_events, max_iter)
     assert float(np.linalg.norm(V, axis=1).max()) > 40.0 and int((P[:, 1] < -1.0).sum()) > 0      # hot, and some tunnelled out
     g.close()
+
+
+def test_failed_step_leaves_the_state_untouched_and_bad_input_is_refused(gpu_lib, oracle_lib):
+    """(i) A step that cannot be completed -- here: one sphere in the middle of 40 that overlap it, more contacts than a
+    timeline holds -- returns PG_ERR_CAPACITY and puts the state back bit for bit (pass 3 had already written it);
+    the handle stays usable.  (ii) Non-capsule players are refused (a sphere player has live table entries against
+    the dynamic spheres which the large-world path does not evaluate).  (iii) The binding refuses arrays of the wrong
+    dtype / shape / layout instead of letting the library copy past them."""
+    n, L = 600, 12.0
+    pos, vel = scenes.sphere_worlds(1, n, L, first_world=55)
+    pos, vel = pos[0].copy(), vel[0].copy()
+    rng = np.random.default_rng(8)
+    pos[:41] = np.array([0.0, 5.0, 0.0], np.float32) + rng.normal(0, 0.03, (41, 3)).astype(np.float32)     # a crush of 41 overlapping spheres
+    vel[:41] = rng.normal(0, 1.0, (41, 3)).astype(np.float32)
+    st = scenes.plane_bodies(scenes.box_planes(L))
+    g = gpu_lib.GpuLargeWorld(n, len(st))
+    g.set(st, pos, vel)
+    with pytest.raises(gpu_lib.PgError, match=r"\(-3\)"):
+        g.step(DT, 1)
+    P, V, R = g.download_state()
+    assert gen.same_bits(P, pos) and gen.same_bits(V, vel) and not R.any()
+    assert len(g.events()) == 0
+    # the same handle, a sane world: steps and matches the oracle
+    pos2, vel2 = scenes.sphere_worlds(1, n, L, first_world=56)
+    g.set(st, pos2[0], vel2[0])
+    o = ora.World(oracle_lib, st, scenes.sphere_bodies(pos2[0], vel2[0]))
+    for s in range(5):
+        _compare_step(g, o, oracle_lib, ("after failure", s))
+    # (iii)
+    with pytest.raises(gpu_lib.PgError):
+        g.upload_state(pos2[0].astype(np.float64), vel2[0])
+    with pytest.raises(gpu_lib.PgError):
+        g.upload_state(pos2[0][:-1], vel2[0][:-1])
+    with pytest.raises(gpu_lib.PgError):
+        g.download_state(np.zeros((n, 3), np.float32)[:, ::-1], np.zeros((n, 3), np.float32), np.zeros(n, np.uint8))
+    g.close()
+    # (ii)
+    statics, p5, v5, players = scenes.level_world(500, 32.0, seed_world=1, with_player=True)
+    g = gpu_lib.GpuLargeWorld(500, len(statics))
+    g.set(gpu_lib.prepare(statics), p5, v5)
+    bad = gpu_lib.prepare(players.copy())
+    bad["collider_type"] = scenes.COLLIDER_SPHERE
+    with pytest.raises(gpu_lib.PgError, match=r"\(-4\)"):
+        g.set_players(bad)
+    g.set_players(gpu_lib.prepare(players))
+    g.close()
