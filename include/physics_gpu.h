@@ -234,6 +234,9 @@ int  pg_large_set_players(PgLarge *w, const PgBody *players, int n);
 int  pg_large_get_players(PgLarge *w, PgBody *out, int cap);
 int  pg_large_upload_state(PgLarge *w, const float *pos, const float *vel, const uint8_t *at_rest_or_null);
 int  pg_large_download_state(PgLarge *w, float *pos, float *vel, uint8_t *at_rest_or_null);
+/* PG_OK only if every step is PROVEN identical to the reference's sequential sweep.  PG_ERR_UNPROVEN: all n_steps ran, but
+ * at least one fixed point did not converge (the state HAS been advanced).  Any other error: the step that failed left
+ * the state as it found it (earlier steps of the same call stay). */
 int  pg_large_step(PgLarge *w, float dt, int n_steps);
 int  pg_large_sync(PgLarge *w);
 /* Broadphase pair set on the current (frozen) state: unordered pairs i<j for which
