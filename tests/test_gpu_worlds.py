@@ -526,3 +526,11 @@ def test_statistics_come_from_the_step_epilogue_and_the_library_allreduce(gpu_li
     for a in (P, V, R):
         a.free()
     w.close()
+
+
+def test_general_kernels_random_campaign(gpu_lib, oracle_lib):
+    """Random mixed worlds (sizes, collider mixes, restitutions, time steps, with and without a player) through the
+    speculate-and-commit kernel of game-sized worlds, in random chunk lengths: state, node matrices and event order
+    bit-exact against the oracle (tests/random_campaign_mixed.py ran 300 cases of it)."""
+    import random_campaign_mixed
+    assert random_campaign_mixed.run(10, seed=77, steps=80, verbose=False) > 200
