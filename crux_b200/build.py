@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-Xptxas", "-v",
 ]
 EXTRA_INCLUDES: list[str] = []
-CU_SOURCES = ["physics_gpu.cu", "pg_general.cu", "pg_spheres.cu", "pg_large.cu", "pg_comm.cu"]
+CU_SOURCES = ["physics_gpu.cu", "pg_general.cu", "pg_spheres.cu", "pg_large.cu", "pg_comm.cu", "pg_debug.cu"]
 HOST_SOURCES = ["host/crux_world.c", "host/crux_colliders.c", "host/crux_scene.c"]
 HEADLESS = os.path.join(LIB, "crux_headless")
 

@@ -26,6 +26,9 @@
 #include <time.h>
 
 #include "crux_scene.h"
+#ifdef CRUX_HAVE_UPLOAD_STATS
+#include "physics_gpu.h"      /* PgDebugDraw (the GPU drop-in build only) */
+#endif
 
 static int *g_ev = NULL;
 static int g_nev = 0, g_cap = 0;
@@ -131,11 +134,12 @@ static void script_after_frame(CruxScene *s, const char *script) {
 int main(int argc, char **argv) {
   if (argc < 4) { fprintf(stderr, "usage: %s scene.json steps out.bin [--player] [--device-steps] [--script pickup|jump]\n", argv[0]); return 2; }
   int steps = atoi(argv[2]), player = 0, device_steps = 0;
-  const char *script = NULL;
+  const char *script = NULL, *debug_path = NULL;
   for (int i = 4; i < argc; i++) {
     if (!strcmp(argv[i], "--player")) player = 1;
     if (!strcmp(argv[i], "--device-steps")) device_steps = 1;
     if (!strcmp(argv[i], "--script") && i + 1 < argc) script = argv[++i];
+    if (!strcmp(argv[i], "--debug-geometry") && i + 1 < argc) debug_path = argv[++i];
   }
   CruxScene *s = crux_scene_load(argv[1], player);
   if (!s) return 1;
@@ -162,6 +166,28 @@ int main(int argc, char **argv) {
     printf("frame loop: %.1f us per frame (%d frames timed)\n",
            ((t_end.tv_sec - t_begin.tv_sec) * 1e6 + (t_end.tv_nsec - t_begin.tv_nsec) * 1e-3) / (timed > 0 ? timed : 1), timed);
   }
+#ifdef CRUX_HAVE_UPLOAD_STATS
+  if (debug_path) {
+    /* what the debug renderer would draw now (debug_renderer.c:11-213), after one more host-side poke of the player
+     * that the device has not seen yet: physics_debug_geometry has to send it up before the kernel runs */
+    if (s->world->num_player_bodies > 0) {
+      struct PhysicsBody *body = &s->world->player_bodies[0];
+      body->position[0] += 0.25f;
+      if (body->scene_node) crux_scene_node_update(body->scene_node);
+    }
+    const int cap = (int)(s->world->num_static_bodies + s->world->num_dynamic_bodies + s->world->num_player_bodies);
+    PgDebugDraw *recs = (PgDebugDraw *)calloc((size_t)(cap > 0 ? cap : 1), sizeof(PgDebugDraw));
+    const int n = physics_debug_geometry(s->world, recs, 0, cap);
+    FILE *df = fopen(debug_path, "wb");
+    if (!df || n < 0) return 1;
+    fwrite(recs, sizeof(PgDebugDraw), (size_t)n, df);
+    fclose(df);
+    free(recs);
+    printf("debug geometry: %d records\n", n);
+  }
+#else
+  (void)debug_path;
+#endif
   FILE *f = fopen(argv[3], "wb");
   if (!f) return 1;
   int hdr[4] = {(int)s->world->num_static_bodies, (int)s->world->num_dynamic_bodies, (int)s->world->num_player_bodies, g_nev};

@@ -170,4 +170,9 @@ void physics_step_n(struct PhysicsWorld *world, float delta_time, int n_steps);
  * device's copy travel (dirty ranges): a frame in which only the player was poked sends one. */
 unsigned long long physics_world_uploaded_records(struct PhysicsWorld *world);
 
+/* Debug-renderer interop (src/physics/debug_renderer.c): one PgDebugDraw record (include/physics_gpu.h) per body in draw
+ * order -- AABB corner vertices, sphere / capsule model matrices -- written by a kernel into host memory or straight
+ * into a device buffer the GL host shares with CUDA.  Returns the number of records, < 0 on error. */
+int physics_debug_geometry(struct PhysicsWorld *world, void *dst, int dst_is_device, int max_records);
+
 #endif /* CRUX_PHYSICS_COMPAT_H */

@@ -365,6 +365,19 @@ static void step_impl(struct PhysicsWorld *physics_world, float delta_time, int 
   if (n_events > 0) replay_events(s, n_events);
 }
 
+/* What physics_debug_render (src/physics/debug_renderer.c:11-213) reads from the bodies each frame, produced on the
+ * device: the records the host changed since the last step go up first (a zero-step frame, same dirty-range path as
+ * physics_step), then one kernel writes a PgDebugDraw per body (players, statics, dynamics) into `dst` -- host memory,
+ * or with dst_is_device a device address such as a GL buffer mapped through cudaGraphicsResourceGetMappedPointer. */
+int physics_debug_geometry(struct PhysicsWorld *physics_world, void *dst, int dst_is_device, int max_records) {
+  Shadow *s = shadow_find(physics_world, 1);
+  if (!s || ensure_gpu(s)) return PG_ERR_CUDA;
+  step_impl(physics_world, 0.0f, 0, 0);
+  int n = pg_worlds_debug_geometry(s->gpu, 0, dst, dst_is_device, max_records);
+  if (n < 0) fprintf(stderr, "Error: physics_debug_geometry: %s\n", pg_last_error());
+  return n;
+}
+
 unsigned long long physics_world_uploaded_records(struct PhysicsWorld *world) {
   Shadow *s = shadow_find(world, 0);
   return s ? s->uploaded_records : 0ull;

@@ -58,6 +58,11 @@ API = [
     ("pg_worlds_launches", _ll, [_vp]),
     ("pg_worlds_last_step_ms", _f, [_vp]),
     ("pg_worlds_stream", _vp, [_vp]),
+    ("pg_worlds_debug_geometry", _i, [_vp, _i, _vp, _i, _i]),
+    ("pg_debug_sphere_mesh", None, [_f, _vp, _vp]),
+    ("pg_debug_capsule_mesh", None, [_vp, _vp, _f, _vp, _vp]),
+    ("pg_debug_box_mesh", None, [_vp, _vp, _vp, _vp]),
+    ("pg_debug_capsule_model", None, [_vp, _vp]),
     ("pg_large_create", _vp, [_i, _i, _i]),
     ("pg_large_destroy", None, [_vp]),
     ("pg_large_set", _i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _f, _f]),
@@ -165,6 +170,38 @@ def node_transform(pos, rot_deg, scale, parent=None) -> np.ndarray:
     par = None if parent is None else np.ascontiguousarray(parent, np.float32)
     lib().pg_node_transform(_ptr(p), _ptr(r), _ptr(s), _ptr(par), _ptr(out))
     return out
+
+
+def debug_sphere_mesh(radius: float):
+    """Vertices (441, 3) and triangle indices (2280,) of physics_debug_sphere_init (debug_renderer.c:371-432)."""
+    v = np.zeros((441, 3), np.float32); idx = np.zeros(2280, np.uint32)
+    lib().pg_debug_sphere_mesh(np.float32(radius), _ptr(v), _ptr(idx))
+    return v, idx
+
+
+def debug_capsule_mesh(seg_a, seg_b, radius: float):
+    """Vertices (882, 3) and triangle indices (4920,) of physics_debug_capsule_init (debug_renderer.c:469-616)."""
+    a = np.ascontiguousarray(seg_a, np.float32); b = np.ascontiguousarray(seg_b, np.float32)
+    v = np.zeros((882, 3), np.float32); idx = np.zeros(4920, np.uint32)
+    lib().pg_debug_capsule_mesh(_ptr(a), _ptr(b), np.float32(radius), _ptr(v), _ptr(idx))
+    return v, idx
+
+
+def debug_box_mesh(center, extents):
+    """Corner vertices (8, 3) and line indices (24,) of physics_debug_AABB_init (debug_renderer.c:311-337)."""
+    c = np.ascontiguousarray(center, np.float32); e = np.ascontiguousarray(extents, np.float32)
+    v = np.zeros((8, 3), np.float32); idx = np.zeros(24, np.uint32)
+    lib().pg_debug_box_mesh(_ptr(c), _ptr(e), _ptr(v), _ptr(idx))
+    return v, idx
+
+
+def debug_capsule_model(body: np.ndarray) -> np.ndarray:
+    """Model matrix (16 floats, column-major) of a capsule drawn without a scene node (debug_renderer.c:53-59)."""
+    rec = np.ascontiguousarray(np.atleast_1d(body)[:1])
+    assert rec.dtype == BODY_DTYPE
+    m = np.zeros(16, np.float32)
+    lib().pg_debug_capsule_model(_ptr(rec), _ptr(m))
+    return m
 
 
 class PinnedArray:
@@ -344,6 +381,21 @@ class GpuWorlds:
         _check(self.L.pg_worlds_stats_allreduce(self.h, comm.h if comm else None, _ptr(h),
                                                 C.c_void_p(dev_out_ptr) if dev_out_ptr else None), "pg_worlds_stats_allreduce")
         return dict(zip(PG_STATS_FIELDS, h.tolist())) if want_host else None
+
+    def debug_geometry(self, world: int = 0, device_ptr: int | None = None, max_records: int | None = None):
+        """One PgDebugDraw record per body of `world` (players, statics, dynamics): what the reference's
+        physics_debug_render reads from the bodies each frame (debug_renderer.c:11-213), built on the device.
+        With `device_ptr` the kernel writes into that device buffer (a mapped GL buffer) and only the count
+        comes back; otherwise a DEBUG_DTYPE array."""
+        from .scenes import DEBUG_DTYPE
+        if device_ptr is not None:
+            return _check(self.L.pg_worlds_debug_geometry(self.h, world, C.c_void_p(device_ptr), 1,
+                                                          int(max_records if max_records is not None else 1 << 30)),
+                          "pg_worlds_debug_geometry")
+        total = sum(self.body_count(world, c) for c in range(3))
+        out = np.zeros(max(total, 1), dtype=DEBUG_DTYPE)
+        n = _check(self.L.pg_worlds_debug_geometry(self.h, world, _ptr(out), 0, len(out)), "pg_worlds_debug_geometry")
+        return out[:int(n)]
 
     @property
     def launches(self) -> int:

@@ -46,6 +46,10 @@ CORE_DTYPE = np.dtype(_CORE_FIELDS)            # == oracle/oracle_abi.h OraBody 
 EVENT_DTYPE = np.dtype([("step", "<i4"), ("event_type", "<i4"), ("a_class", "<i4"),
                         ("a_index", "<i4"), ("b_class", "<i4"), ("b_index", "<i4")])
 assert CORE_DTYPE.itemsize == 232 and BODY_DTYPE.itemsize == 304
+# PgDebugDraw (include/physics_gpu.h): one debug-geometry record per body (src/physics/debug_renderer.c)
+DEBUG_DTYPE = np.dtype([("kind", "<i4"), ("cls", "<i4"), ("index", "<i4"), ("n_indices", "<i4"), ("data", "<f4", (24,))])
+DEBUG_NONE, DEBUG_AABB_LINES, DEBUG_SPHERE_MODEL, DEBUG_CAPSULE_MODEL, DEBUG_CAPSULE_HOST = 0, 1, 2, 3, 4
+assert DEBUG_DTYPE.itemsize == 112
 
 _IDENTITY16 = np.eye(4, dtype=np.float32).reshape(16)
 

@@ -215,6 +215,42 @@ float pg_worlds_last_step_ms(PgWorlds *w);
 void *pg_worlds_stream(PgWorlds *w);   /* cudaStream_t as void* */
 
 /* ------------------------------------------------------------------------------------------
+ * Debug-geometry interop: what physics_debug_render (src/physics/debug_renderer.c:11-213) reads from the
+ * bodies every frame, produced ON THE DEVICE from the resident state, so that a GL host shares a buffer
+ * with CUDA (cudaGraphicsGLRegisterBuffer -> cudaGraphicsResourceGetMappedPointer -> `dst`, dst_is_device = 1)
+ * instead of reading every body back.  One record per body in the reference's draw order: players, statics,
+ * dynamics.  GL itself (VAO/VBO/EBO creation, shaders, draw calls) stays with the host; no GL symbol is linked here.
+ *   PG_DEBUG_AABB_LINES     data[0..23] = the 8 corner vertices physics_debug_AABB_render uploads with glBufferSubData
+ *                           (debug_renderer.c:662-688): world AABB through the scene node (translation, column norms,
+ *                           upper 3x3 / scale[0], AABB_update), corners in the order the 24 line indices (:321-337) expect
+ *   PG_DEBUG_SPHERE_MODEL   data[0..15] = column-major `model` given to shader_set_mat4 (:700): translate(position
+ *                           [+ sphere centre for a dynamic body, :184-193]) * scale(body scale)
+ *   PG_DEBUG_CAPSULE_MODEL  data[0..15] = the scene node's world transform (:49-51, :206)
+ *   PG_DEBUG_CAPSULE_HOST   capsule without a scene node (:53-59, :109-116): model = T R_y R_x R_z S needs sinf/cosf, which
+ *                           never run on the device (parity contract); pg_debug_capsule_model() builds it on the host
+ *   PG_DEBUG_NONE           planes (never drawn, :61, :119, :208) and AABBs without a scene node (a NULL dereference upstream)
+ * ------------------------------------------------------------------------------------------ */
+enum { PG_DEBUG_NONE = 0, PG_DEBUG_AABB_LINES = 1, PG_DEBUG_SPHERE_MODEL = 2, PG_DEBUG_CAPSULE_MODEL = 3, PG_DEBUG_CAPSULE_HOST = 4 };
+typedef struct PgDebugDraw {
+  int32_t kind;
+  int32_t cls, index;     /* which body */
+  int32_t n_indices;      /* element count of the draw call: 24 (GL_LINES), 2280 / 4920 (GL_TRIANGLES), 0 */
+  float data[24];
+} PgDebugDraw;            /* 112 bytes */
+/* Fill one record per body of `world` (players, statics, dynamics).  dst_is_device: `dst` is a device address (a mapped
+ * GL buffer) written by the kernel on the handle's stream -- asynchronous, pg_worlds_sync() or the caller's own
+ * stream order makes it visible; otherwise `dst` is host memory and the call synchronises.  Returns the number of
+ * records (<0: error; PG_ERR_CAPACITY if max_records is too small). */
+int  pg_worlds_debug_geometry(PgWorlds *w, int world, void *dst, int dst_is_device, int max_records);
+/* Host-side halves of the debug renderer (init-time meshes and the one model matrix the device does not build), libm like
+ * the reference.  Sizes: sphere 441 vertices x 3 floats, 2280 indices (:371-432); capsule 882 vertices x 3 floats, 4920
+ * indices (:469-616); box 8 vertices x 3 floats, 24 indices (:311-337). */
+void pg_debug_sphere_mesh(float radius, float *vertices1323, uint32_t *indices2280);
+void pg_debug_capsule_mesh(const float *seg_a3, const float *seg_b3, float radius, float *vertices2646, uint32_t *indices4920);
+void pg_debug_box_mesh(const float *center3, const float *extents3, float *vertices24, uint32_t *indices24);
+void pg_debug_capsule_model(const PgBody *body, float *model16);
+
+/* ------------------------------------------------------------------------------------------
  * One large world of dynamic spheres + static bodies (uniform-grid broadphase).
  * ------------------------------------------------------------------------------------------ */
 typedef struct PgLarge PgLarge;

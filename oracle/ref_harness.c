@@ -211,6 +211,9 @@ void *ref_world_create(void) {
   return w;
 }
 
+/* the wrapped struct PhysicsWorld, for oracle/ref_debug_harness.c (which drives the reference's debug renderer) */
+void *ref_world_pw(void *h) { return ((RefWorld *)h)->pw; }
+
 void ref_world_destroy(void *h) {
   RefWorld *w = (RefWorld *)h;
   struct PhysicsWorld *pw = w->pw;

@@ -212,6 +212,27 @@ CGLM_INLINE void glm_rotate_z(mat4 m, float angle, mat4 dest) {
   t[0][0] = c; t[0][1] = s; t[1][0] = -s; t[1][1] = c;
   glm_mul_rot(m, t, dest);
 }
+/* rotation by `angle` about `axis` (affine.h glm_rotate_make: axis normalised, Rodrigues form built column by column) */
+CGLM_INLINE void glm_vec3_normalize_to(vec3 v, vec3 dest) {
+  float norm = glm_vec3_norm(v);
+  if (norm < FLT_EPSILON) { glm_vec3_zero(dest); return; }
+  glm_vec3_scale(v, 1.0f / norm, dest);
+}
+CGLM_INLINE void glm_rotate_make(mat4 m, float angle, vec3 axis) {
+  vec3 axisn, v, vs;
+  float c = cosf(angle);
+  glm_vec3_normalize_to(axis, axisn);
+  glm_vec3_scale(axisn, 1.0f - c, v);
+  glm_vec3_scale(axisn, sinf(angle), vs);
+  glm_vec3_scale(axisn, v[0], m[0]);
+  glm_vec3_scale(axisn, v[1], m[1]);
+  glm_vec3_scale(axisn, v[2], m[2]);
+  m[0][0] += c;       m[1][0] -= vs[2];   m[2][0] += vs[1];
+  m[0][1] += vs[2];   m[1][1] += c;       m[2][1] -= vs[0];
+  m[0][2] -= vs[1];   m[1][2] += vs[0];   m[2][2] += c;
+  m[0][3] = m[1][3] = m[2][3] = m[3][0] = m[3][1] = m[3][2] = 0.0f;
+  m[3][3] = 1.0f;
+}
 CGLM_INLINE void glm_decompose_scalev(mat4 m, vec3 s) {
   s[0] = glm_vec3_norm(m[0]);
   s[1] = glm_vec3_norm(m[1]);

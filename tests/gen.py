@@ -137,6 +137,73 @@ def mixed_world(rng, node_transform, n_static_boxes=4, n_dyn=24, with_player=Tru
     return cat(st), cat(dy), cat(pl)
 
 
+def debug_gallery(rng, node_transform):
+    """Bodies of every kind the reference's debug renderer draws (debug_renderer.c:11-213), never stepped:
+    players  capsule with a scene node, capsule without one, AABB (node), sphere
+    statics  planes, AABBs (node; rotated, scaled, under non-identity parents), spheres, a capsule
+    dynamics AABBs (node), spheres with centre offsets and non-unit scales, a capsule (node)
+    AABBs and dynamic capsules always carry a node: the reference dereferences it unconditionally."""
+    def body(t, dynamic, node=True):
+        b = rand_body(rng, t, dynamic, node_transform)
+        if not node:
+            b["has_node"] = 0; b["has_parent"] = 0
+            b["node_xform"] = 0; b["parent_xform"] = 0
+        return b
+    pl = [body(COLLIDER_CAPSULE, False), body(COLLIDER_CAPSULE, False, node=False), body(COLLIDER_AABB, False),
+          body(COLLIDER_SPHERE, False, node=False)]
+    pl[1]["rotation"] = [12.5, -70.0, 33.0]; pl[1]["scale"] = [1.0, 1.5, 0.75]
+    st = [body(COLLIDER_PLANE, False) for _ in range(2)] + [body(COLLIDER_AABB, False) for _ in range(6)] + \
+         [body(COLLIDER_SPHERE, False, node=bool(k & 1)) for k in range(3)] + [body(COLLIDER_CAPSULE, False, node=False), body(COLLIDER_CAPSULE, False)]
+    dy = [body(COLLIDER_AABB, True) for _ in range(5)] + [body(COLLIDER_SPHERE, True, node=bool(k & 1)) for k in range(6)] + \
+         [body(COLLIDER_CAPSULE, True)]
+    for group in (pl, st, dy):
+        for b in group:
+            b["entity_type"] = ENTITY_WORLD
+    pl[0]["entity_type"] = ENTITY_PLAYER
+    cat = lambda xs: np.concatenate(xs)
+    return cat(st), cat(dy), cat(pl)
+
+
+def debug_records_from_log(log, statics, dynamics, players):
+    """Turn the reference's render log (ora.RefDebugLib.debug_render) into PgDebugDraw records, one per body in
+    draw order (players, statics, dynamics), plus {record index: model} for capsules drawn without a scene node
+    (those models are built on the host, pg_debug_capsule_model)."""
+    from crux_b200.scenes import (DEBUG_DTYPE, DEBUG_AABB_LINES, DEBUG_SPHERE_MODEL, DEBUG_CAPSULE_MODEL,
+                                  DEBUG_CAPSULE_HOST, CLASS_PLAYER, CLASS_STATIC, CLASS_DYNAMIC)
+    MODEL, SUB, DRAW = 4, 3, 5
+    order = [(CLASS_PLAYER, players), (CLASS_STATIC, statics), (CLASS_DYNAMIC, dynamics)]
+    n = sum(len(a) for _, a in order)
+    out = np.zeros(n, DEBUG_DTYPE)
+    host_models = {}
+    it = iter(log)
+    k = 0
+    for cls, arr in order:
+        for i, b in enumerate(arr):
+            out[k]["cls"] = cls; out[k]["index"] = i
+            t = int(b["collider_type"])
+            if t == COLLIDER_AABB:
+                w, c, tag, m = next(it); assert w == MODEL and tag == 1 and np.array_equal(m, np.eye(4, dtype=np.float32).reshape(16))
+                w, c, tag, v = next(it); assert w == SUB and c == 24
+                w, c, tag, _ = next(it); assert w == DRAW and c == 24
+                out[k]["kind"] = DEBUG_AABB_LINES; out[k]["n_indices"] = 24; out[k]["data"] = v
+            elif t == COLLIDER_SPHERE:
+                w, c, tag, m = next(it); assert w == MODEL and tag == 2
+                w, c, tag, _ = next(it); assert w == DRAW and c == 2280
+                out[k]["kind"] = DEBUG_SPHERE_MODEL; out[k]["n_indices"] = 2280; out[k]["data"][:16] = m
+            elif t == COLLIDER_CAPSULE:
+                w, c, tag, m = next(it); assert w == MODEL and tag == 2
+                w, c, tag, _ = next(it); assert w == DRAW and c == 4920
+                out[k]["n_indices"] = 4920
+                through_node = bool(b["has_node"]) and cls != CLASS_STATIC
+                if through_node:
+                    out[k]["kind"] = DEBUG_CAPSULE_MODEL; out[k]["data"][:16] = m
+                else:
+                    out[k]["kind"] = DEBUG_CAPSULE_HOST; host_models[k] = m.copy()
+            k += 1
+    assert next(it, None) is None, "log entries left over"
+    return out, host_models
+
+
 def bits(a):
     a = np.ascontiguousarray(a)
     return a.view(np.uint32) if a.dtype == np.float32 else a

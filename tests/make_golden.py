@@ -14,6 +14,10 @@ the plain-C restatement and the CUDA path to the reference's own outputs:
                        scene nodes refreshed every step: states after 25/50/150 steps + events
   aabb_unity.npz       inputs/expected outputs of the reference's own Unity test
                        (test/physics/test_aabb.c:24-141)
+  debug_geometry.npz   what the UNMODIFIED debug renderer (src/physics/debug_renderer.c, behind the recording GL stub
+                       of oracle/ref_debug_harness.c) uploads and draws: per-body corner vertices / model matrices
+                       of a gallery of every drawable kind and of the mixed world after 40 stepped frames, and the
+                       init-time sphere / capsule / box meshes
 """
 import os
 import sys
@@ -145,7 +149,61 @@ def main():
         update_scale=np.array([1, 1, 1], np.float32), update_rot_y_deg=np.float32(90.0),
         update_expected=np.array([5, 0, 0, 1, 1, 1], np.float32), update_tol=np.float32(1e-4))
     np.savez_compressed(os.path.join(OUT, "aabb_unity.npz"), **unity)
+    make_debug_fixture(nt)
     print("wrote", sorted(os.listdir(OUT)))
+
+
+def make_debug_fixture(nt):
+    """tests/golden/debug_geometry.npz from the reference's own debug renderer (see the module docstring)."""
+    dbg = ora.RefDebugLib()
+    out = {}
+    # (1) gallery: every drawable kind, not stepped
+    rng = np.random.default_rng(77)
+    S, D, P = gen.debug_gallery(rng, nt)
+    w = ora.World(dbg, S, D, P)
+    init_log = dbg.debug_init(w)
+    recs, host_models = gen.debug_records_from_log(dbg.debug_render(w), S, D, P)
+    out.update(gallery_S=S, gallery_D=D, gallery_P=P, gallery_records=recs,
+               gallery_host_idx=np.array(sorted(host_models), np.int32),
+               gallery_host_models=np.array([host_models[k] for k in sorted(host_models)], np.float32).reshape(-1, 16))
+    # init-time meshes in draw order: (vertex data, index data) per drawable body
+    order = [P, S, D]
+    bodies = [b for arr in order for b in arr if int(b["collider_type"]) != scenes.COLLIDER_PLANE]
+    assert len(init_log) == 2 * len(bodies), (len(init_log), len(bodies))
+    mesh_kind, mesh_shape, mesh_v, mesh_i = [], [], [], []
+    for k, b in enumerate(bodies):
+        (wv, cv, _, v), (wi, ci, _, idx) = init_log[2 * k], init_log[2 * k + 1]
+        assert wv == dbg.VERTEX_DATA and wi == dbg.INDEX_DATA
+        mesh_kind.append(int(b["collider_type"])); mesh_shape.append(np.array(b["shape"], np.float32))
+        vv = np.zeros(2646, np.float32); vv[:len(v)] = v
+        ii = np.zeros(4920, np.uint32); ii[:len(idx)] = idx
+        mesh_v.append(vv); mesh_i.append(ii)
+    out.update(mesh_kind=np.array(mesh_kind, np.int32), mesh_shape=np.array(mesh_shape, np.float32),
+               mesh_vertices=np.array(mesh_v), mesh_indices=np.array(mesh_i))
+    # a few more capsule meshes: tilted, flipped (axis = -z: the rotate-by-pi branch), degenerate (A == B)
+    rng = np.random.default_rng(78)
+    segs = [((0, 0, 0), (0, 0, 1)), ((0, 0, 1), (0, 0, -1)), ((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)), ((1, 0, 0), (-1, 2, 0.5))]
+    segs += [(tuple(rng.uniform(-1, 1, 3)), tuple(rng.uniform(-1, 1, 3))) for _ in range(4)]
+    caps = gen.new_bodies(len(segs))
+    caps["collider_type"] = scenes.COLLIDER_CAPSULE
+    for k, (a, b) in enumerate(segs):
+        caps["shape"][k, :3] = a; caps["shape"][k, 3:6] = b; caps["shape"][k, 6] = np.float32(0.2 + 0.1 * k)
+    w2 = ora.World(dbg, caps, None, None)
+    log2 = dbg.debug_init(w2)
+    out.update(capsule_shapes=np.array(caps["shape"], np.float32),
+               capsule_vertices=np.array([log2[2 * k][3] for k in range(len(segs))], np.float32),
+               capsule_indices=np.array([log2[2 * k + 1][3] for k in range(len(segs))], np.uint32))
+    # (2) the mixed world of mixed_world.npz (seed 5), drawn after 40 stepped frames with node refresh
+    rng = np.random.default_rng(5)
+    s_, d_, p_ = gen.mixed_world(rng, nt, with_player=True)
+    w3 = ora.World(dbg, s_, d_, p_)
+    w3.step(scenes.DT_60HZ, 40, 1)
+    recs3, hm3 = gen.debug_records_from_log(dbg.debug_render(w3), w3.read(0), w3.read(1), w3.read(2))
+    assert not hm3
+    out.update(mixed_steps=np.int32(40), mixed_records=recs3)
+    np.savez_compressed(os.path.join(OUT, "debug_geometry.npz"), **out)
+    kinds = np.bincount(recs["kind"], minlength=5)
+    print("debug_geometry: gallery kinds", kinds.tolist(), "meshes", len(bodies), "mixed records", len(recs3))
 
 
 def scenes_core(n):

@@ -19,6 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libcrux_ref.so")
 REF_O0_SO = os.path.join(ORACLE_DIR, "_ref", "libcrux_ref_O0.so")
+REF_DEBUG_SO = os.path.join(ORACLE_DIR, "_ref", "libcrux_ref_debug.so")
 ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "libcrux_oracle.so")
 REFERENCE_ROOT = "/root/reference"
 
@@ -117,6 +118,39 @@ class _Lib:
 class RefLib(_Lib):
     def __init__(self, path: str = REF_SO):
         super().__init__(path, "ref")
+
+
+class RefDebugLib(_Lib):
+    """The reference physics + its UNMODIFIED debug renderer behind a recording OpenGL stub
+    (oracle/ref_debug_harness.c).  `debug_init` / `debug_render` return the log of one
+    physics_debug_renderer_init / physics_debug_render call as (what, count, tag, data) tuples."""
+    VERTEX_DATA, INDEX_DATA, VERTEX_SUBDATA, MODEL_MAT4, DRAW = 1, 2, 3, 4, 5
+
+    def __init__(self, path: str = REF_DEBUG_SO):
+        super().__init__(path, "ref")
+        d = self.dll
+        d.ref_debug_init.restype = C.c_int; d.ref_debug_init.argtypes = [C.c_void_p]
+        d.ref_debug_render.restype = C.c_int; d.ref_debug_render.argtypes = [C.c_void_p]
+        d.ref_debug_capture.restype = C.c_int
+        d.ref_debug_capture.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+
+    def _log(self, n):
+        out = []
+        buf = np.zeros(8192, np.uint32)
+        what, count, tag = C.c_int(0), C.c_int(0), C.c_int(0)
+        for k in range(n):
+            m = self.dll.ref_debug_capture(k, C.byref(what), C.byref(count), C.byref(tag), _ptr(buf), len(buf))
+            assert m >= 0, m
+            words = buf[:m].copy()
+            data = words if what.value == self.INDEX_DATA else words.view(np.float32)
+            out.append((what.value, count.value, tag.value, data))
+        return out
+
+    def debug_init(self, world: "World"):
+        return self._log(self.dll.ref_debug_init(world.h))
+
+    def debug_render(self, world: "World"):
+        return self._log(self.dll.ref_debug_render(world.h))
 
 
 class OracleLib(_Lib):

@@ -111,3 +111,31 @@ def test_player_pokes_between_frames(tmp_path, gpu_lib, scene):
         for k in (30, 120, 121, 300, 60, 75, 200):          # frames whose script poked the player record
             assert up[k] == 1, (k, up[k])
         assert sum(1 for k, v in up.items() if k > 0 and v == 0) > 100      # resting and unpoked: nothing travels
+
+
+@pytest.mark.gpu
+def test_debug_geometry_through_the_reference_named_api(tmp_path, gpu_lib):
+    """physics_debug_geometry (the drop-in's counterpart of the reads physics_debug_render makes, debug_renderer.c:11-213)
+    on scenes/bouncehouse.json + player after 200 frames and one more host-side poke of the player: the poke must reach
+    the device before the kernel runs (dirty-range upload of a zero-step frame), the player's capsule record carries the
+    scene node's world transform bit for bit, every AABB record is a box around its node."""
+    from crux_b200 import scenes
+    out, dbg = tmp_path / "gpu.bin", tmp_path / "debug.bin"
+    r = _run([EXE, os.path.join(SC, "bouncehouse.json"), "200", str(out), "--player", "--debug-geometry", str(dbg)])
+    hdr, bodies, _ = parse_dump(open(out, "rb").read())
+    ns, nd, npl = (int(x) for x in hdr[:3])
+    recs = np.frombuffer(open(dbg, "rb").read(), dtype=scenes.DEBUG_DTYPE)
+    assert len(recs) == ns + nd + npl and f"debug geometry: {len(recs)} records" in r
+    # draw order: players, statics, dynamics; the dump is statics, dynamics, players
+    assert recs["cls"].tolist() == [2] * npl + [0] * ns + [1] * nd
+    player = bodies[ns + nd]
+    assert recs["kind"][0] == scenes.DEBUG_CAPSULE_MODEL and recs["n_indices"][0] == 4920
+    assert np.array_equal(recs["data"][0][:16].view(np.uint32), player[7:23].view(np.uint32))
+    assert recs["data"][0][12] == player[0]                      # ... which includes the poke (position written into the node)
+    dumped = np.concatenate([bodies[:ns], bodies[ns:ns + nd]])
+    boxes = recs[npl:]
+    assert (boxes["kind"] == scenes.DEBUG_AABB_LINES).all() and (boxes["n_indices"] == 24).all()
+    corners = boxes["data"].reshape(-1, 8, 3)
+    assert (corners[:, 0] >= corners[:, 4]).all()                # corner 0 = centre + extents, corner 4 = centre - extents
+    centre = 0.5 * (corners[:, 0] + corners[:, 4])
+    assert np.abs(centre - dumped[:, 19:22]).max() < 2.0         # the box sits around its node's translation
