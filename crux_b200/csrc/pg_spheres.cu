@@ -273,6 +273,11 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
   if (lane == 0) { S.n_list = 0; S.contacts = 0; }
 
   unsigned rest = 0;                       // bit s: this lane's body of actual slot s is at rest
+  // bit s: that body is at rest AND pass 3 has already looked at exactly its present state and found nothing (no
+  // contact, no event).  A body at rest is never integrated, so until a contact writes it the planes would be
+  // visited with bit-identical inputs and give the bit-identical "nothing" again: the visits are skipped.  In a
+  // thermalised world one body in six lies on the floor and used to pay the exact plane predicate every step.
+  unsigned quiet = 0;
   const size_t base = (size_t)w * v.cap[1];
 #pragma unroll 1
   for (int s = 0; s < CPT; s++) {
@@ -314,6 +319,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
     // exact evaluations of different bodies run in the same SIMT pass instead of one after the
     // other.  Per body the planes stay in order, and a contact re-gates that body's remaining planes
     // against its new state.
+    unsigned fired = 0;                    // bit s: a plane visit of that body fired in this step
 #pragma unroll 1
     for (int g = 0; g < ns; g += 8) {
       const int g_end = min(g + 8, ns);
@@ -323,7 +329,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
 #pragma unroll 1
         for (int s = sg; s < min(sg + 8, n_blocks); s++) {
           const int i = s * 32 + lane;
-          if (i < n) {
+          if (i < n && !((quiet >> s) & 1u)) {
             const float4 a = P4[i];
 #pragma unroll 1
             for (int k = g; k < g_end; k++) if (plane_near(a, S.planes[k])) pend |= 1ull << ((s - sg) * 8 + (k - g));
@@ -337,6 +343,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
             int came_to_rest = 0;
             if (plane_slow_path(P4, V4, i, S.planes[k], restitution, dt, gate_ok, &came_to_rest, leaf)) {
               if (came_to_rest) rest |= 1u << s;
+              fired |= 1u << s;
               if (record) emit_event(v, w, step, 3, PG_CLASS_DYNAMIC, i, PG_CLASS_STATIC, k);
               atomicAdd(&S.contacts, 1);
               const float4 a = P4[i];
@@ -350,6 +357,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
         }
       }
     }
+    quiet = (quiet | rest) & ~fired;
     // Centre the filter's coordinates are taken relative to.  It must sit among the bulk of the
     // bodies whatever a few stragglers do (a sphere that tunnelled through the floor keeps falling
     // for ever): the mean of the bodies within `trim` (twice the mean L1 distance, as of the
@@ -548,6 +556,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
         if (n_chg) {
           if (n_chg > kMaxRowChanges) {
             dirty_rows |= later;                   // too many to track: every later row re-filters itself
+            quiet = 0;                             // ... and every body meets the planes again
           } else {
 #pragma unroll 1
             for (int e = 0; e <= n_chg; e++) {
@@ -557,6 +566,7 @@ k_step_spheres(WorldsView v, float dt_in, int n_steps, int *work_counter, int fi
               int kc = (c >> 5) - rb; if (kc < 0) kc += CPT;
               if (lane == 0) WS[kc * 32 + (c & 31)] = (WS[kc * 32 + (c & 31)] & ~later) | word;
               if (c > i && c < row0 + 32) dirty_rows |= 1u << (c - row0);   // a later row of this block changed
+              if ((c & 31) == lane) quiet &= ~(1u << (c >> 5));             // a written body meets the planes again
             }
             __syncwarp();
           }
