@@ -171,10 +171,10 @@ __device__ int interval_hit_budget(const PgBody &A, const PgBody &B, float t_beg
   unsigned long long path = 0;
   int depth = 0;
   float t0 = t_begin, t1 = t_end;
+  const pgm::PairPre pre = pgm::pair_pre(A, B);      // everything of the distance function that does not depend on the time
   for (;;) {
     if (--budget < 0) return 2;
-    const float mm = pgm::max_move(A, t0, t1) + pgm::max_move(B, t0, t1);
-    const bool open = !(pgm::min_dist(A, B, t0) > mm) && !(pgm::min_dist(A, B, t1) > mm);
+    const bool open = pgm::interval_node_open(A, B, pre, t0, t1);
     if (open) {
       if (t1 - t0 < pgm::kIntervalEps) return 1;
       if (depth >= 62) return 0;
@@ -207,6 +207,7 @@ __device__ bool interval_hit_block(const PgBody &A, const PgBody &B, float t_beg
   __syncthreads();
   if (threadIdx.x == 0) { bs.stack[0] = 0ull; bs.top = 1; bs.found = 0; bs.overflow = 0; }
   __syncthreads();
+  const pgm::PairPre pre = pgm::pair_pre(A, B);
   for (;;) {
     const int n = bs.top;
     const bool stop = n == 0 || bs.found || bs.overflow;
@@ -226,8 +227,7 @@ __device__ bool interval_hit_block(const PgBody &A, const PgBody &B, float t_beg
         const float mid = (t0 + t1) * 0.5f;
         if ((path >> k) & 1ull) t0 = mid; else t1 = mid;
       }
-      const float mm = pgm::max_move(A, t0, t1) + pgm::max_move(B, t0, t1);
-      if (!(pgm::min_dist(A, B, t0) > mm) && !(pgm::min_dist(A, B, t1) > mm)) {
+      if (pgm::interval_node_open(A, B, pre, t0, t1)) {
         if (t1 - t0 < pgm::kIntervalEps) atomicExch(&bs.found, 1);
         else if (depth >= 55) atomicExch(&bs.overflow, 1);
         else {

@@ -936,12 +936,129 @@ __device__ inline float min_dist(const PgBody &A, const PgBody &B, float t) {
   }
 }
 
+// ---- the time-independent part of a pair's distance function, taken out of the interval search ----
+// interval_collision evaluates minimum_object_distance_at_time at two end points per node of its recursion, and every
+// evaluation of a box rebuilds it from the scene node: three column norms, the rotation scaled by 1/scale.x, nine
+// products and nine double-precision |rot| * extent * |scale| terms (distance.c:26-49 + aabb.c:59-78) -- none of which
+// depends on the time; only the translation does (pos + velocity * t).  A game-sized visit is one thread walking some
+// twenty nodes, so that rebuilding WAS the frame time of the drop-in (scenes/bouncehouse.json: 118 of 148 us).  PairPre
+// holds exactly the values those expressions produce -- each rot * shape product, the finished extents, the capsule,
+// the plane's projected radius -- and box_at() redoes only the operations that involve the time, in the reference's
+// order (centre = ((tr + p0) + p1) + p2 per axis), so every distance is bit-identical to min_dist()'s.
+struct BoxPre { V3 pos0, e; float p[9]; int ok; };
+__device__ inline BoxPre box_pre(const float *shape, const float *rot, V3 pos0, V3 scl) {
+  BoxPre r; r.ok = 1; r.pos0 = pos0;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float e = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      r.p[j * 3 + i] = rot[j * 3 + i] * shape[j];
+      e = (float)((double)e + fabs((double)rot[j * 3 + i]) * (double)shape[3 + j] * fabs((double)get(scl, i)));
+    }
+    set(r.e, i, e);
+  }
+  return r;
+}
+__device__ inline BoxPre box_pre_node(const PgBody &b) {          // box_from_node without the advance
+  if (!b.has_node) { BoxPre r; r.ok = 0; r.pos0 = v3(0, 0, 0); r.e = v3(0, 0, 0); for (int k = 0; k < 9; k++) r.p[k] = 0.0f; return r; }
+  NodeFrame f; node_decompose(b.node_xform, f);
+  return box_pre(b.shape, f.rot, f.pos, f.scl);
+}
+__device__ __forceinline__ Box box_at(const BoxPre &r, V3 vel, float t) {     // == aabb_update(shape, rot, pos0 + vel t, scl)
+  if (!r.ok) return zero_box();
+  const V3 tr = muladds(vel, t, r.pos0);
+  Box o;
+  o.c.x = ((tr.x + r.p[0]) + r.p[3]) + r.p[6];
+  o.c.y = ((tr.y + r.p[1]) + r.p[4]) + r.p[7];
+  o.c.z = ((tr.z + r.p[2]) + r.p[5]) + r.p[8];
+  o.e = r.e;
+  return o;
+}
+struct PairPre {
+  int code;               // A.collider_type * 4 + B.collider_type
+  float nA, nB;           // |velocity|: maximum_object_movement_over_time = |v| (t1 - t0), world.c:584-589
+  V3 vA, vB;
+  BoxPre a, b;            // the boxes of the pair (b.pos0 / b.ok: the sphere's node for a box-sphere pair)
+  Pill pill;              // box-capsule: the capsule does not move during the search (distance.c:185-189)
+  float aux;              // box-sphere: world radius; box-plane: projected radius; capsule-plane: the distance itself
+};
+__device__ inline PairPre pair_pre(const PgBody &A, const PgBody &B) {
+  PairPre q;
+  q.code = A.collider_type * 4 + B.collider_type;
+  q.vA = v3p(A.velocity); q.vB = v3p(B.velocity);
+  q.nA = norm(q.vA); q.nB = norm(q.vB);
+  q.aux = 0.0f;
+  switch (q.code) {
+    case PG_AABB * 4 + PG_AABB: q.a = box_pre_node(A); q.b = box_pre_node(B); break;
+    case PG_AABB * 4 + PG_SPHERE:
+      q.a = box_pre_node(A);
+      q.b.ok = B.has_node; q.b.pos0 = v3(0, 0, 0);
+      if (B.has_node) { NodeFrame f; node_decompose(B.node_xform, f); q.b.pos0 = f.pos; q.aux = B.shape[3] * f.scl.x; }
+      break;
+    case PG_AABB * 4 + PG_CAPSULE: q.a = box_pre_node(A); q.pill = pill_from_node(B); break;
+    case PG_AABB * 4 + PG_PLANE:
+      q.a = box_pre(A.shape, A.euler_raw, v3p(A.position), v3p(A.scale));
+      q.aux = proj_radius_f64(q.a.e, v3p(B.shape));
+      break;
+    case PG_CAPSULE * 4 + PG_PLANE: q.aux = min_dist(A, B, 0.0f); break;      // (no term of it depends on the time)
+    default: break;
+  }
+  return q;
+}
+// minimum_object_distance_at_time through the table (min_dist below), with the time-independent part precomputed
+__device__ inline float min_dist_pre(const PgBody &A, const PgBody &B, const PairPre &q, float t) {
+  switch (q.code) {
+    case PG_AABB * 4 + PG_AABB: {
+      const Box a = box_at(q.a, q.vA, t), b = box_at(q.b, q.vB, t);
+      float d2 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        float minA = get(a.c, i) - get(a.e, i), maxA = get(a.c, i) + get(a.e, i);
+        float minB = get(b.c, i) - get(b.e, i), maxB = get(b.c, i) + get(b.e, i);
+        if (minB > maxA) d2 += (minB - maxA) * (minB - maxA);
+        else if (maxB < minA) d2 += (minA - maxB) * (minA - maxB);
+      }
+      return (float)sqrt((double)d2);   // [f64]
+    }
+    case PG_AABB * 4 + PG_SPHERE: {
+      const Box bx = box_at(q.a, q.vA, t);
+      Ball s; s.c = v3(0, 0, 0); s.r = 0.0f;
+      if (q.b.ok) { s.c = add(v3p(B.shape), muladds(q.vB, t, q.b.pos0)); s.r = q.aux; }
+      float d2 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        float v = get(s.c, i), lo = get(bx.c, i) - get(bx.e, i), hi = get(bx.c, i) + get(bx.e, i);
+        if (v < lo) d2 += (lo - v) * (lo - v);
+        if (v > hi) d2 += (v - hi) * (v - hi);
+      }
+      return d2 < (s.r * s.r) ? 0.0f : (float)(sqrt((double)d2) - (double)s.r);   // [f64]
+    }
+    case PG_AABB * 4 + PG_CAPSULE: {
+      const Box bx = box_at(q.a, q.vA, t);
+      const V3 pq = pill_box_pq(q.pill, bx);
+      return glm_max(norm(pq) - q.pill.r, 0);
+    }
+    case PG_AABB * 4 + PG_PLANE: {
+      const Box bx = box_at(q.a, q.vA, t);
+      const float s = dot(v3p(B.shape), bx.c) - B.shape[3];
+      return glm_max(s - q.aux, 0);
+    }
+    case PG_CAPSULE * 4 + PG_PLANE: return q.aux;
+    default: return min_dist(A, B, t);
+  }
+}
+// one node of interval_collision's recursion: do both end points pass?  (world.c:559-565)
+__device__ __forceinline__ bool interval_node_open(const PgBody &A, const PgBody &B, const PairPre &q, float t0, float t1) {
+  const float dt = t1 - t0;
+  const float mm = q.nA * dt + q.nB * dt;
+  return !(min_dist_pre(A, B, q, t0) > mm) && !(min_dist_pre(A, B, q, t1) > mm);
+}
+
 // interval_collision, world.c:557-582 (general collider pair).
 __device__ inline bool interval_hit(const PgBody &A, const PgBody &B, float t_begin, float t_end, float *hit) {
-  return interval_walk(t_begin, t_end, hit, [&](float t0, float t1) {
-    const float mm = max_move(A, t0, t1) + max_move(B, t0, t1);
-    return !(min_dist(A, B, t0) > mm) && !(min_dist(A, B, t1) > mm);
-  });
+  const PairPre q = pair_pre(A, B);
+  return interval_walk(t_begin, t_end, hit, [&](float t0, float t1) { return interval_node_open(A, B, q, t0, t1); });
 }
 
 __device__ inline bool aabb_hits_aabb(const Box &a, const Box &b) {   // aabb.c:100-105

@@ -5,6 +5,7 @@ The fixture tests/golden/debug_geometry.npz was written by tests/make_golden.py 
 debug_renderer.c running behind a recording OpenGL stub (oracle/ref_debug_harness.c).  CPU tests pin the
 fixture to a live run of that build (where oracle/_ref exists) and check the host-side mesh helpers; the
 GPU tests compare the CUDA kernel's records bit for bit, through the C-ABI."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -16,6 +17,20 @@ from crux_b200 import scenes
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 DT = scenes.DT_60HZ
+
+
+def _cudart():
+    for name in ("libcudart.so", "libcudart.so.12", "/usr/local/cuda/lib64/libcudart.so", "/usr/local/cuda/lib64/libcudart.so.12"):
+        try:
+            rt = C.CDLL(name)
+        except OSError:
+            continue
+        rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+        rt.cudaMemset.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
+        rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+        rt.cudaFree.argtypes = [C.c_void_p]
+        return rt
+    pytest.fail("the CUDA runtime library is not on this box")
 
 
 def _fixture():
@@ -103,21 +118,27 @@ def test_debug_geometry_gallery_bit_exact(gpu_lib):
     """Every drawable kind (AABB corners through the node, sphere models, node-driven capsules) equals what the
     reference handed to glBufferSubData / shader_set_mat4; into host memory and into a caller-owned DEVICE buffer
     (the stand-in for a mapped GL buffer)."""
-    import torch
     z = _fixture()
     w = _world(gpu_lib, z["gallery_S"], z["gallery_D"], z["gallery_P"])
     got = w.debug_geometry(0)
     _same_records(got, z["gallery_records"])
     assert set(got["kind"].tolist()) == {0, 1, 2, 3, 4}
-    dev = torch.zeros(len(got) * scenes.DEBUG_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    # a device buffer the CALLER owns, from the CUDA runtime directly (no torch: the buffer is what a GL host would map)
+    rt = _cudart()
+    nbytes = len(got) * scenes.DEBUG_DTYPE.itemsize
+    dev = C.c_void_p()
+    assert rt.cudaMalloc(C.byref(dev), C.c_size_t(nbytes)) == 0
+    assert rt.cudaMemset(dev, 0, C.c_size_t(nbytes)) == 0
     launches = w.launches
-    n = w.debug_geometry(0, device_ptr=dev.data_ptr(), max_records=len(got))
+    n = w.debug_geometry(0, device_ptr=dev.value, max_records=len(got))
     assert n == len(got) and w.launches == launches + 1
     w.sync()
-    torch.cuda.synchronize()
-    _same_records(np.frombuffer(dev.cpu().numpy().tobytes(), dtype=scenes.DEBUG_DTYPE), z["gallery_records"])
+    back = np.zeros(len(got), scenes.DEBUG_DTYPE)
+    assert rt.cudaMemcpy(back.ctypes.data_as(C.c_void_p), dev, C.c_size_t(nbytes), 2) == 0      # cudaMemcpyDeviceToHost
+    _same_records(back, z["gallery_records"])
     with pytest.raises(gpu_lib.PgError):
-        w.debug_geometry(0, device_ptr=dev.data_ptr(), max_records=len(got) - 1)
+        w.debug_geometry(0, device_ptr=dev.value, max_records=len(got) - 1)
+    assert rt.cudaFree(dev) == 0
     w.close()
 
 
