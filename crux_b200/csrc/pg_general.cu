@@ -163,6 +163,7 @@ k_step_general(WorldsView v, float dt_in, int n_steps, int refresh_nodes, int st
 // the result is the sequential one.
 constexpr int kSmallMaxVisits = 2048;
 constexpr int kSmallBudget = 24;         // nodes of interval_collision's recursion a single thread explores before the visit goes to the block
+constexpr int kSmallStageBodies = 48;     // worlds of at most this many bodies keep their records in shared memory (14.6 KB)
 constexpr int kSmallStack = 2048;        // open nodes the block-wide search can hold
 
 // interval_collision (world.c:557-582) with a node budget: 0 = false, 1 = true, 2 = still undecided after
@@ -333,6 +334,24 @@ k_step_small(WorldsView v, float dt_in, int n_steps, int refresh_nodes) {
   PgBody *P = v.bodies[2] + (size_t)w * v.cap[2];
   SmallPlan pl;
   pl.ns = v.counts[w * 3 + 0]; pl.nd = v.counts[w * 3 + 1]; pl.np = v.counts[w * 3 + 2];
+  // A game scene's records live in shared memory for the launch (bouncehouse.json: 15 bodies, 4.5 KB): the kernel is one
+  // block whose every visit is a chain of dependent reads of a few record fields, and those were L2 round trips.
+  __shared__ __align__(16) unsigned char s_bodies_raw[kSmallStageBodies * sizeof(PgBody)];
+  PgBody *const s_bodies = reinterpret_cast<PgBody *>(s_bodies_raw);
+  PgBody *const gS = S, *const gD = D, *const gP = P;
+  const bool in_smem = pl.ns + pl.nd + pl.np <= kSmallStageBodies;
+  if (in_smem) {
+    constexpr int kWords = (int)(sizeof(PgBody) / 16);
+    static_assert(sizeof(PgBody) % 16 == 0, "PgBody is copied in 16-byte pieces");
+    const int n_all = pl.ns + pl.nd + pl.np;
+    for (int k = threadIdx.x; k < n_all * kWords; k += kThreads) {
+      const int b = k / kWords, q = k % kWords;
+      const PgBody *src = b < pl.ns ? gS + b : (b < pl.ns + pl.nd ? gD + (b - pl.ns) : gP + (b - pl.ns - pl.nd));
+      reinterpret_cast<uint4 *>(s_bodies + b)[q] = reinterpret_cast<const uint4 *>(src)[q];
+    }
+    S = s_bodies; D = s_bodies + pl.ns; P = s_bodies + pl.ns + pl.nd;
+    __syncthreads();
+  }
   pl.v1 = pl.np * pl.ns; pl.v2 = pl.np * pl.nd; pl.v3 = pl.nd * pl.ns; pl.v4 = pl.nd * (pl.nd - 1);
   const int V = pl.total();
   const float dt = pgm::clamp_dt(dt_in);
@@ -364,6 +383,9 @@ k_step_small(WorldsView v, float dt_in, int n_steps, int refresh_nodes) {
     __syncthreads();
     // visits whose interval search is a long one: the whole block decides them, one after the other
     auto settle_hard = [&](int from) {
+      int mine = 0;                                      // (most steps have none: one vote instead of a scan by every thread)
+      for (int k = from + (int)threadIdx.x; k < V; k += kThreads) mine |= s_fire[k] == 2;
+      if (!__syncthreads_or(mine)) return;
       for (int k = from; k < V; k++) {
         if (s_fire[k] != 2) continue;                    // (uniform: shared memory, read between barriers)
         float t = 0.0f;
@@ -413,6 +435,16 @@ k_step_small(WorldsView v, float dt_in, int n_steps, int refresh_nodes) {
       for (int i = threadIdx.x; i < pl.nd; i += kThreads) if (D[i].has_node) pgm::node_refresh(D[i]);
       for (int i = threadIdx.x; i < pl.np; i += kThreads) if (P[i].has_node) pgm::node_refresh(P[i]);
       __syncthreads();
+    }
+  }
+  if (in_smem) {
+    constexpr int kWords = (int)(sizeof(PgBody) / 16);
+    const int n_all = pl.ns + pl.nd + pl.np;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_all * kWords; k += kThreads) {
+      const int b = k / kWords, q = k % kWords;
+      PgBody *dst = b < pl.ns ? gS + b : (b < pl.ns + pl.nd ? gD + (b - pl.ns) : gP + (b - pl.ns - pl.nd));
+      reinterpret_cast<uint4 *>(dst)[q] = reinterpret_cast<const uint4 *>(s_bodies + b)[q];
     }
   }
 }
