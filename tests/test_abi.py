@@ -35,6 +35,13 @@ def test_record_layouts_match_header():
     offs = {n: scenes.BODY_DTYPE.fields[n][1] for n in scenes.BODY_DTYPE.names}
     assert (offs["position"], offs["rotation"], offs["scale"], offs["velocity"], offs["restitution"], offs["shape"]) == (0, 12, 24, 36, 48, 52)
     assert (offs["collider_type"], offs["node_xform"], offs["parent_xform"], offs["euler_raw"], offs["euler_node"]) == (80, 104, 168, 232, 268)
+    # PgDebugDraw: kind, cls, index, n_indices, 24 floats
+    d = scenes.DEBUG_DTYPE
+    assert d.itemsize == 112 and [d.fields[n][1] for n in ("kind", "cls", "index", "n_indices", "data")] == [0, 4, 8, 12, 16]
+    header = open(HEADER).read()
+    for name, value in (("PG_DEBUG_NONE", scenes.DEBUG_NONE), ("PG_DEBUG_AABB_LINES", scenes.DEBUG_AABB_LINES), ("PG_DEBUG_SPHERE_MODEL", scenes.DEBUG_SPHERE_MODEL),
+                        ("PG_DEBUG_CAPSULE_MODEL", scenes.DEBUG_CAPSULE_MODEL), ("PG_DEBUG_CAPSULE_HOST", scenes.DEBUG_CAPSULE_HOST)):
+        assert re.search(rf"\b{name} = {value}\b", header), name
 
 
 def test_host_helpers_agree_with_oracle(oracle_lib):
