@@ -191,86 +191,83 @@ int pg_worlds_debug_geometry(PgWorlds *w, int world, void *dst, int dst_is_devic
   return rc == PG_OK ? total : rc;
 }
 
-// physics_debug_sphere_init, debug_renderer.c:371-432 (vertices of the radius-r UV sphere, 21 x 21; 2280 indices)
-void pg_debug_sphere_mesh(float radius, float *vertices, uint32_t *indices) {
-  const int sector_count = 20, stack_count = 20;
-  const float sector_step = (2 * M_PI) / 20;
-  const float stack_step = M_PI / 20;
-  int vi = 0;
-  for (int i = 0; i <= stack_count; i++) {
-    const float stack_angle = (M_PI / 2) - (i * stack_step);      // double arithmetic on the float product, as written upstream
-    const float stack_xy = radius * cosf(stack_angle);
-    const float z = radius * sinf(stack_angle);
-    for (int j = 0; j <= sector_count; j++) {
-      const float sector_angle = j * sector_step;
-      vertices[vi * 3] = stack_xy * cosf(sector_angle);
-      vertices[vi * 3 + 1] = stack_xy * sinf(sector_angle);
-      vertices[vi * 3 + 2] = z;
-      vi++;
-    }
+// Unit meshes of the debug renderer.  Both are latitude rings of kRing + 1 vertices (the seam vertex is doubled) joined
+// by two triangles per quad; the arithmetic types follow debug_renderer.c to the letter (float steps from double
+// constants, `double - float` for the latitude, float products), because the vertices are compared bit for bit.
+constexpr int kRing = 20;        // sectors per ring and stacks per hemisphere (debug_renderer.c:373-374, :477-478)
+
+// ring of vertices at height z and radius rad around `centre`, optionally rotated: returns the next free vertex slot
+static int ring_vertices(float *out, int at, float rad, float z, const float *rot16_or_null, const float *centre3_or_null) {
+  const float dtheta = (2 * M_PI) / kRing;                       // float <- double, as upstream
+  for (int col = 0; col <= kRing; col++) {
+    const float theta = col * dtheta;
+    const float x = rad * cosf(theta), y = rad * sinf(theta);
+    float *v = out + 3 * at++;
+    if (!rot16_or_null) { v[0] = x; v[1] = y; v[2] = z; continue; }
+    // glm_mat4_mulv3(rot, (x, y, z), 1.0f) + centre: four products per row summed left to right
+    for (int k = 0; k < 3; k++)
+      v[k] = (rot16_or_null[0 + k] * x + rot16_or_null[4 + k] * y + rot16_or_null[8 + k] * z + rot16_or_null[12 + k] * 1.0f) + centre3_or_null[k];
   }
-  unsigned n = 0;
-  for (int i = 0; i < stack_count; i++) {
-    int k1 = i * (sector_count + 1), k2 = k1 + sector_count + 1;
-    for (int j = 0; j < sector_count; j++, k1++, k2++) {
-      if (i != 0) { indices[n++] = k1; indices[n++] = k2; indices[n++] = k1 + 1; }
-      if (i != stack_count - 1) { indices[n++] = k1 + 1; indices[n++] = k2; indices[n++] = k2 + 1; }
-    }
-  }
+  return at;
 }
 
-// physics_debug_capsule_init, debug_renderer.c:469-616: two hemispheres of 20 stacks around the end points, built about
-// +z and rotated onto the segment's axis; 42 rings of 21 vertices, 4920 indices.
+// sphere of physics_debug_sphere_init (debug_renderer.c:371-432): 21 rings from the +z pole down, 2280 indices (the two
+// polar rows contribute one triangle per quad)
+void pg_debug_sphere_mesh(float radius, float *vertices, uint32_t *indices) {
+  const float dphi = M_PI / kRing;
+  int at = 0;
+  for (int ring = 0; ring <= kRing; ring++) {
+    const float phi = (M_PI / 2) - (ring * dphi);                  // double arithmetic on the float product
+    at = ring_vertices(vertices, at, radius * cosf(phi), radius * sinf(phi), nullptr, nullptr);
+  }
+  uint32_t *w = indices;
+  for (int ring = 0; ring < kRing; ring++)
+    for (int col = 0; col < kRing; col++) {
+      const uint32_t upper = (uint32_t)(ring * (kRing + 1) + col), lower = upper + kRing + 1;
+      if (ring != 0) { *w++ = upper; *w++ = lower; *w++ = upper + 1; }
+      if (ring != kRing - 1) { *w++ = upper + 1; *w++ = lower; *w++ = lower + 1; }
+    }
+}
+
+// capsule of physics_debug_capsule_init (debug_renderer.c:469-616): a hemisphere of 20 rings below end point A, the two
+// equators, a hemisphere above end point B, all built about +z and turned onto the segment's axis; 42 rings, 4920 indices
 void pg_debug_capsule_mesh(const float *A, const float *B, float radius, float *vertices, uint32_t *indices) {
-  const int sector_count = 20, stack_count = 20, total_stacks = stack_count * 2 + 1;
-  const float sector_step = (2 * M_PI) / sector_count;
   float axis[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]};
   h_normalize(axis);
-  const float z_axis[3] = {0.0f, 0.0f, 1.0f};
-  float rot_axis[3] = {z_axis[1] * axis[2] - z_axis[2] * axis[1], z_axis[2] * axis[0] - z_axis[0] * axis[2],
-                       z_axis[0] * axis[1] - z_axis[1] * axis[0]};
-  const float zdot = z_axis[0] * axis[0] + z_axis[1] * axis[1] + z_axis[2] * axis[2];
-  const float angle = acosf(zdot);
+  // rotation taking +z to the axis: about z x axis by acos(z . axis); a half turn about x when the axis is -z
+  float about[3] = {0.0f * axis[2] - 1.0f * axis[1], 1.0f * axis[0] - 0.0f * axis[2], 0.0f * axis[1] - 0.0f * axis[0]};
+  const float cos_angle = 0.0f * axis[0] + 0.0f * axis[1] + 1.0f * axis[2];
+  const float angle = acosf(cos_angle);
   float rot[16];
-  if (h_norm(rot_axis) > 0.0f) {
-    h_normalize(rot_axis);
-    h_rotate_make(rot, angle, rot_axis);
+  if (h_norm(about) > 0.0f) {
+    h_normalize(about);
+    h_rotate_make(rot, angle, about);
   } else {
     for (int k = 0; k < 16; k++) rot[k] = (k % 5 == 0) ? 1.0f : 0.0f;
-    if (zdot < 0) { const float x_axis[3] = {1.0f, 0.0f, 0.0f}; h_rotate_make(rot, M_PI, x_axis); }
+    if (cos_angle < 0) { const float x_axis[3] = {1.0f, 0.0f, 0.0f}; h_rotate_make(rot, M_PI, x_axis); }
   }
-  int vi = 0;
-  for (int i = 0; i <= total_stacks; i++) {
-    float t, stack_radius, z;
-    const float *center;
-    if (i < stack_count) {
-      t = ((float)i / stack_count); center = A;
-      stack_radius = radius * cosf(t * M_PI / 2.0f); z = -radius * sinf(t * M_PI / 2.0f);
-    } else if (i == stack_count) {
-      center = A; stack_radius = radius; z = 0.0f;
-    } else if (i == stack_count + 1) {
-      center = B; stack_radius = radius; z = 0.0f;
-    } else {
-      t = ((float)(i - (stack_count + 1)) / stack_count); center = B;
-      stack_radius = radius * cosf(t * M_PI / 2.0f); z = radius * sinf(t * M_PI / 2.0f);
+  const int n_rings = 2 * kRing + 2;
+  int at = 0;
+  for (int ring = 0; ring < n_rings; ring++) {
+    const bool lower_half = ring <= kRing;
+    const int from_equator = lower_half ? ring : ring - (kRing + 1);          // 0 at ... see below
+    float rad = radius, z = 0.0f;
+    if (ring < kRing) {                                                         // below A: t = ring / 20
+      const float t = ((float)ring / kRing);
+      rad = radius * cosf(t * M_PI / 2.0f); z = -radius * sinf(t * M_PI / 2.0f);
+    } else if (ring > kRing + 1) {                                              // above B
+      const float t = ((float)from_equator / kRing);
+      rad = radius * cosf(t * M_PI / 2.0f); z = radius * sinf(t * M_PI / 2.0f);
     }
-    for (int j = 0; j <= sector_count; j++) {
-      const float sector_angle = j * sector_step;
-      const float x = stack_radius * cosf(sector_angle), y = stack_radius * sinf(sector_angle);
-      // glm_mat4_mulv3(rot, (x, y, z), 1.0f): four products per row summed left to right
-      for (int k = 0; k < 3; k++)
-        vertices[vi * 3 + k] = (rot[0 + k] * x + rot[4 + k] * y + rot[8 + k] * z + rot[12 + k] * 1.0f) + center[k];
-      vi++;
-    }
+    at = ring_vertices(vertices, at, rad, z, rot, lower_half ? A : B);
   }
-  unsigned n = 0;
-  for (int i = 0; i < total_stacks; i++) {
-    int k1 = i * (sector_count + 1), k2 = k1 + sector_count + 1;
-    for (int j = 0; j < sector_count; j++, k1++, k2++) {
-      indices[n++] = k1; indices[n++] = k1 + 1; indices[n++] = k2;
-      indices[n++] = k1 + 1; indices[n++] = k2 + 1; indices[n++] = k2;
+  uint32_t *w = indices;
+  for (int ring = 0; ring + 1 < n_rings; ring++)
+    for (int col = 0; col < kRing; col++) {
+      const uint32_t upper = (uint32_t)(ring * (kRing + 1) + col), lower = upper + kRing + 1;
+      *w++ = upper; *w++ = upper + 1; *w++ = lower;
+      *w++ = upper + 1; *w++ = lower + 1; *w++ = lower;
     }
-  }
 }
 
 // physics_debug_AABB_init, debug_renderer.c:311-337: local corners and the 12 edges as 24 line indices
