@@ -106,8 +106,23 @@ struct PgWorlds {
   long long pipe_graph_kernels;
 };
 
+// One frame of ONE game-sized world without a single DMA (pg_worlds_frame): the step kernel itself reads the records the
+// host changed out of the pinned block (mapped into the device's address space) and writes every record, the event
+// count and the events of the frame back into it.  `world` < 0: not a frame launch.
+#define PG_FRAME_MAX_RANGES 12
+struct SmallFrame {
+  int world;
+  int counts[3];                       // class lengths of this frame (the kernel stores them as the device's counts)
+  int n_ranges;
+  int cls[PG_FRAME_MAX_RANGES], first[PG_FRAME_MAX_RANGES], count[PG_FRAME_MAX_RANGES];
+  const PgBody *in;                    // the dirty records, back to back in range order (mapped pinned memory)
+  PgBody *out;                         // [cap0 + cap1 + cap2] records of the three classes at their capacity offsets
+  int *cnt_out;                        // events produced by the frame (may exceed max_events)
+  PgEvent *ev_out;                     // min(count, max_events) events, unsorted
+};
 // pg_general.cu
-int pg_launch_general_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes);
+int pg_launch_general_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes, const SmallFrame *frame = nullptr);
+bool pg_small_frame_fits(const PgWorlds *w, const int32_t counts[3]);
 // pg_spheres.cu
 int pg_launch_sphere_step(PgWorlds *w, float dt, int n_steps);
 int pg_launch_sphere_range(PgWorlds *w, float dt, int n_steps, int first, int count, cudaStream_t stream, int *counter, double *stats,

@@ -321,7 +321,7 @@ __device__ int small_test(const SmallPlan &pl, PgBody *S, PgBody *D, PgBody *P, 
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_step_small(WorldsView v, float dt_in, int n_steps, int refresh_nodes) {
+k_step_small(WorldsView v, float dt_in, int n_steps, int refresh_nodes, SmallFrame fr) {
   __shared__ unsigned char s_fire[kSmallMaxVisits];      // 0 / 1, 2 = the single-thread search ran out of budget
   __shared__ float s_t[kSmallMaxVisits];
   __shared__ int s_min;
@@ -334,6 +334,12 @@ k_step_small(WorldsView v, float dt_in, int n_steps, int refresh_nodes) {
   PgBody *P = v.bodies[2] + (size_t)w * v.cap[2];
   SmallPlan pl;
   pl.ns = v.counts[w * 3 + 0]; pl.nd = v.counts[w * 3 + 1]; pl.np = v.counts[w * 3 + 2];
+  const bool framed = fr.world == w;       // this launch is one frame of the drop-in: no copies around it (SmallFrame)
+  if (framed) {
+    pl.ns = fr.counts[0]; pl.nd = fr.counts[1]; pl.np = fr.counts[2];
+    if (threadIdx.x < 3) v.counts[w * 3 + threadIdx.x] = fr.counts[threadIdx.x];
+    if (threadIdx.x == 0) v.n_events[w] = 0;
+  }
   // A game scene's records live in shared memory for the launch (bouncehouse.json: 15 bodies, 4.5 KB): the kernel is one
   // block whose every visit is a chain of dependent reads of a few record fields, and those were L2 round trips.
   __shared__ __align__(16) unsigned char s_bodies_raw[kSmallStageBodies * sizeof(PgBody)];
@@ -351,6 +357,17 @@ k_step_small(WorldsView v, float dt_in, int n_steps, int refresh_nodes) {
     }
     S = s_bodies; D = s_bodies + pl.ns; P = s_bodies + pl.ns + pl.nd;
     __syncthreads();
+    if (framed) {
+      // the records the host changed since the device last saw them, straight out of the pinned block
+      int at = 0;
+      for (int r = 0; r < fr.n_ranges; r++) {
+        PgBody *dst = small_body(S, D, P, fr.cls[r], fr.first[r]);
+        for (int k = threadIdx.x; k < fr.count[r] * kWords; k += kThreads)
+          reinterpret_cast<uint4 *>(dst)[k] = reinterpret_cast<const uint4 *>(fr.in + at)[k];
+        at += fr.count[r];
+      }
+      __syncthreads();
+    }
   }
   pl.v1 = pl.np * pl.ns; pl.v2 = pl.np * pl.nd; pl.v3 = pl.nd * pl.ns; pl.v4 = pl.nd * (pl.nd - 1);
   const int V = pl.total();
@@ -444,7 +461,20 @@ k_step_small(WorldsView v, float dt_in, int n_steps, int refresh_nodes) {
     for (int k = threadIdx.x; k < n_all * kWords; k += kThreads) {
       const int b = k / kWords, q = k % kWords;
       PgBody *dst = b < pl.ns ? gS + b : (b < pl.ns + pl.nd ? gD + (b - pl.ns) : gP + (b - pl.ns - pl.nd));
-      reinterpret_cast<uint4 *>(dst)[q] = reinterpret_cast<const uint4 *>(s_bodies + b)[q];
+      const uint4 word = reinterpret_cast<const uint4 *>(s_bodies + b)[q];
+      reinterpret_cast<uint4 *>(dst)[q] = word;
+      if (framed) {
+        // ... and into the pinned block the host reads after its one synchronisation
+        PgBody *h = b < pl.ns ? fr.out + b : (b < pl.ns + pl.nd ? fr.out + v.cap[0] + (b - pl.ns) : fr.out + v.cap[0] + v.cap[1] + (b - pl.ns - pl.nd));
+        reinterpret_cast<uint4 *>(h)[q] = word;
+      }
+    }
+    if (framed) {
+      const int n_ev = v.n_events[w];                    // (every emit lies before the barrier above)
+      if (threadIdx.x == 0) *fr.cnt_out = n_ev;
+      constexpr int kEvWords = (int)(sizeof(PgEvent) / 16);
+      const uint4 *src = reinterpret_cast<const uint4 *>(v.events + (size_t)w * v.max_events);
+      for (int k = threadIdx.x; k < min(n_ev, v.max_events) * kEvWords; k += kThreads) reinterpret_cast<uint4 *>(fr.ev_out)[k] = src[k];
     }
   }
 }
@@ -528,7 +558,19 @@ struct DevBuf {
 
 }  // namespace
 
-int pg_launch_general_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes) {
+// Can a frame of these class lengths run without copies (k_step_small with the records in shared memory)?
+bool pg_small_frame_fits(const PgWorlds *w, const int32_t counts[3]) {
+  static const bool no_small = getenv("PG_GENERAL_ROW_SWEEP") != nullptr, no_zero_copy = getenv("PG_FRAME_DMA") != nullptr;
+  if (no_small || no_zero_copy || w->v.n_worlds != 1) return false;
+  const long long ns = counts[0], nd = counts[1], np = counts[2];
+  return ns + nd + np <= kSmallStageBodies && np * ns + np * nd + nd * ns + nd * (nd - 1) <= kSmallMaxVisits;
+}
+
+int pg_launch_general_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes, const SmallFrame *frame) {
+  SmallFrame fr;
+  memset(&fr, 0, sizeof(fr));
+  fr.world = -1;
+  if (frame) fr = *frame;
   // game-sized worlds (every world of the handle has at most kSmallMaxVisits visits per step): speculate + commit
   static const bool no_small = getenv("PG_GENERAL_ROW_SWEEP") != nullptr;
   long long worst = 0;
@@ -537,11 +579,12 @@ int pg_launch_general_step(PgWorlds *w, float dt, int n_steps, int refresh_nodes
     worst = std::max(worst, np * ns + np * nd + nd * ns + nd * (nd - 1));
   }
   if (!no_small && worst <= kSmallMaxVisits) {
-    k_step_small<<<w->v.n_worlds, kThreads, 0, w->stream>>>(w->v, dt, n_steps, refresh_nodes);
+    k_step_small<<<w->v.n_worlds, kThreads, 0, w->stream>>>(w->v, dt, n_steps, refresh_nodes, fr);
     PG_CUDA(cudaGetLastError());
     w->launches++;
     return PG_OK;
   }
+  if (frame) { pg_set_error("pg_launch_general_step: a copy-free frame needs the game-sized kernel"); return PG_ERR_ARG; }
   k_step_general<<<w->v.n_worlds, kThreads, 0, w->stream>>>(w->v, dt, n_steps, refresh_nodes,
                                                              w->static_pass_parallel_ok ? 1 : 0);
   PG_CUDA(cudaGetLastError());

@@ -766,22 +766,31 @@ int pg_worlds_frame(PgWorlds *w, int world, const int32_t counts[3], const PgRan
     for (int c = 0; c < 3; c++) { free(w->h_types[c]); w->h_types[c] = (unsigned char *)calloc((size_t)w->v.cap[c], 1); }
   }
   if (n_up > cap_all) { pg_set_error("pg_worlds_frame: ranges overlap (more records than the world holds)"); return PG_ERR_ARG; }
+  // A game-sized world's frame needs no copy at all: the kernel reads the dirty records out of the pinned block and
+  // writes the records, the event count and the events back into it (SmallFrame; pinned memory is mapped into the device's
+  // address space).  Larger worlds: one asynchronous copy per range and per class.
+  const bool zero_copy = n_steps > 0 && n_ranges <= PG_FRAME_MAX_RANGES && pg_small_frame_fits(w, counts);
   // dirty records: one memcpy into the pinned block, one asynchronous copy per range out of it
   PgBody *h_in = reinterpret_cast<PgBody *>(w->h_frame);
   if (n_up) memcpy(h_in, records, sizeof(PgBody) * n_up);
+  SmallFrame fr;
+  memset(&fr, 0, sizeof(fr));
+  fr.world = world;
   size_t at = 0;
   for (int r = 0; r < n_ranges; r++) {
     const PgRange &g = ranges[r];
+    if (zero_copy) { fr.cls[r] = g.cls; fr.first[r] = g.first; fr.count[r] = g.count; }
     if (g.count == 0) continue;
-    PG_CUDA(cudaMemcpyAsync(w->v.bodies[g.cls] + (size_t)world * w->v.cap[g.cls] + g.first, h_in + at, sizeof(PgBody) * (size_t)g.count,
-                            cudaMemcpyHostToDevice, w->stream));
+    if (!zero_copy)
+      PG_CUDA(cudaMemcpyAsync(w->v.bodies[g.cls] + (size_t)world * w->v.cap[g.cls] + g.first, h_in + at, sizeof(PgBody) * (size_t)g.count,
+                              cudaMemcpyHostToDevice, w->stream));
     for (int i = 0; i < g.count; i++) w->h_types[g.cls][g.first + i] = (unsigned char)h_in[at + i].collider_type;
     at += (size_t)g.count;
   }
   bool counts_changed = false;
   for (int c = 0; c < 3; c++) if (w->h_counts[world * 3 + c] != counts[c]) { w->h_counts[world * 3 + c] = counts[c]; counts_changed = true; }
   int *h_cnt = reinterpret_cast<int *>(w->h_frame + off_cnt);
-  if (counts_changed) {
+  if (counts_changed && !zero_copy) {
     for (int c = 0; c < 3; c++) h_cnt[4 + c] = counts[c];
     PG_CUDA(cudaMemcpyAsync(w->v.counts + world * 3, h_cnt + 4, 3 * sizeof(int), cudaMemcpyHostToDevice, w->stream));
   }
@@ -792,28 +801,42 @@ int pg_worlds_frame(PgWorlds *w, int world, const int32_t counts[3], const PgRan
   w->static_pass_parallel_ok = ok && w->v.n_worlds == 1;
   if (w->v.n_worlds > 1) { rc = refresh_parallel_flag(w); if (rc) return rc; }
   const double t1 = frame_timing ? now() : 0.0;
-  PG_CUDA(cudaMemsetAsync(w->v.n_events, 0, sizeof(int) * (size_t)w->v.n_worlds, w->stream));
+  PgBody *h_out = reinterpret_cast<PgBody *>(w->h_frame + off_out);
+  PgEvent *h_ev = reinterpret_cast<PgEvent *>(w->h_frame + off_ev);
+  if (!zero_copy) PG_CUDA(cudaMemsetAsync(w->v.n_events, 0, sizeof(int) * (size_t)w->v.n_worlds, w->stream));
   PG_CUDA(cudaEventRecord(w->ev0, w->stream));
   {
     float cdt = dt;
     if ((double)cdt > 0.01666) cdt = (float)0.01666;
     pg_leaf_lengths(0.0f, cdt, &w->v.leaf_lo, &w->v.leaf_hi);
   }
-  if (n_steps > 0) { rc = pg_launch_general_step(w, dt, n_steps, refresh_nodes); if (rc) return rc; }
+  if (zero_copy) {
+    for (int c = 0; c < 3; c++) fr.counts[c] = counts[c];
+    fr.n_ranges = n_ranges;
+    void *d_frame = nullptr;
+    PG_CUDA(cudaHostGetDevicePointer(&d_frame, w->h_frame, 0));
+    unsigned char *db = static_cast<unsigned char *>(d_frame);
+    fr.in = reinterpret_cast<const PgBody *>(db);
+    fr.out = reinterpret_cast<PgBody *>(db + off_out);
+    fr.cnt_out = reinterpret_cast<int *>(db + off_cnt);
+    fr.ev_out = reinterpret_cast<PgEvent *>(db + off_ev);
+    rc = pg_launch_general_step(w, dt, n_steps, refresh_nodes, &fr);
+    if (rc) return rc;
+  } else if (n_steps > 0) { rc = pg_launch_general_step(w, dt, n_steps, refresh_nodes); if (rc) return rc; }
   PG_CUDA(cudaEventRecord(w->ev1, w->stream));
   w->last_steps = n_steps;
   const double t2 = frame_timing ? now() : 0.0;
   // everything back into the pinned block, then ONE synchronisation
-  PgBody *h_out = reinterpret_cast<PgBody *>(w->h_frame + off_out);
   PgBody *outs[3] = {out_static, out_dynamic, out_player};
   size_t out_at[3] = {0, (size_t)w->v.cap[0], (size_t)w->v.cap[0] + w->v.cap[1]};
-  for (int c = 0; c < 3; c++)
-    if (outs[c] && counts[c] > 0)
-      PG_CUDA(cudaMemcpyAsync(h_out + out_at[c], w->v.bodies[c] + (size_t)world * w->v.cap[c], sizeof(PgBody) * (size_t)counts[c], cudaMemcpyDeviceToHost, w->stream));
-  PgEvent *h_ev = reinterpret_cast<PgEvent *>(w->h_frame + off_ev);
-  PG_CUDA(cudaMemcpyAsync(h_cnt, w->v.n_events + world, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
-  if (w->v.max_events > 0 && events)
-    PG_CUDA(cudaMemcpyAsync(h_ev, w->v.events + (size_t)world * w->v.max_events, sizeof(PgEvent) * (size_t)w->v.max_events, cudaMemcpyDeviceToHost, w->stream));
+  if (!zero_copy) {
+    for (int c = 0; c < 3; c++)
+      if (outs[c] && counts[c] > 0)
+        PG_CUDA(cudaMemcpyAsync(h_out + out_at[c], w->v.bodies[c] + (size_t)world * w->v.cap[c], sizeof(PgBody) * (size_t)counts[c], cudaMemcpyDeviceToHost, w->stream));
+    PG_CUDA(cudaMemcpyAsync(h_cnt, w->v.n_events + world, sizeof(int), cudaMemcpyDeviceToHost, w->stream));
+    if (w->v.max_events > 0 && events)
+      PG_CUDA(cudaMemcpyAsync(h_ev, w->v.events + (size_t)world * w->v.max_events, sizeof(PgEvent) * (size_t)w->v.max_events, cudaMemcpyDeviceToHost, w->stream));
+  }
   const double t3 = frame_timing ? now() : 0.0;
   PG_CUDA(cudaStreamSynchronize(w->stream));
   const double t4 = frame_timing ? now() : 0.0;
