@@ -174,16 +174,25 @@ __device__ int interval_hit_budget(const PgBody &A, const PgBody &B, float t_beg
   int depth = 0;
   float t0 = t_begin, t1 = t_end;
   const pgm::PairPre pre = pgm::pair_pre(A, B);      // everything of the distance function that does not depend on the time
+  // The left child of a node shares its t0: the distance there is carried down instead of evaluated again (a touching
+  // pair is found by walking straight down the left edge of the tree, where that is every second evaluation).
+  float d0 = 0.0f;
+  bool have_d0 = false;
   for (;;) {
     if (--budget < 0) return 2;
-    const bool open = pgm::interval_node_open(A, B, pre, t0, t1);
+    const float len = t1 - t0;
+    const float mm = pre.nA * len + pre.nB * len;       // maximum_object_movement_over_time of both bodies (world.c:559-560)
+    if (!have_d0) d0 = pgm::min_dist_pre(A, B, pre, t0);
+    const bool open = !(d0 > mm) && !(pgm::min_dist_pre(A, B, pre, t1) > mm);
     if (open) {
       if (t1 - t0 < pgm::kIntervalEps) return 1;
       if (depth >= 62) return 0;
       path <<= 1; depth++;
       t1 = (t0 + t1) * 0.5f;
+      have_d0 = true;
       continue;
     }
+    have_d0 = false;
     while (depth > 0 && (path & 1ull)) { path >>= 1; depth--; }
     if (depth == 0) return 0;
     path |= 1ull;

@@ -189,6 +189,11 @@ __device__ inline V3 pill_box_pq(const Pill &p, const Box &bx) {   // distance.c
   q.z = glm_clamp(cp.z, bx.c.z - bx.e.z, bx.c.z + bx.e.z);
   return sub(q, cp);
 }
+// (float)sqrt((double)x) for a float x, as distance.c:91 computes it.  A square root evaluated with q >= 2p + 2 bits and
+// then rounded to p bits equals the correctly rounded p-bit square root (double rounding is innocuous for sqrt: Figueroa,
+// "When is double rounding innocuous?", 1995); here p = 24, q = 53 >= 50, and sqrtf is the correctly rounded IEEE root
+// (-prec-sqrt=true, -ftz=false).  Same bits, a fraction of the instructions of the binary64 root.
+__device__ __forceinline__ float sqrt_f64_as_f32(float x) { return sqrtf(x); }
 __device__ __forceinline__ float proj_radius_f64(V3 e, V3 n) {   // distance.c:267-270 [f64]
   return (float)((double)e.x * fabs((double)n.x) + (double)e.y * fabs((double)n.y) + (double)e.z * fabs((double)n.z));
 }
@@ -876,7 +881,7 @@ __device__ inline float dist_box_box(const PgBody &A, const PgBody &B, float t) 
     if (minB > maxA) d2 += (minB - maxA) * (minB - maxA);
     else if (maxB < minA) d2 += (minA - maxB) * (minA - maxB);
   }
-  return (float)sqrt((double)d2);   // [f64]
+  return sqrt_f64_as_f32(d2);
 }
 __device__ inline float dist_box_ball(const PgBody &A, const PgBody &B, float t) {   // distance.c:94-158
   Box bx = box_from_node(A, true, v3p(A.velocity), t);
@@ -1019,7 +1024,7 @@ __device__ inline float min_dist_pre(const PgBody &A, const PgBody &B, const Pai
         if (minB > maxA) d2 += (minB - maxA) * (minB - maxA);
         else if (maxB < minA) d2 += (minA - maxB) * (minA - maxB);
       }
-      return (float)sqrt((double)d2);   // [f64]
+      return sqrt_f64_as_f32(d2);
     }
     case PG_AABB * 4 + PG_SPHERE: {
       const Box bx = box_at(q.a, q.vA, t);
