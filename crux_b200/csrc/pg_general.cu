@@ -169,11 +169,12 @@ constexpr int kSmallStack = 2048;        // open nodes the block-wide search can
 
 // interval_collision (world.c:557-582) with a node budget: 0 = false, 1 = true, 2 = still undecided after
 // `budget` nodes.  Same tree, same end-point tests as pgm::interval_hit.
-__device__ int interval_hit_budget(const PgBody &A, const PgBody &B, float t_begin, float t_end, int budget) {
+__device__ int interval_hit_budget(const PgBody &A, const PgBody &B, float t_begin, float t_end, int budget, const pgm::BoxPre *na = nullptr,
+                                   const pgm::BoxPre *nb = nullptr) {
   unsigned long long path = 0;
   int depth = 0;
   float t0 = t_begin, t1 = t_end;
-  const pgm::PairPre pre = pgm::pair_pre(A, B);      // everything of the distance function that does not depend on the time
+  const pgm::PairPre pre = pgm::pair_pre(A, B, na, nb);      // everything of the distance function that does not depend on the time
   // The left child of a node shares its t0: the distance there is carried down instead of evaluated again (a touching
   // pair is found by walking straight down the left edge of the tree, where that is every second evaluation).
   float d0 = 0.0f;
@@ -214,11 +215,12 @@ struct BlockSearch {
   unsigned long long stack[kSmallStack];          // node = depth << 56 | path
   int top, found, overflow;
 };
-__device__ bool interval_hit_block(const PgBody &A, const PgBody &B, float t_begin, float t_end, BlockSearch &bs) {
+__device__ bool interval_hit_block(const PgBody &A, const PgBody &B, float t_begin, float t_end, BlockSearch &bs, const pgm::BoxPre *na = nullptr,
+                                   const pgm::BoxPre *nb = nullptr) {
   __syncthreads();
   if (threadIdx.x == 0) { bs.stack[0] = 0ull; bs.top = 1; bs.found = 0; bs.overflow = 0; }
   __syncthreads();
-  const pgm::PairPre pre = pgm::pair_pre(A, B);
+  const pgm::PairPre pre = pgm::pair_pre(A, B, na, nb);
   for (;;) {
     const int n = bs.top;
     const bool stop = n == 0 || bs.found || bs.overflow;
@@ -290,13 +292,16 @@ __device__ __forceinline__ PgBody *small_body(PgBody *S, PgBody *D, PgBody *P, i
 
 // Read-only half of a visit (world.c:481-502) with the interval search either bounded (bs == nullptr: one thread,
 // 2 = undecided) or run by the whole block (bs != nullptr: all threads, identical arguments).
-__device__ int test_visit_small(const PgBody &x, const PgBody &y, float dt, float *t_hit, BlockSearch *bs) {
+// px / py: box_pre_node of x / y where the kernel holds it (null otherwise)
+__device__ int test_visit_small(const PgBody &x, const PgBody &y, float dt, float *t_hit, BlockSearch *bs, const pgm::BoxPre *px = nullptr,
+                                const pgm::BoxPre *py = nullptr) {
   const bool swap = x.collider_type > y.collider_type;
   const PgBody &A = swap ? y : x;
   const PgBody &B = swap ? x : y;
-  if (bs) { if (!interval_hit_block(A, B, 0.0f, dt, *bs)) return 0; }
+  const pgm::BoxPre *na = swap ? py : px, *nb = swap ? px : py;
+  if (bs) { if (!interval_hit_block(A, B, 0.0f, dt, *bs, na, nb)) return 0; }
   else {
-    const int r = interval_hit_budget(A, B, 0.0f, dt, kSmallBudget);
+    const int r = interval_hit_budget(A, B, 0.0f, dt, kSmallBudget, na, nb);
     if (r != 1) return r;
   }
   bool has;
@@ -309,11 +314,16 @@ __device__ int test_visit_small(const PgBody &x, const PgBody &y, float dt, floa
 // Would visit k fire, on the real state (integrations with point <= `applied` done) plus the integrations that lie
 // between `applied` and k?  0 / 1, or 2 = undecided (bs == nullptr only).
 __device__ int small_test(const SmallPlan &pl, PgBody *S, PgBody *D, PgBody *P, int k, int applied, float dt, float *t_hit, BlockSearch *bs,
-                          PgBody *s_tmp) {
+                          PgBody *s_tmp, const pgm::BoxPre *node_pre) {
   int rc, ri, cc, ci, pass;
   pl.decode(k, rc, ri, cc, ci, pass);
   const PgBody *row = small_body(S, D, P, rc, ri);        // a row body is never integrated before its own visits
   const PgBody *col = small_body(S, D, P, cc, ci);
+  // the bodies' boxes through their nodes, built once per step (the node matrix does not change during a step, and the
+  // copy of a column advanced by its own row keeps it)
+  auto slot = [&](int cls, int i) { return cls == PG_CLASS_STATIC ? i : (cls == PG_CLASS_DYNAMIC ? pl.ns + i : pl.ns + pl.nd + i); };
+  const pgm::BoxPre *prow = node_pre && row->collider_type == PG_AABB ? node_pre + slot(rc, ri) : nullptr;
+  const pgm::BoxPre *pcol = node_pre && col->collider_type == PG_AABB ? node_pre + slot(cc, ci) : nullptr;
   const int ip = pl.int_point(cc, ci);
   if (ip > applied && ip <= k && !col->at_rest) {
     // the column as its own row's integration will leave it
@@ -321,13 +331,13 @@ __device__ int small_test(const SmallPlan &pl, PgBody *S, PgBody *D, PgBody *P, 
       __syncthreads();
       if (threadIdx.x == 0) { *s_tmp = *col; integrate_body(*s_tmp, dt); }
       __syncthreads();
-      return test_visit_small(*row, *s_tmp, dt, t_hit, bs);
+      return test_visit_small(*row, *s_tmp, dt, t_hit, bs, prow, pcol);
     }
     PgBody tmp = *col;
     integrate_body(tmp, dt);
-    return test_visit_small(*row, tmp, dt, t_hit, nullptr);
+    return test_visit_small(*row, tmp, dt, t_hit, nullptr, prow, pcol);
   }
-  return test_visit_small(*row, *col, dt, t_hit, bs);
+  return test_visit_small(*row, *col, dt, t_hit, bs, prow, pcol);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -398,13 +408,21 @@ k_step_small(WorldsView v, float dt_in, int n_steps, int refresh_nodes, SmallFra
     applied = to;
     __syncthreads();
   };
+  __shared__ pgm::BoxPre s_node_pre[kSmallStageBodies];
+  const pgm::BoxPre *const node_pre = in_smem ? s_node_pre : nullptr;
   for (int step = 0; step < n_steps; step++) {
     sink.step = step;
     int cursor = 0;
     applied = -1;
+    if (in_smem) {
+      // every box through its node, once per body and step (each of its ~2 n visits used to rebuild it)
+      for (int b = threadIdx.x; b < pl.ns + pl.nd + pl.np; b += kThreads)
+        if (s_bodies[b].collider_type == PG_AABB) s_node_pre[b] = pgm::box_pre_node(s_bodies[b]);
+      __syncthreads();
+    }
     for (int k = threadIdx.x; k < V; k += kThreads) {
       float t = 0.0f;
-      s_fire[k] = (unsigned char)small_test(pl, S, D, P, k, -1, dt, &t, nullptr, nullptr);
+      s_fire[k] = (unsigned char)small_test(pl, S, D, P, k, -1, dt, &t, nullptr, nullptr, node_pre);
       s_t[k] = t;
     }
     __syncthreads();
@@ -416,7 +434,7 @@ k_step_small(WorldsView v, float dt_in, int n_steps, int refresh_nodes, SmallFra
       for (int k = from; k < V; k++) {
         if (s_fire[k] != 2) continue;                    // (uniform: shared memory, read between barriers)
         float t = 0.0f;
-        const int r = small_test(pl, S, D, P, k, applied, dt, &t, &s_bs, &s_tmp);
+        const int r = small_test(pl, S, D, P, k, applied, dt, &t, &s_bs, &s_tmp, node_pre);
         __syncthreads();
         if (threadIdx.x == 0) { s_fire[k] = (unsigned char)r; s_t[k] = t; }
         __syncthreads();
@@ -449,7 +467,7 @@ k_step_small(WorldsView v, float dt_in, int n_steps, int refresh_nodes, SmallFra
         const bool hit_col = (cc2 == rc && ci2 == ri) || (cc2 == cc && ci2 == ci);
         if (!hit_row && !hit_col) continue;
         float t = 0.0f;
-        s_fire[k] = (unsigned char)small_test(pl, S, D, P, k, applied, dt, &t, nullptr, nullptr);
+        s_fire[k] = (unsigned char)small_test(pl, S, D, P, k, applied, dt, &t, nullptr, nullptr, node_pre);
         s_t[k] = t;
       }
       __syncthreads();

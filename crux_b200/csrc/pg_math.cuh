@@ -988,20 +988,21 @@ struct PairPre {
   Pill pill;              // box-capsule: the capsule does not move during the search (distance.c:185-189)
   float aux;              // box-sphere: world radius; box-plane: projected radius; capsule-plane: the distance itself
 };
-__device__ inline PairPre pair_pre(const PgBody &A, const PgBody &B) {
+// na / nb: the caller already holds box_pre_node(A) / box_pre_node(B) (a kernel that builds them once per body and step)
+__device__ inline PairPre pair_pre(const PgBody &A, const PgBody &B, const BoxPre *na = nullptr, const BoxPre *nb = nullptr) {
   PairPre q;
   q.code = A.collider_type * 4 + B.collider_type;
   q.vA = v3p(A.velocity); q.vB = v3p(B.velocity);
   q.nA = norm(q.vA); q.nB = norm(q.vB);
   q.aux = 0.0f;
   switch (q.code) {
-    case PG_AABB * 4 + PG_AABB: q.a = box_pre_node(A); q.b = box_pre_node(B); break;
+    case PG_AABB * 4 + PG_AABB: q.a = na ? *na : box_pre_node(A); q.b = nb ? *nb : box_pre_node(B); break;
     case PG_AABB * 4 + PG_SPHERE:
-      q.a = box_pre_node(A);
+      q.a = na ? *na : box_pre_node(A);
       q.b.ok = B.has_node; q.b.pos0 = v3(0, 0, 0);
       if (B.has_node) { NodeFrame f; node_decompose(B.node_xform, f); q.b.pos0 = f.pos; q.aux = B.shape[3] * f.scl.x; }
       break;
-    case PG_AABB * 4 + PG_CAPSULE: q.a = box_pre_node(A); q.pill = pill_from_node(B); break;
+    case PG_AABB * 4 + PG_CAPSULE: q.a = na ? *na : box_pre_node(A); q.pill = pill_from_node(B); break;
     case PG_AABB * 4 + PG_PLANE:
       q.a = box_pre(A.shape, A.euler_raw, v3p(A.position), v3p(A.scale));
       q.aux = proj_radius_f64(q.a.e, v3p(B.shape));
