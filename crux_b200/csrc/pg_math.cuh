@@ -1062,9 +1062,36 @@ __device__ __forceinline__ bool interval_node_open(const PgBody &A, const PgBody
 }
 
 // interval_collision, world.c:557-582 (general collider pair).
+// The walk of interval_walk() (children left first, true at the first surviving leaf, *hit = its t0) with the distance at
+// t0 carried down left descents: the left child shares its parent's t0, and the same float time gives the same bits.
 __device__ inline bool interval_hit(const PgBody &A, const PgBody &B, float t_begin, float t_end, float *hit) {
   const PairPre q = pair_pre(A, B);
-  return interval_walk(t_begin, t_end, hit, [&](float t0, float t1) { return interval_node_open(A, B, q, t0, t1); });
+  unsigned long long path = 0;
+  int depth = 0;
+  float t0 = t_begin, t1 = t_end, d0 = 0.0f;
+  bool have_d0 = false;
+  for (;;) {
+    const float len = t1 - t0;
+    const float mm = q.nA * len + q.nB * len;
+    if (!have_d0) d0 = min_dist_pre(A, B, q, t0);
+    if (!(d0 > mm) && !(min_dist_pre(A, B, q, t1) > mm)) {
+      if (len < kIntervalEps) { if (hit) *hit = t0; return true; }
+      if (depth >= 62) return false;                 // unreachable for finite end points
+      path <<= 1; depth++;
+      t1 = (t0 + t1) * 0.5f;
+      have_d0 = true;
+      continue;
+    }
+    have_d0 = false;
+    while (depth > 0 && (path & 1ull)) { path >>= 1; depth--; }   // right children are finished
+    if (depth == 0) return false;
+    path |= 1ull;                                    // left child failed: take its right sibling
+    t0 = t_begin; t1 = t_end;
+    for (int k = depth - 1; k >= 0; k--) {
+      const float mid = (t0 + t1) * 0.5f;
+      if ((path >> k) & 1ull) t0 = mid; else t1 = mid;
+    }
+  }
 }
 
 __device__ inline bool aabb_hits_aabb(const Box &a, const Box &b) {   // aabb.c:100-105
