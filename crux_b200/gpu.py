@@ -389,8 +389,9 @@ class GpuWorlds:
         comes back; otherwise a DEBUG_DTYPE array."""
         from .scenes import DEBUG_DTYPE
         if device_ptr is not None:
-            return _check(self.L.pg_worlds_debug_geometry(self.h, world, C.c_void_p(device_ptr), 1,
-                                                          int(max_records if max_records is not None else 1 << 30)),
+            if max_records is None or int(max_records) < 0:
+                raise PgError("debug_geometry(device_ptr=...): max_records (the room of the device buffer, in records) is required")
+            return _check(self.L.pg_worlds_debug_geometry(self.h, world, C.c_void_p(device_ptr), 1, int(max_records)),
                           "pg_worlds_debug_geometry")
         total = sum(self.body_count(world, c) for c in range(3))
         out = np.zeros(max(total, 1), dtype=DEBUG_DTYPE)
